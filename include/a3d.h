@@ -1,0 +1,202 @@
+/*
+ * a3d.h — C ABI of the B200 view-gain library (liba3d_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of ethz-asl/mav_active_3d_planning:
+ * SimulatedSensorEvaluator::computeGain → CameraModel ray casters → voxblox map lookups →
+ * VoxelType/Naive/Frontier gain fold.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference checkout).  Plain pointers and sizes only; all pointers are HOST
+ * memory unless the function name ends in _dev.  The caller owns every buffer.  One thread per
+ * context (thread-compatible, not thread-safe) — like the reference, which is single-threaded
+ * (active_3d_planning_ros/src/planner/ros_planner.cpp:93-105).
+ *
+ * There is no CPU fallback: every function that computes does so in sm_100a CUDA kernels and
+ * returns A3D_ERR_CUDA if no device is usable.
+ *
+ * All functions return 0 (A3D_OK) or a negative error code; a3d_last_error() gives the text.
+ */
+#ifndef A3D_H_
+#define A3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3D_OK 0
+#define A3D_ERR_INVALID (-1)     /* bad argument (the reference throws std::invalid_argument,
+                                    active_3d_planning_core/src/module/module.cpp:11-16) */
+#define A3D_ERR_CUDA (-2)        /* CUDA runtime error / no device */
+#define A3D_ERR_STATE (-3)       /* call order (e.g. upload before a3d_map_config) */
+#define A3D_ERR_CAPACITY (-4)    /* caller buffer too small (a3d_visible_voxels) */
+#define A3D_ERR_UNSUPPORTED (-5)
+
+/* OccupancyMap states, active_3d_planning_core/include/active_3d_planning_core/map/occupancy_map.h:17-19 */
+#define A3D_OCCUPIED 0
+#define A3D_FREE 1
+#define A3D_UNKNOWN 2
+
+/* sensor model kinds = registered type strings "SimpleRayCaster" / "IterativeRayCaster"
+   (core/src/module/sensor_model/simple_ray_caster.cpp:10-11, iterative_ray_caster.cpp:12-13) */
+#define A3D_CASTER_SIMPLE 0
+#define A3D_CASTER_ITERATIVE 1
+
+/* evaluator kinds = "VoxelTypeEvaluator" / "NaiveEvaluator" / "FrontierEvaluator"
+   (core/src/module/trajectory_evaluator/voxel_type_evaluator.cpp:13-14, naive_evaluator.cpp:9-10,
+   frontier_evaluator.cpp:9-10) */
+#define A3D_EVAL_VOXEL_TYPE 0
+#define A3D_EVAL_NAIVE 1
+#define A3D_EVAL_FRONTIER 2
+
+typedef struct a3d_ctx a3d_ctx;
+typedef struct a3d_caster a3d_caster;
+typedef struct a3d_eval a3d_eval;
+
+/* Parameters of a CameraModel subclass exactly as setupFromParamMap parses them
+   (core/src/module/sensor_model/sensor_model.cpp:9-27, camera_model.cpp:170-183,
+   simple_ray_caster.cpp:15-30, iterative_ray_caster.cpp:18-46). */
+typedef struct {
+  int32_t kind;               /* A3D_CASTER_* */
+  int32_t resolution_x;       /* "resolution_x" (640) */
+  int32_t resolution_y;       /* "resolution_y" (480) */
+  int32_t _pad;
+  double ray_length;          /* "ray_length" (5.0) */
+  double focal_length;        /* "focal_length" (320.0) */
+  double ray_step;            /* "ray_step"; <= 0 selects the default = map voxel size */
+  double downsampling_factor; /* "downsampling_factor" (1.0) */
+  double mount_t[3];          /* "mounting_translation_{x,y,z}" */
+  double mount_q[4];          /* "mounting_rotation_{w,x,y,z}", normalised by the caller like
+                                 sensor_model.cpp:27 does */
+} a3d_caster_params;
+
+/* Parameters of a SimulatedSensorEvaluator subclass + its BoundingVolume
+   (core/src/module/trajectory_evaluator/simulated_sensor_evaluator.cpp:16-43,
+   voxel_type_evaluator.cpp:19-55, frontier_evaluator.cpp:15-67, core/src/data/bounding_volume.cpp:12-31). */
+typedef struct {
+  int32_t kind;               /* A3D_EVAL_* */
+  int32_t clear_from_parents; /* "clear_from_parents" (false) */
+  int32_t accurate_frontiers; /* "accurate_frontiers" (false) */
+  int32_t surface_frontiers;  /* "surface_frontiers" (true) */
+  double checking_distance;   /* "checking_distance" (1.0) */
+  double gains[6];            /* gain_unknown, gain_occupied, gain_free, gain_unknown_outer,
+                                 gain_occupied_outer, gain_free_outer */
+  int32_t bv_is_setup;        /* BoundingVolume::is_setup */
+  int32_t _pad;
+  double bv_min[3];           /* x_min, y_min, z_min */
+  double bv_max[3];           /* x_max, y_max, z_max */
+  double bv_quat[4];          /* w,x,y,z of AngleAxis(rotation*pi/-180, UnitZ) (bounding_volume.cpp:21) */
+} a3d_eval_params;
+
+/* Derived constants of a caster (members c_res_x_, c_res_y_, c_n_sections_, c_split_distances_,
+   c_split_widths_, c_field_of_view_{x,y}_ of the reference classes). */
+typedef struct {
+  int32_t c_res_x, c_res_y, c_n_sections, samples_per_full_ray;
+  double fov_x, fov_y, ray_step;
+  double split_distances[33];
+  int32_t split_widths[33];
+  int32_t _pad;
+} a3d_caster_info;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* One context = one GPU (one process per GPU; multi-GPU runs shard segments across processes). */
+int a3d_ctx_create(int device_id, a3d_ctx** out);
+void a3d_ctx_destroy(a3d_ctx* ctx);
+/* Text of the last error on this context (or of the last failed a3d_ctx_create if ctx == NULL). */
+const char* a3d_last_error(const a3d_ctx* ctx);
+/* The cudaStream_t all work of this context is issued on (for event timing by the caller). */
+void* a3d_ctx_stream(a3d_ctx* ctx);
+/* Device time in ms of the ray-cast/gain kernel of the most recent a3d_compute_gains*() call
+   (CUDA events on the context stream); < 0 if none. */
+float a3d_last_kernel_ms(a3d_ctx* ctx);
+/* Number of kernels this context has launched so far. */
+uint64_t a3d_kernel_launches(a3d_ctx* ctx);
+
+/* ---- map mirror: replaces VoxbloxMap (active_3d_planning_voxblox/src/map/voxblox.cpp) ------- */
+/* voxblox::EsdfServer layer parameters (tsdf_voxel_size, tsdf_voxels_per_side,
+   app_reconstruction/launch/example.launch:143-144); voxblox.cpp:26-27 caches the derived sizes. */
+int a3d_map_config(a3d_ctx* ctx, float voxel_size, int voxels_per_side);
+/* Insert-or-overwrite n blocks = the integrator's updated-block list for this planning step.
+   block_idx n×3; esdf_dist / esdf_observed / tsdf_weight n×vps³ in voxblox linear voxel order
+   x + vps*(y + vps*z); tsdf_weight may be NULL.  Replaces the esdf_map_in/tsdf_map_in layer
+   merge of voxblox::EsdfServer (run_experiment.launch:180-181). */
+int a3d_map_upload_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* esdf_dist,
+                          const uint8_t* esdf_observed, const float* tsdf_weight);
+/* Same with payload pointers in device memory (e.g. the receive buffer of an NCCL broadcast);
+   block_idx stays on the host. */
+int a3d_map_upload_blocks_dev(a3d_ctx* ctx, int n, const int32_t* block_idx,
+                              const float* esdf_dist_dev, const uint8_t* esdf_observed_dev,
+                              const float* tsdf_weight_dev);
+int a3d_map_remove_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx);
+int a3d_map_clear(a3d_ctx* ctx);
+int64_t a3d_map_num_blocks(const a3d_ctx* ctx);
+/* OccupancyMap::getVoxelSize (voxblox.cpp:63) */
+double a3d_map_voxel_size(const a3d_ctx* ctx);
+/* Batched map virtuals, n points (n×3 doubles):
+   getVoxelState voxblox.cpp:48-60 | getVoxelCenter :66-81 | isObserved :43-45 |
+   getVoxelWeight :101-115 | EsdfMap::getDistanceAtPosition as used at :35-36,:50 */
+int a3d_map_voxel_state(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out);
+int a3d_map_voxel_center(a3d_ctx* ctx, int64_t n, const double* pts, double* out);
+int a3d_map_is_observed(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out);
+int a3d_map_voxel_weight(a3d_ctx* ctx, int64_t n, const double* pts, double* out);
+int a3d_map_distance(a3d_ctx* ctx, int64_t n, const double* pts, double* dist, uint8_t* ok);
+
+/* ---- sensor model / evaluator objects ------------------------------------------------------- */
+/* Needs a configured map (ray_step default and c_res_* depend on the voxel size,
+   simple_ray_caster.cpp:17-29). */
+int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out);
+void a3d_caster_destroy(a3d_caster* c);
+int a3d_caster_get_info(const a3d_caster* c, a3d_caster_info* out);
+/* CameraModel::getDirectionVector for ray (i,j) as the casters call it (camera_model.cpp:161-168) */
+int a3d_caster_direction(const a3d_caster* c, int i, int j, double* out3);
+int a3d_eval_create(a3d_ctx* ctx, const a3d_eval_params* p, a3d_eval** out);
+void a3d_eval_destroy(a3d_eval* e);
+
+/* ---- the hot call ---------------------------------------------------------------------------
+ * Batched SimulatedSensorEvaluator::computeGain (simulated_sensor_evaluator.cpp:45-82): for every
+ * segment, ray-cast its sampled views (CameraModel::getVisibleVoxelsFromTrajectory,
+ * camera_model.cpp:15-60), adjacent-unique the voxel-centre list, drop entries outside the
+ * bounding volume, and fold the list into a gain (computeGainFromVisibleVoxels).
+ *   pos n_views×3, quat n_views×4 (w,x,y,z): body poses trajectory[idx].position_W /
+ *   orientation_W_B of the sampled trajectory points (the mounting transform is applied inside);
+ *   view_segment n_views, non-decreasing, values in [0,n_segments): which segment a view belongs to.
+ * Outputs, one per segment (each nullable except gains_out):
+ *   gains_out      TrajectorySegment::gain
+ *   n_visible_out  size of the voxel list the reference would store in SimulatedSensorInfo
+ *   n_samples_out  ray samples taken (= getVoxelState calls made by the caster)
+ *   digests_out    order-sensitive 64-bit digest of that stored list (DESIGN.md "digest")
+ * Synchronous on return.  clear_from_parents is not supported by the batch call. */
+int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
+                      const double* pos, const double* quat, const int32_t* view_segment,
+                      int n_segments, double* gains_out, uint64_t* n_visible_out,
+                      uint64_t* n_samples_out, uint64_t* digests_out);
+/* Same with every array in device memory; enqueued on the context stream, NOT synchronised.
+   view_first_dev: n_segments+1 int32 prefix offsets of each segment's views. */
+int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
+                          int n_views, const double* pos_dev, const double* quat_dev,
+                          const int32_t* view_first_dev, int n_segments, double* gains_dev,
+                          uint64_t* n_visible_dev, uint64_t* n_samples_dev, uint64_t* digests_dev);
+
+/* One segment with its voxel list materialised (parity / visualisation / the per-segment
+ * SensorModel::getVisibleVoxelsFromTrajectory + storeTrajectoryInformation API):
+ *   eval == NULL: the sensor model's list (camera_model.cpp:15-60), no gain;
+ *   eval != NULL: the list the evaluator stores (after the bounding-volume filter) and its gain.
+ * centres_out cap×3 doubles; *n_out = full list length even if > cap (then A3D_ERR_CAPACITY). */
+int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
+                       const double* pos, const double* quat, double* centres_out, int64_t cap,
+                       int64_t* n_out, int64_t* n_samples_out, double* gain_out);
+
+/* computeGainFromVisibleVoxels on an explicit stored list (the SimulatedSensorUpdater path,
+ * core/src/module/trajectory_evaluator/evaluator_updater/simulated_sensor_updater.cpp:18-22).
+ * n_left_out (nullable): list size after the fold's own erasures (Naive/Frontier drop observed
+ * voxels, naive_evaluator.cpp:28-35, frontier_evaluator.cpp:110-116); keep_out (nullable, n bytes):
+ * which entries survive. */
+int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* centres,
+                         double* gain_out, int64_t* n_left_out, uint8_t* keep_out);
+
+/* BoundingVolume::contains (core/src/data/bounding_volume.cpp:33-57), batched. */
+int a3d_bv_contains(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* pts, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A3D_H_ */

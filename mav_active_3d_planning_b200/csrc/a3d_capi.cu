@@ -1,0 +1,922 @@
+// a3d_capi.cu — host side of the C ABI declared in include/a3d.h: context, GPU block-hash mirror of
+// the voxblox layers (slot allocator + open-addressing table + voxel slab), caster/evaluator
+// objects with their host-precomputed tables, and the launch plumbing of the hot call.
+//
+// No CPU compute path exists here: every query and every gain goes through the kernels in
+// a3d_kernels.cu; a missing/unusable device is an error (A3D_ERR_CUDA).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/a3d.h"
+#include "a3d_kernels.cuh"
+
+using namespace a3d;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Key3 {
+  int32_t x, y, z;
+  bool operator==(const Key3& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct Key3Hash {
+  size_t operator()(const Key3& k) const {
+    return (static_cast<size_t>(static_cast<uint32_t>(k.x)) * 73856093u) ^
+           (static_cast<size_t>(static_cast<uint32_t>(k.y)) * 19349663u) ^
+           (static_cast<size_t>(static_cast<uint32_t>(k.z)) * 83492791u);
+  }
+};
+
+inline uint32_t host_hash3(int x, int y, int z) {  // must equal a3d::hash3
+  uint32_t h = static_cast<uint32_t>(x) * 73856093u ^ static_cast<uint32_t>(y) * 19349663u ^
+               static_cast<uint32_t>(z) * 83492791u;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return h;
+}
+
+template <typename T>
+struct DevBuf {  // grow-only device scratch
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    const size_t want = std::max(n, cap + cap / 2);
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct a3d_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  uint64_t launches = 0;
+  mutable std::string err;
+
+  // map
+  bool configured = false;
+  float vs_f = 0, vs_inv_f = 0, bs_f = 0, bs_inv_f = 0;
+  int vps = 0, nv = 0;
+  std::unordered_map<Key3, int32_t, Key3Hash> slots;
+  std::vector<int32_t> free_slots;
+  int32_t next_slot = 0;
+  std::vector<HashEntry> h_table;
+  DevBuf<HashEntry> d_table;
+  float* d_dist = nullptr;
+  float* d_weight = nullptr;
+  size_t slab_slots = 0;
+  bool has_weight = false;
+
+  // staging / scratch
+  DevBuf<float> st_dist, st_w;
+  DevBuf<uint8_t> st_obs;
+  DevBuf<int32_t> st_slots;
+  DevBuf<double> sc_pts, sc_out;
+  DevBuf<uint8_t> sc_u8;
+  DevBuf<double> sc_pos, sc_quat, sc_gains, sc_centres;
+  DevBuf<int32_t> sc_first;
+  DevBuf<unsigned long long> sc_nvis, sc_nsamp, sc_dig, sc_cnt;
+  DevBuf<int8_t> sc_tables;
+  DevBuf<unsigned int> sc_counter;
+
+  int fail(int code, const std::string& msg) const {
+    err = msg;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) const {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return A3D_ERR_CUDA;
+  }
+  MapView view() const {
+    MapView m{};
+    m.table = d_table.p;
+    m.dist = d_dist;
+    m.weight = has_weight ? d_weight : nullptr;
+    m.meta = nullptr;
+    m.mask = static_cast<uint32_t>(h_table.size() - 1);
+    m.vps = vps;
+    m.nv = nv;
+    m.vs_f = vs_f;
+    m.vs_inv_f = vs_inv_f;
+    m.bs_f = bs_f;
+    m.bs_inv_f = bs_inv_f;
+    m.c_vs = static_cast<double>(vs_f);
+    return m;
+  }
+};
+
+struct a3d_caster {
+  a3d_ctx* ctx;
+  a3d_caster_params p;
+  a3d_caster_info info;
+  std::vector<double> h_dirs;
+  double* d_dirs = nullptr;
+  double* d_dseq = nullptr;
+  int32_t* d_kcount = nullptr;
+  int32_t* d_seg_end = nullptr;
+  CasterView view{};
+};
+
+struct a3d_eval {
+  a3d_ctx* ctx;
+  a3d_eval_params p;
+  EvalView view{};
+};
+
+#define CK(call)                                          \
+  do {                                                    \
+    cudaError_t _e = (call);                              \
+    if (_e != cudaSuccess) return ctx->cuda_fail(_e, #call); \
+  } while (0)
+
+namespace {
+
+void table_insert(std::vector<HashEntry>& t, int x, int y, int z, int slot) {
+  const uint32_t mask = static_cast<uint32_t>(t.size() - 1);
+  uint32_t h = host_hash3(x, y, z) & mask;
+  while (t[h].slot >= 0) {
+    if (t[h].x == x && t[h].y == y && t[h].z == z) {
+      t[h].slot = slot;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+  t[h] = HashEntry{x, y, z, slot};
+}
+
+void table_rebuild(a3d_ctx* ctx, size_t min_entries) {
+  size_t cap = 1024;
+  while (cap < 4 * min_entries) cap <<= 1;  // load factor <= 0.25
+  ctx->h_table.assign(cap, HashEntry{0, 0, 0, -1});
+  for (const auto& kv : ctx->slots)
+    table_insert(ctx->h_table, kv.first.x, kv.first.y, kv.first.z, kv.second);
+}
+
+int table_upload(a3d_ctx* ctx) {
+  CK(ctx->d_table.reserve(ctx->h_table.size()));
+  CK(cudaMemcpyAsync(ctx->d_table.p, ctx->h_table.data(), ctx->h_table.size() * sizeof(HashEntry),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  return A3D_OK;
+}
+
+int slab_reserve(a3d_ctx* ctx, size_t n_slots, bool want_weight) {
+  const size_t nv = static_cast<size_t>(ctx->nv);
+  if (n_slots > ctx->slab_slots) {
+    const size_t cap = std::max<size_t>(std::max<size_t>(n_slots, ctx->slab_slots * 2), 64);
+    float* nd = nullptr;
+    CK(cudaMalloc(&nd, cap * nv * sizeof(float)));
+    if (ctx->d_dist) {
+      CK(cudaMemcpyAsync(nd, ctx->d_dist, ctx->slab_slots * nv * sizeof(float),
+                         cudaMemcpyDeviceToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_dist);
+    }
+    ctx->d_dist = nd;
+    if (ctx->d_weight) {
+      float* nw = nullptr;
+      CK(cudaMalloc(&nw, cap * nv * sizeof(float)));
+      CK(cudaMemcpyAsync(nw, ctx->d_weight, ctx->slab_slots * nv * sizeof(float),
+                         cudaMemcpyDeviceToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_weight);
+      ctx->d_weight = nw;
+    }
+    ctx->slab_slots = cap;
+  }
+  if (want_weight && !ctx->d_weight) {
+    CK(cudaMalloc(&ctx->d_weight, ctx->slab_slots * nv * sizeof(float)));
+    CK(cudaMemsetAsync(ctx->d_weight, 0, ctx->slab_slots * nv * sizeof(float), ctx->stream));
+    ctx->has_weight = true;
+  }
+  return A3D_OK;
+}
+
+// Shared by the host- and device-pointer upload entry points.
+int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* dist,
+                       const uint8_t* obs, const float* w, bool payload_on_device) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
+  if (n < 0 || (n > 0 && (!block_idx || !dist || !obs)))
+    return ctx->fail(A3D_ERR_INVALID, "null block payload");
+  if (n == 0) return A3D_OK;
+  CK(cudaSetDevice(ctx->device));
+  // slot assignment
+  std::vector<int32_t> slot_of(n);
+  bool table_dirty = false;
+  for (int i = 0; i < n; ++i) {
+    const Key3 k{block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2]};
+    auto it = ctx->slots.find(k);
+    if (it != ctx->slots.end()) {
+      slot_of[i] = it->second;
+      continue;
+    }
+    int32_t s;
+    if (!ctx->free_slots.empty()) {
+      s = ctx->free_slots.back();
+      ctx->free_slots.pop_back();
+    } else {
+      s = ctx->next_slot++;
+    }
+    ctx->slots.emplace(k, s);
+    slot_of[i] = s;
+    table_dirty = true;
+  }
+  int rc = slab_reserve(ctx, static_cast<size_t>(ctx->next_slot), w != nullptr);
+  if (rc) return rc;
+  if (table_dirty) {
+    if (ctx->h_table.empty() || 4 * ctx->slots.size() > ctx->h_table.size()) {
+      table_rebuild(ctx, ctx->slots.size());
+    } else {
+      for (int i = 0; i < n; ++i)
+        table_insert(ctx->h_table, block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2],
+                     slot_of[i]);
+    }
+    rc = table_upload(ctx);
+    if (rc) return rc;
+  }
+  // payload, in chunks bounded by the staging size
+  const size_t nv = static_cast<size_t>(ctx->nv);
+  const int chunk = static_cast<int>(std::max<size_t>(1, (size_t(256) << 20) / (nv * 4)));
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int m = std::min(chunk, n - i0);
+    CK(ctx->st_slots.reserve(m));
+    CK(cudaMemcpyAsync(ctx->st_slots.p, slot_of.data() + i0, m * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    const float* dsrc = dist + static_cast<size_t>(i0) * nv;
+    const uint8_t* osrc = obs + static_cast<size_t>(i0) * nv;
+    const float* wsrc = w ? w + static_cast<size_t>(i0) * nv : nullptr;
+    if (!payload_on_device) {
+      CK(ctx->st_dist.reserve(m * nv));
+      CK(ctx->st_obs.reserve(m * nv));
+      CK(cudaMemcpyAsync(ctx->st_dist.p, dsrc, m * nv * sizeof(float), cudaMemcpyHostToDevice,
+                         ctx->stream));
+      CK(cudaMemcpyAsync(ctx->st_obs.p, osrc, m * nv, cudaMemcpyHostToDevice, ctx->stream));
+      dsrc = ctx->st_dist.p;
+      osrc = ctx->st_obs.p;
+      if (w) {
+        CK(ctx->st_w.reserve(m * nv));
+        CK(cudaMemcpyAsync(ctx->st_w.p, wsrc, m * nv * sizeof(float), cudaMemcpyHostToDevice,
+                           ctx->stream));
+        wsrc = ctx->st_w.p;
+      }
+    }
+    launch_apply_blocks(ctx->stream, m, ctx->nv, ctx->st_slots.p, dsrc, osrc, wsrc, ctx->d_dist,
+                        ctx->has_weight ? ctx->d_weight : nullptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));  // staging buffers are reused by the next chunk
+  }
+  return A3D_OK;
+}
+
+int point_query(a3d_ctx* ctx, int what, int64_t n, const double* pts, void* out0, size_t out0_elt,
+                void* out1) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
+  if (n < 0 || (n > 0 && (!pts || !out0))) return ctx->fail(A3D_ERR_INVALID, "null argument");
+  if (n == 0) return A3D_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->h_table.empty()) {
+    table_rebuild(ctx, 0);
+    int rc = table_upload(ctx);
+    if (rc) return rc;
+  }
+  CK(ctx->sc_pts.reserve(3 * n));
+  CK(cudaMemcpyAsync(ctx->sc_pts.p, pts, 3 * n * sizeof(double), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  const size_t out0_bytes = static_cast<size_t>(n) * out0_elt;
+  CK(ctx->sc_out.reserve((out0_bytes + 7) / 8));
+  CK(ctx->sc_u8.reserve(n));
+  launch_point_query(ctx->stream, ctx->view(), what, n, ctx->sc_pts.p, ctx->sc_out.p, ctx->sc_u8.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out0, ctx->sc_out.p, out0_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out1) CK(cudaMemcpyAsync(out1, ctx->sc_u8.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return A3D_OK;
+}
+
+EvalView make_eval_view(const a3d_ctx* ctx, const a3d_eval_params& p) {
+  EvalView v{};
+  v.kind = p.kind;
+  v.accurate_frontiers = p.accurate_frontiers;
+  v.surface_frontiers = p.surface_frontiers;
+  v.bv_is_setup = p.bv_is_setup;
+  v.nb_step = static_cast<double>(ctx->vs_f) * p.checking_distance;  // frontier_evaluator.cpp:30-31
+  for (int i = 0; i < 6; ++i) v.gains[i] = p.gains[i];
+  for (int i = 0; i < 3; ++i) {
+    v.bv_min[i] = p.bv_min[i];
+    v.bv_max[i] = p.bv_max[i];
+  }
+  v.bv_q = Q4{p.bv_quat[0], p.bv_quat[1], p.bv_quat[2], p.bv_quat[3]};
+  return v;
+}
+
+// Enqueue the cast+gain kernel for a batch whose inputs/outputs are already on the device.
+int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const double* pos_dev,
+                 const double* quat_dev, const int32_t* first_dev, int n_segments, double* gains_dev,
+                 unsigned long long* nvis_dev, unsigned long long* nsamp_dev,
+                 unsigned long long* dig_dev, double* centres_dev, long long cap, bool emit) {
+  if (ctx->h_table.empty()) {
+    table_rebuild(ctx, 0);
+    int rc = table_upload(ctx);
+    if (rc) return rc;
+  }
+  const int block = cast_gain_block_threads();
+  const int warps_per_block = block / 32;
+  int grid = (n_segments + warps_per_block - 1) / warps_per_block;
+  grid = std::max(1, std::min(grid, ctx->sm_count * 32));
+  Batch b{};
+  b.pos = pos_dev;
+  b.quat = quat_dev;
+  b.view_first = first_dev;
+  b.n_segments = n_segments;
+  b.gains = gains_dev;
+  b.n_visible = nvis_dev;
+  b.n_samples = nsamp_dev;
+  b.digests = dig_dev;
+  b.centres_out = centres_dev;
+  b.cap = cap;
+  if (c->view.kind == A3D_CASTER_ITERATIVE) {
+    b.table_stride = (static_cast<size_t>(c->view.n_rays) + 15) / 16 * 16;
+    CK(ctx->sc_tables.reserve(b.table_stride * grid * warps_per_block));
+    b.tables = ctx->sc_tables.p;
+  }
+  CK(ctx->sc_counter.reserve(1));
+  b.work_counter = ctx->sc_counter.p;
+  CK(cudaMemsetAsync(ctx->sc_counter.p, 0, sizeof(unsigned int), ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  launch_cast_gain(ctx->stream, ctx->view(), c->view, e ? &e->view : nullptr, b, dig_dev != nullptr,
+                   emit, grid, block);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  return A3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int a3d_ctx_create(int device_id, a3d_ctx** out) {
+  if (!out) return A3D_ERR_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return A3D_ERR_CUDA;
+  }
+  if (device_id < 0 || device_id >= n_dev) {
+    g_create_error = "device_id out of range";
+    return A3D_ERR_INVALID;
+  }
+  e = cudaSetDevice(device_id);
+  if (e != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return A3D_ERR_CUDA;
+  }
+  a3d_ctx* ctx = new a3d_ctx();
+  ctx->device = device_id;
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, device_id);
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    g_create_error = "liba3d_b200 is built for sm_100a only; device is sm_" +
+                     std::to_string(prop.major) + std::to_string(prop.minor);
+    delete ctx;
+    return A3D_ERR_CUDA;
+  }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    g_create_error = "stream/event creation failed";
+    delete ctx;
+    return A3D_ERR_CUDA;
+  }
+  *out = ctx;
+  return A3D_OK;
+}
+
+void a3d_ctx_destroy(a3d_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_dist) cudaFree(ctx->d_dist);
+  if (ctx->d_weight) cudaFree(ctx->d_weight);
+  ctx->d_table.release();
+  ctx->st_dist.release();
+  ctx->st_w.release();
+  ctx->st_obs.release();
+  ctx->st_slots.release();
+  ctx->sc_pts.release();
+  ctx->sc_out.release();
+  ctx->sc_u8.release();
+  ctx->sc_pos.release();
+  ctx->sc_quat.release();
+  ctx->sc_gains.release();
+  ctx->sc_centres.release();
+  ctx->sc_first.release();
+  ctx->sc_nvis.release();
+  ctx->sc_nsamp.release();
+  ctx->sc_dig.release();
+  ctx->sc_cnt.release();
+  ctx->sc_tables.release();
+  ctx->sc_counter.release();
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* a3d_last_error(const a3d_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+void* a3d_ctx_stream(a3d_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+float a3d_last_kernel_ms(a3d_ctx* ctx) {
+  if (!ctx || !ctx->timed) return -1.0f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+uint64_t a3d_kernel_launches(a3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int a3d_map_config(a3d_ctx* ctx, float voxel_size, int vps) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!(voxel_size > 0.0f) || vps < 1 || vps > 64)
+    return ctx->fail(A3D_ERR_INVALID, "voxel_size must be > 0 and 1 <= voxels_per_side <= 64");
+  if (ctx->configured && !ctx->slots.empty())
+    return ctx->fail(A3D_ERR_STATE, "map already holds blocks; a3d_map_clear first");
+  // voxblox Layer / Block constructors
+  ctx->vs_f = voxel_size;
+  ctx->vps = vps;
+  ctx->nv = vps * vps * vps;
+  ctx->vs_inv_f = static_cast<float>(1.0 / static_cast<double>(voxel_size));
+  ctx->bs_f = voxel_size * static_cast<float>(vps);
+  ctx->bs_inv_f = static_cast<float>(1.0 / static_cast<double>(ctx->bs_f));
+  ctx->configured = true;
+  return A3D_OK;
+}
+
+int a3d_map_upload_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* esdf_dist,
+                          const uint8_t* esdf_observed, const float* tsdf_weight) {
+  return upload_blocks_impl(ctx, n, block_idx, esdf_dist, esdf_observed, tsdf_weight, false);
+}
+int a3d_map_upload_blocks_dev(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* dist_dev,
+                              const uint8_t* obs_dev, const float* w_dev) {
+  return upload_blocks_impl(ctx, n, block_idx, dist_dev, obs_dev, w_dev, true);
+}
+
+int a3d_map_remove_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
+  if (n < 0 || (n > 0 && !block_idx)) return ctx->fail(A3D_ERR_INVALID, "null block_idx");
+  CK(cudaSetDevice(ctx->device));
+  bool dirty = false;
+  for (int i = 0; i < n; ++i) {
+    auto it = ctx->slots.find(Key3{block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2]});
+    if (it == ctx->slots.end()) continue;
+    ctx->free_slots.push_back(it->second);
+    ctx->slots.erase(it);
+    dirty = true;
+  }
+  if (dirty) {
+    table_rebuild(ctx, ctx->slots.size());
+    int rc = table_upload(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return A3D_OK;
+}
+
+int a3d_map_clear(a3d_ctx* ctx) {
+  if (!ctx) return A3D_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  ctx->slots.clear();
+  ctx->free_slots.clear();
+  ctx->next_slot = 0;
+  if (ctx->configured) {
+    table_rebuild(ctx, 0);
+    int rc = table_upload(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return A3D_OK;
+}
+
+int64_t a3d_map_num_blocks(const a3d_ctx* ctx) {
+  return ctx ? static_cast<int64_t>(ctx->slots.size()) : 0;
+}
+double a3d_map_voxel_size(const a3d_ctx* ctx) {
+  return ctx ? static_cast<double>(ctx->vs_f) : 0.0;
+}
+
+int a3d_map_voxel_state(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out) {
+  return point_query(ctx, kQueryState, n, pts, out, 1, nullptr);
+}
+int a3d_map_voxel_center(a3d_ctx* ctx, int64_t n, const double* pts, double* out) {
+  return point_query(ctx, kQueryCenter, n, pts, out, 24, nullptr);
+}
+int a3d_map_is_observed(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out) {
+  return point_query(ctx, kQueryObserved, n, pts, out, 1, nullptr);
+}
+int a3d_map_voxel_weight(a3d_ctx* ctx, int64_t n, const double* pts, double* out) {
+  return point_query(ctx, kQueryWeight, n, pts, out, 8, nullptr);
+}
+int a3d_map_distance(a3d_ctx* ctx, int64_t n, const double* pts, double* dist, uint8_t* ok) {
+  if (ctx && n > 0 && !ok) return ctx->fail(A3D_ERR_INVALID, "null argument");
+  return point_query(ctx, kQueryDistance, n, pts, dist, 8, ok);
+}
+
+// ---- caster ---------------------------------------------------------------------------------
+int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out) {
+  if (!ctx || !out) return A3D_ERR_INVALID;
+  *out = nullptr;
+  if (!p) return ctx->fail(A3D_ERR_INVALID, "null params");
+  if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
+  // CameraModel::checkParamsValid (camera_model.cpp:185-200)
+  if (!(p->ray_length > 0.0)) return ctx->fail(A3D_ERR_INVALID, "ray_length expected > 0.0");
+  if (!(p->focal_length > 0.0)) return ctx->fail(A3D_ERR_INVALID, "focal_length expected > 0.0");
+  if (p->resolution_x <= 0) return ctx->fail(A3D_ERR_INVALID, "resolution_x expected > 0");
+  if (p->resolution_y <= 0) return ctx->fail(A3D_ERR_INVALID, "resolution_y expected > 0");
+  if (p->kind != A3D_CASTER_SIMPLE && p->kind != A3D_CASTER_ITERATIVE)
+    return ctx->fail(A3D_ERR_INVALID, "unknown caster kind");
+  if (!(p->downsampling_factor > 0.0))
+    return ctx->fail(A3D_ERR_INVALID, "downsampling_factor expected > 0.0");
+  CK(cudaSetDevice(ctx->device));
+
+  a3d_caster_info info{};
+  const double vs = static_cast<double>(ctx->vs_f);  // OccupancyMap::getVoxelSize
+  // camera_model.cpp:181-182
+  info.fov_x = 2.0 * std::atan2(static_cast<double>(p->resolution_x), p->focal_length * 2.0);
+  info.fov_y = 2.0 * std::atan2(static_cast<double>(p->resolution_y), p->focal_length * 2.0);
+  info.ray_step = p->ray_step > 0.0 ? p->ray_step : vs;
+  // simple_ray_caster.cpp:22-29 == iterative_ray_caster.cpp:25-32
+  info.c_res_x = std::min(
+      static_cast<int>(std::ceil(p->ray_length * info.fov_x / (vs * p->downsampling_factor))),
+      p->resolution_x);
+  info.c_res_y = std::min(
+      static_cast<int>(std::ceil(p->ray_length * info.fov_y / (vs * p->downsampling_factor))),
+      p->resolution_y);
+  if (info.c_res_x < 2 || info.c_res_y < 2)
+    return ctx->fail(A3D_ERR_INVALID,
+                     "derived ray grid smaller than 2x2 (the reference divides by c_res-1)");
+  const int n_rays = info.c_res_x * info.c_res_y;
+  int n_sections = 0;
+  std::vector<double> split;  // c_split_distances_
+  if (p->kind == A3D_CASTER_ITERATIVE) {
+    // iterative_ray_caster.cpp:35-45
+    n_sections = static_cast<int>(std::floor(std::log2(
+        std::min(static_cast<double>(info.c_res_x), static_cast<double>(info.c_res_y)))));
+    if (n_sections < 1 || n_sections > 31)
+      return ctx->fail(A3D_ERR_INVALID, "c_n_sections out of range");
+    split.assign(n_sections + 1, 0.0);
+    for (int t = 1; t <= n_sections; ++t)
+      split[t] = p->ray_length / std::pow(2.0, static_cast<double>(n_sections - t));
+    for (int t = 0; t <= n_sections; ++t) {
+      info.split_distances[t] = split[t];
+      info.split_widths[t] = t < n_sections ? (1 << (n_sections - 1 - t)) : 0;
+    }
+  }
+  info.c_n_sections = n_sections;
+
+  // Accumulated sample distances (simple_ray_caster.cpp:46-50, iterative_ray_caster.cpp:75-79):
+  // d_0 = start, d_{k+1} = d_k + ray_step while d_k < ray_length.  One sequence per start section.
+  const int n_starts = p->kind == A3D_CASTER_ITERATIVE ? n_sections : 1;
+  std::vector<std::vector<double>> seqs(n_starts);
+  size_t kmax = 1;
+  for (int s = 0; s < n_starts; ++s) {
+    double d = p->kind == A3D_CASTER_ITERATIVE ? split[s] : 0.0;
+    while (d < p->ray_length) {
+      seqs[s].push_back(d);
+      d += info.ray_step;
+      if (seqs[s].size() > (size_t(1) << 24))
+        return ctx->fail(A3D_ERR_INVALID, "ray_step too small for ray_length");
+    }
+    kmax = std::max(kmax, seqs[s].size());
+  }
+  info.samples_per_full_ray = static_cast<int32_t>(seqs[0].size());
+  kmax = (kmax + 31) / 32 * 32;
+  std::vector<double> dseq(static_cast<size_t>(n_starts) * kmax, 0.0);
+  std::vector<int32_t> kcount(n_starts), seg_end(static_cast<size_t>(n_starts) * std::max(1, n_sections), 0);
+  for (int s = 0; s < n_starts; ++s) {
+    std::copy(seqs[s].begin(), seqs[s].end(), dseq.begin() + static_cast<size_t>(s) * kmax);
+    kcount[s] = static_cast<int32_t>(seqs[s].size());
+    for (int t = 0; t < n_sections; ++t) {
+      int cnt = 0;
+      for (double d : seqs[s])
+        if (d < split[t + 1]) ++cnt;
+      seg_end[static_cast<size_t>(s) * n_sections + t] = cnt;
+    }
+  }
+
+  // Camera-frame directions (camera_model.cpp:161-168 as called at simple_ray_caster.cpp:41-44)
+  a3d_caster* c = new a3d_caster();
+  c->ctx = ctx;
+  c->p = *p;
+  c->info = info;
+  c->h_dirs.resize(static_cast<size_t>(n_rays) * 3);
+  for (int i = 0; i < info.c_res_x; ++i) {
+    for (int j = 0; j < info.c_res_y; ++j) {
+      const double rx = static_cast<double>(i) / (static_cast<double>(info.c_res_x) - 1.0);
+      const double ry = static_cast<double>(j) / (static_cast<double>(info.c_res_y) - 1.0);
+      const double vx = p->focal_length;
+      const double vy = (0.5 - rx) * static_cast<double>(p->resolution_x);
+      const double vz = (0.5 - ry) * static_cast<double>(p->resolution_y);
+      const double nrm = std::sqrt((vx * vx + vy * vy) + vz * vz);
+      double* o = &c->h_dirs[(static_cast<size_t>(i) * info.c_res_y + j) * 3];
+      o[0] = vx / nrm;
+      o[1] = vy / nrm;
+      o[2] = vz / nrm;
+    }
+  }
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  };
+  cudaError_t e = up(reinterpret_cast<void**>(&c->d_dirs), c->h_dirs.data(), c->h_dirs.size() * 8);
+  if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&c->d_dseq), dseq.data(), dseq.size() * 8);
+  if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&c->d_kcount), kcount.data(), kcount.size() * 4);
+  if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&c->d_seg_end), seg_end.data(), seg_end.size() * 4);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    a3d_caster_destroy(c);
+    return ctx->cuda_fail(e, "caster table upload");
+  }
+  CasterView& v = c->view;
+  v.kind = p->kind;
+  v.res_x = info.c_res_x;
+  v.res_y = info.c_res_y;
+  v.n_rays = n_rays;
+  v.n_sections = n_sections;
+  v.n_starts = n_starts;
+  v.kmax = static_cast<int32_t>(kmax);
+  v.cam_dirs = c->d_dirs;
+  v.dseq = c->d_dseq;
+  v.kcount = c->d_kcount;
+  v.seg_end = c->d_seg_end;
+  for (int i = 0; i < 3; ++i) v.mount_t[i] = p->mount_t[i];
+  v.mount_q = Q4{p->mount_q[0], p->mount_q[1], p->mount_q[2], p->mount_q[3]};
+  *out = c;
+  return A3D_OK;
+}
+
+void a3d_caster_destroy(a3d_caster* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  if (c->d_dirs) cudaFree(c->d_dirs);
+  if (c->d_dseq) cudaFree(c->d_dseq);
+  if (c->d_kcount) cudaFree(c->d_kcount);
+  if (c->d_seg_end) cudaFree(c->d_seg_end);
+  delete c;
+}
+
+int a3d_caster_get_info(const a3d_caster* c, a3d_caster_info* out) {
+  if (!c || !out) return A3D_ERR_INVALID;
+  *out = c->info;
+  return A3D_OK;
+}
+int a3d_caster_direction(const a3d_caster* c, int i, int j, double* out3) {
+  if (!c || !out3 || i < 0 || j < 0 || i >= c->info.c_res_x || j >= c->info.c_res_y)
+    return A3D_ERR_INVALID;
+  const double* d = &c->h_dirs[(static_cast<size_t>(i) * c->info.c_res_y + j) * 3];
+  out3[0] = d[0];
+  out3[1] = d[1];
+  out3[2] = d[2];
+  return A3D_OK;
+}
+
+int a3d_eval_create(a3d_ctx* ctx, const a3d_eval_params* p, a3d_eval** out) {
+  if (!ctx || !out) return A3D_ERR_INVALID;
+  *out = nullptr;
+  if (!p) return ctx->fail(A3D_ERR_INVALID, "null params");
+  if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
+  if (p->kind < A3D_EVAL_VOXEL_TYPE || p->kind > A3D_EVAL_FRONTIER)
+    return ctx->fail(A3D_ERR_INVALID, "unknown evaluator kind");
+  a3d_eval* e = new a3d_eval();
+  e->ctx = ctx;
+  e->p = *p;
+  e->view = make_eval_view(ctx, *p);
+  *out = e;
+  return A3D_OK;
+}
+void a3d_eval_destroy(a3d_eval* e) { delete e; }
+
+// ---- hot call --------------------------------------------------------------------------------
+int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
+                          const double* pos_dev, const double* quat_dev,
+                          const int32_t* view_first_dev, int n_segments, double* gains_dev,
+                          uint64_t* n_visible_dev, uint64_t* n_samples_dev, uint64_t* digests_dev) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!caster || !eval || caster->ctx != ctx || eval->ctx != ctx)
+    return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
+  if (eval->p.clear_from_parents)
+    return ctx->fail(A3D_ERR_UNSUPPORTED, "clear_from_parents is not supported by the batch call");
+  if (n_views < 0 || n_segments < 0) return ctx->fail(A3D_ERR_INVALID, "negative count");
+  if (n_segments == 0) return A3D_OK;
+  if (!pos_dev || !quat_dev || !view_first_dev || !gains_dev)
+    return ctx->fail(A3D_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return enqueue_cast(ctx, caster, eval, pos_dev, quat_dev, view_first_dev, n_segments, gains_dev,
+                      reinterpret_cast<unsigned long long*>(n_visible_dev),
+                      reinterpret_cast<unsigned long long*>(n_samples_dev),
+                      reinterpret_cast<unsigned long long*>(digests_dev), nullptr, 0, false);
+}
+
+int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
+                      const double* pos, const double* quat, const int32_t* view_segment,
+                      int n_segments, double* gains_out, uint64_t* n_visible_out,
+                      uint64_t* n_samples_out, uint64_t* digests_out) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!caster || !eval || caster->ctx != ctx || eval->ctx != ctx)
+    return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
+  if (n_views < 0 || n_segments < 0) return ctx->fail(A3D_ERR_INVALID, "negative count");
+  if (n_segments == 0) return A3D_OK;
+  if ((n_views > 0 && (!pos || !quat || !view_segment)) || !gains_out)
+    return ctx->fail(A3D_ERR_INVALID, "null argument");
+  std::vector<int32_t> first(static_cast<size_t>(n_segments) + 1, 0);
+  for (int v = 0; v < n_views; ++v) {
+    const int s = view_segment[v];
+    if (s < 0 || s >= n_segments) return ctx->fail(A3D_ERR_INVALID, "view_segment out of range");
+    if (v > 0 && s < view_segment[v - 1])
+      return ctx->fail(A3D_ERR_INVALID, "view_segment must be non-decreasing");
+    first[s + 1]++;
+  }
+  for (int s = 0; s < n_segments; ++s) first[s + 1] += first[s];
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->sc_pos.reserve(3 * static_cast<size_t>(std::max(n_views, 1))));
+  CK(ctx->sc_quat.reserve(4 * static_cast<size_t>(std::max(n_views, 1))));
+  CK(ctx->sc_first.reserve(first.size()));
+  CK(ctx->sc_gains.reserve(n_segments));
+  CK(ctx->sc_nvis.reserve(n_segments));
+  CK(ctx->sc_nsamp.reserve(n_segments));
+  if (digests_out) CK(ctx->sc_dig.reserve(n_segments));
+  if (n_views > 0) {
+    CK(cudaMemcpyAsync(ctx->sc_pos.p, pos, 3 * sizeof(double) * n_views, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sc_quat.p, quat, 4 * sizeof(double) * n_views, cudaMemcpyHostToDevice,
+                       ctx->stream));
+  }
+  CK(cudaMemcpyAsync(ctx->sc_first.p, first.data(), first.size() * sizeof(int32_t),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  int rc = a3d_compute_gains_dev(ctx, caster, eval, n_views, ctx->sc_pos.p, ctx->sc_quat.p,
+                                 ctx->sc_first.p, n_segments, ctx->sc_gains.p,
+                                 reinterpret_cast<uint64_t*>(ctx->sc_nvis.p),
+                                 reinterpret_cast<uint64_t*>(ctx->sc_nsamp.p),
+                                 digests_out ? reinterpret_cast<uint64_t*>(ctx->sc_dig.p) : nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(gains_out, ctx->sc_gains.p, sizeof(double) * n_segments,
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_visible_out)
+    CK(cudaMemcpyAsync(n_visible_out, ctx->sc_nvis.p, 8 * static_cast<size_t>(n_segments),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_samples_out)
+    CK(cudaMemcpyAsync(n_samples_out, ctx->sc_nsamp.p, 8 * static_cast<size_t>(n_segments),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  if (digests_out)
+    CK(cudaMemcpyAsync(digests_out, ctx->sc_dig.p, 8 * static_cast<size_t>(n_segments),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return A3D_OK;
+}
+
+int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
+                       const double* pos, const double* quat, double* centres_out, int64_t cap,
+                       int64_t* n_out, int64_t* n_samples_out, double* gain_out) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!caster || caster->ctx != ctx || (eval && eval->ctx != ctx))
+    return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
+  if (eval && eval->p.clear_from_parents)
+    return ctx->fail(A3D_ERR_UNSUPPORTED, "clear_from_parents is not supported");
+  if (n_views < 0 || cap < 0 || (n_views > 0 && (!pos || !quat)) || (cap > 0 && !centres_out) ||
+      !n_out)
+    return ctx->fail(A3D_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const int32_t first[2] = {0, n_views};
+  CK(ctx->sc_pos.reserve(3 * static_cast<size_t>(std::max(n_views, 1))));
+  CK(ctx->sc_quat.reserve(4 * static_cast<size_t>(std::max(n_views, 1))));
+  CK(ctx->sc_first.reserve(2));
+  CK(ctx->sc_gains.reserve(1));
+  CK(ctx->sc_nvis.reserve(1));
+  CK(ctx->sc_nsamp.reserve(1));
+  CK(ctx->sc_centres.reserve(3 * static_cast<size_t>(std::max<int64_t>(cap, 1))));
+  if (n_views > 0) {
+    CK(cudaMemcpyAsync(ctx->sc_pos.p, pos, 3 * sizeof(double) * n_views, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sc_quat.p, quat, 4 * sizeof(double) * n_views, cudaMemcpyHostToDevice,
+                       ctx->stream));
+  }
+  CK(cudaMemcpyAsync(ctx->sc_first.p, first, sizeof(first), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = enqueue_cast(ctx, caster, eval, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, 1,
+                        ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr,
+                        ctx->sc_centres.p, cap, true);
+  if (rc) return rc;
+  unsigned long long nvis = 0, nsamp = 0;
+  double gain = 0.0;
+  CK(cudaMemcpyAsync(&nvis, ctx->sc_nvis.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&nsamp, ctx->sc_nsamp.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&gain, ctx->sc_gains.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int64_t n_copy = std::min<int64_t>(static_cast<int64_t>(nvis), cap);
+  if (n_copy > 0) {
+    CK(cudaMemcpyAsync(centres_out, ctx->sc_centres.p, 24 * static_cast<size_t>(n_copy),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  *n_out = static_cast<int64_t>(nvis);
+  if (n_samples_out) *n_samples_out = static_cast<int64_t>(nsamp);
+  if (gain_out) *gain_out = gain;
+  if (static_cast<int64_t>(nvis) > cap)
+    return ctx->fail(A3D_ERR_CAPACITY, "centres_out too small for the voxel list");
+  return A3D_OK;
+}
+
+int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* centres,
+                         double* gain_out, int64_t* n_left_out, uint8_t* keep_out) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!eval || eval->ctx != ctx) return ctx->fail(A3D_ERR_INVALID, "eval missing");
+  if (n < 0 || (n > 0 && !centres) || !gain_out) return ctx->fail(A3D_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->h_table.empty()) {
+    table_rebuild(ctx, 0);
+    int rc = table_upload(ctx);
+    if (rc) return rc;
+  }
+  unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (n > 0) {
+    CK(ctx->sc_pts.reserve(3 * n));
+    CK(ctx->sc_cnt.reserve(8));
+    CK(ctx->sc_u8.reserve(n));
+    CK(cudaMemcpyAsync(ctx->sc_pts.p, centres, 24 * static_cast<size_t>(n), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CK(cudaMemsetAsync(ctx->sc_cnt.p, 0, 64, ctx->stream));
+    launch_gain_from_voxels(ctx->stream, ctx->view(), eval->view, n, ctx->sc_pts.p, ctx->sc_cnt.p,
+                            keep_out ? ctx->sc_u8.p : nullptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cnt, ctx->sc_cnt.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    if (keep_out)
+      CK(cudaMemcpyAsync(keep_out, ctx->sc_u8.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (eval->p.kind == A3D_EVAL_VOXEL_TYPE) {
+    // fall-through sums of voxel_type_evaluator.cpp:69-85
+    double g = 0.0;
+    for (int o = 0; o < 2; ++o) {
+      const double n_unk = static_cast<double>(cnt[2 + 3 * o]);
+      const double n_free = static_cast<double>(cnt[1 + 3 * o] + cnt[2 + 3 * o]);
+      const double n_occ = static_cast<double>(cnt[0 + 3 * o] + cnt[1 + 3 * o] + cnt[2 + 3 * o]);
+      g += n_unk * eval->p.gains[0 + 3 * o];
+      g += n_free * eval->p.gains[2 + 3 * o];
+      g += n_occ * eval->p.gains[1 + 3 * o];
+    }
+    *gain_out = g;
+  } else {
+    *gain_out = static_cast<double>(cnt[0]);
+  }
+  if (n_left_out) *n_left_out = static_cast<int64_t>(cnt[6]);
+  return A3D_OK;
+}
+
+int a3d_bv_contains(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* pts, uint8_t* out) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!eval || eval->ctx != ctx) return ctx->fail(A3D_ERR_INVALID, "eval missing");
+  if (n < 0 || (n > 0 && (!pts || !out))) return ctx->fail(A3D_ERR_INVALID, "bad argument");
+  if (n == 0) return A3D_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->sc_pts.reserve(3 * n));
+  CK(ctx->sc_u8.reserve(n));
+  CK(cudaMemcpyAsync(ctx->sc_pts.p, pts, 24 * static_cast<size_t>(n), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  launch_bv_contains(ctx->stream, eval->view, n, ctx->sc_pts.p, ctx->sc_u8.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->sc_u8.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return A3D_OK;
+}
+
+}  // extern "C"

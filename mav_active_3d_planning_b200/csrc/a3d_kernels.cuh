@@ -1,0 +1,64 @@
+// a3d_kernels.cuh — kernel-side views of caster / batch state + launch prototypes.
+#pragma once
+
+#include "a3d_device.cuh"
+
+namespace a3d {
+
+// Host-precomputed, view-independent tables of one CameraModel subclass.
+struct CasterView {
+  int32_t kind;        // A3D_CASTER_*
+  int32_t res_x, res_y, n_rays;
+  int32_t n_sections;  // iterative only (0 for simple)
+  int32_t n_starts;    // number of distance sequences (1 for simple, n_sections for iterative)
+  int32_t kmax;        // row stride of dseq
+  int32_t _pad;
+  const double* __restrict__ cam_dirs;  // n_rays×3 camera-frame unit directions, ray r = i*res_y + j
+  const double* __restrict__ dseq;      // n_starts×kmax accumulated sample distances
+  const int32_t* __restrict__ kcount;   // n_starts: samples of a full (unoccluded) ray
+  const int32_t* __restrict__ seg_end;  // n_starts×n_sections: #samples lying in sections <= t
+  double mount_t[3];
+  Q4 mount_q;
+};
+
+struct Batch {
+  const double* __restrict__ pos;          // n_views×3
+  const double* __restrict__ quat;         // n_views×4 (w,x,y,z)
+  const int32_t* __restrict__ view_first;  // n_segments+1
+  int32_t n_segments;
+  int32_t _pad;
+  double* gains;
+  unsigned long long* n_visible;
+  unsigned long long* n_samples;
+  unsigned long long* digests;
+  double* centres_out;  // emit mode (single segment): cap×3
+  long long cap;
+  int8_t* tables;       // per-warp ray tables (iterative), table_stride bytes each
+  size_t table_stride;
+  unsigned int* work_counter;
+};
+
+enum { kEvalNone = -1 };
+
+struct LaunchCfg {
+  int grid, block;
+};
+
+// launchers (a3d_kernels.cu)
+void launch_apply_blocks(cudaStream_t st, int n, int nv, const int32_t* slots_dev,
+                         const float* dist_src, const uint8_t* obs_src, const float* w_src,
+                         float* dist_slab, float* weight_slab);
+void launch_point_query(cudaStream_t st, const MapView& m, int what, long long n, const double* pts,
+                        void* out0, void* out1);
+void launch_bv_contains(cudaStream_t st, const EvalView& e, long long n, const double* pts,
+                        uint8_t* out);
+void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView* e,
+                      const Batch& b, bool digest, bool emit, int grid, int block);
+void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& e, long long n,
+                             const double* centres, unsigned long long* counters /*8*/,
+                             uint8_t* keep);
+int cast_gain_block_threads();
+
+enum { kQueryState = 0, kQueryCenter = 1, kQueryObserved = 2, kQueryWeight = 3, kQueryDistance = 4 };
+
+}  // namespace a3d

@@ -1,0 +1,319 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for voxel states, centres, ordered visible-voxel lists, counts and digests; gains within
+1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import CAM_BASE, CAM_CFG4
+
+pytestmark = pytest.mark.gpu
+
+GAIN_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle_py
+    return oracle_py
+
+
+@pytest.fixture(scope="module")
+def capi(built):
+    from mav_active_3d_planning_b200 import capi
+    return capi
+
+
+def make_pair(capi, O, m):
+    ctx = capi.Context(0)
+    ctx.upload_map(m)
+    return ctx, O.OracleMap.from_synth(m)
+
+
+def probe_points(m, n, seed):
+    """Random points + points hugging voxel/block faces and voxel centres (fp edge cases)."""
+    rng = np.random.default_rng(seed)
+    ext = np.array(m.extent)
+    pts = [rng.random((n, 3)) * (ext + 2.0) - 1.0]
+    vs = float(np.float32(m.voxel_size))
+    g = rng.integers(0, (ext / vs).astype(int), (n, 3))
+    pts.append(g * vs)                                    # on voxel faces
+    pts.append(g * vs + rng.normal(0, 2e-7, (n, 3)))      # ulps around faces
+    pts.append((g + 0.5) * vs)                            # voxel centres (double)
+    pts.append((g + 0.5) * vs + rng.normal(0, 2e-7, (n, 3)))
+    bs = vs * m.vps
+    gb = rng.integers(0, (ext / bs).astype(int) + 1, (n, 3))
+    pts.append(gb * bs + rng.normal(0, 1e-6, (n, 3)))     # around block faces
+    pts.append(np.nextafter(np.float32(gb * bs), np.float32(-1e9)).astype(np.float64))
+    return np.concatenate(pts)
+
+
+@pytest.mark.parametrize("vs", [0.2, 0.1])
+def test_map_queries_bit_exact(capi, O, vs):
+    from mav_active_3d_planning_b200 import synth
+    m = synth.room_map(vs)
+    ctx, om = make_pair(capi, O, m)
+    pts = probe_points(m, 20000, 11)
+    assert np.array_equal(ctx.voxel_state(pts), om.voxel_state(pts))
+    assert np.array_equal(ctx.voxel_center(pts), om.voxel_center(pts))
+    assert np.array_equal(ctx.is_observed(pts), om.is_observed(pts))
+    assert np.array_equal(ctx.voxel_weight(pts), om.voxel_weight(pts))
+    d, ok = ctx.distance(pts)
+    od, ook = om.distance(pts)
+    assert np.array_equal(ok, ook) and np.array_equal(d[ok == 1], od[ook == 1])
+    # states at emitted voxel centres (the fold's lookups)
+    c = om.voxel_center(pts)
+    assert np.array_equal(ctx.voxel_state(c), om.voxel_state(c))
+    ctx.close()
+
+
+def test_map_vps8_and_delta_updates(capi, O):
+    from mav_active_3d_planning_b200 import synth
+    m = synth.room_map(0.2, vps=8)
+    ctx, om = make_pair(capi, O, m)
+    assert ctx.num_blocks == om.num_blocks == m.n_blocks
+    pts = probe_points(m, 5000, 3)
+    assert np.array_equal(ctx.voxel_state(pts), om.voxel_state(pts))
+    # overwrite 10 % of blocks, remove 5 %, add new ones
+    rng = np.random.default_rng(5)
+    sel = rng.choice(m.n_blocks, m.n_blocks // 10, replace=False)
+    nd = m.dist[sel] + rng.normal(0, 0.05, m.dist[sel].shape).astype(np.float32)
+    no = np.ones_like(m.observed[sel])
+    ctx.upload_blocks(m.block_idx[sel], nd, no)
+    om.upload_blocks(m.block_idx[sel], nd, no)
+    rem = rng.choice(m.n_blocks, m.n_blocks // 20, replace=False)
+    ctx.remove_blocks(m.block_idx[rem])
+    om.remove_blocks(m.block_idx[rem])
+    new_idx = np.array([[-1, 0, 0], [-1, 1, 0], [40, 40, 40]], np.int32)
+    nd = np.full((3, 512), 0.7, np.float32)
+    ctx.upload_blocks(new_idx, nd, np.ones((3, 512), np.uint8))
+    om.upload_blocks(new_idx, nd, np.ones((3, 512), np.uint8))
+    assert ctx.num_blocks == om.num_blocks
+    pts = np.concatenate([pts, probe_points(m, 2000, 4) - [1.6, 0, 0]])
+    assert np.array_equal(ctx.voxel_state(pts), om.voxel_state(pts))
+    assert np.array_equal(ctx.is_observed(pts), om.is_observed(pts))
+    ctx.clear()
+    assert ctx.num_blocks == 0
+    assert np.all(ctx.voxel_state(pts[:100]) == 2)
+    ctx.close()
+
+
+def test_empty_map_and_empty_batches(capi, O):
+    ctx = capi.Context(0)
+    ctx.map_config(0.2, 16)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    ev = ctx.evaluator("VoxelTypeEvaluator")
+    pos = np.array([[1.0, 2.0, 3.0]])
+    quat = np.array([[1.0, 0, 0, 0]])
+    r = ctx.compute_gains(caster, ev, pos, quat)
+    # nothing allocated: every sample UNKNOWN, nothing occludes → free-space count, gain = count
+    assert r["n_samples"][0] == 19529 and r["gain"][0] == r["n_visible"][0] > 0
+    # a segment without views and a zero-length batch
+    r = ctx.compute_gains(caster, ev, pos, quat, view_segment=np.array([1], np.int32), n_segments=3)
+    assert list(r["n_visible"]) == [0, r["n_visible"][1], 0] and r["gain"][0] == 0
+    r = ctx.compute_gains(caster, ev, np.zeros((0, 3)), np.zeros((0, 4)), n_segments=0)
+    assert len(r["gain"]) == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["IterativeRayCaster", "SimpleRayCaster"])
+def test_cfg1_visible_voxel_lists_bit_exact(capi, O, room02, kind):
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    caster = ctx.caster(kind, **CAM_BASE)
+    oc = om.caster(kind, **CAM_BASE)
+    info = caster.info
+    assert (info.c_res_x, info.c_res_y, info.c_n_sections) == (oc.c_res_x, oc.c_res_y,
+                                                                oc.c_n_sections if kind[0] == "I" else 0)
+    for i, j in [(0, 0), (3, 7), (info.c_res_x - 1, info.c_res_y - 1)]:
+        assert np.array_equal(caster.direction(i, j), oc.direction(i, j))
+    pos, quat = synth.candidate_views(room02, 8, seed=21)
+    for v in range(8):
+        got, ns, _ = ctx.visible_voxels(caster, pos[v:v + 1], quat[v:v + 1])
+        want, ons = oc.visible_voxels(pos[v:v + 1], quat[v:v + 1])
+        assert ns == ons
+        assert got.shape == want.shape and np.array_equal(got, want)
+    ctx.close()
+
+
+def test_cfg1_gains_64_views(capi, O, room02):
+    """BASELINE config 1: 0.2 m room, IterativeRayCaster + VoxelTypeEvaluator, 64 views."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    oc = om.caster("IterativeRayCaster", **CAM_BASE)
+    pos, quat = synth.candidate_views(room02, 64)
+    for kw in (dict(), dict(gain_unknown=1.0, gain_free=0.5, gain_occupied=0.25),
+               dict(gain_unknown=1.0, gain_free=0.5, gain_occupied=0.25, gain_unknown_outer=0.1,
+                    gain_free_outer=0.05, gain_occupied_outer=0.025,
+                    bounding_volume=dict(x_min=4, x_max=16, y_min=4, y_max=16, z_min=0.5, z_max=6,
+                                         rotation=20.0))):
+        got = ctx.compute_gains(caster, ctx.evaluator("VoxelTypeEvaluator", **kw), pos, quat)
+        want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator", **kw), pos, quat)
+        assert np.array_equal(got["n_samples"], want["n_samples"])
+        assert np.array_equal(got["n_visible"], want["n_visible"])
+        assert np.array_equal(got["digest"], want["digest"])
+        assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
+        assert got["gain"].max() > 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("ekind,kw", [
+    ("NaiveEvaluator", {}),
+    ("FrontierEvaluator", {}),
+    ("FrontierEvaluator", dict(accurate_frontiers=True)),
+    ("FrontierEvaluator", dict(surface_frontiers=False, checking_distance=2.0)),
+])
+def test_naive_and_frontier_gains(capi, O, room02, ekind, kw):
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    pos, quat = synth.candidate_views(room02, 16, seed=9)
+    for ckind in ("IterativeRayCaster", "SimpleRayCaster"):
+        caster = ctx.caster(ckind, **CAM_BASE)
+        oc = om.caster(ckind, **CAM_BASE)
+        got = ctx.compute_gains(caster, ctx.evaluator(ekind, **kw), pos, quat)
+        want = oc.compute_gains(O.eval_params(ekind, **kw), pos, quat)
+        assert np.array_equal(got["digest"], want["digest"])
+        assert np.array_equal(got["n_visible"], want["n_visible"])
+        assert np.array_equal(got["gain"], want["gain"])  # integer-valued gains: exact
+    ctx.close()
+
+
+def test_multi_view_segments_and_mounting(capi, O, room02):
+    """sampling_time > 0: several views per segment share one list (std::unique and the gain sum
+    span them, camera_model.cpp:21-58); non-default mounting transform (camera_model.cpp:24-28)."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    cam = dict(CAM_BASE, mounting_translation=(0.1, -0.05, 0.2), mounting_rotation=(0.9, 0.1, -0.2, 0.3))
+    caster = ctx.caster("IterativeRayCaster", **cam)
+    oc = om.caster("IterativeRayCaster", **cam)
+    pos, quat = synth.candidate_views(room02, 20, seed=13)
+    # make consecutive views of a segment nearly identical so cross-view adjacency matters
+    pos[1::2] = pos[0::2]
+    quat[1::2] = quat[0::2]
+    seg = np.repeat(np.arange(4, dtype=np.int32), 5)
+    got = ctx.compute_gains(caster, ctx.evaluator("VoxelTypeEvaluator"), pos, quat, seg, 4)
+    want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos, quat, seg, 4)
+    for k in ("n_samples", "n_visible", "digest"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
+    lst, _, _ = ctx.visible_voxels(caster, pos[:5], quat[:5])
+    olst, _ = oc.visible_voxels(pos[:5], quat[:5])
+    assert np.array_equal(lst, olst)
+    ctx.close()
+
+
+def test_stored_list_and_gain_from_voxels(capi, O, room02):
+    """SimulatedSensorUpdater path: fold a stored list again (simulated_sensor_updater.cpp:18-22)."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    bv = dict(x_min=2, x_max=18, y_min=2, y_max=18, z_min=0.5, z_max=7)
+    pos, quat = synth.candidate_views(room02, 3, seed=17)
+    caster = ctx.caster("SimpleRayCaster", **CAM_BASE)
+    oc = om.caster("SimpleRayCaster", **CAM_BASE)
+    for ekind in ("VoxelTypeEvaluator", "NaiveEvaluator", "FrontierEvaluator"):
+        ev = ctx.evaluator(ekind, bounding_volume=bv, gain_free=0.5)
+        oe = O.eval_params(ekind, bounding_volume=bv, gain_free=0.5)
+        for v in range(3):
+            lst, ns, gain = ctx.visible_voxels(caster, pos[v:v + 1], quat[v:v + 1], evaluator=ev)
+            want = oc.compute_gains(oe, pos[v:v + 1], quat[v:v + 1])
+            assert len(lst) == want["n_visible"][0] and O.digest(lst) == want["digest"][0]
+            assert np.isclose(gain, want["gain"][0], rtol=GAIN_RTOL, atol=0)
+            assert np.all(O.bv_contains(oe, lst) == 1)
+            assert np.array_equal(ctx.bv_contains(ev, lst), O.bv_contains(oe, lst))
+            g2, left, keep = ctx.gain_from_voxels(ev, lst, want_keep=True)
+            og2, oleft = om.gain_from_voxels(oe, lst)
+            assert np.isclose(g2, og2, rtol=GAIN_RTOL, atol=0) and left == oleft
+            assert keep.sum() == left
+    ctx.close()
+
+
+def test_cfg2_subset_digests(capi, O, room01):
+    """BASELINE config 2 (0.1 m room, Iterative + VoxelType): oracle-checked subset of 48 views."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room01)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    oc = om.caster("IterativeRayCaster", **CAM_BASE)
+    pos, quat = synth.candidate_views(room01, 4096)
+    sel = slice(0, 48)
+    got = ctx.compute_gains(caster, ctx.evaluator("VoxelTypeEvaluator"), pos[sel], quat[sel])
+    want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos[sel], quat[sel], n_threads=8)
+    for k in ("n_samples", "n_visible", "digest"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
+    ctx.close()
+
+
+def test_cfg2_full_size_properties(capi, room01):
+    """Full 4096-segment batch: size-independent properties (no oracle at this size):
+    permutation equivariance, batch-split invariance, digest == digest of the materialised list,
+    gain == count of UNKNOWN-state entries of that list, no adjacent duplicates."""
+    from mav_active_3d_planning_b200 import synth
+    ctx = capi.Context(0)
+    ctx.upload_map(room01)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    ev = ctx.evaluator("VoxelTypeEvaluator")
+    pos, quat = synth.candidate_views(room01, 4096)
+    full = ctx.compute_gains(caster, ev, pos, quat)
+    assert full["gain"].sum() > 0 and (full["n_visible"] <= full["n_samples"]).all()
+    perm = np.random.default_rng(1).permutation(4096)
+    p = ctx.compute_gains(caster, ev, pos[perm], quat[perm])
+    for k in full:
+        assert np.array_equal(p[k], full[k][perm]), k
+    half = ctx.compute_gains(caster, ev, pos[1000:1300], quat[1000:1300])
+    for k in full:
+        assert np.array_equal(half[k], full[k][1000:1300]), k
+    from oracle import oracle_py as O
+    for v in (0, 777, 4095):
+        lst, ns, gain = ctx.visible_voxels(caster, pos[v:v + 1], quat[v:v + 1], evaluator=ev)
+        assert len(lst) == full["n_visible"][v] and ns == full["n_samples"][v]
+        assert O.digest(lst) == full["digest"][v]
+        assert gain == full["gain"][v] == float((ctx.voxel_state(lst) == 2).sum())
+        assert not np.any(np.all(lst[1:] == lst[:-1], axis=1))
+    ctx.close()
+
+
+def test_cfg4_simple_and_iterative_640x480(capi, O, room01):
+    """BASELINE config 4: 640×480 f=320, 8 m range, bit-exact ordered voxel sets (ds=1 → 126×103
+    rays) for both casters, plus one literal 640×480-ray view (downsampling_factor 0.19)."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room01)
+    pos, quat = synth.candidate_views(room01, 4, seed=33)
+    for kind in ("SimpleRayCaster", "IterativeRayCaster"):
+        caster = ctx.caster(kind, **CAM_CFG4)
+        oc = om.caster(kind, **CAM_CFG4)
+        assert (caster.info.c_res_x, caster.info.c_res_y) == (126, 103)
+        for v in range(2):
+            got, ns, _ = ctx.visible_voxels(caster, pos[v:v + 1], quat[v:v + 1])
+            want, ons = oc.visible_voxels(pos[v:v + 1], quat[v:v + 1])
+            assert ns == ons and np.array_equal(got, want)
+    kw = dict(CAM_CFG4, downsampling_factor=0.19)
+    caster = ctx.caster("IterativeRayCaster", **kw)
+    oc = om.caster("IterativeRayCaster", **kw)
+    assert (caster.info.c_res_x, caster.info.c_res_y, caster.info.c_n_sections) == (640, 480, 8)
+    got = ctx.compute_gains(caster, ctx.evaluator("VoxelTypeEvaluator"), pos[:1], quat[:1])
+    want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos[:1], quat[:1])
+    for k in ("n_samples", "n_visible", "digest", "gain"):
+        assert np.array_equal(got[k], want[k]), k
+    ctx.close()
+
+
+def test_error_codes(capi):
+    ctx = capi.Context(0)
+    with pytest.raises(capi.A3DError) as e:
+        ctx.caster("SimpleRayCaster")          # map not configured
+    assert e.value.code == -3
+    ctx.map_config(0.1, 16)
+    with pytest.raises(capi.A3DError) as e:
+        ctx.caster("SimpleRayCaster", ray_length=-1.0)   # camera_model.cpp:185-188
+    assert e.value.code == -1 and "ray_length" in str(e.value)
+    caster = ctx.caster("SimpleRayCaster", **CAM_BASE)
+    ev = ctx.evaluator("VoxelTypeEvaluator", clear_from_parents=True)
+    with pytest.raises(capi.A3DError) as e:
+        ctx.compute_gains(caster, ev, np.zeros((1, 3)), np.array([[1.0, 0, 0, 0]]))
+    assert e.value.code == -5
+    ev = ctx.evaluator("VoxelTypeEvaluator")
+    with pytest.raises(capi.A3DError) as e:
+        ctx.compute_gains(caster, ev, np.zeros((2, 3)), np.array([[1.0, 0, 0, 0]] * 2),
+                          view_segment=np.array([1, 0], np.int32), n_segments=2)
+    assert e.value.code == -1
+    ctx.close()
