@@ -135,6 +135,9 @@ double a3d_map_voxel_size(const a3d_ctx* ctx);
    getVoxelState voxblox.cpp:48-60 | getVoxelCenter :66-81 | isObserved :43-45 |
    getVoxelWeight :101-115 | EsdfMap::getDistanceAtPosition as used at :35-36,:50 */
 int a3d_map_voxel_state(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out);
+/* Same result as a3d_map_voxel_state, computed by the literal 8-lookup path that never reads the
+   apron / meta acceleration structures (self-check of the device mirror). */
+int a3d_map_voxel_state_literal(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out);
 int a3d_map_voxel_center(a3d_ctx* ctx, int64_t n, const double* pts, double* out);
 int a3d_map_is_observed(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out);
 int a3d_map_voxel_weight(a3d_ctx* ctx, int64_t n, const double* pts, double* out);

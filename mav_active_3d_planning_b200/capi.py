@@ -32,7 +32,7 @@ EXPORTS = [
     "a3d_ctx_create", "a3d_ctx_destroy", "a3d_last_error", "a3d_ctx_stream", "a3d_last_kernel_ms",
     "a3d_kernel_launches", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev",
     "a3d_map_remove_blocks", "a3d_map_clear", "a3d_map_num_blocks", "a3d_map_voxel_size",
-    "a3d_map_voxel_state", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
+    "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
     "a3d_map_distance", "a3d_caster_create", "a3d_caster_destroy", "a3d_caster_get_info",
     "a3d_caster_direction", "a3d_eval_create", "a3d_eval_destroy", "a3d_compute_gains",
     "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_bv_contains",
@@ -142,7 +142,7 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_map_num_blocks.restype = i64
     lib.a3d_map_voxel_size.argtypes = [vp]
     lib.a3d_map_voxel_size.restype = dbl
-    for name in ("a3d_map_voxel_state", "a3d_map_voxel_center", "a3d_map_is_observed",
+    for name in ("a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed",
                  "a3d_map_voxel_weight"):
         getattr(lib, name).argtypes = [vp, i64, vp, vp]
     lib.a3d_map_distance.argtypes = [vp, i64, vp, vp, vp]
@@ -254,6 +254,12 @@ class Context:
         pts = _pts(pts)
         out = np.empty(len(pts), np.uint8)
         self._ck(self.lib.a3d_map_voxel_state(self.h, len(pts), _ptr(pts), _ptr(out)))
+        return out
+
+    def voxel_state_literal(self, pts):
+        pts = _pts(pts)
+        out = np.empty(len(pts), np.uint8)
+        self._ck(self.lib.a3d_map_voxel_state_literal(self.h, len(pts), _ptr(pts), _ptr(out)))
         return out
 
     def voxel_center(self, pts):

@@ -83,15 +83,18 @@ struct a3d_ctx {
   int32_t next_slot = 0;
   std::vector<HashEntry> h_table;
   DevBuf<HashEntry> d_table;
-  float* d_dist = nullptr;
-  float* d_weight = nullptr;
+  std::vector<Key3> slot_key;  // slot → block index (valid for allocated slots)
+  float* d_dist = nullptr;     // padded cubes, P^3 floats per slot
+  uint8_t* d_meta = nullptr;   // padded cubes, P^3 bytes per slot
+  float* d_weight = nullptr;   // vps^3 floats per slot
   size_t slab_slots = 0;
   bool has_weight = false;
+  int P = 0, P3 = 0;
 
   // staging / scratch
   DevBuf<float> st_dist, st_w;
   DevBuf<uint8_t> st_obs;
-  DevBuf<int32_t> st_slots;
+  DevBuf<int32_t> st_slots, st_aff_slots, st_aff_nbr, st_aff_idx;
   DevBuf<double> sc_pts, sc_out;
   DevBuf<uint8_t> sc_u8;
   DevBuf<double> sc_pos, sc_quat, sc_gains, sc_centres;
@@ -113,7 +116,9 @@ struct a3d_ctx {
     m.table = d_table.p;
     m.dist = d_dist;
     m.weight = has_weight ? d_weight : nullptr;
-    m.meta = nullptr;
+    m.meta = d_meta;
+    m.P = P;
+    m.P3 = P3;
     m.mask = static_cast<uint32_t>(h_table.size() - 1);
     m.vps = vps;
     m.nv = nv;
@@ -180,27 +185,31 @@ int table_upload(a3d_ctx* ctx) {
   return A3D_OK;
 }
 
+template <typename T>
+int slab_grow(a3d_ctx* ctx, T** slab, size_t old_slots, size_t new_slots, size_t per_slot) {
+  T* nd = nullptr;
+  CK(cudaMalloc(&nd, new_slots * per_slot * sizeof(T)));
+  if (*slab) {
+    CK(cudaMemcpyAsync(nd, *slab, old_slots * per_slot * sizeof(T), cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(*slab);
+  }
+  *slab = nd;
+  return A3D_OK;
+}
+
 int slab_reserve(a3d_ctx* ctx, size_t n_slots, bool want_weight) {
-  const size_t nv = static_cast<size_t>(ctx->nv);
+  const size_t nv = static_cast<size_t>(ctx->nv), p3 = static_cast<size_t>(ctx->P3);
   if (n_slots > ctx->slab_slots) {
     const size_t cap = std::max<size_t>(std::max<size_t>(n_slots, ctx->slab_slots * 2), 64);
-    float* nd = nullptr;
-    CK(cudaMalloc(&nd, cap * nv * sizeof(float)));
-    if (ctx->d_dist) {
-      CK(cudaMemcpyAsync(nd, ctx->d_dist, ctx->slab_slots * nv * sizeof(float),
-                         cudaMemcpyDeviceToDevice, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      cudaFree(ctx->d_dist);
-    }
-    ctx->d_dist = nd;
+    int rc = slab_grow(ctx, &ctx->d_dist, ctx->slab_slots, cap, p3);
+    if (rc) return rc;
+    rc = slab_grow(ctx, &ctx->d_meta, ctx->slab_slots, cap, p3);
+    if (rc) return rc;
     if (ctx->d_weight) {
-      float* nw = nullptr;
-      CK(cudaMalloc(&nw, cap * nv * sizeof(float)));
-      CK(cudaMemcpyAsync(nw, ctx->d_weight, ctx->slab_slots * nv * sizeof(float),
-                         cudaMemcpyDeviceToDevice, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      cudaFree(ctx->d_weight);
-      ctx->d_weight = nw;
+      rc = slab_grow(ctx, &ctx->d_weight, ctx->slab_slots, cap, nv);
+      if (rc) return rc;
     }
     ctx->slab_slots = cap;
   }
@@ -210,6 +219,57 @@ int slab_reserve(a3d_ctx* ctx, size_t n_slots, bool want_weight) {
     ctx->has_weight = true;
   }
   return A3D_OK;
+}
+
+// K1b + K1c for every allocated block in `affected` (slots): refresh aprons, rebuild meta bytes.
+int refresh_blocks(a3d_ctx* ctx, const std::vector<int32_t>& affected) {
+  const int n = static_cast<int>(affected.size());
+  if (n == 0) return A3D_OK;
+  std::vector<int32_t> nbr(static_cast<size_t>(n) * 27), idx(static_cast<size_t>(n) * 3);
+  for (int a = 0; a < n; ++a) {
+    const Key3 k = ctx->slot_key[affected[a]];
+    idx[3 * a] = k.x;
+    idx[3 * a + 1] = k.y;
+    idx[3 * a + 2] = k.z;
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          auto it = ctx->slots.find(Key3{k.x + dx, k.y + dy, k.z + dz});
+          nbr[static_cast<size_t>(a) * 27 + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] =
+              it == ctx->slots.end() ? -1 : it->second;
+        }
+  }
+  CK(ctx->st_aff_slots.reserve(n));
+  CK(ctx->st_aff_nbr.reserve(nbr.size()));
+  CK(ctx->st_aff_idx.reserve(idx.size()));
+  CK(cudaMemcpyAsync(ctx->st_aff_slots.p, affected.data(), n * sizeof(int32_t),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->st_aff_nbr.p, nbr.data(), nbr.size() * sizeof(int32_t),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->st_aff_idx.p, idx.data(), idx.size() * sizeof(int32_t),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  const MapView mv = ctx->view();
+  launch_refresh_aprons(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_nbr.p, ctx->d_dist);
+  launch_build_meta(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_meta);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
+  return A3D_OK;
+}
+
+// Slots of the allocated blocks in the 3x3x3 neighbourhood of the given block indices.
+void collect_affected(a3d_ctx* ctx, int n, const int32_t* block_idx, std::vector<int32_t>* out) {
+  std::vector<uint8_t> seen(static_cast<size_t>(ctx->next_slot), 0);
+  for (int i = 0; i < n; ++i)
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          auto it = ctx->slots.find(
+              Key3{block_idx[3 * i] + dx, block_idx[3 * i + 1] + dy, block_idx[3 * i + 2] + dz});
+          if (it == ctx->slots.end() || seen[it->second]) continue;
+          seen[it->second] = 1;
+          out->push_back(it->second);
+        }
 }
 
 // Shared by the host- and device-pointer upload entry points.
@@ -239,6 +299,8 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
       s = ctx->next_slot++;
     }
     ctx->slots.emplace(k, s);
+    if (ctx->slot_key.size() <= static_cast<size_t>(s)) ctx->slot_key.resize(s + 1);
+    ctx->slot_key[s] = k;
     slot_of[i] = s;
     table_dirty = true;
   }
@@ -281,13 +343,16 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
         wsrc = ctx->st_w.p;
       }
     }
-    launch_apply_blocks(ctx->stream, m, ctx->nv, ctx->st_slots.p, dsrc, osrc, wsrc, ctx->d_dist,
+    launch_apply_blocks(ctx->stream, ctx->view(), m, ctx->st_slots.p, dsrc, osrc, wsrc, ctx->d_dist,
                         ctx->has_weight ? ctx->d_weight : nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));  // staging buffers are reused by the next chunk
   }
-  return A3D_OK;
+  // aprons + meta of the uploaded blocks and of their allocated neighbours
+  std::vector<int32_t> affected;
+  collect_affected(ctx, n, block_idx, &affected);
+  return refresh_blocks(ctx, affected);
 }
 
 int point_query(a3d_ctx* ctx, int what, int64_t n, const double* pts, void* out0, size_t out0_elt,
@@ -425,7 +490,11 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->d_dist) cudaFree(ctx->d_dist);
   if (ctx->d_weight) cudaFree(ctx->d_weight);
+  if (ctx->d_meta) cudaFree(ctx->d_meta);
   ctx->d_table.release();
+  ctx->st_aff_slots.release();
+  ctx->st_aff_nbr.release();
+  ctx->st_aff_idx.release();
   ctx->st_dist.release();
   ctx->st_w.release();
   ctx->st_obs.release();
@@ -473,6 +542,8 @@ int a3d_map_config(a3d_ctx* ctx, float voxel_size, int vps) {
   ctx->vs_f = voxel_size;
   ctx->vps = vps;
   ctx->nv = vps * vps * vps;
+  ctx->P = vps + 2;
+  ctx->P3 = ctx->P * ctx->P * ctx->P;
   ctx->vs_inv_f = static_cast<float>(1.0 / static_cast<double>(voxel_size));
   ctx->bs_f = voxel_size * static_cast<float>(vps);
   ctx->bs_inv_f = static_cast<float>(1.0 / static_cast<double>(ctx->bs_f));
@@ -506,6 +577,11 @@ int a3d_map_remove_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx) {
     table_rebuild(ctx, ctx->slots.size());
     int rc = table_upload(ctx);
     if (rc) return rc;
+    // the removed blocks' neighbours must stop mirroring them
+    std::vector<int32_t> affected;
+    collect_affected(ctx, n, block_idx, &affected);
+    rc = refresh_blocks(ctx, affected);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
   }
   return A3D_OK;
@@ -535,6 +611,9 @@ double a3d_map_voxel_size(const a3d_ctx* ctx) {
 
 int a3d_map_voxel_state(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out) {
   return point_query(ctx, kQueryState, n, pts, out, 1, nullptr);
+}
+int a3d_map_voxel_state_literal(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out) {
+  return point_query(ctx, kQueryStateGeneric, n, pts, out, 1, nullptr);
 }
 int a3d_map_voxel_center(a3d_ctx* ctx, int64_t n, const double* pts, double* out) {
   return point_query(ctx, kQueryCenter, n, pts, out, 24, nullptr);

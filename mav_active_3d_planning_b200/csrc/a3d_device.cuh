@@ -13,6 +13,17 @@
 //   a3d::voxel_weight  VoxbloxMap::getVoxelWeight  voxblox.cpp:101-115
 //   a3d::bv_contains   BoundingVolume::contains    active_3d_planning_core/src/data/bounding_volume.cpp:33-57
 //   a3d::rotate        Eigen::Quaterniond * Vector3d as used at camera_model.cpp:27, simple_ray_caster.cpp:45
+//
+// HBM layout of the map mirror (DESIGN.md "data layout"):
+//   table   open-addressing hash, 16 B entries {bx,by,bz,slot}
+//   dist    per slot a PADDED cube of P^3 floats, P = vps+2: voxel (x,y,z), x,y,z in [-1,vps], lives at
+//           ((z+1)*P + (y+1))*P + (x+1).  The interior is the block's ESDF distances; the one-voxel
+//           apron mirrors the 26 neighbouring blocks (kUnobservedBits where the neighbour is not
+//           allocated), so the 8 corners of any interpolation cell are addressed inside ONE block.
+//   meta    per slot P^3 bytes, same indexing: bits 1:0 class of the interpolation cell whose base
+//           (lowest) corner is this voxel, bits 3:2 exact voxel state at this voxel's centre,
+//           bit 4 observed.  Built on the device after every delta (k_build_meta).
+//   weight  per slot vps^3 floats (TSDF weights, nearest-voxel reads only)
 #pragma once
 
 #include <cuda_runtime.h>
@@ -25,6 +36,10 @@ namespace a3d {
 constexpr uint32_t kUnobservedBits = 0x7FD5A3D1u;
 constexpr float kCoordEps = 1e-6f;
 
+// cell classes (meta bits 1:0)
+enum { kCellUnknown = 0, kCellFree = 1, kCellOccupied = 2, kCellMixed = 3 };
+constexpr int kMaxVps = 64;
+
 struct HashEntry {  // 16 B, one LDG.128 per probe
   int32_t x, y, z;
   int32_t slot;  // < 0: empty
@@ -32,12 +47,14 @@ struct HashEntry {  // 16 B, one LDG.128 per probe
 
 struct MapView {
   const HashEntry* __restrict__ table;
-  const float* __restrict__ dist;    // slab: [slot][vps^3], kUnobservedBits where !observed
-  const float* __restrict__ weight;  // TSDF weights slab or nullptr
-  const uint8_t* __restrict__ meta;  // per-voxel meta byte slab (see a3d_kernels.cu, k_build_meta)
+  const float* __restrict__ dist;    // padded slab
+  const uint8_t* __restrict__ meta;  // padded slab
+  const float* __restrict__ weight;  // unpadded TSDF weights slab or nullptr
   uint32_t mask;                     // table capacity - 1
   int32_t vps;
   int32_t nv;                        // vps^3
+  int32_t P;                         // vps + 2
+  int32_t P3;                        // P^3
   float vs_f, vs_inv_f, bs_f, bs_inv_f;
   double c_vs;                       // double(vs_f), VoxbloxMap::c_voxel_size_
 };
@@ -47,6 +64,13 @@ struct D3 {
 };
 struct Q4 {
   double w, x, y, z;
+};
+
+// Per-CTA shared-memory tables of voxblox getCenterPointFromGridIndex(i, voxel_size) for
+// i in [-1, vps]: removes 3 int→float→double→float conversion chains per lookup from the XU pipe.
+struct CenterTables {
+  float f[kMaxVps + 2];
+  double d[kMaxVps + 2];
 };
 
 __device__ __forceinline__ uint32_t hash3(int x, int y, int z) {
@@ -84,6 +108,18 @@ __device__ __forceinline__ float origin_point(int i, float size) {
   return __fmul_rn(__int2float_rn(i), size);
 }
 
+__device__ __forceinline__ void init_center_tables(const MapView& m, CenterTables* t) {
+  for (int i = threadIdx.x; i < m.vps + 2; i += blockDim.x) {
+    const float c = center_point(i - 1, m.vs_f);
+    t->f[i] = c;
+    t->d[i] = static_cast<double>(c);
+  }
+}
+
+__device__ __forceinline__ size_t padded_index(const MapView& m, int slot, int x, int y, int z) {
+  return static_cast<size_t>(slot) * m.P3 + ((z + 1) * m.P + (y + 1)) * m.P + (x + 1);
+}
+
 // Eigen cross / quaternion-vector product, exact op order (see oracle/a3d_oracle.cpp rotate()).
 __device__ __forceinline__ D3 cross(const D3& a, const D3& b) {
   D3 r;
@@ -118,74 +154,9 @@ __device__ __forceinline__ Q4 qmul(const Q4& a, const Q4& b) {
   return r;
 }
 
-// ---- interpolated ESDF distance (generic path) -------------------------------------------------
-// Returns true and *dist when all 8 surrounding voxels exist and are observed.
-__device__ inline bool interp_distance(const MapView& m, float px, float py, float pz,
-                                             float* dist_out) {
-  const float p[3] = {px, py, pz};
-  int b[3], v[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) b[k] = grid_index(p[k], m.bs_inv_f);
-  int slot = find_slot(m, b[0], b[1], b[2]);
-  if (slot < 0) return false;
-  bool moved = false;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float origin = origin_point(b[k], m.bs_f);
-    v[k] = grid_index(__fsub_rn(p[k], origin), m.vs_inv_f);
-    const float centre = __fadd_rn(origin, center_point(v[k], m.vs_f));
-    if (__fsub_rn(p[k], centre) < 0.0f) {
-      v[k]--;
-      if (v[k] < 0) {
-        b[k]--;
-        v[k] += m.vps;
-        moved = true;
-      }
-    }
-  }
-  if (moved) {
-    slot = find_slot(m, b[0], b[1], b[2]);
-    if (slot < 0) return false;
-  }
-  // carry pattern of the +1 corners
-  const int cx = (v[0] + 1 >= m.vps), cy = (v[1] + 1 >= m.vps), cz = (v[2] + 1 >= m.vps);
-  const int c0x = (v[0] >= m.vps), c0y = (v[1] >= m.vps), c0z = (v[2] >= m.vps);  // fp artefact
-  float d[8];
-  float o[3];
-  int cached_key = -1, cached_slot = -1;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int ox = (i >> 2) & 1, oy = (i >> 1) & 1, oz = i & 1;
-    int vi[3] = {v[0] + ox, v[1] + oy, v[2] + oz};
-    const int kx = ox ? cx : c0x, ky = oy ? cy : c0y, kz = oz ? cz : c0z;
-    int s = slot;
-    if (kx | ky | kz) {
-      const int key = kx | (ky << 1) | (kz << 2);
-      if (key != cached_key) {
-        cached_slot = find_slot(m, b[0] + kx, b[1] + ky, b[2] + kz);
-        cached_key = key;
-      }
-      s = cached_slot;
-      if (s < 0) return false;
-      vi[0] -= kx ? m.vps : 0;
-      vi[1] -= ky ? m.vps : 0;
-      vi[2] -= kz ? m.vps : 0;
-    }
-    if (i == 0) {
-      const int nb[3] = {b[0] + kx, b[1] + ky, b[2] + kz};
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float voxel_pos = __fadd_rn(origin_point(nb[k], m.bs_f), center_point(vi[k], m.vs_f));
-        o[k] = __fmul_rn(__fsub_rn(p[k], voxel_pos), m.vs_inv_f);
-      }
-    }
-    const int lin = vi[0] + m.vps * (vi[1] + m.vps * vi[2]);
-    if (lin < 0 || lin >= m.nv) return false;
-    const float dv = __ldg(m.dist + static_cast<size_t>(s) * m.nv + lin);
-    if (__float_as_uint(dv) == kUnobservedBits) return false;
-    d[i] = dv;
-  }
-  // q * (T * d) with the summation order fixed in SURVEY.md A.3 / oracle
+// voxblox Interpolator::interpMember: q * (T * d) with the summation order fixed in SURVEY.md A.3
+// (zero-coefficient terms dropped).  d[i]: corner (i>>2&1, i>>1&1, i&1); o: voxel offsets.
+__device__ __forceinline__ float interp8(const float (&d)[8], const float (&o)[3]) {
   const float q4 = __fmul_rn(o[0], o[1]);
   const float q5 = __fmul_rn(o[1], o[2]);
   const float q6 = __fmul_rn(o[2], o[0]);
@@ -207,62 +178,204 @@ __device__ inline bool interp_distance(const MapView& m, float px, float py, flo
   const float u5 = __fmul_rn(q5, w5);
   const float u6 = __fmul_rn(q6, w6);
   const float u7 = __fmul_rn(q7, w7);
-  *dist_out = __fadd_rn(__fadd_rn(__fadd_rn(u0, u4), __fadd_rn(u2, u6)),
-                        __fadd_rn(__fadd_rn(u1, u5), __fadd_rn(u3, u7)));
+  return __fadd_rn(__fadd_rn(__fadd_rn(u0, u4), __fadd_rn(u2, u6)),
+                   __fadd_rn(__fadd_rn(u1, u5), __fadd_rn(u3, u7)));
+}
+
+// ---- interpolated ESDF distance, literal generic path --------------------------------------------
+// One hash lookup per distinct corner block, interiors only (never reads aprons or meta): this is
+// the definition the apron/meta fast path must agree with, the builder of the meta bytes, and the
+// fallback for the floating-point artefact cases (voxel index outside [0,vps) before the shift).
+static __device__ __noinline__ bool interp_distance_generic(const MapView& m, float px, float py, float pz,
+                                                     float* dist_out) {
+  const float p[3] = {px, py, pz};
+  int b[3], v[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) b[k] = grid_index(p[k], m.bs_inv_f);
+  if (find_slot(m, b[0], b[1], b[2]) < 0) return false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float origin = origin_point(b[k], m.bs_f);
+    v[k] = grid_index(__fsub_rn(p[k], origin), m.vs_inv_f);
+    const float centre = __fadd_rn(origin, center_point(v[k], m.vs_f));
+    if (__fsub_rn(p[k], centre) < 0.0f) {
+      v[k]--;
+      if (v[k] < 0) {
+        b[k]--;
+        v[k] += m.vps;
+      }
+    }
+  }
+  float d[8];
+  float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    int vi[3] = {v[0] + ((i >> 2) & 1), v[1] + ((i >> 1) & 1), v[2] + (i & 1)};
+    int nb[3] = {b[0], b[1], b[2]};
+    if (find_slot(m, nb[0], nb[1], nb[2]) < 0) return false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (vi[k] >= m.vps) {
+        nb[k]++;
+        vi[k] -= m.vps;
+      }
+    }
+    const int s = find_slot(m, nb[0], nb[1], nb[2]);
+    if (s < 0) return false;
+    if (i == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float voxel_pos = __fadd_rn(origin_point(nb[k], m.bs_f), center_point(vi[k], m.vs_f));
+        o[k] = __fmul_rn(__fsub_rn(p[k], voxel_pos), m.vs_inv_f);
+      }
+    }
+    // voxblox computeLinearIndexFromVoxelIndex; out-of-range is UB upstream, defined as "no voxel"
+    const int lin = vi[0] + m.vps * (vi[1] + m.vps * vi[2]);
+    if (lin < 0 || lin >= m.nv) return false;
+    const int z = lin / (m.vps * m.vps), rem = lin - z * m.vps * m.vps;
+    const int y = rem / m.vps, x = rem - y * m.vps;
+    const float dv = __ldg(m.dist + padded_index(m, s, x, y, z));
+    if (__float_as_uint(dv) == kUnobservedBits) return false;
+    d[i] = dv;
+  }
+  *dist_out = interp8(d, o);
   return true;
 }
 
-__device__ __forceinline__ int voxel_state_f(const MapView& m, float px, float py, float pz) {
-  float dist;
-  if (!interp_distance(m, px, py, pz, &dist)) return 2;         // UNKNOWN
-  return (static_cast<double>(dist) < m.c_vs) ? 0 : 1;          // OCCUPIED : FREE
-}
-__device__ __forceinline__ int voxel_state(const MapView& m, const D3& p) {
-  return voxel_state_f(m, __double2float_rn(p.x), __double2float_rn(p.y), __double2float_rn(p.z));
+__device__ __forceinline__ int state_from_distance(const MapView& m, bool ok, float dist) {
+  if (!ok) return 2;                                    // UNKNOWN
+  return (static_cast<double>(dist) < m.c_vs) ? 0 : 1;  // OCCUPIED : FREE
 }
 
-// getVoxelCenter; also returns the block index and (unclamped) voxel index it derived.
-__device__ __forceinline__ D3 voxel_center(const MapView& m, const D3& p, int* b_out, int* v_out) {
+static __device__ __noinline__ int voxel_state_generic(const MapView& m, float px, float py, float pz) {
+  float dist = 0.f;
+  const bool ok = interp_distance_generic(m, px, py, pz, &dist);
+  return state_from_distance(m, ok, dist);
+}
+
+// ---- fast path ----------------------------------------------------------------------------------
+// State of the float point p whose block index b, block origin and slot (= find_slot(b), may be
+// < 0) the caller already has.  Uses the cell class when it is definite, else the 8 padded-cube
+// corners; falls back to the generic path for artefact indices.
+__device__ __forceinline__ int voxel_state_in_block(const MapView& m, const CenterTables& ct,
+                                                    const float (&p)[3], const int (&b)[3],
+                                                    const float (&origin)[3], int slot) {
+  if (slot < 0) return 2;
+  int v[3];
+  bool artefact = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    v[k] = grid_index(__fsub_rn(p[k], origin[k]), m.vs_inv_f);
+    artefact |= (v[k] < 0) | (v[k] >= m.vps);
+  }
+  if (artefact) return voxel_state_generic(m, p[0], p[1], p[2]);
+  int base[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float centre = __fadd_rn(origin[k], ct.f[v[k] + 1]);
+    base[k] = v[k] - ((__fsub_rn(p[k], centre) < 0.0f) ? 1 : 0);
+  }
+  const size_t at = padded_index(m, slot, base[0], base[1], base[2]);
+  const int cls = __ldg(m.meta + at) & 3;
+  if (cls != kCellMixed) return cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
+  float d[8], o[3];
+  const float* __restrict__ dp = m.dist + at;
+  const int P = m.P, PP = m.P * m.P;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    d[i] = __ldg(dp + ((i >> 2) & 1) + ((i >> 1) & 1) * P + (i & 1) * PP);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    // corner 0 position as the reference forms it: in the shifted block's own frame
+    const float voxel_pos = base[k] < 0
+                                ? __fadd_rn(origin_point(b[k] - 1, m.bs_f), ct.f[m.vps])
+                                : __fadd_rn(origin[k], ct.f[base[k] + 1]);
+    o[k] = __fmul_rn(__fsub_rn(p[k], voxel_pos), m.vs_inv_f);
+  }
+  return state_from_distance(m, true, interp8(d, o));
+}
+
+__device__ __forceinline__ int voxel_state(const MapView& m, const CenterTables& ct, const D3& pd) {
+  const float p[3] = {__double2float_rn(pd.x), __double2float_rn(pd.y), __double2float_rn(pd.z)};
+  int b[3];
+  float origin[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    b[k] = grid_index(p[k], m.bs_inv_f);
+    origin[k] = origin_point(b[k], m.bs_f);
+  }
+  return voxel_state_in_block(m, ct, p, b, origin, find_slot(m, b[0], b[1], b[2]));
+}
+
+// getVoxelCenter given the block index / origin of the point; v_out: unclamped voxel index.
+__device__ __forceinline__ D3 voxel_center_in_block(const MapView& m, const CenterTables& ct,
+                                                    const D3& p, const float (&origin)[3],
+                                                    int (&v_out)[3]) {
   const double pp[3] = {p.x, p.y, p.z};
   double c[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const int b = grid_index(__double2float_rn(pp[k]), m.bs_inv_f);
-    const double origin = static_cast<double>(origin_point(b, m.bs_f));
-    const int v = grid_index(__double2float_rn(__dsub_rn(pp[k], origin)), m.vs_inv_f);
-    c[k] = __dadd_rn(origin, static_cast<double>(center_point(v, m.vs_f)));
-    b_out[k] = b;
+    const double od = static_cast<double>(origin[k]);
+    const int v = grid_index(__double2float_rn(__dsub_rn(pp[k], od)), m.vs_inv_f);
+    const double cp = (v >= -1 && v <= m.vps) ? ct.d[v + 1]
+                                              : static_cast<double>(center_point(v, m.vs_f));
+    c[k] = __dadd_rn(od, cp);
     v_out[k] = v;
   }
   return D3{c[0], c[1], c[2]};
 }
 
-// Nearest-voxel linear address (block by coordinates, truncated voxel index); -1 if no block.
-__device__ __forceinline__ int64_t nearest_voxel(const MapView& m, const D3& p) {
+__device__ __forceinline__ D3 voxel_center(const MapView& m, const CenterTables& ct, const D3& p) {
+  float origin[3];
+  origin[0] = origin_point(grid_index(__double2float_rn(p.x), m.bs_inv_f), m.bs_f);
+  origin[1] = origin_point(grid_index(__double2float_rn(p.y), m.bs_inv_f), m.bs_f);
+  origin[2] = origin_point(grid_index(__double2float_rn(p.z), m.bs_inv_f), m.bs_f);
+  int v[3];
+  return voxel_center_in_block(m, ct, p, origin, v);
+}
+
+// Nearest-voxel address parts (block by coordinates, truncated voxel index); slot -1 if no block.
+__device__ __forceinline__ int nearest_voxel(const MapView& m, const D3& p, int (&v)[3]) {
   const float pf[3] = {__double2float_rn(p.x), __double2float_rn(p.y), __double2float_rn(p.z)};
   int b[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) b[k] = grid_index(pf[k], m.bs_inv_f);
   const int slot = find_slot(m, b[0], b[1], b[2]);
-  if (slot < 0) return -1;
-  int v[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     v[k] = grid_index(__fsub_rn(pf[k], origin_point(b[k], m.bs_f)), m.vs_inv_f);
     v[k] = max(min(v[k], m.vps - 1), 0);
   }
-  return static_cast<int64_t>(slot) * m.nv + (v[0] + m.vps * (v[1] + m.vps * v[2]));
+  return slot;
 }
 __device__ __forceinline__ bool is_observed(const MapView& m, const D3& p) {
-  const int64_t a = nearest_voxel(m, p);
-  if (a < 0) return false;
-  return __float_as_uint(__ldg(m.dist + a)) != kUnobservedBits;
+  int v[3];
+  const int slot = nearest_voxel(m, p, v);
+  if (slot < 0) return false;
+  return (__ldg(m.meta + padded_index(m, slot, v[0], v[1], v[2])) >> 4) & 1;
 }
 __device__ __forceinline__ double voxel_weight(const MapView& m, const D3& p) {
   if (!m.weight) return 0.0;
-  const int64_t a = nearest_voxel(m, p);
-  if (a < 0) return 0.0;
-  return static_cast<double>(__ldg(m.weight + a));
+  int v[3];
+  const int slot = nearest_voxel(m, p, v);
+  if (slot < 0) return 0.0;
+  return static_cast<double>(
+      __ldg(m.weight + static_cast<size_t>(slot) * m.nv + v[0] + m.vps * (v[1] + m.vps * v[2])));
+}
+
+// State / observed flag at an emitted voxel CENTRE c = voxel_center(...) with block index b and
+// unclamped voxel index v, slot = find_slot(b): one meta byte (DESIGN.md "centre state").
+// Returns state | observed << 2.
+__device__ __forceinline__ int centre_state(const MapView& m, const CenterTables& ct, const D3& c,
+                                            int slot, const int (&v)[3]) {
+  const bool in_range = (v[0] >= 0) & (v[0] < m.vps) & (v[1] >= 0) & (v[1] < m.vps) & (v[2] >= 0) &
+                        (v[2] < m.vps);
+  if (!in_range) {  // fp artefact: voxel index -1 / vps — evaluate literally
+    return voxel_state(m, ct, c) | (is_observed(m, c) ? 4 : 0);
+  }
+  if (slot < 0) return 2;
+  const int meta = __ldg(m.meta + padded_index(m, slot, v[0], v[1], v[2]));
+  return ((meta >> 2) & 3) | ((meta >> 2) & 4);
 }
 
 struct EvalView {
@@ -287,8 +400,7 @@ __device__ __forceinline__ bool bv_contains(const EvalView& e, const D3& p) {
   return true;
 }
 
-// FrontierEvaluator neighbour order (frontier_evaluator.cpp:33-65), packed 2 bits per axis
-// (0: 0, 1: +, 2: -), x | y<<2 | z<<4.
+// FrontierEvaluator neighbour order (frontier_evaluator.cpp:33-65).
 __device__ __forceinline__ void frontier_offset(bool accurate, int i, int* sx, int* sy, int* sz) {
   // 6-neighbourhood: +x,-x,+y,-y,+z,-z
   if (!accurate) {
@@ -311,13 +423,14 @@ __device__ __forceinline__ void frontier_offset(bool accurate, int i, int* sx, i
     g = 2;
     r = i - 17;
   }
-  const int ys[3] = {0, 1, -1};
+  const int r3 = r / 3, rm = r - 3 * r3;
   *sx = g == 0 ? 1 : (g == 1 ? 0 : -1);
-  *sy = ys[r % 3];
-  *sz = ys[r / 3];
+  *sy = rm == 0 ? 0 : (rm == 1 ? 1 : -1);
+  *sz = r3 == 0 ? 0 : (r3 == 1 ? 1 : -1);
 }
 
-__device__ __forceinline__ bool is_frontier_voxel(const MapView& m, const EvalView& e, const D3& c) {
+__device__ __forceinline__ bool is_frontier_voxel(const MapView& m, const CenterTables& ct,
+                                                  const EvalView& e, const D3& c) {
   const int n = e.accurate_frontiers ? 26 : 6;
 #pragma unroll 1
   for (int i = 0; i < n; ++i) {
@@ -328,7 +441,7 @@ __device__ __forceinline__ bool is_frontier_voxel(const MapView& m, const EvalVi
     q.x = __dadd_rn(c.x, sx > 0 ? e.nb_step : (sx < 0 ? -e.nb_step : 0.0));
     q.y = __dadd_rn(c.y, sy > 0 ? e.nb_step : (sy < 0 ? -e.nb_step : 0.0));
     q.z = __dadd_rn(c.z, sz > 0 ? e.nb_step : (sz < 0 ? -e.nb_step : 0.0));
-    const int s = voxel_state(m, q);
+    const int s = voxel_state(m, ct, q);
     if (s == 2) continue;
     if (e.surface_frontiers) return s == 0;
     return true;

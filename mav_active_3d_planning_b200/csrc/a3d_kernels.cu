@@ -1,6 +1,9 @@
 // a3d_kernels.cu — sm_100a kernels of the view-gain path.
 //
-//   k_apply_blocks       K1: merge an uploaded block delta (distance + observed flag) into the slab
+//   k_apply_blocks       K1a: merge an uploaded block delta (distance + observed flag) into the
+//                        padded slab interiors
+//   k_refresh_aprons     K1b: re-mirror the one-voxel aprons of every block touched by the delta
+//   k_build_meta         K1c: per-voxel meta byte (cell class, exact centre state, observed)
 //   k_point_query        batched OccupancyMap/TSDFMap virtuals (voxblox.cpp:43-115)
 //   k_cast_gain          K2/K3 + fold: SimpleRayCaster / IterativeRayCaster march
 //                        (simple_ray_caster.cpp:32-66, iterative_ray_caster.cpp:48-119), adjacent
@@ -18,59 +21,169 @@
 // neighbouring lane (shuffle) or from a warp-uniform carry across chunks, rays and views.
 #include "a3d_kernels.cuh"
 
+#include <algorithm>
+
 #include "../../include/a3d.h"
 
 namespace a3d {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+static inline int grid_for(long long total, int block, int per_sm = 16) {
+  return static_cast<int>(std::max<long long>(
+      1, std::min<long long>((total + block - 1) / block, 148LL * per_sm)));
+}
+
 // ---------------------------------------------------------------------------------------------
-__global__ void k_apply_blocks(int n, int nv, const int32_t* __restrict__ slots,
+__global__ void k_apply_blocks(MapView m, int n, const int32_t* __restrict__ slots,
                                const float* __restrict__ dist_src, const uint8_t* __restrict__ obs_src,
                                const float* __restrict__ w_src, float* __restrict__ dist_slab,
                                float* __restrict__ weight_slab) {
-  const long long total = static_cast<long long>(n) * nv;
+  const long long total = static_cast<long long>(n) * m.nv;
+  const int vv = m.vps * m.vps;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int blk = static_cast<int>(i / nv);
-    const int lin = static_cast<int>(i - static_cast<long long>(blk) * nv);
-    const size_t dst = static_cast<size_t>(slots[blk]) * nv + lin;
-    float d = dist_src[i];
+    const int blk = static_cast<int>(i / m.nv);
+    const int lin = static_cast<int>(i - static_cast<long long>(blk) * m.nv);
+    const int z = lin / vv, rem = lin - z * vv, y = rem / m.vps, x = rem - y * m.vps;
+    const int slot = slots[blk];
+    const float d = dist_src[i];
     uint32_t bits = __float_as_uint(d);
     if (!obs_src[i]) {
       bits = kUnobservedBits;
     } else if (d != d) {
       bits = 0x7FC00000u;  // canonical NaN for observed voxels
     }
-    dist_slab[dst] = __uint_as_float(bits);
-    if (weight_slab) weight_slab[dst] = w_src ? w_src[i] : 0.0f;
+    dist_slab[padded_index(m, slot, x, y, z)] = __uint_as_float(bits);
+    if (weight_slab) weight_slab[static_cast<size_t>(slot) * m.nv + lin] = w_src ? w_src[i] : 0.0f;
   }
 }
 
-void launch_apply_blocks(cudaStream_t st, int n, int nv, const int32_t* slots_dev,
+void launch_apply_blocks(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                          const float* dist_src, const uint8_t* obs_src, const float* w_src,
                          float* dist_slab, float* weight_slab) {
   if (n <= 0) return;
-  const long long total = static_cast<long long>(n) * nv;
-  const int block = 256;
-  const int grid = static_cast<int>(std::min<long long>((total + block - 1) / block, 148LL * 16));
-  k_apply_blocks<<<grid, block, 0, st>>>(n, nv, slots_dev, dist_src, obs_src, w_src, dist_slab,
-                                         weight_slab);
+  const long long total = static_cast<long long>(n) * m.nv;
+  k_apply_blocks<<<grid_for(total, 256), 256, 0, st>>>(m, n, slots_dev, dist_src, obs_src, w_src,
+                                                       dist_slab, weight_slab);
+}
+
+// For every affected block (slot, 27 neighbour slots in (dz,dy,dx) order, -1 = not allocated) copy
+// the facing layer of each neighbour's interior into the apron; kUnobservedBits if it is missing.
+__global__ void k_refresh_aprons(MapView m, int n, const int32_t* __restrict__ slots,
+                                 const int32_t* __restrict__ nbr, float* __restrict__ dist_slab) {
+  const int P = m.P;
+  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+    const int slot = slots[a];
+    const int32_t* nb = nbr + static_cast<size_t>(a) * 27;
+    for (int i = threadIdx.x; i < m.P3; i += blockDim.x) {
+      const int z = i / (P * P) - 1, rem = i % (P * P), y = rem / P - 1, x = rem % P - 1;
+      const int dx = x < 0 ? -1 : (x >= m.vps ? 1 : 0);
+      const int dy = y < 0 ? -1 : (y >= m.vps ? 1 : 0);
+      const int dz = z < 0 ? -1 : (z >= m.vps ? 1 : 0);
+      if ((dx | dy | dz) == 0) continue;  // interior
+      const int src = nb[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+      float val = __uint_as_float(kUnobservedBits);
+      if (src >= 0)
+        val = dist_slab[padded_index(m, src, x - dx * m.vps, y - dy * m.vps, z - dz * m.vps)];
+      dist_slab[static_cast<size_t>(slot) * m.P3 + i] = val;
+    }
+  }
+}
+
+void launch_refresh_aprons(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
+                           const int32_t* nbr_dev, float* dist_slab) {
+  if (n <= 0) return;
+  k_refresh_aprons<<<std::min(n, 148 * 8), 256, 0, st>>>(m, n, slots_dev, nbr_dev, dist_slab);
+}
+
+// Meta byte per padded voxel of every affected block.
+//   bits 1:0  class of the cell with base corner here: UNKNOWN if any of the 8 corners is
+//             unobserved/missing; FREE / OCCUPIED only when every corner is on the same side of the
+//             voxel size by more than the worst-case rounding error of interp8 (DESIGN.md "cell
+//             class margin"), so the class equals the interpolated test for every point of the cell;
+//             MIXED otherwise (the kernel interpolates).
+//   bits 3:2  exact state at the voxel centre, evaluated with the literal generic path
+//   bit 4     observed
+__global__ void k_build_meta(MapView m, int n, const int32_t* __restrict__ slots,
+                             const int32_t* __restrict__ block_idx, uint8_t* __restrict__ meta_slab) {
+  const int P = m.P, PP = m.P * m.P;
+  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+    const int slot = slots[a];
+    const float* __restrict__ dp = m.dist + static_cast<size_t>(slot) * m.P3;
+    for (int i = threadIdx.x; i < m.P3; i += blockDim.x) {
+      const int z = i / PP - 1, rem = i % PP, y = rem / P - 1, x = rem % P - 1;
+      int cls = kCellUnknown;
+      if (x < m.vps && y < m.vps && z < m.vps) {
+        bool all_obs = true, any_nan = false;
+        float mn = 3.0e38f, mx = -3.0e38f, amax = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float d = dp[i + ((c >> 2) & 1) + ((c >> 1) & 1) * P + (c & 1) * PP];
+          all_obs &= (__float_as_uint(d) != kUnobservedBits);
+          any_nan |= (d != d);
+          mn = fminf(mn, d);
+          mx = fmaxf(mx, d);
+          amax = fmaxf(amax, fabsf(d));
+        }
+        if (all_obs) {
+          const double margin = 1.0e-4 * fmax(static_cast<double>(amax), m.c_vs);
+          if (any_nan || !(amax < 1.0e30f)) {
+            cls = kCellMixed;
+          } else if (static_cast<double>(mn) - margin >= m.c_vs) {
+            cls = kCellFree;
+          } else if (static_cast<double>(mx) + margin < m.c_vs) {
+            cls = kCellOccupied;
+          } else {
+            cls = kCellMixed;
+          }
+        }
+      }
+      int centre = 2, obs = 0;
+      if (x >= 0 && x < m.vps && y >= 0 && y < m.vps && z >= 0 && z < m.vps) {
+        obs = __float_as_uint(dp[i]) != kUnobservedBits;
+        // centre exactly as getVoxelCenter forms it (voxblox.cpp:72-79), cast like getVoxelState
+        const int32_t* bi = block_idx + 3 * a;
+        const double cx = __dadd_rn(static_cast<double>(origin_point(bi[0], m.bs_f)),
+                                    static_cast<double>(center_point(x, m.vs_f)));
+        const double cy = __dadd_rn(static_cast<double>(origin_point(bi[1], m.bs_f)),
+                                    static_cast<double>(center_point(y, m.vs_f)));
+        const double cz = __dadd_rn(static_cast<double>(origin_point(bi[2], m.bs_f)),
+                                    static_cast<double>(center_point(z, m.vs_f)));
+        centre = voxel_state_generic(m, __double2float_rn(cx), __double2float_rn(cy),
+                                     __double2float_rn(cz));
+      }
+      meta_slab[static_cast<size_t>(slot) * m.P3 + i] =
+          static_cast<uint8_t>(cls | (centre << 2) | (obs << 4));
+    }
+  }
+}
+
+void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
+                       const int32_t* block_idx_dev, uint8_t* meta_slab) {
+  if (n <= 0) return;
+  k_build_meta<<<std::min(n, 148 * 8), 256, 0, st>>>(m, n, slots_dev, block_idx_dev, meta_slab);
 }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void k_point_query(MapView m, int what, long long n, const double* __restrict__ pts,
                               void* out0, void* out1) {
+  __shared__ CenterTables ct;
+  init_center_tables(m, &ct);
+  __syncthreads();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const D3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
     switch (what) {
       case kQueryState:
-        static_cast<uint8_t*>(out0)[i] = static_cast<uint8_t>(voxel_state(m, p));
+        static_cast<uint8_t*>(out0)[i] = static_cast<uint8_t>(voxel_state(m, ct, p));
+        break;
+      case kQueryStateGeneric:
+        static_cast<uint8_t*>(out0)[i] = static_cast<uint8_t>(voxel_state_generic(
+            m, __double2float_rn(p.x), __double2float_rn(p.y), __double2float_rn(p.z)));
         break;
       case kQueryCenter: {
-        int b[3], v[3];
-        const D3 c = voxel_center(m, p, b, v);
+        const D3 c = voxel_center(m, ct, p);
         double* o = static_cast<double*>(out0);
         o[3 * i] = c.x;
         o[3 * i + 1] = c.y;
@@ -85,8 +198,8 @@ __global__ void k_point_query(MapView m, int what, long long n, const double* __
         break;
       case kQueryDistance: {
         float d = 0.0f;
-        const bool ok = interp_distance(m, __double2float_rn(p.x), __double2float_rn(p.y),
-                                        __double2float_rn(p.z), &d);
+        const bool ok = interp_distance_generic(m, __double2float_rn(p.x), __double2float_rn(p.y),
+                                                __double2float_rn(p.z), &d);
         static_cast<double*>(out0)[i] = ok ? static_cast<double>(d) : 0.0;
         static_cast<uint8_t*>(out1)[i] = ok ? 1 : 0;
         break;
@@ -98,9 +211,7 @@ __global__ void k_point_query(MapView m, int what, long long n, const double* __
 void launch_point_query(cudaStream_t st, const MapView& m, int what, long long n, const double* pts,
                         void* out0, void* out1) {
   if (n <= 0) return;
-  const int block = 128;
-  const int grid = static_cast<int>(std::min<long long>((n + block - 1) / block, 148LL * 16));
-  k_point_query<<<grid, block, 0, st>>>(m, what, n, pts, out0, out1);
+  k_point_query<<<grid_for(n, 128), 128, 0, st>>>(m, what, n, pts, out0, out1);
 }
 
 __global__ void k_bv_contains(EvalView e, long long n, const double* __restrict__ pts,
@@ -112,30 +223,10 @@ __global__ void k_bv_contains(EvalView e, long long n, const double* __restrict_
 void launch_bv_contains(cudaStream_t st, const EvalView& e, long long n, const double* pts,
                         uint8_t* out) {
   if (n <= 0) return;
-  const int block = 128;
-  const int grid = static_cast<int>(std::min<long long>((n + block - 1) / block, 148LL * 16));
-  k_bv_contains<<<grid, block, 0, st>>>(e, n, pts, out);
+  k_bv_contains<<<grid_for(n, 128), 128, 0, st>>>(e, n, pts, out);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Evaluator fold of one retained entry.  cnt: VoxelType → [state + 3*outside]; Naive/Frontier → [0].
-template <int EVAL>
-__device__ __forceinline__ void fold_entry(const MapView& m, const EvalView& e, const D3& c,
-                                           unsigned (&cnt)[6]) {
-  if (EVAL == A3D_EVAL_VOXEL_TYPE) {
-    const int s = voxel_state(m, c);
-    const int outside = bv_contains(e, c) ? 0 : 3;
-    cnt[s + outside]++;
-  } else if (EVAL == A3D_EVAL_NAIVE) {
-    if (!is_observed(m, c)) cnt[0]++;
-  } else if (EVAL == A3D_EVAL_FRONTIER) {
-    if (!is_observed(m, c)) {
-      cnt[1]++;
-      if (is_frontier_voxel(m, e, c)) cnt[0]++;
-    }
-  }
-}
-
 // VoxelTypeEvaluator's switch without breaks (voxel_type_evaluator.cpp:69-85): UNKNOWN adds
 // unknown+free+occupied, FREE adds free+occupied, OCCUPIED adds occupied.
 __device__ __forceinline__ double voxel_type_gain(const EvalView& e, const unsigned long long* n) {
@@ -163,17 +254,17 @@ __global__ void __launch_bounds__(kCastBlock)
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   int8_t* const table = ITER ? b.tables + gwarp * b.table_stride : nullptr;
 
+  __shared__ CenterTables ct;
   __shared__ unsigned long long pw[33];  // kDigestMul^i
-  if (DIGEST) {
-    if (threadIdx.x == 0) {
-      unsigned long long p = 1;
-      for (int i = 0; i < 33; ++i) {
-        pw[i] = p;
-        p *= kDigestMul;
-      }
+  init_center_tables(m, &ct);
+  if (DIGEST && threadIdx.x == 0) {
+    unsigned long long p = 1;
+    for (int i = 0; i < 33; ++i) {
+      pw[i] = p;
+      p *= kDigestMul;
     }
-    __syncthreads();
   }
+  __syncthreads();
   const double kNaN = __longlong_as_double(0x7FF8000000000000ll);
 
   for (;;) {
@@ -184,6 +275,7 @@ __global__ void __launch_bounds__(kCastBlock)
     const int v_begin = b.view_first[seg], v_end = b.view_first[seg + 1];
 
     D3 carry{kNaN, kNaN, kNaN};  // previous raw list entry (NaN: none yet)
+    // per-lane counters: VoxelType → [state + 3*outside]; Naive/Frontier → [0]
     unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long n_vis = 0, n_samp = 0, digest = 0;
 
@@ -204,109 +296,159 @@ __global__ void __launch_bounds__(kCastBlock)
         __syncwarp();
       }
 
-      int ri = 0, rj = 0;  // ray r = ri*res_y + rj, scan order i-major
-      for (int r = 0; r < c.n_rays; ++r, ++rj) {
-        if (rj == c.res_y) {
-          rj = 0;
-          ++ri;
+      // rays in scan order (i-major), 32 at a time: lane L prepares ray g+L (direction, start
+      // section), then the warp walks them one by one
+      for (int g = 0; g < c.n_rays; g += 32) {
+        const int my_r = g + static_cast<int>(lane);
+        const bool my_valid = my_r < c.n_rays;
+        const int my_ri = my_valid ? my_r / c.res_y : 0;
+        const int my_rj = my_valid ? my_r - my_ri * c.res_y : 0;
+        D3 my_dir{0.0, 0.0, 0.0};
+        int my_s = -1;
+        if (my_valid) {
+          my_dir = rotate(q, D3{c.cam_dirs[3 * my_r], c.cam_dirs[3 * my_r + 1],
+                                c.cam_dirs[3 * my_r + 2]});
+          my_s = ITER ? static_cast<int>(table[my_r]) : 0;
         }
-        int s = 0;
-        if (ITER) {
-          s = table[r];
+        const int n_in_group = min(32, c.n_rays - g);
+        for (int l = 0; l < n_in_group; ++l) {
+          const int s = __shfl_sync(kFull, my_s, l);
           if (s < 0) continue;  // already occluded ray
-        }
-        const D3 dir = rotate(q, D3{c.cam_dirs[3 * r], c.cam_dirs[3 * r + 1], c.cam_dirs[3 * r + 2]});
-        const double* __restrict__ ds = c.dseq + static_cast<size_t>(s) * c.kmax;
-        const int K = c.kcount[s];
-        int hit_k = -1;
+          const D3 dir{__shfl_sync(kFull, my_dir.x, l), __shfl_sync(kFull, my_dir.y, l),
+                       __shfl_sync(kFull, my_dir.z, l)};
+          const double* __restrict__ ds = c.dseq + static_cast<size_t>(s) * c.kmax;
+          const int K = c.kcount[s];
+          int hit_k = -1;
 
-        for (int k0 = 0; k0 < K; k0 += 32) {
-          const int k = k0 + static_cast<int>(lane);
-          const bool valid = k < K;
-          const double d = valid ? ds[k] : 0.0;
-          const D3 P{__dadd_rn(P0.x, __dmul_rn(d, dir.x)), __dadd_rn(P0.y, __dmul_rn(d, dir.y)),
-                     __dadd_rn(P0.z, __dmul_rn(d, dir.z))};
-          int st = 1;
-          if (valid) st = voxel_state(m, P);
-          const unsigned occ = __ballot_sync(kFull, valid && st == 0);
-          int n_emit = min(32, K - k0);
-          if (occ) {
-            const int h = __ffs(occ) - 1;
-            hit_k = k0 + h;
-            // Simple: state tested before the push (hit excluded, simple_ray_caster.cpp:52-61);
-            // Iterative: pushed, then tested (hit included, iterative_ray_caster.cpp:81-93)
-            n_emit = ITER ? h + 1 : h;
-          }
-          int bi[3], vi[3];
-          const D3 cc = voxel_center(m, P, bi, vi);
-          double px = __shfl_up_sync(kFull, cc.x, 1);
-          double py = __shfl_up_sync(kFull, cc.y, 1);
-          double pz = __shfl_up_sync(kFull, cc.z, 1);
-          if (lane == 0) {
-            px = carry.x;
-            py = carry.y;
-            pz = carry.z;
-          }
-          bool keep = (static_cast<int>(lane) < n_emit) && !(cc.x == px && cc.y == py && cc.z == pz);
-          if (n_emit > 0) {
-            carry.x = __shfl_sync(kFull, cc.x, n_emit - 1);
-            carry.y = __shfl_sync(kFull, cc.y, n_emit - 1);
-            carry.z = __shfl_sync(kFull, cc.z, n_emit - 1);
-          }
-          if (EVAL != kEvalNone) {
-            if (keep && e.bv_is_setup) keep = bv_contains(e, cc);
-          }
-          const unsigned km = __ballot_sync(kFull, keep);
-          const int nk = __popc(km);
-          const int rank = __popc(km & lt_mask);
-          if (EMIT) {
-            const long long idx = static_cast<long long>(n_vis) + rank;
-            if (keep && idx < b.cap) {
-              b.centres_out[3 * idx] = cc.x;
-              b.centres_out[3 * idx + 1] = cc.y;
-              b.centres_out[3 * idx + 2] = cc.z;
-            }
-          }
-          if (DIGEST) {
-            unsigned long long contrib = keep ? digest_entry(cc) * pw[nk - 1 - rank] : 0ull;
+          for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + static_cast<int>(lane);
+            const bool valid = k < K;
+            const double d = valid ? ds[k] : 0.0;
+            const D3 Pd{__dadd_rn(P0.x, __dmul_rn(d, dir.x)), __dadd_rn(P0.y, __dmul_rn(d, dir.y)),
+                        __dadd_rn(P0.z, __dmul_rn(d, dir.z))};
+            // shared by getVoxelState and getVoxelCenter: float point, block index, block origin
+            const float pf[3] = {__double2float_rn(Pd.x), __double2float_rn(Pd.y),
+                                 __double2float_rn(Pd.z)};
+            int bi[3];
+            float origin[3];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(kFull, contrib, off);
-            digest = digest * pw[nk] + contrib;
-          }
-          n_vis += nk;
-          if (EVAL != kEvalNone) {
-            if (keep) fold_entry<EVAL>(m, e, cc, cnt);
-          }
-          if (occ) break;
-        }
-        n_samp += (hit_k >= 0) ? (hit_k + 1) : K;
-
-        if (ITER) {
-          // markNeighboringRays calls of this ray, applied in one pass (DESIGN.md "ray table"):
-          // completed sections t = s..t_last each mark the w[t]-square with t+1; a hit in section
-          // seg_h marks its square with -1 last.
-          const bool hit = hit_k >= 0;
-          int seg_h = s;
-          if (hit) {
-            while (hit_k >= c.seg_end[s * c.n_sections + seg_h]) ++seg_h;
-          }
-          const int t_last = hit ? seg_h : c.n_sections - 2;
-          const int w0 = 1 << (c.n_sections - 1 - s);
-          if (t_last >= s && w0 > 1) {
-            const int nx = min(w0, c.res_x - ri), ny = min(w0, c.res_y - rj);
-            for (int cell = lane; cell < nx * ny; cell += 32) {
-              const int dx = cell / ny, dy = cell - dx * ny;
-              const int mx = max(dx, dy);
-              const int tmax = mx == 0 ? c.n_sections - 1 : c.n_sections - 2 - (31 - __clz(mx));
-              const int t = min(tmax, t_last);
-              const int val = (hit && t == seg_h) ? -1 : t + 1;
-              table[(ri + dx) * c.res_y + rj + dy] = static_cast<int8_t>(val);
+            for (int a = 0; a < 3; ++a) {
+              bi[a] = grid_index(pf[a], m.bs_inv_f);
+              origin[a] = origin_point(bi[a], m.bs_f);
             }
-            __syncwarp();
+            const int slot = find_slot(m, bi[0], bi[1], bi[2]);
+            int st = 1;
+            if (valid) st = voxel_state_in_block(m, ct, pf, bi, origin, slot);
+            const unsigned occ = __ballot_sync(kFull, valid && st == 0);
+            int n_emit = min(32, K - k0);
+            if (occ) {
+              const int h = __ffs(occ) - 1;
+              hit_k = k0 + h;
+              // Simple: state tested before the push (hit excluded, simple_ray_caster.cpp:52-61);
+              // Iterative: pushed, then tested (hit included, iterative_ray_caster.cpp:81-93)
+              n_emit = ITER ? h + 1 : h;
+            }
+            int vi[3];
+            const D3 cc = voxel_center_in_block(m, ct, Pd, origin, vi);
+            double px = __shfl_up_sync(kFull, cc.x, 1);
+            double py = __shfl_up_sync(kFull, cc.y, 1);
+            double pz = __shfl_up_sync(kFull, cc.z, 1);
+            if (lane == 0) {
+              px = carry.x;
+              py = carry.y;
+              pz = carry.z;
+            }
+            bool keep =
+                (static_cast<int>(lane) < n_emit) && !(cc.x == px && cc.y == py && cc.z == pz);
+            if (n_emit > 0) {
+              carry.x = __shfl_sync(kFull, cc.x, n_emit - 1);
+              carry.y = __shfl_sync(kFull, cc.y, n_emit - 1);
+              carry.z = __shfl_sync(kFull, cc.z, n_emit - 1);
+            }
+            bool inside = true;
+            if (EVAL != kEvalNone) {
+              if (e.bv_is_setup) {
+                inside = bv_contains(e, cc);
+                keep = keep && inside;  // simulated_sensor_evaluator.cpp:50-57
+              }
+            }
+            const unsigned km = __ballot_sync(kFull, keep);
+            const int nk = __popc(km);
+            const int rank = __popc(km & lt_mask);
+            if (EMIT) {
+              const long long idx = static_cast<long long>(n_vis) + rank;
+              if (keep && idx < b.cap) {
+                b.centres_out[3 * idx] = cc.x;
+                b.centres_out[3 * idx + 1] = cc.y;
+                b.centres_out[3 * idx + 2] = cc.z;
+              }
+            }
+            if (DIGEST) {
+              unsigned long long contrib = keep ? digest_entry(cc) * pw[nk - 1 - rank] : 0ull;
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1)
+                contrib += __shfl_xor_sync(kFull, contrib, off);
+              digest = digest * pw[nk] + contrib;
+            }
+            n_vis += nk;
+            if (EVAL != kEvalNone) {
+              if (keep) {
+                // the entry's centre lies in block bi (same block index as the sample point)
+                const int cs = centre_state(m, ct, cc, slot, vi);
+                if (EVAL == A3D_EVAL_VOXEL_TYPE) {
+                  cnt[cs & 3]++;  // retained entries are always inside the bounding volume
+                } else if (!(cs & 4)) {
+                  if (EVAL == A3D_EVAL_NAIVE) {
+                    cnt[0]++;
+                  } else if (is_frontier_voxel(m, ct, e, cc)) {
+                    cnt[0]++;
+                  }
+                }
+              }
+            }
+            if (occ) break;
           }
-        }
-      }  // rays
-    }    // views
+          n_samp += (hit_k >= 0) ? (hit_k + 1) : K;
+
+          if (ITER) {
+            // markNeighboringRays calls of this ray, applied in one pass (DESIGN.md "ray table"):
+            // completed sections t = s..t_last each mark the w[t]-square with t+1; a hit in section
+            // seg_h marks its square with -1 last.
+            const bool hit = hit_k >= 0;
+            int seg_h = s;
+            if (hit) {
+              while (hit_k >= c.seg_end[s * c.n_sections + seg_h]) ++seg_h;
+            }
+            const int t_last = hit ? seg_h : c.n_sections - 2;
+            const int w0 = 1 << (c.n_sections - 1 - s);
+            if (t_last >= s && w0 > 1) {
+              const int r = g + l;
+              const int ri = r / c.res_y, rj = r - ri * c.res_y;
+              const int nx = min(w0, c.res_x - ri), ny = min(w0, c.res_y - rj);
+              for (int cell = lane; cell < nx * ny; cell += 32) {
+                const int dx = cell / ny, dy = cell - dx * ny;
+                const int mx = max(dx, dy);
+                const int tmax = mx == 0 ? c.n_sections - 1 : c.n_sections - 2 - (31 - __clz(mx));
+                const int t = min(tmax, t_last);
+                const int val = (hit && t == seg_h) ? -1 : t + 1;
+                table[(ri + dx) * c.res_y + rj + dy] = static_cast<int8_t>(val);
+              }
+              // the same marks applied to the start sections already held in registers
+              if (my_valid) {
+                const int dx = my_ri - ri, dy = my_rj - rj;
+                if (dx >= 0 && dy >= 0 && dx < nx && dy < ny) {
+                  const int mx = max(dx, dy);
+                  const int tmax = mx == 0 ? c.n_sections - 1 : c.n_sections - 2 - (31 - __clz(mx));
+                  const int t = min(tmax, t_last);
+                  my_s = (hit && t == seg_h) ? -1 : t + 1;
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }  // rays of the group
+      }    // ray groups
+    }      // views
 
     // per-segment reduction and write-out
     unsigned long long tot[6];
@@ -379,6 +521,9 @@ __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
                                    const double* __restrict__ centres,
                                    unsigned long long* __restrict__ counters,
                                    uint8_t* __restrict__ keep) {
+  __shared__ CenterTables ct;
+  init_center_tables(m, &ct);
+  __syncthreads();
   unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
   unsigned left = 0;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -386,15 +531,17 @@ __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
     const D3 c{centres[3 * i], centres[3 * i + 1], centres[3 * i + 2]};
     bool kp = true;
     if (e.kind == A3D_EVAL_VOXEL_TYPE) {
-      fold_entry<A3D_EVAL_VOXEL_TYPE>(m, e, c, cnt);
+      const int s = voxel_state(m, ct, c);
+      cnt[s + (bv_contains(e, c) ? 0 : 3)]++;
     } else {
       kp = !is_observed(m, c);
       if (kp && e.kind == A3D_EVAL_NAIVE) cnt[0]++;
-      if (kp && e.kind == A3D_EVAL_FRONTIER && is_frontier_voxel(m, e, c)) cnt[0]++;
+      if (kp && e.kind == A3D_EVAL_FRONTIER && is_frontier_voxel(m, ct, e, c)) cnt[0]++;
     }
     if (kp) left++;
     if (keep) keep[i] = kp ? 1 : 0;
   }
+  __syncwarp();
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const unsigned t = __reduce_add_sync(kFull, cnt[i]);
@@ -407,9 +554,7 @@ __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
 void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& e, long long n,
                              const double* centres, unsigned long long* counters, uint8_t* keep) {
   if (n <= 0) return;
-  const int block = 128;
-  const int grid = static_cast<int>(std::min<long long>((n + block - 1) / block, 148LL * 16));
-  k_gain_from_voxels<<<grid, block, 0, st>>>(m, e, n, centres, counters, keep);
+  k_gain_from_voxels<<<grid_for(n, 128), 128, 0, st>>>(m, e, n, centres, counters, keep);
 }
 
 }  // namespace a3d

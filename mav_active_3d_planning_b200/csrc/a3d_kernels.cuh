@@ -45,9 +45,13 @@ struct LaunchCfg {
 };
 
 // launchers (a3d_kernels.cu)
-void launch_apply_blocks(cudaStream_t st, int n, int nv, const int32_t* slots_dev,
+void launch_apply_blocks(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                          const float* dist_src, const uint8_t* obs_src, const float* w_src,
                          float* dist_slab, float* weight_slab);
+void launch_refresh_aprons(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
+                           const int32_t* nbr_dev /*n×27*/, float* dist_slab);
+void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
+                       const int32_t* block_idx_dev /*n×3*/, uint8_t* meta_slab);
 void launch_point_query(cudaStream_t st, const MapView& m, int what, long long n, const double* pts,
                         void* out0, void* out1);
 void launch_bv_contains(cudaStream_t st, const EvalView& e, long long n, const double* pts,
@@ -59,6 +63,7 @@ void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& 
                              uint8_t* keep);
 int cast_gain_block_threads();
 
-enum { kQueryState = 0, kQueryCenter = 1, kQueryObserved = 2, kQueryWeight = 3, kQueryDistance = 4 };
+enum { kQueryState = 0, kQueryCenter = 1, kQueryObserved = 2, kQueryWeight = 3, kQueryDistance = 4,
+       kQueryStateGeneric = 5 };
 
 }  // namespace a3d

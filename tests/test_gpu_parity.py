@@ -66,6 +66,17 @@ def test_map_queries_bit_exact(capi, O, vs):
     ctx.close()
 
 
+def test_fast_path_equals_literal_path_at_scale(capi, room01):
+    """Apron + meta-byte fast path vs the literal 8-lookup path on 4M points (incl. fp edge cases)."""
+    ctx = capi.Context(0)
+    ctx.upload_map(room01)
+    pts = probe_points(room01, 600000, 23)
+    assert np.array_equal(ctx.voxel_state(pts), ctx.voxel_state_literal(pts))
+    c = ctx.voxel_center(pts)
+    assert np.array_equal(ctx.voxel_state(c), ctx.voxel_state_literal(c))
+    ctx.close()
+
+
 def test_map_vps8_and_delta_updates(capi, O):
     from mav_active_3d_planning_b200 import synth
     m = synth.room_map(0.2, vps=8)
