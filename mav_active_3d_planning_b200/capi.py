@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liba3d_b200.so")
+LIB_PATH = os.environ.get("A3D_LIB_PATH") or os.path.join(_HERE, "liba3d_b200.so")
 
 OCCUPIED, FREE, UNKNOWN = 0, 1, 2
 CASTER_SIMPLE, CASTER_ITERATIVE = 0, 1

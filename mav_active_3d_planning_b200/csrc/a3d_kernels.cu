@@ -244,9 +244,12 @@ __device__ __forceinline__ double voxel_type_gain(const EvalView& e, const unsig
 }
 
 constexpr int kCastBlock = 32;  // one warp per CTA: a warp owns a whole segment
+#ifndef A3D_CAST_MIN_BLOCKS
+#define A3D_CAST_MIN_BLOCKS 24  // resident CTAs (= warps) per SM the register allocation must allow
+#endif
 
 template <int CASTER, int EVAL, bool DIGEST, bool EMIT>
-__global__ void __launch_bounds__(kCastBlock)
+__global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
     k_cast_gain(const MapView m, const CasterView c, const EvalView e, const Batch b) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
