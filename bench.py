@@ -278,7 +278,8 @@ def run_ours(args):
             if world > 1:
                 dist.broadcast(payload, src=0)  # delta still travels rank0 → all on the device side
             ctx.upload_blocks(d_idx, h_ddist, h_dobs)
-            r = ctx.compute_gains(caster, ev, h_pos, h_quat, h_seg, n_seg, digests=False)
+            r = ctx.compute_gains(caster, ev, h_pos, h_quat, h_seg, n_seg, digests=False,
+                                  set_digests=False)
             return r
         for _ in range(2):
             step_host()
@@ -329,7 +330,8 @@ def run_ours(args):
         "kernel_ms": k_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "kernel": "k_cast_gain<Iterative,VoxelType>",
+                     "kernel": ("k_cast_wave" if ctx.last_cast_kernel == 2 else "k_cast_gain") +
+                     "<Iterative,VoxelType>",
                      "algorithmic_bytes_per_launch": alg_bytes},
         "e2e": {"value": steps_views / e2e_s, "unit": "views/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},

@@ -110,6 +110,12 @@ void* a3d_ctx_stream(a3d_ctx* ctx);
 float a3d_last_kernel_ms(a3d_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 uint64_t a3d_kernel_launches(a3d_ctx* ctx);
+/* Tuning / test knobs.  "cast_kernel": 0 = automatic (default), 1 = always the scan-order kernel
+   (k_cast_gain), 2 = require the wavefront kernel (k_cast_wave; errors if ordered outputs are asked). */
+int a3d_set_option(a3d_ctx* ctx, const char* name, int64_t value);
+/* Which kernel the last a3d_compute_gains*() used: 1 scan-order, 2 wavefront (+ scan-order re-evaluation
+   of flagged segments). */
+int a3d_last_cast_kernel(const a3d_ctx* ctx);
 
 /* ---- map mirror: replaces VoxbloxMap (active_3d_planning_voxblox/src/map/voxblox.cpp) ------- */
 /* voxblox::EsdfServer layer parameters (tsdf_voxel_size, tsdf_voxels_per_side,
@@ -166,18 +172,21 @@ void a3d_eval_destroy(a3d_eval* e);
  *   gains_out      TrajectorySegment::gain
  *   n_visible_out  size of the voxel list the reference would store in SimulatedSensorInfo
  *   n_samples_out  ray samples taken (= getVoxelState calls made by the caster)
- *   digests_out    order-sensitive 64-bit digest of that stored list (DESIGN.md "digest")
+ *   digests_out    order-sensitive 64-bit digest of that stored list (DESIGN.md "digest");
+ *                  asking for it selects the scan-order kernel
+ *   set_digests_out  order-independent digest of the same list (sum of per-entry hashes mod 2^64)
  * Synchronous on return.  clear_from_parents is not supported by the batch call. */
 int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                       const double* pos, const double* quat, const int32_t* view_segment,
                       int n_segments, double* gains_out, uint64_t* n_visible_out,
-                      uint64_t* n_samples_out, uint64_t* digests_out);
+                      uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* set_digests_out);
 /* Same with every array in device memory; enqueued on the context stream, NOT synchronised.
    view_first_dev: n_segments+1 int32 prefix offsets of each segment's views. */
 int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
                           int n_views, const double* pos_dev, const double* quat_dev,
                           const int32_t* view_first_dev, int n_segments, double* gains_dev,
-                          uint64_t* n_visible_dev, uint64_t* n_samples_dev, uint64_t* digests_dev);
+                          uint64_t* n_visible_dev, uint64_t* n_samples_dev, uint64_t* digests_dev,
+                          uint64_t* set_digests_dev);
 
 /* One segment with its voxel list materialised (parity / visualisation / the per-segment
  * SensorModel::getVisibleVoxelsFromTrajectory + storeTrajectoryInformation API):

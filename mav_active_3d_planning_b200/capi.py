@@ -30,7 +30,7 @@ _EVAL_KINDS = {"VoxelTypeEvaluator": EVAL_VOXEL_TYPE, "NaiveEvaluator": EVAL_NAI
 # every symbol include/a3d.h declares
 EXPORTS = [
     "a3d_ctx_create", "a3d_ctx_destroy", "a3d_last_error", "a3d_ctx_stream", "a3d_last_kernel_ms",
-    "a3d_kernel_launches", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev",
+    "a3d_kernel_launches", "a3d_set_option", "a3d_last_cast_kernel", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev",
     "a3d_map_remove_blocks", "a3d_map_clear", "a3d_map_num_blocks", "a3d_map_voxel_size",
     "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
     "a3d_map_distance", "a3d_caster_create", "a3d_caster_destroy", "a3d_caster_get_info",
@@ -154,8 +154,10 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_eval_create.argtypes = [vp, P(EvalParams), P(vp)]
     lib.a3d_eval_destroy.argtypes = [vp]
     lib.a3d_eval_destroy.restype = None
-    lib.a3d_compute_gains.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
-    lib.a3d_compute_gains_dev.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.a3d_compute_gains.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.a3d_compute_gains_dev.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.a3d_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.a3d_last_cast_kernel.argtypes = [vp]
     lib.a3d_visible_voxels.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, i64, P(i64), P(i64), P(dbl)]
     lib.a3d_gain_from_voxels.argtypes = [vp, vp, i64, vp, P(dbl), P(i64), vp]
     lib.a3d_bv_contains.argtypes = [vp, vp, i64, vp, vp]
@@ -307,10 +309,19 @@ class Context:
         return int(self.lib.a3d_kernel_launches(self.h))
 
     # ---- hot call ----
+    def set_option(self, name: str, value: int):
+        self._ck(self.lib.a3d_set_option(self.h, name.encode(), int(value)))
+
+    @property
+    def last_cast_kernel(self) -> int:
+        return int(self.lib.a3d_last_cast_kernel(self.h))
+
     def compute_gains(self, caster, evaluator, pos, quat, view_segment=None, n_segments=None,
-                      digests=True):
+                      digests=True, set_digests=True):
         """Batched SimulatedSensorEvaluator::computeGain.  Returns dict(gain, n_visible, n_samples,
-        digest) of per-segment arrays.  Default: one view per segment."""
+        digest, set_digest) of per-segment arrays.  Default: one view per segment.  ``digests=True``
+        (ordered digest) selects the scan-order kernel; with ``digests=False`` the wavefront kernel
+        runs."""
         pos = _pts(pos)
         quat = np.ascontiguousarray(quat, np.float64)
         n_views = len(pos)
@@ -323,18 +334,19 @@ class Context:
         nvis = np.zeros(n_segments, np.uint64)
         nsamp = np.zeros(n_segments, np.uint64)
         dig = np.zeros(n_segments, np.uint64) if digests else None
+        sdig = np.zeros(n_segments, np.uint64) if set_digests else None
         self._ck(self.lib.a3d_compute_gains(self.h, caster.h, evaluator.h, n_views, _ptr(pos),
                                             _ptr(quat), _ptr(view_segment), n_segments, _ptr(gains),
-                                            _ptr(nvis), _ptr(nsamp), _ptr(dig)))
-        return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig)
+                                            _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(sdig)))
+        return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig, set_digest=sdig)
 
     def compute_gains_dev(self, caster, evaluator, n_views, pos_ptr, quat_ptr, first_ptr, n_segments,
-                          gains_ptr, nvis_ptr=0, nsamp_ptr=0, dig_ptr=0):
+                          gains_ptr, nvis_ptr=0, nsamp_ptr=0, dig_ptr=0, set_dig_ptr=0):
         """Device-pointer variant (enqueue only, no sync)."""
         self._ck(self.lib.a3d_compute_gains_dev(self.h, caster.h, evaluator.h, n_views, pos_ptr,
                                                 quat_ptr, first_ptr, n_segments, gains_ptr,
                                                 nvis_ptr or None, nsamp_ptr or None,
-                                                dig_ptr or None))
+                                                dig_ptr or None, set_dig_ptr or None))
 
     def visible_voxels(self, caster, pos, quat, evaluator=None, cap=None):
         """One segment: ordered voxel-centre list (+gain if an evaluator is given)."""

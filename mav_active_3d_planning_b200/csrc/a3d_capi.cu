@@ -101,7 +101,10 @@ struct a3d_ctx {
   DevBuf<int32_t> sc_first;
   DevBuf<unsigned long long> sc_nvis, sc_nsamp, sc_dig, sc_cnt;
   DevBuf<int8_t> sc_tables;
-  DevBuf<unsigned int> sc_counter;
+  DevBuf<unsigned int> sc_counter, sc_inexact;
+  DevBuf<uint8_t> sc_wave;
+  int opt_cast_kernel = 0;  // 0 auto, 1 scan-order kernel (k_cast_gain), 2 wavefront kernel (k_cast_wave)
+  int last_cast_kernel = 0;
 
   int fail(int code, const std::string& msg) const {
     err = msg;
@@ -398,20 +401,19 @@ EvalView make_eval_view(const a3d_ctx* ctx, const a3d_eval_params& p) {
   return v;
 }
 
-// Enqueue the cast+gain kernel for a batch whose inputs/outputs are already on the device.
+// Enqueue the cast+gain work for a batch whose inputs/outputs are already on the device.
+// Kernel choice: the wavefront kernel (k_cast_wave) when only order-free outputs are wanted, else the
+// scan-order kernel (k_cast_gain), which also re-evaluates the rare segments k_cast_wave flags.
 int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const double* pos_dev,
                  const double* quat_dev, const int32_t* first_dev, int n_segments, double* gains_dev,
                  unsigned long long* nvis_dev, unsigned long long* nsamp_dev,
-                 unsigned long long* dig_dev, double* centres_dev, long long cap, bool emit) {
+                 unsigned long long* dig_dev, unsigned long long* set_dig_dev, double* centres_dev,
+                 long long cap, bool emit) {
   if (ctx->h_table.empty()) {
     table_rebuild(ctx, 0);
     int rc = table_upload(ctx);
     if (rc) return rc;
   }
-  const int block = cast_gain_block_threads();
-  const int warps_per_block = block / 32;
-  int grid = (n_segments + warps_per_block - 1) / warps_per_block;
-  grid = std::max(1, std::min(grid, ctx->sm_count * 32));
   Batch b{};
   b.pos = pos_dev;
   b.quat = quat_dev;
@@ -421,21 +423,57 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   b.n_visible = nvis_dev;
   b.n_samples = nsamp_dev;
   b.digests = dig_dev;
+  b.set_digests = set_dig_dev;
   b.centres_out = centres_dev;
   b.cap = cap;
-  if (c->view.kind == A3D_CASTER_ITERATIVE) {
-    b.table_stride = (static_cast<size_t>(c->view.n_rays) + 15) / 16 * 16;
-    CK(ctx->sc_tables.reserve(b.table_stride * grid * warps_per_block));
-    b.tables = ctx->sc_tables.p;
-  }
-  CK(ctx->sc_counter.reserve(1));
-  b.work_counter = ctx->sc_counter.p;
-  CK(cudaMemsetAsync(ctx->sc_counter.p, 0, sizeof(unsigned int), ctx->stream));
+  CK(ctx->sc_counter.reserve(2));
+  CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+
+  const bool wave_ok = e && !emit && !dig_dev &&
+                       std::min(c->view.res_x, c->view.res_y) <= cast_wave_max_diag() &&
+                       c->view.n_rays < (1 << 24);
+  if (ctx->opt_cast_kernel == 2 && !wave_ok)
+    return ctx->fail(A3D_ERR_UNSUPPORTED,
+                     "cast_kernel=2 (wavefront) cannot produce ordered lists/digests");
+  const bool use_wave = wave_ok && ctx->opt_cast_kernel != 1;
+  ctx->last_cast_kernel = use_wave ? 2 : 1;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  launch_cast_gain(ctx->stream, ctx->view(), c->view, e ? &e->view : nullptr, b, dig_dev != nullptr,
-                   emit, grid, block);
-  ctx->launches++;
-  CK(cudaGetLastError());
+  const unsigned int* seg_mask = nullptr;
+  if (use_wave) {
+    int grid = std::max(1, std::min(n_segments, ctx->sm_count * 12));
+    size_t stride = 0;
+    while (grid > 1 && wave_scratch_bytes(c->view.n_rays, grid, set_dig_dev != nullptr, &stride) >
+                           (size_t(6) << 30))
+      grid /= 2;
+    CK(ctx->sc_wave.reserve(wave_scratch_bytes(c->view.n_rays, grid, set_dig_dev != nullptr, &stride)));
+    const size_t n_words = static_cast<size_t>(n_segments) / 32 + 1;
+    CK(ctx->sc_inexact.reserve(n_words));
+    CK(cudaMemsetAsync(ctx->sc_inexact.p, 0, n_words * sizeof(unsigned int), ctx->stream));
+    b.work_counter = ctx->sc_counter.p;
+    launch_cast_wave(ctx->stream, ctx->view(), c->view, e->view, b, set_dig_dev != nullptr, grid,
+                     ctx->sc_wave.p, ctx->sc_inexact.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    seg_mask = ctx->sc_inexact.p;
+  }
+  {
+    // scan-order kernel: everything (no wave) or only the segments the wave kernel flagged
+    const int block = cast_gain_block_threads();
+    const int warps_per_block = block / 32;
+    int grid = (n_segments + warps_per_block - 1) / warps_per_block;
+    grid = std::max(1, std::min(grid, ctx->sm_count * 32));
+    if (c->view.kind == A3D_CASTER_ITERATIVE) {
+      b.table_stride = (static_cast<size_t>(c->view.n_rays) + 15) / 16 * 16;
+      CK(ctx->sc_tables.reserve(b.table_stride * grid * warps_per_block));
+      b.tables = ctx->sc_tables.p;
+    }
+    b.work_counter = ctx->sc_counter.p + 1;
+    b.seg_mask = seg_mask;
+    launch_cast_gain(ctx->stream, ctx->view(), c->view, e ? &e->view : nullptr, b,
+                     dig_dev != nullptr || set_dig_dev != nullptr, emit, grid, block);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
   return A3D_OK;
@@ -513,6 +551,8 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
   ctx->sc_cnt.release();
   ctx->sc_tables.release();
   ctx->sc_counter.release();
+  ctx->sc_inexact.release();
+  ctx->sc_wave.release();
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -759,6 +799,9 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   v.seg_end = c->d_seg_end;
   for (int i = 0; i < 3; ++i) v.mount_t[i] = p->mount_t[i];
   v.mount_q = Q4{p->mount_q[0], p->mount_q[1], p->mount_q[2], p->mount_q[3]};
+  v.ray_step = info.ray_step;
+  v.ray_length = p->ray_length;
+  for (int t = 0; t <= n_sections; ++t) v.split[t] = split[t];
   *out = c;
   return A3D_OK;
 }
@@ -808,7 +851,8 @@ void a3d_eval_destroy(a3d_eval* e) { delete e; }
 int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                           const double* pos_dev, const double* quat_dev,
                           const int32_t* view_first_dev, int n_segments, double* gains_dev,
-                          uint64_t* n_visible_dev, uint64_t* n_samples_dev, uint64_t* digests_dev) {
+                          uint64_t* n_visible_dev, uint64_t* n_samples_dev, uint64_t* digests_dev,
+                          uint64_t* set_digests_dev) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!caster || !eval || caster->ctx != ctx || eval->ctx != ctx)
     return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
@@ -822,13 +866,26 @@ int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval
   return enqueue_cast(ctx, caster, eval, pos_dev, quat_dev, view_first_dev, n_segments, gains_dev,
                       reinterpret_cast<unsigned long long*>(n_visible_dev),
                       reinterpret_cast<unsigned long long*>(n_samples_dev),
-                      reinterpret_cast<unsigned long long*>(digests_dev), nullptr, 0, false);
+                      reinterpret_cast<unsigned long long*>(digests_dev),
+                      reinterpret_cast<unsigned long long*>(set_digests_dev), nullptr, 0, false);
 }
+
+int a3d_set_option(a3d_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return A3D_ERR_INVALID;
+  if (std::strcmp(name, "cast_kernel") == 0) {
+    if (value < 0 || value > 2) return ctx->fail(A3D_ERR_INVALID, "cast_kernel must be 0, 1 or 2");
+    ctx->opt_cast_kernel = static_cast<int>(value);
+    return A3D_OK;
+  }
+  return ctx->fail(A3D_ERR_INVALID, std::string("unknown option ") + name);
+}
+
+int a3d_last_cast_kernel(const a3d_ctx* ctx) { return ctx ? ctx->last_cast_kernel : 0; }
 
 int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                       const double* pos, const double* quat, const int32_t* view_segment,
                       int n_segments, double* gains_out, uint64_t* n_visible_out,
-                      uint64_t* n_samples_out, uint64_t* digests_out) {
+                      uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* set_digests_out) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!caster || !eval || caster->ctx != ctx || eval->ctx != ctx)
     return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
@@ -852,7 +909,7 @@ int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* ev
   CK(ctx->sc_gains.reserve(n_segments));
   CK(ctx->sc_nvis.reserve(n_segments));
   CK(ctx->sc_nsamp.reserve(n_segments));
-  if (digests_out) CK(ctx->sc_dig.reserve(n_segments));
+  if (digests_out || set_digests_out) CK(ctx->sc_dig.reserve(2 * static_cast<size_t>(n_segments)));
   if (n_views > 0) {
     CK(cudaMemcpyAsync(ctx->sc_pos.p, pos, 3 * sizeof(double) * n_views, cudaMemcpyHostToDevice,
                        ctx->stream));
@@ -865,7 +922,10 @@ int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* ev
                                  ctx->sc_first.p, n_segments, ctx->sc_gains.p,
                                  reinterpret_cast<uint64_t*>(ctx->sc_nvis.p),
                                  reinterpret_cast<uint64_t*>(ctx->sc_nsamp.p),
-                                 digests_out ? reinterpret_cast<uint64_t*>(ctx->sc_dig.p) : nullptr);
+                                 digests_out ? reinterpret_cast<uint64_t*>(ctx->sc_dig.p) : nullptr,
+                                 set_digests_out
+                                     ? reinterpret_cast<uint64_t*>(ctx->sc_dig.p + n_segments)
+                                     : nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(gains_out, ctx->sc_gains.p, sizeof(double) * n_segments,
                      cudaMemcpyDeviceToHost, ctx->stream));
@@ -878,6 +938,9 @@ int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* ev
   if (digests_out)
     CK(cudaMemcpyAsync(digests_out, ctx->sc_dig.p, 8 * static_cast<size_t>(n_segments),
                        cudaMemcpyDeviceToHost, ctx->stream));
+  if (set_digests_out)
+    CK(cudaMemcpyAsync(set_digests_out, ctx->sc_dig.p + n_segments,
+                       8 * static_cast<size_t>(n_segments), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return A3D_OK;
 }
@@ -910,7 +973,7 @@ int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* e
   }
   CK(cudaMemcpyAsync(ctx->sc_first.p, first, sizeof(first), cudaMemcpyHostToDevice, ctx->stream));
   int rc = enqueue_cast(ctx, caster, eval, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, 1,
-                        ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr,
+                        ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr,
                         ctx->sc_centres.p, cap, true);
   if (rc) return rc;
   unsigned long long nvis = 0, nsamp = 0;

@@ -275,12 +275,13 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
     if (lane == 0) seg = static_cast<int>(atomicAdd(b.work_counter, 1u));
     seg = __shfl_sync(kFull, seg, 0);
     if (seg >= b.n_segments) break;
+    if (b.seg_mask && !((b.seg_mask[seg >> 5] >> (seg & 31)) & 1u)) continue;
     const int v_begin = b.view_first[seg], v_end = b.view_first[seg + 1];
 
     D3 carry{kNaN, kNaN, kNaN};  // previous raw list entry (NaN: none yet)
     // per-lane counters: VoxelType → [state + 3*outside]; Naive/Frontier → [0]
     unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
-    unsigned long long n_vis = 0, n_samp = 0, digest = 0;
+    unsigned long long n_vis = 0, n_samp = 0, digest = 0, set_digest = 0;
 
     for (int view = v_begin; view < v_end; ++view) {
       // camera pose = body pose ∘ mounting transform (camera_model.cpp:24-28)
@@ -387,11 +388,16 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
               }
             }
             if (DIGEST) {
-              unsigned long long contrib = keep ? digest_entry(cc) * pw[nk - 1 - rank] : 0ull;
+              const unsigned long long eh = keep ? digest_entry(cc) : 0ull;
+              unsigned long long contrib = keep ? eh * pw[nk - 1 - rank] : 0ull;
+              unsigned long long plain = eh;
 #pragma unroll
-              for (int off = 16; off > 0; off >>= 1)
+              for (int off = 16; off > 0; off >>= 1) {
                 contrib += __shfl_xor_sync(kFull, contrib, off);
+                plain += __shfl_xor_sync(kFull, plain, off);
+              }
               digest = digest * pw[nk] + contrib;
+              set_digest += plain;
             }
             n_vis += nk;
             if (EVAL != kEvalNone) {
@@ -468,6 +474,7 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
       if (b.n_visible) b.n_visible[seg] = n_vis;
       if (b.n_samples) b.n_samples[seg] = n_samp;
       if (DIGEST && b.digests) b.digests[seg] = digest;
+      if (DIGEST && b.set_digests) b.set_digests[seg] = set_digest;
     }
   }
 }

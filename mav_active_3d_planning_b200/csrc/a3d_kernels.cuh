@@ -19,6 +19,8 @@ struct CasterView {
   const int32_t* __restrict__ seg_end;  // n_starts×n_sections: #samples lying in sections <= t
   double mount_t[3];
   Q4 mount_q;
+  double ray_step, ray_length;
+  double split[33];  // c_split_distances_ (iterative)
 };
 
 struct Batch {
@@ -30,7 +32,9 @@ struct Batch {
   double* gains;
   unsigned long long* n_visible;
   unsigned long long* n_samples;
-  unsigned long long* digests;
+  unsigned long long* digests;      // order-sensitive digest (k_cast_gain only)
+  unsigned long long* set_digests;  // order-independent digest (both kernels)
+  const unsigned int* seg_mask;     // k_cast_gain: if set, only segments whose bit is 1 are evaluated
   double* centres_out;  // emit mode (single segment): cap×3
   long long cap;
   int8_t* tables;       // per-warp ray tables (iterative), table_stride bytes each
@@ -62,6 +66,12 @@ void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& 
                              const double* centres, unsigned long long* counters /*8*/,
                              uint8_t* keep);
 int cast_gain_block_threads();
+// throughput kernel (a3d_wave.cu)
+size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride);
+void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
+                      const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact);
+int cast_wave_threads();
+int cast_wave_max_diag();
 
 enum { kQueryState = 0, kQueryCenter = 1, kQueryObserved = 2, kQueryWeight = 3, kQueryDistance = 4,
        kQueryStateGeneric = 5 };

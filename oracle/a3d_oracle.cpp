@@ -477,6 +477,12 @@ uint64_t digestList(const std::vector<V3>& v) {
   for (const V3& c : v) h = h * kDigestMul + digestEntry(c);
   return h;
 }
+// order-independent companion: sum of the per-entry hashes mod 2^64
+uint64_t digestSet(const std::vector<V3>& v) {
+  uint64_t h = 0;
+  for (const V3& c : v) h += digestEntry(c);
+  return h;
+}
 
 }  // namespace
 
@@ -643,7 +649,7 @@ int orc_compute_gains(const orc_caster* c, const orc_eval_params* e, int n_views
                       const double* quat, const int32_t* view_segment, int n_segments,
                       const int32_t* parent, double* gains_out, uint64_t* n_visible_out,
                       uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* n_fold_out,
-                      int n_threads) {
+                      int n_threads, uint64_t* set_digests_out) {
   // view ranges per segment
   std::vector<int> first(n_segments + 1, 0);
   for (int v = 0; v < n_views; ++v) {
@@ -683,6 +689,7 @@ int orc_compute_gains(const orc_caster* c, const orc_eval_params* e, int n_views
     if (n_visible_out) n_visible_out[s] = new_voxels.size();
     if (n_samples_out) n_samples_out[s] = static_cast<uint64_t>(ns);
     if (digests_out) digests_out[s] = digestList(new_voxels);
+    if (set_digests_out) set_digests_out[s] = digestSet(new_voxels);
     uint64_t lookups = 0;
     gains_out[s] = foldGain(*c->map, *e, &new_voxels, &lookups);
     if (n_fold_out) n_fold_out[s] = lookups;
@@ -716,6 +723,12 @@ double orc_gain_from_voxels(const orc_map* m, const orc_eval_params* e, int64_t 
 void orc_bv_contains(const orc_eval_params* e, int64_t n, const double* p, uint8_t* out) {
   for (int64_t i = 0; i < n; ++i)
     out[i] = bvContains(*e, V3{p[3 * i], p[3 * i + 1], p[3 * i + 2]}) ? 1 : 0;
+}
+
+uint64_t orc_digest_set(int64_t n, const double* c) {
+  uint64_t h = 0;
+  for (int64_t i = 0; i < n; ++i) h += digestEntry(V3{c[3 * i], c[3 * i + 1], c[3 * i + 2]});
+  return h;
 }
 
 uint64_t orc_digest(int64_t n, const double* c) {

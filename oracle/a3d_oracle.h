@@ -103,7 +103,7 @@ int orc_compute_gains(const orc_caster* c, const orc_eval_params* e, int n_views
                       const double* quat, const int32_t* view_segment, int n_segments,
                       const int32_t* parent, double* gains_out, uint64_t* n_visible_out,
                       uint64_t* n_samples_out, uint64_t* digests_out,
-                      uint64_t* n_fold_lookups_out, int n_threads);
+                      uint64_t* n_fold_lookups_out, int n_threads, uint64_t* set_digests_out);
 /* computeGainFromVisibleVoxels on an explicit list (n×3 centres) — SimulatedSensorUpdater path.
    Returns gain; n_left (nullable) = list size after the fold's own erasures. */
 double orc_gain_from_voxels(const orc_map* m, const orc_eval_params* e, int64_t n,
@@ -112,6 +112,8 @@ double orc_gain_from_voxels(const orc_map* m, const orc_eval_params* e, int64_t 
 void orc_bv_contains(const orc_eval_params* e, int64_t n, const double* pts, uint8_t* out);
 /* order-sensitive digest of a centre list (shared definition with the product) */
 uint64_t orc_digest(int64_t n, const double* centres);
+/* order-independent companion: sum of the per-entry hashes mod 2^64 */
+uint64_t orc_digest_set(int64_t n, const double* centres);
 
 #ifdef __cplusplus
 }

@@ -83,7 +83,9 @@ def lib():
     L.orc_visible_voxels.argtypes = [vp, C.c_int, vp, vp, vp, i64, P(i64)]
     L.orc_visible_voxels.restype = i64
     L.orc_compute_gains.argtypes = [vp, P(EvalParams), C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
-                                    vp, vp, vp, C.c_int]
+                                    vp, vp, vp, C.c_int, vp]
+    L.orc_digest_set.argtypes = [i64, vp]
+    L.orc_digest_set.restype = C.c_uint64
     L.orc_gain_from_voxels.argtypes = [vp, P(EvalParams), i64, vp, P(i64)]
     L.orc_gain_from_voxels.restype = dbl
     L.orc_bv_contains.argtypes = [P(EvalParams), i64, vp, vp]
@@ -287,12 +289,15 @@ class OracleCaster:
         nsamp = np.zeros(n_segments, np.uint64)
         dig = np.zeros(n_segments, np.uint64)
         fold = np.zeros(n_segments, np.uint64)
+        sdig = np.zeros(n_segments, np.uint64)
         rc = self.L.orc_compute_gains(self.h, C.byref(eparams), n_views, _ptr(pos), _ptr(quat),
                                       _ptr(view_segment), n_segments, _ptr(parent), _ptr(gains),
-                                      _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(fold), n_threads)
+                                      _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(fold), n_threads,
+                                      _ptr(sdig))
         if rc:
             raise ValueError("orc_compute_gains: bad view_segment")
-        return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig, n_fold_lookups=fold)
+        return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig, set_digest=sdig,
+                    n_fold_lookups=fold)
 
 
 def sample_viewpoints(sampling_time, times_ns):
@@ -307,6 +312,11 @@ def bv_contains(eparams, pts):
     out = np.empty(len(pts), np.uint8)
     lib().orc_bv_contains(C.byref(eparams), len(pts), _ptr(pts), _ptr(out))
     return out
+
+
+def digest_set(centres):
+    centres = _pts(centres) if len(centres) else np.zeros((0, 3))
+    return int(lib().orc_digest_set(len(centres), _ptr(centres)))
 
 
 def digest(centres):

@@ -328,3 +328,109 @@ def test_error_codes(capi):
                           view_segment=np.array([1, 0], np.int32), n_segments=2)
     assert e.value.code == -1
     ctx.close()
+
+
+# ---- wavefront kernel (k_cast_wave): same gains / counts / order-independent digest -----------------
+def _wave(ctx, caster, ev, *a, **kw):
+    ctx.set_option("cast_kernel", 2)
+    try:
+        r = ctx.compute_gains(caster, ev, *a, digests=False, **kw)
+    finally:
+        ctx.set_option("cast_kernel", 0)
+    assert ctx.last_cast_kernel == 2
+    return r
+
+
+def _check_wave(got, want):
+    for k in ("n_samples", "n_visible", "set_digest"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("ckind", ["IterativeRayCaster", "SimpleRayCaster"])
+@pytest.mark.parametrize("ekind,kw", [
+    ("VoxelTypeEvaluator", {}),
+    ("VoxelTypeEvaluator", dict(gain_unknown=1.0, gain_free=0.5, gain_occupied=0.25,
+                                bounding_volume=dict(x_min=4, x_max=16, y_min=4, y_max=16, z_min=0.5,
+                                                     z_max=6, rotation=20.0))),
+    ("NaiveEvaluator", {}),
+    ("FrontierEvaluator", dict(accurate_frontiers=True)),
+])
+def test_wave_kernel_cfg1(capi, O, room02, ckind, ekind, kw):
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    caster = ctx.caster(ckind, **CAM_BASE)
+    oc = om.caster(ckind, **CAM_BASE)
+    pos, quat = synth.candidate_views(room02, 64)
+    got = _wave(ctx, caster, ctx.evaluator(ekind, **kw), pos, quat)
+    want = oc.compute_gains(O.eval_params(ekind, **kw), pos, quat, n_threads=8)
+    _check_wave(got, want)
+    assert got["gain"].max() > 0
+    # scan-order kernel agrees on the order-independent digest too
+    ref = ctx.compute_gains(caster, ctx.evaluator(ekind, **kw), pos, quat)
+    assert np.array_equal(ref["set_digest"], want["set_digest"])
+    assert np.array_equal(ref["digest"], want["digest"])
+    ctx.close()
+
+
+def test_wave_kernel_multi_view_mounting_vps8(capi, O):
+    from mav_active_3d_planning_b200 import synth
+    m = synth.room_map(0.2, vps=8)
+    ctx, om = make_pair(capi, O, m)
+    cam = dict(CAM_BASE, mounting_translation=(0.1, -0.05, 0.2), mounting_rotation=(0.9, 0.1, -0.2, 0.3))
+    pos, quat = synth.candidate_views(m, 20, seed=13)
+    pos[1::2] = pos[0::2]
+    quat[1::2] = quat[0::2]
+    seg = np.repeat(np.arange(4, dtype=np.int32), 5)
+    for ckind in ("IterativeRayCaster", "SimpleRayCaster"):
+        caster = ctx.caster(ckind, **cam)
+        oc = om.caster(ckind, **cam)
+        got = _wave(ctx, caster, ctx.evaluator("VoxelTypeEvaluator"), pos, quat, seg, 5)
+        want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos, quat, seg, 5)
+        _check_wave(got, want)
+        assert got["n_visible"][4] == 0
+    ctx.close()
+
+
+def test_wave_kernel_cfg2_and_cfg4(capi, O, room01):
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room01)
+    pos, quat = synth.candidate_views(room01, 4096)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    oc = om.caster("IterativeRayCaster", **CAM_BASE)
+    ev = ctx.evaluator("VoxelTypeEvaluator")
+    got = _wave(ctx, caster, ev, pos[:48], quat[:48])
+    want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos[:48], quat[:48], n_threads=8)
+    _check_wave(got, want)
+    # full 4096-segment batch: wavefront kernel == scan-order kernel on every segment
+    full_w = _wave(ctx, caster, ev, pos, quat)
+    full_s = ctx.compute_gains(caster, ev, pos, quat)
+    _check_wave(full_w, full_s)
+    # cfg4: 640x480 f=320, 8 m, both casters (126x103 rays) and one literal 640x480-ray view
+    for kind in ("SimpleRayCaster", "IterativeRayCaster"):
+        c4 = ctx.caster(kind, **CAM_CFG4)
+        o4 = om.caster(kind, **CAM_CFG4)
+        _check_wave(_wave(ctx, c4, ev, pos[:6], quat[:6]),
+                    o4.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos[:6], quat[:6], n_threads=6))
+    kw = dict(CAM_CFG4, downsampling_factor=0.19)
+    c4 = ctx.caster("IterativeRayCaster", **kw)
+    o4 = om.caster("IterativeRayCaster", **kw)
+    _check_wave(_wave(ctx, c4, ev, pos[:1], quat[:1]),
+                o4.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos[:1], quat[:1]))
+    ctx.close()
+
+
+def test_wave_kernel_empty_map_and_far_poses(capi, O):
+    """Unallocated space and poses beyond the 20-bit voxel-key range (scan-order re-evaluation)."""
+    ctx = capi.Context(0)
+    ctx.map_config(0.2, 16)
+    om = O.OracleMap(0.2, 16)
+    pos = np.array([[1.0, 2.0, 3.0], [2.0e5, -3.0e5, 10.0], [104857.0, 0.3, 0.2]])
+    quat = np.array([[1.0, 0, 0, 0], [0.6, 0, 0, 0.8], [1.0, 0, 0, 0]])
+    for ckind in ("IterativeRayCaster", "SimpleRayCaster"):
+        caster = ctx.caster(ckind, **CAM_BASE)
+        oc = om.caster(ckind, **CAM_BASE)
+        got = _wave(ctx, caster, ctx.evaluator("VoxelTypeEvaluator"), pos, quat)
+        want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos, quat)
+        _check_wave(got, want)
+    ctx.close()
