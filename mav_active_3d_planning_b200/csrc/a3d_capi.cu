@@ -801,7 +801,7 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   v.mount_q = Q4{p->mount_q[0], p->mount_q[1], p->mount_q[2], p->mount_q[3]};
   v.ray_step = info.ray_step;
   v.ray_length = p->ray_length;
-  for (int t = 0; t <= n_sections; ++t) v.split[t] = split[t];
+  for (size_t t = 0; t < split.size(); ++t) v.split[t] = split[t];
   *out = c;
   return A3D_OK;
 }

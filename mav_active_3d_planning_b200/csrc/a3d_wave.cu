@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         P0.z = __dadd_rn(P0.z, mt.z);
         q = qmul(q, c.mount_q);
       }
-      // per-view init: ray table, start sections, record flags
+      // per-view init: ray table, start sections, record flags (after the previous view's fix-up)
+      __syncthreads();
       for (int r = threadIdx.x; r < n_rays; r += kWaveThreads) {
         if (ITER) {
           table[r] = 0u;
