@@ -85,7 +85,12 @@ struct a3d_ctx {
   DevBuf<HashEntry> d_table;
   std::vector<Key3> slot_key;  // slot → block index (valid for allocated slots)
   float* d_dist = nullptr;     // padded cubes, P^3 floats per slot
-  uint8_t* d_meta = nullptr;   // padded cubes, P^3 bytes per slot
+  uint32_t* d_mword = nullptr; // meta words, vps^3 per slot
+  std::vector<int32_t> h_dir;  // dense directory over [dir_lo, dir_lo + dir_n)
+  DevBuf<int32_t> d_dir;
+  int32_t dir_lo[3] = {0, 0, 0};
+  uint32_t dir_n[3] = {0, 0, 0};
+  bool dir_enabled = false;
   float* d_weight = nullptr;   // vps^3 floats per slot
   size_t slab_slots = 0;
   bool has_weight = false;
@@ -119,7 +124,12 @@ struct a3d_ctx {
     m.table = d_table.p;
     m.dist = d_dist;
     m.weight = has_weight ? d_weight : nullptr;
-    m.meta = d_meta;
+    m.mword = d_mword;
+    m.dir = dir_enabled ? d_dir.p : nullptr;
+    for (int k = 0; k < 3; ++k) {
+      m.dir_lo[k] = dir_lo[k];
+      m.dir_n[k] = dir_n[k];
+    }
     m.P = P;
     m.P3 = P3;
     m.mask = static_cast<uint32_t>(h_table.size() - 1);
@@ -143,6 +153,7 @@ struct a3d_caster {
   double* d_dseq = nullptr;
   int32_t* d_kcount = nullptr;
   int32_t* d_seg_end = nullptr;
+  int32_t* d_units = nullptr;  // unit_diag[n_units] followed by unit_i0[n_units]
   CasterView view{};
 };
 
@@ -181,10 +192,62 @@ void table_rebuild(a3d_ctx* ctx, size_t min_entries) {
     table_insert(ctx->h_table, kv.first.x, kv.first.y, kv.first.z, kv.second);
 }
 
+// Dense directory over the bounding box of the allocated block indices (grown with slack so that a
+// moving frontier does not rebuild it every step).  Disabled when the box exceeds 64 Mi entries.
+void dir_rebuild(a3d_ctx* ctx) {
+  ctx->dir_enabled = false;
+  if (ctx->slots.empty()) {
+    ctx->h_dir.clear();
+    return;
+  }
+  int32_t lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+  for (const auto& kv : ctx->slots) {
+    const int32_t c[3] = {kv.first.x, kv.first.y, kv.first.z};
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = std::min(lo[k], c[k]);
+      hi[k] = std::max(hi[k], c[k]);
+    }
+  }
+  bool covered = !ctx->h_dir.empty();
+  for (int k = 0; k < 3 && covered; ++k)
+    covered = lo[k] >= ctx->dir_lo[k] &&
+              static_cast<int64_t>(hi[k]) < static_cast<int64_t>(ctx->dir_lo[k]) + ctx->dir_n[k];
+  if (!covered) {
+    double total = 1.0;
+    for (int k = 0; k < 3; ++k) {
+      const int64_t ext = static_cast<int64_t>(hi[k]) - lo[k] + 1;
+      const int64_t slack = std::max<int64_t>(2, ext / 8);
+      ctx->dir_lo[k] = static_cast<int32_t>(std::max<int64_t>(INT32_MIN / 2, lo[k] - slack));
+      ctx->dir_n[k] = static_cast<uint32_t>(ext + 2 * slack);
+      total *= static_cast<double>(ctx->dir_n[k]);
+    }
+    if (total > 64.0 * 1024 * 1024) {
+      ctx->h_dir.clear();
+      return;
+    }
+  }
+  const size_t n = static_cast<size_t>(ctx->dir_n[0]) * ctx->dir_n[1] * ctx->dir_n[2];
+  ctx->h_dir.assign(n, -1);
+  for (const auto& kv : ctx->slots) {
+    const size_t ux = static_cast<size_t>(kv.first.x - ctx->dir_lo[0]);
+    const size_t uy = static_cast<size_t>(kv.first.y - ctx->dir_lo[1]);
+    const size_t uz = static_cast<size_t>(kv.first.z - ctx->dir_lo[2]);
+    ctx->h_dir[(uz * ctx->dir_n[1] + uy) * ctx->dir_n[0] + ux] = kv.second;
+  }
+  ctx->dir_enabled = true;
+}
+
+// Uploads the hash table and (re)builds + uploads its directory.
 int table_upload(a3d_ctx* ctx) {
   CK(ctx->d_table.reserve(ctx->h_table.size()));
   CK(cudaMemcpyAsync(ctx->d_table.p, ctx->h_table.data(), ctx->h_table.size() * sizeof(HashEntry),
                      cudaMemcpyHostToDevice, ctx->stream));
+  dir_rebuild(ctx);
+  if (ctx->dir_enabled) {
+    CK(ctx->d_dir.reserve(ctx->h_dir.size()));
+    CK(cudaMemcpyAsync(ctx->d_dir.p, ctx->h_dir.data(), ctx->h_dir.size() * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  }
   return A3D_OK;
 }
 
@@ -208,7 +271,7 @@ int slab_reserve(a3d_ctx* ctx, size_t n_slots, bool want_weight) {
     const size_t cap = std::max<size_t>(std::max<size_t>(n_slots, ctx->slab_slots * 2), 64);
     int rc = slab_grow(ctx, &ctx->d_dist, ctx->slab_slots, cap, p3);
     if (rc) return rc;
-    rc = slab_grow(ctx, &ctx->d_meta, ctx->slab_slots, cap, p3);
+    rc = slab_grow(ctx, &ctx->d_mword, ctx->slab_slots, cap, nv);
     if (rc) return rc;
     if (ctx->d_weight) {
       rc = slab_grow(ctx, &ctx->d_weight, ctx->slab_slots, cap, nv);
@@ -253,7 +316,7 @@ int refresh_blocks(a3d_ctx* ctx, const std::vector<int32_t>& affected) {
                      cudaMemcpyHostToDevice, ctx->stream));
   const MapView mv = ctx->view();
   launch_refresh_aprons(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_nbr.p, ctx->d_dist);
-  launch_build_meta(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_meta);
+  launch_build_meta(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword);
   ctx->launches += 2;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
@@ -528,7 +591,8 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->d_dist) cudaFree(ctx->d_dist);
   if (ctx->d_weight) cudaFree(ctx->d_weight);
-  if (ctx->d_meta) cudaFree(ctx->d_meta);
+  if (ctx->d_mword) cudaFree(ctx->d_mword);
+  ctx->d_dir.release();
   ctx->d_table.release();
   ctx->st_aff_slots.release();
   ctx->st_aff_nbr.release();
@@ -780,6 +844,24 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&c->d_dseq), dseq.data(), dseq.size() * 8);
   if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&c->d_kcount), kcount.data(), kcount.size() * 4);
   if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&c->d_seg_end), seg_end.data(), seg_end.size() * 4);
+  // leaf-supply units of the wavefront kernel
+  std::vector<int32_t> units;
+  int n_units = (n_rays + 31) / 32;
+  if (p->kind == A3D_CASTER_ITERATIVE) {
+    std::vector<int32_t> ud, ui;
+    for (int dg = 0; dg < info.c_res_x + info.c_res_y - 1; ++dg) {
+      const int i_lo = std::max(0, dg - (info.c_res_y - 1)), i_hi = std::min(info.c_res_x - 1, dg);
+      for (int i0 = i_lo; i0 <= i_hi; i0 += 32) {
+        ud.push_back(dg);
+        ui.push_back(i0);
+      }
+    }
+    n_units = static_cast<int>(ud.size());
+    units = ud;
+    units.insert(units.end(), ui.begin(), ui.end());
+    if (e == cudaSuccess)
+      e = up(reinterpret_cast<void**>(&c->d_units), units.data(), units.size() * 4);
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     a3d_caster_destroy(c);
@@ -799,6 +881,9 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   v.seg_end = c->d_seg_end;
   for (int i = 0; i < 3; ++i) v.mount_t[i] = p->mount_t[i];
   v.mount_q = Q4{p->mount_q[0], p->mount_q[1], p->mount_q[2], p->mount_q[3]};
+  v.n_units = n_units;
+  v.unit_diag = c->d_units;
+  v.unit_i0 = c->d_units ? c->d_units + n_units : nullptr;
   v.ray_step = info.ray_step;
   v.ray_length = p->ray_length;
   for (size_t t = 0; t < split.size(); ++t) v.split[t] = split[t];
@@ -813,6 +898,7 @@ void a3d_caster_destroy(a3d_caster* c) {
   if (c->d_dseq) cudaFree(c->d_dseq);
   if (c->d_kcount) cudaFree(c->d_kcount);
   if (c->d_seg_end) cudaFree(c->d_seg_end);
+  if (c->d_units) cudaFree(c->d_units);
   delete c;
 }
 

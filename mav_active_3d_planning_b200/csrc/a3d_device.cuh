@@ -20,9 +20,14 @@
 //           ((z+1)*P + (y+1))*P + (x+1).  The interior is the block's ESDF distances; the one-voxel
 //           apron mirrors the 26 neighbouring blocks (kUnobservedBits where the neighbour is not
 //           allocated), so the 8 corners of any interpolation cell are addressed inside ONE block.
-//   meta    per slot P^3 bytes, same indexing: bits 1:0 class of the interpolation cell whose base
-//           (lowest) corner is this voxel, bits 3:2 exact voxel state at this voxel's centre,
-//           bit 4 observed.  Built on the device after every delta (k_build_meta).
+//   mword   per slot vps^3 32-bit meta words (voxel linear order x + vps*(y + vps*z)): bits 2c+1:2c =
+//           class of the interpolation cell whose base corner is voxel - (c&1, c>>1&1, c>>2&1), c in
+//           0..7, i.e. the 8 cells a point inside this voxel can interpolate in; bits 17:16 exact
+//           voxel state at this voxel's centre; bit 18 observed.  One load per sample serves both
+//           getVoxelState and the evaluator's lookup of the emitted centre.  Built on the device
+//           after every delta (k_build_meta).
+//   dir     dense directory of slots over the bounding box of allocated block indices, an
+//           accelerator in front of the hash (1 load, no probe loop); absent for huge extents
 //   weight  per slot vps^3 floats (TSDF weights, nearest-voxel reads only)
 #pragma once
 
@@ -47,9 +52,12 @@ struct HashEntry {  // 16 B, one LDG.128 per probe
 
 struct MapView {
   const HashEntry* __restrict__ table;
-  const float* __restrict__ dist;    // padded slab
-  const uint8_t* __restrict__ meta;  // padded slab
-  const float* __restrict__ weight;  // unpadded TSDF weights slab or nullptr
+  const float* __restrict__ dist;      // padded slab
+  const uint32_t* __restrict__ mword;  // meta words, vps^3 per slot
+  const float* __restrict__ weight;    // unpadded TSDF weights slab or nullptr
+  const int32_t* __restrict__ dir;     // block directory or nullptr
+  int32_t dir_lo[3];
+  uint32_t dir_n[3];
   uint32_t mask;                     // table capacity - 1
   int32_t vps;
   int32_t nv;                        // vps^3
@@ -85,6 +93,13 @@ __device__ __forceinline__ uint32_t hash3(int x, int y, int z) {
 // Block index → slab slot, or -1.  Open addressing, linear probing, no tombstones (the host
 // rebuilds the table on removal).
 __device__ __forceinline__ int find_slot(const MapView& m, int bx, int by, int bz) {
+  if (m.dir) {
+    const uint32_t ux = static_cast<uint32_t>(bx - m.dir_lo[0]);
+    const uint32_t uy = static_cast<uint32_t>(by - m.dir_lo[1]);
+    const uint32_t uz = static_cast<uint32_t>(bz - m.dir_lo[2]);
+    if (ux >= m.dir_n[0] || uy >= m.dir_n[1] || uz >= m.dir_n[2]) return -1;
+    return __ldg(m.dir + (static_cast<size_t>(uz) * m.dir_n[1] + uy) * m.dir_n[0] + ux);
+  }
   uint32_t h = hash3(bx, by, bz) & m.mask;
 #pragma unroll 1
   for (;;) {
@@ -254,32 +269,40 @@ static __device__ __noinline__ int voxel_state_generic(const MapView& m, float p
 }
 
 // ---- fast path ----------------------------------------------------------------------------------
+constexpr uint32_t kWordNoBlock = 0x00020000u;  // centre state UNKNOWN, not observed, all cells UNKNOWN
+
 // State of the float point p whose block index b, block origin and slot (= find_slot(b), may be
 // < 0) the caller already has.  Uses the cell class when it is definite, else the 8 padded-cube
-// corners; falls back to the generic path for artefact indices.
+// corners; falls back to the generic path for artefact indices.  Also returns the voxel index v the
+// point falls in and that voxel's meta word (valid when the return value of *v_ok is true).
 __device__ __forceinline__ int voxel_state_in_block(const MapView& m, const CenterTables& ct,
                                                     const float (&p)[3], const int (&b)[3],
-                                                    const float (&origin)[3], int slot) {
-  if (slot < 0) return 2;
-  int v[3];
+                                                    const float (&origin)[3], int slot, int (&v)[3],
+                                                    uint32_t* word_out, bool* v_ok) {
   bool artefact = false;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     v[k] = grid_index(__fsub_rn(p[k], origin[k]), m.vs_inv_f);
-    artefact |= (v[k] < 0) | (v[k] >= m.vps);
+    artefact |= static_cast<unsigned>(v[k]) >= static_cast<unsigned>(m.vps);
   }
+  *v_ok = !artefact;
+  *word_out = kWordNoBlock;
+  if (slot < 0) return 2;
   if (artefact) return voxel_state_generic(m, p[0], p[1], p[2]);
-  int base[3];
+  int sc = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float centre = __fadd_rn(origin[k], ct.f[v[k] + 1]);
-    base[k] = v[k] - ((__fsub_rn(p[k], centre) < 0.0f) ? 1 : 0);
+    sc |= (__fsub_rn(p[k], centre) < 0.0f) ? (1 << k) : 0;
   }
-  const size_t at = padded_index(m, slot, base[0], base[1], base[2]);
-  const int cls = __ldg(m.meta + at) & 3;
+  const uint32_t word =
+      __ldg(m.mword + static_cast<size_t>(slot) * m.nv + (v[2] * m.vps + v[1]) * m.vps + v[0]);
+  *word_out = word;
+  const int cls = (word >> (2 * sc)) & 3;
   if (cls != kCellMixed) return cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
+  const int base[3] = {v[0] - (sc & 1), v[1] - ((sc >> 1) & 1), v[2] - (sc >> 2)};
   float d[8], o[3];
-  const float* __restrict__ dp = m.dist + at;
+  const float* __restrict__ dp = m.dist + padded_index(m, slot, base[0], base[1], base[2]);
   const int P = m.P, PP = m.P * m.P;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -304,7 +327,10 @@ __device__ __forceinline__ int voxel_state(const MapView& m, const CenterTables&
     b[k] = grid_index(p[k], m.bs_inv_f);
     origin[k] = origin_point(b[k], m.bs_f);
   }
-  return voxel_state_in_block(m, ct, p, b, origin, find_slot(m, b[0], b[1], b[2]));
+  int v[3];
+  uint32_t word;
+  bool v_ok;
+  return voxel_state_in_block(m, ct, p, b, origin, find_slot(m, b[0], b[1], b[2]), v, &word, &v_ok);
 }
 
 // getVoxelCenter given the block index / origin of the point; v_out: unclamped voxel index.
@@ -352,7 +378,8 @@ __device__ __forceinline__ bool is_observed(const MapView& m, const D3& p) {
   int v[3];
   const int slot = nearest_voxel(m, p, v);
   if (slot < 0) return false;
-  return (__ldg(m.meta + padded_index(m, slot, v[0], v[1], v[2])) >> 4) & 1;
+  return (__ldg(m.mword + static_cast<size_t>(slot) * m.nv + (v[2] * m.vps + v[1]) * m.vps + v[0]) >>
+          18) & 1;
 }
 __device__ __forceinline__ double voxel_weight(const MapView& m, const D3& p) {
   if (!m.weight) return 0.0;
@@ -374,8 +401,13 @@ __device__ __forceinline__ int centre_state(const MapView& m, const CenterTables
     return voxel_state(m, ct, c) | (is_observed(m, c) ? 4 : 0);
   }
   if (slot < 0) return 2;
-  const int meta = __ldg(m.meta + padded_index(m, slot, v[0], v[1], v[2]));
-  return ((meta >> 2) & 3) | ((meta >> 2) & 4);
+  const uint32_t word =
+      __ldg(m.mword + static_cast<size_t>(slot) * m.nv + (v[2] * m.vps + v[1]) * m.vps + v[0]);
+  return static_cast<int>((word >> 16) & 7);
+}
+// the same from an already loaded meta word of that voxel
+__device__ __forceinline__ int centre_state_from_word(uint32_t word) {
+  return static_cast<int>((word >> 16) & 7);
 }
 
 struct EvalView {

@@ -97,72 +97,84 @@ void launch_refresh_aprons(cudaStream_t st, const MapView& m, int n, const int32
   k_refresh_aprons<<<std::min(n, 148 * 8), 256, 0, st>>>(m, n, slots_dev, nbr_dev, dist_slab);
 }
 
-// Meta byte per padded voxel of every affected block.
-//   bits 1:0  class of the cell with base corner here: UNKNOWN if any of the 8 corners is
-//             unobserved/missing; FREE / OCCUPIED only when every corner is on the same side of the
-//             voxel size by more than the worst-case rounding error of interp8 (DESIGN.md "cell
-//             class margin"), so the class equals the interpolated test for every point of the cell;
-//             MIXED otherwise (the kernel interpolates).
-//   bits 3:2  exact state at the voxel centre, evaluated with the literal generic path
-//   bit 4     observed
-__global__ void k_build_meta(MapView m, int n, const int32_t* __restrict__ slots,
-                             const int32_t* __restrict__ block_idx, uint8_t* __restrict__ meta_slab) {
+// Class of the interpolation cell whose base corner is padded voxel i of the block at dp:
+// UNKNOWN if any of the 8 corners is unobserved/missing; FREE / OCCUPIED only when every corner is
+// on the same side of the voxel size by more than the worst-case rounding error of interp8
+// (DESIGN.md "cell class margin"), so the class equals the interpolated test for every point of
+// the cell; MIXED otherwise (the kernels interpolate).
+__device__ __forceinline__ int cell_class(const MapView& m, const float* __restrict__ dp, int i) {
   const int P = m.P, PP = m.P * m.P;
+  bool all_obs = true, any_nan = false;
+  float mn = 3.0e38f, mx = -3.0e38f, amax = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float d = dp[i + ((c >> 2) & 1) + ((c >> 1) & 1) * P + (c & 1) * PP];
+    all_obs &= (__float_as_uint(d) != kUnobservedBits);
+    any_nan |= (d != d);
+    mn = fminf(mn, d);
+    mx = fmaxf(mx, d);
+    amax = fmaxf(amax, fabsf(d));
+  }
+  if (!all_obs) return kCellUnknown;
+  const double margin = 1.0e-4 * fmax(static_cast<double>(amax), m.c_vs);
+  if (any_nan || !(amax < 1.0e30f)) return kCellMixed;
+  if (static_cast<double>(mn) - margin >= m.c_vs) return kCellFree;
+  if (static_cast<double>(mx) + margin < m.c_vs) return kCellOccupied;
+  return kCellMixed;
+}
+
+// Meta word per voxel of every affected block (layout: a3d_device.cuh header).  One CTA per block;
+// the (vps+1)^3 cell classes are staged in shared memory when they fit.
+__global__ void k_build_meta(MapView m, int n, const int32_t* __restrict__ slots,
+                             const int32_t* __restrict__ block_idx, uint32_t* __restrict__ mword_slab,
+                             int use_smem) {
+  extern __shared__ uint8_t s_cls[];
+  const int P = m.P, PP = m.P * m.P, vps = m.vps;
   for (int a = blockIdx.x; a < n; a += gridDim.x) {
     const int slot = slots[a];
     const float* __restrict__ dp = m.dist + static_cast<size_t>(slot) * m.P3;
-    for (int i = threadIdx.x; i < m.P3; i += blockDim.x) {
-      const int z = i / PP - 1, rem = i % PP, y = rem / P - 1, x = rem % P - 1;
-      int cls = kCellUnknown;
-      if (x < m.vps && y < m.vps && z < m.vps) {
-        bool all_obs = true, any_nan = false;
-        float mn = 3.0e38f, mx = -3.0e38f, amax = 0.0f;
+    if (use_smem) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < m.P3; i += blockDim.x) {
+        const int z = i / PP, rem = i % PP, y = rem / P, x = rem % P;  // padded coords (base + 1)
+        s_cls[i] = (x <= vps && y <= vps && z <= vps) ? cell_class(m, dp, i) : kCellUnknown;
+      }
+      __syncthreads();
+    }
+    const int32_t* bi = block_idx + 3 * a;
+    for (int lin = threadIdx.x; lin < m.nv; lin += blockDim.x) {
+      const int z = lin / (vps * vps), rem = lin % (vps * vps), y = rem / vps, x = rem % vps;
+      uint32_t word = 0;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float d = dp[i + ((c >> 2) & 1) + ((c >> 1) & 1) * P + (c & 1) * PP];
-          all_obs &= (__float_as_uint(d) != kUnobservedBits);
-          any_nan |= (d != d);
-          mn = fminf(mn, d);
-          mx = fmaxf(mx, d);
-          amax = fmaxf(amax, fabsf(d));
-        }
-        if (all_obs) {
-          const double margin = 1.0e-4 * fmax(static_cast<double>(amax), m.c_vs);
-          if (any_nan || !(amax < 1.0e30f)) {
-            cls = kCellMixed;
-          } else if (static_cast<double>(mn) - margin >= m.c_vs) {
-            cls = kCellFree;
-          } else if (static_cast<double>(mx) + margin < m.c_vs) {
-            cls = kCellOccupied;
-          } else {
-            cls = kCellMixed;
-          }
-        }
+      for (int c = 0; c < 8; ++c) {
+        // cell with base = voxel - (c&1, c>>1&1, c>>2&1); padded index of the base = base + 1
+        const int i = ((z + 1 - (c >> 2)) * P + (y + 1 - ((c >> 1) & 1))) * P + (x + 1 - (c & 1));
+        const int cls = use_smem ? s_cls[i] : cell_class(m, dp, i);
+        word |= static_cast<uint32_t>(cls) << (2 * c);
       }
-      int centre = 2, obs = 0;
-      if (x >= 0 && x < m.vps && y >= 0 && y < m.vps && z >= 0 && z < m.vps) {
-        obs = __float_as_uint(dp[i]) != kUnobservedBits;
-        // centre exactly as getVoxelCenter forms it (voxblox.cpp:72-79), cast like getVoxelState
-        const int32_t* bi = block_idx + 3 * a;
-        const double cx = __dadd_rn(static_cast<double>(origin_point(bi[0], m.bs_f)),
-                                    static_cast<double>(center_point(x, m.vs_f)));
-        const double cy = __dadd_rn(static_cast<double>(origin_point(bi[1], m.bs_f)),
-                                    static_cast<double>(center_point(y, m.vs_f)));
-        const double cz = __dadd_rn(static_cast<double>(origin_point(bi[2], m.bs_f)),
-                                    static_cast<double>(center_point(z, m.vs_f)));
-        centre = voxel_state_generic(m, __double2float_rn(cx), __double2float_rn(cy),
-                                     __double2float_rn(cz));
-      }
-      meta_slab[static_cast<size_t>(slot) * m.P3 + i] =
-          static_cast<uint8_t>(cls | (centre << 2) | (obs << 4));
+      const int obs = __float_as_uint(dp[((z + 1) * P + (y + 1)) * P + (x + 1)]) != kUnobservedBits;
+      // centre exactly as getVoxelCenter forms it (voxblox.cpp:72-79), cast like getVoxelState
+      const double cx = __dadd_rn(static_cast<double>(origin_point(bi[0], m.bs_f)),
+                                  static_cast<double>(center_point(x, m.vs_f)));
+      const double cy = __dadd_rn(static_cast<double>(origin_point(bi[1], m.bs_f)),
+                                  static_cast<double>(center_point(y, m.vs_f)));
+      const double cz = __dadd_rn(static_cast<double>(origin_point(bi[2], m.bs_f)),
+                                  static_cast<double>(center_point(z, m.vs_f)));
+      const int centre = voxel_state_generic(m, __double2float_rn(cx), __double2float_rn(cy),
+                                             __double2float_rn(cz));
+      word |= static_cast<uint32_t>(centre) << 16;
+      word |= static_cast<uint32_t>(obs) << 18;
+      mword_slab[static_cast<size_t>(slot) * m.nv + lin] = word;
     }
   }
 }
 
 void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
-                       const int32_t* block_idx_dev, uint8_t* meta_slab) {
+                       const int32_t* block_idx_dev, uint32_t* mword_slab) {
   if (n <= 0) return;
-  k_build_meta<<<std::min(n, 148 * 8), 256, 0, st>>>(m, n, slots_dev, block_idx_dev, meta_slab);
+  const int use_smem = m.P3 <= 40 * 1024;
+  k_build_meta<<<std::min(n, 148 * 8), 256, use_smem ? m.P3 : 0, st>>>(m, n, slots_dev, block_idx_dev,
+                                                                       mword_slab, use_smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -341,8 +353,10 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
               origin[a] = origin_point(bi[a], m.bs_f);
             }
             const int slot = find_slot(m, bi[0], bi[1], bi[2]);
-            int st = 1;
-            if (valid) st = voxel_state_in_block(m, ct, pf, bi, origin, slot);
+            int st = 1, vs_i[3];
+            uint32_t word;
+            bool v_ok;
+            if (valid) st = voxel_state_in_block(m, ct, pf, bi, origin, slot, vs_i, &word, &v_ok);
             const unsigned occ = __ballot_sync(kFull, valid && st == 0);
             int n_emit = min(32, K - k0);
             if (occ) {

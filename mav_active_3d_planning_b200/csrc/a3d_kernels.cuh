@@ -21,6 +21,12 @@ struct CasterView {
   Q4 mount_q;
   double ray_step, ray_length;
   double split[33];  // c_split_distances_ (iterative)
+  // leaf-supply units of k_cast_wave: iterative → unit u covers rays (i, diag-i), i in
+  // [unit_i0[u], unit_i0[u]+32) of anti-diagonal unit_diag[u]; simple → rays [32u, 32u+32)
+  int32_t n_units;
+  int32_t _pad2;
+  const int32_t* __restrict__ unit_diag;
+  const int32_t* __restrict__ unit_i0;
 };
 
 struct Batch {
@@ -55,7 +61,7 @@ void launch_apply_blocks(cudaStream_t st, const MapView& m, int n, const int32_t
 void launch_refresh_aprons(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                            const int32_t* nbr_dev /*n×27*/, float* dist_slab);
 void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
-                       const int32_t* block_idx_dev /*n×3*/, uint8_t* meta_slab);
+                       const int32_t* block_idx_dev /*n×3*/, uint32_t* mword_slab);
 void launch_point_query(cudaStream_t st, const MapView& m, int what, long long n, const double* pts,
                         void* out0, void* out1);
 void launch_bv_contains(cudaStream_t st, const EvalView& e, long long n, const double* pts,

@@ -4,25 +4,30 @@
 // order-independent digest of the stored list, but mapped lane-per-ray instead of warp-per-ray:
 //
 //  * One CTA of 2 warps owns a trajectory segment at a time (atomic work counter).
-//  * Every lane marches its OWN ray: the previous raw list entry it needs for the adjacent-unique
-//    test (camera_model.cpp:58) is in its own registers, the sample distance is accumulated in a
-//    register exactly like the reference does (`distance += p_ray_step_`), and no shuffle or ballot
-//    is needed per sample.  Voxel identity is a packed integer key (block*vps+voxel per axis, 20
-//    bits each) that is equal iff the reference's double centre triples are equal (fp artefact
-//    indices are canonicalised or flagged, see make_key).
+//  * Every lane marches its OWN ray part: the previous raw list entry it needs for the
+//    adjacent-unique test (camera_model.cpp:58) is in its own registers, the sample distance is
+//    accumulated in a register exactly like the reference does (`distance += p_ray_step_`), and no
+//    shuffle or ballot is needed per sample.  Voxel identity is the integer triple
+//    g = block*vps + voxel (+ artefact flags), equal iff the reference's double centre triples are
+//    equal (fp artefact indices are canonicalised or flagged, see make_ident_slow).  Lanes are
+//    persistent: when a ray ends (range or OCCUPIED hit) the lane pulls the next ready ray, so
+//    occlusion does not idle lanes.
 //  * What couples rays — `std::unique` across the boundary between two consecutive rays / views —
 //    is repaired afterwards: each ray part records its first and last key and what its first entry
-//    contributed; a scan-order pass (fix_up) un-counts first entries that equal the previous
+//    contributed; a scan-order pass (fix-up) un-counts first entries that equal the previous
 //    emitted entry.
 //  * IterativeRayCaster (iterative_ray_caster.cpp:48-119): the ray table makes ray (i,j) depend on
-//    rays (i'<=i, j'<=j) only, so rays on one anti-diagonal are independent.  Warp 0 ("scheduler")
-//    walks the anti-diagonals, casts the rays that start before the last section only up to
-//    c_split_distances_[n-1] — the part that decides every markNeighboringRays call — and applies
-//    their marks in scan order with last-writer-wins resolved by a per-entry writer index.  Rays
-//    whose entry reads n-1 (fresh last-section starts AND survivors of warp 0, whose own cell gets
-//    marked n-1) are cast through the last section by warp 1 ("leaf") with persistent lanes that
-//    pull a new ray as soon as theirs ends, so occlusion does not idle lanes.
-//  * SimpleRayCaster (simple_ray_caster.cpp:32-66): all rays independent; both warps are leaf warps.
+//    rays (i'<=i, j'<=j) only, so rays on one anti-diagonal are independent.  Warp 0 walks the
+//    anti-diagonals: it casts the rays that start before the last section only up to
+//    c_split_distances_[n-1] — the part that decides every markNeighboringRays call ("marking
+//    parts") — and applies their marks in scan order, last-writer-wins resolved by a per-entry
+//    writer index.  Every ray whose table entry then reads n-1 (fresh last-section starts AND
+//    survivors of the marking parts, whose own cell gets marked n-1) has its last section cast as a
+//    "leaf part".  Leaf parts come from a shared supply (one unit = up to 32 rays of a finished
+//    anti-diagonal); warp 1 only casts leaf parts, warp 0 fills the lanes its marking parts leave
+//    idle with leaf parts too.
+//  * SimpleRayCaster (simple_ray_caster.cpp:32-66): all rays independent; both warps cast leaf
+//    parts (whole rays).
 #include <algorithm>
 
 #include "../../include/a3d.h"
@@ -34,21 +39,32 @@ namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kWaveThreads = 64;
-constexpr uint64_t kNoKey = ~0ull;          // "no previous entry"
+constexpr uint64_t kNoKey = ~0ull;  // "no entry"
 constexpr uint64_t kKeyOverflow = 1ull << 63;
 constexpr int kKeyBits = 20, kKeyBias = 1 << 19;
 constexpr int kCatNone = 7;
+constexpr int kNoIdent = INT32_MIN;
 #ifndef A3D_WAVE_MIN_BLOCKS
 #define A3D_WAVE_MIN_BLOCKS 10  // resident 2-warp CTAs per SM the register allocation must allow
 #endif
+constexpr int kPendCap = 96;    // per-warp ring of ready rays (top-up adds <= 32 while count <= 64)
+constexpr int kMarkCap = 1024;  // max rays of one anti-diagonal (min(c_res_x, c_res_y))
 
 // info byte of a ray-part record: bits 2:0 category counted for the first entry (kCatNone: not
-// counted), bit 3: part emitted at least one entry
+// counted), bit 3: part emitted at least one entry, bit 4: its first entry was kept (counted in
+// n_visible)
 struct Records {
   unsigned long long* first_key;   // [2][n_rays]
   unsigned long long* last_key;    // [2][n_rays]
   unsigned long long* first_hash;  // [2][n_rays] (digest mode only)
   uint8_t* info;                   // [2][n_rays]
+};
+
+struct WaveScratch {
+  uint32_t* table;     // per CTA: n_rays entries (writer+1) << 8 | uint8(value)
+  uint8_t* start_s;    // per CTA: original start section of rays cast as marking parts, 0xFF none
+  Records rec;         // per CTA
+  size_t rays_stride;  // n_rays rounded up (elements) per CTA
 };
 
 struct LaneCounters {
@@ -58,48 +74,44 @@ struct LaneCounters {
   unsigned inexact;
 };
 
-// Packed voxel identity of getVoxelCenter's result for block index b, unclamped voxel index v.
-// Two entries have equal keys iff their centre doubles (voxblox.cpp:72-79) are equal:
-//  - v in [0,vps) on every axis (canonical): the centre is a function of g = b*vps+v alone;
-//  - an artefact index (v = -1, vps, ...) names the same voxel as (b', v mod vps); its centre double
-//    is compared with that voxel's canonical centre and the axis is flagged if they differ, so a
-//    flagged key only equals keys built from the very same (b, v).
-__device__ __noinline__ uint64_t make_key_slow(const MapView& m, const CenterTables& ct,
-                                               const int (&b)[3], const int (&v)[3]) {
-  uint64_t key = 0;
+// Identity of an emitted list entry: g[k] = b[k]*vps + v[k]; flags bit k: axis k keeps a raw artefact
+// voxel index (v = -1 or vps) whose centre double differs from the canonical voxel's.
+struct Ident {
+  int g0, g1, g2, flags;
+};
+
+// Artefact voxel indices (getGridIndexFromPoint lands one voxel outside the block because of the
+// float block-index rounding): per axis, name the voxel canonically when its centre double
+// (voxblox.cpp:72-79) equals the canonical voxel's centre double, else keep it raw and flag it.
+__device__ __noinline__ Ident make_ident_slow(const MapView& m, const CenterTables& ct,
+                                              const int (&b)[3], const int (&v)[3], unsigned* inexact) {
+  int g[3], flags = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const long long g = static_cast<long long>(b[k]) * m.vps + v[k];
-    if (g < -kKeyBias || g >= kKeyBias) return kKeyOverflow;
-    key |= static_cast<uint64_t>(g + kKeyBias) << (kKeyBits * k);
-    if (v[k] < 0 || v[k] >= m.vps) {
-      const int bq = b[k] + (v[k] < 0 ? -((-v[k] + m.vps - 1) / m.vps) : v[k] / m.vps);
-      const int vq = v[k] - (bq - b[k]) * m.vps;
-      const double cp_a = (v[k] >= -1 && v[k] <= m.vps)
-                              ? ct.d[v[k] + 1]
-                              : static_cast<double>(center_point(v[k], m.vs_f));
-      const double a = __dadd_rn(static_cast<double>(origin_point(b[k], m.bs_f)), cp_a);
-      const double c = __dadd_rn(static_cast<double>(origin_point(bq, m.bs_f)), ct.d[vq + 1]);
-      if (a != c) key |= 1ull << (60 + k);
+    g[k] = b[k] * m.vps + v[k];
+    if (v[k] >= 0 && v[k] < m.vps) continue;
+    if (v[k] < -1 || v[k] > m.vps) {
+      *inexact = 1;  // not an artefact the reference arithmetic can produce; scan-order kernel decides
+      continue;
     }
+    const int bq = v[k] < 0 ? b[k] - 1 : b[k] + 1;
+    const int vq = v[k] < 0 ? m.vps - 1 : 0;
+    const double a = __dadd_rn(static_cast<double>(origin_point(b[k], m.bs_f)), ct.d[v[k] + 1]);
+    const double c = __dadd_rn(static_cast<double>(origin_point(bq, m.bs_f)), ct.d[vq + 1]);
+    if (a != c) flags |= 1 << k;
   }
-  return key;
+  return Ident{g[0], g[1], g[2], flags};
 }
 
-__device__ __forceinline__ uint64_t make_key(const MapView& m, const CenterTables& ct,
-                                             const int (&b)[3], const int (&v)[3], bool* canonical) {
-  const unsigned vmax = static_cast<unsigned>(m.vps);
-  const bool canon = (static_cast<unsigned>(v[0]) < vmax) & (static_cast<unsigned>(v[1]) < vmax) &
-                     (static_cast<unsigned>(v[2]) < vmax);
-  const int g0 = b[0] * m.vps + v[0] + kKeyBias, g1 = b[1] * m.vps + v[1] + kKeyBias,
-            g2 = b[2] * m.vps + v[2] + kKeyBias;
-  const bool in_range = (static_cast<unsigned>(g0 | g1 | g2) >> kKeyBits) == 0 &&
-                        (abs(b[0]) | abs(b[1]) | abs(b[2])) < (1 << 24);
-  *canonical = canon;
-  if (canon & in_range)
-    return static_cast<uint64_t>(g0) | (static_cast<uint64_t>(g1) << kKeyBits) |
-           (static_cast<uint64_t>(g2) << (2 * kKeyBits));
-  return make_key_slow(m, ct, b, v);
+__device__ __forceinline__ uint64_t pack_key(const Ident& id, unsigned* inexact) {
+  const unsigned u0 = static_cast<unsigned>(id.g0 + kKeyBias), u1 = static_cast<unsigned>(id.g1 + kKeyBias),
+                 u2 = static_cast<unsigned>(id.g2 + kKeyBias);
+  if ((u0 | u1 | u2) >> kKeyBits) {
+    *inexact = 1;
+    return kKeyOverflow;
+  }
+  return static_cast<uint64_t>(u0) | (static_cast<uint64_t>(u1) << kKeyBits) |
+         (static_cast<uint64_t>(u2) << (2 * kKeyBits)) | (static_cast<uint64_t>(id.flags) << 60);
 }
 
 // Per-lane state of the ray part a lane is marching.
@@ -107,9 +119,10 @@ struct RayState {
   D3 dir;
   double d;      // distance of the next sample (accumulated like `distance += p_ray_step_`)
   double d_end;  // exclusive end of this part
-  uint64_t prev_key, first_key;
-  unsigned long long first_hash;
   double hit_d;  // distance of the OCCUPIED sample that ended the part, < 0 if none
+  Ident prev;    // previous raw entry (g0 == kNoIdent: none yet)
+  uint64_t first_key;
+  unsigned long long first_hash;
   int info;
   int r;
 };
@@ -119,10 +132,10 @@ __device__ __forceinline__ void ray_begin(RayState& rs, const CasterView& c, con
   rs.dir = rotate(q, D3{c.cam_dirs[3 * r], c.cam_dirs[3 * r + 1], c.cam_dirs[3 * r + 2]});
   rs.d = d0;
   rs.d_end = d_end;
-  rs.prev_key = kNoKey;
+  rs.hit_d = -1.0;
+  rs.prev = Ident{kNoIdent, 0, 0, 0};
   rs.first_key = kNoKey;
   rs.first_hash = 0;
-  rs.hit_d = -1.0;
   rs.info = kCatNone;
   rs.r = r;
 }
@@ -135,11 +148,12 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
                                          LaneCounters& lc) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   const double d_this = rs.d;
-  const D3 Pd{__dadd_rn(P0.x, __dmul_rn(d_this, rs.dir.x)), __dadd_rn(P0.y, __dmul_rn(d_this, rs.dir.y)),
-              __dadd_rn(P0.z, __dmul_rn(d_this, rs.dir.z))};
+  const double pp[3] = {__dadd_rn(P0.x, __dmul_rn(d_this, rs.dir.x)),
+                        __dadd_rn(P0.y, __dmul_rn(d_this, rs.dir.y)),
+                        __dadd_rn(P0.z, __dmul_rn(d_this, rs.dir.z))};
   rs.d = __dadd_rn(d_this, step);
   lc.n_samp++;
-  const float pf[3] = {__double2float_rn(Pd.x), __double2float_rn(Pd.y), __double2float_rn(Pd.z)};
+  const float pf[3] = {__double2float_rn(pp[0]), __double2float_rn(pp[1]), __double2float_rn(pp[2])};
   int bi[3];
   float origin[3];
 #pragma unroll
@@ -148,20 +162,25 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     origin[a] = origin_point(bi[a], m.bs_f);
   }
   const int slot = find_slot(m, bi[0], bi[1], bi[2]);
-  const int st = voxel_state_in_block(m, ct, pf, bi, origin, slot);
+  int vs[3];
+  uint32_t word;
+  bool vs_ok;
+  const int st = voxel_state_in_block(m, ct, pf, bi, origin, slot, vs, &word, &vs_ok);
   if (ITER || st != 0) {
     // getVoxelCenter identity (voxblox.cpp:66-81)
-    const double pp[3] = {Pd.x, Pd.y, Pd.z};
     int vi[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
       vi[a] = grid_index(__double2float_rn(__dsub_rn(pp[a], static_cast<double>(origin[a]))),
                          m.vs_inv_f);
-    bool canonical;
-    const uint64_t key = make_key(m, ct, bi, vi, &canonical);
-    if (key == kKeyOverflow) lc.inexact = 1;
-    bool keep = key != rs.prev_key;
-    rs.prev_key = key;
+    const unsigned vmax = static_cast<unsigned>(m.vps);
+    const bool canonical = (static_cast<unsigned>(vi[0]) < vmax) & (static_cast<unsigned>(vi[1]) < vmax) &
+                           (static_cast<unsigned>(vi[2]) < vmax);
+    Ident id{bi[0] * m.vps + vi[0], bi[1] * m.vps + vi[1], bi[2] * m.vps + vi[2], 0};
+    if (!canonical) id = make_ident_slow(m, ct, bi, vi, &lc.inexact);
+    bool keep = (id.g0 != rs.prev.g0) | (id.g1 != rs.prev.g1) | (id.g2 != rs.prev.g2) |
+                (id.flags != rs.prev.flags);
+    rs.prev = id;
     D3 cc{0.0, 0.0, 0.0};
     const bool need_cc = DIGEST || e.bv_is_setup || EVAL == A3D_EVAL_FRONTIER || !canonical;
     if (need_cc) {
@@ -179,7 +198,14 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     unsigned long long h = 0;
     if (keep) {
       lc.n_vis++;
-      const int cs = centre_state(m, ct, cc, slot, vi);
+      // state / observed flag at the emitted centre: the meta word of its voxel — usually the word
+      // getVoxelState just loaded (same voxel index from both index computations)
+      int cs;
+      if (vs_ok & (vi[0] == vs[0]) & (vi[1] == vs[1]) & (vi[2] == vs[2])) {
+        cs = centre_state_from_word(word);
+      } else {
+        cs = centre_state(m, ct, cc, slot, vi);
+      }
       if (EVAL == A3D_EVAL_VOXEL_TYPE) {
         cat = cs & 3;  // retained entries are always inside the bounding volume
       } else if (!(cs & 4)) {
@@ -196,7 +222,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
       }
     }
     if (rs.first_key == kNoKey) {
-      rs.first_key = key;
+      rs.first_key = pack_key(id, &lc.inexact);
       rs.info = (keep ? cat : kCatNone) | 8 | (keep ? 16 : 0);
       rs.first_hash = h;
     }
@@ -208,24 +234,16 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
   return !(rs.d < rs.d_end);
 }
 
-struct WaveScratch {
-  uint32_t* table;     // per CTA: n_rays entries (writer+1) << 8 | uint8(value)
-  uint8_t* start_s;    // per CTA: original start section of rays cast by the scheduler, 0xFF none
-  Records rec;         // per CTA
-  size_t rays_stride;  // n_rays rounded up (elements) per CTA
-};
-
 __device__ __forceinline__ void store_record(const Records& rec, size_t base, int part, int n_rays,
-                                             const RayState& rs, bool digest) {
+                                             const RayState& rs, LaneCounters& lc, bool digest) {
   const size_t at = base * 2 + static_cast<size_t>(part) * n_rays + rs.r;
-  rec.first_key[at] = rs.first_key;
-  rec.last_key[at] = rs.prev_key;
   rec.info[at] = static_cast<uint8_t>(rs.info);
-  if (digest) rec.first_hash[at] = rs.first_hash;
+  if (rs.info & 8) {
+    rec.first_key[at] = rs.first_key;
+    rec.last_key[at] = pack_key(rs.prev, &lc.inexact);
+    if (digest) rec.first_hash[at] = rs.first_hash;
+  }
 }
-
-constexpr int kPendCap = 96;     // leaf ring capacity (top-up adds <= 32 while count <= 64)
-constexpr int kMarkCap = 1024;   // max rays of one anti-diagonal (min(c_res_x, c_res_y))
 
 }  // namespace
 
@@ -239,13 +257,16 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   const unsigned lt_mask = (1u << lane) - 1u;
   const int n_rays = c.n_rays;
   const int n = c.n_sections;
+  const int n_diag = c.res_x + c.res_y - 1;
+  const int n_units = c.n_units;
 
   __shared__ CenterTables ct;
   __shared__ int s_seg;
-  __shared__ volatile int s_done_diag;        // anti-diagonals fully processed by the scheduler
-  __shared__ unsigned s_next_ray;             // simple caster: next unassigned ray
-  __shared__ unsigned s_pending[2][kPendCap];  // per-warp ring of rays waiting for a lane
-  __shared__ unsigned s_mark_list[kMarkCap];  // scheduler: marking rays of the current diagonal
+  __shared__ volatile int s_done_diag;         // anti-diagonals whose table entries are final
+  __shared__ unsigned s_unit_cursor;           // next leaf-supply unit
+  __shared__ unsigned s_pending[2][kPendCap];  // per-warp ring of ready rays waiting for a lane
+  __shared__ unsigned s_mark_list[kMarkCap];   // marking rays of the current diagonal: r << 8 | s
+  __shared__ double s_mark_hit[kMarkCap];      // their hit distance (< 0: none)
   __shared__ unsigned s_cnt[6], s_nvis, s_nsamp, s_inexact;
   __shared__ unsigned long long s_digest;
   init_center_tables(m, &ct);
@@ -254,7 +275,8 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   volatile uint32_t* const table = ws.table + cta_base;
   volatile uint8_t* const start_s = ws.start_s + cta_base;
   const double step = c.ray_step;
-  const int n_diag = c.res_x + c.res_y - 1;
+  const double d_leaf_end = c.ray_length;
+  const double d_mark_end = (ITER && n > 1) ? c.split[n - 1] : 0.0;
 
   for (;;) {
     __syncthreads();
@@ -289,162 +311,177 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         ws.rec.info[cta_base * 2 + n_rays + r] = kCatNone;
       }
       if (threadIdx.x == 0) {
-        s_done_diag = 0;
-        s_next_ray = 0;
+        s_done_diag = (ITER && n > 1) ? 0 : n_diag;
+        s_unit_cursor = 0;
       }
       __syncthreads();
 
-      if (ITER && warp == 0) {
-        // ---------------- scheduler: sections before the last one + all marks -----------------
-        const double d_end = n > 1 ? c.split[n - 1] : 0.0;
-        for (int dg = 0; n > 1 && dg < n_diag; ++dg) {
-          const int i_lo = max(0, dg - (c.res_y - 1)), i_hi = min(c.res_x - 1, dg);
-          // gather the rays of this diagonal that start before the last section (scan order)
-          int n_mark = 0;
-          for (int base = i_lo; base <= i_hi; base += 32) {
-            const int i = base + static_cast<int>(lane);
-            int s = -1, r = 0;
-            if (i <= i_hi) {
-              r = i * c.res_y + (dg - i);
-              s = static_cast<int>(static_cast<int8_t>(table[r] & 0xFFu));
-            }
-            const bool marking = s >= 0 && s < n - 1;
-            const unsigned mm = __ballot_sync(kFull, marking);
-            if (marking)
-              s_mark_list[n_mark + __popc(mm & lt_mask)] = (static_cast<unsigned>(r) << 8) | s;
-            n_mark += __popc(mm);
-          }
-          __syncwarp();
-          for (int q0 = 0; q0 < n_mark; q0 += 32) {
-            const int nb = min(32, n_mark - q0);
-            RayState rs;
-            rs.r = -1;
-            rs.hit_d = -1.0;
-            int s = 0;
-            if (static_cast<int>(lane) < nb) {
-              const unsigned it = s_mark_list[q0 + lane];
-              s = static_cast<int>(it & 0xFF);
-              ray_begin(rs, c, q, static_cast<int>(it >> 8), c.split[s], d_end);
-              bool done = !(rs.d < rs.d_end);
-              while (!done) done = ray_step<CASTER, EVAL, DIGEST>(m, ct, e, P0, step, rs, lc);
-              store_record(ws.rec, cta_base, 0, n_rays, rs, DIGEST);
-              start_s[rs.r] = static_cast<uint8_t>(s);
-            }
-            __syncwarp();
-            // markNeighboringRays of each ray of the batch, in scan order (DESIGN.md "ray table")
-            for (int qi = 0; qi < nb; ++qi) {
-              const int rr = __shfl_sync(kFull, rs.r, qi);
-              const int ss = __shfl_sync(kFull, s, qi);
-              const double hd = __shfl_sync(kFull, rs.hit_d, qi);
-              const bool hit = hd >= 0.0;
-              int seg_h = ss;
-              if (hit) {
-                while (!(hd < c.split[seg_h + 1])) ++seg_h;
-              }
-              const int t_last = hit ? seg_h : n - 2;
-              const int w0 = 1 << (n - 1 - ss);
-              const int ri = rr / c.res_y, rj = rr - ri * c.res_y;
-              const int nx = min(w0, c.res_x - ri), ny = min(w0, c.res_y - rj);
-              const unsigned writer = static_cast<unsigned>(rr) + 1u;
-              for (int cell = lane; cell < nx * ny; cell += 32) {
-                const int dx = cell / ny, dy = cell - dx * ny;
-                const int mx = max(dx, dy);
-                const int tmax = mx == 0 ? n - 1 : n - 2 - (31 - __clz(mx));
-                const int t = min(tmax, t_last);
-                const int val = (hit && t == seg_h) ? -1 : t + 1;
-                const int at = (ri + dx) * c.res_y + rj + dy;
-                if ((table[at] >> 8) < writer) table[at] = (writer << 8) | static_cast<uint8_t>(val);
-              }
-              __syncwarp();
-            }
-          }
-          __threadfence_block();
-          if (lane == 0) s_done_diag = dg + 1;
-        }
-      } else {
-        // ---------------- leaf: persistent lanes over the rays that are ready -------------------
-        // Iterative: last section of every ray whose table entry reads n-1, discovered diagonal by
-        // diagonal behind the scheduler.  Simple: every ray, full length.
+      // ---------------- persistent-lane engine ----------------------------------------------------
+      {
         unsigned* const pending = s_pending[warp];
         int pend_head = 0, pend_count = 0;  // ring state (warp-uniform)
-        int cur_diag = 0, cur_i = 0;        // iterative: scan position
-        bool source_done = false;
-        const double d_end = c.ray_length;
+        bool supply_done = false;
+        // scheduler state (warp 0 of the iterative caster)
+        const bool scheduler = ITER && warp == 0 && n > 1;
+        bool sched_done = !scheduler;
+        int cur_diag = -1, n_mark = 0, mark_head = 0, n_run = 0;
+        // lane state
         RayState rs;
         rs.r = -1;
-        bool active = false;
+        int role = 0;  // 0 idle, 1 leaf part, 2 marking part
+        int mark_idx = 0, mark_s = 0;
+
         for (;;) {
-          const unsigned idle = __ballot_sync(kFull, !active);
-          if (idle) {
-            // ---- top up the pending ring ----
-            while (!source_done && pend_count <= kPendCap - 32 && pend_count < __popc(idle)) {
-              if (ITER) {
-                if (cur_diag >= n_diag) {
-                  source_done = true;
-                  break;
+          // ---- 1. scheduler: finish the current diagonal, open the next ones ----
+          while (!sched_done && mark_head == n_mark && n_run == 0) {
+            if (cur_diag >= 0) {
+              // markNeighboringRays of every marking ray of the diagonal, in scan order
+              for (int qi = 0; qi < n_mark; ++qi) {
+                const unsigned it = s_mark_list[qi];
+                const int rr = static_cast<int>(it >> 8), ss = static_cast<int>(it & 0xFF);
+                const double hd = s_mark_hit[qi];
+                const bool hit = hd >= 0.0;
+                int seg_h = ss;
+                if (hit) {
+                  while (!(hd < c.split[seg_h + 1])) ++seg_h;
                 }
-                if (n > 1 && s_done_diag <= cur_diag) break;  // entries of this diagonal not final
-                const int i_lo = max(0, cur_diag - (c.res_y - 1)), i_hi = min(c.res_x - 1, cur_diag);
-                const int i = i_lo + cur_i + static_cast<int>(lane);
+                const int t_last = hit ? seg_h : n - 2;
+                const int w0 = 1 << (n - 1 - ss);
+                const int ri = rr / c.res_y, rj = rr - ri * c.res_y;
+                const int nx = min(w0, c.res_x - ri), ny = min(w0, c.res_y - rj);
+                const unsigned writer = static_cast<unsigned>(rr) + 1u;
+                for (int cell = lane; cell < nx * ny; cell += 32) {
+                  const int dx = cell / ny, dy = cell - dx * ny;
+                  const int mx = max(dx, dy);
+                  const int tmax = mx == 0 ? n - 1 : n - 2 - (31 - __clz(mx));
+                  const int t = min(tmax, t_last);
+                  const int val = (hit && t == seg_h) ? -1 : t + 1;
+                  const int at = (ri + dx) * c.res_y + rj + dy;
+                  if ((table[at] >> 8) < writer) table[at] = (writer << 8) | static_cast<uint8_t>(val);
+                }
+                __syncwarp();
+              }
+              __threadfence_block();
+              if (lane == 0) s_done_diag = cur_diag + 1;
+            }
+            ++cur_diag;
+            n_mark = 0;
+            mark_head = 0;
+            if (cur_diag >= n_diag) {
+              sched_done = true;
+              break;
+            }
+            // gather the rays of this diagonal that start before the last section (scan order)
+            const int i_lo = max(0, cur_diag - (c.res_y - 1)), i_hi = min(c.res_x - 1, cur_diag);
+            for (int base = i_lo; base <= i_hi; base += 32) {
+              const int i = base + static_cast<int>(lane);
+              int s = -1, r = 0;
+              if (i <= i_hi) {
+                r = i * c.res_y + (cur_diag - i);
+                s = static_cast<int>(static_cast<int8_t>(table[r] & 0xFFu));
+              }
+              const bool marking = s >= 0 && s < n - 1;
+              const unsigned mm = __ballot_sync(kFull, marking);
+              if (marking)
+                s_mark_list[n_mark + __popc(mm & lt_mask)] = (static_cast<unsigned>(r) << 8) | s;
+              n_mark += __popc(mm);
+            }
+            __syncwarp();
+          }
+
+          // ---- 2. give work to idle lanes: marking parts first, then leaf parts ----
+          const unsigned idle = __ballot_sync(kFull, role == 0);
+          if (idle) {
+            int n_idle = __popc(idle);
+            const int rank = __popc(idle & lt_mask);
+            int take_mark = 0;
+            if (scheduler) {
+              take_mark = min(n_idle, n_mark - mark_head);
+              if (role == 0 && rank < take_mark) {
+                const unsigned it = s_mark_list[mark_head + rank];
+                mark_idx = mark_head + rank;
+                mark_s = static_cast<int>(it & 0xFF);
+                ray_begin(rs, c, q, static_cast<int>(it >> 8), c.split[mark_s], d_mark_end);
+                role = 2;  // split[s] < split[n-1] for s < n-1: at least one sample
+              }
+              mark_head += take_mark;
+              n_run += take_mark;
+              n_idle -= take_mark;
+            }
+            if (n_idle > 0) {
+              // top up the ring from the shared supply
+              while (!supply_done && pend_count < n_idle && pend_count <= kPendCap - 32) {
+                int u = -1;
+                if (lane == 0) {
+                  const unsigned cur = *reinterpret_cast<volatile unsigned*>(&s_unit_cursor);
+                  if (cur >= static_cast<unsigned>(n_units)) {
+                    u = -2;
+                  } else if (!ITER || c.unit_diag[cur] < s_done_diag) {
+                    if (atomicCAS(&s_unit_cursor, cur, cur + 1) == cur) u = static_cast<int>(cur);
+                  }
+                }
+                u = __shfl_sync(kFull, u, 0);
+                if (u == -2) supply_done = true;
+                if (u < 0) break;
                 bool ready = false;
                 int rr = 0;
-                if (i <= i_hi) {
-                  rr = i * c.res_y + (cur_diag - i);
-                  ready = static_cast<int>(static_cast<int8_t>(table[rr] & 0xFFu)) == n - 1;
+                if (ITER) {
+                  const int dg = c.unit_diag[u];
+                  const int i = c.unit_i0[u] + static_cast<int>(lane);
+                  if (i <= min(c.res_x - 1, dg)) {
+                    rr = i * c.res_y + (dg - i);
+                    ready = static_cast<int>(static_cast<int8_t>(table[rr] & 0xFFu)) == n - 1;
+                  }
+                } else {
+                  rr = u * 32 + static_cast<int>(lane);
+                  ready = rr < n_rays;
                 }
                 const unsigned mm = __ballot_sync(kFull, ready);
                 if (ready) pending[(pend_head + pend_count + __popc(mm & lt_mask)) % kPendCap] = rr;
                 pend_count += __popc(mm);
-                cur_i += 32;
-                if (i_lo + cur_i > i_hi) {
-                  cur_i = 0;
-                  ++cur_diag;
-                }
-              } else {
-                unsigned first = 0;
-                if (lane == 0) first = atomicAdd(&s_next_ray, 32u);
-                first = __shfl_sync(kFull, first, 0);
-                if (first >= static_cast<unsigned>(n_rays)) {
-                  source_done = true;
-                  break;
-                }
-                const int cnt = min(32, n_rays - static_cast<int>(first));
-                if (static_cast<int>(lane) < cnt)
-                  pending[(pend_head + pend_count + lane) % kPendCap] = first + lane;
-                pend_count += cnt;
+                __syncwarp();
               }
+              const int lrank = rank - take_mark;
+              if (role == 0 && lrank >= 0 && lrank < pend_count) {
+                const int r = static_cast<int>(pending[(pend_head + lrank) % kPendCap]);
+                double d0 = 0.0;
+                if (ITER) {
+                  const int s0 = start_s[r] == 0xFF ? n - 1 : start_s[r];
+                  const int k0 = s0 == n - 1 ? 0 : c.seg_end[s0 * n + (n - 2)];
+                  d0 = k0 < c.kcount[s0] ? c.dseq[static_cast<size_t>(s0) * c.kmax + k0] : d_leaf_end;
+                }
+                ray_begin(rs, c, q, r, d0, d_leaf_end);
+                role = (rs.d < rs.d_end) ? 1 : 0;
+              }
+              const int taken = min(n_idle, pend_count);
+              pend_head = (pend_head + taken) % kPendCap;
+              pend_count -= taken;
               __syncwarp();
             }
-            // ---- hand rays to idle lanes ----
-            const int rank = __popc(idle & lt_mask);
-            if (!active && rank < pend_count) {
-              const int r = static_cast<int>(pending[(pend_head + rank) % kPendCap]);
-              double d0 = 0.0;
-              if (ITER) {
-                const int s0 = start_s[r] == 0xFF ? n - 1 : start_s[r];
-                const int k0 = s0 == n - 1 ? 0 : c.seg_end[s0 * n + (n - 2)];
-                d0 = k0 < c.kcount[s0] ? c.dseq[static_cast<size_t>(s0) * c.kmax + k0] : d_end;
-              }
-              ray_begin(rs, c, q, r, d0, d_end);
-              active = rs.d < rs.d_end;
-              if (!active) store_record(ws.rec, cta_base, 1, n_rays, rs, DIGEST);
-            }
-            const int taken = min(__popc(idle), pend_count);
-            pend_head = (pend_head + taken) % kPendCap;
-            pend_count -= taken;
-            __syncwarp();
-            if (__ballot_sync(kFull, active) == 0) {
-              if (source_done && pend_count == 0) break;
-              if (pend_count == 0) __nanosleep(64);
-              continue;
-            }
           }
-          if (active) {
+
+          // ---- 3. anything left to do? ----
+          const unsigned busy = __ballot_sync(kFull, role != 0);
+          if (busy == 0) {
+            if (sched_done && supply_done && pend_count == 0) break;
+            if (sched_done && pend_count == 0) __nanosleep(64);  // wait for the scheduler warp
+            continue;
+          }
+
+          // ---- 4. one sample per busy lane ----
+          bool fin_mark = false;
+          if (role != 0) {
             if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, P0, step, rs, lc)) {
-              store_record(ws.rec, cta_base, 1, n_rays, rs, DIGEST);
-              active = false;
+              store_record(ws.rec, cta_base, role == 2 ? 0 : 1, n_rays, rs, lc, DIGEST);
+              if (role == 2) {
+                s_mark_hit[mark_idx] = rs.hit_d;
+                start_s[rs.r] = static_cast<uint8_t>(mark_s);
+                fin_mark = true;
+              }
+              role = 0;
             }
           }
+          if (scheduler) n_run -= __popc(__ballot_sync(kFull, fin_mark));
           __syncwarp();
         }
       }
@@ -571,9 +608,9 @@ static void launch_wave_c(cudaStream_t st, const MapView& m, const CasterView& c
   }
 }
 
-// scratch: wave_scratch_bytes() bytes, carved here.  b.digests receives the ORDER-INDEPENDENT digest
-// (sum of digest_entry over the stored list, mod 2^64).  inexact: one bit per segment, set when a
-// voxel key overflowed the 20-bit packing (the host re-evaluates those with k_cast_gain).
+// scratch: wave_scratch_bytes() bytes, carved here.  b.set_digests receives the ORDER-INDEPENDENT
+// digest (sum of digest_entry over the stored list, mod 2^64).  inexact: one bit per segment, set
+// when a voxel key overflowed the 20-bit packing (the host re-evaluates those with k_cast_gain).
 void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                       const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact) {
   size_t stride = 0;
