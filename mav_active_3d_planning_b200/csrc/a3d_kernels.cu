@@ -257,7 +257,7 @@ __device__ __forceinline__ double voxel_type_gain(const EvalView& e, const unsig
 
 constexpr int kCastBlock = 32;  // one warp per CTA: a warp owns a whole segment
 #ifndef A3D_CAST_MIN_BLOCKS
-#define A3D_CAST_MIN_BLOCKS 24  // resident CTAs (= warps) per SM the register allocation must allow
+#define A3D_CAST_MIN_BLOCKS 28  // resident CTAs (= warps) per SM the register allocation must allow
 #endif
 
 template <int CASTER, int EVAL, bool DIGEST, bool EMIT>

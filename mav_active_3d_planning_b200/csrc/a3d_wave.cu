@@ -67,28 +67,34 @@ struct WaveScratch {
   size_t rays_stride;  // n_rays rounded up (elements) per CTA
 };
 
+// Per-lane accumulators of a segment.  `packed`: three 21-bit fields, field c counts list entries of
+// fold category c (VoxelType: voxel state 0/1/2; Naive/Frontier: field 0 = entries that score).
 struct LaneCounters {
-  unsigned cnt[6];
-  unsigned n_vis, n_samp;
+  unsigned long long packed;
   unsigned long long digest;
+  unsigned n_vis, n_samp;
   unsigned inexact;
 };
+constexpr int kFieldBits = 21;
 
-// Identity of an emitted list entry: g[k] = b[k]*vps + v[k]; flags bit k: axis k keeps a raw artefact
-// voxel index (v = -1 or vps) whose centre double differs from the canonical voxel's.
+// Identity of an emitted list entry: g[k] = b[k]*vps + v[k]; bit 30 of g[k] set: axis k keeps a raw
+// artefact voxel index (v = -1 or vps) whose centre double differs from the canonical voxel's
+// (valid g are < 2^19 in magnitude, larger ones flag the segment for the scan-order kernel).
 struct Ident {
-  int g0, g1, g2, flags;
+  int g0, g1, g2;
 };
+constexpr int kRawAxisBit = 1 << 30;
 
 // Artefact voxel indices (getGridIndexFromPoint lands one voxel outside the block because of the
 // float block-index rounding): per axis, name the voxel canonically when its centre double
 // (voxblox.cpp:72-79) equals the canonical voxel's centre double, else keep it raw and flag it.
 __device__ __noinline__ Ident make_ident_slow(const MapView& m, const CenterTables& ct,
                                               const int (&b)[3], const int (&v)[3], unsigned* inexact) {
-  int g[3], flags = 0;
+  int g[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     g[k] = b[k] * m.vps + v[k];
+    if (g[k] <= -kKeyBias || g[k] >= kKeyBias) *inexact = 1;
     if (v[k] >= 0 && v[k] < m.vps) continue;
     if (v[k] < -1 || v[k] > m.vps) {
       *inexact = 1;  // not an artefact the reference arithmetic can produce; scan-order kernel decides
@@ -98,59 +104,67 @@ __device__ __noinline__ Ident make_ident_slow(const MapView& m, const CenterTabl
     const int vq = v[k] < 0 ? m.vps - 1 : 0;
     const double a = __dadd_rn(static_cast<double>(origin_point(b[k], m.bs_f)), ct.d[v[k] + 1]);
     const double c = __dadd_rn(static_cast<double>(origin_point(bq, m.bs_f)), ct.d[vq + 1]);
-    if (a != c) flags |= 1 << k;
+    if (a != c) g[k] ^= kRawAxisBit;
   }
-  return Ident{g[0], g[1], g[2], flags};
+  return Ident{g[0], g[1], g[2]};
 }
 
 __device__ __forceinline__ uint64_t pack_key(const Ident& id, unsigned* inexact) {
-  const unsigned u0 = static_cast<unsigned>(id.g0 + kKeyBias), u1 = static_cast<unsigned>(id.g1 + kKeyBias),
-                 u2 = static_cast<unsigned>(id.g2 + kKeyBias);
+  // bit30 != bit31 ⇒ raw-axis flag
+  const int flags = static_cast<int>(static_cast<unsigned>(id.g0 ^ (id.g0 << 1)) >> 31) |
+                    static_cast<int>(static_cast<unsigned>(id.g1 ^ (id.g1 << 1)) >> 31) << 1 |
+                    static_cast<int>(static_cast<unsigned>(id.g2 ^ (id.g2 << 1)) >> 31) << 2;
+  const int h0 = (flags & 1) ? id.g0 ^ kRawAxisBit : id.g0, h1 = (flags & 2) ? id.g1 ^ kRawAxisBit : id.g1,
+            h2 = (flags & 4) ? id.g2 ^ kRawAxisBit : id.g2;
+  const unsigned u0 = static_cast<unsigned>(h0 + kKeyBias), u1 = static_cast<unsigned>(h1 + kKeyBias),
+                 u2 = static_cast<unsigned>(h2 + kKeyBias);
   if ((u0 | u1 | u2) >> kKeyBits) {
     *inexact = 1;
     return kKeyOverflow;
   }
   return static_cast<uint64_t>(u0) | (static_cast<uint64_t>(u1) << kKeyBits) |
-         (static_cast<uint64_t>(u2) << (2 * kKeyBits)) | (static_cast<uint64_t>(id.flags) << 60);
+         (static_cast<uint64_t>(u2) << (2 * kKeyBits)) | (static_cast<uint64_t>(flags) << 60);
 }
 
-// Per-lane state of the ray part a lane is marching.
+// Per-lane state of the ray part a lane is marching (kept small: it lives in registers across the
+// whole engine loop).
 struct RayState {
-  D3 dir;
-  double d;      // distance of the next sample (accumulated like `distance += p_ray_step_`)
-  double d_end;  // exclusive end of this part
-  double hit_d;  // distance of the OCCUPIED sample that ended the part, < 0 if none
-  Ident prev;    // previous raw entry (g0 == kNoIdent: none yet)
-  uint64_t first_key;
-  unsigned long long first_hash;
-  int info;
-  int r;
+  double dx, dy, dz;  // world direction
+  double d;           // distance of the next sample (accumulated like `distance += p_ray_step_`)
+  Ident prev;         // previous raw entry (g0 == kNoIdent: none yet)
+  int r;              // ray id
 };
 
-__device__ __forceinline__ void ray_begin(RayState& rs, const CasterView& c, const Q4& q, int r,
-                                          double d0, double d_end) {
-  rs.dir = rotate(q, D3{c.cam_dirs[3 * r], c.cam_dirs[3 * r + 1], c.cam_dirs[3 * r + 2]});
+struct ViewShared {  // per-view constants, one copy per CTA in shared memory
+  double P0[3];
+  double q[4];
+};
+
+__device__ __forceinline__ void ray_begin(RayState& rs, const CasterView& c, const ViewShared& vw,
+                                          int r, double d0) {
+  const Q4 q{vw.q[0], vw.q[1], vw.q[2], vw.q[3]};
+  const D3 dir = rotate(q, D3{c.cam_dirs[3 * r], c.cam_dirs[3 * r + 1], c.cam_dirs[3 * r + 2]});
+  rs.dx = dir.x;
+  rs.dy = dir.y;
+  rs.dz = dir.z;
   rs.d = d0;
-  rs.d_end = d_end;
-  rs.hit_d = -1.0;
-  rs.prev = Ident{kNoIdent, 0, 0, 0};
-  rs.first_key = kNoKey;
-  rs.first_hash = 0;
-  rs.info = kCatNone;
+  rs.prev = Ident{kNoIdent, 0, 0};
   rs.r = r;
 }
 
-// One sample of the lane's ray.  Returns true when the part is finished (hit or end reached).
-// Precondition: rs.d < rs.d_end.
+// One sample of the lane's ray.  Returns true when the part is finished (hit or end reached);
+// *hit_d = distance of the OCCUPIED sample that ended it (unchanged otherwise).
+// rec_at: index of this part's record.  Precondition: rs.d < d_end.
 template <int CASTER, int EVAL, bool DIGEST>
 __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
-                                         const D3& P0, const double step, RayState& rs,
-                                         LaneCounters& lc) {
+                                         const ViewShared& vw, const double step, const double d_end,
+                                         RayState& rs, LaneCounters& lc, const Records& rec,
+                                         size_t rec_at, double* hit_d) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   const double d_this = rs.d;
-  const double pp[3] = {__dadd_rn(P0.x, __dmul_rn(d_this, rs.dir.x)),
-                        __dadd_rn(P0.y, __dmul_rn(d_this, rs.dir.y)),
-                        __dadd_rn(P0.z, __dmul_rn(d_this, rs.dir.z))};
+  const double pp[3] = {__dadd_rn(vw.P0[0], __dmul_rn(d_this, rs.dx)),
+                        __dadd_rn(vw.P0[1], __dmul_rn(d_this, rs.dy)),
+                        __dadd_rn(vw.P0[2], __dmul_rn(d_this, rs.dz))};
   rs.d = __dadd_rn(d_this, step);
   lc.n_samp++;
   const float pf[3] = {__double2float_rn(pp[0]), __double2float_rn(pp[1]), __double2float_rn(pp[2])};
@@ -176,10 +190,10 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     const unsigned vmax = static_cast<unsigned>(m.vps);
     const bool canonical = (static_cast<unsigned>(vi[0]) < vmax) & (static_cast<unsigned>(vi[1]) < vmax) &
                            (static_cast<unsigned>(vi[2]) < vmax);
-    Ident id{bi[0] * m.vps + vi[0], bi[1] * m.vps + vi[1], bi[2] * m.vps + vi[2], 0};
+    Ident id{bi[0] * m.vps + vi[0], bi[1] * m.vps + vi[1], bi[2] * m.vps + vi[2]};
     if (!canonical) id = make_ident_slow(m, ct, bi, vi, &lc.inexact);
-    bool keep = (id.g0 != rs.prev.g0) | (id.g1 != rs.prev.g1) | (id.g2 != rs.prev.g2) |
-                (id.flags != rs.prev.flags);
+    const bool first = rs.prev.g0 == kNoIdent;
+    bool keep = (id.g0 != rs.prev.g0) | (id.g1 != rs.prev.g1) | (id.g2 != rs.prev.g2);
     rs.prev = id;
     D3 cc{0.0, 0.0, 0.0};
     const bool need_cc = DIGEST || e.bv_is_setup || EVAL == A3D_EVAL_FRONTIER || !canonical;
@@ -215,35 +229,29 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
           cat = 0;
         }
       }
-      if (cat != kCatNone) lc.cnt[cat]++;
+      if (cat != kCatNone) lc.packed += 1ull << (kFieldBits * cat);
       if (DIGEST) {
         h = digest_entry(cc);
         lc.digest += h;
       }
     }
-    if (rs.first_key == kNoKey) {
-      rs.first_key = pack_key(id, &lc.inexact);
-      rs.info = (keep ? cat : kCatNone) | 8 | (keep ? 16 : 0);
-      rs.first_hash = h;
+    if (first) {
+      // record of the part's first entry, written once
+      rec.first_key[rec_at] = pack_key(id, &lc.inexact);
+      rec.info[rec_at] = static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0));
+      if (DIGEST) rec.first_hash[rec_at] = h;
     }
   }
   if (st == 0) {
-    rs.hit_d = d_this;
+    *hit_d = d_this;
     return true;
   }
-  return !(rs.d < rs.d_end);
+  return !(rs.d < d_end);
 }
 
-__device__ __forceinline__ void store_record(const Records& rec, size_t base, int part, int n_rays,
-                                             const RayState& rs, LaneCounters& lc, bool digest) {
-  const size_t at = base * 2 + static_cast<size_t>(part) * n_rays + rs.r;
-  rec.info[at] = static_cast<uint8_t>(rs.info);
-  if (rs.info & 8) {
-    rec.first_key[at] = rs.first_key;
-    rec.last_key[at] = pack_key(rs.prev, &lc.inexact);
-    if (digest) rec.first_hash[at] = rs.first_hash;
-  }
-}
+#ifndef A3D_WAVE_STEPS
+#define A3D_WAVE_STEPS 4  // samples marched between two rounds of lane bookkeeping
+#endif
 
 }  // namespace
 
@@ -261,14 +269,15 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   const int n_units = c.n_units;
 
   __shared__ CenterTables ct;
+  __shared__ ViewShared vw;
   __shared__ int s_seg;
   __shared__ volatile int s_done_diag;         // anti-diagonals whose table entries are final
   __shared__ unsigned s_unit_cursor;           // next leaf-supply unit
   __shared__ unsigned s_pending[2][kPendCap];  // per-warp ring of ready rays waiting for a lane
   __shared__ unsigned s_mark_list[kMarkCap];   // marking rays of the current diagonal: r << 8 | s
   __shared__ double s_mark_hit[kMarkCap];      // their hit distance (< 0: none)
-  __shared__ unsigned s_cnt[6], s_nvis, s_nsamp, s_inexact;
-  __shared__ unsigned long long s_digest;
+  __shared__ unsigned long long s_packed, s_digest;
+  __shared__ unsigned s_nvis, s_nsamp, s_inexact;
   init_center_tables(m, &ct);
 
   const size_t cta_base = static_cast<size_t>(blockIdx.x) * ws.rays_stride;
@@ -290,18 +299,24 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
     uint64_t carry_key = kNoKey;  // last emitted key so far in this segment (warp 0, uniform)
 
     for (int view = v_begin; view < v_end; ++view) {
-      // camera pose = body pose ∘ mounting transform (camera_model.cpp:24-28)
-      D3 P0{b.pos[3 * view], b.pos[3 * view + 1], b.pos[3 * view + 2]};
-      Q4 q{b.quat[4 * view], b.quat[4 * view + 1], b.quat[4 * view + 2], b.quat[4 * view + 3]};
-      {
-        const D3 mt = rotate(q, D3{c.mount_t[0], c.mount_t[1], c.mount_t[2]});
-        P0.x = __dadd_rn(P0.x, mt.x);
-        P0.y = __dadd_rn(P0.y, mt.y);
-        P0.z = __dadd_rn(P0.z, mt.z);
-        q = qmul(q, c.mount_q);
-      }
-      // per-view init: ray table, start sections, record flags (after the previous view's fix-up)
+      // per-view init (after the previous view's fix-up): pose, ray table, start sections, records
       __syncthreads();
+      if (threadIdx.x == 0) {
+        // camera pose = body pose ∘ mounting transform (camera_model.cpp:24-28)
+        D3 P0{b.pos[3 * view], b.pos[3 * view + 1], b.pos[3 * view + 2]};
+        Q4 q{b.quat[4 * view], b.quat[4 * view + 1], b.quat[4 * view + 2], b.quat[4 * view + 3]};
+        const D3 mt = rotate(q, D3{c.mount_t[0], c.mount_t[1], c.mount_t[2]});
+        vw.P0[0] = __dadd_rn(P0.x, mt.x);
+        vw.P0[1] = __dadd_rn(P0.y, mt.y);
+        vw.P0[2] = __dadd_rn(P0.z, mt.z);
+        q = qmul(q, c.mount_q);
+        vw.q[0] = q.w;
+        vw.q[1] = q.x;
+        vw.q[2] = q.y;
+        vw.q[3] = q.z;
+        s_done_diag = (ITER && n > 1) ? 0 : n_diag;
+        s_unit_cursor = 0;
+      }
       for (int r = threadIdx.x; r < n_rays; r += kWaveThreads) {
         if (ITER) {
           table[r] = 0u;
@@ -309,10 +324,6 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         }
         ws.rec.info[cta_base * 2 + r] = kCatNone;
         ws.rec.info[cta_base * 2 + n_rays + r] = kCatNone;
-      }
-      if (threadIdx.x == 0) {
-        s_done_diag = (ITER && n > 1) ? 0 : n_diag;
-        s_unit_cursor = 0;
       }
       __syncthreads();
 
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         RayState rs;
         rs.r = -1;
         int role = 0;  // 0 idle, 1 leaf part, 2 marking part
-        int mark_idx = 0, mark_s = 0;
+        int mark_idx = 0;
 
         for (;;) {
           // ---- 1. scheduler: finish the current diagonal, open the next ones ----
@@ -400,8 +411,10 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
               if (role == 0 && rank < take_mark) {
                 const unsigned it = s_mark_list[mark_head + rank];
                 mark_idx = mark_head + rank;
-                mark_s = static_cast<int>(it & 0xFF);
-                ray_begin(rs, c, q, static_cast<int>(it >> 8), c.split[mark_s], d_mark_end);
+                const int ms = static_cast<int>(it & 0xFF);
+                ray_begin(rs, c, vw, static_cast<int>(it >> 8), c.split[ms]);
+                start_s[rs.r] = static_cast<uint8_t>(ms);  // read by leaf lanes after the diagonal
+                s_mark_hit[mark_idx] = -1.0;
                 role = 2;  // split[s] < split[n-1] for s < n-1: at least one sample
               }
               mark_head += take_mark;
@@ -450,8 +463,8 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                   const int k0 = s0 == n - 1 ? 0 : c.seg_end[s0 * n + (n - 2)];
                   d0 = k0 < c.kcount[s0] ? c.dseq[static_cast<size_t>(s0) * c.kmax + k0] : d_leaf_end;
                 }
-                ray_begin(rs, c, q, r, d0, d_leaf_end);
-                role = (rs.d < rs.d_end) ? 1 : 0;
+                ray_begin(rs, c, vw, r, d0);
+                role = (rs.d < d_leaf_end) ? 1 : 0;
               }
               const int taken = min(n_idle, pend_count);
               pend_head = (pend_head + taken) % kPendCap;
@@ -468,17 +481,22 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
             continue;
           }
 
-          // ---- 4. one sample per busy lane ----
+          // ---- 4. a few samples per busy lane ----
           bool fin_mark = false;
-          if (role != 0) {
-            if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, P0, step, rs, lc)) {
-              store_record(ws.rec, cta_base, role == 2 ? 0 : 1, n_rays, rs, lc, DIGEST);
-              if (role == 2) {
-                s_mark_hit[mark_idx] = rs.hit_d;
-                start_s[rs.r] = static_cast<uint8_t>(mark_s);
-                fin_mark = true;
+#pragma unroll 1
+          for (int it = 0; it < A3D_WAVE_STEPS; ++it) {
+            if (role != 0) {
+              const size_t rec_at = cta_base * 2 + (role == 2 ? 0 : static_cast<size_t>(n_rays)) + rs.r;
+              double hit_d = -1.0;
+              if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, step, role == 2 ? d_mark_end : d_leaf_end,
+                                                 rs, lc, ws.rec, rec_at, &hit_d)) {
+                if (rs.prev.g0 != kNoIdent) ws.rec.last_key[rec_at] = pack_key(rs.prev, &lc.inexact);
+                if (role == 2) {
+                  s_mark_hit[mark_idx] = hit_d;
+                  fin_mark = true;
+                }
+                role = 0;
               }
-              role = 0;
             }
           }
           if (scheduler) n_run -= __popc(__ballot_sync(kFull, fin_mark));
@@ -513,7 +531,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
           if (emitted && fk == prev && (info & 16)) {
             // the first entry of this part repeats the previous raw entry: std::unique drops it
             lc.n_vis--;
-            if ((info & 7) != kCatNone) lc.cnt[info & 7]--;
+            if ((info & 7) != kCatNone) lc.packed -= 1ull << (kFieldBits * (info & 7));
             if (DIGEST) lc.digest -= ws.rec.first_hash[at];
           }
           if (em) carry_key = __shfl_sync(kFull, lk, 31 - __clz(em));
@@ -521,30 +539,30 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
       }
     }  // views
 
-    // ---------------- per-segment reduction (lane counters are modular: fix-up may decrement) ----
+    // ---------------- per-segment reduction ---------------------------------------------------------
+    // Lane accumulators are modular (the fix-up may decrement a lane that never incremented); the
+    // field sums are exact as long as every per-segment count stays below 2^21 per field — larger
+    // segments are flagged for the scan-order kernel.
     if (threadIdx.x == 0) {
-      for (int i = 0; i < 6; ++i) s_cnt[i] = 0;
+      s_packed = 0;
+      s_digest = 0;
       s_nvis = 0;
       s_nsamp = 0;
       s_inexact = 0;
-      s_digest = 0;
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const unsigned t = __reduce_add_sync(kFull, lc.cnt[i]);
-      if (lane == 0 && t) atomicAdd(&s_cnt[i], t);
-    }
     {
+      unsigned long long pk = lc.packed, dg = lc.digest;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        pk += __shfl_xor_sync(kFull, pk, off);
+        if (DIGEST) dg += __shfl_xor_sync(kFull, dg, off);
+      }
       const unsigned tv = __reduce_add_sync(kFull, lc.n_vis);
       const unsigned tsmp = __reduce_add_sync(kFull, lc.n_samp);
       const unsigned tin = __reduce_or_sync(kFull, lc.inexact);
-      unsigned long long dg = lc.digest;
-      if (DIGEST) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) dg += __shfl_xor_sync(kFull, dg, off);
-      }
       if (lane == 0) {
+        atomicAdd(&s_packed, pk);
         atomicAdd(&s_nvis, tv);
         atomicAdd(&s_nsamp, tsmp);
         atomicOr(&s_inexact, tin);
@@ -553,23 +571,28 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+      const unsigned long long fmask = (1ull << kFieldBits) - 1;
+      const unsigned long long c0 = s_packed & fmask, c1 = (s_packed >> kFieldBits) & fmask,
+                               c2 = (s_packed >> (2 * kFieldBits)) & fmask;
+      unsigned inexact = s_inexact;
+      if (s_nvis >= (1u << kFieldBits)) inexact = 1;  // a field may have wrapped
       // VoxelTypeEvaluator's switch without breaks (voxel_type_evaluator.cpp:69-85)
       double g = 0.0;
       if (EVAL == A3D_EVAL_VOXEL_TYPE) {
-        const double n_unk = static_cast<double>(s_cnt[2]);
-        const double n_free = static_cast<double>(s_cnt[1]) + n_unk;
-        const double n_occ = static_cast<double>(s_cnt[0]) + n_free;
+        const double n_unk = static_cast<double>(c2);
+        const double n_free = static_cast<double>(c1) + n_unk;
+        const double n_occ = static_cast<double>(c0) + n_free;
         g += n_unk * e.gains[0];
         g += n_free * e.gains[2];
         g += n_occ * e.gains[1];
       } else {
-        g = static_cast<double>(s_cnt[0]);
+        g = static_cast<double>(c0);
       }
       b.gains[seg] = g;
       if (b.n_visible) b.n_visible[seg] = s_nvis;
       if (b.n_samples) b.n_samples[seg] = s_nsamp;
       if (DIGEST && b.set_digests) b.set_digests[seg] = s_digest;
-      if (s_inexact) atomicOr(&inexact_flags[seg >> 5], 1u << (seg & 31));
+      if (inexact) atomicOr(&inexact_flags[seg >> 5], 1u << (seg & 31));
     }
   }
 }
