@@ -179,7 +179,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mav_active_3d_planning_b200 import capi
+    from mav_active_3d_planning_b200 import capi, scheduler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -195,8 +195,9 @@ def run_ours(args):
     n_seg = args.views
     # every rank evaluates its own shard of the global candidate list (weak scaling)
     m, pos_all, quat_all, (d_idx, d_dist, d_obs) = make_workload(n_seg * world)
-    pos = np.ascontiguousarray(pos_all[rank * n_seg:(rank + 1) * n_seg])
-    quat = np.ascontiguousarray(quat_all[rank * n_seg:(rank + 1) * n_seg])
+    lo, hi = scheduler.shard_bounds(n_seg * world, world, rank)
+    pos = np.ascontiguousarray(pos_all[lo:hi])
+    quat = np.ascontiguousarray(quat_all[lo:hi])
 
     ctx = capi.Context(local)
     ctx.upload_map(m)
@@ -211,7 +212,6 @@ def run_ours(args):
     t_gain = torch.zeros(n_seg, dtype=torch.float64, device=dev)
     t_nvis = torch.zeros(n_seg, dtype=torch.int64, device=dev)
     t_nsamp = torch.zeros(n_seg, dtype=torch.int64, device=dev)
-    t_all = torch.zeros(n_seg * world, dtype=torch.float64, device=dev)
     nv = m.vps ** 3
     n_delta = d_idx.shape[0]
     dist_bytes = n_delta * nv * 4
@@ -229,8 +229,7 @@ def run_ours(args):
         ctx.compute_gains_dev(caster, ev, n_seg, t_pos.data_ptr(), t_quat.data_ptr(),
                               t_first.data_ptr(), n_seg, t_gain.data_ptr(), t_nvis.data_ptr(),
                               t_nsamp.data_ptr(), 0)
-        if world > 1:
-            dist.all_gather_into_tensor(t_all, t_gain)
+        return scheduler.gather_gains(t_gain, n_seg * world)
 
     def barrier():
         if world > 1:

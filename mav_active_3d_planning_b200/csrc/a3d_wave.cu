@@ -69,10 +69,12 @@ struct WaveScratch {
 
 // Per-lane accumulators of a segment.  `packed`: three 21-bit fields, field c counts list entries of
 // fold category c (VoxelType: voxel state 0/1/2; Naive/Frontier: field 0 = entries that score).
+// field 0..2: VoxelType → entries of voxel state 0/1/2; Naive/Frontier → field 0 = entries that score,
+// field 1 = other retained entries.  n_visible = sum of the fields.
 struct LaneCounters {
   unsigned long long packed;
-  unsigned long long digest;
-  unsigned n_vis, n_samp;
+  unsigned long long digest;  // DIGEST instantiations only
+  unsigned n_samp;
   unsigned inexact;
 };
 constexpr int kFieldBits = 21;
@@ -88,8 +90,9 @@ constexpr int kRawAxisBit = 1 << 30;
 // Artefact voxel indices (getGridIndexFromPoint lands one voxel outside the block because of the
 // float block-index rounding): per axis, name the voxel canonically when its centre double
 // (voxblox.cpp:72-79) equals the canonical voxel's centre double, else keep it raw and flag it.
-__device__ __noinline__ Ident make_ident_slow(const MapView& m, const CenterTables& ct,
-                                              const int (&b)[3], const int (&v)[3], unsigned* inexact) {
+__device__ __noinline__ Ident make_ident_slow(const MapView& m, const CenterTables& ct, int b0, int b1,
+                                              int b2, int v0, int v1, int v2, unsigned* inexact) {
+  const int b[3] = {b0, b1, b2}, v[3] = {v0, v1, v2};
   int g[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -191,7 +194,11 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     const bool canonical = (static_cast<unsigned>(vi[0]) < vmax) & (static_cast<unsigned>(vi[1]) < vmax) &
                            (static_cast<unsigned>(vi[2]) < vmax);
     Ident id{bi[0] * m.vps + vi[0], bi[1] * m.vps + vi[1], bi[2] * m.vps + vi[2]};
-    if (!canonical) id = make_ident_slow(m, ct, bi, vi, &lc.inexact);
+    if (!canonical) {
+      unsigned bad = 0;
+      id = make_ident_slow(m, ct, bi[0], bi[1], bi[2], vi[0], vi[1], vi[2], &bad);
+      lc.inexact |= bad;
+    }
     const bool first = rs.prev.g0 == kNoIdent;
     bool keep = (id.g0 != rs.prev.g0) | (id.g1 != rs.prev.g1) | (id.g2 != rs.prev.g2);
     rs.prev = id;
@@ -211,7 +218,6 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     int cat = kCatNone;
     unsigned long long h = 0;
     if (keep) {
-      lc.n_vis++;
       // state / observed flag at the emitted centre: the meta word of its voxel — usually the word
       // getVoxelState just loaded (same voxel index from both index computations)
       int cs;
@@ -222,14 +228,17 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
       }
       if (EVAL == A3D_EVAL_VOXEL_TYPE) {
         cat = cs & 3;  // retained entries are always inside the bounding volume
-      } else if (!(cs & 4)) {
-        if (EVAL == A3D_EVAL_NAIVE) {
-          cat = 0;
-        } else if (is_frontier_voxel(m, ct, e, cc)) {
-          cat = 0;
+      } else {
+        cat = 1;
+        if (!(cs & 4)) {
+          if (EVAL == A3D_EVAL_NAIVE) {
+            cat = 0;
+          } else if (is_frontier_voxel(m, ct, e, cc)) {
+            cat = 0;
+          }
         }
       }
-      if (cat != kCatNone) lc.packed += 1ull << (kFieldBits * cat);
+      lc.packed += 1ull << (kFieldBits * cat);
       if (DIGEST) {
         h = digest_entry(cc);
         lc.digest += h;
@@ -237,7 +246,9 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     }
     if (first) {
       // record of the part's first entry, written once
-      rec.first_key[rec_at] = pack_key(id, &lc.inexact);
+      unsigned bad = 0;
+      rec.first_key[rec_at] = pack_key(id, &bad);
+      lc.inexact |= bad;
       rec.info[rec_at] = static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0));
       if (DIGEST) rec.first_hash[rec_at] = h;
     }
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   __shared__ unsigned s_mark_list[kMarkCap];   // marking rays of the current diagonal: r << 8 | s
   __shared__ double s_mark_hit[kMarkCap];      // their hit distance (< 0: none)
   __shared__ unsigned long long s_packed, s_digest;
-  __shared__ unsigned s_nvis, s_nsamp, s_inexact;
+  __shared__ unsigned s_nsamp, s_inexact;
   init_center_tables(m, &ct);
 
   const size_t cta_base = static_cast<size_t>(blockIdx.x) * ws.rays_stride;
@@ -490,7 +501,11 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
               double hit_d = -1.0;
               if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, step, role == 2 ? d_mark_end : d_leaf_end,
                                                  rs, lc, ws.rec, rec_at, &hit_d)) {
-                if (rs.prev.g0 != kNoIdent) ws.rec.last_key[rec_at] = pack_key(rs.prev, &lc.inexact);
+                if (rs.prev.g0 != kNoIdent) {
+                  unsigned bad = 0;
+                  ws.rec.last_key[rec_at] = pack_key(rs.prev, &bad);
+                  lc.inexact |= bad;
+                }
                 if (role == 2) {
                   s_mark_hit[mark_idx] = hit_d;
                   fin_mark = true;
@@ -530,8 +545,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
           if (!below) prev = carry_key;
           if (emitted && fk == prev && (info & 16)) {
             // the first entry of this part repeats the previous raw entry: std::unique drops it
-            lc.n_vis--;
-            if ((info & 7) != kCatNone) lc.packed -= 1ull << (kFieldBits * (info & 7));
+            lc.packed -= 1ull << (kFieldBits * (info & 7));
             if (DIGEST) lc.digest -= ws.rec.first_hash[at];
           }
           if (em) carry_key = __shfl_sync(kFull, lk, 31 - __clz(em));
@@ -546,7 +560,6 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
     if (threadIdx.x == 0) {
       s_packed = 0;
       s_digest = 0;
-      s_nvis = 0;
       s_nsamp = 0;
       s_inexact = 0;
     }
@@ -558,12 +571,10 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         pk += __shfl_xor_sync(kFull, pk, off);
         if (DIGEST) dg += __shfl_xor_sync(kFull, dg, off);
       }
-      const unsigned tv = __reduce_add_sync(kFull, lc.n_vis);
       const unsigned tsmp = __reduce_add_sync(kFull, lc.n_samp);
       const unsigned tin = __reduce_or_sync(kFull, lc.inexact);
       if (lane == 0) {
         atomicAdd(&s_packed, pk);
-        atomicAdd(&s_nvis, tv);
         atomicAdd(&s_nsamp, tsmp);
         atomicOr(&s_inexact, tin);
         if (DIGEST) atomicAdd(&s_digest, dg);
@@ -575,7 +586,9 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
       const unsigned long long c0 = s_packed & fmask, c1 = (s_packed >> kFieldBits) & fmask,
                                c2 = (s_packed >> (2 * kFieldBits)) & fmask;
       unsigned inexact = s_inexact;
-      if (s_nvis >= (1u << kFieldBits)) inexact = 1;  // a field may have wrapped
+      // a field may have wrapped if the segment has 2^21 or more samples
+      if (s_nsamp >= (1u << kFieldBits)) inexact = 1;
+      const unsigned long long n_vis_total = c0 + c1 + c2;
       // VoxelTypeEvaluator's switch without breaks (voxel_type_evaluator.cpp:69-85)
       double g = 0.0;
       if (EVAL == A3D_EVAL_VOXEL_TYPE) {
@@ -589,7 +602,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         g = static_cast<double>(c0);
       }
       b.gains[seg] = g;
-      if (b.n_visible) b.n_visible[seg] = s_nvis;
+      if (b.n_visible) b.n_visible[seg] = n_vis_total;
       if (b.n_samples) b.n_samples[seg] = s_nsamp;
       if (DIGEST && b.set_digests) b.set_digests[seg] = s_digest;
       if (inexact) atomicOr(&inexact_flags[seg >> 5], 1u << (seg & 31));
