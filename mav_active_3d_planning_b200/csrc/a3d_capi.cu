@@ -882,6 +882,7 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   for (int i = 0; i < 3; ++i) v.mount_t[i] = p->mount_t[i];
   v.mount_q = Q4{p->mount_q[0], p->mount_q[1], p->mount_q[2], p->mount_q[3]};
   v.n_units = n_units;
+  v.diag_max = std::min(info.c_res_x, info.c_res_y);
   v.unit_diag = c->d_units;
   v.unit_i0 = c->d_units ? c->d_units + n_units : nullptr;
   v.ray_step = info.ray_step;

@@ -24,7 +24,7 @@ struct CasterView {
   // leaf-supply units of k_cast_wave: iterative → unit u covers rays (i, diag-i), i in
   // [unit_i0[u], unit_i0[u]+32) of anti-diagonal unit_diag[u]; simple → rays [32u, 32u+32)
   int32_t n_units;
-  int32_t _pad2;
+  int32_t diag_max;  // longest anti-diagonal = min(res_x, res_y)
   const int32_t* __restrict__ unit_diag;
   const int32_t* __restrict__ unit_i0;
 };

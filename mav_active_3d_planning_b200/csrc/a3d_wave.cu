@@ -155,9 +155,59 @@ __device__ __forceinline__ void ray_begin(RayState& rs, const CasterView& c, con
   rs.r = r;
 }
 
+// Everything about one sample that the list logic needs.
+struct SampleInfo {
+  int st;    // voxel state at the sample point
+  int cs;    // state | observed << 2 at the centre of the voxel getVoxelCenter names
+  Ident id;  // identity of that voxel
+};
+
+// Rare cases of a sample, evaluated literally: artefact voxel indices, interpolation cells that
+// straddle the occupied threshold, centre voxel != state voxel.
+__device__ __noinline__ SampleInfo sample_slow(const MapView& m, const CenterTables& ct, float pf0,
+                                               float pf1, float pf2, int b0, int b1, int b2, int slot,
+                                               int vi0, int vi1, int vi2, unsigned* inexact) {
+  const float pf[3] = {pf0, pf1, pf2};
+  const int bi[3] = {b0, b1, b2}, vi[3] = {vi0, vi1, vi2};
+  float origin[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) origin[a] = origin_point(bi[a], m.bs_f);
+  SampleInfo si;
+  int vs[3];
+  uint32_t word;
+  bool vs_ok;
+  si.st = voxel_state_in_block(m, ct, pf, bi, origin, slot, vs, &word, &vs_ok);
+  const unsigned vmax = static_cast<unsigned>(m.vps);
+  const bool canonical = (static_cast<unsigned>(vi0) < vmax) & (static_cast<unsigned>(vi1) < vmax) &
+                         (static_cast<unsigned>(vi2) < vmax);
+  if (canonical) {
+    si.id = Ident{b0 * m.vps + vi0, b1 * m.vps + vi1, b2 * m.vps + vi2};
+  } else {
+    si.id = make_ident_slow(m, ct, b0, b1, b2, vi0, vi1, vi2, inexact);
+  }
+  if (vs_ok & (vi0 == vs[0]) & (vi1 == vs[1]) & (vi2 == vs[2])) {
+    si.cs = centre_state_from_word(word);
+  } else {
+    double cp[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      cp[a] = (vi[a] >= -1 && vi[a] <= m.vps) ? ct.d[vi[a] + 1]
+                                              : static_cast<double>(center_point(vi[a], m.vs_f));
+    const D3 cc{__dadd_rn(static_cast<double>(origin[0]), cp[0]),
+                __dadd_rn(static_cast<double>(origin[1]), cp[1]),
+                __dadd_rn(static_cast<double>(origin[2]), cp[2])};
+    si.cs = centre_state(m, ct, cc, slot, vi);
+  }
+  return si;
+}
+
 // One sample of the lane's ray.  Returns true when the part is finished (hit or end reached);
 // *hit_d = distance of the OCCUPIED sample that ended it (unchanged otherwise).
 // rec_at: index of this part's record.  Precondition: rs.d < d_end.
+//
+// The common case — allocated or unallocated block, in-range voxel indices that agree between
+// getVoxelState's and getVoxelCenter's index arithmetic, definite cell class — is straight-line
+// code around one meta-word load; everything else goes through sample_slow().
 template <int CASTER, int EVAL, bool DIGEST>
 __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
                                          const ViewShared& vw, const double step, const double d_end,
@@ -170,90 +220,87 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
                         __dadd_rn(vw.P0[2], __dmul_rn(d_this, rs.dz))};
   rs.d = __dadd_rn(d_this, step);
   lc.n_samp++;
-  const float pf[3] = {__double2float_rn(pp[0]), __double2float_rn(pp[1]), __double2float_rn(pp[2])};
-  int bi[3];
-  float origin[3];
+  float pf[3], origin[3];
+  int bi[3], vs[3], vi[3];
+  int sc = 0;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
+    pf[a] = __double2float_rn(pp[a]);
     bi[a] = grid_index(pf[a], m.bs_inv_f);
     origin[a] = origin_point(bi[a], m.bs_f);
+    // voxel index as getVoxelState derives it (float subtraction) ...
+    vs[a] = grid_index(__fsub_rn(pf[a], origin[a]), m.vs_inv_f);
+    // ... and as getVoxelCenter derives it (double subtraction, voxblox.cpp:74-77)
+    vi[a] = grid_index(__double2float_rn(__dsub_rn(pp[a], static_cast<double>(origin[a]))),
+                       m.vs_inv_f);
+  }
+  const unsigned vmax = static_cast<unsigned>(m.vps);
+  const bool in_range = (static_cast<unsigned>(vs[0]) < vmax) & (static_cast<unsigned>(vs[1]) < vmax) &
+                        (static_cast<unsigned>(vs[2]) < vmax);
+  const bool same = (vs[0] == vi[0]) & (vs[1] == vi[1]) & (vs[2] == vi[2]);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float centre = __fadd_rn(origin[a], ct.f[min(static_cast<unsigned>(vs[a]), vmax) + 1]);
+    sc |= (__fsub_rn(pf[a], centre) < 0.0f) ? (1 << a) : 0;
   }
   const int slot = find_slot(m, bi[0], bi[1], bi[2]);
-  int vs[3];
-  uint32_t word;
-  bool vs_ok;
-  const int st = voxel_state_in_block(m, ct, pf, bi, origin, slot, vs, &word, &vs_ok);
-  if (ITER || st != 0) {
-    // getVoxelCenter identity (voxblox.cpp:66-81)
-    int vi[3];
+  uint32_t word = kWordNoBlock;
+  if (slot >= 0 && in_range)
+    word = __ldg(m.mword + static_cast<size_t>(slot) * m.nv + (vs[2] * m.vps + vs[1]) * m.vps + vs[0]);
+  const int cls = (word >> (2 * sc)) & 3;
+  SampleInfo si;
+  si.st = cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
+  si.cs = centre_state_from_word(word);
+  si.id = Ident{bi[0] * m.vps + vi[0], bi[1] * m.vps + vi[1], bi[2] * m.vps + vi[2]};
+  if (!(in_range & same) | (cls == kCellMixed)) {
+    unsigned bad = 0;
+    si = sample_slow(m, ct, pf[0], pf[1], pf[2], bi[0], bi[1], bi[2], slot, vi[0], vi[1], vi[2], &bad);
+    lc.inexact |= bad;
+  }
+  const bool emit = ITER || si.st != 0;
+  bool keep = emit & ((si.id.g0 != rs.prev.g0) | (si.id.g1 != rs.prev.g1) | (si.id.g2 != rs.prev.g2));
+  const bool first = emit & (rs.prev.g0 == kNoIdent);
+  if (emit) rs.prev = si.id;
+  D3 cc{0.0, 0.0, 0.0};
+  if (DIGEST || e.bv_is_setup || EVAL == A3D_EVAL_FRONTIER) {
+    double cp[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
-      vi[a] = grid_index(__double2float_rn(__dsub_rn(pp[a], static_cast<double>(origin[a]))),
-                         m.vs_inv_f);
-    const unsigned vmax = static_cast<unsigned>(m.vps);
-    const bool canonical = (static_cast<unsigned>(vi[0]) < vmax) & (static_cast<unsigned>(vi[1]) < vmax) &
-                           (static_cast<unsigned>(vi[2]) < vmax);
-    Ident id{bi[0] * m.vps + vi[0], bi[1] * m.vps + vi[1], bi[2] * m.vps + vi[2]};
-    if (!canonical) {
-      unsigned bad = 0;
-      id = make_ident_slow(m, ct, bi[0], bi[1], bi[2], vi[0], vi[1], vi[2], &bad);
-      lc.inexact |= bad;
-    }
-    const bool first = rs.prev.g0 == kNoIdent;
-    bool keep = (id.g0 != rs.prev.g0) | (id.g1 != rs.prev.g1) | (id.g2 != rs.prev.g2);
-    rs.prev = id;
-    D3 cc{0.0, 0.0, 0.0};
-    const bool need_cc = DIGEST || e.bv_is_setup || EVAL == A3D_EVAL_FRONTIER || !canonical;
-    if (need_cc) {
-      double cp[3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-        cp[a] = (vi[a] >= -1 && vi[a] <= m.vps) ? ct.d[vi[a] + 1]
-                                                : static_cast<double>(center_point(vi[a], m.vs_f));
-      cc.x = __dadd_rn(static_cast<double>(origin[0]), cp[0]);
-      cc.y = __dadd_rn(static_cast<double>(origin[1]), cp[1]);
-      cc.z = __dadd_rn(static_cast<double>(origin[2]), cp[2]);
-    }
+      cp[a] = (vi[a] >= -1 && vi[a] <= m.vps) ? ct.d[vi[a] + 1]
+                                              : static_cast<double>(center_point(vi[a], m.vs_f));
+    cc.x = __dadd_rn(static_cast<double>(origin[0]), cp[0]);
+    cc.y = __dadd_rn(static_cast<double>(origin[1]), cp[1]);
+    cc.z = __dadd_rn(static_cast<double>(origin[2]), cp[2]);
     if (e.bv_is_setup) keep = keep && bv_contains(e, cc);  // simulated_sensor_evaluator.cpp:50-57
-    int cat = kCatNone;
-    unsigned long long h = 0;
-    if (keep) {
-      // state / observed flag at the emitted centre: the meta word of its voxel — usually the word
-      // getVoxelState just loaded (same voxel index from both index computations)
-      int cs;
-      if (vs_ok & (vi[0] == vs[0]) & (vi[1] == vs[1]) & (vi[2] == vs[2])) {
-        cs = centre_state_from_word(word);
-      } else {
-        cs = centre_state(m, ct, cc, slot, vi);
+  }
+  int cat;
+  if (EVAL == A3D_EVAL_VOXEL_TYPE) {
+    cat = si.cs & 3;  // retained entries are always inside the bounding volume
+  } else {
+    cat = 1;
+    if (keep && !(si.cs & 4)) {
+      if (EVAL == A3D_EVAL_NAIVE) {
+        cat = 0;
+      } else if (is_frontier_voxel(m, ct, e, cc)) {
+        cat = 0;
       }
-      if (EVAL == A3D_EVAL_VOXEL_TYPE) {
-        cat = cs & 3;  // retained entries are always inside the bounding volume
-      } else {
-        cat = 1;
-        if (!(cs & 4)) {
-          if (EVAL == A3D_EVAL_NAIVE) {
-            cat = 0;
-          } else if (is_frontier_voxel(m, ct, e, cc)) {
-            cat = 0;
-          }
-        }
-      }
-      lc.packed += 1ull << (kFieldBits * cat);
-      if (DIGEST) {
-        h = digest_entry(cc);
-        lc.digest += h;
-      }
-    }
-    if (first) {
-      // record of the part's first entry, written once
-      unsigned bad = 0;
-      rec.first_key[rec_at] = pack_key(id, &bad);
-      lc.inexact |= bad;
-      rec.info[rec_at] = static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0));
-      if (DIGEST) rec.first_hash[rec_at] = h;
     }
   }
-  if (st == 0) {
+  lc.packed += static_cast<unsigned long long>(keep) << (kFieldBits * cat);
+  unsigned long long h = 0;
+  if (DIGEST) {
+    h = keep ? digest_entry(cc) : 0ull;
+    lc.digest += h;
+  }
+  if (first) {
+    // record of the part's first entry, written once
+    unsigned bad = 0;
+    rec.first_key[rec_at] = pack_key(si.id, &bad);
+    lc.inexact |= bad;
+    rec.info[rec_at] = static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0));
+    if (DIGEST) rec.first_hash[rec_at] = h;
+  }
+  if (si.st == 0) {
     *hit_d = d_this;
     return true;
   }
@@ -285,8 +332,11 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   __shared__ volatile int s_done_diag;         // anti-diagonals whose table entries are final
   __shared__ unsigned s_unit_cursor;           // next leaf-supply unit
   __shared__ unsigned s_pending[2][kPendCap];  // per-warp ring of ready rays waiting for a lane
-  __shared__ unsigned s_mark_list[kMarkCap];   // marking rays of the current diagonal: r << 8 | s
-  __shared__ double s_mark_hit[kMarkCap];      // their hit distance (< 0: none)
+  // marking rays of the current diagonal (dynamic shared memory, sized by the longest diagonal):
+  // their hit distance (< 0: none) and r << 8 | s
+  extern __shared__ double s_dyn[];
+  double* const s_mark_hit = s_dyn;
+  unsigned* const s_mark_list = reinterpret_cast<unsigned*>(s_dyn + c.diag_max);
   __shared__ unsigned long long s_packed, s_digest;
   __shared__ unsigned s_nsamp, s_inexact;
   init_center_tables(m, &ct);
@@ -622,9 +672,11 @@ static void launch_wave_t(cudaStream_t st, const MapView& m, const CasterView& c
                           const Batch& b, bool digest, int grid, const WaveScratch& ws,
                           unsigned int* inexact) {
   if (digest)
-    k_cast_wave<CASTER, EVAL, true><<<grid, kWaveThreads, 0, st>>>(m, c, e, b, ws, inexact);
+    k_cast_wave<CASTER, EVAL, true>
+        <<<grid, kWaveThreads, static_cast<size_t>(c.diag_max) * 12, st>>>(m, c, e, b, ws, inexact);
   else
-    k_cast_wave<CASTER, EVAL, false><<<grid, kWaveThreads, 0, st>>>(m, c, e, b, ws, inexact);
+    k_cast_wave<CASTER, EVAL, false>
+        <<<grid, kWaveThreads, static_cast<size_t>(c.diag_max) * 12, st>>>(m, c, e, b, ws, inexact);
 }
 
 template <int CASTER>
