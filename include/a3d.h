@@ -205,6 +205,12 @@ int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* e
 int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* centres,
                          double* gain_out, int64_t* n_left_out, uint8_t* keep_out);
 
+/* clear_from_parents step of SimulatedSensorEvaluator::computeGain
+ * (simulated_sensor_evaluator.cpp:60-76) for ONE ancestor: keep_inout[i] is cleared if centres[i]
+ * occurs anywhere in other[0..m) (exact comparison of the three doubles, like std::find). */
+int a3d_filter_not_in(a3d_ctx* ctx, int64_t n, const double* centres, int64_t m,
+                      const double* other, uint8_t* keep_inout);
+
 /* BoundingVolume::contains (core/src/data/bounding_volume.cpp:33-57), batched. */
 int a3d_bv_contains(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* pts, uint8_t* out);
 

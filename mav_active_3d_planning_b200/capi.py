@@ -35,7 +35,7 @@ EXPORTS = [
     "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
     "a3d_map_distance", "a3d_caster_create", "a3d_caster_destroy", "a3d_caster_get_info",
     "a3d_caster_direction", "a3d_eval_create", "a3d_eval_destroy", "a3d_compute_gains",
-    "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_bv_contains",
+    "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_filter_not_in", "a3d_bv_contains",
 ]
 
 
@@ -161,6 +161,7 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_visible_voxels.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, i64, P(i64), P(i64), P(dbl)]
     lib.a3d_gain_from_voxels.argtypes = [vp, vp, i64, vp, P(dbl), P(i64), vp]
     lib.a3d_bv_contains.argtypes = [vp, vp, i64, vp, vp]
+    lib.a3d_filter_not_in.argtypes = [vp, i64, vp, i64, vp, vp]
     _lib = lib
     return lib
 
@@ -369,6 +370,15 @@ class Context:
         self._ck(self.lib.a3d_gain_from_voxels(self.h, evaluator.h, len(centres), _ptr(centres),
                                                C.byref(gain), C.byref(left), _ptr(keep)))
         return float(gain.value), int(left.value), keep
+
+    def filter_not_in(self, centres, other):
+        """keep mask of ``centres`` entries that do not occur in ``other`` (clear_from_parents)."""
+        centres = _pts(centres) if len(centres) else np.zeros((0, 3))
+        other = _pts(other) if len(other) else np.zeros((0, 3))
+        keep = np.ones(len(centres), np.uint8)
+        self._ck(self.lib.a3d_filter_not_in(self.h, len(centres), _ptr(centres), len(other),
+                                            _ptr(other), _ptr(keep)))
+        return keep
 
     def bv_contains(self, evaluator, pts):
         pts = _pts(pts)

@@ -1130,6 +1130,29 @@ int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const do
   return A3D_OK;
 }
 
+int a3d_filter_not_in(a3d_ctx* ctx, int64_t n, const double* centres, int64_t m,
+                      const double* other, uint8_t* keep_inout) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (n < 0 || m < 0 || (n > 0 && (!centres || !keep_inout)) || (m > 0 && !other))
+    return ctx->fail(A3D_ERR_INVALID, "bad argument");
+  if (n == 0 || m == 0) return A3D_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->sc_pts.reserve(3 * n));
+  CK(ctx->sc_out.reserve(3 * m));
+  CK(ctx->sc_u8.reserve(n));
+  CK(cudaMemcpyAsync(ctx->sc_pts.p, centres, 24 * static_cast<size_t>(n), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaMemcpyAsync(ctx->sc_out.p, other, 24 * static_cast<size_t>(m), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaMemcpyAsync(ctx->sc_u8.p, keep_inout, n, cudaMemcpyHostToDevice, ctx->stream));
+  launch_filter_not_in(ctx->stream, n, ctx->sc_pts.p, m, ctx->sc_out.p, ctx->sc_u8.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(keep_inout, ctx->sc_u8.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return A3D_OK;
+}
+
 int a3d_bv_contains(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* pts, uint8_t* out) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!eval || eval->ctx != ctx) return ctx->fail(A3D_ERR_INVALID, "eval missing");

@@ -540,6 +540,39 @@ void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, co
 int cast_gain_block_threads() { return kCastBlock; }
 
 // ---------------------------------------------------------------------------------------------
+// clear_from_parents (simulated_sensor_evaluator.cpp:60-76): keep[i] = 0 if centre i occurs anywhere
+// in the ancestor's stored list (exact double comparison, like std::find on Eigen::Vector3d).
+__global__ void k_filter_not_in(long long n, const double* __restrict__ a, long long m,
+                                const double* __restrict__ other, uint8_t* __restrict__ keep) {
+  __shared__ double tile[256 * 3];
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  double x = 0, y = 0, z = 0;
+  if (i < n) {
+    x = a[3 * i];
+    y = a[3 * i + 1];
+    z = a[3 * i + 2];
+  }
+  bool found = false;
+  for (long long t0 = 0; t0 < m; t0 += 256) {
+    const int cnt = static_cast<int>(min(256LL, m - t0));
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt * 3; k += blockDim.x) tile[k] = other[3 * t0 + k];
+    __syncthreads();
+    if (i < n && !found) {
+      for (int k = 0; k < cnt; ++k)
+        found |= (tile[3 * k] == x) & (tile[3 * k + 1] == y) & (tile[3 * k + 2] == z);
+    }
+  }
+  if (i < n && found) keep[i] = 0;
+}
+
+void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long long m,
+                          const double* other, uint8_t* keep) {
+  if (n <= 0 || m <= 0) return;
+  k_filter_not_in<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(n, a, m, other, keep);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4: fold of a stored list.  counters[0..5] VoxelType state counts / [0] gain count, [6] survivors.
 __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
                                    const double* __restrict__ centres,

@@ -71,6 +71,8 @@ void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, co
 void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& e, long long n,
                              const double* centres, unsigned long long* counters /*8*/,
                              uint8_t* keep);
+void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long long m,
+                          const double* other, uint8_t* keep);
 int cast_gain_block_threads();
 // throughput kernel (a3d_wave.cu)
 size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride);

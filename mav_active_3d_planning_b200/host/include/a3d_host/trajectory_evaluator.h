@@ -1,0 +1,139 @@
+// trajectory_evaluator.h — gain evaluators of the path.
+//   TrajectoryEvaluator (+ Cost/Value/NextSelector/EvaluatorUpdater bases)
+//                               core/include/.../module/trajectory_evaluator.h:24-90, src/module/trajectory_evaluator.cpp
+//   SimulatedSensorEvaluator    .../trajectory_evaluator/simulated_sensor_evaluator.h:18-60, .cpp:16-91
+//   VoxelTypeEvaluator          .../voxel_type_evaluator.h, .cpp:19-89
+//   NaiveEvaluator              .../naive_evaluator.h, .cpp:15-38
+//   FrontierEvaluator           .../frontier_evaluator.h, .cpp:15-124
+// computeGains() is the additive batch entry point: the reference evaluates one
+// segment per call (online_planner.cpp:414-416); a B200 wants thousands per launch.
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "a3d_host/sensor_model.h"
+
+struct a3d_eval;
+
+namespace active_3d_planning {
+
+class CostComputer : public Module {
+ public:
+  explicit CostComputer(PlannerI& planner) : Module(planner) {}  // NOLINT
+  virtual bool computeCost(TrajectorySegment* traj_in) = 0;
+};
+class ValueComputer : public Module {
+ public:
+  explicit ValueComputer(PlannerI& planner) : Module(planner) {}  // NOLINT
+  virtual bool computeValue(TrajectorySegment* traj_in) = 0;
+};
+class NextSelector : public Module {
+ public:
+  explicit NextSelector(PlannerI& planner) : Module(planner) {}  // NOLINT
+  virtual int selectNextBest(TrajectorySegment* traj_in) = 0;
+};
+class EvaluatorUpdater : public Module {
+ public:
+  explicit EvaluatorUpdater(PlannerI& planner) : Module(planner) {}  // NOLINT
+  virtual bool updateSegment(TrajectorySegment* segment) = 0;
+};
+
+class TrajectoryEvaluator : public Module {
+ public:
+  explicit TrajectoryEvaluator(PlannerI& planner);  // NOLINT
+  virtual ~TrajectoryEvaluator() = default;
+  virtual bool computeGain(TrajectorySegment* traj_in) = 0;
+  // these four delegate to modules created lazily from <ns>/cost_computer etc.; the concrete cost /
+  // value / selector / updater types are outside this path — register your own
+  virtual bool computeCost(TrajectorySegment* traj_in);
+  virtual bool computeValue(TrajectorySegment* traj_in);
+  virtual int selectNextBest(TrajectorySegment* traj_in);
+  virtual bool updateSegment(TrajectorySegment* segment);
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+
+ protected:
+  std::unique_ptr<BoundingVolume> bounding_volume_;
+  std::string p_cost_args_, p_value_args_, p_next_args_, p_updater_args_;
+  std::unique_ptr<CostComputer> cost_computer_;
+  std::unique_ptr<ValueComputer> value_computer_;
+  std::unique_ptr<NextSelector> next_selector_;
+  std::unique_ptr<EvaluatorUpdater> evaluator_updater_;
+};
+
+namespace trajectory_evaluator {
+
+// what computeGain stores in TrajectorySegment::info
+struct SimulatedSensorInfo : public TrajectoryInfo {
+  virtual ~SimulatedSensorInfo() = default;
+  std::vector<Eigen::Vector3d> visible_voxels;
+};
+
+class SimulatedSensorEvaluator : public TrajectoryEvaluator {
+ public:
+  explicit SimulatedSensorEvaluator(PlannerI& planner);  // NOLINT
+  ~SimulatedSensorEvaluator() override;
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+  bool computeGain(TrajectorySegment* traj_in) override;
+
+  // Batch: gains of many segments in one launch (no voxel lists are stored in the segments).
+  // Returns false if clear_from_parents is set (needs the per-segment lists).
+  virtual bool computeGains(const std::vector<TrajectorySegment*>& segments);
+  // fold of the list already stored in the segment (SimulatedSensorUpdater path)
+  virtual bool computeGainFromVisibleVoxels(TrajectorySegment* traj_in);
+  SensorModel* sensorModel() { return sensor_model_.get(); }
+
+ protected:
+  virtual bool storeTrajectoryInformation(TrajectorySegment* traj_in,
+                                          const std::vector<Eigen::Vector3d>& new_voxels);
+  virtual int evalKind() const = 0;
+  // evaluator-specific parameters → a3d_eval_params (called at the end of setupFromParamMap)
+  void buildEval();
+  virtual void fillEvalParams(void* a3d_eval_params_ptr) {}
+  map::OccupancyMap* map_;
+  map::VoxbloxMap* gpu_map_;
+  std::unique_ptr<SensorModel> sensor_model_;
+  a3d_eval* eval_;
+  bool p_clear_from_parents_, p_visualize_sensor_view_;
+};
+
+class VoxelTypeEvaluator : public SimulatedSensorEvaluator {
+ public:
+  explicit VoxelTypeEvaluator(PlannerI& planner) : SimulatedSensorEvaluator(planner) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+
+ protected:
+  int evalKind() const override;
+  void fillEvalParams(void* p) override;
+  static ModuleFactoryRegistry::Registration<VoxelTypeEvaluator> registration;
+  double p_gain_unknown_, p_gain_occupied_, p_gain_free_, p_gain_unknown_outer_, p_gain_occupied_outer_,
+      p_gain_free_outer_, c_min_gain_, c_max_gain_;
+  std::unique_ptr<BoundingVolume> outer_volume_;  // constructed, never consulted (as in the reference)
+};
+
+class NaiveEvaluator : public SimulatedSensorEvaluator {
+ public:
+  explicit NaiveEvaluator(PlannerI& planner) : SimulatedSensorEvaluator(planner) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+
+ protected:
+  int evalKind() const override;
+  static ModuleFactoryRegistry::Registration<NaiveEvaluator> registration;
+};
+
+class FrontierEvaluator : public SimulatedSensorEvaluator {
+ public:
+  explicit FrontierEvaluator(PlannerI& planner) : SimulatedSensorEvaluator(planner) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+
+ protected:
+  int evalKind() const override;
+  void fillEvalParams(void* p) override;
+  static ModuleFactoryRegistry::Registration<FrontierEvaluator> registration;
+  bool p_accurate_frontiers_, p_surface_frontiers_;
+  double p_checking_distance_;
+};
+
+}  // namespace trajectory_evaluator
+}  // namespace active_3d_planning

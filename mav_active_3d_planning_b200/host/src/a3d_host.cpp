@@ -1,0 +1,847 @@
+// a3d_host.cpp — C++ host side of the view-gain path: the reference's module classes as thin shells
+// over the C ABI (include/a3d.h).  No map arithmetic, ray casting or gain folding happens here; the
+// host code parses parameters, samples view points, moves buffers and keeps the reference's
+// ownership / error conventions.  Reference citations are relative to the reference checkout.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <numeric>
+#include <stdexcept>
+
+#include "../../../include/a3d.h"
+#include "a3d_host/trajectory_evaluator.h"
+#include "a3d_host/yaml_factory.h"
+
+namespace active_3d_planning {
+
+[[noreturn]] void a3d_fatal(const std::string& message) {
+  // the reference aborts through glog's LOG(FATAL); a throw lets embedding code decide
+  throw std::runtime_error(message);
+}
+
+// ---- module system ------------------------------------------------------------------------------
+void ModuleBase::assureParamsValid() {  // core/src/module/module.cpp:11-16
+  std::string error_message;
+  if (!checkParamsValid(&error_message)) {
+    throw std::invalid_argument("Invalid parameters: " + error_message);
+  }
+}
+
+ModuleFactoryRegistry& ModuleFactoryRegistry::Instance() {
+  static ModuleFactoryRegistry instance;
+  return instance;
+}
+ModuleFactoryRegistry::ModuleMap& ModuleFactoryRegistry::getRegistryMap() {
+  static ModuleMap module_map;
+  return module_map;
+}
+std::string ModuleFactoryRegistry::listTypes() {
+  std::string out;
+  for (const auto& kv : getRegistryMap()) out += (out.empty() ? "" : ", ") + kv.first;
+  return out;
+}
+bool ModuleFactoryRegistry::isRegistered(const std::string& name) {
+  return getRegistryMap().count(name) != 0;
+}
+
+void ModuleFactory::getDefaultType(const std::type_index& module_index, std::string* type) {
+  // module_factory.cpp:14-25 — of the reference's defaults only BoundingVolume is on this path
+  if (module_index == std::type_index(typeid(BoundingVolume))) *type = "BoundingVolume";
+}
+void ModuleFactory::registerLinkableModule(const std::string& name, Module* module) {
+  linkable_module_list_[name] = module;  // module_factory.cpp:27-31
+}
+Module* ModuleFactory::readLinkableModule(const std::string& name) {
+  auto it = linkable_module_list_.find(name);  // module_factory.cpp:33-41
+  if (it == linkable_module_list_.end()) {
+    printError("No module with name '" + name + "' registered to the linkable module list.");
+    return nullptr;
+  }
+  return it->second;
+}
+
+// ---- data -----------------------------------------------------------------------------------------
+TrajectorySegment* TrajectorySegment::spawnChild() {
+  children.push_back(std::unique_ptr<TrajectorySegment>(new TrajectorySegment()));
+  children.back()->parent = this;
+  return children.back().get();
+}
+void TrajectorySegment::getChildren(std::vector<TrajectorySegment*>* result) {
+  for (auto& c : children) result->push_back(c.get());
+}
+void TrajectorySegment::getLeaves(std::vector<TrajectorySegment*>* result) {
+  if (children.empty()) {
+    result->push_back(this);
+    return;
+  }
+  for (auto& c : children) c->getLeaves(result);
+}
+void TrajectorySegment::getTree(std::vector<TrajectorySegment*>* result) {
+  result->push_back(this);
+  for (auto& c : children) c->getTree(result);
+}
+void TrajectorySegment::getTree(std::vector<TrajectorySegment*>* result, int maxdepth) {
+  result->push_back(this);
+  if (maxdepth > 0)
+    for (auto& c : children) c->getTree(result, maxdepth - 1);
+}
+TrajectorySegment TrajectorySegment::shallowCopy() {
+  TrajectorySegment copy;
+  copy.trajectory = trajectory;
+  copy.gain = gain;
+  copy.cost = cost;
+  copy.value = value;
+  copy.tg_visited = tg_visited;
+  copy.parent = parent;
+  return copy;
+}
+
+ModuleFactoryRegistry::Registration<BoundingVolume> BoundingVolume::registration("BoundingVolume");
+
+BoundingVolume::BoundingVolume(PlannerI& planner)
+    : Module(planner), is_setup(false), x_min(0), x_max(0), y_min(0), y_max(0), z_min(0), z_max(0),
+      rotation(0) {}
+
+void BoundingVolume::setupFromParamMap(Module::ParamMap* param_map) {  // bounding_volume.cpp:12-31
+  setParam<double>(param_map, "x_min", &x_min, 0.0);
+  setParam<double>(param_map, "x_max", &x_max, 0.0);
+  setParam<double>(param_map, "y_min", &y_min, 0.0);
+  setParam<double>(param_map, "y_max", &y_max, 0.0);
+  setParam<double>(param_map, "z_min", &z_min, 0.0);
+  setParam<double>(param_map, "z_max", &z_max, 0.0);
+  setParam<double>(param_map, "rotation", &rotation, 0.0);
+  rotation_quat = Eigen::AngleAxisd(rotation * M_PI / -180.0, Eigen::Vector3d::UnitZ());
+  is_setup = x_max > x_min && y_max > y_min && z_max > z_min;
+}
+
+bool BoundingVolume::contains(const Eigen::Vector3d& point) {  // bounding_volume.cpp:33-57
+  // single points are host logic of the planner (RRT sampling etc.); the per-voxel tests of the
+  // hot path run on the device (a3d_bv_contains / inside the cast kernels)
+  if (!is_setup) return true;
+  const Eigen::Vector3d r = rotation_quat * point;
+  return !(r.x() < x_min || r.x() > x_max || r.y() < y_min || r.y() > y_max || r.z() < z_min ||
+           r.z() > z_max);
+}
+
+// ---- map ------------------------------------------------------------------------------------------
+namespace map {
+
+ModuleFactoryRegistry::Registration<VoxbloxMap> VoxbloxMap::registration("VoxbloxMap");
+
+VoxbloxMap::VoxbloxMap(PlannerI& planner)
+    : TSDFMap(planner), ctx_(nullptr), p_voxel_size_(0.1), p_voxels_per_side_(16), c_voxel_size_(0.1),
+      c_maximum_weight_(10000.0), p_device_(0) {}
+
+VoxbloxMap::~VoxbloxMap() {
+  if (ctx_) a3d_ctx_destroy(ctx_);
+}
+
+void VoxbloxMap::check(int rc, const char* what) {
+  if (rc == A3D_OK) return;
+  planner_.printError(std::string("VoxbloxMap: ") + what + ": " + a3d_last_error(ctx_));
+  throw std::runtime_error(std::string(what) + ": " + a3d_last_error(ctx_));
+}
+
+void VoxbloxMap::setupFromParamMap(Module::ParamMap* param_map) {
+  setParam<double>(param_map, "tsdf_voxel_size", &p_voxel_size_, 0.1);
+  setParam<int>(param_map, "tsdf_voxels_per_side", &p_voxels_per_side_, 16);
+  setParam<double>(param_map, "max_weight", &c_maximum_weight_, 10000.0);
+  setParam<int>(param_map, "device", &p_device_, 0);
+  if (!(p_voxel_size_ > 0.0) || p_voxels_per_side_ < 1) return;  // reported by checkParamsValid
+  const int rc = a3d_ctx_create(p_device_, &ctx_);
+  if (rc != A3D_OK) {
+    // no CPU fallback: a map without a device cannot answer anything
+    throw std::runtime_error(std::string("VoxbloxMap: no usable B200 device: ") + a3d_last_error(nullptr));
+  }
+  check(a3d_map_config(ctx_, static_cast<float>(p_voxel_size_), p_voxels_per_side_), "a3d_map_config");
+  c_voxel_size_ = a3d_map_voxel_size(ctx_);  // double(float voxel size), voxblox.cpp:26
+}
+
+bool VoxbloxMap::checkParamsValid(std::string* error_message) {
+  if (!(p_voxel_size_ > 0.0)) {
+    *error_message = "tsdf_voxel_size expected > 0.0";
+    return false;
+  }
+  if (p_voxels_per_side_ < 1 || p_voxels_per_side_ > 64) {
+    *error_message = "tsdf_voxels_per_side expected in [1, 64]";
+    return false;
+  }
+  return true;
+}
+
+bool VoxbloxMap::uploadBlocks(int n, const int32_t* block_idx, const float* esdf_distance,
+                              const uint8_t* esdf_observed, const float* tsdf_weight) {
+  check(a3d_map_upload_blocks(ctx_, n, block_idx, esdf_distance, esdf_observed, tsdf_weight),
+        "a3d_map_upload_blocks");
+  return true;
+}
+bool VoxbloxMap::removeBlocks(int n, const int32_t* block_idx) {
+  check(a3d_map_remove_blocks(ctx_, n, block_idx), "a3d_map_remove_blocks");
+  return true;
+}
+int64_t VoxbloxMap::numBlocks() const { return a3d_map_num_blocks(ctx_); }
+
+bool VoxbloxMap::isTraversable(const Eigen::Vector3d& position, const Eigen::Quaterniond&) {
+  // voxblox.cpp:32-41: observed (interpolation succeeds) and farther than the collision radius
+  double d = 0.0;
+  uint8_t ok = 0;
+  check(a3d_map_distance(ctx_, 1, position.data(), &d, &ok), "a3d_map_distance");
+  return ok && d > planner_.getSystemConstraints().collision_radius;
+}
+bool VoxbloxMap::isObserved(const Eigen::Vector3d& point) {
+  uint8_t o = 0;
+  check(a3d_map_is_observed(ctx_, 1, point.data(), &o), "a3d_map_is_observed");
+  return o != 0;
+}
+unsigned char VoxbloxMap::getVoxelState(const Eigen::Vector3d& point) {
+  uint8_t s = UNKNOWN;
+  check(a3d_map_voxel_state(ctx_, 1, point.data(), &s), "a3d_map_voxel_state");
+  return s;
+}
+void VoxbloxMap::getVoxelStates(const std::vector<Eigen::Vector3d>& points,
+                                std::vector<unsigned char>* states) {
+  std::vector<double> flat(points.size() * 3);
+  for (size_t i = 0; i < points.size(); ++i)
+    for (int k = 0; k < 3; ++k) flat[3 * i + k] = points[i][k];
+  states->assign(points.size(), UNKNOWN);
+  check(a3d_map_voxel_state(ctx_, static_cast<int64_t>(points.size()), flat.data(), states->data()),
+        "a3d_map_voxel_state");
+}
+double VoxbloxMap::getVoxelSize() { return c_voxel_size_; }
+bool VoxbloxMap::getVoxelCenter(Eigen::Vector3d* center, const Eigen::Vector3d& point) {
+  double c[3];
+  check(a3d_map_voxel_center(ctx_, 1, point.data(), c), "a3d_map_voxel_center");
+  *center = Eigen::Vector3d(c[0], c[1], c[2]);
+  return true;
+}
+double VoxbloxMap::getVoxelDistance(const Eigen::Vector3d&) {
+  // voxblox.cpp:84-98 reads the TSDF layer's distance; only the VoxelWeightEvaluator (outside this
+  // path) uses it and the mirror does not hold TSDF distances yet
+  planner_.printError("VoxbloxMap::getVoxelDistance is not mirrored on the device");
+  return 0.0;
+}
+double VoxbloxMap::getVoxelWeight(const Eigen::Vector3d& point) {
+  double w = 0.0;
+  check(a3d_map_voxel_weight(ctx_, 1, point.data(), &w), "a3d_map_voxel_weight");
+  return w;
+}
+double VoxbloxMap::getMaximumWeight() { return c_maximum_weight_; }
+
+}  // namespace map
+
+// ---- sensor models ----------------------------------------------------------------------------------
+SensorModel::SensorModel(PlannerI& planner) : Module(planner), map_(nullptr) {}
+
+void SensorModel::setupFromParamMap(Module::ParamMap* param_map) {  // sensor_model.cpp:9-27
+  map_ = dynamic_cast<map::OccupancyMap*>(&(planner_.getMap()));
+  if (!map_) planner_.printError("'SensorModel' requires a map of type 'OccupancyMap'!");
+  double tx, ty, tz, rx, ry, rz, rw;
+  setParam<double>(param_map, "mounting_translation_x", &tx, 0.0);
+  setParam<double>(param_map, "mounting_translation_y", &ty, 0.0);
+  setParam<double>(param_map, "mounting_translation_z", &tz, 0.0);
+  setParam<double>(param_map, "mounting_rotation_x", &rx, 0.0);
+  setParam<double>(param_map, "mounting_rotation_y", &ry, 0.0);
+  setParam<double>(param_map, "mounting_rotation_z", &rz, 0.0);
+  setParam<double>(param_map, "mounting_rotation_w", &rw, 1.0);
+  mounting_translation_ = Eigen::Vector3d(tx, ty, tz);
+  mounting_rotation_ = Eigen::Quaterniond(rw, rx, ry, rz).normalized();
+}
+
+namespace sensor_model {
+
+CameraModel::CameraModel(PlannerI& planner)
+    : SensorModel(planner), gpu_map_(nullptr), caster_(nullptr), caster_camera_(nullptr),
+      p_ray_length_(5.0), p_sampling_time_(0.0), p_focal_length_(320.0), p_ray_step_(0.0),
+      p_downsampling_factor_(1.0), p_resolution_x_(640), p_resolution_y_(480), p_test_(false),
+      c_field_of_view_x_(0.0), c_field_of_view_y_(0.0) {}
+
+CameraModel::~CameraModel() {
+  if (caster_) a3d_caster_destroy(caster_);
+  if (caster_camera_) a3d_caster_destroy(caster_camera_);
+}
+
+void CameraModel::setupFromParamMap(Module::ParamMap* param_map) {  // camera_model.cpp:170-183
+  SensorModel::setupFromParamMap(param_map);
+  setParam<double>(param_map, "ray_length", &p_ray_length_, 5.0);
+  setParam<double>(param_map, "sampling_time", &p_sampling_time_, 0.0);
+  setParam<double>(param_map, "focal_length", &p_focal_length_, 320.0);
+  setParam<int>(param_map, "resolution_x", &p_resolution_x_, 640);
+  setParam<int>(param_map, "resolution_y", &p_resolution_y_, 480);
+  setParam<bool>(param_map, "test", &p_test_, false);
+  c_field_of_view_x_ = 2.0 * atan2(p_resolution_x_, p_focal_length_ * 2.0);
+  c_field_of_view_y_ = 2.0 * atan2(p_resolution_y_, p_focal_length_ * 2.0);
+}
+
+bool CameraModel::checkParamsValid(std::string* error_message) {  // camera_model.cpp:185-200
+  if (p_ray_length_ <= 0.0) {
+    *error_message = "ray_length expected > 0.0";
+    return false;
+  } else if (p_focal_length_ <= 0.0) {
+    *error_message = "focal_length expected > 0.0";
+    return false;
+  } else if (p_resolution_x_ <= 0) {
+    *error_message = "resolution_x expected > 0";
+    return false;
+  } else if (p_resolution_y_ <= 0) {
+    *error_message = "resolution_y expected > 0";
+    return false;
+  } else if (!caster_) {
+    *error_message = "ray caster could not be created on the device";
+    return false;
+  }
+  return true;
+}
+
+void CameraModel::buildCasters(Module::ParamMap* param_map) {
+  // ray_step / downsampling_factor and the derived ray grid (simple_ray_caster.cpp:15-30,
+  // iterative_ray_caster.cpp:18-46); the tables are built inside a3d_caster_create
+  setParam<double>(param_map, "ray_step", &p_ray_step_, map_ ? map_->getVoxelSize() : 0.0);
+  setParam<double>(param_map, "downsampling_factor", &p_downsampling_factor_, 1.0);
+  gpu_map_ = dynamic_cast<map::VoxbloxMap*>(map_);
+  if (!gpu_map_) {
+    planner_.printError("'CameraModel' (B200) requires the device map 'VoxbloxMap'!");
+    return;
+  }
+  if (p_ray_length_ <= 0.0 || p_focal_length_ <= 0.0 || p_resolution_x_ <= 0 || p_resolution_y_ <= 0)
+    return;  // reported by checkParamsValid
+  a3d_caster_params p{};
+  p.kind = casterKind();
+  p.resolution_x = p_resolution_x_;
+  p.resolution_y = p_resolution_y_;
+  p.ray_length = p_ray_length_;
+  p.focal_length = p_focal_length_;
+  p.ray_step = p_ray_step_;
+  p.downsampling_factor = p_downsampling_factor_;
+  for (int k = 0; k < 3; ++k) p.mount_t[k] = mounting_translation_[k];
+  p.mount_q[0] = mounting_rotation_.w();
+  p.mount_q[1] = mounting_rotation_.x();
+  p.mount_q[2] = mounting_rotation_.y();
+  p.mount_q[3] = mounting_rotation_.z();
+  if (a3d_caster_create(gpu_map_->context(), &p, &caster_) != A3D_OK) {
+    planner_.printError(std::string("a3d_caster_create: ") + a3d_last_error(gpu_map_->context()));
+    caster_ = nullptr;
+    return;
+  }
+  for (int k = 0; k < 3; ++k) p.mount_t[k] = 0.0;
+  p.mount_q[0] = 1.0;
+  p.mount_q[1] = p.mount_q[2] = p.mount_q[3] = 0.0;
+  if (a3d_caster_create(gpu_map_->context(), &p, &caster_camera_) != A3D_OK) caster_camera_ = nullptr;
+}
+
+int CameraModel::rayGridX() const {
+  a3d_caster_info i{};
+  return caster_ && a3d_caster_get_info(caster_, &i) == A3D_OK ? i.c_res_x : 0;
+}
+int CameraModel::rayGridY() const {
+  a3d_caster_info i{};
+  return caster_ && a3d_caster_get_info(caster_, &i) == A3D_OK ? i.c_res_y : 0;
+}
+int CameraModel::numSections() const {
+  a3d_caster_info i{};
+  return caster_ && a3d_caster_get_info(caster_, &i) == A3D_OK ? i.c_n_sections : 0;
+}
+
+void CameraModel::sampleViewpoints(std::vector<int>* result, const TrajectorySegment& traj_in) {
+  // camera_model.cpp:62-83 (host logic on the trajectory's time stamps)
+  const int n = static_cast<int>(traj_in.trajectory.size());
+  if (p_sampling_time_ <= 0.0) {
+    result->push_back(n - 1);
+    return;
+  }
+  const int64_t sampling_time_ns = static_cast<int64_t>(p_sampling_time_ * 1.0e9);
+  if (sampling_time_ns >= traj_in.trajectory.back().time_from_start_ns) {
+    result->push_back(n - 1);
+    return;
+  }
+  int64_t current_time = sampling_time_ns;
+  for (int i = 0; i < n; ++i) {
+    if (traj_in.trajectory[i].time_from_start_ns >= current_time) {
+      current_time += sampling_time_ns;
+      result->push_back(i);
+    }
+  }
+}
+
+void CameraModel::getDirectionVector(Eigen::Vector3d* result, double relative_x, double relative_y) {
+  *result = Eigen::Vector3d(p_focal_length_, (0.5 - relative_x) * static_cast<double>(p_resolution_x_),
+                            (0.5 - relative_y) * static_cast<double>(p_resolution_y_))
+                .normalized();  // camera_model.cpp:161-168
+}
+
+namespace detail {
+// poses of the sampled trajectory points, flat
+void gatherPoses(const TrajectorySegment& traj, const std::vector<int>& indices, std::vector<double>* pos,
+                 std::vector<double>* quat) {
+  for (int idx : indices) {
+    const EigenTrajectoryPoint& p = traj.trajectory[idx];
+    for (int k = 0; k < 3; ++k) pos->push_back(p.position_W[k]);
+    quat->push_back(p.orientation_W_B.w());
+    quat->push_back(p.orientation_W_B.x());
+    quat->push_back(p.orientation_W_B.y());
+    quat->push_back(p.orientation_W_B.z());
+  }
+}
+
+bool runVisible(a3d_ctx* ctx, a3d_caster* caster, a3d_eval* eval, int n_views, const double* pos,
+                const double* quat, std::vector<Eigen::Vector3d>* out, double* gain, PlannerI& planner) {
+  a3d_caster_info info{};
+  a3d_caster_get_info(caster, &info);
+  int64_t cap = static_cast<int64_t>(std::max(1, n_views)) * info.c_res_x * info.c_res_y *
+                std::max(1, info.samples_per_full_ray);
+  std::vector<double> flat(static_cast<size_t>(cap) * 3);
+  int64_t n = 0, n_samples = 0;
+  const int rc = a3d_visible_voxels(ctx, caster, eval, n_views, pos, quat, flat.data(), cap, &n,
+                                    &n_samples, gain);
+  if (rc != A3D_OK) {
+    planner.printError(std::string("a3d_visible_voxels: ") + a3d_last_error(ctx));
+    return false;
+  }
+  out->reserve(out->size() + static_cast<size_t>(n));
+  for (int64_t i = 0; i < n; ++i)
+    out->push_back(Eigen::Vector3d(flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]));
+  return true;
+}
+}  // namespace detail
+using detail::gatherPoses;
+using detail::runVisible;
+
+bool CameraModel::getVisibleVoxelsFromTrajectory(std::vector<Eigen::Vector3d>* result,
+                                                 const TrajectorySegment& traj_in) {
+  // camera_model.cpp:15-60: sample poses, cast every pose, adjacent-unique over the whole list —
+  // one device call (mounting transform and unique are applied inside)
+  if (!caster_ || traj_in.trajectory.empty()) return false;
+  std::vector<int> indices;
+  sampleViewpoints(&indices, traj_in);
+  std::vector<double> pos, quat;
+  gatherPoses(traj_in, indices, &pos, &quat);
+  const size_t before = result->size();
+  if (!runVisible(gpu_map_->context(), caster_, nullptr, static_cast<int>(indices.size()), pos.data(),
+                  quat.data(), result, nullptr, planner_))
+    return false;
+  // entries appended to a non-empty *result still get the reference's whole-vector unique
+  if (before > 0) result->erase(std::unique(result->begin(), result->end()), result->end());
+  return true;
+}
+
+bool CameraModel::getVisibleVoxels(std::vector<Eigen::Vector3d>* result, const Eigen::Vector3d& position,
+                                   const Eigen::Quaterniond& orientation) {
+  if (!caster_camera_) return false;
+  const double quat[4] = {orientation.w(), orientation.x(), orientation.y(), orientation.z()};
+  return runVisible(gpu_map_->context(), caster_camera_, nullptr, 1, position.data(), quat, result,
+                    nullptr, planner_);
+}
+
+ModuleFactoryRegistry::Registration<SimpleRayCaster> SimpleRayCaster::registration("SimpleRayCaster");
+void SimpleRayCaster::setupFromParamMap(Module::ParamMap* param_map) {
+  CameraModel::setupFromParamMap(param_map);
+  buildCasters(param_map);
+}
+int SimpleRayCaster::casterKind() const { return A3D_CASTER_SIMPLE; }
+
+ModuleFactoryRegistry::Registration<IterativeRayCaster> IterativeRayCaster::registration(
+    "IterativeRayCaster");
+void IterativeRayCaster::setupFromParamMap(Module::ParamMap* param_map) {
+  CameraModel::setupFromParamMap(param_map);
+  buildCasters(param_map);
+}
+int IterativeRayCaster::casterKind() const { return A3D_CASTER_ITERATIVE; }
+
+}  // namespace sensor_model
+
+// ---- evaluators ---------------------------------------------------------------------------------------
+TrajectoryEvaluator::TrajectoryEvaluator(PlannerI& planner) : Module(planner) {}
+
+void TrajectoryEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
+  // trajectory_evaluator.cpp:12-28: child modules default to namespace extensions
+  const std::string ns = (*param_map)["param_namespace"];
+  setParam<std::string>(param_map, "cost_computer_args", &p_cost_args_, ns + "/cost_computer");
+  setParam<std::string>(param_map, "value_computer_args", &p_value_args_, ns + "/value_computer");
+  setParam<std::string>(param_map, "next_selector_args", &p_next_args_, ns + "/next_selector");
+  setParam<std::string>(param_map, "evaluator_updater_args", &p_updater_args_, ns + "/evaluator_updater");
+  std::string bounding_volume_args;
+  setParam<std::string>(param_map, "bounding_volume_args", &bounding_volume_args, ns + "/bounding_volume");
+  bounding_volume_ =
+      planner_.getFactory().createModule<BoundingVolume>(bounding_volume_args, planner_, verbose_modules_);
+}
+bool TrajectoryEvaluator::computeCost(TrajectorySegment* traj_in) {
+  if (!cost_computer_)
+    cost_computer_ = planner_.getFactory().createModule<CostComputer>(p_cost_args_, planner_, verbose_modules_);
+  return cost_computer_->computeCost(traj_in);
+}
+bool TrajectoryEvaluator::computeValue(TrajectorySegment* traj_in) {
+  if (!value_computer_)
+    value_computer_ =
+        planner_.getFactory().createModule<ValueComputer>(p_value_args_, planner_, verbose_modules_);
+  return value_computer_->computeValue(traj_in);
+}
+int TrajectoryEvaluator::selectNextBest(TrajectorySegment* traj_in) {
+  if (!next_selector_)
+    next_selector_ = planner_.getFactory().createModule<NextSelector>(p_next_args_, planner_, verbose_modules_);
+  return next_selector_->selectNextBest(traj_in);
+}
+bool TrajectoryEvaluator::updateSegment(TrajectorySegment* segment) {
+  if (!evaluator_updater_)
+    evaluator_updater_ =
+        planner_.getFactory().createModule<EvaluatorUpdater>(p_updater_args_, planner_, verbose_modules_);
+  return evaluator_updater_->updateSegment(segment);
+}
+
+namespace trajectory_evaluator {
+using sensor_model::detail::gatherPoses;
+using sensor_model::detail::runVisible;
+
+SimulatedSensorEvaluator::SimulatedSensorEvaluator(PlannerI& planner)
+    : TrajectoryEvaluator(planner), map_(nullptr), gpu_map_(nullptr), eval_(nullptr),
+      p_clear_from_parents_(false), p_visualize_sensor_view_(false) {}
+
+SimulatedSensorEvaluator::~SimulatedSensorEvaluator() {
+  if (eval_) a3d_eval_destroy(eval_);
+}
+
+void SimulatedSensorEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
+  // simulated_sensor_evaluator.cpp:16-43
+  setParam<bool>(param_map, "clear_from_parents", &p_clear_from_parents_, false);
+  setParam<bool>(param_map, "visualize_sensor_view", &p_visualize_sensor_view_, false);
+  map_ = dynamic_cast<map::OccupancyMap*>(&(planner_.getMap()));
+  if (!map_) planner_.printError("'SimulatedSensorEvaluator' requires a map of type 'OccupancyMap'!");
+  gpu_map_ = dynamic_cast<map::VoxbloxMap*>(map_);
+  planner_.getFactory().registerLinkableModule("SimulatedSensorEvaluator", this);
+  std::string args;
+  const std::string param_ns = (*param_map)["param_namespace"];
+  setParam<std::string>(param_map, "sensor_model_args", &args, param_ns + "/sensor_model");
+  sensor_model_ = planner_.getFactory().createModule<SensorModel>(args, planner_, verbose_modules_);
+  TrajectoryEvaluator::setupFromParamMap(param_map);
+}
+
+void SimulatedSensorEvaluator::buildEval() {
+  if (!gpu_map_) {
+    planner_.printError("'SimulatedSensorEvaluator' (B200) requires the device map 'VoxbloxMap'!");
+    return;
+  }
+  a3d_eval_params p{};
+  p.kind = evalKind();
+  p.clear_from_parents = 0;  // handled per segment in computeGain (a3d_filter_not_in)
+  p.surface_frontiers = 1;
+  p.checking_distance = 1.0;
+  p.gains[0] = 1.0;
+  fillEvalParams(&p);
+  p.bv_is_setup = bounding_volume_ && bounding_volume_->is_setup;
+  if (bounding_volume_) {
+    p.bv_min[0] = bounding_volume_->x_min;
+    p.bv_min[1] = bounding_volume_->y_min;
+    p.bv_min[2] = bounding_volume_->z_min;
+    p.bv_max[0] = bounding_volume_->x_max;
+    p.bv_max[1] = bounding_volume_->y_max;
+    p.bv_max[2] = bounding_volume_->z_max;
+    p.bv_quat[0] = bounding_volume_->rotation_quat.w();
+    p.bv_quat[1] = bounding_volume_->rotation_quat.x();
+    p.bv_quat[2] = bounding_volume_->rotation_quat.y();
+    p.bv_quat[3] = bounding_volume_->rotation_quat.z();
+  } else {
+    p.bv_quat[0] = 1.0;
+  }
+  if (eval_) a3d_eval_destroy(eval_);
+  eval_ = nullptr;
+  if (a3d_eval_create(gpu_map_->context(), &p, &eval_) != A3D_OK)
+    planner_.printError(std::string("a3d_eval_create: ") + a3d_last_error(gpu_map_->context()));
+}
+
+bool SimulatedSensorEvaluator::computeGain(TrajectorySegment* traj_in) {
+  // simulated_sensor_evaluator.cpp:45-82
+  auto* cam = dynamic_cast<sensor_model::CameraModel*>(sensor_model_.get());
+  if (!cam || !cam->handle() || !eval_ || traj_in->trajectory.empty()) return false;
+  std::vector<int> indices;
+  cam->sampleViewpoints(&indices, *traj_in);
+  std::vector<double> pos, quat;
+  gatherPoses(*traj_in, indices, &pos, &quat);
+  // visible voxels, already restricted to the bounding volume (:50-57)
+  std::vector<Eigen::Vector3d> new_voxels;
+  if (!runVisible(gpu_map_->context(), cam->handle(), eval_, static_cast<int>(indices.size()), pos.data(),
+                  quat.data(), &new_voxels, nullptr, planner_))
+    return false;
+  if (p_clear_from_parents_) {  // :60-76, one device pass per ancestor
+    std::vector<uint8_t> keep(new_voxels.size(), 1);
+    std::vector<double> flat(new_voxels.size() * 3);
+    for (size_t i = 0; i < new_voxels.size(); ++i)
+      for (int k = 0; k < 3; ++k) flat[3 * i + k] = new_voxels[i][k];
+    for (TrajectorySegment* previous = traj_in->parent; previous; previous = previous->parent) {
+      auto* info = dynamic_cast<SimulatedSensorInfo*>(previous->info.get());
+      if (!info || info->visible_voxels.empty()) continue;
+      std::vector<double> old(info->visible_voxels.size() * 3);
+      for (size_t i = 0; i < info->visible_voxels.size(); ++i)
+        for (int k = 0; k < 3; ++k) old[3 * i + k] = info->visible_voxels[i][k];
+      if (a3d_filter_not_in(gpu_map_->context(), static_cast<int64_t>(new_voxels.size()), flat.data(),
+                            static_cast<int64_t>(info->visible_voxels.size()), old.data(),
+                            keep.data()) != A3D_OK) {
+        planner_.printError(std::string("a3d_filter_not_in: ") + a3d_last_error(gpu_map_->context()));
+        return false;
+      }
+    }
+    size_t w = 0;
+    for (size_t i = 0; i < new_voxels.size(); ++i)
+      if (keep[i]) new_voxels[w++] = new_voxels[i];
+    new_voxels.resize(w);
+  }
+  storeTrajectoryInformation(traj_in, new_voxels);
+  computeGainFromVisibleVoxels(traj_in);
+  return true;
+}
+
+bool SimulatedSensorEvaluator::storeTrajectoryInformation(TrajectorySegment* traj_in,
+                                                          const std::vector<Eigen::Vector3d>& new_voxels) {
+  SimulatedSensorInfo* new_info = new SimulatedSensorInfo();  // :84-91
+  new_info->visible_voxels.assign(new_voxels.begin(), new_voxels.end());
+  traj_in->info.reset(new_info);
+  return true;
+}
+
+bool SimulatedSensorEvaluator::computeGainFromVisibleVoxels(TrajectorySegment* traj_in) {
+  // voxel_type_evaluator.cpp:57-89 / naive_evaluator.cpp:20-38 / frontier_evaluator.cpp:100-124:
+  // the fold runs on the device; Naive and Frontier also drop the observed entries from the list
+  traj_in->gain = 0.0;
+  if (!traj_in->info || !eval_) return false;
+  auto* info = dynamic_cast<SimulatedSensorInfo*>(traj_in->info.get());
+  if (!info) return false;
+  const size_t n = info->visible_voxels.size();
+  std::vector<double> flat(n * 3);
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) flat[3 * i + k] = info->visible_voxels[i][k];
+  std::vector<uint8_t> keep(n, 1);
+  double gain = 0.0;
+  int64_t n_left = 0;
+  const bool erases = evalKind() != A3D_EVAL_VOXEL_TYPE;
+  if (a3d_gain_from_voxels(gpu_map_->context(), eval_, static_cast<int64_t>(n), flat.data(), &gain, &n_left,
+                           erases ? keep.data() : nullptr) != A3D_OK) {
+    planner_.printError(std::string("a3d_gain_from_voxels: ") + a3d_last_error(gpu_map_->context()));
+    return false;
+  }
+  if (erases) {
+    size_t w = 0;
+    for (size_t i = 0; i < n; ++i)
+      if (keep[i]) info->visible_voxels[w++] = info->visible_voxels[i];
+    info->visible_voxels.resize(w);
+  }
+  traj_in->gain = gain;
+  return true;
+}
+
+bool SimulatedSensorEvaluator::computeGains(const std::vector<TrajectorySegment*>& segments) {
+  auto* cam = dynamic_cast<sensor_model::CameraModel*>(sensor_model_.get());
+  if (!cam || !cam->handle() || !eval_) return false;
+  if (p_clear_from_parents_) {
+    planner_.printWarning("computeGains: clear_from_parents needs per-segment lists; use computeGain");
+    return false;
+  }
+  std::vector<double> pos, quat;
+  std::vector<int32_t> view_segment;
+  for (size_t s = 0; s < segments.size(); ++s) {
+    if (segments[s]->trajectory.empty()) continue;
+    std::vector<int> indices;
+    cam->sampleViewpoints(&indices, *segments[s]);
+    gatherPoses(*segments[s], indices, &pos, &quat);
+    view_segment.insert(view_segment.end(), indices.size(), static_cast<int32_t>(s));
+  }
+  std::vector<double> gains(segments.size(), 0.0);
+  const int rc = a3d_compute_gains(gpu_map_->context(), cam->handle(), eval_,
+                                   static_cast<int>(view_segment.size()), pos.data(), quat.data(),
+                                   view_segment.data(), static_cast<int>(segments.size()), gains.data(),
+                                   nullptr, nullptr, nullptr, nullptr);
+  if (rc != A3D_OK) {
+    planner_.printError(std::string("a3d_compute_gains: ") + a3d_last_error(gpu_map_->context()));
+    return false;
+  }
+  for (size_t s = 0; s < segments.size(); ++s) segments[s]->gain = gains[s];
+  return true;
+}
+
+ModuleFactoryRegistry::Registration<VoxelTypeEvaluator> VoxelTypeEvaluator::registration(
+    "VoxelTypeEvaluator");
+void VoxelTypeEvaluator::setupFromParamMap(Module::ParamMap* param_map) {  // voxel_type_evaluator.cpp:19-55
+  SimulatedSensorEvaluator::setupFromParamMap(param_map);
+  setParam<double>(param_map, "gain_unknown", &p_gain_unknown_, 1.0);
+  setParam<double>(param_map, "gain_occupied", &p_gain_occupied_, 0.0);
+  setParam<double>(param_map, "gain_free", &p_gain_free_, 0.0);
+  setParam<double>(param_map, "gain_unknown_outer", &p_gain_unknown_outer_, 0.0);
+  setParam<double>(param_map, "gain_occupied_outer", &p_gain_occupied_outer_, 0.0);
+  setParam<double>(param_map, "gain_free_outer", &p_gain_free_outer_, 0.0);
+  const std::string ns = (*param_map)["param_namespace"];
+  std::string outer_volume_args;
+  setParam<std::string>(param_map, "outer_volume_args", &outer_volume_args, ns + "/outer_volume");
+  outer_volume_ =
+      planner_.getFactory().createModule<BoundingVolume>(outer_volume_args, planner_, verbose_modules_);
+  c_min_gain_ = std::min({p_gain_unknown_, p_gain_occupied_, p_gain_free_, p_gain_unknown_outer_,
+                          p_gain_occupied_outer_, p_gain_free_outer_});
+  c_max_gain_ = std::max({p_gain_unknown_, p_gain_occupied_, p_gain_free_, p_gain_unknown_outer_,
+                          p_gain_occupied_outer_, p_gain_free_outer_});
+  buildEval();
+}
+int VoxelTypeEvaluator::evalKind() const { return A3D_EVAL_VOXEL_TYPE; }
+void VoxelTypeEvaluator::fillEvalParams(void* ptr) {
+  auto* p = static_cast<a3d_eval_params*>(ptr);
+  p->gains[0] = p_gain_unknown_;
+  p->gains[1] = p_gain_occupied_;
+  p->gains[2] = p_gain_free_;
+  p->gains[3] = p_gain_unknown_outer_;
+  p->gains[4] = p_gain_occupied_outer_;
+  p->gains[5] = p_gain_free_outer_;
+}
+
+ModuleFactoryRegistry::Registration<NaiveEvaluator> NaiveEvaluator::registration("NaiveEvaluator");
+void NaiveEvaluator::setupFromParamMap(Module::ParamMap* param_map) {  // naive_evaluator.cpp:15-18
+  SimulatedSensorEvaluator::setupFromParamMap(param_map);
+  buildEval();
+}
+int NaiveEvaluator::evalKind() const { return A3D_EVAL_NAIVE; }
+
+ModuleFactoryRegistry::Registration<FrontierEvaluator> FrontierEvaluator::registration("FrontierEvaluator");
+void FrontierEvaluator::setupFromParamMap(Module::ParamMap* param_map) {  // frontier_evaluator.cpp:15-28
+  SimulatedSensorEvaluator::setupFromParamMap(param_map);
+  setParam<bool>(param_map, "accurate_frontiers", &p_accurate_frontiers_, false);
+  setParam<bool>(param_map, "surface_frontiers", &p_surface_frontiers_, true);
+  setParam<double>(param_map, "checking_distance", &p_checking_distance_, 1.0);
+  buildEval();
+}
+int FrontierEvaluator::evalKind() const { return A3D_EVAL_FRONTIER; }
+void FrontierEvaluator::fillEvalParams(void* ptr) {
+  auto* p = static_cast<a3d_eval_params*>(ptr);
+  p->accurate_frontiers = p_accurate_frontiers_ ? 1 : 0;
+  p->surface_frontiers = p_surface_frontiers_ ? 1 : 0;
+  p->checking_distance = p_checking_distance_;
+}
+
+}  // namespace trajectory_evaluator
+
+// ---- YAML factory -----------------------------------------------------------------------------------------
+namespace {
+std::string trim(const std::string& s) {
+  const size_t a = s.find_first_not_of(" \t\r\n");
+  if (a == std::string::npos) return "";
+  const size_t b = s.find_last_not_of(" \t\r\n");
+  return s.substr(a, b - a + 1);
+}
+// strip a trailing comment that is not inside quotes
+std::string stripComment(const std::string& s) {
+  char quote = 0;
+  for (size_t i = 0; i < s.size(); ++i) {
+    const char c = s[i];
+    if (quote) {
+      if (c == quote) quote = 0;
+    } else if (c == '"' || c == '\'') {
+      quote = c;
+    } else if (c == '#' && (i == 0 || s[i - 1] == ' ' || s[i - 1] == '\t')) {
+      return s.substr(0, i);
+    }
+  }
+  return s;
+}
+// YAML scalar → the string XmlRpc's operator<< would produce (module_factory_ros.cpp:37-39)
+std::string scalarToParamString(std::string v) {
+  v = trim(v);
+  if (v.size() >= 2 && ((v.front() == '"' && v.back() == '"') || (v.front() == '\'' && v.back() == '\'')))
+    return v.substr(1, v.size() - 2);
+  std::string low = v;
+  std::transform(low.begin(), low.end(), low.begin(), ::tolower);
+  if (low == "true" || low == "yes" || low == "on") return "1";
+  if (low == "false" || low == "no" || low == "off") return "0";
+  return v;
+}
+}  // namespace
+
+std::string YamlTree::normalize(const std::string& ns) const {
+  std::string out;
+  bool slash = false;
+  for (char c : "/" + ns) {
+    if (c == '/') {
+      if (!slash) out += c;
+      slash = true;
+    } else {
+      out += c;
+      slash = false;
+    }
+  }
+  while (out.size() > 1 && out.back() == '/') out.pop_back();
+  return out;
+}
+
+bool YamlTree::loadFile(const std::string& path, std::string* error) {
+  std::ifstream f(path);
+  if (!f) {
+    if (error) *error = "cannot open " + path;
+    return false;
+  }
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return loadString(ss.str(), error);
+}
+
+bool YamlTree::loadString(const std::string& text, std::string* error) {
+  std::vector<std::pair<int, std::string>> stack;  // (indent, key)
+  std::istringstream in(text);
+  std::string raw;
+  int line_no = 0;
+  while (std::getline(in, raw)) {
+    ++line_no;
+    const std::string line = stripComment(raw);
+    if (trim(line).empty() || trim(line) == "---") continue;
+    const int indent = static_cast<int>(line.find_first_not_of(' '));
+    if (line[indent] == '\t' || line[indent] == '-') {
+      if (error) *error = "line " + std::to_string(line_no) + ": tabs / sequences are not supported";
+      return false;
+    }
+    const size_t colon = line.find(':', indent);
+    if (colon == std::string::npos) {
+      if (error) *error = "line " + std::to_string(line_no) + ": expected 'key: value'";
+      return false;
+    }
+    std::string key = trim(line.substr(indent, colon - indent));
+    if (key.size() >= 2 && (key.front() == '"' || key.front() == '\'')) key = key.substr(1, key.size() - 2);
+    const std::string value = trim(line.substr(colon + 1));
+    while (!stack.empty() && stack.back().first >= indent) stack.pop_back();
+    std::string path = root_;
+    for (const auto& e : stack) path += "/" + e.second;
+    path += "/" + key;
+    if (value.empty()) {
+      stack.push_back({indent, key});
+    } else {
+      values_[normalize(path)] = scalarToParamString(value);
+    }
+  }
+  return true;
+}
+
+bool YamlTree::hasNamespace(const std::string& ns) const {
+  const std::string prefix = normalize(ns) + "/";
+  auto it = values_.lower_bound(prefix);
+  return it != values_.end() && it->first.compare(0, prefix.size(), prefix) == 0;
+}
+
+std::map<std::string, std::string> YamlTree::scalars(const std::string& ns) const {
+  std::map<std::string, std::string> out;
+  const std::string prefix = normalize(ns) == "/" ? "/" : normalize(ns) + "/";
+  for (auto it = values_.lower_bound(prefix); it != values_.end(); ++it) {
+    if (it->first.compare(0, prefix.size(), prefix) != 0) break;
+    const std::string rest = it->first.substr(prefix.size());
+    if (rest.find('/') == std::string::npos) out[rest] = it->second;
+  }
+  return out;
+}
+
+bool ModuleFactoryYaml::getParamMapAndType(Module::ParamMap* map, std::string* type, std::string args) {
+  // module_factory_ros.cpp:17-56
+  for (const auto& kv : tree_.scalars(args)) (*map)[kv.first] = kv.second;
+  auto it = map->find("type");
+  if (it != map->end()) *type = it->second;
+  (*map)["param_namespace"] = args;
+  if (map->find("verbose_text") == map->end())
+    (*map)["verbose_text"] = "Creating Module '" + *type + "' from namespace '" + args + "'";
+  return true;
+}
+void ModuleFactoryYaml::printVerbose(const Module::ParamMap& map) {
+  auto it = map.find("verbose_text");
+  if (it != map.end()) verboseLog.push_back(it->second);
+}
+void ModuleFactoryYaml::printError(const std::string& message) { std::cerr << "[a3d] " << message << "\n"; }
+
+}  // namespace active_3d_planning

@@ -1,0 +1,206 @@
+// test_host.cpp — driver for the C++ host mirror.
+//   test_host config <planner.yaml> [namespace]     CPU only: YAML → ParamMaps as the ROS factory would
+//                                                    build them, registered module types
+//   test_host gains <planner.yaml> <map.bin> <segments.bin> <out.txt>
+//                                                    GPU: build VoxbloxMap + the configured evaluator
+//                                                    from the YAML, upload the map dump, evaluate the
+//                                                    segments one by one (reference API) and as a batch
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+
+#include "a3d_host/trajectory_evaluator.h"
+#include "a3d_host/yaml_factory.h"
+
+using namespace active_3d_planning;  // NOLINT
+
+namespace {
+
+class TestPlanner : public PlannerI {
+ public:
+  explicit TestPlanner(const YamlTree& tree) : factory_(tree) {}
+  void build(const std::string& map_ns, const std::string& eval_ns) {
+    map_ = factory_.createModule<Map>(map_ns, *this, true);
+    evaluator_ = factory_.createModule<TrajectoryEvaluator>(eval_ns, *this, true);
+  }
+  const Eigen::Vector3d& getCurrentPosition() const override { return position_; }
+  const Eigen::Quaterniond& getCurrentOrientation() const override { return orientation_; }
+  TrajectoryEvaluator& getTrajectoryEvaluator() override { return *evaluator_; }
+  ModuleFactory& getFactory() override { return factory_; }
+  Map& getMap() override { return *map_; }
+  SystemConstraints& getSystemConstraints() override { return constraints_; }
+  void printInfo(const std::string& t) override { std::cout << "[info] " << t << "\n"; }
+  void printWarning(const std::string& t) override { std::cout << "[warn] " << t << "\n"; }
+  void printError(const std::string& t) override { std::cout << "[error] " << t << "\n"; }
+  ModuleFactoryYaml factory_;
+  std::unique_ptr<Map> map_;
+  std::unique_ptr<TrajectoryEvaluator> evaluator_;
+  SystemConstraints constraints_;
+  Eigen::Vector3d position_;
+  Eigen::Quaterniond orientation_;
+};
+
+template <typename T>
+bool readVec(std::ifstream& f, std::vector<T>* v, size_t n) {
+  v->resize(n);
+  f.read(reinterpret_cast<char*>(v->data()), static_cast<std::streamsize>(n * sizeof(T)));
+  return static_cast<bool>(f);
+}
+
+uint64_t digestOf(const std::vector<Eigen::Vector3d>& v) {  // DESIGN.md "digest"
+  auto rotl = [](uint64_t x, int r) { return (x << r) | (x >> (64 - r)); };
+  uint64_t h = 0;
+  for (const auto& c : v) {
+    uint64_t b[3];
+    for (int k = 0; k < 3; ++k) {
+      const double d = c[k];
+      std::memcpy(&b[k], &d, 8);
+    }
+    uint64_t e = b[0] * 0x9E3779B97F4A7C15ull;
+    e ^= rotl(b[1], 23) * 0xC2B2AE3D27D4EB4Full;
+    e ^= rotl(b[2], 47) * 0x165667B19E3779F9ull;
+    e ^= e >> 31;
+    h = h * 0x100000001B3ull + e;
+  }
+  return h;
+}
+
+int runConfig(int argc, char** argv) {
+  YamlTree tree;
+  std::string err;
+  if (!tree.loadFile(argv[2], &err)) {
+    std::cerr << err << "\n";
+    return 2;
+  }
+  const std::string ns = argc > 3 ? argv[3] : "/trajectory_evaluator";
+  ModuleFactoryYaml factory(tree);
+  Module::ParamMap map;
+  std::string type = "NoDefaultTypeAvailable";
+  factory.getParamMapAndType(&map, &type, ns);
+  std::cout << "namespace " << ns << " type " << type << "\n";
+  for (const auto& kv : map)
+    if (kv.first != "verbose_text") std::cout << "param " << kv.first << " = " << kv.second << "\n";
+  Module::ParamMap smap;
+  std::string stype = "NoDefaultTypeAvailable";
+  factory.getParamMapAndType(&smap, &stype, ns + "/sensor_model");
+  std::cout << "namespace " << ns << "/sensor_model type " << stype << "\n";
+  for (const auto& kv : smap)
+    if (kv.first != "verbose_text") std::cout << "param " << kv.first << " = " << kv.second << "\n";
+  std::cout << "registered " << ModuleFactoryRegistry::listTypes() << "\n";
+  return 0;
+}
+
+int runGains(char** argv) {
+  YamlTree tree;
+  std::string err;
+  if (!tree.loadFile(argv[2], &err)) {
+    std::cerr << err << "\n";
+    return 2;
+  }
+  std::ifstream mf(argv[3], std::ios::binary), sf(argv[4], std::ios::binary);
+  if (!mf || !sf) {
+    std::cerr << "cannot open inputs\n";
+    return 2;
+  }
+  int32_t vps = 0, n_blocks = 0;
+  float vs = 0;
+  mf.read(reinterpret_cast<char*>(&vps), 4);
+  mf.read(reinterpret_cast<char*>(&vs), 4);
+  mf.read(reinterpret_cast<char*>(&n_blocks), 4);
+  const size_t nv = static_cast<size_t>(vps) * vps * vps;
+  std::vector<int32_t> idx;
+  std::vector<float> dist, weight;
+  std::vector<uint8_t> obs;
+  if (!readVec(mf, &idx, 3 * static_cast<size_t>(n_blocks)) || !readVec(mf, &dist, nv * n_blocks) ||
+      !readVec(mf, &obs, nv * n_blocks) || !readVec(mf, &weight, nv * n_blocks)) {
+    std::cerr << "short map file\n";
+    return 2;
+  }
+  // map parameters live in the map namespace of the config store, like the voxblox server params
+  tree.set("/map/type", "VoxbloxMap");
+  tree.set("/map/tsdf_voxel_size", std::to_string(vs));
+  tree.set("/map/tsdf_voxels_per_side", std::to_string(vps));
+
+  TestPlanner planner(tree);
+  planner.build("/map", "/trajectory_evaluator");
+  auto* vmap = dynamic_cast<map::VoxbloxMap*>(planner.map_.get());
+  auto* eval = dynamic_cast<trajectory_evaluator::SimulatedSensorEvaluator*>(planner.evaluator_.get());
+  if (!vmap || !eval) {
+    std::cerr << "config does not name a VoxbloxMap / SimulatedSensorEvaluator\n";
+    return 2;
+  }
+  vmap->uploadBlocks(n_blocks, idx.data(), dist.data(), obs.data(), weight.data());
+
+  int32_t n_seg = 0, pts = 0;
+  sf.read(reinterpret_cast<char*>(&n_seg), 4);
+  sf.read(reinterpret_cast<char*>(&pts), 4);
+  TrajectorySegment root;
+  std::vector<TrajectorySegment*> segments;
+  for (int s = 0; s < n_seg; ++s) {
+    TrajectorySegment* seg = (s == 0) ? &root : segments.back()->spawnChild();  // a chain: parents matter
+    for (int p = 0; p < pts; ++p) {
+      int64_t t;
+      double v[7];
+      sf.read(reinterpret_cast<char*>(&t), 8);
+      sf.read(reinterpret_cast<char*>(v), 56);
+      EigenTrajectoryPoint tp;
+      tp.time_from_start_ns = t;
+      tp.position_W = Eigen::Vector3d(v[0], v[1], v[2]);
+      tp.orientation_W_B = Eigen::Quaterniond(v[3], v[4], v[5], v[6]);
+      seg->trajectory.push_back(tp);
+    }
+    segments.push_back(seg);
+  }
+  std::ofstream out(argv[5]);
+  out.precision(17);
+  auto* cam = dynamic_cast<sensor_model::CameraModel*>(eval->sensorModel());
+  out << "grid " << cam->rayGridX() << " " << cam->rayGridY() << " " << cam->numSections() << "\n";
+  // reference API: one segment per call, voxel list stored in the segment
+  for (int s = 0; s < n_seg; ++s) {
+    const bool ok = eval->computeGain(segments[s]);
+    auto* info = dynamic_cast<trajectory_evaluator::SimulatedSensorInfo*>(segments[s]->info.get());
+    out << "single " << s << " " << ok << " " << segments[s]->gain << " "
+        << (info ? info->visible_voxels.size() : 0) << " " << (info ? digestOf(info->visible_voxels) : 0)
+        << "\n";
+  }
+  // updater path: fold the stored lists again
+  for (int s = 0; s < n_seg; ++s) {
+    const double before = segments[s]->gain;
+    eval->computeGainFromVisibleVoxels(segments[s]);
+    out << "refold " << s << " " << (before == segments[s]->gain) << "\n";
+  }
+  // sensor model alone
+  std::vector<Eigen::Vector3d> lst;
+  eval->sensorModel()->getVisibleVoxelsFromTrajectory(&lst, *segments[0]);
+  out << "sensor 0 " << lst.size() << " " << digestOf(lst) << "\n";
+  // batch API
+  std::vector<double> single(n_seg);
+  for (int s = 0; s < n_seg; ++s) single[s] = segments[s]->gain;
+  const bool bok = eval->computeGains(segments);
+  for (int s = 0; s < n_seg; ++s) out << "batch " << s << " " << bok << " " << segments[s]->gain << "\n";
+  // map virtuals
+  Eigen::Vector3d c;
+  vmap->getVoxelCenter(&c, segments[0]->trajectory.back().position_W);
+  out << "center " << c.x() << " " << c.y() << " " << c.z() << " state "
+      << static_cast<int>(vmap->getVoxelState(segments[0]->trajectory.back().position_W)) << " observed "
+      << vmap->isObserved(segments[0]->trajectory.back().position_W) << " voxel_size " << vmap->getVoxelSize()
+      << "\n";
+  for (const auto& line : planner.factory_.verboseLog) out << "# " << line.substr(0, line.find('\n')) << "\n";
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    if (argc >= 3 && std::strcmp(argv[1], "config") == 0) return runConfig(argc, argv);
+    if (argc >= 6 && std::strcmp(argv[1], "gains") == 0) return runGains(argv);
+  } catch (const std::exception& e) {
+    std::cerr << "exception: " << e.what() << "\n";
+    return 3;
+  }
+  std::cerr << "usage: test_host config <yaml> [ns] | gains <yaml> <map.bin> <segments.bin> <out.txt>\n";
+  return 1;
+}

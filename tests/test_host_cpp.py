@@ -1,0 +1,179 @@
+"""C++ host mirror of the reference module API (mav_active_3d_planning_b200/host): YAML → ParamMap
+exactly like ModuleFactoryROS, registry of type strings (CPU); modules built from YAML evaluating
+segments through the C ABI, against the oracle (GPU)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HOST = os.path.join(ROOT, "mav_active_3d_planning_b200", "host")
+GOLD = os.path.join(ROOT, "tests", "golden")
+EXE = os.path.join(HOST, "test_host")
+
+
+def run_config(yaml, ns=None):
+    out = subprocess.run([EXE, "config", yaml] + ([ns] if ns else []), capture_output=True, text=True,
+                         check=True).stdout
+    params, types, registered = {}, {}, []
+    cur = None
+    for line in out.splitlines():
+        t = line.split()
+        if t[0] == "namespace":
+            cur = t[1]
+            types[cur] = t[3]
+            params[cur] = {}
+        elif t[0] == "param":
+            params[cur][t[1]] = line.split(" = ", 1)[1]
+        elif t[0] == "registered":
+            registered = [x.strip() for x in line[len("registered "):].split(",")]
+    return params, types, registered
+
+
+def test_yaml_factory_builds_param_maps_like_the_ros_factory(built):
+    p, t, reg = run_config(os.path.join(GOLD, "planner_naive_iterative.yaml"))
+    ev, sm = "/trajectory_evaluator", "/trajectory_evaluator/sensor_model"
+    assert t[ev] == "NaiveEvaluator" and t[sm] == "IterativeRayCaster"
+    # direct scalar children only; bools as 1/0; quotes stripped; param_namespace recorded
+    assert p[ev] == {"type": "NaiveEvaluator", "clear_from_parents": "0", "visualize_sensor_view": "1",
+                     "bounding_volume_args": "/target_bounding_volume", "param_namespace": ev}
+    assert p[sm]["downsampling_factor"] == "1.0" and p[sm]["resolution_x"] == "320"
+    assert p[sm]["param_namespace"] == sm and "cost_computer" not in p[ev]
+    # every type string of the path resolves
+    for name in ("SimpleRayCaster", "IterativeRayCaster", "VoxelTypeEvaluator", "NaiveEvaluator",
+                 "FrontierEvaluator", "BoundingVolume", "VoxbloxMap"):
+        assert name in reg
+    p, t, _ = run_config(os.path.join(GOLD, "planner_naive_iterative.yaml"), "/target_bounding_volume")
+    assert p["/target_bounding_volume"]["x_max"] == "18.0"
+
+
+def test_reference_planner_configs_load_unchanged(built):
+    cfg = "/root/reference/active_3d_planning_app_reconstruction/cfg/planners"
+    if not os.path.isdir(cfg):
+        pytest.skip("reference checkout not present on this machine")
+    p, t, _ = run_config(os.path.join(cfg, "example_config.yaml"))
+    assert t["/trajectory_evaluator"] == "NaiveEvaluator"
+    assert t["/trajectory_evaluator/sensor_model"] == "IterativeRayCaster"
+    assert p["/trajectory_evaluator/sensor_model"]["downsampling_factor"] == "3.0"
+    assert p["/trajectory_evaluator"]["clear_from_parents"] == "0"
+    p, t, _ = run_config(os.path.join(cfg, "reconstruction_planner.yaml"))
+    assert t["/trajectory_evaluator"] == "RRTStarEvaluatorAdapter"   # out-of-scope wrapper, still parsed
+    for f in os.listdir(cfg):
+        subprocess.run([EXE, "config", os.path.join(cfg, f)], capture_output=True, check=True)
+
+
+def write_inputs(tmp, m, pos, quat, pts_per_seg, dt_ns):
+    mp, sp = os.path.join(tmp, "map.bin"), os.path.join(tmp, "segments.bin")
+    with open(mp, "wb") as f:
+        f.write(struct.pack("<ifi", m.vps, m.voxel_size, m.n_blocks))
+        f.write(np.ascontiguousarray(m.block_idx, np.int32).tobytes())
+        f.write(np.ascontiguousarray(m.dist, np.float32).tobytes())
+        f.write(np.ascontiguousarray(m.observed, np.uint8).tobytes())
+        f.write(np.ascontiguousarray(m.weight, np.float32).tobytes())
+    n_seg = len(pos) // pts_per_seg
+    with open(sp, "wb") as f:
+        f.write(struct.pack("<ii", n_seg, pts_per_seg))
+        for s in range(n_seg):
+            for k in range(pts_per_seg):
+                i = s * pts_per_seg + k
+                f.write(struct.pack("<q", k * dt_ns))
+                f.write(np.concatenate([pos[i], quat[i]]).astype(np.float64).tobytes())
+    return mp, sp
+
+
+def parse_out(path):
+    res = {"single": {}, "refold": {}, "batch": {}}
+    for line in open(path):
+        t = line.split()
+        if not t or t[0] == "#":
+            continue
+        if t[0] == "grid":
+            res["grid"] = tuple(int(x) for x in t[1:4])
+        elif t[0] == "single":
+            res["single"][int(t[1])] = (int(t[2]), float(t[3]), int(t[4]), int(t[5]))
+        elif t[0] == "refold":
+            res["refold"][int(t[1])] = int(t[2])
+        elif t[0] == "batch":
+            res["batch"][int(t[1])] = (int(t[2]), float(t[3]))
+        elif t[0] == "sensor":
+            res["sensor"] = (int(t[2]), int(t[3]))
+        elif t[0] == "center":
+            res["center"] = [float(x) for x in t[1:4]]
+            res["state"], res["observed"], res["voxel_size"] = int(t[5]), int(t[7]), float(t[9])
+    return res
+
+
+@pytest.mark.gpu
+def test_modules_from_yaml_match_oracle_naive_iterative(built, room02, tmp_path):
+    from mav_active_3d_planning_b200 import synth
+    from oracle import oracle_py as O
+    pos, quat = synth.candidate_views(room02, 6, seed=3)
+    mp, sp = write_inputs(str(tmp_path), room02, pos, quat, 1, 0)
+    out = os.path.join(str(tmp_path), "out.txt")
+    subprocess.run([EXE, "gains", os.path.join(GOLD, "planner_naive_iterative.yaml"), mp, sp, out],
+                   check=True, timeout=300)
+    r = parse_out(out)
+    om = O.OracleMap.from_synth(room02)
+    cam = dict(resolution_x=320, resolution_y=240, focal_length=160.0, ray_length=5.0)
+    oc = om.caster("IterativeRayCaster", **cam)
+    bv = dict(x_min=2, x_max=18, y_min=2, y_max=18, z_min=0.5, z_max=7)
+    ep = O.eval_params("NaiveEvaluator", bounding_volume=bv)
+    want = oc.compute_gains(ep, pos, quat)
+    assert r["grid"] == (oc.c_res_x, oc.c_res_y, oc.c_n_sections)
+    for s in range(6):
+        ok, gain, n_list, dig = r["single"][s]
+        assert ok == 1 and gain == want["gain"][s]
+        # Naive erases the observed entries from the stored list: what is left is what it counted
+        assert n_list == int(want["gain"][s])
+        assert r["refold"][s] == 1
+        assert r["batch"][s] == (1, want["gain"][s])
+    lst, _ = oc.visible_voxels(pos[:1], quat[:1])
+    assert r["sensor"] == (len(lst), O.digest(lst))
+    assert r["center"] == list(om.voxel_center(pos[:1])[0])
+    assert r["state"] == om.voxel_state(pos[:1])[0] and r["observed"] == om.is_observed(pos[:1])[0]
+    assert r["voxel_size"] == om.voxel_size
+
+
+@pytest.mark.gpu
+def test_modules_from_yaml_match_oracle_voxeltype_parents(built, room02, tmp_path):
+    """sampling_time > 0 (several views per segment), mounted camera, clear_from_parents along a chain."""
+    from mav_active_3d_planning_b200 import synth
+    from oracle import oracle_py as O
+    n_seg, pts = 4, 5
+    pos, quat = synth.candidate_views(room02, n_seg * pts, seed=29)
+    # segments revisit nearby places so that parents actually clear voxels
+    for s in range(1, n_seg):
+        pos[s * pts:(s + 1) * pts] = pos[:pts] + 0.05 * s
+        quat[s * pts:(s + 1) * pts] = quat[:pts]
+    dt = 250_000_000   # 0.25 s between trajectory points → sampling_time 0.5 s picks points 2 and 4
+    mp, sp = write_inputs(str(tmp_path), room02, pos, quat, pts, dt)
+    out = os.path.join(str(tmp_path), "out.txt")
+    subprocess.run([EXE, "gains", os.path.join(GOLD, "planner_voxeltype_simple_parents.yaml"), mp, sp, out],
+                   check=True, timeout=300)
+    r = parse_out(out)
+    om = O.OracleMap.from_synth(room02)
+    cam = dict(resolution_x=320, resolution_y=240, focal_length=160.0, ray_length=5.0,
+               downsampling_factor=2.0, mounting_translation=(0.1, 0.0, -0.05),
+               mounting_rotation=(0.99, 0.0, 0.1, 0.0))
+    oc = om.caster("SimpleRayCaster", **cam)
+    ep = O.eval_params("VoxelTypeEvaluator", clear_from_parents=True, gain_unknown=1.0, gain_free=0.5,
+                       gain_occupied=0.25)
+    times = np.arange(pts, dtype=np.int64) * dt
+    sel = O.sample_viewpoints(0.5, times)
+    assert list(sel) == [2, 4]
+    vp = np.concatenate([pos[s * pts + sel] for s in range(n_seg)])
+    vq = np.concatenate([quat[s * pts + sel] for s in range(n_seg)])
+    seg = np.repeat(np.arange(n_seg, dtype=np.int32), len(sel))
+    parent = np.arange(-1, n_seg - 1, dtype=np.int32)     # a chain, like the driver builds
+    want = oc.compute_gains(ep, vp, vq, seg, n_seg, parent=parent)
+    for s in range(n_seg):
+        ok, gain, n_list, dig = r["single"][s]
+        assert ok == 1 and n_list == want["n_visible"][s] and dig == want["digest"][s]
+        assert np.isclose(gain, want["gain"][s], rtol=1e-5, atol=0)
+        assert r["refold"][s] == 1
+    assert want["n_visible"][1] < want["n_visible"][0]    # parents did clear something
+    # the batch API refuses clear_from_parents
+    assert all(v[0] == 0 for v in r["batch"].values())
