@@ -158,7 +158,8 @@ def room_map(voxel_size=0.1, vps=16, dmax=2.0) -> SynthMap:
     return _build(voxel_size, vps, extent, boxes, wps, 6.0, dmax, 2)
 
 
-def clutter_map(voxel_size=0.05, vps=16, dmax=2.0, extent=(50.0, 50.0, 20.0), n_boxes=200) -> SynthMap:
+def clutter_map(voxel_size=0.05, vps=16, dmax=2.0, extent=(50.0, 50.0, 20.0), n_boxes=200,
+                obs_radius=8.0) -> SynthMap:
     """M-clutter: shell + 200 boxes, observed within 8 m of a 12-waypoint lawn-mower path."""
     boxes = _make_boxes(n_boxes, 7, extent, 0.5, 3.0, min(12.0, extent[2] * 0.6))
     wps = []
@@ -168,7 +169,7 @@ def clutter_map(voxel_size=0.05, vps=16, dmax=2.0, extent=(50.0, 50.0, 20.0), n_
         if row % 2:
             xs = xs[::-1]
         wps += [(float(x), ys, 3.0) for x in xs]
-    return _build(voxel_size, vps, extent, boxes, wps, 8.0, dmax, 2)
+    return _build(voxel_size, vps, extent, boxes, wps, obs_radius, dmax, 2)
 
 
 def yaw_quat(yaw: np.ndarray) -> np.ndarray:

@@ -434,3 +434,27 @@ def test_wave_kernel_empty_map_and_far_poses(capi, O):
         want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos, quat)
         _check_wave(got, want)
     ctx.close()
+
+
+def test_cfg3_small_clutter_frontier(capi, O):
+    """BASELINE config 3 at reduced extent: cluttered map at 0.05 m voxels (158x129 rays, 7 sections),
+    frontier / unknown-voxel gain, wavefront and scan-order kernels against the oracle."""
+    from mav_active_3d_planning_b200 import synth
+    m = synth.clutter_map(0.05, extent=(16.0, 16.0, 8.0), n_boxes=30, obs_radius=3.5)
+    assert 0.2 < m.observed.mean() < 0.95
+    ctx, om = make_pair(capi, O, m)
+    pos, quat = synth.candidate_views(m, 6, seed=41)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    oc = om.caster("IterativeRayCaster", **CAM_BASE)
+    assert (caster.info.c_res_x, caster.info.c_res_y, caster.info.c_n_sections) == (158, 129, 7)
+    for ekind, kw in (("FrontierEvaluator", {}), ("FrontierEvaluator", dict(accurate_frontiers=True)),
+                      ("VoxelTypeEvaluator", {})):
+        want = oc.compute_gains(O.eval_params(ekind, **kw), pos, quat, n_threads=6)
+        ev = ctx.evaluator(ekind, **kw)
+        _check_wave(_wave(ctx, caster, ev, pos, quat), want)
+        got = ctx.compute_gains(caster, ev, pos, quat)
+        for k in ("n_samples", "n_visible", "digest", "set_digest"):
+            assert np.array_equal(got[k], want[k]), k
+        assert np.array_equal(got["gain"], want["gain"])
+        assert want["gain"].max() > 0
+    ctx.close()
