@@ -888,6 +888,15 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   v.ray_step = info.ray_step;
   v.ray_length = p->ray_length;
   for (size_t t = 0; t < split.size(); ++t) v.split[t] = split[t];
+  for (int s0 = 0; s0 < n_sections; ++s0) {
+    v.leaf_d0[s0] = p->ray_length;
+    for (double d : seqs[s0]) {
+      if (!(d < split[n_sections - 1])) {
+        v.leaf_d0[s0] = d;
+        break;
+      }
+    }
+  }
   *out = c;
   return A3D_OK;
 }

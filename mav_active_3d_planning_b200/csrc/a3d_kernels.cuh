@@ -20,7 +20,8 @@ struct CasterView {
   double mount_t[3];
   Q4 mount_q;
   double ray_step, ray_length;
-  double split[33];  // c_split_distances_ (iterative)
+  double split[33];    // c_split_distances_ (iterative)
+  double leaf_d0[33];  // per start section: first accumulated sample distance >= split[n-1] (or ray_length)
   // leaf-supply units of k_cast_wave: iterative → unit u covers rays (i, diag-i), i in
   // [unit_i0[u], unit_i0[u]+32) of anti-diagonal unit_diag[u]; simple → rays [32u, 32u+32)
   int32_t n_units;

@@ -308,7 +308,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
 }
 
 #ifndef A3D_WAVE_STEPS
-#define A3D_WAVE_STEPS 4  // samples marched between two rounds of lane bookkeeping
+#define A3D_WAVE_STEPS 8  // samples marched between two rounds of lane bookkeeping
 #endif
 
 }  // namespace
@@ -420,6 +420,18 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                 const int t_last = hit ? seg_h : n - 2;
                 const int w0 = 1 << (n - 1 - ss);
                 const int ri = rr / c.res_y, rj = rr - ri * c.res_y;
+                if (w0 == 2) {
+                  // start section n-2 (most marking rays): the 2x2 square gets one value
+                  const int val = hit ? -1 : n - 1;
+                  const int dx = lane >> 1, dy = lane & 1;
+                  if (lane < 4 && ri + dx < c.res_x && rj + dy < c.res_y) {
+                    const int at = (ri + dx) * c.res_y + rj + dy;
+                    const unsigned writer = static_cast<unsigned>(rr) + 1u;
+                    if ((table[at] >> 8) < writer) table[at] = (writer << 8) | static_cast<uint8_t>(val);
+                  }
+                  __syncwarp();
+                  continue;
+                }
                 const int nx = min(w0, c.res_x - ri), ny = min(w0, c.res_y - rj);
                 const unsigned writer = static_cast<unsigned>(rr) + 1u;
                 for (int cell = lane; cell < nx * ny; cell += 32) {
@@ -521,8 +533,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                 double d0 = 0.0;
                 if (ITER) {
                   const int s0 = start_s[r] == 0xFF ? n - 1 : start_s[r];
-                  const int k0 = s0 == n - 1 ? 0 : c.seg_end[s0 * n + (n - 2)];
-                  d0 = k0 < c.kcount[s0] ? c.dseq[static_cast<size_t>(s0) * c.kmax + k0] : d_leaf_end;
+                  d0 = c.leaf_d0[s0];  // accumulated distance at which a ray started in s0 enters section n-1
                 }
                 ray_begin(rs, c, vw, r, d0);
                 role = (rs.d < d_leaf_end) ? 1 : 0;
