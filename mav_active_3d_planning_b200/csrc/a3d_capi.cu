@@ -132,6 +132,7 @@ struct a3d_ctx {
     }
     m.P = P;
     m.P3 = P3;
+    m.brick_nx = (vps % 4 == 0) ? vps / 4 : 0;
     m.mask = static_cast<uint32_t>(h_table.size() - 1);
     m.vps = vps;
     m.nv = nv;

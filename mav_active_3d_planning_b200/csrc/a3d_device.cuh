@@ -63,6 +63,7 @@ struct MapView {
   int32_t nv;                        // vps^3
   int32_t P;                         // vps + 2
   int32_t P3;                        // P^3
+  int32_t brick_nx;                  // vps/4 if the meta words are stored in 4x4x2 bricks, else 0
   float vs_f, vs_inv_f, bs_f, bs_inv_f;
   double c_vs;                       // double(vs_f), VoxbloxMap::c_voxel_size_
 };
@@ -129,6 +130,17 @@ __device__ __forceinline__ void init_center_tables(const MapView& m, CenterTable
     t->f[i] = c;
     t->d[i] = static_cast<double>(c);
   }
+}
+
+// Index of voxel (x,y,z) in a block's meta-word array.  When vps is a multiple of 4 the words are
+// stored in 4x4x2 bricks (32 words = one 128-byte line) so that a step in any direction usually stays
+// in the line the lane touched last; otherwise plain voxblox linear order.
+__device__ __forceinline__ int mword_offset(const MapView& m, int x, int y, int z) {
+  if (m.brick_nx) {
+    const int brick = ((z >> 1) * m.brick_nx + (y >> 2)) * m.brick_nx + (x >> 2);
+    return (brick << 5) | ((z & 1) << 4) | ((y & 3) << 2) | (x & 3);
+  }
+  return (z * m.vps + y) * m.vps + x;
 }
 
 __device__ __forceinline__ size_t padded_index(const MapView& m, int slot, int x, int y, int z) {
@@ -296,7 +308,7 @@ __device__ __forceinline__ int voxel_state_in_block(const MapView& m, const Cent
     sc |= (__fsub_rn(p[k], centre) < 0.0f) ? (1 << k) : 0;
   }
   const uint32_t word =
-      __ldg(m.mword + static_cast<size_t>(slot) * m.nv + (v[2] * m.vps + v[1]) * m.vps + v[0]);
+      __ldg(m.mword + static_cast<size_t>(slot) * m.nv + mword_offset(m, v[0], v[1], v[2]));
   *word_out = word;
   const int cls = (word >> (2 * sc)) & 3;
   if (cls != kCellMixed) return cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
@@ -378,7 +390,7 @@ __device__ __forceinline__ bool is_observed(const MapView& m, const D3& p) {
   int v[3];
   const int slot = nearest_voxel(m, p, v);
   if (slot < 0) return false;
-  return (__ldg(m.mword + static_cast<size_t>(slot) * m.nv + (v[2] * m.vps + v[1]) * m.vps + v[0]) >>
+  return (__ldg(m.mword + static_cast<size_t>(slot) * m.nv + mword_offset(m, v[0], v[1], v[2])) >>
           18) & 1;
 }
 __device__ __forceinline__ double voxel_weight(const MapView& m, const D3& p) {
@@ -402,7 +414,7 @@ __device__ __forceinline__ int centre_state(const MapView& m, const CenterTables
   }
   if (slot < 0) return 2;
   const uint32_t word =
-      __ldg(m.mword + static_cast<size_t>(slot) * m.nv + (v[2] * m.vps + v[1]) * m.vps + v[0]);
+      __ldg(m.mword + static_cast<size_t>(slot) * m.nv + mword_offset(m, v[0], v[1], v[2]));
   return static_cast<int>((word >> 16) & 7);
 }
 // the same from an already loaded meta word of that voxel

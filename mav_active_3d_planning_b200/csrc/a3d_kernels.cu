@@ -164,7 +164,7 @@ __global__ void k_build_meta(MapView m, int n, const int32_t* __restrict__ slots
                                              __double2float_rn(cz));
       word |= static_cast<uint32_t>(centre) << 16;
       word |= static_cast<uint32_t>(obs) << 18;
-      mword_slab[static_cast<size_t>(slot) * m.nv + lin] = word;
+      mword_slab[static_cast<size_t>(slot) * m.nv + mword_offset(m, x, y, z)] = word;
     }
   }
 }

@@ -246,7 +246,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
   const int slot = find_slot(m, bi[0], bi[1], bi[2]);
   uint32_t word = kWordNoBlock;
   if (slot >= 0 && in_range)
-    word = __ldg(m.mword + static_cast<size_t>(slot) * m.nv + (vs[2] * m.vps + vs[1]) * m.vps + vs[0]);
+    word = __ldg(m.mword + static_cast<size_t>(slot) * m.nv + mword_offset(m, vs[0], vs[1], vs[2]));
   const int cls = (word >> (2 * sc)) & 3;
   SampleInfo si;
   si.st = cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
