@@ -47,6 +47,8 @@ extern "C" {
 #define A3D_EVAL_VOXEL_TYPE 0
 #define A3D_EVAL_NAIVE 1
 #define A3D_EVAL_FRONTIER 2
+/* "VoxelWeightEvaluator" (voxel_weight_evaluator.cpp:12-13): evaluated by the scan-order kernel */
+#define A3D_EVAL_VOXEL_WEIGHT 3
 
 typedef struct a3d_ctx a3d_ctx;
 typedef struct a3d_caster a3d_caster;
@@ -85,6 +87,9 @@ typedef struct {
   double bv_min[3];           /* x_min, y_min, z_min */
   double bv_max[3];           /* x_max, y_max, z_max */
   double bv_quat[4];          /* w,x,y,z of AngleAxis(rotation*pi/-180, UnitZ) (bounding_volume.cpp:21) */
+  /* VoxelWeightEvaluator (voxel_weight_evaluator.cpp:17-22): "frontier_voxel_weight" (1.0),
+     "min_impact_factor" (0.0), "new_voxel_weight" (0.01), "ray_angle_x" / "ray_angle_y" (0.0025) */
+  double frontier_voxel_weight, min_impact_factor, new_voxel_weight, ray_angle_x, ray_angle_y;
 } a3d_eval_params;
 
 /* Derived constants of a caster (members c_res_x_, c_res_y_, c_n_sections_, c_split_distances_,
@@ -175,18 +180,22 @@ void a3d_eval_destroy(a3d_eval* e);
  *   digests_out    order-sensitive 64-bit digest of that stored list (DESIGN.md "digest");
  *                  asking for it selects the scan-order kernel
  *   set_digests_out  order-independent digest of the same list (sum of per-entry hashes mod 2^64)
+ *   seg_origin (input, nullable, n_segments×3): position of each segment's last trajectory point,
+ *                  the `origin` of VoxelWeightEvaluator (voxel_weight_evaluator.cpp:53); default =
+ *                  body position of the segment's last view
  * Synchronous on return.  clear_from_parents is not supported by the batch call. */
 int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                       const double* pos, const double* quat, const int32_t* view_segment,
                       int n_segments, double* gains_out, uint64_t* n_visible_out,
-                      uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* set_digests_out);
+                      uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* set_digests_out,
+                      const double* seg_origin);
 /* Same with every array in device memory; enqueued on the context stream, NOT synchronised.
    view_first_dev: n_segments+1 int32 prefix offsets of each segment's views. */
 int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
                           int n_views, const double* pos_dev, const double* quat_dev,
                           const int32_t* view_first_dev, int n_segments, double* gains_dev,
                           uint64_t* n_visible_dev, uint64_t* n_samples_dev, uint64_t* digests_dev,
-                          uint64_t* set_digests_dev);
+                          uint64_t* set_digests_dev, const double* seg_origin_dev);
 
 /* One segment with its voxel list materialised (parity / visualisation / the per-segment
  * SensorModel::getVisibleVoxelsFromTrajectory + storeTrajectoryInformation API):
@@ -195,7 +204,8 @@ int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval
  * centres_out cap×3 doubles; *n_out = full list length even if > cap (then A3D_ERR_CAPACITY). */
 int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                        const double* pos, const double* quat, double* centres_out, int64_t cap,
-                       int64_t* n_out, int64_t* n_samples_out, double* gain_out);
+                       int64_t* n_out, int64_t* n_samples_out, double* gain_out,
+                       const double* origin /* 3 doubles, nullable: see seg_origin */);
 
 /* computeGainFromVisibleVoxels on an explicit stored list (the SimulatedSensorUpdater path,
  * core/src/module/trajectory_evaluator/evaluator_updater/simulated_sensor_updater.cpp:18-22).
@@ -203,7 +213,8 @@ int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* e
  * voxels, naive_evaluator.cpp:28-35, frontier_evaluator.cpp:110-116); keep_out (nullable, n bytes):
  * which entries survive. */
 int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* centres,
-                         double* gain_out, int64_t* n_left_out, uint8_t* keep_out);
+                         double* gain_out, int64_t* n_left_out, uint8_t* keep_out,
+                         const double* origin /* 3 doubles, VoxelWeightEvaluator only, else nullable */);
 
 /* clear_from_parents step of SimulatedSensorEvaluator::computeGain
  * (simulated_sensor_evaluator.cpp:60-76) for ONE ancestor: keep_inout[i] is cleared if centres[i]

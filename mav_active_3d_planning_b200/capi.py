@@ -22,10 +22,10 @@ LIB_PATH = os.environ.get("A3D_LIB_PATH") or os.path.join(_HERE, "liba3d_b200.so
 
 OCCUPIED, FREE, UNKNOWN = 0, 1, 2
 CASTER_SIMPLE, CASTER_ITERATIVE = 0, 1
-EVAL_VOXEL_TYPE, EVAL_NAIVE, EVAL_FRONTIER = 0, 1, 2
+EVAL_VOXEL_TYPE, EVAL_NAIVE, EVAL_FRONTIER, EVAL_VOXEL_WEIGHT = 0, 1, 2, 3
 _CASTER_KINDS = {"SimpleRayCaster": CASTER_SIMPLE, "IterativeRayCaster": CASTER_ITERATIVE}
 _EVAL_KINDS = {"VoxelTypeEvaluator": EVAL_VOXEL_TYPE, "NaiveEvaluator": EVAL_NAIVE,
-               "FrontierEvaluator": EVAL_FRONTIER}
+               "FrontierEvaluator": EVAL_FRONTIER, "VoxelWeightEvaluator": EVAL_VOXEL_WEIGHT}
 
 # every symbol include/a3d.h declares
 EXPORTS = [
@@ -51,7 +51,10 @@ class EvalParams(C.Structure):
                 ("accurate_frontiers", C.c_int32), ("surface_frontiers", C.c_int32),
                 ("checking_distance", C.c_double), ("gains", C.c_double * 6),
                 ("bv_is_setup", C.c_int32), ("_pad", C.c_int32), ("bv_min", C.c_double * 3),
-                ("bv_max", C.c_double * 3), ("bv_quat", C.c_double * 4)]
+                ("bv_max", C.c_double * 3), ("bv_quat", C.c_double * 4),
+                ("frontier_voxel_weight", C.c_double), ("min_impact_factor", C.c_double),
+                ("new_voxel_weight", C.c_double), ("ray_angle_x", C.c_double),
+                ("ray_angle_y", C.c_double)]
 
 
 class CasterInfo(C.Structure):
@@ -83,7 +86,8 @@ def caster_params(kind, *, ray_length=5.0, focal_length=320.0, resolution_x=640,
 def eval_params(kind, *, clear_from_parents=False, accurate_frontiers=False, surface_frontiers=True,
                 checking_distance=1.0, gain_unknown=1.0, gain_occupied=0.0, gain_free=0.0,
                 gain_unknown_outer=0.0, gain_occupied_outer=0.0, gain_free_outer=0.0,
-                bounding_volume=None, cls=EvalParams):
+                bounding_volume=None, frontier_voxel_weight=1.0, min_impact_factor=0.0,
+                new_voxel_weight=0.01, ray_angle_x=0.0025, ray_angle_y=0.0025, cls=EvalParams):
     """Reference parameter names/defaults (voxel_type_evaluator.cpp:24-31,
     frontier_evaluator.cpp:17-20, simulated_sensor_evaluator.cpp:17).  ``bounding_volume`` is a dict
     with x_min..z_max and optional rotation [deg] (bounding_volume.cpp:12-31) or None."""
@@ -91,6 +95,9 @@ def eval_params(kind, *, clear_from_parents=False, accurate_frontiers=False, sur
         kind = _EVAL_KINDS[kind]
     p = cls()
     p.kind = kind
+    p.frontier_voxel_weight, p.min_impact_factor = float(frontier_voxel_weight), float(min_impact_factor)
+    p.new_voxel_weight = float(new_voxel_weight)
+    p.ray_angle_x, p.ray_angle_y = float(ray_angle_x), float(ray_angle_y)
     p.clear_from_parents = int(bool(clear_from_parents))
     p.accurate_frontiers = int(bool(accurate_frontiers))
     p.surface_frontiers = int(bool(surface_frontiers))
@@ -154,12 +161,13 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_eval_create.argtypes = [vp, P(EvalParams), P(vp)]
     lib.a3d_eval_destroy.argtypes = [vp]
     lib.a3d_eval_destroy.restype = None
-    lib.a3d_compute_gains.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
-    lib.a3d_compute_gains_dev.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.a3d_compute_gains.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.a3d_compute_gains_dev.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp,
+                                          vp]
     lib.a3d_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.a3d_last_cast_kernel.argtypes = [vp]
-    lib.a3d_visible_voxels.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, i64, P(i64), P(i64), P(dbl)]
-    lib.a3d_gain_from_voxels.argtypes = [vp, vp, i64, vp, P(dbl), P(i64), vp]
+    lib.a3d_visible_voxels.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, i64, P(i64), P(i64), P(dbl), vp]
+    lib.a3d_gain_from_voxels.argtypes = [vp, vp, i64, vp, P(dbl), P(i64), vp, vp]
     lib.a3d_bv_contains.argtypes = [vp, vp, i64, vp, vp]
     lib.a3d_filter_not_in.argtypes = [vp, i64, vp, i64, vp, vp]
     _lib = lib
@@ -318,7 +326,7 @@ class Context:
         return int(self.lib.a3d_last_cast_kernel(self.h))
 
     def compute_gains(self, caster, evaluator, pos, quat, view_segment=None, n_segments=None,
-                      digests=True, set_digests=True):
+                      digests=True, set_digests=True, seg_origin=None):
         """Batched SimulatedSensorEvaluator::computeGain.  Returns dict(gain, n_visible, n_samples,
         digest, set_digest) of per-segment arrays.  Default: one view per segment.  ``digests=True``
         (ordered digest) selects the scan-order kernel; with ``digests=False`` the wavefront kernel
@@ -338,7 +346,9 @@ class Context:
         sdig = np.zeros(n_segments, np.uint64) if set_digests else None
         self._ck(self.lib.a3d_compute_gains(self.h, caster.h, evaluator.h, n_views, _ptr(pos),
                                             _ptr(quat), _ptr(view_segment), n_segments, _ptr(gains),
-                                            _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(sdig)))
+                                            _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(sdig),
+                                            _ptr(None if seg_origin is None else
+                                                 np.ascontiguousarray(seg_origin, np.float64))))
         return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig, set_digest=sdig)
 
     def compute_gains_dev(self, caster, evaluator, n_views, pos_ptr, quat_ptr, first_ptr, n_segments,
@@ -347,9 +357,9 @@ class Context:
         self._ck(self.lib.a3d_compute_gains_dev(self.h, caster.h, evaluator.h, n_views, pos_ptr,
                                                 quat_ptr, first_ptr, n_segments, gains_ptr,
                                                 nvis_ptr or None, nsamp_ptr or None,
-                                                dig_ptr or None, set_dig_ptr or None))
+                                                dig_ptr or None, set_dig_ptr or None, None))
 
-    def visible_voxels(self, caster, pos, quat, evaluator=None, cap=None):
+    def visible_voxels(self, caster, pos, quat, evaluator=None, cap=None, origin=None):
         """One segment: ordered voxel-centre list (+gain if an evaluator is given)."""
         pos = _pts(pos)
         quat = np.ascontiguousarray(quat, np.float64)
@@ -360,15 +370,19 @@ class Context:
         n_out, n_samp, gain = C.c_int64(), C.c_int64(), C.c_double()
         self._ck(self.lib.a3d_visible_voxels(self.h, caster.h, evaluator.h if evaluator else None,
                                              len(pos), _ptr(pos), _ptr(quat), _ptr(out), cap,
-                                             C.byref(n_out), C.byref(n_samp), C.byref(gain)))
+                                             C.byref(n_out), C.byref(n_samp), C.byref(gain),
+                                             _ptr(None if origin is None else
+                                                  np.ascontiguousarray(origin, np.float64))))
         return out[:n_out.value].copy(), int(n_samp.value), float(gain.value)
 
-    def gain_from_voxels(self, evaluator, centres, want_keep=False):
+    def gain_from_voxels(self, evaluator, centres, want_keep=False, origin=None):
         centres = _pts(centres) if len(centres) else np.zeros((0, 3))
         gain, left = C.c_double(), C.c_int64()
         keep = np.zeros(len(centres), np.uint8) if want_keep else None
         self._ck(self.lib.a3d_gain_from_voxels(self.h, evaluator.h, len(centres), _ptr(centres),
-                                               C.byref(gain), C.byref(left), _ptr(keep)))
+                                               C.byref(gain), C.byref(left), _ptr(keep),
+                                               _ptr(None if origin is None else
+                                                    np.ascontiguousarray(origin, np.float64))))
         return float(gain.value), int(left.value), keep
 
     def filter_not_in(self, centres, other):

@@ -102,7 +102,7 @@ struct a3d_ctx {
   DevBuf<int32_t> st_slots, st_aff_slots, st_aff_nbr, st_aff_idx;
   DevBuf<double> sc_pts, sc_out;
   DevBuf<uint8_t> sc_u8;
-  DevBuf<double> sc_pos, sc_quat, sc_gains, sc_centres;
+  DevBuf<double> sc_pos, sc_quat, sc_gains, sc_centres, sc_origin;
   DevBuf<int32_t> sc_first;
   DevBuf<unsigned long long> sc_nvis, sc_nsamp, sc_dig, sc_cnt;
   DevBuf<int8_t> sc_tables;
@@ -462,6 +462,10 @@ EvalView make_eval_view(const a3d_ctx* ctx, const a3d_eval_params& p) {
     v.bv_max[i] = p.bv_max[i];
   }
   v.bv_q = Q4{p.bv_quat[0], p.bv_quat[1], p.bv_quat[2], p.bv_quat[3]};
+  v.frontier_voxel_weight = p.frontier_voxel_weight;
+  v.min_impact_factor = p.min_impact_factor;
+  v.new_voxel_weight = p.new_voxel_weight;
+  v.ray_angle_xy = p.ray_angle_x * p.ray_angle_y;
   return v;
 }
 
@@ -472,7 +476,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
                  const double* quat_dev, const int32_t* first_dev, int n_segments, double* gains_dev,
                  unsigned long long* nvis_dev, unsigned long long* nsamp_dev,
                  unsigned long long* dig_dev, unsigned long long* set_dig_dev, double* centres_dev,
-                 long long cap, bool emit) {
+                 long long cap, bool emit, const double* seg_origin_dev) {
   if (ctx->h_table.empty()) {
     table_rebuild(ctx, 0);
     int rc = table_upload(ctx);
@@ -490,10 +494,11 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   b.set_digests = set_dig_dev;
   b.centres_out = centres_dev;
   b.cap = cap;
+  b.seg_origin = seg_origin_dev;
   CK(ctx->sc_counter.reserve(2));
   CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 2 * sizeof(unsigned int), ctx->stream));
 
-  const bool wave_ok = e && !emit && !dig_dev &&
+  const bool wave_ok = e && !emit && !dig_dev && e->p.kind != A3D_EVAL_VOXEL_WEIGHT &&
                        std::min(c->view.res_x, c->view.res_y) <= cast_wave_max_diag() &&
                        c->view.n_rays < (1 << 24);
   if (ctx->opt_cast_kernel == 2 && !wave_ok)
@@ -616,6 +621,7 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
   ctx->sc_cnt.release();
   ctx->sc_tables.release();
   ctx->sc_counter.release();
+  ctx->sc_origin.release();
   ctx->sc_inexact.release();
   ctx->sc_wave.release();
   cudaEventDestroy(ctx->ev0);
@@ -933,8 +939,10 @@ int a3d_eval_create(a3d_ctx* ctx, const a3d_eval_params* p, a3d_eval** out) {
   *out = nullptr;
   if (!p) return ctx->fail(A3D_ERR_INVALID, "null params");
   if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
-  if (p->kind < A3D_EVAL_VOXEL_TYPE || p->kind > A3D_EVAL_FRONTIER)
+  if (p->kind < A3D_EVAL_VOXEL_TYPE || p->kind > A3D_EVAL_VOXEL_WEIGHT)
     return ctx->fail(A3D_ERR_INVALID, "unknown evaluator kind");
+  if (p->kind == A3D_EVAL_VOXEL_WEIGHT && !(p->ray_angle_x * p->ray_angle_y > 0.0))
+    return ctx->fail(A3D_ERR_INVALID, "ray_angle_x * ray_angle_y expected > 0.0");
   a3d_eval* e = new a3d_eval();
   e->ctx = ctx;
   e->p = *p;
@@ -949,7 +957,7 @@ int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval
                           const double* pos_dev, const double* quat_dev,
                           const int32_t* view_first_dev, int n_segments, double* gains_dev,
                           uint64_t* n_visible_dev, uint64_t* n_samples_dev, uint64_t* digests_dev,
-                          uint64_t* set_digests_dev) {
+                          uint64_t* set_digests_dev, const double* seg_origin_dev) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!caster || !eval || caster->ctx != ctx || eval->ctx != ctx)
     return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
@@ -964,7 +972,8 @@ int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval
                       reinterpret_cast<unsigned long long*>(n_visible_dev),
                       reinterpret_cast<unsigned long long*>(n_samples_dev),
                       reinterpret_cast<unsigned long long*>(digests_dev),
-                      reinterpret_cast<unsigned long long*>(set_digests_dev), nullptr, 0, false);
+                      reinterpret_cast<unsigned long long*>(set_digests_dev), nullptr, 0, false,
+                      seg_origin_dev);
 }
 
 int a3d_set_option(a3d_ctx* ctx, const char* name, int64_t value) {
@@ -982,7 +991,8 @@ int a3d_last_cast_kernel(const a3d_ctx* ctx) { return ctx ? ctx->last_cast_kerne
 int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                       const double* pos, const double* quat, const int32_t* view_segment,
                       int n_segments, double* gains_out, uint64_t* n_visible_out,
-                      uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* set_digests_out) {
+                      uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* set_digests_out,
+                      const double* seg_origin) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!caster || !eval || caster->ctx != ctx || eval->ctx != ctx)
     return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
@@ -1015,6 +1025,13 @@ int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* ev
   }
   CK(cudaMemcpyAsync(ctx->sc_first.p, first.data(), first.size() * sizeof(int32_t),
                      cudaMemcpyHostToDevice, ctx->stream));
+  const double* origin_dev = nullptr;
+  if (seg_origin) {
+    CK(ctx->sc_origin.reserve(3 * static_cast<size_t>(n_segments)));
+    CK(cudaMemcpyAsync(ctx->sc_origin.p, seg_origin, 24 * static_cast<size_t>(n_segments),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    origin_dev = ctx->sc_origin.p;
+  }
   int rc = a3d_compute_gains_dev(ctx, caster, eval, n_views, ctx->sc_pos.p, ctx->sc_quat.p,
                                  ctx->sc_first.p, n_segments, ctx->sc_gains.p,
                                  reinterpret_cast<uint64_t*>(ctx->sc_nvis.p),
@@ -1022,7 +1039,8 @@ int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* ev
                                  digests_out ? reinterpret_cast<uint64_t*>(ctx->sc_dig.p) : nullptr,
                                  set_digests_out
                                      ? reinterpret_cast<uint64_t*>(ctx->sc_dig.p + n_segments)
-                                     : nullptr);
+                                     : nullptr,
+                                 origin_dev);
   if (rc) return rc;
   CK(cudaMemcpyAsync(gains_out, ctx->sc_gains.p, sizeof(double) * n_segments,
                      cudaMemcpyDeviceToHost, ctx->stream));
@@ -1044,7 +1062,7 @@ int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* ev
 
 int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                        const double* pos, const double* quat, double* centres_out, int64_t cap,
-                       int64_t* n_out, int64_t* n_samples_out, double* gain_out) {
+                       int64_t* n_out, int64_t* n_samples_out, double* gain_out, const double* origin) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!caster || caster->ctx != ctx || (eval && eval->ctx != ctx))
     return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
@@ -1069,9 +1087,15 @@ int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* e
                        ctx->stream));
   }
   CK(cudaMemcpyAsync(ctx->sc_first.p, first, sizeof(first), cudaMemcpyHostToDevice, ctx->stream));
+  const double* origin_dev = nullptr;
+  if (origin) {
+    CK(ctx->sc_origin.reserve(3));
+    CK(cudaMemcpyAsync(ctx->sc_origin.p, origin, 24, cudaMemcpyHostToDevice, ctx->stream));
+    origin_dev = ctx->sc_origin.p;
+  }
   int rc = enqueue_cast(ctx, caster, eval, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, 1,
                         ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr,
-                        ctx->sc_centres.p, cap, true);
+                        ctx->sc_centres.p, cap, true, origin_dev);
   if (rc) return rc;
   unsigned long long nvis = 0, nsamp = 0;
   double gain = 0.0;
@@ -1094,7 +1118,7 @@ int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* e
 }
 
 int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* centres,
-                         double* gain_out, int64_t* n_left_out, uint8_t* keep_out) {
+                         double* gain_out, int64_t* n_left_out, uint8_t* keep_out, const double* origin) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!eval || eval->ctx != ctx) return ctx->fail(A3D_ERR_INVALID, "eval missing");
   if (n < 0 || (n > 0 && !centres) || !gain_out) return ctx->fail(A3D_ERR_INVALID, "bad argument");
@@ -1105,6 +1129,9 @@ int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const do
     if (rc) return rc;
   }
   unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (eval->p.kind == A3D_EVAL_VOXEL_WEIGHT && !origin)
+    return ctx->fail(A3D_ERR_INVALID, "VoxelWeightEvaluator needs the segment origin");
+  const D3 o = origin ? D3{origin[0], origin[1], origin[2]} : D3{0.0, 0.0, 0.0};
   if (n > 0) {
     CK(ctx->sc_pts.reserve(3 * n));
     CK(ctx->sc_cnt.reserve(8));
@@ -1112,14 +1139,23 @@ int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const do
     CK(cudaMemcpyAsync(ctx->sc_pts.p, centres, 24 * static_cast<size_t>(n), cudaMemcpyHostToDevice,
                        ctx->stream));
     CK(cudaMemsetAsync(ctx->sc_cnt.p, 0, 64, ctx->stream));
+    // counters[7] doubles as the double accumulator of the VoxelWeight gain
     launch_gain_from_voxels(ctx->stream, ctx->view(), eval->view, n, ctx->sc_pts.p, ctx->sc_cnt.p,
-                            keep_out ? ctx->sc_u8.p : nullptr);
+                            keep_out ? ctx->sc_u8.p : nullptr, o,
+                            reinterpret_cast<double*>(ctx->sc_cnt.p + 7));
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cnt, ctx->sc_cnt.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
     if (keep_out)
       CK(cudaMemcpyAsync(keep_out, ctx->sc_u8.p, n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (eval->p.kind == A3D_EVAL_VOXEL_WEIGHT) {
+    double g = 0.0;
+    std::memcpy(&g, &cnt[7], sizeof(double));
+    *gain_out = g;
+    if (n_left_out) *n_left_out = n;  // the list is not modified (voxel_weight_evaluator.cpp:43-58)
+    return A3D_OK;
   }
   if (eval->p.kind == A3D_EVAL_VOXEL_TYPE) {
     // fall-through sums of voxel_type_evaluator.cpp:69-85

@@ -430,6 +430,8 @@ struct EvalView {
   double gains[6];
   double bv_min[3], bv_max[3];
   Q4 bv_q;
+  // VoxelWeightEvaluator (voxel_weight_evaluator.cpp:17-22)
+  double frontier_voxel_weight, min_impact_factor, new_voxel_weight, ray_angle_xy;  // rx*ry
 };
 
 __device__ __forceinline__ bool bv_contains(const EvalView& e, const D3& p) {
@@ -491,6 +493,27 @@ __device__ __forceinline__ bool is_frontier_voxel(const MapView& m, const Center
     return true;
   }
   return false;
+}
+
+// VoxelWeightEvaluator::getVoxelValue (voxel_weight_evaluator.cpp:60-83) for a list entry with centre
+// c, given its state cs (centre_state) and TSDF weight w.
+__device__ __forceinline__ double voxel_weight_value(const MapView& m, const CenterTables& ct,
+                                                     const EvalView& e, const D3& c, int cs, double w,
+                                                     const D3& origin) {
+  const int state = cs & 3;
+  if (state == 0) {  // surface voxel
+    const double dx = c.x - origin.x, dy = c.y - origin.y, dz = c.z - origin.z;
+    const double z = sqrt((dx * dx + dy * dy) + dz * dz);
+    const double spanned_angle = 2.0 * atan2(m.c_vs, z * 2.0);
+    const double new_weight = spanned_angle * spanned_angle / e.ray_angle_xy / (z * z);
+    const double gain = new_weight / (new_weight + w);
+    return gain > e.min_impact_factor ? gain : 0.0;
+  }
+  if (state == 2) {  // unobserved voxel
+    if (e.frontier_voxel_weight > 0.0 && is_frontier_voxel(m, ct, e, c)) return e.frontier_voxel_weight;
+    return e.new_voxel_weight;
+  }
+  return 0.0;
 }
 
 // order-sensitive digest (DESIGN.md "digest"): h = h * kDigestMul + digest_entry(c)

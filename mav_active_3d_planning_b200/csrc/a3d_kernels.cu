@@ -294,6 +294,15 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
     // per-lane counters: VoxelType → [state + 3*outside]; Naive/Frontier → [0]
     unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long n_vis = 0, n_samp = 0, digest = 0, set_digest = 0;
+    double wsum = 0.0;  // VoxelWeightEvaluator: per-lane partial gain
+    D3 seg_org{0.0, 0.0, 0.0};
+    if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+      if (b.seg_origin) {
+        seg_org = D3{b.seg_origin[3 * seg], b.seg_origin[3 * seg + 1], b.seg_origin[3 * seg + 2]};
+      } else if (v_end > v_begin) {
+        seg_org = D3{b.pos[3 * (v_end - 1)], b.pos[3 * (v_end - 1) + 1], b.pos[3 * (v_end - 1) + 2]};
+      }
+    }
 
     for (int view = v_begin; view < v_end; ++view) {
       // camera pose = body pose ∘ mounting transform (camera_model.cpp:24-28)
@@ -420,6 +429,9 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
                 const int cs = centre_state(m, ct, cc, slot, vi);
                 if (EVAL == A3D_EVAL_VOXEL_TYPE) {
                   cnt[cs & 3]++;  // retained entries are always inside the bounding volume
+                } else if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+                  const double w = (cs & 3) == 0 ? voxel_weight(m, cc) : 0.0;
+                  wsum += voxel_weight_value(m, ct, e, cc, cs, w, seg_org);
                 } else if (!(cs & 4)) {
                   if (EVAL == A3D_EVAL_NAIVE) {
                     cnt[0]++;
@@ -477,9 +489,15 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
     unsigned long long tot[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) tot[i] = __reduce_add_sync(kFull, cnt[i]);
+    if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(kFull, wsum, off);
+    }
     if (lane == 0) {
       if (EVAL == A3D_EVAL_VOXEL_TYPE) {
         b.gains[seg] = voxel_type_gain(e, tot);
+      } else if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+        b.gains[seg] = wsum;
       } else if (EVAL != kEvalNone) {
         b.gains[seg] = static_cast<double>(tot[0]);
       } else if (b.gains) {
@@ -522,6 +540,9 @@ static void launch_cast_gain_c(cudaStream_t st, const MapView& m, const CasterVi
       break;
     case A3D_EVAL_NAIVE:
       launch_cast_gain_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, *e, b, digest, emit, grid, block);
+      break;
+    case A3D_EVAL_VOXEL_WEIGHT:
+      launch_cast_gain_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, *e, b, digest, emit, grid, block);
       break;
     default:
       launch_cast_gain_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, *e, b, digest, emit, grid, block);
@@ -577,12 +598,13 @@ void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long lo
 __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
                                    const double* __restrict__ centres,
                                    unsigned long long* __restrict__ counters,
-                                   uint8_t* __restrict__ keep) {
+                                   uint8_t* __restrict__ keep, D3 origin, double* __restrict__ gain_acc) {
   __shared__ CenterTables ct;
   init_center_tables(m, &ct);
   __syncthreads();
   unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
   unsigned left = 0;
+  double wsum = 0.0;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const D3 c{centres[3 * i], centres[3 * i + 1], centres[3 * i + 2]};
@@ -590,6 +612,9 @@ __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
     if (e.kind == A3D_EVAL_VOXEL_TYPE) {
       const int s = voxel_state(m, ct, c);
       cnt[s + (bv_contains(e, c) ? 0 : 3)]++;
+    } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
+      const int s = voxel_state(m, ct, c);
+      wsum += voxel_weight_value(m, ct, e, c, s, s == 0 ? voxel_weight(m, c) : 0.0, origin);
     } else {
       kp = !is_observed(m, c);
       if (kp && e.kind == A3D_EVAL_NAIVE) cnt[0]++;
@@ -606,12 +631,19 @@ __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
   }
   const unsigned tl = __reduce_add_sync(kFull, left);
   if ((threadIdx.x & 31) == 0 && tl) atomicAdd(counters + 6, static_cast<unsigned long long>(tl));
+  if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(kFull, wsum, off);
+    if ((threadIdx.x & 31) == 0 && wsum != 0.0) atomicAdd(gain_acc, wsum);
+  }
 }
 
 void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& e, long long n,
-                             const double* centres, unsigned long long* counters, uint8_t* keep) {
+                             const double* centres, unsigned long long* counters, uint8_t* keep,
+                             D3 origin, double* gain_acc) {
   if (n <= 0) return;
-  k_gain_from_voxels<<<grid_for(n, 128), 128, 0, st>>>(m, e, n, centres, counters, keep);
+  k_gain_from_voxels<<<grid_for(n, 128), 128, 0, st>>>(m, e, n, centres, counters, keep, origin,
+                                                       gain_acc);
 }
 
 }  // namespace a3d

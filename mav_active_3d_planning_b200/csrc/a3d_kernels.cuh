@@ -42,6 +42,7 @@ struct Batch {
   unsigned long long* digests;      // order-sensitive digest (k_cast_gain only)
   unsigned long long* set_digests;  // order-independent digest (both kernels)
   const unsigned int* seg_mask;     // k_cast_gain: if set, only segments whose bit is 1 are evaluated
+  const double* seg_origin;         // n_segments×3 or null (VoxelWeightEvaluator's origin)
   double* centres_out;  // emit mode (single segment): cap×3
   long long cap;
   int8_t* tables;       // per-warp ray tables (iterative), table_stride bytes each
@@ -71,7 +72,7 @@ void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, co
                       const Batch& b, bool digest, bool emit, int grid, int block);
 void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& e, long long n,
                              const double* centres, unsigned long long* counters /*8*/,
-                             uint8_t* keep);
+                             uint8_t* keep, D3 origin, double* gain_acc /*1, VoxelWeight*/);
 void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long long m,
                           const double* other, uint8_t* keep);
 int cast_gain_block_threads();

@@ -5,6 +5,7 @@
 //   VoxelTypeEvaluator          .../voxel_type_evaluator.h, .cpp:19-89
 //   NaiveEvaluator              .../naive_evaluator.h, .cpp:15-38
 //   FrontierEvaluator           .../frontier_evaluator.h, .cpp:15-124
+//   VoxelWeightEvaluator        .../voxel_weight_evaluator.h, .cpp:15-83
 // computeGains() is the additive batch entry point: the reference evaluates one
 // segment per call (online_planner.cpp:414-416); a B200 wants thousands per launch.
 #pragma once
@@ -130,9 +131,25 @@ class FrontierEvaluator : public SimulatedSensorEvaluator {
  protected:
   int evalKind() const override;
   void fillEvalParams(void* p) override;
+  void readFrontierParams(Module::ParamMap* param_map);
   static ModuleFactoryRegistry::Registration<FrontierEvaluator> registration;
   bool p_accurate_frontiers_, p_surface_frontiers_;
   double p_checking_distance_;
+};
+
+// Reconstruction gain of the paper: TSDF-weight based impact of surface voxels, frontier and new
+// voxels with fixed weights.  Evaluated by the scan-order kernel.
+class VoxelWeightEvaluator : public FrontierEvaluator {
+ public:
+  explicit VoxelWeightEvaluator(PlannerI& planner) : FrontierEvaluator(planner) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+
+ protected:
+  int evalKind() const override;
+  void fillEvalParams(void* p) override;
+  static ModuleFactoryRegistry::Registration<VoxelWeightEvaluator> registration;
+  double p_frontier_voxel_weight_, p_min_impact_factor_, p_new_voxel_weight_, p_ray_angle_x_,
+      p_ray_angle_y_;
 };
 
 }  // namespace trajectory_evaluator

@@ -393,7 +393,7 @@ bool runVisible(a3d_ctx* ctx, a3d_caster* caster, a3d_eval* eval, int n_views, c
   std::vector<double> flat(static_cast<size_t>(cap) * 3);
   int64_t n = 0, n_samples = 0;
   const int rc = a3d_visible_voxels(ctx, caster, eval, n_views, pos, quat, flat.data(), cap, &n,
-                                    &n_samples, gain);
+                                    &n_samples, gain, nullptr);
   if (rc != A3D_OK) {
     planner.printError(std::string("a3d_visible_voxels: ") + a3d_last_error(ctx));
     return false;
@@ -526,6 +526,7 @@ void SimulatedSensorEvaluator::buildEval() {
   p.surface_frontiers = 1;
   p.checking_distance = 1.0;
   p.gains[0] = 1.0;
+  p.ray_angle_x = p.ray_angle_y = 0.0025;
   fillEvalParams(&p);
   p.bv_is_setup = bounding_volume_ && bounding_volume_->is_setup;
   if (bounding_volume_) {
@@ -611,9 +612,11 @@ bool SimulatedSensorEvaluator::computeGainFromVisibleVoxels(TrajectorySegment* t
   std::vector<uint8_t> keep(n, 1);
   double gain = 0.0;
   int64_t n_left = 0;
-  const bool erases = evalKind() != A3D_EVAL_VOXEL_TYPE;
+  const bool erases = evalKind() == A3D_EVAL_NAIVE || evalKind() == A3D_EVAL_FRONTIER;
+  // VoxelWeightEvaluator measures from the segment's last trajectory point (voxel_weight_evaluator.cpp:53)
+  const double* origin = traj_in->trajectory.empty() ? nullptr : traj_in->trajectory.back().position_W.data();
   if (a3d_gain_from_voxels(gpu_map_->context(), eval_, static_cast<int64_t>(n), flat.data(), &gain, &n_left,
-                           erases ? keep.data() : nullptr) != A3D_OK) {
+                           erases ? keep.data() : nullptr, origin) != A3D_OK) {
     planner_.printError(std::string("a3d_gain_from_voxels: ") + a3d_last_error(gpu_map_->context()));
     return false;
   }
@@ -643,11 +646,14 @@ bool SimulatedSensorEvaluator::computeGains(const std::vector<TrajectorySegment*
     gatherPoses(*segments[s], indices, &pos, &quat);
     view_segment.insert(view_segment.end(), indices.size(), static_cast<int32_t>(s));
   }
-  std::vector<double> gains(segments.size(), 0.0);
+  std::vector<double> gains(segments.size(), 0.0), origins(segments.size() * 3, 0.0);
+  for (size_t s = 0; s < segments.size(); ++s)
+    if (!segments[s]->trajectory.empty())
+      for (int k = 0; k < 3; ++k) origins[3 * s + k] = segments[s]->trajectory.back().position_W[k];
   const int rc = a3d_compute_gains(gpu_map_->context(), cam->handle(), eval_,
                                    static_cast<int>(view_segment.size()), pos.data(), quat.data(),
                                    view_segment.data(), static_cast<int>(segments.size()), gains.data(),
-                                   nullptr, nullptr, nullptr, nullptr);
+                                   nullptr, nullptr, nullptr, nullptr, origins.data());
   if (rc != A3D_OK) {
     planner_.printError(std::string("a3d_compute_gains: ") + a3d_last_error(gpu_map_->context()));
     return false;
@@ -697,10 +703,7 @@ int NaiveEvaluator::evalKind() const { return A3D_EVAL_NAIVE; }
 
 ModuleFactoryRegistry::Registration<FrontierEvaluator> FrontierEvaluator::registration("FrontierEvaluator");
 void FrontierEvaluator::setupFromParamMap(Module::ParamMap* param_map) {  // frontier_evaluator.cpp:15-28
-  SimulatedSensorEvaluator::setupFromParamMap(param_map);
-  setParam<bool>(param_map, "accurate_frontiers", &p_accurate_frontiers_, false);
-  setParam<bool>(param_map, "surface_frontiers", &p_surface_frontiers_, true);
-  setParam<double>(param_map, "checking_distance", &p_checking_distance_, 1.0);
+  readFrontierParams(param_map);
   buildEval();
 }
 int FrontierEvaluator::evalKind() const { return A3D_EVAL_FRONTIER; }
@@ -709,6 +712,36 @@ void FrontierEvaluator::fillEvalParams(void* ptr) {
   p->accurate_frontiers = p_accurate_frontiers_ ? 1 : 0;
   p->surface_frontiers = p_surface_frontiers_ ? 1 : 0;
   p->checking_distance = p_checking_distance_;
+}
+void FrontierEvaluator::readFrontierParams(Module::ParamMap* param_map) {
+  SimulatedSensorEvaluator::setupFromParamMap(param_map);
+  setParam<bool>(param_map, "accurate_frontiers", &p_accurate_frontiers_, false);
+  setParam<bool>(param_map, "surface_frontiers", &p_surface_frontiers_, true);
+  setParam<double>(param_map, "checking_distance", &p_checking_distance_, 1.0);
+}
+
+ModuleFactoryRegistry::Registration<VoxelWeightEvaluator> VoxelWeightEvaluator::registration(
+    "VoxelWeightEvaluator");
+void VoxelWeightEvaluator::setupFromParamMap(Module::ParamMap* param_map) {  // voxel_weight_evaluator.cpp:15-33
+  readFrontierParams(param_map);
+  setParam<double>(param_map, "frontier_voxel_weight", &p_frontier_voxel_weight_, 1.0);
+  setParam<double>(param_map, "min_impact_factor", &p_min_impact_factor_, 0.0);
+  setParam<double>(param_map, "new_voxel_weight", &p_new_voxel_weight_, 0.01);
+  setParam<double>(param_map, "ray_angle_x", &p_ray_angle_x_, 0.0025);
+  setParam<double>(param_map, "ray_angle_y", &p_ray_angle_y_, 0.0025);
+  if (!dynamic_cast<map::TSDFMap*>(&(planner_.getMap())))
+    planner_.printError("'VoxelWeightEvaluator' requires a map of type 'TSDFMap'!");
+  buildEval();
+}
+int VoxelWeightEvaluator::evalKind() const { return A3D_EVAL_VOXEL_WEIGHT; }
+void VoxelWeightEvaluator::fillEvalParams(void* ptr) {
+  FrontierEvaluator::fillEvalParams(ptr);
+  auto* p = static_cast<a3d_eval_params*>(ptr);
+  p->frontier_voxel_weight = p_frontier_voxel_weight_;
+  p->min_impact_factor = p_min_impact_factor_;
+  p->new_voxel_weight = p_new_voxel_weight_;
+  p->ray_angle_x = p_ray_angle_x_;
+  p->ray_angle_y = p_ray_angle_y_;
 }
 
 }  // namespace trajectory_evaluator

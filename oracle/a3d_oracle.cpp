@@ -407,9 +407,33 @@ bool isFrontierVoxel(const orc_map& m, const orc_eval_params& e, const std::vect
 // computeGainFromVisibleVoxels: voxel_type_evaluator.cpp:57-89, naive_evaluator.cpp:20-38,
 // frontier_evaluator.cpp:100-124.  Mutates the list like the reference does.
 double foldGain(const orc_map& m, const orc_eval_params& e, std::vector<V3>* voxels,
-                uint64_t* lookups) {
+                uint64_t* lookups, const V3& origin) {
   double gain = 0.0;
-  if (e.kind == ORC_EVAL_VOXEL_TYPE) {
+  if (e.kind == ORC_EVAL_VOXEL_WEIGHT) {
+    // voxel_weight_evaluator.cpp:43-83 (the stored list is not modified)
+    const std::vector<V3> nb = frontierOffsets(m, e);
+    for (size_t i = 0; i < voxels->size(); ++i) {
+      const V3& voxel = (*voxels)[i];
+      const unsigned char s = m.getVoxelState(voxel);
+      *lookups += 8;
+      if (s == ORC_OCCUPIED) {
+        const V3 dv{voxel.x - origin.x, voxel.y - origin.y, voxel.z - origin.z};
+        const double z = std::sqrt((dv.x * dv.x + dv.y * dv.y) + dv.z * dv.z);
+        const double spanned_angle = 2.0 * std::atan2(m.c_voxel_size, z * 2.0);
+        const double new_weight =
+            std::pow(spanned_angle, 2.0) / (e.ray_angle_x * e.ray_angle_y) / std::pow(z, 2.0);
+        *lookups += 1;
+        const double g = new_weight / (new_weight + m.getVoxelWeight(voxel));
+        if (g > e.min_impact_factor) gain += g;
+      } else if (s == ORC_UNKNOWN) {
+        if (e.frontier_voxel_weight > 0.0 && isFrontierVoxel(m, e, nb, voxel, lookups)) {
+          gain += e.frontier_voxel_weight;
+        } else {
+          gain += e.new_voxel_weight;
+        }
+      }
+    }
+  } else if (e.kind == ORC_EVAL_VOXEL_TYPE) {
     const double g_unknown = e.gains[0], g_occupied = e.gains[1], g_free = e.gains[2];
     const double g_unknown_o = e.gains[3], g_occupied_o = e.gains[4], g_free_o = e.gains[5];
     for (size_t i = 0; i < voxels->size(); ++i) {
@@ -649,7 +673,7 @@ int orc_compute_gains(const orc_caster* c, const orc_eval_params* e, int n_views
                       const double* quat, const int32_t* view_segment, int n_segments,
                       const int32_t* parent, double* gains_out, uint64_t* n_visible_out,
                       uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* n_fold_out,
-                      int n_threads, uint64_t* set_digests_out) {
+                      int n_threads, uint64_t* set_digests_out, const double* seg_origin) {
   // view ranges per segment
   std::vector<int> first(n_segments + 1, 0);
   for (int v = 0; v < n_views; ++v) {
@@ -691,7 +715,13 @@ int orc_compute_gains(const orc_caster* c, const orc_eval_params* e, int n_views
     if (digests_out) digests_out[s] = digestList(new_voxels);
     if (set_digests_out) set_digests_out[s] = digestSet(new_voxels);
     uint64_t lookups = 0;
-    gains_out[s] = foldGain(*c->map, *e, &new_voxels, &lookups);
+    V3 origin{0, 0, 0};
+    if (seg_origin) {
+      origin = V3{seg_origin[3 * s], seg_origin[3 * s + 1], seg_origin[3 * s + 2]};
+    } else if (nv > 0) {
+      origin = V3{pos[3 * (v0 + nv - 1)], pos[3 * (v0 + nv - 1) + 1], pos[3 * (v0 + nv - 1) + 2]};
+    }
+    gains_out[s] = foldGain(*c->map, *e, &new_voxels, &lookups, origin);
     if (n_fold_out) n_fold_out[s] = lookups;
     if (keep_lists) stored[s] = std::move(new_voxels);
   };
@@ -711,11 +741,12 @@ int orc_compute_gains(const orc_caster* c, const orc_eval_params* e, int n_views
 }
 
 double orc_gain_from_voxels(const orc_map* m, const orc_eval_params* e, int64_t n,
-                            const double* centres, int64_t* n_left) {
+                            const double* centres, int64_t* n_left, const double* origin) {
   std::vector<V3> v(static_cast<size_t>(n));
   for (int64_t i = 0; i < n; ++i) v[i] = V3{centres[3 * i], centres[3 * i + 1], centres[3 * i + 2]};
   uint64_t lookups = 0;
-  const double g = foldGain(*m, *e, &v, &lookups);
+  const V3 o = origin ? V3{origin[0], origin[1], origin[2]} : V3{0, 0, 0};
+  const double g = foldGain(*m, *e, &v, &lookups, o);
   if (n_left) *n_left = static_cast<int64_t>(v.size());
   return g;
 }

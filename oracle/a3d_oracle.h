@@ -26,7 +26,7 @@ typedef struct orc_caster orc_caster;
 
 enum { ORC_OCCUPIED = 0, ORC_FREE = 1, ORC_UNKNOWN = 2 }; /* occupancy_map.h:17-19 */
 enum { ORC_CASTER_SIMPLE = 0, ORC_CASTER_ITERATIVE = 1 };
-enum { ORC_EVAL_VOXEL_TYPE = 0, ORC_EVAL_NAIVE = 1, ORC_EVAL_FRONTIER = 2 };
+enum { ORC_EVAL_VOXEL_TYPE = 0, ORC_EVAL_NAIVE = 1, ORC_EVAL_FRONTIER = 2, ORC_EVAL_VOXEL_WEIGHT = 3 };
 
 typedef struct {
   int32_t kind;                /* ORC_CASTER_* */
@@ -55,6 +55,8 @@ typedef struct {
   double bv_min[3];
   double bv_max[3];
   double bv_quat[4];            /* w,x,y,z of AngleAxis(-rotation*pi/180, Z) (bounding_volume.cpp:21) */
+  /* voxel_weight_evaluator.cpp:17-22 */
+  double frontier_voxel_weight, min_impact_factor, new_voxel_weight, ray_angle_x, ray_angle_y;
 } orc_eval_params;
 
 /* ---- map (VoxbloxLite: restated voxblox Layer<EsdfVoxel>/<TsdfVoxel> + Interpolator) ---- */
@@ -103,11 +105,14 @@ int orc_compute_gains(const orc_caster* c, const orc_eval_params* e, int n_views
                       const double* quat, const int32_t* view_segment, int n_segments,
                       const int32_t* parent, double* gains_out, uint64_t* n_visible_out,
                       uint64_t* n_samples_out, uint64_t* digests_out,
-                      uint64_t* n_fold_lookups_out, int n_threads, uint64_t* set_digests_out);
+                      uint64_t* n_fold_lookups_out, int n_threads, uint64_t* set_digests_out,
+                      const double* seg_origin /* n_segments x 3, nullable: position of the segment's last
+                                                  trajectory point (voxel_weight_evaluator.cpp:53);
+                                                  default = body position of its last view */);
 /* computeGainFromVisibleVoxels on an explicit list (n×3 centres) — SimulatedSensorUpdater path.
    Returns gain; n_left (nullable) = list size after the fold's own erasures. */
 double orc_gain_from_voxels(const orc_map* m, const orc_eval_params* e, int64_t n,
-                            const double* centres, int64_t* n_left);
+                            const double* centres, int64_t* n_left, const double* origin /*3, nullable*/);
 /* BoundingVolume::contains (bounding_volume.cpp:33-57) */
 void orc_bv_contains(const orc_eval_params* e, int64_t n, const double* pts, uint8_t* out);
 /* order-sensitive digest of a centre list (shared definition with the product) */

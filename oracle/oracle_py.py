@@ -28,11 +28,15 @@ class EvalParams(C.Structure):
                 ("accurate_frontiers", C.c_int32), ("surface_frontiers", C.c_int32),
                 ("checking_distance", C.c_double), ("gains", C.c_double * 6),
                 ("bv_is_setup", C.c_int32), ("_pad", C.c_int32), ("bv_min", C.c_double * 3),
-                ("bv_max", C.c_double * 3), ("bv_quat", C.c_double * 4)]
+                ("bv_max", C.c_double * 3), ("bv_quat", C.c_double * 4),
+                ("frontier_voxel_weight", C.c_double), ("min_impact_factor", C.c_double),
+                ("new_voxel_weight", C.c_double), ("ray_angle_x", C.c_double),
+                ("ray_angle_y", C.c_double)]
 
 
 _CASTER_KINDS = {"SimpleRayCaster": 0, "IterativeRayCaster": 1}
-_EVAL_KINDS = {"VoxelTypeEvaluator": 0, "NaiveEvaluator": 1, "FrontierEvaluator": 2}
+_EVAL_KINDS = {"VoxelTypeEvaluator": 0, "NaiveEvaluator": 1, "FrontierEvaluator": 2,
+               "VoxelWeightEvaluator": 3}
 
 
 def build(force: bool = False) -> str:
@@ -83,10 +87,10 @@ def lib():
     L.orc_visible_voxels.argtypes = [vp, C.c_int, vp, vp, vp, i64, P(i64)]
     L.orc_visible_voxels.restype = i64
     L.orc_compute_gains.argtypes = [vp, P(EvalParams), C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
-                                    vp, vp, vp, C.c_int, vp]
+                                    vp, vp, vp, C.c_int, vp, vp]
     L.orc_digest_set.argtypes = [i64, vp]
     L.orc_digest_set.restype = C.c_uint64
-    L.orc_gain_from_voxels.argtypes = [vp, P(EvalParams), i64, vp, P(i64)]
+    L.orc_gain_from_voxels.argtypes = [vp, P(EvalParams), i64, vp, P(i64), vp]
     L.orc_gain_from_voxels.restype = dbl
     L.orc_bv_contains.argtypes = [P(EvalParams), i64, vp, vp]
     L.orc_bv_contains.restype = None
@@ -126,10 +130,14 @@ def caster_params(kind, *, ray_length=5.0, focal_length=320.0, resolution_x=640,
 def eval_params(kind, *, clear_from_parents=False, accurate_frontiers=False, surface_frontiers=True,
                 checking_distance=1.0, gain_unknown=1.0, gain_occupied=0.0, gain_free=0.0,
                 gain_unknown_outer=0.0, gain_occupied_outer=0.0, gain_free_outer=0.0,
-                bounding_volume=None):
+                bounding_volume=None, frontier_voxel_weight=1.0, min_impact_factor=0.0,
+                new_voxel_weight=0.01, ray_angle_x=0.0025, ray_angle_y=0.0025):
     if isinstance(kind, str):
         kind = _EVAL_KINDS[kind]
     p = EvalParams()
+    p.frontier_voxel_weight, p.min_impact_factor = float(frontier_voxel_weight), float(min_impact_factor)
+    p.new_voxel_weight = float(new_voxel_weight)
+    p.ray_angle_x, p.ray_angle_y = float(ray_angle_x), float(ray_angle_y)
     p.kind = kind
     p.clear_from_parents = int(bool(clear_from_parents))
     p.accurate_frontiers = int(bool(accurate_frontiers))
@@ -223,11 +231,13 @@ class OracleMap:
     def caster(self, kind, **kw):
         return OracleCaster(self, caster_params(kind, **kw))
 
-    def gain_from_voxels(self, eparams, centres):
+    def gain_from_voxels(self, eparams, centres, origin=None):
         centres = _pts(centres) if len(centres) else np.zeros((0, 3))
         left = C.c_int64()
+        if origin is not None:
+            origin = np.ascontiguousarray(origin, np.float64)
         g = self.L.orc_gain_from_voxels(self.h, C.byref(eparams), len(centres), _ptr(centres),
-                                        C.byref(left))
+                                        C.byref(left), _ptr(origin))
         return float(g), int(left.value)
 
 
@@ -273,7 +283,7 @@ class OracleCaster:
         return out[:n].copy(), int(ns.value)
 
     def compute_gains(self, eparams, pos, quat, view_segment=None, n_segments=None, parent=None,
-                      n_threads=1):
+                      n_threads=1, seg_origin=None):
         pos = _pts(pos)
         quat = np.ascontiguousarray(quat, np.float64)
         n_views = len(pos)
@@ -293,7 +303,9 @@ class OracleCaster:
         rc = self.L.orc_compute_gains(self.h, C.byref(eparams), n_views, _ptr(pos), _ptr(quat),
                                       _ptr(view_segment), n_segments, _ptr(parent), _ptr(gains),
                                       _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(fold), n_threads,
-                                      _ptr(sdig))
+                                      _ptr(sdig),
+                                      _ptr(None if seg_origin is None
+                                           else np.ascontiguousarray(seg_origin, np.float64)))
         if rc:
             raise ValueError("orc_compute_gains: bad view_segment")
         return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig, set_digest=sdig,

@@ -458,3 +458,42 @@ def test_cfg3_small_clutter_frontier(capi, O):
         assert np.array_equal(got["gain"], want["gain"])
         assert want["gain"].max() > 0
     ctx.close()
+
+
+@pytest.mark.parametrize("ckind", ["IterativeRayCaster", "SimpleRayCaster"])
+def test_voxel_weight_evaluator(capi, O, room02, ckind):
+    """VoxelWeightEvaluator (voxel_weight_evaluator.cpp:43-83): TSDF-weight impact of
+    surface voxels + frontier / new-voxel weights; atan2/pow/sqrt in double → 1e-5 relative."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    caster = ctx.caster(ckind, **CAM_BASE)
+    oc = om.caster(ckind, **CAM_BASE)
+    pos, quat = synth.candidate_views(room02, 24, seed=51)
+    for kw in (dict(), dict(frontier_voxel_weight=0.5, min_impact_factor=0.02, new_voxel_weight=0.05,
+                            ray_angle_x=0.003, ray_angle_y=0.002, accurate_frontiers=True,
+                            bounding_volume=dict(x_min=3, x_max=17, y_min=3, y_max=17, z_min=0.5, z_max=8))):
+        ev = ctx.evaluator("VoxelWeightEvaluator", **kw)
+        oe = O.eval_params("VoxelWeightEvaluator", **kw)
+        got = ctx.compute_gains(caster, ev, pos, quat)
+        want = oc.compute_gains(oe, pos, quat, n_threads=8)
+        assert ctx.last_cast_kernel == 1          # scan-order kernel
+        for k in ("n_samples", "n_visible", "digest"):
+            assert np.array_equal(got[k], want[k]), k
+        assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
+        assert want["gain"].max() > 1.0
+        # digests=False must not switch to the wavefront kernel for this evaluator
+        got2 = ctx.compute_gains(caster, ev, pos, quat, digests=False)
+        assert ctx.last_cast_kernel == 1 and np.allclose(got2["gain"], want["gain"], rtol=GAIN_RTOL)
+        # multi-view segments with an explicit origin per segment, and the stored-list fold
+        seg = np.repeat(np.arange(6, dtype=np.int32), 4)
+        org = pos[::4] + 0.3
+        got = ctx.compute_gains(caster, ev, pos, quat, seg, 6, seg_origin=org)
+        want = oc.compute_gains(oe, pos, quat, seg, 6, seg_origin=org)
+        assert np.array_equal(got["digest"], want["digest"])
+        assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
+        lst, _, g1 = ctx.visible_voxels(caster, pos[:4], quat[:4], evaluator=ev, origin=org[0])
+        assert np.isclose(g1, want["gain"][0], rtol=GAIN_RTOL)
+        g2, left, _ = ctx.gain_from_voxels(ev, lst, origin=org[0])
+        og2, oleft = om.gain_from_voxels(oe, lst, origin=org[0])
+        assert np.isclose(g2, og2, rtol=GAIN_RTOL) and left == oleft == len(lst)
+    ctx.close()
