@@ -153,6 +153,11 @@ int a3d_map_voxel_center(a3d_ctx* ctx, int64_t n, const double* pts, double* out
 int a3d_map_is_observed(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out);
 int a3d_map_voxel_weight(a3d_ctx* ctx, int64_t n, const double* pts, double* out);
 int a3d_map_distance(a3d_ctx* ctx, int64_t n, const double* pts, double* dist, uint8_t* ok);
+/* Batched VoxbloxMap::isTraversable (voxblox.cpp:32-41): observed and interpolated ESDF distance >
+   collision_radius — the collision checks of TrajectoryGenerator::checkTraversable
+   (core/src/module/trajectory_generator.cpp:30-46) and RRT::connectPoses (rrt.cpp:251-258). */
+int a3d_map_traversable(a3d_ctx* ctx, int64_t n, const double* pts, double collision_radius,
+                        uint8_t* out);
 
 /* ---- sensor model / evaluator objects ------------------------------------------------------- */
 /* Needs a configured map (ray_step default and c_res_* depend on the voxel size,

@@ -33,7 +33,7 @@ EXPORTS = [
     "a3d_kernel_launches", "a3d_set_option", "a3d_last_cast_kernel", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev",
     "a3d_map_remove_blocks", "a3d_map_clear", "a3d_map_num_blocks", "a3d_map_voxel_size",
     "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
-    "a3d_map_distance", "a3d_caster_create", "a3d_caster_destroy", "a3d_caster_get_info",
+    "a3d_map_distance", "a3d_map_traversable", "a3d_caster_create", "a3d_caster_destroy", "a3d_caster_get_info",
     "a3d_caster_direction", "a3d_eval_create", "a3d_eval_destroy", "a3d_compute_gains",
     "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_filter_not_in", "a3d_bv_contains",
 ]
@@ -153,6 +153,7 @@ def load_library(path: str = LIB_PATH):
                  "a3d_map_voxel_weight"):
         getattr(lib, name).argtypes = [vp, i64, vp, vp]
     lib.a3d_map_distance.argtypes = [vp, i64, vp, vp, vp]
+    lib.a3d_map_traversable.argtypes = [vp, i64, vp, dbl, vp]
     lib.a3d_caster_create.argtypes = [vp, P(CasterParams), P(vp)]
     lib.a3d_caster_destroy.argtypes = [vp]
     lib.a3d_caster_destroy.restype = None
@@ -297,6 +298,13 @@ class Context:
         ok = np.empty(len(pts), np.uint8)
         self._ck(self.lib.a3d_map_distance(self.h, len(pts), _ptr(pts), _ptr(d), _ptr(ok)))
         return d, ok
+
+    def traversable(self, pts, collision_radius):
+        pts = _pts(pts)
+        out = np.empty(len(pts), np.uint8)
+        self._ck(self.lib.a3d_map_traversable(self.h, len(pts), _ptr(pts), float(collision_radius),
+                                              _ptr(out)))
+        return out
 
     # ---- modules ----
     def caster(self, kind, **kw):

@@ -423,7 +423,7 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
 }
 
 int point_query(a3d_ctx* ctx, int what, int64_t n, const double* pts, void* out0, size_t out0_elt,
-                void* out1) {
+                void* out1, double arg = 0.0) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
   if (n < 0 || (n > 0 && (!pts || !out0))) return ctx->fail(A3D_ERR_INVALID, "null argument");
@@ -440,7 +440,8 @@ int point_query(a3d_ctx* ctx, int what, int64_t n, const double* pts, void* out0
   const size_t out0_bytes = static_cast<size_t>(n) * out0_elt;
   CK(ctx->sc_out.reserve((out0_bytes + 7) / 8));
   CK(ctx->sc_u8.reserve(n));
-  launch_point_query(ctx->stream, ctx->view(), what, n, ctx->sc_pts.p, ctx->sc_out.p, ctx->sc_u8.p);
+  launch_point_query(ctx->stream, ctx->view(), what, n, ctx->sc_pts.p, ctx->sc_out.p, ctx->sc_u8.p,
+                     arg);
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out0, ctx->sc_out.p, out0_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -734,6 +735,10 @@ int a3d_map_is_observed(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out
 }
 int a3d_map_voxel_weight(a3d_ctx* ctx, int64_t n, const double* pts, double* out) {
   return point_query(ctx, kQueryWeight, n, pts, out, 8, nullptr);
+}
+int a3d_map_traversable(a3d_ctx* ctx, int64_t n, const double* pts, double collision_radius,
+                        uint8_t* out) {
+  return point_query(ctx, kQueryTraversable, n, pts, out, 1, nullptr, collision_radius);
 }
 int a3d_map_distance(a3d_ctx* ctx, int64_t n, const double* pts, double* dist, uint8_t* ok) {
   if (ctx && n > 0 && !ok) return ctx->fail(A3D_ERR_INVALID, "null argument");

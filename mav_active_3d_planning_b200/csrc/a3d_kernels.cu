@@ -179,7 +179,7 @@ void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* 
 
 // ---------------------------------------------------------------------------------------------
 __global__ void k_point_query(MapView m, int what, long long n, const double* __restrict__ pts,
-                              void* out0, void* out1) {
+                              void* out0, void* out1, double arg) {
   __shared__ CenterTables ct;
   init_center_tables(m, &ct);
   __syncthreads();
@@ -208,6 +208,13 @@ __global__ void k_point_query(MapView m, int what, long long n, const double* __
       case kQueryWeight:
         static_cast<double*>(out0)[i] = voxel_weight(m, p);
         break;
+      case kQueryTraversable: {  // VoxbloxMap::isTraversable (voxblox.cpp:32-41)
+        float d = 0.0f;
+        const bool ok = interp_distance_generic(m, __double2float_rn(p.x), __double2float_rn(p.y),
+                                                __double2float_rn(p.z), &d);
+        static_cast<uint8_t*>(out0)[i] = (ok && static_cast<double>(d) > arg) ? 1 : 0;
+        break;
+      }
       case kQueryDistance: {
         float d = 0.0f;
         const bool ok = interp_distance_generic(m, __double2float_rn(p.x), __double2float_rn(p.y),
@@ -221,9 +228,9 @@ __global__ void k_point_query(MapView m, int what, long long n, const double* __
 }
 
 void launch_point_query(cudaStream_t st, const MapView& m, int what, long long n, const double* pts,
-                        void* out0, void* out1) {
+                        void* out0, void* out1, double arg) {
   if (n <= 0) return;
-  k_point_query<<<grid_for(n, 128), 128, 0, st>>>(m, what, n, pts, out0, out1);
+  k_point_query<<<grid_for(n, 128), 128, 0, st>>>(m, what, n, pts, out0, out1, arg);
 }
 
 __global__ void k_bv_contains(EvalView e, long long n, const double* __restrict__ pts,

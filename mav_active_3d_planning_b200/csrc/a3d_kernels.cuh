@@ -65,7 +65,7 @@ void launch_refresh_aprons(cudaStream_t st, const MapView& m, int n, const int32
 void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                        const int32_t* block_idx_dev /*n×3*/, uint32_t* mword_slab);
 void launch_point_query(cudaStream_t st, const MapView& m, int what, long long n, const double* pts,
-                        void* out0, void* out1);
+                        void* out0, void* out1, double arg = 0.0);
 void launch_bv_contains(cudaStream_t st, const EvalView& e, long long n, const double* pts,
                         uint8_t* out);
 void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView* e,
@@ -84,6 +84,6 @@ int cast_wave_threads();
 int cast_wave_max_diag();
 
 enum { kQueryState = 0, kQueryCenter = 1, kQueryObserved = 2, kQueryWeight = 3, kQueryDistance = 4,
-       kQueryStateGeneric = 5 };
+       kQueryStateGeneric = 5, kQueryTraversable = 6 };
 
 }  // namespace a3d

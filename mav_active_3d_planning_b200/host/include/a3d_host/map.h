@@ -31,7 +31,7 @@ namespace map {
 class OccupancyMap : public Map {
  public:
   explicit OccupancyMap(PlannerI& planner) : Map(planner) {}  // NOLINT
-  static const unsigned char OCCUPIED = 0, FREE = 1, UNKNOWN = 2;
+  static constexpr unsigned char OCCUPIED = 0, FREE = 1, UNKNOWN = 2;
   virtual unsigned char getVoxelState(const Eigen::Vector3d& point) = 0;
   virtual double getVoxelSize() = 0;
   virtual bool getVoxelCenter(Eigen::Vector3d* center, const Eigen::Vector3d& point) = 0;
@@ -74,6 +74,8 @@ class VoxbloxMap : public TSDFMap {
 
   // batched queries (one kernel launch each)
   void getVoxelStates(const std::vector<Eigen::Vector3d>& points, std::vector<unsigned char>* states);
+  // isTraversable for many points (the collision checks of a whole candidate trajectory / RRT edge)
+  void areTraversable(const std::vector<Eigen::Vector3d>& points, std::vector<unsigned char>* out);
 
   a3d_ctx* context() { return ctx_; }
 

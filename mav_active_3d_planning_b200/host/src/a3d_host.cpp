@@ -209,6 +209,15 @@ void VoxbloxMap::getVoxelStates(const std::vector<Eigen::Vector3d>& points,
   check(a3d_map_voxel_state(ctx_, static_cast<int64_t>(points.size()), flat.data(), states->data()),
         "a3d_map_voxel_state");
 }
+void VoxbloxMap::areTraversable(const std::vector<Eigen::Vector3d>& points, std::vector<unsigned char>* out) {
+  std::vector<double> flat(points.size() * 3);
+  for (size_t i = 0; i < points.size(); ++i)
+    for (int k = 0; k < 3; ++k) flat[3 * i + k] = points[i][k];
+  out->assign(points.size(), 0);
+  check(a3d_map_traversable(ctx_, static_cast<int64_t>(points.size()), flat.data(),
+                            planner_.getSystemConstraints().collision_radius, out->data()),
+        "a3d_map_traversable");
+}
 double VoxbloxMap::getVoxelSize() { return c_voxel_size_; }
 bool VoxbloxMap::getVoxelCenter(Eigen::Vector3d* center, const Eigen::Vector3d& point) {
   double c[3];

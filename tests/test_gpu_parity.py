@@ -60,6 +60,8 @@ def test_map_queries_bit_exact(capi, O, vs):
     d, ok = ctx.distance(pts)
     od, ook = om.distance(pts)
     assert np.array_equal(ok, ook) and np.array_equal(d[ok == 1], od[ook == 1])
+    for radius in (0.3, 1.0):   # VoxbloxMap::isTraversable (voxblox.cpp:32-41)
+        assert np.array_equal(ctx.traversable(pts, radius), ((ook == 1) & (od > radius)).astype(np.uint8))
     # states at emitted voxel centres (the fold's lookups)
     c = om.voxel_center(pts)
     assert np.array_equal(ctx.voxel_state(c), om.voxel_state(c))
