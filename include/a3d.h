@@ -40,6 +40,9 @@ extern "C" {
    (core/src/module/sensor_model/simple_ray_caster.cpp:10-11, iterative_ray_caster.cpp:12-13) */
 #define A3D_CASTER_SIMPLE 0
 #define A3D_CASTER_ITERATIVE 1
+/* "IterativeRayCasterLidar" (iterative_ray_caster_lidar.cpp:12-13): the iterative scheme over the
+   spherical direction model of LidarModel (lidar_model.cpp:159-165) */
+#define A3D_CASTER_ITERATIVE_LIDAR 2
 
 /* evaluator kinds = "VoxelTypeEvaluator" / "NaiveEvaluator" / "FrontierEvaluator"
    (core/src/module/trajectory_evaluator/voxel_type_evaluator.cpp:13-14, naive_evaluator.cpp:9-10,
@@ -69,6 +72,8 @@ typedef struct {
   double mount_t[3];          /* "mounting_translation_{x,y,z}" */
   double mount_q[4];          /* "mounting_rotation_{w,x,y,z}", normalised by the caller like
                                  sensor_model.cpp:27 does */
+  double field_of_view_x;     /* lidar only: "field_of_view_x" [deg] (360.0), lidar_model.cpp:170 */
+  double field_of_view_y;     /* lidar only: "field_of_view_y" [deg] (30.0) */
 } a3d_caster_params;
 
 /* Parameters of a SimulatedSensorEvaluator subclass + its BoundingVolume

@@ -21,9 +21,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("A3D_LIB_PATH") or os.path.join(_HERE, "liba3d_b200.so")
 
 OCCUPIED, FREE, UNKNOWN = 0, 1, 2
-CASTER_SIMPLE, CASTER_ITERATIVE = 0, 1
+CASTER_SIMPLE, CASTER_ITERATIVE, CASTER_ITERATIVE_LIDAR = 0, 1, 2
 EVAL_VOXEL_TYPE, EVAL_NAIVE, EVAL_FRONTIER, EVAL_VOXEL_WEIGHT = 0, 1, 2, 3
-_CASTER_KINDS = {"SimpleRayCaster": CASTER_SIMPLE, "IterativeRayCaster": CASTER_ITERATIVE}
+_CASTER_KINDS = {"SimpleRayCaster": CASTER_SIMPLE, "IterativeRayCaster": CASTER_ITERATIVE,
+                 "IterativeRayCasterLidar": CASTER_ITERATIVE_LIDAR}
 _EVAL_KINDS = {"VoxelTypeEvaluator": EVAL_VOXEL_TYPE, "NaiveEvaluator": EVAL_NAIVE,
                "FrontierEvaluator": EVAL_FRONTIER, "VoxelWeightEvaluator": EVAL_VOXEL_WEIGHT}
 
@@ -43,7 +44,8 @@ class CasterParams(C.Structure):
     _fields_ = [("kind", C.c_int32), ("resolution_x", C.c_int32), ("resolution_y", C.c_int32),
                 ("_pad", C.c_int32), ("ray_length", C.c_double), ("focal_length", C.c_double),
                 ("ray_step", C.c_double), ("downsampling_factor", C.c_double),
-                ("mount_t", C.c_double * 3), ("mount_q", C.c_double * 4)]
+                ("mount_t", C.c_double * 3), ("mount_q", C.c_double * 4),
+                ("field_of_view_x", C.c_double), ("field_of_view_y", C.c_double)]
 
 
 class EvalParams(C.Structure):
@@ -66,13 +68,15 @@ class CasterInfo(C.Structure):
 
 def caster_params(kind, *, ray_length=5.0, focal_length=320.0, resolution_x=640, resolution_y=480,
                   ray_step=0.0, downsampling_factor=1.0, mounting_translation=(0.0, 0.0, 0.0),
-                  mounting_rotation=(1.0, 0.0, 0.0, 0.0), cls=CasterParams):
+                  mounting_rotation=(1.0, 0.0, 0.0, 0.0), field_of_view_x=360.0, field_of_view_y=30.0,
+                  cls=CasterParams):
     """Reference parameter names/defaults (camera_model.cpp:170-183, sensor_model.cpp:18-27).
     ``mounting_rotation`` is (w,x,y,z) and is normalised here like sensor_model.cpp:27."""
     if isinstance(kind, str):
         kind = _CASTER_KINDS[kind]
     p = cls()
     p.kind = kind
+    p.field_of_view_x, p.field_of_view_y = float(field_of_view_x), float(field_of_view_y)
     p.resolution_x, p.resolution_y = int(resolution_x), int(resolution_y)
     p.ray_length, p.focal_length = float(ray_length), float(focal_length)
     p.ray_step, p.downsampling_factor = float(ray_step), float(downsampling_factor)

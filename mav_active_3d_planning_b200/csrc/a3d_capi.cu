@@ -753,11 +753,18 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
   // CameraModel::checkParamsValid (camera_model.cpp:185-200)
   if (!(p->ray_length > 0.0)) return ctx->fail(A3D_ERR_INVALID, "ray_length expected > 0.0");
-  if (!(p->focal_length > 0.0)) return ctx->fail(A3D_ERR_INVALID, "focal_length expected > 0.0");
+  const bool lidar = p->kind == A3D_CASTER_ITERATIVE_LIDAR;
+  if (!lidar && !(p->focal_length > 0.0))
+    return ctx->fail(A3D_ERR_INVALID, "focal_length expected > 0.0");
+  if (lidar && !(p->field_of_view_x > 0.0))
+    return ctx->fail(A3D_ERR_INVALID, "field_of_view_x expected > 0.0");  // lidar_model.cpp:185-187
+  if (lidar && !(p->field_of_view_y > 0.0))
+    return ctx->fail(A3D_ERR_INVALID, "field_of_view_y expected > 0.0");
   if (p->resolution_x <= 0) return ctx->fail(A3D_ERR_INVALID, "resolution_x expected > 0");
   if (p->resolution_y <= 0) return ctx->fail(A3D_ERR_INVALID, "resolution_y expected > 0");
-  if (p->kind != A3D_CASTER_SIMPLE && p->kind != A3D_CASTER_ITERATIVE)
+  if (p->kind != A3D_CASTER_SIMPLE && p->kind != A3D_CASTER_ITERATIVE && !lidar)
     return ctx->fail(A3D_ERR_INVALID, "unknown caster kind");
+  const bool iterative = p->kind != A3D_CASTER_SIMPLE;
   if (!(p->downsampling_factor > 0.0))
     return ctx->fail(A3D_ERR_INVALID, "downsampling_factor expected > 0.0");
   CK(cudaSetDevice(ctx->device));
@@ -767,6 +774,12 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   // camera_model.cpp:181-182
   info.fov_x = 2.0 * std::atan2(static_cast<double>(p->resolution_x), p->focal_length * 2.0);
   info.fov_y = 2.0 * std::atan2(static_cast<double>(p->resolution_y), p->focal_length * 2.0);
+  if (lidar) {  // lidar_model.cpp:170-177
+    info.fov_x = p->field_of_view_x;
+    info.fov_y = p->field_of_view_y;
+    info.fov_x *= M_PI / 180.0;
+    info.fov_y *= M_PI / 180.0;
+  }
   info.ray_step = p->ray_step > 0.0 ? p->ray_step : vs;
   // simple_ray_caster.cpp:22-29 == iterative_ray_caster.cpp:25-32
   info.c_res_x = std::min(
@@ -781,7 +794,7 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   const int n_rays = info.c_res_x * info.c_res_y;
   int n_sections = 0;
   std::vector<double> split;  // c_split_distances_
-  if (p->kind == A3D_CASTER_ITERATIVE) {
+  if (iterative) {
     // iterative_ray_caster.cpp:35-45
     n_sections = static_cast<int>(std::floor(std::log2(
         std::min(static_cast<double>(info.c_res_x), static_cast<double>(info.c_res_y)))));
@@ -799,11 +812,11 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
 
   // Accumulated sample distances (simple_ray_caster.cpp:46-50, iterative_ray_caster.cpp:75-79):
   // d_0 = start, d_{k+1} = d_k + ray_step while d_k < ray_length.  One sequence per start section.
-  const int n_starts = p->kind == A3D_CASTER_ITERATIVE ? n_sections : 1;
+  const int n_starts = iterative ? n_sections : 1;
   std::vector<std::vector<double>> seqs(n_starts);
   size_t kmax = 1;
   for (int s = 0; s < n_starts; ++s) {
-    double d = p->kind == A3D_CASTER_ITERATIVE ? split[s] : 0.0;
+    double d = iterative ? split[s] : 0.0;
     while (d < p->ray_length) {
       seqs[s].push_back(d);
       d += info.ray_step;
@@ -837,11 +850,19 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
     for (int j = 0; j < info.c_res_y; ++j) {
       const double rx = static_cast<double>(i) / (static_cast<double>(info.c_res_x) - 1.0);
       const double ry = static_cast<double>(j) / (static_cast<double>(info.c_res_y) - 1.0);
+      double* o = &c->h_dirs[(static_cast<size_t>(i) * info.c_res_y + j) * 3];
+      if (lidar) {  // LidarModel::getDirectionVector (lidar_model.cpp:159-165)
+        const double phi = (0.5 - rx) * info.fov_x;
+        const double theta = M_PI / 2.0 + (ry - 0.5) * info.fov_y;
+        o[0] = std::sin(theta) * std::cos(phi);
+        o[1] = std::sin(theta) * std::sin(phi);
+        o[2] = std::cos(theta);
+        continue;
+      }
       const double vx = p->focal_length;
       const double vy = (0.5 - rx) * static_cast<double>(p->resolution_x);
       const double vz = (0.5 - ry) * static_cast<double>(p->resolution_y);
       const double nrm = std::sqrt((vx * vx + vy * vy) + vz * vz);
-      double* o = &c->h_dirs[(static_cast<size_t>(i) * info.c_res_y + j) * 3];
       o[0] = vx / nrm;
       o[1] = vy / nrm;
       o[2] = vz / nrm;
@@ -859,7 +880,7 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
   // leaf-supply units of the wavefront kernel
   std::vector<int32_t> units;
   int n_units = (n_rays + 31) / 32;
-  if (p->kind == A3D_CASTER_ITERATIVE) {
+  if (iterative) {
     std::vector<int32_t> ud, ui;
     for (int dg = 0; dg < info.c_res_x + info.c_res_y - 1; ++dg) {
       const int i_lo = std::max(0, dg - (info.c_res_y - 1)), i_hi = std::min(info.c_res_x - 1, dg);
@@ -880,7 +901,7 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
     return ctx->cuda_fail(e, "caster table upload");
   }
   CasterView& v = c->view;
-  v.kind = p->kind;
+  v.kind = iterative ? A3D_CASTER_ITERATIVE : A3D_CASTER_SIMPLE;  // the kernels know two schemes
   v.res_x = info.c_res_x;
   v.res_y = info.c_res_y;
   v.n_rays = n_rays;

@@ -63,6 +63,7 @@ class CameraModel : public SensorModel {
   a3d_caster* caster_;          // with the mounting transform (trajectory-level calls)
   a3d_caster* caster_camera_;   // identity mount (getVisibleVoxels takes a camera pose)
   double p_ray_length_, p_sampling_time_, p_focal_length_, p_ray_step_, p_downsampling_factor_;
+  double p_fov_x_deg_, p_fov_y_deg_;  // lidar casters only
   int p_resolution_x_, p_resolution_y_;
   bool p_test_;
   double c_field_of_view_x_, c_field_of_view_y_;
@@ -86,6 +87,21 @@ class IterativeRayCaster : public CameraModel {
  protected:
   int casterKind() const override;
   static ModuleFactoryRegistry::Registration<IterativeRayCaster> registration;
+};
+
+// IterativeRayCasterLidar (iterative_ray_caster_lidar.cpp, lidar_model.cpp:159-200): the iterative
+// scheme over a spherical direction model.  The reference derives it from LidarModel, whose
+// trajectory-level logic is identical to CameraModel's; here it shares that code by deriving from
+// CameraModel and only parses the lidar parameter set.
+class IterativeRayCasterLidar : public CameraModel {
+ public:
+  explicit IterativeRayCasterLidar(PlannerI& planner) : CameraModel(planner) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+  bool checkParamsValid(std::string* error_message) override;
+
+ protected:
+  int casterKind() const override;
+  static ModuleFactoryRegistry::Registration<IterativeRayCasterLidar> registration;
 };
 
 }  // namespace sensor_model

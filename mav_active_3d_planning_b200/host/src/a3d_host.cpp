@@ -263,7 +263,8 @@ namespace sensor_model {
 CameraModel::CameraModel(PlannerI& planner)
     : SensorModel(planner), gpu_map_(nullptr), caster_(nullptr), caster_camera_(nullptr),
       p_ray_length_(5.0), p_sampling_time_(0.0), p_focal_length_(320.0), p_ray_step_(0.0),
-      p_downsampling_factor_(1.0), p_resolution_x_(640), p_resolution_y_(480), p_test_(false),
+      p_downsampling_factor_(1.0), p_fov_x_deg_(360.0), p_fov_y_deg_(30.0), p_resolution_x_(640),
+      p_resolution_y_(480), p_test_(false),
       c_field_of_view_x_(0.0), c_field_of_view_y_(0.0) {}
 
 CameraModel::~CameraModel() {
@@ -317,6 +318,8 @@ void CameraModel::buildCasters(Module::ParamMap* param_map) {
     return;  // reported by checkParamsValid
   a3d_caster_params p{};
   p.kind = casterKind();
+  p.field_of_view_x = p_fov_x_deg_;
+  p.field_of_view_y = p_fov_y_deg_;
   p.resolution_x = p_resolution_x_;
   p.resolution_y = p_resolution_y_;
   p.ray_length = p_ray_length_;
@@ -456,6 +459,34 @@ void IterativeRayCaster::setupFromParamMap(Module::ParamMap* param_map) {
   buildCasters(param_map);
 }
 int IterativeRayCaster::casterKind() const { return A3D_CASTER_ITERATIVE; }
+
+ModuleFactoryRegistry::Registration<IterativeRayCasterLidar> IterativeRayCasterLidar::registration(
+    "IterativeRayCasterLidar");
+void IterativeRayCasterLidar::setupFromParamMap(Module::ParamMap* param_map) {  // lidar_model.cpp:167-178
+  SensorModel::setupFromParamMap(param_map);
+  setParam<double>(param_map, "ray_length", &p_ray_length_, 5.0);
+  setParam<double>(param_map, "sampling_time", &p_sampling_time_, 0.0);
+  setParam<double>(param_map, "field_of_view_x", &p_fov_x_deg_, 360.0);
+  setParam<double>(param_map, "field_of_view_y", &p_fov_y_deg_, 30.0);
+  setParam<int>(param_map, "resolution_x", &p_resolution_x_, 1024);
+  setParam<int>(param_map, "resolution_y", &p_resolution_y_, 128);
+  setParam<bool>(param_map, "test", &p_test_, false);
+  c_field_of_view_x_ = p_fov_x_deg_ * M_PI / 180.0;
+  c_field_of_view_y_ = p_fov_y_deg_ * M_PI / 180.0;
+  p_focal_length_ = 1.0;  // unused by the lidar model
+  buildCasters(param_map);
+}
+bool IterativeRayCasterLidar::checkParamsValid(std::string* error_message) {  // lidar_model.cpp:180-198
+  if (p_fov_x_deg_ <= 0.0) {
+    *error_message = "field_of_view_x expected > 0.0";
+    return false;
+  } else if (p_fov_y_deg_ <= 0.0) {
+    *error_message = "field_of_view_y expected > 0.0";
+    return false;
+  }
+  return CameraModel::checkParamsValid(error_message);
+}
+int IterativeRayCasterLidar::casterKind() const { return A3D_CASTER_ITERATIVE_LIDAR; }
 
 }  // namespace sensor_model
 

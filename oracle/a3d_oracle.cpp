@@ -259,8 +259,13 @@ struct orc_caster {
   std::vector<double> c_split_distances;
   std::vector<int> c_split_widths;
 
-  // camera_model.cpp:161-168
+  // camera_model.cpp:161-168; lidar_model.cpp:159-165 for the lidar caster
   V3 directionVector(double relative_x, double relative_y) const {
+    if (p.kind == ORC_CASTER_ITERATIVE_LIDAR) {
+      const double phi = (0.5 - relative_x) * fov_x;
+      const double theta = M_PI / 2.0 + (relative_y - 0.5) * fov_y;
+      return V3{std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta)};
+    }
     const V3 v{p.focal_length, (0.5 - relative_x) * static_cast<double>(p.resolution_x),
                (0.5 - relative_y) * static_cast<double>(p.resolution_y)};
     const double n = std::sqrt((v.x * v.x + v.y * v.y) + v.z * v.z);  // Eigen normalized()
@@ -347,7 +352,7 @@ struct orc_caster {
       orientation = qmul(orientation, mq);
       if (p.kind == ORC_CASTER_SIMPLE)
         simpleVisible(result, position, orientation, n_samples);
-      else
+      else  // IterativeRayCaster and IterativeRayCasterLidar share the loop (only directions differ)
         iterativeVisible(result, position, orientation, n_samples);
     }
     result->erase(std::unique(result->begin(), result->end()), result->end());
@@ -584,6 +589,12 @@ orc_caster* orc_caster_create(const orc_map* m, const orc_caster_params* p) {
   // camera_model.cpp:181-182
   c->fov_x = 2.0 * std::atan2(static_cast<double>(p->resolution_x), p->focal_length * 2.0);
   c->fov_y = 2.0 * std::atan2(static_cast<double>(p->resolution_y), p->focal_length * 2.0);
+  if (p->kind == ORC_CASTER_ITERATIVE_LIDAR) {  // lidar_model.cpp:170-177
+    c->fov_x = p->field_of_view_x;
+    c->fov_y = p->field_of_view_y;
+    c->fov_x *= M_PI / 180.0;
+    c->fov_y *= M_PI / 180.0;
+  }
   const double vs = m->c_voxel_size;
   c->ray_step = p->ray_step > 0.0 ? p->ray_step : vs;  // simple_ray_caster.cpp:17
   // simple_ray_caster.cpp:22-29 / iterative_ray_caster.cpp:25-32
@@ -594,8 +605,8 @@ orc_caster* orc_caster_create(const orc_map* m, const orc_caster_params* p) {
       static_cast<int>(std::ceil(p->ray_length * c->fov_y / (vs * p->downsampling_factor))),
       p->resolution_y);
   c->c_n_sections = 0;
-  if (p->kind == ORC_CASTER_ITERATIVE) {
-    // iterative_ray_caster.cpp:35-45
+  if (p->kind != ORC_CASTER_SIMPLE) {
+    // iterative_ray_caster.cpp:35-45 == iterative_ray_caster_lidar.cpp:35-45
     c->c_n_sections = static_cast<int>(std::floor(std::log2(
         std::min(static_cast<double>(c->c_res_x), static_cast<double>(c->c_res_y)))));
     c->c_split_widths.push_back(0);

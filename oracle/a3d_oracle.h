@@ -25,7 +25,7 @@ typedef struct orc_map orc_map;
 typedef struct orc_caster orc_caster;
 
 enum { ORC_OCCUPIED = 0, ORC_FREE = 1, ORC_UNKNOWN = 2 }; /* occupancy_map.h:17-19 */
-enum { ORC_CASTER_SIMPLE = 0, ORC_CASTER_ITERATIVE = 1 };
+enum { ORC_CASTER_SIMPLE = 0, ORC_CASTER_ITERATIVE = 1, ORC_CASTER_ITERATIVE_LIDAR = 2 };
 enum { ORC_EVAL_VOXEL_TYPE = 0, ORC_EVAL_NAIVE = 1, ORC_EVAL_FRONTIER = 2, ORC_EVAL_VOXEL_WEIGHT = 3 };
 
 typedef struct {
@@ -39,6 +39,8 @@ typedef struct {
   double downsampling_factor;  /* simple_ray_caster.cpp:18 */
   double mount_t[3];           /* sensor_model.cpp:18-20 */
   double mount_q[4];           /* w,x,y,z, already normalised (sensor_model.cpp:21-27) */
+  double field_of_view_x;      /* lidar only, degrees (lidar_model.cpp:170-171) */
+  double field_of_view_y;
 } orc_caster_params;
 
 typedef struct {

@@ -20,7 +20,8 @@ class CasterParams(C.Structure):
     _fields_ = [("kind", C.c_int32), ("resolution_x", C.c_int32), ("resolution_y", C.c_int32),
                 ("_pad", C.c_int32), ("ray_length", C.c_double), ("focal_length", C.c_double),
                 ("ray_step", C.c_double), ("downsampling_factor", C.c_double),
-                ("mount_t", C.c_double * 3), ("mount_q", C.c_double * 4)]
+                ("mount_t", C.c_double * 3), ("mount_q", C.c_double * 4),
+                ("field_of_view_x", C.c_double), ("field_of_view_y", C.c_double)]
 
 
 class EvalParams(C.Structure):
@@ -34,7 +35,7 @@ class EvalParams(C.Structure):
                 ("ray_angle_y", C.c_double)]
 
 
-_CASTER_KINDS = {"SimpleRayCaster": 0, "IterativeRayCaster": 1}
+_CASTER_KINDS = {"SimpleRayCaster": 0, "IterativeRayCaster": 1, "IterativeRayCasterLidar": 2}
 _EVAL_KINDS = {"VoxelTypeEvaluator": 0, "NaiveEvaluator": 1, "FrontierEvaluator": 2,
                "VoxelWeightEvaluator": 3}
 
@@ -112,10 +113,11 @@ def _pts(p):
 
 def caster_params(kind, *, ray_length=5.0, focal_length=320.0, resolution_x=640, resolution_y=480,
                   ray_step=0.0, downsampling_factor=1.0, mounting_translation=(0.0, 0.0, 0.0),
-                  mounting_rotation=(1.0, 0.0, 0.0, 0.0)):
+                  mounting_rotation=(1.0, 0.0, 0.0, 0.0), field_of_view_x=360.0, field_of_view_y=30.0):
     if isinstance(kind, str):
         kind = _CASTER_KINDS[kind]
     p = CasterParams()
+    p.field_of_view_x, p.field_of_view_y = float(field_of_view_x), float(field_of_view_y)
     p.kind = kind
     p.resolution_x, p.resolution_y = int(resolution_x), int(resolution_y)
     p.ray_length, p.focal_length = float(ray_length), float(focal_length)

@@ -21,7 +21,7 @@ def test_param_struct_layouts_match_header(built):
     # sizes implied by include/a3d.h (all fields 4- or 8-byte, no implicit padding)
     import ctypes as C
     from mav_active_3d_planning_b200 import capi
-    assert C.sizeof(capi.CasterParams) == 4 * 4 + 8 * 4 + 8 * 3 + 8 * 4
+    assert C.sizeof(capi.CasterParams) == 4 * 4 + 8 * 4 + 8 * 3 + 8 * 4 + 8 * 2
     assert C.sizeof(capi.EvalParams) == 4 * 4 + 8 + 8 * 6 + 4 * 2 + 8 * 3 + 8 * 3 + 8 * 4 + 8 * 5
     assert C.sizeof(capi.CasterInfo) == 4 * 4 + 8 * 3 + 8 * 33 + 4 * 33 + 4
 

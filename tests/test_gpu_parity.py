@@ -499,3 +499,29 @@ def test_voxel_weight_evaluator(capi, O, room02, ckind):
         og2, oleft = om.gain_from_voxels(oe, lst, origin=org[0])
         assert np.isclose(g2, og2, rtol=GAIN_RTOL) and left == oleft == len(lst)
     ctx.close()
+
+
+def test_iterative_ray_caster_lidar(capi, O, room02):
+    """IterativeRayCasterLidar (iterative_ray_caster_lidar.cpp, lidar_model.cpp:159-165; SURVEY.md
+    §8(f)-4): the iterative scheme over the spherical direction table."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    lid = dict(ray_length=5.0, field_of_view_x=360.0, field_of_view_y=30.0, resolution_x=1024,
+               resolution_y=128, downsampling_factor=2.0)
+    caster = ctx.caster("IterativeRayCasterLidar", **lid)
+    oc = om.caster("IterativeRayCasterLidar", **lid)
+    assert (caster.info.c_res_x, caster.info.c_res_y, caster.info.c_n_sections) == (
+        oc.c_res_x, oc.c_res_y, oc.c_n_sections)
+    for i, j in [(0, 0), (5, 3), (oc.c_res_x - 1, oc.c_res_y - 1)]:
+        assert np.array_equal(caster.direction(i, j), oc.direction(i, j))
+    pos, quat = synth.candidate_views(room02, 12, seed=61)
+    lst, ns, _ = ctx.visible_voxels(caster, pos[:1], quat[:1])
+    olst, ons = oc.visible_voxels(pos[:1], quat[:1])
+    assert ns == ons and np.array_equal(lst, olst)
+    ev = ctx.evaluator("VoxelTypeEvaluator")
+    want = oc.compute_gains(O.eval_params("VoxelTypeEvaluator"), pos, quat, n_threads=8)
+    got = ctx.compute_gains(caster, ev, pos, quat)
+    for k in ("n_samples", "n_visible", "digest", "gain"):
+        assert np.array_equal(got[k], want[k]), k
+    _check_wave(_wave(ctx, caster, ev, pos, quat), want)
+    ctx.close()
