@@ -56,6 +56,7 @@ extern "C" {
 typedef struct a3d_ctx a3d_ctx;
 typedef struct a3d_caster a3d_caster;
 typedef struct a3d_eval a3d_eval;
+typedef struct a3d_store a3d_store;
 
 /* Parameters of a CameraModel subclass exactly as setupFromParamMap parses them
    (core/src/module/sensor_model/sensor_model.cpp:9-27, camera_model.cpp:170-183,
@@ -225,6 +226,35 @@ int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* e
 int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* centres,
                          double* gain_out, int64_t* n_left_out, uint8_t* keep_out,
                          const double* origin /* 3 doubles, VoxelWeightEvaluator only, else nullable */);
+
+/* ---- device-resident stored lists -------------------------------------------
+ * The reference keeps each segment's voxel list in TrajectorySegment::info (SimulatedSensorInfo,
+ * simulated_sensor_evaluator.h:54-58) so that SimulatedSensorUpdater can re-fold the gain after the
+ * map changed without casting rays again (evaluator_updater/simulated_sensor_updater.cpp:18-22).  A
+ * store keeps those lists in HBM, keyed by a caller-chosen 64-bit id (e.g. the segment's address). */
+int a3d_store_create(a3d_ctx* ctx, a3d_store** out);
+void a3d_store_destroy(a3d_store* store);
+/* a3d_compute_gains + keep every segment's stored list under seg_keys[s] (replacing older lists of
+ * the same key).  Two passes: gains/sizes (wavefront kernel), then the scan-order kernel writes the
+ * ordered lists into an exactly sized device arena. */
+int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
+                             a3d_store* store, int n_views, const double* pos, const double* quat,
+                             const int32_t* view_segment, int n_segments, const uint64_t* seg_keys,
+                             double* gains_out, uint64_t* n_visible_out, const double* seg_origin);
+/* computeGainFromVisibleVoxels for n stored lists against the CURRENT map, one launch.  Naive and
+ * Frontier evaluators also erase the observed entries from the stored lists, like the reference.
+ * n_left_out (nullable): list sizes afterwards.  Unknown key → A3D_ERR_INVALID. */
+int a3d_store_refold(a3d_ctx* ctx, const a3d_eval* eval, a3d_store* store, int n,
+                     const uint64_t* seg_keys, double* gains_out, uint64_t* n_left_out,
+                     const double* seg_origin);
+int a3d_store_erase(a3d_store* store, int n, const uint64_t* seg_keys);
+/* number of entries stored under key, -1 if absent */
+int64_t a3d_store_list_size(const a3d_store* store, uint64_t key);
+/* copy a stored list back (cap×3 doubles); *n_out = its length */
+int a3d_store_get(a3d_ctx* ctx, const a3d_store* store, uint64_t key, double* centres_out, int64_t cap,
+                  int64_t* n_out);
+/* bytes of HBM currently held by the store */
+int64_t a3d_store_bytes(const a3d_store* store);
 
 /* clear_from_parents step of SimulatedSensorEvaluator::computeGain
  * (simulated_sensor_evaluator.cpp:60-76) for ONE ancestor: keep_inout[i] is cleared if centres[i]

@@ -36,7 +36,9 @@ EXPORTS = [
     "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
     "a3d_map_distance", "a3d_map_traversable", "a3d_caster_create", "a3d_caster_destroy", "a3d_caster_get_info",
     "a3d_caster_direction", "a3d_eval_create", "a3d_eval_destroy", "a3d_compute_gains",
-    "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_filter_not_in", "a3d_bv_contains",
+    "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_filter_not_in",
+    "a3d_bv_contains", "a3d_store_create", "a3d_store_destroy", "a3d_compute_gains_stored",
+    "a3d_store_refold", "a3d_store_erase", "a3d_store_list_size", "a3d_store_get", "a3d_store_bytes",
 ]
 
 
@@ -175,6 +177,17 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_gain_from_voxels.argtypes = [vp, vp, i64, vp, P(dbl), P(i64), vp, vp]
     lib.a3d_bv_contains.argtypes = [vp, vp, i64, vp, vp]
     lib.a3d_filter_not_in.argtypes = [vp, i64, vp, i64, vp, vp]
+    lib.a3d_store_create.argtypes = [vp, P(vp)]
+    lib.a3d_store_destroy.argtypes = [vp]
+    lib.a3d_store_destroy.restype = None
+    lib.a3d_compute_gains_stored.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.a3d_store_refold.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.a3d_store_erase.argtypes = [vp, C.c_int, vp]
+    lib.a3d_store_list_size.argtypes = [vp, u64]
+    lib.a3d_store_list_size.restype = i64
+    lib.a3d_store_get.argtypes = [vp, vp, u64, vp, i64, P(i64)]
+    lib.a3d_store_bytes.argtypes = [vp]
+    lib.a3d_store_bytes.restype = i64
     _lib = lib
     return lib
 
@@ -411,6 +424,73 @@ class Context:
         out = np.empty(len(pts), np.uint8)
         self._ck(self.lib.a3d_bv_contains(self.h, evaluator.h, len(pts), _ptr(pts), _ptr(out)))
         return out
+
+
+class Store:
+    """Device-resident stored voxel lists (the SimulatedSensorInfo lists kept in HBM)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._ck(ctx.lib.a3d_store_create(ctx.h, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.a3d_store_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute_gains(self, caster, evaluator, keys, pos, quat, view_segment=None, seg_origin=None):
+        pos = _pts(pos)
+        quat = np.ascontiguousarray(quat, np.float64)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        n_seg = len(keys)
+        if view_segment is None:
+            view_segment = np.arange(len(pos), dtype=np.int32)
+        view_segment = np.ascontiguousarray(view_segment, np.int32)
+        gains = np.zeros(n_seg, np.float64)
+        nvis = np.zeros(n_seg, np.uint64)
+        org = None if seg_origin is None else np.ascontiguousarray(seg_origin, np.float64)
+        self.ctx._ck(self.ctx.lib.a3d_compute_gains_stored(
+            self.ctx.h, caster.h, evaluator.h, self.h, len(pos), _ptr(pos), _ptr(quat),
+            _ptr(view_segment), n_seg, _ptr(keys), _ptr(gains), _ptr(nvis), _ptr(org)))
+        return dict(gain=gains, n_visible=nvis)
+
+    def refold(self, evaluator, keys, seg_origin=None):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        gains = np.zeros(len(keys), np.float64)
+        left = np.zeros(len(keys), np.uint64)
+        org = None if seg_origin is None else np.ascontiguousarray(seg_origin, np.float64)
+        self.ctx._ck(self.ctx.lib.a3d_store_refold(self.ctx.h, evaluator.h, self.h, len(keys),
+                                                   _ptr(keys), _ptr(gains), _ptr(left), _ptr(org)))
+        return gains, left
+
+    def erase(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        self.ctx._ck(self.ctx.lib.a3d_store_erase(self.h, len(keys), _ptr(keys)))
+
+    def list_size(self, key) -> int:
+        return int(self.ctx.lib.a3d_store_list_size(self.h, int(key)))
+
+    def get(self, key):
+        n = self.list_size(key)
+        if n < 0:
+            raise KeyError(key)
+        out = np.empty((max(n, 1), 3), np.float64)
+        n_out = C.c_int64()
+        self.ctx._ck(self.ctx.lib.a3d_store_get(self.ctx.h, self.h, int(key), _ptr(out), max(n, 1),
+                                                C.byref(n_out)))
+        return out[:n].copy()
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.ctx.lib.a3d_store_bytes(self.h))
 
 
 class Caster:

@@ -164,6 +164,36 @@ struct a3d_eval {
   EvalView view{};
 };
 
+// Device-resident stored lists: every a3d_compute_gains_stored call owns one arena; a key maps to a
+// slice of an arena; an arena is freed when its last key is replaced or erased.
+struct StoreArena {
+  double* p = nullptr;
+  size_t entries = 0;
+  int live = 0;
+};
+struct StoreEntry {
+  int arena;
+  long long offset, count;
+};
+struct a3d_store {
+  a3d_ctx* ctx;
+  std::vector<StoreArena> arenas;
+  std::unordered_map<uint64_t, StoreEntry> lists;
+  DevBuf<long long> d_off, d_cnt;
+  DevBuf<double> d_gain, d_origin;
+  void drop(uint64_t key) {
+    auto it = lists.find(key);
+    if (it == lists.end()) return;
+    StoreArena& a = arenas[it->second.arena];
+    if (--a.live == 0 && a.p) {
+      cudaFree(a.p);
+      a.p = nullptr;
+      a.entries = 0;
+    }
+    lists.erase(it);
+  }
+};
+
 #define CK(call)                                          \
   do {                                                    \
     cudaError_t _e = (call);                              \
@@ -1199,6 +1229,191 @@ int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const do
     *gain_out = static_cast<double>(cnt[0]);
   }
   if (n_left_out) *n_left_out = static_cast<int64_t>(cnt[6]);
+  return A3D_OK;
+}
+
+int a3d_store_create(a3d_ctx* ctx, a3d_store** out) {
+  if (!ctx || !out) return A3D_ERR_INVALID;
+  *out = new a3d_store();
+  (*out)->ctx = ctx;
+  return A3D_OK;
+}
+void a3d_store_destroy(a3d_store* store) {
+  if (!store) return;
+  cudaSetDevice(store->ctx->device);
+  cudaStreamSynchronize(store->ctx->stream);
+  for (auto& a : store->arenas)
+    if (a.p) cudaFree(a.p);
+  store->d_off.release();
+  store->d_cnt.release();
+  store->d_gain.release();
+  store->d_origin.release();
+  delete store;
+}
+int a3d_store_erase(a3d_store* store, int n, const uint64_t* seg_keys) {
+  if (!store || n < 0 || (n > 0 && !seg_keys)) return A3D_ERR_INVALID;
+  cudaSetDevice(store->ctx->device);
+  cudaStreamSynchronize(store->ctx->stream);
+  for (int i = 0; i < n; ++i) store->drop(seg_keys[i]);
+  return A3D_OK;
+}
+int64_t a3d_store_list_size(const a3d_store* store, uint64_t key) {
+  if (!store) return -1;
+  auto it = store->lists.find(key);
+  return it == store->lists.end() ? -1 : it->second.count;
+}
+int64_t a3d_store_bytes(const a3d_store* store) {
+  int64_t b = 0;
+  if (store)
+    for (const auto& a : store->arenas) b += static_cast<int64_t>(a.entries) * 24;
+  return b;
+}
+int a3d_store_get(a3d_ctx* ctx, const a3d_store* store, uint64_t key, double* centres_out, int64_t cap,
+                  int64_t* n_out) {
+  if (!ctx || !store || store->ctx != ctx || !n_out || cap < 0 || (cap > 0 && !centres_out))
+    return ctx ? ctx->fail(A3D_ERR_INVALID, "bad argument") : A3D_ERR_INVALID;
+  auto it = store->lists.find(key);
+  if (it == store->lists.end()) return ctx->fail(A3D_ERR_INVALID, "key not in store");
+  *n_out = it->second.count;
+  const int64_t n = std::min<int64_t>(cap, it->second.count);
+  CK(cudaSetDevice(ctx->device));
+  if (n > 0) {
+    CK(cudaMemcpyAsync(centres_out, store->arenas[it->second.arena].p + 3 * it->second.offset,
+                       24 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return it->second.count > cap ? ctx->fail(A3D_ERR_CAPACITY, "centres_out too small") : A3D_OK;
+}
+
+int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
+                             a3d_store* store, int n_views, const double* pos, const double* quat,
+                             const int32_t* view_segment, int n_segments, const uint64_t* seg_keys,
+                             double* gains_out, uint64_t* n_visible_out, const double* seg_origin) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!store || store->ctx != ctx || (n_segments > 0 && !seg_keys))
+    return ctx->fail(A3D_ERR_INVALID, "store/keys missing");
+  // pass 1: gains and list sizes
+  std::vector<uint64_t> nvis(static_cast<size_t>(std::max(n_segments, 0)));
+  int rc = a3d_compute_gains(ctx, caster, eval, n_views, pos, quat, view_segment, n_segments, gains_out,
+                             nvis.data(), nullptr, nullptr, nullptr, seg_origin);
+  if (rc) return rc;
+  if (n_segments == 0) return A3D_OK;
+  std::vector<long long> off(static_cast<size_t>(n_segments) + 1, 0);
+  for (int s = 0; s < n_segments; ++s) off[s + 1] = off[s] + static_cast<long long>(nvis[s]);
+  const size_t total = static_cast<size_t>(off[n_segments]);
+  // pass 2: ordered lists into one exactly sized arena (inputs are still in the context scratch)
+  StoreArena arena;
+  arena.entries = total;
+  CK(cudaMalloc(&arena.p, std::max<size_t>(total, 1) * 24));
+  CK(store->d_off.reserve(off.size()));
+  CK(cudaMemcpyAsync(store->d_off.p, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  {
+    Batch b{};
+    b.pos = ctx->sc_pos.p;
+    b.quat = ctx->sc_quat.p;
+    b.view_first = ctx->sc_first.p;
+    b.n_segments = n_segments;
+    b.gains = ctx->sc_gains.p;
+    b.n_visible = ctx->sc_nvis.p;
+    b.n_samples = ctx->sc_nsamp.p;
+    b.centres_out = arena.p;
+    b.emit_offset = store->d_off.p;
+    b.seg_origin = seg_origin ? ctx->sc_origin.p : nullptr;
+    const int block = cast_gain_block_threads();
+    int grid = std::max(1, std::min(n_segments, ctx->sm_count * 32));
+    if (caster->view.kind == A3D_CASTER_ITERATIVE) {
+      b.table_stride = (static_cast<size_t>(caster->view.n_rays) + 15) / 16 * 16;
+      CK(ctx->sc_tables.reserve(b.table_stride * grid));
+      b.tables = ctx->sc_tables.p;
+    }
+    CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+    b.work_counter = ctx->sc_counter.p;
+    launch_cast_gain(ctx->stream, ctx->view(), caster->view, &eval->view, b, false, true, grid, block);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  const int arena_id = static_cast<int>(store->arenas.size());
+  store->arenas.push_back(arena);
+  for (int s = 0; s < n_segments; ++s) {
+    store->drop(seg_keys[s]);
+    store->lists[seg_keys[s]] = StoreEntry{arena_id, off[s], static_cast<long long>(nvis[s])};
+    store->arenas[arena_id].live++;
+  }
+  if (store->arenas[arena_id].live == 0) {
+    cudaFree(store->arenas[arena_id].p);
+    store->arenas[arena_id].p = nullptr;
+    store->arenas[arena_id].entries = 0;
+  }
+  if (n_visible_out) std::copy(nvis.begin(), nvis.end(), n_visible_out);
+  return A3D_OK;
+}
+
+int a3d_store_refold(a3d_ctx* ctx, const a3d_eval* eval, a3d_store* store, int n,
+                     const uint64_t* seg_keys, double* gains_out, uint64_t* n_left_out,
+                     const double* seg_origin) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!store || store->ctx != ctx || !eval || eval->ctx != ctx || n < 0 ||
+      (n > 0 && (!seg_keys || !gains_out)))
+    return ctx->fail(A3D_ERR_INVALID, "bad argument");
+  if (eval->p.kind == A3D_EVAL_VOXEL_WEIGHT && !seg_origin)
+    return ctx->fail(A3D_ERR_INVALID, "VoxelWeightEvaluator needs the segment origins");
+  if (n == 0) return A3D_OK;
+  CK(cudaSetDevice(ctx->device));
+  // group the requested lists by arena (one launch per arena; typically one)
+  std::vector<int> order(n);
+  std::vector<const StoreEntry*> ent(n);
+  for (int i = 0; i < n; ++i) {
+    auto it = store->lists.find(seg_keys[i]);
+    if (it == store->lists.end()) return ctx->fail(A3D_ERR_INVALID, "key not in store");
+    ent[i] = &it->second;
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ent[a]->arena < ent[b]->arena; });
+  std::vector<long long> off(n), cnt(n);
+  std::vector<double> org(seg_origin ? 3 * static_cast<size_t>(n) : 0), gains(n);
+  for (int k = 0; k < n; ++k) {
+    off[k] = ent[order[k]]->offset;
+    cnt[k] = ent[order[k]]->count;
+    if (seg_origin)
+      for (int c = 0; c < 3; ++c) org[3 * k + c] = seg_origin[3 * order[k] + c];
+  }
+  CK(store->d_off.reserve(n));
+  CK(store->d_cnt.reserve(n));
+  CK(store->d_gain.reserve(n));
+  CK(cudaMemcpyAsync(store->d_off.p, off.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(store->d_cnt.p, cnt.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  if (seg_origin) {
+    CK(store->d_origin.reserve(org.size()));
+    CK(cudaMemcpyAsync(store->d_origin.p, org.data(), org.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (ctx->h_table.empty()) {
+    table_rebuild(ctx, 0);
+    int rc = table_upload(ctx);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int k0 = 0; k0 < n;) {
+    int k1 = k0;
+    while (k1 < n && ent[order[k1]]->arena == ent[order[k0]]->arena) ++k1;
+    launch_refold(ctx->stream, ctx->view(), eval->view, k1 - k0, store->arenas[ent[order[k0]]->arena].p,
+                  store->d_off.p + k0, store->d_cnt.p + k0, seg_origin ? store->d_origin.p + 3 * k0 : nullptr,
+                  store->d_gain.p + k0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    k0 = k1;
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  CK(cudaMemcpyAsync(gains.data(), store->d_gain.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(cnt.data(), store->d_cnt.p, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < n; ++k) {
+    gains_out[order[k]] = gains[k];
+    store->lists[seg_keys[order[k]]].count = cnt[k];
+    if (n_left_out) n_left_out[order[k]] = static_cast<uint64_t>(cnt[k]);
+  }
   return A3D_OK;
 }
 

@@ -301,6 +301,8 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
     // per-lane counters: VoxelType → [state + 3*outside]; Naive/Frontier → [0]
     unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long n_vis = 0, n_samp = 0, digest = 0, set_digest = 0;
+    const long long emit_base = (EMIT && b.emit_offset) ? b.emit_offset[seg] : 0;
+    const long long emit_cap = (EMIT && b.emit_offset) ? b.emit_offset[seg + 1] - emit_base : b.cap;
     double wsum = 0.0;  // VoxelWeightEvaluator: per-lane partial gain
     D3 seg_org{0.0, 0.0, 0.0};
     if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
@@ -411,10 +413,11 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
             const int rank = __popc(km & lt_mask);
             if (EMIT) {
               const long long idx = static_cast<long long>(n_vis) + rank;
-              if (keep && idx < b.cap) {
-                b.centres_out[3 * idx] = cc.x;
-                b.centres_out[3 * idx + 1] = cc.y;
-                b.centres_out[3 * idx + 2] = cc.z;
+              if (keep && idx < emit_cap) {
+                double* dst = b.centres_out + 3 * (emit_base + idx);
+                dst[0] = cc.x;
+                dst[1] = cc.y;
+                dst[2] = cc.z;
               }
             }
             if (DIGEST) {
@@ -566,6 +569,106 @@ void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, co
 }
 
 int cast_gain_block_threads() { return kCastBlock; }
+
+// ---------------------------------------------------------------------------------------------
+// Re-fold of stored lists that live on the device (SimulatedSensorUpdater::updateSegment,
+// simulated_sensor_updater.cpp:18-22 → computeGainFromVisibleVoxels).  One CTA per list.  Naive and
+// Frontier erase the observed entries from the list like the reference does (naive_evaluator.cpp:28-35,
+// frontier_evaluator.cpp:110-116): stable in-place compaction, chunk by chunk.
+__global__ void __launch_bounds__(256)
+    k_refold(MapView m, EvalView e, int n, double* __restrict__ pool,
+             const long long* __restrict__ offsets, long long* __restrict__ counts,
+             const double* __restrict__ origins, double* __restrict__ gains_out) {
+  __shared__ CenterTables ct;
+  __shared__ unsigned s_warp[8];
+  __shared__ unsigned long long s_cnt[6];
+  __shared__ double s_w;
+  __shared__ long long s_base;
+  init_center_tables(m, &ct);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool erases = e.kind == A3D_EVAL_NAIVE || e.kind == A3D_EVAL_FRONTIER;
+  for (int li = blockIdx.x; li < n; li += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+      s_w = 0.0;
+      s_base = 0;
+    }
+    __syncthreads();
+    double* list = pool + 3 * offsets[li];
+    const long long cnt = counts[li];
+    const D3 origin = origins ? D3{origins[3 * li], origins[3 * li + 1], origins[3 * li + 2]}
+                              : D3{0.0, 0.0, 0.0};
+    unsigned c[6] = {0, 0, 0, 0, 0, 0};
+    double wsum = 0.0;
+    for (long long c0 = 0; c0 < cnt; c0 += blockDim.x) {
+      const long long i = c0 + threadIdx.x;
+      bool kp = false;
+      D3 v{0.0, 0.0, 0.0};
+      if (i < cnt) {
+        v = D3{list[3 * i], list[3 * i + 1], list[3 * i + 2]};
+        kp = true;
+        if (e.kind == A3D_EVAL_VOXEL_TYPE) {
+          c[voxel_state(m, ct, v) + (bv_contains(e, v) ? 0 : 3)]++;
+        } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
+          const int s = voxel_state(m, ct, v);
+          wsum += voxel_weight_value(m, ct, e, v, s, s == 0 ? voxel_weight(m, v) : 0.0, origin);
+        } else {
+          kp = !is_observed(m, v);
+          if (kp && (e.kind == A3D_EVAL_NAIVE || is_frontier_voxel(m, ct, e, v))) c[0]++;
+        }
+      }
+      if (erases) {
+        // stable compaction of this chunk to list[s_base ...)
+        const unsigned bal = __ballot_sync(kFull, kp);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();  // all reads of the chunk are done, warp counts visible
+        unsigned before = 0, total = 0;
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) {
+          before += w < warp ? s_warp[w] : 0;
+          total += s_warp[w];
+        }
+        const long long base = s_base;
+        if (kp) {
+          double* dst = list + 3 * (base + before + __popc(bal & ((1u << lane) - 1u)));
+          dst[0] = v.x;
+          dst[1] = v.y;
+          dst[2] = v.z;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + total;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const unsigned t = __reduce_add_sync(kFull, c[k]);
+      if (lane == 0 && t) atomicAdd(&s_cnt[k], static_cast<unsigned long long>(t));
+    }
+    if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(kFull, wsum, off);
+      if (lane == 0) atomicAdd(&s_w, wsum);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (e.kind == A3D_EVAL_VOXEL_TYPE) {
+        gains_out[li] = voxel_type_gain(e, s_cnt);
+      } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
+        gains_out[li] = s_w;
+      } else {
+        gains_out[li] = static_cast<double>(s_cnt[0]);
+        counts[li] = s_base;
+      }
+    }
+  }
+}
+
+void launch_refold(cudaStream_t st, const MapView& m, const EvalView& e, int n, double* pool,
+                   const long long* offsets, long long* counts, const double* origins,
+                   double* gains_out) {
+  if (n <= 0) return;
+  k_refold<<<std::min(n, 148 * 8), 256, 0, st>>>(m, e, n, pool, offsets, counts, origins, gains_out);
+}
 
 // ---------------------------------------------------------------------------------------------
 // clear_from_parents (simulated_sensor_evaluator.cpp:60-76): keep[i] = 0 if centre i occurs anywhere

@@ -43,8 +43,9 @@ struct Batch {
   unsigned long long* set_digests;  // order-independent digest (both kernels)
   const unsigned int* seg_mask;     // k_cast_gain: if set, only segments whose bit is 1 are evaluated
   const double* seg_origin;         // n_segments×3 or null (VoxelWeightEvaluator's origin)
-  double* centres_out;  // emit mode (single segment): cap×3
+  double* centres_out;  // emit mode: cap×3 (single segment) or the pool the offsets index
   long long cap;
+  const long long* emit_offset;  // emit mode, many segments: n_segments+1 entry offsets into centres_out
   int8_t* tables;       // per-warp ray tables (iterative), table_stride bytes each
   size_t table_stride;
   unsigned int* work_counter;
@@ -73,6 +74,10 @@ void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, co
 void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& e, long long n,
                              const double* centres, unsigned long long* counters /*8*/,
                              uint8_t* keep, D3 origin, double* gain_acc /*1, VoxelWeight*/);
+// re-fold of device-resident stored lists, one CTA per list (SimulatedSensorUpdater path)
+void launch_refold(cudaStream_t st, const MapView& m, const EvalView& e, int n, double* pool,
+                   const long long* offsets /*n*/, long long* counts /*n, in/out*/,
+                   const double* origins /*n×3 or null*/, double* gains_out /*n*/);
 void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long long m,
                           const double* other, uint8_t* keep);
 int cast_gain_block_threads();

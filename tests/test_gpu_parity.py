@@ -525,3 +525,53 @@ def test_iterative_ray_caster_lidar(capi, O, room02):
         assert np.array_equal(got[k], want[k]), k
     _check_wave(_wave(ctx, caster, ev, pos, quat), want)
     ctx.close()
+
+
+def test_device_resident_lists_and_refold(capi, O, room02):
+    """stored lists kept in HBM and re-folded after map deltas without re-casting
+    (SimulatedSensorUpdater, simulated_sensor_updater.cpp:18-22)."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    oc = om.caster("IterativeRayCaster", **CAM_BASE)
+    pos, quat = synth.candidate_views(room02, 12, seed=71)
+    keys = np.arange(1000, 1012, dtype=np.uint64)
+    rng = np.random.default_rng(9)
+    for ekind in ("VoxelTypeEvaluator", "NaiveEvaluator", "FrontierEvaluator"):
+        kw = dict(gain_free=0.5) if ekind[0] == "V" else {}
+        ev = ctx.evaluator(ekind, **kw)
+        oe = O.eval_params(ekind, **kw)
+        store = capi.Store(ctx)
+        got = store.compute_gains(caster, ev, keys, pos, quat)
+        want = oc.compute_gains(oe, pos, quat)
+        assert np.array_equal(got["n_visible"], want["n_visible"])
+        assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
+        lists = [store.get(k) for k in keys]
+        for s in range(12):
+            assert len(lists[s]) == want["n_visible"][s] and O.digest(lists[s]) == want["digest"][s]
+        assert store.nbytes == 24 * int(want["n_visible"].sum())
+        # two rounds of map deltas: more of the map becomes observed, distances move
+        for _ in range(2):
+            sel = rng.choice(room02.n_blocks, room02.n_blocks // 5, replace=False)
+            nd = (room02.dist[sel] + rng.normal(0, 0.05, room02.dist[sel].shape)).astype(np.float32)
+            no = np.maximum(room02.observed[sel], (rng.random(room02.observed[sel].shape) < 0.5)).astype(np.uint8)
+            ctx.upload_blocks(room02.block_idx[sel], nd, no)
+            om.upload_blocks(room02.block_idx[sel], nd, no)
+            gains, left = store.refold(ev, keys)
+            for s in range(12):
+                og, oleft = om.gain_from_voxels(oe, lists[s])
+                assert np.isclose(gains[s], og, rtol=GAIN_RTOL, atol=0) and left[s] == oleft
+                if ekind[0] != "V":   # the reference erases observed entries from the stored list
+                    lists[s] = lists[s][om.is_observed(lists[s]) == 0] if len(lists[s]) else lists[s]
+                    assert np.array_equal(store.get(keys[s]), lists[s])
+        # restore the map for the next evaluator, replace half of the keys, erase the rest
+        ctx.upload_blocks(room02.block_idx, room02.dist, room02.observed, room02.weight)
+        om.upload_blocks(room02.block_idx, room02.dist, room02.observed, room02.weight)
+        store.compute_gains(caster, ev, keys[:6], pos[:6], quat[:6])
+        store.erase(keys[6:])
+        assert store.list_size(keys[7]) == -1 and store.list_size(keys[0]) == want["n_visible"][0]
+        assert store.nbytes == 24 * int(want["n_visible"][:6].sum())
+        with pytest.raises(capi.A3DError):
+            store.refold(ev, keys[6:8])
+        store.close()
+    ctx.close()
