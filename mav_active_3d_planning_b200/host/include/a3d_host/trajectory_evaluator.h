@@ -17,6 +17,7 @@
 #include "a3d_host/sensor_model.h"
 
 struct a3d_eval;
+struct a3d_store;
 
 namespace active_3d_planning {
 
@@ -71,6 +72,22 @@ struct SimulatedSensorInfo : public TrajectoryInfo {
   std::vector<Eigen::Vector3d> visible_voxels;
 };
 
+// Handle of the evaluator's device-resident list store; segments only hold weak references, so
+// they may outlive the evaluator.
+struct DeviceListStore {
+  explicit DeviceListStore(a3d_store* s) : store(s) {}
+  ~DeviceListStore();
+  a3d_store* store;
+};
+// TrajectorySegment::info of a segment whose voxel list lives in HBM instead of
+// in SimulatedSensorInfo::visible_voxels.  Destroying the info releases the list.
+struct DeviceSensorInfo : public TrajectoryInfo {
+  ~DeviceSensorInfo() override;
+  uint64_t key = 0;
+  uint64_t n_voxels = 0;
+  std::weak_ptr<DeviceListStore> store;
+};
+
 class SimulatedSensorEvaluator : public TrajectoryEvaluator {
  public:
   explicit SimulatedSensorEvaluator(PlannerI& planner);  // NOLINT
@@ -81,8 +98,15 @@ class SimulatedSensorEvaluator : public TrajectoryEvaluator {
   // Batch: gains of many segments in one launch (no voxel lists are stored in the segments).
   // Returns false if clear_from_parents is set (needs the per-segment lists).
   virtual bool computeGains(const std::vector<TrajectorySegment*>& segments);
-  // fold of the list already stored in the segment (SimulatedSensorUpdater path)
+  // fold of the list already stored in the segment (SimulatedSensorUpdater path); works for
+  // host-side SimulatedSensorInfo lists and for DeviceSensorInfo
   virtual bool computeGainFromVisibleVoxels(TrajectorySegment* traj_in);
+  // Batch computeGain that keeps every segment's list on the device (info = DeviceSensorInfo) ...
+  virtual bool computeGainsStored(const std::vector<TrajectorySegment*>& segments);
+  // ... and the batch re-fold of such segments after the map changed: what UpdateAll /
+  // SimulatedSensorUpdater do segment by segment (update_all.cpp:16-27,
+  // simulated_sensor_updater.cpp:18-22), in one launch
+  virtual bool updateGains(const std::vector<TrajectorySegment*>& segments);
   SensorModel* sensorModel() { return sensor_model_.get(); }
 
  protected:
@@ -96,6 +120,8 @@ class SimulatedSensorEvaluator : public TrajectoryEvaluator {
   map::VoxbloxMap* gpu_map_;
   std::unique_ptr<SensorModel> sensor_model_;
   a3d_eval* eval_;
+  std::shared_ptr<DeviceListStore> device_lists_;
+  uint64_t next_key_ = 1;
   bool p_clear_from_parents_, p_visualize_sensor_view_;
 };
 

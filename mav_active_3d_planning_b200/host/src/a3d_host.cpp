@@ -536,8 +536,87 @@ SimulatedSensorEvaluator::SimulatedSensorEvaluator(PlannerI& planner)
     : TrajectoryEvaluator(planner), map_(nullptr), gpu_map_(nullptr), eval_(nullptr),
       p_clear_from_parents_(false), p_visualize_sensor_view_(false) {}
 
+DeviceListStore::~DeviceListStore() {
+  if (store) a3d_store_destroy(store);
+}
+DeviceSensorInfo::~DeviceSensorInfo() {
+  if (auto s = store.lock()) a3d_store_erase(s->store, 1, &key);
+}
+
 SimulatedSensorEvaluator::~SimulatedSensorEvaluator() {
+  device_lists_.reset();  // before the evaluator object; the map (context) outlives the evaluator
   if (eval_) a3d_eval_destroy(eval_);
+}
+
+bool SimulatedSensorEvaluator::computeGainsStored(const std::vector<TrajectorySegment*>& segments) {
+  auto* cam = dynamic_cast<sensor_model::CameraModel*>(sensor_model_.get());
+  if (!cam || !cam->handle() || !eval_ || p_clear_from_parents_) return false;
+  if (!device_lists_) {
+    a3d_store* st = nullptr;
+    if (a3d_store_create(gpu_map_->context(), &st) != A3D_OK) return false;
+    device_lists_ = std::make_shared<DeviceListStore>(st);
+  }
+  std::vector<double> pos, quat, origins(segments.size() * 3, 0.0);
+  std::vector<int32_t> view_segment;
+  std::vector<uint64_t> keys(segments.size()), n_vis(segments.size());
+  for (size_t s = 0; s < segments.size(); ++s) {
+    keys[s] = next_key_++;
+    if (segments[s]->trajectory.empty()) continue;
+    std::vector<int> indices;
+    cam->sampleViewpoints(&indices, *segments[s]);
+    gatherPoses(*segments[s], indices, &pos, &quat);
+    view_segment.insert(view_segment.end(), indices.size(), static_cast<int32_t>(s));
+    for (int k = 0; k < 3; ++k) origins[3 * s + k] = segments[s]->trajectory.back().position_W[k];
+  }
+  std::vector<double> gains(segments.size(), 0.0);
+  if (a3d_compute_gains_stored(gpu_map_->context(), cam->handle(), eval_, device_lists_->store,
+                               static_cast<int>(view_segment.size()), pos.data(), quat.data(),
+                               view_segment.data(), static_cast<int>(segments.size()), keys.data(),
+                               gains.data(), n_vis.data(), origins.data()) != A3D_OK) {
+    planner_.printError(std::string("a3d_compute_gains_stored: ") + a3d_last_error(gpu_map_->context()));
+    return false;
+  }
+  for (size_t s = 0; s < segments.size(); ++s) {
+    auto* info = new DeviceSensorInfo();
+    info->key = keys[s];
+    info->n_voxels = n_vis[s];
+    info->store = device_lists_;
+    segments[s]->info.reset(info);  // releases whatever list the segment held before
+    segments[s]->gain = gains[s];
+  }
+  return true;
+}
+
+bool SimulatedSensorEvaluator::updateGains(const std::vector<TrajectorySegment*>& segments) {
+  if (!eval_) return false;
+  std::vector<TrajectorySegment*> on_device;
+  std::vector<uint64_t> keys;
+  std::vector<double> origins;
+  bool ok = true;
+  for (TrajectorySegment* seg : segments) {
+    auto* dinfo = dynamic_cast<DeviceSensorInfo*>(seg->info.get());
+    if (dinfo && device_lists_ && dinfo->store.lock() == device_lists_) {
+      on_device.push_back(seg);
+      keys.push_back(dinfo->key);
+      for (int k = 0; k < 3; ++k)
+        origins.push_back(seg->trajectory.empty() ? 0.0 : seg->trajectory.back().position_W[k]);
+    } else {
+      ok = computeGainFromVisibleVoxels(seg) && ok;  // host-side list
+    }
+  }
+  if (on_device.empty()) return ok;
+  std::vector<double> gains(on_device.size());
+  std::vector<uint64_t> left(on_device.size());
+  if (a3d_store_refold(gpu_map_->context(), eval_, device_lists_->store, static_cast<int>(keys.size()),
+                       keys.data(), gains.data(), left.data(), origins.data()) != A3D_OK) {
+    planner_.printError(std::string("a3d_store_refold: ") + a3d_last_error(gpu_map_->context()));
+    return false;
+  }
+  for (size_t i = 0; i < on_device.size(); ++i) {
+    on_device[i]->gain = gains[i];
+    static_cast<DeviceSensorInfo*>(on_device[i]->info.get())->n_voxels = left[i];
+  }
+  return ok;
 }
 
 void SimulatedSensorEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
@@ -643,6 +722,7 @@ bool SimulatedSensorEvaluator::computeGainFromVisibleVoxels(TrajectorySegment* t
   // the fold runs on the device; Naive and Frontier also drop the observed entries from the list
   traj_in->gain = 0.0;
   if (!traj_in->info || !eval_) return false;
+  if (dynamic_cast<DeviceSensorInfo*>(traj_in->info.get())) return updateGains({traj_in});
   auto* info = dynamic_cast<SimulatedSensorInfo*>(traj_in->info.get());
   if (!info) return false;
   const size_t n = info->visible_voxels.size();

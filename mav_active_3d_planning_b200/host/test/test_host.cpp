@@ -180,6 +180,22 @@ int runGains(char** argv) {
   for (int s = 0; s < n_seg; ++s) single[s] = segments[s]->gain;
   const bool bok = eval->computeGains(segments);
   for (int s = 0; s < n_seg; ++s) out << "batch " << s << " " << bok << " " << segments[s]->gain << "\n";
+  // device-resident lists (batch) and their re-fold; then free them by dropping the infos
+  if (bok) {
+    std::vector<double> batch(n_seg);
+    for (int s = 0; s < n_seg; ++s) batch[s] = segments[s]->gain;
+    const bool sok = eval->computeGainsStored(segments);
+    for (int s = 0; s < n_seg; ++s) {
+      auto* di = dynamic_cast<trajectory_evaluator::DeviceSensorInfo*>(segments[s]->info.get());
+      out << "stored " << s << " " << sok << " " << (segments[s]->gain == batch[s]) << " "
+          << (di ? di->n_voxels : 0) << "\n";
+    }
+    const bool uok = eval->updateGains(segments);
+    for (int s = 0; s < n_seg; ++s) out << "update " << s << " " << uok << " " << segments[s]->gain << "\n";
+    eval->computeGainFromVisibleVoxels(segments[0]);  // single-segment updater path on a device list
+    out << "update_single 0 " << segments[0]->gain << "\n";
+    for (int s = 0; s < n_seg; ++s) segments[s]->info.reset();
+  }
   // map virtuals
   Eigen::Vector3d c;
   vmap->getVoxelCenter(&c, segments[0]->trajectory.back().position_W);

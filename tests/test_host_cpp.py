@@ -85,7 +85,7 @@ def write_inputs(tmp, m, pos, quat, pts_per_seg, dt_ns):
 
 
 def parse_out(path):
-    res = {"single": {}, "refold": {}, "batch": {}}
+    res = {"single": {}, "refold": {}, "batch": {}, "stored": {}, "update": {}}
     for line in open(path):
         t = line.split()
         if not t or t[0] == "#":
@@ -98,6 +98,12 @@ def parse_out(path):
             res["refold"][int(t[1])] = int(t[2])
         elif t[0] == "batch":
             res["batch"][int(t[1])] = (int(t[2]), float(t[3]))
+        elif t[0] == "stored":
+            res["stored"][int(t[1])] = (int(t[2]), int(t[3]), int(t[4]))
+        elif t[0] == "update":
+            res["update"][int(t[1])] = (int(t[2]), float(t[3]))
+        elif t[0] == "update_single":
+            res["update_single"] = float(t[2])
         elif t[0] == "sensor":
             res["sensor"] = (int(t[2]), int(t[3]))
         elif t[0] == "center":
@@ -130,6 +136,10 @@ def test_modules_from_yaml_match_oracle_naive_iterative(built, room02, tmp_path)
         assert n_list == int(want["gain"][s])
         assert r["refold"][s] == 1
         assert r["batch"][s] == (1, want["gain"][s])
+        # device-resident lists: same gains, list size before the fold's erasure, re-fold unchanged map
+        assert r["stored"][s] == (1, 1, int(want["n_visible"][s]))
+        assert r["update"][s] == (1, want["gain"][s])
+    assert r["update_single"] == want["gain"][0]
     lst, _ = oc.visible_voxels(pos[:1], quat[:1])
     assert r["sensor"] == (len(lst), O.digest(lst))
     assert r["center"] == list(om.voxel_center(pos[:1])[0])
