@@ -540,7 +540,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const unsigned int* seg_mask = nullptr;
   if (use_wave) {
-    int grid = std::max(1, std::min(n_segments, ctx->sm_count * 12));
+    int grid = std::max(1, std::min(n_segments, ctx->sm_count * cast_wave_blocks_per_sm()));
     size_t stride = 0;
     while (grid > 1 && wave_scratch_bytes(c->view.n_rays, grid, set_dig_dev != nullptr, &stride) >
                            (size_t(6) << 30))

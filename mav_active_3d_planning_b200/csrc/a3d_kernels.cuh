@@ -87,6 +87,7 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
                       const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact);
 int cast_wave_threads();
 int cast_wave_max_diag();
+int cast_wave_blocks_per_sm();
 
 enum { kQueryState = 0, kQueryCenter = 1, kQueryObserved = 2, kQueryWeight = 3, kQueryDistance = 4,
        kQueryStateGeneric = 5, kQueryTraversable = 6 };

@@ -38,7 +38,11 @@ namespace a3d {
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kWaveThreads = 64;
+#ifndef A3D_WAVE_WARPS
+#define A3D_WAVE_WARPS 2  // warps per CTA: warp 0 schedules (iterative caster), all cast leaf parts
+#endif
+constexpr int kWaveWarps = A3D_WAVE_WARPS;
+constexpr int kWaveThreads = 32 * kWaveWarps;
 constexpr uint64_t kNoKey = ~0ull;  // "no entry"
 constexpr uint64_t kKeyOverflow = 1ull << 63;
 constexpr int kKeyBits = 20, kKeyBias = 1 << 19;
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   __shared__ int s_seg;
   __shared__ volatile int s_done_diag;         // anti-diagonals whose table entries are final
   __shared__ unsigned s_unit_cursor;           // next leaf-supply unit
-  __shared__ unsigned s_pending[2][kPendCap];  // per-warp ring of ready rays waiting for a lane
+  __shared__ unsigned s_pending[kWaveWarps][kPendCap];  // per-warp ring of ready rays waiting for a lane
   // marking rays of the current diagonal (dynamic shared memory, sized by the longest diagonal):
   // their hit distance (< 0: none) and r << 8 | s
   extern __shared__ double s_dyn[];
@@ -739,5 +743,6 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
 
 int cast_wave_threads() { return kWaveThreads; }
 int cast_wave_max_diag() { return kMarkCap; }
+int cast_wave_blocks_per_sm() { return A3D_WAVE_MIN_BLOCKS; }
 
 }  // namespace a3d
