@@ -5,6 +5,7 @@
 // No CPU compute path exists here: every query and every gain goes through the kernels in
 // a3d_kernels.cu; a missing/unusable device is an error (A3D_ERR_CUDA).
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -91,6 +92,10 @@ struct a3d_ctx {
   int32_t dir_lo[3] = {0, 0, 0};
   uint32_t dir_n[3] = {0, 0, 0};
   bool dir_enabled = false;
+  uint32_t* d_vol = nullptr;   // dense meta volume over the directory's box (a3d_device.cuh)
+  size_t vol_words = 0;        // allocated size
+  bool vol_stale = true;       // box changed (or never built): rebuilt lazily by vol_ensure()
+  bool vol_on = false;         // d_vol holds the current map
   float* d_weight = nullptr;   // vps^3 floats per slot
   size_t slab_slots = 0;
   bool has_weight = false;
@@ -133,6 +138,17 @@ struct a3d_ctx {
     m.P = P;
     m.P3 = P3;
     m.brick_nx = (vps % 4 == 0) ? vps / 4 : 0;
+    m.vps_shift = -1;
+    for (int k = 0; k < 7; ++k)
+      if ((1 << k) == vps) m.vps_shift = k;
+    // 16 float roundings of magnitude <= vps+1 voxels plus voxblox's 1e-6 index epsilons (block
+    // epsilon counts vps times in voxel units); see ray_step() in a3d_wave.cu
+    m.fast_c0 = static_cast<float>((vps + 1) * (16.0 * 5.97e-8 + 1.1e-6));
+    m.vol = (vol_on && !vol_stale) ? d_vol : nullptr;
+    for (int k = 0; k < 3; ++k) {
+      m.vol_lo[k] = dir_lo[k] * vps;
+      m.vol_n[k] = dir_n[k] * static_cast<uint32_t>(vps);
+    }
     m.mask = static_cast<uint32_t>(h_table.size() - 1);
     m.vps = vps;
     m.nv = nv;
@@ -229,6 +245,7 @@ void dir_rebuild(a3d_ctx* ctx) {
   ctx->dir_enabled = false;
   if (ctx->slots.empty()) {
     ctx->h_dir.clear();
+    ctx->vol_stale = true;
     return;
   }
   int32_t lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
@@ -244,6 +261,7 @@ void dir_rebuild(a3d_ctx* ctx) {
     covered = lo[k] >= ctx->dir_lo[k] &&
               static_cast<int64_t>(hi[k]) < static_cast<int64_t>(ctx->dir_lo[k]) + ctx->dir_n[k];
   if (!covered) {
+    ctx->vol_stale = true;
     double total = 1.0;
     for (int k = 0; k < 3; ++k) {
       const int64_t ext = static_cast<int64_t>(hi[k]) - lo[k] + 1;
@@ -347,7 +365,8 @@ int refresh_blocks(a3d_ctx* ctx, const std::vector<int32_t>& affected) {
                      cudaMemcpyHostToDevice, ctx->stream));
   const MapView mv = ctx->view();
   launch_refresh_aprons(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_nbr.p, ctx->d_dist);
-  launch_build_meta(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword);
+  launch_build_meta(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword,
+                    mv.vol ? ctx->d_vol : nullptr);
   ctx->launches += 2;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
@@ -367,6 +386,54 @@ void collect_affected(a3d_ctx* ctx, int n, const int32_t* block_idx, std::vector
           seen[it->second] = 1;
           out->push_back(it->second);
         }
+}
+
+// Brings the dense meta volume in line with the map before a cast: a no-op unless the directory's box
+// changed since the last build (block updates inside the box are written by k_build_meta directly).
+int vol_ensure(a3d_ctx* ctx) {
+  if (!ctx->vol_stale) return A3D_OK;
+  ctx->vol_on = false;
+  const MapView m0 = ctx->view();
+  const double words = static_cast<double>(m0.vol_n[0]) * m0.vol_n[1] * m0.vol_n[2];
+  const double allocated = static_cast<double>(ctx->slots.size()) * ctx->nv;
+  const bool eligible = ctx->dir_enabled && m0.vps_shift >= 2 && !ctx->slots.empty() &&
+                        words < 2147483648.0 && words <= 64.0 * allocated + 16.0 * 1024 * 1024;
+  if (!eligible) {
+    ctx->vol_stale = false;
+    return A3D_OK;
+  }
+  const size_t n_words = static_cast<size_t>(words);
+  if (n_words > ctx->vol_words) {
+    if (ctx->d_vol) cudaFree(ctx->d_vol);
+    ctx->d_vol = nullptr;
+    ctx->vol_words = 0;
+    CK(cudaMalloc(&ctx->d_vol, n_words * sizeof(uint32_t)));
+    ctx->vol_words = n_words;
+  }
+  const int n = static_cast<int>(ctx->slots.size());
+  std::vector<int32_t> sl(n), idx(static_cast<size_t>(n) * 3);
+  int a = 0;
+  for (const auto& kv : ctx->slots) {
+    sl[a] = kv.second;
+    idx[3 * a] = kv.first.x;
+    idx[3 * a + 1] = kv.first.y;
+    idx[3 * a + 2] = kv.first.z;
+    ++a;
+  }
+  CK(ctx->st_aff_slots.reserve(n));
+  CK(ctx->st_aff_idx.reserve(idx.size()));
+  CK(cudaMemcpyAsync(ctx->st_aff_slots.p, sl.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaMemcpyAsync(ctx->st_aff_idx.p, idx.data(), idx.size() * sizeof(int32_t),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  launch_vol_fill(ctx->stream, m0, ctx->d_vol, 0, nullptr);
+  launch_vol_scatter(ctx->stream, m0, ctx->d_vol, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
+  ctx->vol_on = true;
+  ctx->vol_stale = false;
+  return A3D_OK;
 }
 
 // Shared by the host- and device-pointer upload entry points.
@@ -537,9 +604,15 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
                      "cast_kernel=2 (wavefront) cannot produce ordered lists/digests");
   const bool use_wave = wave_ok && ctx->opt_cast_kernel != 1;
   ctx->last_cast_kernel = use_wave ? 2 : 1;
+  if (use_wave) {
+    int rc = vol_ensure(ctx);
+    if (rc) return rc;
+  }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const unsigned int* seg_mask = nullptr;
   if (use_wave) {
+    // as many CTAs as can be resident (measured: trimming the grid so that every CTA gets the same
+    // number of segments is slower — throughput follows the number of resident warps)
     int grid = std::max(1, std::min(n_segments, ctx->sm_count * cast_wave_blocks_per_sm()));
     size_t stride = 0;
     while (grid > 1 && wave_scratch_bytes(c->view.n_rays, grid, set_dig_dev != nullptr, &stride) >
@@ -630,6 +703,11 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
   if (ctx->d_weight) cudaFree(ctx->d_weight);
   if (ctx->d_mword) cudaFree(ctx->d_mword);
   ctx->d_dir.release();
+  if (ctx->d_vol) cudaFree(ctx->d_vol);
+  ctx->d_vol = nullptr;
+  ctx->vol_words = 0;
+  ctx->vol_stale = true;
+  ctx->vol_on = false;
   ctx->d_table.release();
   ctx->st_aff_slots.release();
   ctx->st_aff_nbr.release();
@@ -719,6 +797,18 @@ int a3d_map_remove_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx) {
     table_rebuild(ctx, ctx->slots.size());
     int rc = table_upload(ctx);
     if (rc) return rc;
+    const MapView mv = ctx->view();
+    if (mv.vol) {
+      // removed blocks inside the (unchanged) box read "no block" again; blocks that were not
+      // allocated hold that value already
+      CK(ctx->st_aff_idx.reserve(static_cast<size_t>(n) * 3));
+      CK(cudaMemcpyAsync(ctx->st_aff_idx.p, block_idx, static_cast<size_t>(n) * 3 * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, ctx->stream));
+      launch_vol_fill(ctx->stream, mv, ctx->d_vol, n, ctx->st_aff_idx.p);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
     // the removed blocks' neighbours must stop mirroring them
     std::vector<int32_t> affected;
     collect_affected(ctx, n, block_idx, &affected);
@@ -735,6 +825,7 @@ int a3d_map_clear(a3d_ctx* ctx) {
   ctx->slots.clear();
   ctx->free_slots.clear();
   ctx->next_slot = 0;
+  ctx->vol_stale = true;
   if (ctx->configured) {
     table_rebuild(ctx, 0);
     int rc = table_upload(ctx);

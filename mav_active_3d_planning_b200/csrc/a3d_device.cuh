@@ -29,6 +29,9 @@
 //   dir     dense directory of slots over the bounding box of allocated block indices, an
 //           accelerator in front of the hash (1 load, no probe loop); absent for huge extents
 //   weight  per slot vps^3 floats (TSDF weights, nearest-voxel reads only)
+//   vol     the meta words a second time as ONE dense array over the directory's box, indexed by global
+//           voxel coordinate (4x4x2 bricks = one 128-byte line each): the throughput kernel's
+//           certified samples need a single load and no block lookup (a3d_wave.cu sample_prepare)
 #pragma once
 
 #include <cuda_runtime.h>
@@ -64,6 +67,14 @@ struct MapView {
   int32_t P;                         // vps + 2
   int32_t P3;                        // P^3
   int32_t brick_nx;                  // vps/4 if the meta words are stored in 4x4x2 bricks, else 0
+  int32_t vps_shift;                 // log2(vps) when vps is a power of two, else -1
+  // dense meta volume: the meta words again, indexed by GLOBAL voxel coordinate g = block*vps + voxel
+  // over the directory's box, in 4x4x2 bricks (vol_offset); kWordNoBlock where no block is allocated.
+  // nullptr when the box is too large or vps is not a power of two >= 4.
+  const uint32_t* __restrict__ vol;
+  int32_t vol_lo[3];                 // first voxel coordinate of the box
+  uint32_t vol_n[3];                 // box size in voxels
+  float fast_c0;                     // absolute part of the index-certification margin (a3d_wave.cu)
   float vs_f, vs_inv_f, bs_f, bs_inv_f;
   double c_vs;                       // double(vs_f), VoxbloxMap::c_voxel_size_
 };
@@ -141,6 +152,13 @@ __device__ __forceinline__ int mword_offset(const MapView& m, int x, int y, int 
     return (brick << 5) | ((z & 1) << 4) | ((y & 3) << 2) | (x & 3);
   }
   return (z * m.vps + y) * m.vps + x;
+}
+
+// Offset of box-relative voxel (u0,u1,u2) in the dense meta volume: 4x4x2 bricks of 32 words (one
+// 128-byte line), bricks x fastest.  vol_n[] are multiples of vps, vps a power of two >= 4.
+__device__ __forceinline__ uint32_t vol_offset(const MapView& m, uint32_t u0, uint32_t u1, uint32_t u2) {
+  const uint32_t brick = ((u2 >> 1) * (m.vol_n[1] >> 2) + (u1 >> 2)) * (m.vol_n[0] >> 2) + (u0 >> 2);
+  return (brick << 5) | ((u2 & 1u) << 4) | ((u1 & 3u) << 2) | (u0 & 3u);
 }
 
 __device__ __forceinline__ size_t padded_index(const MapView& m, int slot, int x, int y, int z) {

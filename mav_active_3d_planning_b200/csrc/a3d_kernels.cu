@@ -125,9 +125,16 @@ __device__ __forceinline__ int cell_class(const MapView& m, const float* __restr
 
 // Meta word per voxel of every affected block (layout: a3d_device.cuh header).  One CTA per block;
 // the (vps+1)^3 cell classes are staged in shared memory when they fit.
+// Index of voxel (x,y,z) of block bi in the dense meta volume (the block lies inside the box).
+__device__ __forceinline__ size_t vol_index(const MapView& m, const int32_t* bi, int x, int y, int z) {
+  return vol_offset(m, static_cast<uint32_t>(bi[0] * m.vps + x - m.vol_lo[0]),
+                    static_cast<uint32_t>(bi[1] * m.vps + y - m.vol_lo[1]),
+                    static_cast<uint32_t>(bi[2] * m.vps + z - m.vol_lo[2]));
+}
+
 __global__ void k_build_meta(MapView m, int n, const int32_t* __restrict__ slots,
                              const int32_t* __restrict__ block_idx, uint32_t* __restrict__ mword_slab,
-                             int use_smem) {
+                             uint32_t* __restrict__ vol, int use_smem) {
   extern __shared__ uint8_t s_cls[];
   const int P = m.P, PP = m.P * m.P, vps = m.vps;
   for (int a = blockIdx.x; a < n; a += gridDim.x) {
@@ -165,16 +172,52 @@ __global__ void k_build_meta(MapView m, int n, const int32_t* __restrict__ slots
       word |= static_cast<uint32_t>(centre) << 16;
       word |= static_cast<uint32_t>(obs) << 18;
       mword_slab[static_cast<size_t>(slot) * m.nv + mword_offset(m, x, y, z)] = word;
+      if (vol) vol[vol_index(m, bi, x, y, z)] = word;
     }
   }
 }
 
 void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
-                       const int32_t* block_idx_dev, uint32_t* mword_slab) {
+                       const int32_t* block_idx_dev, uint32_t* mword_slab, uint32_t* vol) {
   if (n <= 0) return;
   const int use_smem = m.P3 <= 40 * 1024;
   k_build_meta<<<std::min(n, 148 * 8), 256, use_smem ? m.P3 : 0, st>>>(m, n, slots_dev, block_idx_dev,
-                                                                       mword_slab, use_smem);
+                                                                       mword_slab, vol, use_smem);
+}
+
+__global__ void k_vol_fill_all(uint32_t* __restrict__ vol, size_t n_words) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_words;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    vol[i] = kWordNoBlock;
+}
+
+// one CTA per listed block: slots == nullptr writes "no block", else copies the block's meta words
+__global__ void k_vol_blocks(MapView m, uint32_t* __restrict__ vol, int n,
+                             const int32_t* __restrict__ slots, const int32_t* __restrict__ block_idx) {
+  const int vps = m.vps;
+  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+    const int32_t* bi = block_idx + 3 * a;
+    const uint32_t* src = slots ? m.mword + static_cast<size_t>(slots[a]) * m.nv : nullptr;
+    for (int lin = threadIdx.x; lin < m.nv; lin += blockDim.x) {
+      const int z = lin / (vps * vps), rem = lin % (vps * vps), y = rem / vps, x = rem % vps;
+      vol[vol_index(m, bi, x, y, z)] = src ? src[mword_offset(m, x, y, z)] : kWordNoBlock;
+    }
+  }
+}
+
+void launch_vol_fill(cudaStream_t st, const MapView& m, uint32_t* vol, int n_blocks,
+                     const int32_t* block_idx_dev) {
+  if (!block_idx_dev) {
+    const size_t n_words = static_cast<size_t>(m.vol_n[0]) * m.vol_n[1] * m.vol_n[2];
+    if (n_words) k_vol_fill_all<<<148 * 8, 256, 0, st>>>(vol, n_words);
+  } else if (n_blocks > 0) {
+    k_vol_blocks<<<std::min(n_blocks, 148 * 8), 256, 0, st>>>(m, vol, n_blocks, nullptr, block_idx_dev);
+  }
+}
+
+void launch_vol_scatter(cudaStream_t st, const MapView& m, uint32_t* vol, int n, const int32_t* slots_dev,
+                        const int32_t* block_idx_dev) {
+  if (n > 0) k_vol_blocks<<<std::min(n, 148 * 8), 256, 0, st>>>(m, vol, n, slots_dev, block_idx_dev);
 }
 
 // ---------------------------------------------------------------------------------------------

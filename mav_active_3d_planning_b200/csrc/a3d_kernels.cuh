@@ -64,7 +64,14 @@ void launch_apply_blocks(cudaStream_t st, const MapView& m, int n, const int32_t
 void launch_refresh_aprons(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                            const int32_t* nbr_dev /*n×27*/, float* dist_slab);
 void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
-                       const int32_t* block_idx_dev /*n×3*/, uint32_t* mword_slab);
+                       const int32_t* block_idx_dev /*n×3*/, uint32_t* mword_slab,
+                       uint32_t* vol /*dense meta volume described by m.vol_lo / m.vol_n, or null*/);
+// dense meta volume maintenance: fill everything / the listed blocks with "no block", copy the
+// listed blocks' meta words in
+void launch_vol_fill(cudaStream_t st, const MapView& m, uint32_t* vol, int n_blocks,
+                     const int32_t* block_idx_dev /*n×3, or null: whole volume*/);
+void launch_vol_scatter(cudaStream_t st, const MapView& m, uint32_t* vol, int n, const int32_t* slots_dev,
+                        const int32_t* block_idx_dev /*n×3*/);
 void launch_point_query(cudaStream_t st, const MapView& m, int what, long long n, const double* pts,
                         void* out0, void* out1, double arg = 0.0);
 void launch_bv_contains(cudaStream_t st, const EvalView& e, long long n, const double* pts,

@@ -79,7 +79,6 @@ struct LaneCounters {
   unsigned long long packed;
   unsigned long long digest;  // DIGEST instantiations only
   unsigned n_samp;
-  unsigned inexact;
 };
 constexpr int kFieldBits = 21;
 
@@ -135,28 +134,105 @@ __device__ __forceinline__ uint64_t pack_key(const Ident& id, unsigned* inexact)
 
 // Per-lane state of the ray part a lane is marching (kept small: it lives in registers across the
 // whole engine loop).
+#ifndef A3D_WAVE_PREFETCH
+#define A3D_WAVE_PREFETCH 0  // 1: request a sample's meta word one step ahead of its use
+#endif
+
+// Index part of a sample: voxel coordinate, cell octant and the meta word (requested).
+struct Prefetched {
+  int g0, g1, g2;  // floor(pf / voxel_size) per axis
+  int flags;       // bits 2:0 cell octant, bit 3: certified (see ray_step)
+  uint32_t word;   // meta word of voxel g (certified samples only)
+};
+
+// Per-lane state that is read once per sample or less lives in shared memory, one column per
+// thread: the kernel is register-bound (measured: every spilled value costs more than these loads).
+struct LaneTable {
+  double dir[3][kWaveThreads];  // world direction of the lane's ray
+  int r[kWaveThreads];          // ray id
+  int mark[kWaveThreads];       // index of the lane's marking part in the diagonal's list
+  unsigned inexact;             // any lane met a case the scan-order kernel must decide
+};
+
 struct RayState {
-  double dx, dy, dz;  // world direction
   double d;           // distance of the next sample (accumulated like `distance += p_ray_step_`)
   Ident prev;         // previous raw entry (g0 == kNoIdent: none yet)
-  int r;              // ray id
+#if A3D_WAVE_PREFETCH
+  Prefetched nx;      // the sample at distance d
+#endif
 };
 
 struct ViewShared {  // per-view constants, one copy per CTA in shared memory
   double P0[3];
   double q[4];
+  // index-certification margin of this view (NaN: no sample of the view may take the fast path)
+  float delta, delta_hi;  // delta_hi = 0.5f - delta
 };
 
-__device__ __forceinline__ void ray_begin(RayState& rs, const CasterView& c, const ViewShared& vw,
-                                          int r, double d0) {
+// Bounding-volume test on integer voxel coordinates: for an axis-aligned volume, centre(g) inside
+// [bv_min, bv_max] <=> lo <= g <= hi per axis (the centre double is monotone in g).  Built once per
+// CTA from the literal centre arithmetic; fast == 0: use bv_contains() on the centre itself.
+struct BvGrid {
+  int lo[3], hi[3];
+  int fast;
+};
+
+__device__ __forceinline__ double centre_of(const MapView& m, const CenterTables& ct, int g) {
+  const int b = g >> m.vps_shift, v = g & (m.vps - 1);
+  return __dadd_rn(static_cast<double>(origin_point(b, m.bs_f)), ct.d[v + 1]);
+}
+
+// threads 0..2, one axis each
+__device__ void init_bv_grid(const MapView& m, const CenterTables& ct, const EvalView& e, BvGrid* g) {
+  const int a = threadIdx.x;
+  if (a == 0) g->fast = 1;
+  __syncwarp();
+  if (a >= 3) return;
+  const bool identity = e.bv_q.w == 1.0 && e.bv_q.x == 0.0 && e.bv_q.y == 0.0 && e.bv_q.z == 0.0;
+  bool ok = e.bv_is_setup && identity && m.vps_shift >= 0;
+  int lo = INT32_MIN, hi = INT32_MAX;
+  if (ok) {
+    const double lim = 1048576.0;  // certified samples have |g| < 2^21
+    const double tl = e.bv_min[a] / m.c_vs, th = e.bv_max[a] / m.c_vs;
+    if (tl != tl || th != th) ok = false;
+    if (ok && tl > -lim) {
+      // smallest g whose centre is not below bv_min
+      int q = static_cast<int>(floor(fmin(tl, lim))) - 3;
+      ok = centre_of(m, ct, q) < e.bv_min[a];
+      int it = 0;
+      while (ok && centre_of(m, ct, q) < e.bv_min[a]) {
+        ++q;
+        if (++it > 8) ok = false;
+      }
+      lo = q;
+    }
+    if (ok && th < lim) {
+      // largest g whose centre is not above bv_max
+      int q = static_cast<int>(floor(fmax(th, -lim))) + 3;
+      ok = centre_of(m, ct, q) > e.bv_max[a];
+      int it = 0;
+      while (ok && centre_of(m, ct, q) > e.bv_max[a]) {
+        --q;
+        if (++it > 8) ok = false;
+      }
+      hi = q;
+    }
+  }
+  g->lo[a] = lo;
+  g->hi[a] = hi;
+  if (!ok) g->fast = 0;
+}
+
+__device__ __forceinline__ void ray_begin(RayState& rs, LaneTable& lt, const CasterView& c,
+                                          const ViewShared& vw, int r, double d0) {
   const Q4 q{vw.q[0], vw.q[1], vw.q[2], vw.q[3]};
   const D3 dir = rotate(q, D3{c.cam_dirs[3 * r], c.cam_dirs[3 * r + 1], c.cam_dirs[3 * r + 2]});
-  rs.dx = dir.x;
-  rs.dy = dir.y;
-  rs.dz = dir.z;
+  lt.dir[0][threadIdx.x] = dir.x;
+  lt.dir[1][threadIdx.x] = dir.y;
+  lt.dir[2][threadIdx.x] = dir.z;
   rs.d = d0;
   rs.prev = Ident{kNoIdent, 0, 0};
-  rs.r = r;
+  lt.r[threadIdx.x] = r;
 }
 
 // Everything about one sample that the list logic needs.
@@ -205,25 +281,16 @@ __device__ __noinline__ SampleInfo sample_slow(const MapView& m, const CenterTab
   return si;
 }
 
-// One sample of the lane's ray.  Returns true when the part is finished (hit or end reached);
-// *hit_d = distance of the OCCUPIED sample that ended it (unchanged otherwise).
-// rec_at: index of this part's record.  Precondition: rs.d < d_end.
-//
-// The common case — allocated or unallocated block, in-range voxel indices that agree between
-// getVoxelState's and getVoxelCenter's index arithmetic, definite cell class — is straight-line
-// code around one meta-word load; everything else goes through sample_slow().
-template <int CASTER, int EVAL, bool DIGEST>
-__device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
-                                         const ViewShared& vw, const double step, const double d_end,
-                                         RayState& rs, LaneCounters& lc, const Records& rec,
-                                         size_t rec_at, double* hit_d) {
-  constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
-  const double d_this = rs.d;
-  const double pp[3] = {__dadd_rn(vw.P0[0], __dmul_rn(d_this, rs.dx)),
-                        __dadd_rn(vw.P0[1], __dmul_rn(d_this, rs.dy)),
-                        __dadd_rn(vw.P0[2], __dmul_rn(d_this, rs.dz))};
-  rs.d = __dadd_rn(d_this, step);
-  lc.n_samp++;
+// One sample, literally as the reference computes it (voxblox index arithmetic on the float point
+// for the state, on the double point for the voxel centre).  Used for the samples the margin test
+// of ray_step() cannot certify.
+struct ExactOut {
+  SampleInfo si;
+  D3 cc;  // voxel centre (voxblox.cpp:72-79)
+};
+__device__ __noinline__ void sample_exact(const MapView& m, const CenterTables& ct, double p0, double p1,
+                                          double p2, ExactOut* out, unsigned* inexact) {
+  const double pp[3] = {p0, p1, p2};
   float pf[3], origin[3];
   int bi[3], vs[3], vi[3];
   int sc = 0;
@@ -256,27 +323,164 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
   si.st = cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
   si.cs = centre_state_from_word(word);
   si.id = Ident{bi[0] * m.vps + vi[0], bi[1] * m.vps + vi[1], bi[2] * m.vps + vi[2]};
-  if (!(in_range & same) | (cls == kCellMixed)) {
+  if (!(in_range & same) | (cls == kCellMixed))
+    si = sample_slow(m, ct, pf[0], pf[1], pf[2], bi[0], bi[1], bi[2], slot, vi[0], vi[1], vi[2], inexact);
+  out->si = si;
+  double cp[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    cp[a] = (vi[a] >= -1 && vi[a] <= m.vps) ? ct.d[vi[a] + 1]
+                                            : static_cast<double>(center_point(vi[a], m.vs_f));
+  out->cc.x = __dadd_rn(static_cast<double>(origin[0]), cp[0]);
+  out->cc.y = __dadd_rn(static_cast<double>(origin[1]), cp[1]);
+  out->cc.z = __dadd_rn(static_cast<double>(origin[2]), cp[2]);
+}
+
+// Position of the sample at distance d of the lane's ray, double and float (the reference casts the
+// double point to voxblox::Point).
+__device__ __forceinline__ void sample_point(const ViewShared& vw, const LaneTable& lt, double d,
+                                             double (&pp)[3], float (&pf)[3]) {
+  const double dx = lt.dir[0][threadIdx.x], dy = lt.dir[1][threadIdx.x], dz = lt.dir[2][threadIdx.x];
+  pp[0] = __dadd_rn(vw.P0[0], __dmul_rn(d, dx));
+  pp[1] = __dadd_rn(vw.P0[1], __dmul_rn(d, dy));
+  pp[2] = __dadd_rn(vw.P0[2], __dmul_rn(d, dz));
+#pragma unroll
+  for (int a = 0; a < 3; ++a) pf[a] = __double2float_rn(pp[a]);
+}
+
+// Index arithmetic of the sample at distance d and the request for its meta word.
+//
+// With T = pf * (1/voxel_size) per axis, g = floor(T) is the global voxel coordinate
+// block*vps + voxel and frac(T) tells the half of the voxel (= interpolation cell octant).  The
+// reference reaches the same numbers through ~8 float roundings (block index, block origin,
+// in-block offset, voxel index, each with voxblox's +1e-6; once more from the double point for
+// getVoxelCenter), whose combined error in voxel units is below
+//     delta = 5e-7 * max|T| + (vps+1) * (16 * 2^-24 + 1.1e-6).
+// When frac(T) keeps a distance > delta from 0, 1/2 and 1 on all three axes, every one of those
+// floors and the centre comparison provably land where floor(T) / frac(T) say: block and voxel
+// indices are in range, getVoxelState's and getVoxelCenter's voxels coincide and no artefact index
+// can occur ("certified").  Such a sample costs one load from the dense meta volume (or a directory
+// load and a meta-word load when the volume is not available).  Everything else (≈ 12*delta of the
+// samples, plus cells whose class is MIXED) is evaluated literally by ray_step().
+__device__ __forceinline__ Prefetched sample_prepare(const MapView& m, const ViewShared& vw,
+                                                     const LaneTable& lt, double d) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (T + kMagic) - kMagic = rint(T) for |T| < 2^22
+  double pp[3];
+  float pf[3];
+  sample_point(vw, lt, d, pp, pf);
+  int g[3];
+  int sc = 0;
+  bool safe = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float T = __fmul_rn(pf[a], m.vs_inv_f);
+    const float s = __fadd_rn(T, kMagic);
+    const float fr = __fsub_rn(T, __fsub_rn(s, kMagic));  // T - rint(T), exact, in [-1/2, 1/2]
+    const float af = fabsf(fr);
+    safe &= (af > vw.delta) & (af < vw.delta_hi);
+    const int below = __float_as_int(fr) >> 31;  // -1 when T is below its nearest integer
+    g[a] = (__float_as_int(s) - 0x4B400000) + below;
+    sc |= (below + 1) << a;  // bit set: the point is below the voxel centre on this axis
+  }
+  Prefetched nx;
+  nx.g0 = g[0];
+  nx.g1 = g[1];
+  nx.g2 = g[2];
+  nx.flags = sc | (safe ? 8 : 0);
+  nx.word = kWordNoBlock;
+  if (safe) {
+    if (m.vol) {
+      // dense meta volume: one load, no block lookup
+      const unsigned u0 = static_cast<unsigned>(g[0] - m.vol_lo[0]),
+                     u1 = static_cast<unsigned>(g[1] - m.vol_lo[1]),
+                     u2 = static_cast<unsigned>(g[2] - m.vol_lo[2]);
+      if ((u0 < m.vol_n[0]) & (u1 < m.vol_n[1]) & (u2 < m.vol_n[2]))
+        nx.word = __ldg(m.vol + vol_offset(m, u0, u1, u2));
+    } else {
+      const int vmask = m.vps - 1;
+      const int slot = find_slot(m, g[0] >> m.vps_shift, g[1] >> m.vps_shift, g[2] >> m.vps_shift);
+      if (slot >= 0)
+        nx.word = __ldg(m.mword + static_cast<size_t>(slot) * m.nv +
+                        mword_offset(m, g[0] & vmask, g[1] & vmask, g[2] & vmask));
+    }
+  }
+  return nx;
+}
+
+// One sample of the lane's ray: folds the prepared sample rs.nx (distance rs.d) and prepares the
+// next one.  Returns true when the part is finished (hit or end reached); *hit_d = distance of the
+// OCCUPIED sample that ended it (unchanged otherwise).
+// rec_base + part_off + ray: index of this part's record.  Precondition: rs.d < d_end (and rs.nx
+// prepared for rs.d when prefetching).
+template <int CASTER, int EVAL, bool DIGEST>
+__device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
+                                         const ViewShared& vw, const BvGrid& bvg, const double step,
+                                         const double d_end, RayState& rs, LaneTable& lt,
+                                         LaneCounters& lc, const Records& rec, size_t rec_base,
+                                         int part_off, double* hit_d) {
+  constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
+  const double d_this = rs.d;
+#if A3D_WAVE_PREFETCH
+  const Prefetched cur = rs.nx;
+  rs.d = __dadd_rn(d_this, step);
+  const bool more = rs.d < d_end;
+  if (more) rs.nx = sample_prepare(m, vw, lt, rs.d);  // its load overlaps the fold below
+#else
+  const Prefetched cur = sample_prepare(m, vw, lt, d_this);
+  rs.d = __dadd_rn(d_this, step);
+  const bool more = rs.d < d_end;
+#endif
+  lc.n_samp++;
+  const int g[3] = {cur.g0, cur.g1, cur.g2};
+  const int sc = cur.flags & 7;
+  const bool safe = (cur.flags & 8) != 0;
+  SampleInfo si;
+  D3 cc{0.0, 0.0, 0.0};
+  bool in_bv = true;
+  constexpr bool kNeedCentre = DIGEST || EVAL == A3D_EVAL_FRONTIER;
+  if (safe) {
+    const int b0 = g[0] >> m.vps_shift, b1 = g[1] >> m.vps_shift, b2 = g[2] >> m.vps_shift;
+    const int vmask = m.vps - 1;
+    const int v0 = g[0] & vmask, v1 = g[1] & vmask, v2 = g[2] & vmask;
+    const uint32_t word = cur.word;
+    const int cls = (word >> (2 * sc)) & 3;
+    si.st = cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
+    si.cs = centre_state_from_word(word);
+    si.id = Ident{g[0], g[1], g[2]};
+    if (cls == kCellMixed) {
+      unsigned bad = 0;
+      double pp[3];
+      float pf[3];
+      sample_point(vw, lt, d_this, pp, pf);
+      si = sample_slow(m, ct, pf[0], pf[1], pf[2], b0, b1, b2, find_slot(m, b0, b1, b2), v0, v1, v2, &bad);
+      if (bad) lt.inexact = 1;
+    }
+    if (kNeedCentre || (e.bv_is_setup && !bvg.fast)) {
+      cc.x = __dadd_rn(static_cast<double>(origin_point(b0, m.bs_f)), ct.d[v0 + 1]);
+      cc.y = __dadd_rn(static_cast<double>(origin_point(b1, m.bs_f)), ct.d[v1 + 1]);
+      cc.z = __dadd_rn(static_cast<double>(origin_point(b2, m.bs_f)), ct.d[v2 + 1]);
+      if (e.bv_is_setup) in_bv = bv_contains(e, cc);  // simulated_sensor_evaluator.cpp:50-57
+    } else if (e.bv_is_setup) {
+      in_bv = (g[0] >= bvg.lo[0]) & (g[0] <= bvg.hi[0]) & (g[1] >= bvg.lo[1]) & (g[1] <= bvg.hi[1]) &
+              (g[2] >= bvg.lo[2]) & (g[2] <= bvg.hi[2]);
+    }
+  } else {
+    ExactOut out;
     unsigned bad = 0;
-    si = sample_slow(m, ct, pf[0], pf[1], pf[2], bi[0], bi[1], bi[2], slot, vi[0], vi[1], vi[2], &bad);
-    lc.inexact |= bad;
+    double pp[3];
+    float pf[3];
+    sample_point(vw, lt, d_this, pp, pf);
+    sample_exact(m, ct, pp[0], pp[1], pp[2], &out, &bad);
+    if (bad) lt.inexact = 1;
+    si = out.si;
+    cc = out.cc;
+    if (e.bv_is_setup) in_bv = bv_contains(e, cc);
   }
   const bool emit = ITER || si.st != 0;
-  bool keep = emit & ((si.id.g0 != rs.prev.g0) | (si.id.g1 != rs.prev.g1) | (si.id.g2 != rs.prev.g2));
+  const bool keep = emit & in_bv &
+                    ((si.id.g0 != rs.prev.g0) | (si.id.g1 != rs.prev.g1) | (si.id.g2 != rs.prev.g2));
   const bool first = emit & (rs.prev.g0 == kNoIdent);
   if (emit) rs.prev = si.id;
-  D3 cc{0.0, 0.0, 0.0};
-  if (DIGEST || e.bv_is_setup || EVAL == A3D_EVAL_FRONTIER) {
-    double cp[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-      cp[a] = (vi[a] >= -1 && vi[a] <= m.vps) ? ct.d[vi[a] + 1]
-                                              : static_cast<double>(center_point(vi[a], m.vs_f));
-    cc.x = __dadd_rn(static_cast<double>(origin[0]), cp[0]);
-    cc.y = __dadd_rn(static_cast<double>(origin[1]), cp[1]);
-    cc.z = __dadd_rn(static_cast<double>(origin[2]), cp[2]);
-    if (e.bv_is_setup) keep = keep && bv_contains(e, cc);  // simulated_sensor_evaluator.cpp:50-57
-  }
   int cat;
   if (EVAL == A3D_EVAL_VOXEL_TYPE) {
     cat = si.cs & 3;  // retained entries are always inside the bounding volume
@@ -299,20 +503,24 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
   if (first) {
     // record of the part's first entry, written once
     unsigned bad = 0;
-    rec.first_key[rec_at] = pack_key(si.id, &bad);
-    lc.inexact |= bad;
-    rec.info[rec_at] = static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0));
+    const size_t rec_at = rec_base + part_off + lt.r[threadIdx.x];
+    __stcs(&rec.first_key[rec_at], pack_key(si.id, &bad));
+    if (bad) lt.inexact = 1;
+    __stcs(&rec.info[rec_at], static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0)));
     if (DIGEST) rec.first_hash[rec_at] = h;
   }
   if (si.st == 0) {
     *hit_d = d_this;
     return true;
   }
-  return !(rs.d < d_end);
+  return !more;
 }
 
 #ifndef A3D_WAVE_STEPS
-#define A3D_WAVE_STEPS 8  // samples marched between two rounds of lane bookkeeping
+#define A3D_WAVE_STEPS 16  // samples marched between two rounds of lane bookkeeping
+#endif
+#ifndef A3D_WAVE_MARK_STEPS
+#define A3D_WAVE_MARK_STEPS 24  // ... while marking parts are in flight (scheduler warp)
 #endif
 
 }  // namespace
@@ -342,11 +550,15 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   double* const s_mark_hit = s_dyn;
   unsigned* const s_mark_list = reinterpret_cast<unsigned*>(s_dyn + c.diag_max);
   __shared__ unsigned long long s_packed, s_digest;
-  __shared__ unsigned s_nsamp, s_inexact;
+  __shared__ unsigned s_nsamp;
+  __shared__ BvGrid bvg;
+  __shared__ LaneTable lt;
   init_center_tables(m, &ct);
+  __syncthreads();
+  if (threadIdx.x < 32) init_bv_grid(m, ct, e, &bvg);
 
   const size_t cta_base = static_cast<size_t>(blockIdx.x) * ws.rays_stride;
-  volatile uint32_t* const table = ws.table + cta_base;
+  uint32_t* const table = ws.table + cta_base;  // written by atomics, read with __ldcg
   volatile uint8_t* const start_s = ws.start_s + cta_base;
   const double step = c.ray_step;
   const double d_leaf_end = c.ray_length;
@@ -354,7 +566,10 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
 
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_seg = static_cast<int>(atomicAdd(b.work_counter, 1u));
+    if (threadIdx.x == 0) {
+      s_seg = static_cast<int>(atomicAdd(b.work_counter, 1u));
+      lt.inexact = 0;
+    }
     __syncthreads();
     const int seg = s_seg;
     if (seg >= b.n_segments) break;
@@ -379,6 +594,13 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         vw.q[1] = q.x;
         vw.q[2] = q.y;
         vw.q[3] = q.z;
+        // margin of the certified index path for every sample this view can produce
+        const double reach = fmax(fmax(fabs(vw.P0[0]), fabs(vw.P0[1])), fabs(vw.P0[2])) + c.ray_length;
+        const double t_max = reach * static_cast<double>(m.vs_inv_f) * 1.001 + 2.0;
+        float delta = __int_as_float(0x7FC00000);
+        if (m.vps_shift >= 0 && t_max < 1048576.0) delta = static_cast<float>(t_max * 5e-7) + m.fast_c0;
+        vw.delta = delta;
+        vw.delta_hi = 0.5f - delta;
         s_done_diag = (ITER && n > 1) ? 0 : n_diag;
         s_unit_cursor = 0;
       }
@@ -387,8 +609,8 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
           table[r] = 0u;
           start_s[r] = 0xFF;
         }
-        ws.rec.info[cta_base * 2 + r] = kCatNone;
-        ws.rec.info[cta_base * 2 + n_rays + r] = kCatNone;
+        __stcs(&ws.rec.info[cta_base * 2 + r], static_cast<uint8_t>(kCatNone));
+        __stcs(&ws.rec.info[cta_base * 2 + n_rays + r], static_cast<uint8_t>(kCatNone));
       }
       __syncthreads();
 
@@ -403,19 +625,21 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         int cur_diag = -1, n_mark = 0, mark_head = 0, n_run = 0;
         // lane state
         RayState rs;
-        rs.r = -1;
         int role = 0;  // 0 idle, 1 leaf part, 2 marking part
-        int mark_idx = 0;
 
         for (;;) {
           // ---- 1. scheduler: finish the current diagonal, open the next ones ----
           while (!sched_done && mark_head == n_mark && n_run == 0) {
             if (cur_diag >= 0) {
-              // markNeighboringRays of every marking ray of the diagonal, in scan order
-              for (int qi = 0; qi < n_mark; ++qi) {
-                const unsigned it = s_mark_list[qi];
+              // markNeighboringRays of every marking ray of the diagonal.  An entry keeps the value
+              // of its highest writer (= last writer in scan order), so the marks commute: they are
+              // applied with fire-and-forget atomicMax on (writer << 8 | value), one ray per lane.
+              for (int base = 0; base < n_mark; base += 32) {
+                const int qi = base + static_cast<int>(lane);
+                const bool valid = qi < n_mark;
+                const unsigned it = valid ? s_mark_list[qi] : 0u;
                 const int rr = static_cast<int>(it >> 8), ss = static_cast<int>(it & 0xFF);
-                const double hd = s_mark_hit[qi];
+                const double hd = valid ? s_mark_hit[qi] : -1.0;
                 const bool hit = hd >= 0.0;
                 int seg_h = ss;
                 if (hit) {
@@ -424,30 +648,35 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                 const int t_last = hit ? seg_h : n - 2;
                 const int w0 = 1 << (n - 1 - ss);
                 const int ri = rr / c.res_y, rj = rr - ri * c.res_y;
-                if (w0 == 2) {
+                const unsigned wr = (static_cast<unsigned>(rr) + 1u) << 8;
+                if (valid && w0 == 2) {
                   // start section n-2 (most marking rays): the 2x2 square gets one value
-                  const int val = hit ? -1 : n - 1;
-                  const int dx = lane >> 1, dy = lane & 1;
-                  if (lane < 4 && ri + dx < c.res_x && rj + dy < c.res_y) {
-                    const int at = (ri + dx) * c.res_y + rj + dy;
-                    const unsigned writer = static_cast<unsigned>(rr) + 1u;
-                    if ((table[at] >> 8) < writer) table[at] = (writer << 8) | static_cast<uint8_t>(val);
+                  const unsigned ent = wr | static_cast<uint8_t>(hit ? -1 : n - 1);
+                  const bool in_x = ri + 1 < c.res_x, in_y = rj + 1 < c.res_y;
+                  atomicMax(&table[rr], ent);
+                  if (in_y) atomicMax(&table[rr + 1], ent);
+                  if (in_x) atomicMax(&table[rr + c.res_y], ent);
+                  if (in_x && in_y) atomicMax(&table[rr + c.res_y + 1], ent);
+                }
+                // larger squares: the warp shares the cells of one ray at a time
+                unsigned big = __ballot_sync(kFull, valid && w0 > 2);
+                while (big) {
+                  const int src = __ffs(big) - 1;
+                  big &= big - 1;
+                  const int b_ri = __shfl_sync(kFull, ri, src), b_rj = __shfl_sync(kFull, rj, src);
+                  const int b_w0 = __shfl_sync(kFull, w0, src), b_tl = __shfl_sync(kFull, t_last, src);
+                  const int b_sh = __shfl_sync(kFull, hit ? seg_h : -1, src);
+                  const unsigned b_wr = __shfl_sync(kFull, wr, src);
+                  const int nx = min(b_w0, c.res_x - b_ri), ny = min(b_w0, c.res_y - b_rj);
+                  for (int cell = lane; cell < nx * ny; cell += 32) {
+                    const int dx = cell / ny, dy = cell - dx * ny;
+                    const int mx = max(dx, dy);
+                    const int tmax = mx == 0 ? n - 1 : n - 2 - (31 - __clz(mx));
+                    const int t = min(tmax, b_tl);
+                    const int val = (t == b_sh) ? -1 : t + 1;
+                    atomicMax(&table[(b_ri + dx) * c.res_y + b_rj + dy], b_wr | static_cast<uint8_t>(val));
                   }
-                  __syncwarp();
-                  continue;
                 }
-                const int nx = min(w0, c.res_x - ri), ny = min(w0, c.res_y - rj);
-                const unsigned writer = static_cast<unsigned>(rr) + 1u;
-                for (int cell = lane; cell < nx * ny; cell += 32) {
-                  const int dx = cell / ny, dy = cell - dx * ny;
-                  const int mx = max(dx, dy);
-                  const int tmax = mx == 0 ? n - 1 : n - 2 - (31 - __clz(mx));
-                  const int t = min(tmax, t_last);
-                  const int val = (hit && t == seg_h) ? -1 : t + 1;
-                  const int at = (ri + dx) * c.res_y + rj + dy;
-                  if ((table[at] >> 8) < writer) table[at] = (writer << 8) | static_cast<uint8_t>(val);
-                }
-                __syncwarp();
               }
               __threadfence_block();
               if (lane == 0) s_done_diag = cur_diag + 1;
@@ -466,7 +695,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
               int s = -1, r = 0;
               if (i <= i_hi) {
                 r = i * c.res_y + (cur_diag - i);
-                s = static_cast<int>(static_cast<int8_t>(table[r] & 0xFFu));
+                s = static_cast<int>(static_cast<int8_t>(__ldcg(&table[r]) & 0xFFu));
               }
               const bool marking = s >= 0 && s < n - 1;
               const unsigned mm = __ballot_sync(kFull, marking);
@@ -487,10 +716,14 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
               take_mark = min(n_idle, n_mark - mark_head);
               if (role == 0 && rank < take_mark) {
                 const unsigned it = s_mark_list[mark_head + rank];
-                mark_idx = mark_head + rank;
+                const int mark_idx = mark_head + rank;
+                lt.mark[threadIdx.x] = mark_idx;
                 const int ms = static_cast<int>(it & 0xFF);
-                ray_begin(rs, c, vw, static_cast<int>(it >> 8), c.split[ms]);
-                start_s[rs.r] = static_cast<uint8_t>(ms);  // read by leaf lanes after the diagonal
+                ray_begin(rs, lt, c, vw, static_cast<int>(it >> 8), c.split[ms]);
+#if A3D_WAVE_PREFETCH
+                rs.nx = sample_prepare(m, vw, lt, rs.d);
+#endif
+                start_s[it >> 8] = static_cast<uint8_t>(ms);  // read by leaf lanes after the diagonal
                 s_mark_hit[mark_idx] = -1.0;
                 role = 2;  // split[s] < split[n-1] for s < n-1: at least one sample
               }
@@ -520,7 +753,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                   const int i = c.unit_i0[u] + static_cast<int>(lane);
                   if (i <= min(c.res_x - 1, dg)) {
                     rr = i * c.res_y + (dg - i);
-                    ready = static_cast<int>(static_cast<int8_t>(table[rr] & 0xFFu)) == n - 1;
+                    ready = static_cast<int>(static_cast<int8_t>(__ldcg(&table[rr]) & 0xFFu)) == n - 1;
                   }
                 } else {
                   rr = u * 32 + static_cast<int>(lane);
@@ -539,8 +772,11 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                   const int s0 = start_s[r] == 0xFF ? n - 1 : start_s[r];
                   d0 = c.leaf_d0[s0];  // accumulated distance at which a ray started in s0 enters section n-1
                 }
-                ray_begin(rs, c, vw, r, d0);
+                ray_begin(rs, lt, c, vw, r, d0);
                 role = (rs.d < d_leaf_end) ? 1 : 0;
+#if A3D_WAVE_PREFETCH
+                if (role) rs.nx = sample_prepare(m, vw, lt, rs.d);
+#endif
               }
               const int taken = min(n_idle, pend_count);
               pend_head = (pend_head + taken) % kPendCap;
@@ -558,28 +794,38 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
           }
 
           // ---- 4. a few samples per busy lane ----
-          bool fin_mark = false;
+          // The scheduler warp stays in the loop until the marking parts in flight are done (bounded)
+          // and leaves it the moment they are, so that the next anti-diagonal opens without delay.
+          int run_left = n_run;
+          const int max_it = (scheduler && run_left > 0) ? A3D_WAVE_MARK_STEPS : A3D_WAVE_STEPS;
 #pragma unroll 1
-          for (int it = 0; it < A3D_WAVE_STEPS; ++it) {
+          for (int it = 0; it < max_it; ++it) {
+            bool fin_mark = false;
             if (role != 0) {
-              const size_t rec_at = cta_base * 2 + (role == 2 ? 0 : static_cast<size_t>(n_rays)) + rs.r;
               double hit_d = -1.0;
-              if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, step, role == 2 ? d_mark_end : d_leaf_end,
-                                                 rs, lc, ws.rec, rec_at, &hit_d)) {
+              if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, bvg, step, role == 2 ? d_mark_end : d_leaf_end,
+                                                 rs, lt, lc, ws.rec, cta_base * 2, role == 2 ? 0 : n_rays,
+                                                 &hit_d)) {
                 if (rs.prev.g0 != kNoIdent) {
                   unsigned bad = 0;
-                  ws.rec.last_key[rec_at] = pack_key(rs.prev, &bad);
-                  lc.inexact |= bad;
+                  const size_t rec_at =
+                      cta_base * 2 + (role == 2 ? 0 : static_cast<size_t>(n_rays)) + lt.r[threadIdx.x];
+                  __stcs(&ws.rec.last_key[rec_at], pack_key(rs.prev, &bad));
+                  if (bad) lt.inexact = 1;
                 }
                 if (role == 2) {
-                  s_mark_hit[mark_idx] = hit_d;
+                  s_mark_hit[lt.mark[threadIdx.x]] = hit_d;
                   fin_mark = true;
                 }
                 role = 0;
               }
             }
+            if (scheduler && run_left > 0) {
+              run_left -= __popc(__ballot_sync(kFull, fin_mark));
+              if (run_left == 0) break;
+            }
           }
-          if (scheduler) n_run -= __popc(__ballot_sync(kFull, fin_mark));
+          n_run = run_left;
           __syncwarp();
         }
       }
@@ -596,10 +842,10 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
           size_t at = 0;
           if (rr < n_rays) {
             at = cta_base * 2 + static_cast<size_t>(part) * n_rays + rr;
-            info = ws.rec.info[at];
+            info = __ldcs(&ws.rec.info[at]);
             if (info & 8) {
-              fk = ws.rec.first_key[at];
-              lk = ws.rec.last_key[at];
+              fk = __ldcs(&ws.rec.first_key[at]);
+              lk = __ldcs(&ws.rec.last_key[at]);
             }
           }
           const bool emitted = (info & 8) != 0;
@@ -626,7 +872,6 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
       s_packed = 0;
       s_digest = 0;
       s_nsamp = 0;
-      s_inexact = 0;
     }
     __syncthreads();
     {
@@ -637,11 +882,9 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         if (DIGEST) dg += __shfl_xor_sync(kFull, dg, off);
       }
       const unsigned tsmp = __reduce_add_sync(kFull, lc.n_samp);
-      const unsigned tin = __reduce_or_sync(kFull, lc.inexact);
       if (lane == 0) {
         atomicAdd(&s_packed, pk);
         atomicAdd(&s_nsamp, tsmp);
-        atomicOr(&s_inexact, tin);
         if (DIGEST) atomicAdd(&s_digest, dg);
       }
     }
@@ -650,7 +893,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
       const unsigned long long fmask = (1ull << kFieldBits) - 1;
       const unsigned long long c0 = s_packed & fmask, c1 = (s_packed >> kFieldBits) & fmask,
                                c2 = (s_packed >> (2 * kFieldBits)) & fmask;
-      unsigned inexact = s_inexact;
+      unsigned inexact = lt.inexact;
       // a field may have wrapped if the segment has 2^21 or more samples
       if (s_nsamp >= (1u << kFieldBits)) inexact = 1;
       const unsigned long long n_vis_total = c0 + c1 + c2;

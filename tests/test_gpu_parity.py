@@ -422,6 +422,96 @@ def test_wave_kernel_cfg2_and_cfg4(capi, O, room01):
     ctx.close()
 
 
+def test_wave_axis_aligned_bounding_volume(capi, O, room02):
+    """Axis-aligned volume whose faces coincide with voxel centres / voxel faces: the wavefront
+    kernel tests it on integer voxel coordinates (BvGrid), the reference on the centre doubles."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    oc = om.caster("IterativeRayCaster", **CAM_BASE)
+    pos, quat = synth.candidate_views(room02, 32, seed=3)
+    vs = float(np.float32(0.2))
+    for bv in (dict(x_min=20.5 * vs, x_max=70.5 * vs, y_min=4.0, y_max=16.0, z_min=0.5 * vs, z_max=12.5 * vs),
+               dict(x_min=4.1, x_max=13.9, y_min=30 * vs, y_max=60 * vs, z_min=-100.0, z_max=1e9),
+               dict(x_min=6.0, x_max=5.0, y_min=0.0, y_max=20.0, z_min=0.0, z_max=10.0)):  # not a volume: ignored
+        for ekind in ("VoxelTypeEvaluator", "NaiveEvaluator"):
+            kw = dict(bounding_volume=bv)
+            got = _wave(ctx, caster, ctx.evaluator(ekind, **kw), pos, quat)
+            want = oc.compute_gains(O.eval_params(ekind, **kw), pos, quat, n_threads=8)
+            _check_wave(got, want)
+    ctx.close()
+
+
+def test_wave_far_from_origin(capi, O):
+    """The same room 9.6 km / 6.4 km / 1.6 km away from the origin: fp32 coordinates carry ~1e-3 m
+    of rounding there, voxblox's index arithmetic produces artefact indices and most samples fail
+    the wavefront kernel's certification margin (literal path)."""
+    import dataclasses
+    from mav_active_3d_planning_b200 import synth
+    m0 = synth.room_map(0.2)
+    shift = np.array([3000, -2000, 500], np.int32)
+    m = dataclasses.replace(m0, block_idx=m0.block_idx + shift)
+    ctx, om = make_pair(capi, O, m)
+    pos, quat = synth.candidate_views(m0, 24, seed=5)
+    pos = pos + shift.astype(np.float64) * float(np.float32(0.2) * np.float32(16))
+    for ckind in ("IterativeRayCaster", "SimpleRayCaster"):
+        caster = ctx.caster(ckind, **CAM_BASE)
+        oc = om.caster(ckind, **CAM_BASE)
+        for ekind in ("VoxelTypeEvaluator", "FrontierEvaluator"):
+            got = _wave(ctx, caster, ctx.evaluator(ekind), pos, quat)
+            want = oc.compute_gains(O.eval_params(ekind), pos, quat, n_threads=8)
+            _check_wave(got, want)
+    assert got["n_visible"].max() > 0
+    ctx.close()
+
+
+def test_wave_dense_volume_tracks_map_edits(capi, O):
+    """Uploads that grow the block box, overwrites and removals between casts: the dense meta
+    volume the wavefront kernel reads must follow every edit."""
+    from mav_active_3d_planning_b200 import synth
+    m = synth.room_map(0.2)
+    rng = np.random.default_rng(17)
+    order = rng.permutation(m.n_blocks)
+    ctx = capi.Context(0)
+    ctx.map_config(m.voxel_size, m.vps)
+    om = O.OracleMap(m.voxel_size, m.vps)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    oc = om.caster("IterativeRayCaster", **CAM_BASE)
+    ev, ep = ctx.evaluator("VoxelTypeEvaluator"), O.eval_params("VoxelTypeEvaluator")
+    pos, quat = synth.candidate_views(m, 16, seed=9)
+
+    def check():
+        _check_wave(_wave(ctx, caster, ev, pos, quat), oc.compute_gains(ep, pos, quat, n_threads=8))
+
+    third = m.n_blocks // 3
+    for part in (order[:third], order[third:2 * third], order[2 * third:]):   # box grows
+        for mm in (ctx, om):
+            mm.upload_blocks(m.block_idx[part], m.dist[part], m.observed[part])
+        check()
+    sel = order[:m.n_blocks // 8]                                             # overwrite in place
+    nd = (m.dist[sel] * 0.5).astype(np.float32)
+    for mm in (ctx, om):
+        mm.upload_blocks(m.block_idx[sel], nd, np.ones_like(m.observed[sel]))
+    check()
+    rem = order[m.n_blocks // 8: m.n_blocks // 4]                             # remove
+    for mm in (ctx, om):
+        mm.remove_blocks(m.block_idx[rem])
+    check()
+    far = np.array([[60, 2, 1], [-9, 0, 0]], np.int32)                        # far blocks: new box
+    fd = np.full((2, m.vps ** 3), 0.9, np.float32)
+    for mm in (ctx, om):
+        mm.upload_blocks(far, fd, np.ones((2, m.vps ** 3), np.uint8))
+    check()
+    ctx.clear()
+    for mm in (ctx,):
+        mm.upload_blocks(m.block_idx[sel], m.dist[sel], m.observed[sel])
+    om2 = O.OracleMap(m.voxel_size, m.vps)
+    om2.upload_blocks(m.block_idx[sel], m.dist[sel], m.observed[sel])
+    _check_wave(_wave(ctx, caster, ev, pos, quat),
+                om2.caster("IterativeRayCaster", **CAM_BASE).compute_gains(ep, pos, quat, n_threads=8))
+    ctx.close()
+
+
 def test_wave_kernel_empty_map_and_far_poses(capi, O):
     """Unallocated space and poses beyond the 20-bit voxel-key range (scan-order re-evaluation)."""
     ctx = capi.Context(0)
