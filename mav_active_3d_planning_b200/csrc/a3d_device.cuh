@@ -301,6 +301,30 @@ static __device__ __noinline__ int voxel_state_generic(const MapView& m, float p
 // ---- fast path ----------------------------------------------------------------------------------
 constexpr uint32_t kWordNoBlock = 0x00020000u;  // centre state UNKNOWN, not observed, all cells UNKNOWN
 
+// State of the float point p inside a MIXED interpolation cell: voxel v (in range) of allocated block
+// b (slot), octant sc.  Reads the 8 corners from the padded cube and interpolates like the reference.
+__device__ __forceinline__ int mixed_cell_state(const MapView& m, const CenterTables& ct,
+                                                const float (&p)[3], const int (&b)[3],
+                                                const float (&origin)[3], int slot, const int (&v)[3],
+                                                int sc) {
+  const int base[3] = {v[0] - (sc & 1), v[1] - ((sc >> 1) & 1), v[2] - (sc >> 2)};
+  float d[8], o[3];
+  const float* __restrict__ dp = m.dist + padded_index(m, slot, base[0], base[1], base[2]);
+  const int P = m.P, PP = m.P * m.P;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    d[i] = __ldg(dp + ((i >> 2) & 1) + ((i >> 1) & 1) * P + (i & 1) * PP);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    // corner 0 position as the reference forms it: in the shifted block's own frame
+    const float voxel_pos = base[k] < 0
+                                ? __fadd_rn(origin_point(b[k] - 1, m.bs_f), ct.f[m.vps])
+                                : __fadd_rn(origin[k], ct.f[base[k] + 1]);
+    o[k] = __fmul_rn(__fsub_rn(p[k], voxel_pos), m.vs_inv_f);
+  }
+  return state_from_distance(m, true, interp8(d, o));
+}
+
 // State of the float point p whose block index b, block origin and slot (= find_slot(b), may be
 // < 0) the caller already has.  Uses the cell class when it is definite, else the 8 padded-cube
 // corners; falls back to the generic path for artefact indices.  Also returns the voxel index v the
@@ -330,22 +354,7 @@ __device__ __forceinline__ int voxel_state_in_block(const MapView& m, const Cent
   *word_out = word;
   const int cls = (word >> (2 * sc)) & 3;
   if (cls != kCellMixed) return cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
-  const int base[3] = {v[0] - (sc & 1), v[1] - ((sc >> 1) & 1), v[2] - (sc >> 2)};
-  float d[8], o[3];
-  const float* __restrict__ dp = m.dist + padded_index(m, slot, base[0], base[1], base[2]);
-  const int P = m.P, PP = m.P * m.P;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    d[i] = __ldg(dp + ((i >> 2) & 1) + ((i >> 1) & 1) * P + (i & 1) * PP);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    // corner 0 position as the reference forms it: in the shifted block's own frame
-    const float voxel_pos = base[k] < 0
-                                ? __fadd_rn(origin_point(b[k] - 1, m.bs_f), ct.f[m.vps])
-                                : __fadd_rn(origin[k], ct.f[base[k] + 1]);
-    o[k] = __fmul_rn(__fsub_rn(p[k], voxel_pos), m.vs_inv_f);
-  }
-  return state_from_distance(m, true, interp8(d, o));
+  return mixed_cell_state(m, ct, p, b, origin, slot, v, sc);
 }
 
 __device__ __forceinline__ int voxel_state(const MapView& m, const CenterTables& ct, const D3& pd) {

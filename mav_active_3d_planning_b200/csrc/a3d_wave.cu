@@ -281,6 +281,20 @@ __device__ __noinline__ SampleInfo sample_slow(const MapView& m, const CenterTab
   return si;
 }
 
+// State of a certified sample whose interpolation cell straddles the occupied threshold: the
+// literal trilinear interpolation over the cell's 8 corners.
+__device__ __noinline__ int mixed_state(const MapView& m, const CenterTables& ct, float pf0, float pf1,
+                                        float pf2, int g0, int g1, int g2, int sc) {
+  const float pf[3] = {pf0, pf1, pf2};
+  const int vmask = m.vps - 1;
+  const int b[3] = {g0 >> m.vps_shift, g1 >> m.vps_shift, g2 >> m.vps_shift};
+  const int v[3] = {g0 & vmask, g1 & vmask, g2 & vmask};
+  float origin[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) origin[a] = origin_point(b[a], m.bs_f);
+  return mixed_cell_state(m, ct, pf, b, origin, find_slot(m, b[0], b[1], b[2]), v, sc);
+}
+
 // One sample, literally as the reference computes it (voxblox index arithmetic on the float point
 // for the state, on the double point for the voxel centre).  Used for the samples the margin test
 // of ray_step() cannot certify.
@@ -382,6 +396,25 @@ __device__ __forceinline__ Prefetched sample_prepare(const MapView& m, const Vie
     g[a] = (__float_as_int(s) - 0x4B400000) + below;
     sc |= (below + 1) << a;  // bit set: the point is below the voxel centre on this axis
   }
+  if (!safe) {
+    // Margin not met: the reference's own index arithmetic, inline.  If it stays in range and
+    // getVoxelState's voxel equals getVoxelCenter's, the sample is an ordinary one after all.
+    int sc_l = 0;
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int bi = grid_index(pf[a], m.bs_inv_f);
+      const float origin = origin_point(bi, m.bs_f);
+      const int vs = grid_index(__fsub_rn(pf[a], origin), m.vs_inv_f);
+      const int vi = grid_index(__double2float_rn(__dsub_rn(pp[a], static_cast<double>(origin))), m.vs_inv_f);
+      ok &= (static_cast<unsigned>(vs) < static_cast<unsigned>(m.vps)) & (vs == vi);
+      const float centre = __fadd_rn(origin, center_point(min(max(vs, 0), m.vps - 1), m.vs_f));
+      sc_l |= (__fsub_rn(pf[a], centre) < 0.0f) ? (1 << a) : 0;
+      g[a] = bi * m.vps + vs;
+    }
+    sc = sc_l;
+    safe = ok && m.vps_shift >= 0 && vw.delta == vw.delta;  // (NaN margin: certification is off)
+  }
   Prefetched nx;
   nx.g0 = g[0];
   nx.g1 = g[1];
@@ -448,12 +481,10 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     si.cs = centre_state_from_word(word);
     si.id = Ident{g[0], g[1], g[2]};
     if (cls == kCellMixed) {
-      unsigned bad = 0;
       double pp[3];
       float pf[3];
       sample_point(vw, lt, d_this, pp, pf);
-      si = sample_slow(m, ct, pf[0], pf[1], pf[2], b0, b1, b2, find_slot(m, b0, b1, b2), v0, v1, v2, &bad);
-      if (bad) lt.inexact = 1;
+      si.st = mixed_state(m, ct, pf[0], pf[1], pf[2], g[0], g[1], g[2], sc);
     }
     if (kNeedCentre || (e.bv_is_setup && !bvg.fast)) {
       cc.x = __dadd_rn(static_cast<double>(origin_point(b0, m.bs_f)), ct.d[v0 + 1]);
@@ -517,10 +548,13 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
 }
 
 #ifndef A3D_WAVE_STEPS
-#define A3D_WAVE_STEPS 16  // samples marched between two rounds of lane bookkeeping
+#define A3D_WAVE_STEPS 64  // most samples marched between two rounds of lane bookkeeping
+#endif
+#ifndef A3D_WAVE_IDLE_BREAK
+#define A3D_WAVE_IDLE_BREAK 12  // idle lanes that end a round early (32: never)
 #endif
 #ifndef A3D_WAVE_MARK_STEPS
-#define A3D_WAVE_MARK_STEPS 24  // ... while marking parts are in flight (scheduler warp)
+#define A3D_WAVE_MARK_STEPS 64  // ... while marking parts are in flight (scheduler warp)
 #endif
 
 }  // namespace
@@ -824,6 +858,10 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
               run_left -= __popc(__ballot_sync(kFull, fin_mark));
               if (run_left == 0) break;
             }
+#if A3D_WAVE_IDLE_BREAK < 32
+            // enough lanes ran out of ray: hand out new work now instead of idling to the round's end
+            if (!supply_done && __popc(__ballot_sync(kFull, role == 0)) >= A3D_WAVE_IDLE_BREAK) break;
+#endif
           }
           n_run = run_left;
           __syncwarp();
