@@ -149,6 +149,7 @@ struct Prefetched {
 // thread: the kernel is register-bound (measured: every spilled value costs more than these loads).
 struct LaneTable {
   double dir[3][kWaveThreads];  // world direction of the lane's ray
+  double d_end[kWaveThreads];   // the part ends before this distance
   int r[kWaveThreads];          // ray id
   int mark[kWaveThreads];       // index of the lane's marking part in the diagonal's list
   unsigned inexact;             // any lane met a case the scan-order kernel must decide
@@ -441,27 +442,26 @@ __device__ __forceinline__ Prefetched sample_prepare(const MapView& m, const Vie
 }
 
 // One sample of the lane's ray: folds the prepared sample rs.nx (distance rs.d) and prepares the
-// next one.  Returns true when the part is finished (hit or end reached); *hit_d = distance of the
-// OCCUPIED sample that ended it (unchanged otherwise).
-// rec_base + part_off + ray: index of this part's record.  Precondition: rs.d < d_end (and rs.nx
-// prepared for rs.d when prefetching).
+// next one.  Returns true when the part is finished (hit or end reached) and then leaves in rs.d the
+// distance of the OCCUPIED sample that ended it, or -1.
+// rec_base + (marking part ? 0 : n_rays) + ray: index of this part's record.  Precondition:
+// rs.d < lt.d_end (and rs.nx prepared for rs.d when prefetching).
 template <int CASTER, int EVAL, bool DIGEST>
 __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
                                          const ViewShared& vw, const BvGrid& bvg, const double step,
-                                         const double d_end, RayState& rs, LaneTable& lt,
-                                         LaneCounters& lc, const Records& rec, size_t rec_base,
-                                         int part_off, double* hit_d) {
+                                         RayState& rs, LaneTable& lt, LaneCounters& lc,
+                                         const Records& rec, size_t rec_base, int role, int n_rays) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   const double d_this = rs.d;
 #if A3D_WAVE_PREFETCH
   const Prefetched cur = rs.nx;
   rs.d = __dadd_rn(d_this, step);
-  const bool more = rs.d < d_end;
+  const bool more = rs.d < lt.d_end[threadIdx.x];
   if (more) rs.nx = sample_prepare(m, vw, lt, rs.d);  // its load overlaps the fold below
 #else
   const Prefetched cur = sample_prepare(m, vw, lt, d_this);
   rs.d = __dadd_rn(d_this, step);
-  const bool more = rs.d < d_end;
+  const bool more = rs.d < lt.d_end[threadIdx.x];
 #endif
   lc.n_samp++;
   const int g[3] = {cur.g0, cur.g1, cur.g2};
@@ -534,21 +534,25 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
   if (first) {
     // record of the part's first entry, written once
     unsigned bad = 0;
-    const size_t rec_at = rec_base + part_off + lt.r[threadIdx.x];
+    const size_t rec_at = rec_base + (role == 2 ? 0 : n_rays) + lt.r[threadIdx.x];
     __stcs(&rec.first_key[rec_at], pack_key(si.id, &bad));
     if (bad) lt.inexact = 1;
     __stcs(&rec.info[rec_at], static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0)));
     if (DIGEST) rec.first_hash[rec_at] = h;
   }
   if (si.st == 0) {
-    *hit_d = d_this;
+    rs.d = d_this;
     return true;
   }
+  if (!more) rs.d = -1.0;
   return !more;
 }
 
 #ifndef A3D_WAVE_STEPS
 #define A3D_WAVE_STEPS 64  // most samples marched between two rounds of lane bookkeeping
+#endif
+#ifndef A3D_WAVE_DRY_STEPS
+#define A3D_WAVE_DRY_STEPS 8  // round length while idle lanes cannot be refilled
 #endif
 #ifndef A3D_WAVE_IDLE_BREAK
 #define A3D_WAVE_IDLE_BREAK 12  // idle lanes that end a round early (32: never)
@@ -742,6 +746,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
 
           // ---- 2. give work to idle lanes: marking parts first, then leaf parts ----
           const unsigned idle = __ballot_sync(kFull, role == 0);
+          bool starved = false;  // lanes stayed idle: nothing to hand out right now
           if (idle) {
             int n_idle = __popc(idle);
             const int rank = __popc(idle & lt_mask);
@@ -758,7 +763,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                 rs.nx = sample_prepare(m, vw, lt, rs.d);
 #endif
                 start_s[it >> 8] = static_cast<uint8_t>(ms);  // read by leaf lanes after the diagonal
-                s_mark_hit[mark_idx] = -1.0;
+                lt.d_end[threadIdx.x] = d_mark_end;
                 role = 2;  // split[s] < split[n-1] for s < n-1: at least one sample
               }
               mark_head += take_mark;
@@ -807,6 +812,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                   d0 = c.leaf_d0[s0];  // accumulated distance at which a ray started in s0 enters section n-1
                 }
                 ray_begin(rs, lt, c, vw, r, d0);
+                lt.d_end[threadIdx.x] = d_leaf_end;
                 role = (rs.d < d_leaf_end) ? 1 : 0;
 #if A3D_WAVE_PREFETCH
                 if (role) rs.nx = sample_prepare(m, vw, lt, rs.d);
@@ -815,6 +821,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
               const int taken = min(n_idle, pend_count);
               pend_head = (pend_head + taken) % kPendCap;
               pend_count -= taken;
+              starved = taken < n_idle;
               __syncwarp();
             }
           }
@@ -827,43 +834,38 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
             continue;
           }
 
-          // ---- 4. a few samples per busy lane ----
-          // The scheduler warp stays in the loop until the marking parts in flight are done (bounded)
-          // and leaves it the moment they are, so that the next anti-diagonal opens without delay.
-          int run_left = n_run;
-          const int max_it = (scheduler && run_left > 0) ? A3D_WAVE_MARK_STEPS : A3D_WAVE_STEPS;
+          // ---- 4. samples: every busy lane marches its own part ----
+          // A round ends when (a) the marking parts in flight are all done, so that the scheduler can
+          // open the next anti-diagonal without delay, (b) enough lanes ran out of ray and there is
+          // work to hand out, or (c) after max_it samples.  While the supply is dry (the scheduler
+          // has not released more rays yet) rounds are short instead.
+          const bool marks_running = scheduler && n_run > 0;
+          const int max_it = marks_running ? A3D_WAVE_MARK_STEPS
+                                           : ((starved && !supply_done) ? A3D_WAVE_DRY_STEPS : A3D_WAVE_STEPS);
+          const int idle_limit = (starved || supply_done) ? 33 : A3D_WAVE_IDLE_BREAK;
 #pragma unroll 1
           for (int it = 0; it < max_it; ++it) {
-            bool fin_mark = false;
-            if (role != 0) {
-              double hit_d = -1.0;
-              if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, bvg, step, role == 2 ? d_mark_end : d_leaf_end,
-                                                 rs, lt, lc, ws.rec, cta_base * 2, role == 2 ? 0 : n_rays,
-                                                 &hit_d)) {
-                if (rs.prev.g0 != kNoIdent) {
-                  unsigned bad = 0;
-                  const size_t rec_at =
-                      cta_base * 2 + (role == 2 ? 0 : static_cast<size_t>(n_rays)) + lt.r[threadIdx.x];
-                  __stcs(&ws.rec.last_key[rec_at], pack_key(rs.prev, &bad));
-                  if (bad) lt.inexact = 1;
-                }
-                if (role == 2) {
-                  s_mark_hit[lt.mark[threadIdx.x]] = hit_d;
-                  fin_mark = true;
-                }
-                role = 0;
-              }
+            if (role > 0) {
+              if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, bvg, step, rs, lt, lc, ws.rec, cta_base * 2,
+                                                 role, n_rays))
+                role = -role;  // finished: bookkeeping after the round
             }
-            if (scheduler && run_left > 0) {
-              run_left -= __popc(__ballot_sync(kFull, fin_mark));
-              if (run_left == 0) break;
-            }
-#if A3D_WAVE_IDLE_BREAK < 32
-            // enough lanes ran out of ray: hand out new work now instead of idling to the round's end
-            if (!supply_done && __popc(__ballot_sync(kFull, role == 0)) >= A3D_WAVE_IDLE_BREAK) break;
-#endif
+            if (marks_running && __popc(__ballot_sync(kFull, role == -2)) == n_run) break;
+            if (__popc(__ballot_sync(kFull, role <= 0)) >= idle_limit) break;
           }
-          n_run = run_left;
+          // parts that ended in this round: last key for the fix-up, hit distance for the marks
+          n_run -= __popc(__ballot_sync(kFull, role == -2));
+          if (role < 0) {
+            if (rs.prev.g0 != kNoIdent) {
+              unsigned bad = 0;
+              const size_t rec_at =
+                  cta_base * 2 + (role == -2 ? 0 : static_cast<size_t>(n_rays)) + lt.r[threadIdx.x];
+              __stcs(&ws.rec.last_key[rec_at], pack_key(rs.prev, &bad));
+              if (bad) lt.inexact = 1;
+            }
+            if (role == -2) s_mark_hit[lt.mark[threadIdx.x]] = rs.d;
+            role = 0;
+          }
           __syncwarp();
         }
       }
