@@ -149,6 +149,8 @@ struct a3d_ctx {
       m.vol_lo[k] = dir_lo[k] * vps;
       m.vol_n[k] = dir_n[k] * static_cast<uint32_t>(vps);
     }
+    m.vol_bx = m.vol_n[0] >> 2;
+    m.vol_by = m.vol_n[1] >> 2;
     m.mask = static_cast<uint32_t>(h_table.size() - 1);
     m.vps = vps;
     m.nv = nv;

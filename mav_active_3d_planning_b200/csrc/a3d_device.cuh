@@ -74,6 +74,7 @@ struct MapView {
   const uint32_t* __restrict__ vol;
   int32_t vol_lo[3];                 // first voxel coordinate of the box
   uint32_t vol_n[3];                 // box size in voxels
+  uint32_t vol_bx, vol_by;           // box size in bricks along x, y (vol_n >> 2)
   float fast_c0;                     // absolute part of the index-certification margin (a3d_wave.cu)
   float vs_f, vs_inv_f, bs_f, bs_inv_f;
   double c_vs;                       // double(vs_f), VoxbloxMap::c_voxel_size_
@@ -157,7 +158,7 @@ __device__ __forceinline__ int mword_offset(const MapView& m, int x, int y, int 
 // Offset of box-relative voxel (u0,u1,u2) in the dense meta volume: 4x4x2 bricks of 32 words (one
 // 128-byte line), bricks x fastest.  vol_n[] are multiples of vps, vps a power of two >= 4.
 __device__ __forceinline__ uint32_t vol_offset(const MapView& m, uint32_t u0, uint32_t u1, uint32_t u2) {
-  const uint32_t brick = ((u2 >> 1) * (m.vol_n[1] >> 2) + (u1 >> 2)) * (m.vol_n[0] >> 2) + (u0 >> 2);
+  const uint32_t brick = ((u2 >> 1) * m.vol_by + (u1 >> 2)) * m.vol_bx + (u0 >> 2);
   return (brick << 5) | ((u2 & 1u) << 4) | ((u1 & 3u) << 2) | (u0 & 3u);
 }
 

@@ -176,6 +176,9 @@ struct ViewShared {  // per-view constants, one copy per CTA in shared memory
 struct BvGrid {
   int lo[3], hi[3];
   int fast;
+  int mode;  // 0: no volume, 1: test on voxel coordinates (lo/hi), 2: bv_contains() on the centre
+  // what one retained entry of fold category 0..2 adds to LaneCounters::packed; [3]: nothing
+  unsigned long long inc[4];
 };
 
 __device__ __forceinline__ double centre_of(const MapView& m, const CenterTables& ct, int g) {
@@ -222,6 +225,10 @@ __device__ void init_bv_grid(const MapView& m, const CenterTables& ct, const Eva
   g->lo[a] = lo;
   g->hi[a] = hi;
   if (!ok) g->fast = 0;
+  g->inc[a] = 1ull << (kFieldBits * a);
+  if (a == 0) g->inc[3] = 0;
+  __syncwarp(0x7u);  // threads 0..2 (the others left above)
+  if (a == 0) g->mode = !e.bv_is_setup ? 0 : (g->fast ? 1 : 2);
 }
 
 __device__ __forceinline__ void ray_begin(RayState& rs, LaneTable& lt, const CasterView& c,
@@ -448,8 +455,8 @@ __device__ __forceinline__ Prefetched sample_prepare(const MapView& m, const Vie
 // rs.d < lt.d_end (and rs.nx prepared for rs.d when prefetching).
 template <int CASTER, int EVAL, bool DIGEST>
 __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
-                                         const ViewShared& vw, const BvGrid& bvg, const double step,
-                                         RayState& rs, LaneTable& lt, LaneCounters& lc,
+                                         const ViewShared& vw, const BvGrid& bvg, const int bv_mode,
+                                         const double step, RayState& rs, LaneTable& lt, LaneCounters& lc,
                                          const Records& rec, size_t rec_base, int role, int n_rays) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   const double d_this = rs.d;
@@ -486,12 +493,12 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
       sample_point(vw, lt, d_this, pp, pf);
       si.st = mixed_state(m, ct, pf[0], pf[1], pf[2], g[0], g[1], g[2], sc);
     }
-    if (kNeedCentre || (e.bv_is_setup && !bvg.fast)) {
+    if (kNeedCentre || bv_mode == 2) {
       cc.x = __dadd_rn(static_cast<double>(origin_point(b0, m.bs_f)), ct.d[v0 + 1]);
       cc.y = __dadd_rn(static_cast<double>(origin_point(b1, m.bs_f)), ct.d[v1 + 1]);
       cc.z = __dadd_rn(static_cast<double>(origin_point(b2, m.bs_f)), ct.d[v2 + 1]);
-      if (e.bv_is_setup) in_bv = bv_contains(e, cc);  // simulated_sensor_evaluator.cpp:50-57
-    } else if (e.bv_is_setup) {
+      if (bv_mode) in_bv = bv_contains(e, cc);  // simulated_sensor_evaluator.cpp:50-57
+    } else if (bv_mode) {
       in_bv = (g[0] >= bvg.lo[0]) & (g[0] <= bvg.hi[0]) & (g[1] >= bvg.lo[1]) & (g[1] <= bvg.hi[1]) &
               (g[2] >= bvg.lo[2]) & (g[2] <= bvg.hi[2]);
     }
@@ -505,7 +512,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     if (bad) lt.inexact = 1;
     si = out.si;
     cc = out.cc;
-    if (e.bv_is_setup) in_bv = bv_contains(e, cc);
+    if (bv_mode) in_bv = bv_contains(e, cc);
   }
   const bool emit = ITER || si.st != 0;
   const bool keep = emit & in_bv &
@@ -525,7 +532,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
       }
     }
   }
-  lc.packed += static_cast<unsigned long long>(keep) << (kFieldBits * cat);
+  lc.packed += bvg.inc[keep ? cat : 3];
   unsigned long long h = 0;
   if (DIGEST) {
     h = keep ? digest_entry(cc) : 0ull;
@@ -594,6 +601,8 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   init_center_tables(m, &ct);
   __syncthreads();
   if (threadIdx.x < 32) init_bv_grid(m, ct, e, &bvg);
+  __syncthreads();
+  const int bv_mode = bvg.mode;
 
   const size_t cta_base = static_cast<size_t>(blockIdx.x) * ws.rays_stride;
   uint32_t* const table = ws.table + cta_base;  // written by atomics, read with __ldcg
@@ -846,12 +855,13 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
 #pragma unroll 1
           for (int it = 0; it < max_it; ++it) {
             if (role > 0) {
-              if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, bvg, step, rs, lt, lc, ws.rec, cta_base * 2,
+              if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, bvg, bv_mode, step, rs, lt, lc, ws.rec, cta_base * 2,
                                                  role, n_rays))
                 role = -role;  // finished: bookkeeping after the round
             }
-            if (marks_running && __popc(__ballot_sync(kFull, role == -2)) == n_run) break;
-            if (__popc(__ballot_sync(kFull, role <= 0)) >= idle_limit) break;
+            bool stop = __popc(__ballot_sync(kFull, role <= 0)) >= idle_limit;
+            if (marks_running) stop |= __popc(__ballot_sync(kFull, role == -2)) == n_run;
+            if (stop) break;
           }
           // parts that ended in this round: last key for the fix-up, hit distance for the marks
           n_run -= __popc(__ballot_sync(kFull, role == -2));
