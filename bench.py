@@ -36,7 +36,7 @@ WORKLOAD = ("cfg2: room 20x20x10 m @0.1 m voxels (vps 16), IterativeRayCaster 32
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--views", type=int, default=4096, help="candidate segments per GPU")
