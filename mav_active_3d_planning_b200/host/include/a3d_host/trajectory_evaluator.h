@@ -6,6 +6,9 @@
 //   NaiveEvaluator              .../naive_evaluator.h, .cpp:15-38
 //   FrontierEvaluator           .../frontier_evaluator.h, .cpp:15-124
 //   VoxelWeightEvaluator        .../voxel_weight_evaluator.h, .cpp:15-83
+//   YawPlanningEvaluator        .../yaw_planning_evaluator.h:18-72, .cpp:13-160
+//   SimpleYawPlanningEvaluator  .../simple_yaw_planning_evaluator.h, .cpp:14-43
+//   ContinuousYawPlanningEvaluator  .../continuous_yaw_planning_evaluator.h, .cpp:19-107
 // computeGains() is the additive batch entry point: the reference evaluates one
 // segment per call (online_planner.cpp:414-416); a B200 wants thousands per launch.
 #pragma once
@@ -176,6 +179,79 @@ class VoxelWeightEvaluator : public FrontierEvaluator {
   static ModuleFactoryRegistry::Registration<VoxelWeightEvaluator> registration;
   double p_frontier_voxel_weight_, p_min_impact_factor_, p_new_voxel_weight_, p_ray_angle_x_,
       p_ray_angle_y_;
+};
+
+// What the yaw-planning evaluators store in TrajectorySegment::info: every oriented copy of the
+// segment (yaw_planning_evaluator.h:64-71).
+struct YawPlanningInfo : public TrajectoryInfo {
+  virtual ~YawPlanningInfo() = default;
+  std::vector<TrajectorySegment> orientations;
+  int active_orientation = 0;
+};
+
+// Evaluates n_directions yaw copies of a segment with the following evaluator and keeps the best.
+// The copies of one segment — or of a whole batch of segments (computeGains) — are evaluated in ONE
+// launch when the following evaluator is a SimulatedSensorEvaluator that can batch (SURVEY.md
+// §8(f)-1: "the 12 yaw copies as one mini-batch"); otherwise one by one like the reference.
+class YawPlanningEvaluator : public TrajectoryEvaluator {
+ public:
+  explicit YawPlanningEvaluator(PlannerI& planner);  // NOLINT
+  bool computeGain(TrajectorySegment* traj_in) override;
+  bool computeCost(TrajectorySegment* traj_in) override;
+  bool computeValue(TrajectorySegment* traj_in) override;
+  int selectNextBest(TrajectorySegment* traj_in) override;
+  bool updateSegment(TrajectorySegment* segment) override;
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+  bool checkParamsValid(std::string* error_message) override;
+  // additive: computeGain for many segments, all their orientations in one launch
+  virtual bool computeGains(const std::vector<TrajectorySegment*>& segments);
+  TrajectoryEvaluator* followingEvaluator() { return following_evaluator_.get(); }
+
+ protected:
+  std::unique_ptr<TrajectoryEvaluator> following_evaluator_;
+  int p_n_directions_;
+  bool p_select_by_value_;
+  double p_update_range_;  // update only gains within this distance (0.0: all, < 0: none)
+  double p_update_gain_;   // update only gains above this
+  bool p_batch_orientations_;     // additive parameter, default true
+  bool p_keep_visible_voxels_;    // additive: batch path keeps each copy's voxel list on the device
+
+  virtual double sampleYaw(double original_yaw, int sample) = 0;
+  virtual void setTrajectoryYaw(TrajectorySegment* segment, double start_yaw, double target_yaw) = 0;
+  virtual void setBestYaw(TrajectorySegment* segment);
+  // creates info->orientations of the segment (yaw_planning_evaluator.cpp:49-60, without evaluating)
+  void spawnOrientations(TrajectorySegment* traj_in);
+  // gain (and cost/value if select_by_value) of the given oriented copies
+  bool evaluateOrientations(const std::vector<TrajectorySegment*>& copies);
+};
+
+class SimpleYawPlanningEvaluator : public YawPlanningEvaluator {
+ public:
+  explicit SimpleYawPlanningEvaluator(PlannerI& planner) : YawPlanningEvaluator(planner) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+
+ protected:
+  double sampleYaw(double original_yaw, int sample_number) override;
+  void setTrajectoryYaw(TrajectorySegment* segment, double start_yaw, double target_yaw) override;
+  static ModuleFactoryRegistry::Registration<SimpleYawPlanningEvaluator> registration;
+  bool p_visualize_followup_;
+};
+
+// Splits the full yaw circle into n_directions sections of which n_sections_fov adjacent ones make up
+// the sensor's field of view; the gain of a yaw is the sum over its sections.
+class ContinuousYawPlanningEvaluator : public YawPlanningEvaluator {
+ public:
+  explicit ContinuousYawPlanningEvaluator(PlannerI& planner) : YawPlanningEvaluator(planner) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+  bool computeGain(TrajectorySegment* traj_in) override;
+
+ protected:
+  double sampleYaw(double original_yaw, int sample_number) override;
+  void setTrajectoryYaw(TrajectorySegment* segment, double start_yaw, double target_yaw) override;
+  void setBestYaw(TrajectorySegment* segment) override;
+  static ModuleFactoryRegistry::Registration<ContinuousYawPlanningEvaluator> registration;
+  bool p_visualize_followup_;
+  int p_n_sections_fov_;
 };
 
 }  // namespace trajectory_evaluator

@@ -4,6 +4,7 @@
 // ownership / error conventions.  Reference citations are relative to the reference checkout.
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -862,6 +863,234 @@ void VoxelWeightEvaluator::fillEvalParams(void* ptr) {
   p->new_voxel_weight = p_new_voxel_weight_;
   p->ray_angle_x = p_ray_angle_x_;
   p->ray_angle_y = p_ray_angle_y_;
+}
+
+// ---- yaw planning -------------------------------------------------------------------------------
+namespace {
+double angleScaled(double angle) {  // tools/defaults.cpp:11-14
+  angle = std::fmod(angle, 2.0 * M_PI);
+  return angle + 2.0 * M_PI * (angle < 0);
+}
+}  // namespace
+
+YawPlanningEvaluator::YawPlanningEvaluator(PlannerI& planner)
+    : TrajectoryEvaluator(planner), p_n_directions_(4), p_select_by_value_(false), p_update_range_(-1.0),
+      p_update_gain_(0.0), p_batch_orientations_(true), p_keep_visible_voxels_(false) {}
+
+void YawPlanningEvaluator::setupFromParamMap(Module::ParamMap* param_map) {  // yaw_planning_evaluator.cpp:17-38
+  setParam<int>(param_map, "n_directions", &p_n_directions_, 4);
+  setParam<bool>(param_map, "select_by_value", &p_select_by_value_, false);
+  setParam<double>(param_map, "update_range", &p_update_range_, -1.0);  // default is no updates
+  setParam<double>(param_map, "update_gain", &p_update_gain_, 0.0);
+  setParam<bool>(param_map, "batch_orientations", &p_batch_orientations_, true);
+  setParam<bool>(param_map, "keep_visible_voxels", &p_keep_visible_voxels_, false);
+  planner_.getFactory().registerLinkableModule("YawPlanningEvaluator", this);
+  std::string args;
+  const std::string param_ns = (*param_map)["param_namespace"];
+  setParam<std::string>(param_map, "following_evaluator_args", &args, param_ns + "/following_evaluator");
+  following_evaluator_ =
+      planner_.getFactory().createModule<TrajectoryEvaluator>(args, planner_, verbose_modules_);
+  TrajectoryEvaluator::setupFromParamMap(param_map);
+}
+
+bool YawPlanningEvaluator::checkParamsValid(std::string* error_message) {
+  if (p_n_directions_ < 1) {
+    *error_message = "n_directions expected > 0";
+    return false;
+  }
+  return TrajectoryEvaluator::checkParamsValid(error_message);
+}
+
+void YawPlanningEvaluator::spawnOrientations(TrajectorySegment* traj_in) {
+  const double start_yaw = traj_in->trajectory.front().getYaw();
+  const double original_yaw = traj_in->trajectory.back().getYaw();
+  traj_in->info = std::make_unique<YawPlanningInfo>();
+  auto* info = static_cast<YawPlanningInfo*>(traj_in->info.get());
+  info->active_orientation = 0;
+  info->orientations.reserve(p_n_directions_);
+  for (int i = 0; i < p_n_directions_; ++i) {
+    info->orientations.push_back(traj_in->shallowCopy());
+    setTrajectoryYaw(&info->orientations.back(), start_yaw, sampleYaw(original_yaw, i));
+  }
+}
+
+bool YawPlanningEvaluator::evaluateOrientations(const std::vector<TrajectorySegment*>& copies) {
+  if (copies.empty()) return true;
+  bool done = false;
+  auto* sim = dynamic_cast<SimulatedSensorEvaluator*>(following_evaluator_.get());
+  if (p_batch_orientations_ && sim)
+    done = p_keep_visible_voxels_ ? sim->computeGainsStored(copies) : sim->computeGains(copies);
+  bool ok = true;
+  if (!done)  // the reference's loop (yaw_planning_evaluator.cpp:57-60)
+    for (TrajectorySegment* c : copies) ok = following_evaluator_->computeGain(c) && ok;
+  if (p_select_by_value_)
+    for (TrajectorySegment* c : copies) {
+      following_evaluator_->computeCost(c);
+      following_evaluator_->computeValue(c);
+    }
+  return ok;
+}
+
+bool YawPlanningEvaluator::computeGain(TrajectorySegment* traj_in) {  // yaw_planning_evaluator.cpp:48-71
+  spawnOrientations(traj_in);
+  auto* info = static_cast<YawPlanningInfo*>(traj_in->info.get());
+  std::vector<TrajectorySegment*> copies;
+  for (auto& o : info->orientations) copies.push_back(&o);
+  evaluateOrientations(copies);
+  setBestYaw(traj_in);
+  return true;
+}
+
+bool YawPlanningEvaluator::computeGains(const std::vector<TrajectorySegment*>& segments) {
+  std::vector<TrajectorySegment*> copies;
+  for (TrajectorySegment* seg : segments) {
+    spawnOrientations(seg);
+    for (auto& o : static_cast<YawPlanningInfo*>(seg->info.get())->orientations) copies.push_back(&o);
+  }
+  const bool ok = evaluateOrientations(copies);
+  for (TrajectorySegment* seg : segments) setBestYaw(seg);
+  return ok;
+}
+
+void YawPlanningEvaluator::setBestYaw(TrajectorySegment* segment) {  // yaw_planning_evaluator.cpp:73-110
+  auto* info = static_cast<YawPlanningInfo*>(segment->info.get());
+  double min_gain = std::numeric_limits<double>::max();
+  double max_gain = std::numeric_limits<double>::lowest();
+  int max_index = 0;
+  for (size_t i = 0; i < info->orientations.size(); ++i) {
+    const double gain = p_select_by_value_ ? info->orientations[i].value : info->orientations[i].gain;
+    if (gain > max_gain) {
+      max_gain = gain;
+      max_index = static_cast<int>(i);
+    } else if (gain < min_gain) {
+      min_gain = gain;
+    }
+  }
+  double best_yaw;
+  if (max_gain > min_gain) {
+    best_yaw = angleScaled(info->orientations[max_index].trajectory.back().getYaw());
+  } else {  // indifferent, use direction of travel
+    const Eigen::Vector3d direction =
+        segment->trajectory.back().position_W - segment->trajectory.front().position_W;
+    best_yaw = angleScaled(std::atan2(direction[1], direction[0]));
+  }
+  setTrajectoryYaw(segment, segment->trajectory.front().getYaw(), best_yaw);
+  info->active_orientation = max_index;
+  segment->gain = info->orientations[max_index].gain;
+  if (p_select_by_value_) {
+    segment->cost = info->orientations[max_index].cost;
+    segment->value = info->orientations[max_index].value;
+  }
+}
+
+bool YawPlanningEvaluator::computeCost(TrajectorySegment* traj_in) {
+  return following_evaluator_->computeCost(traj_in);
+}
+bool YawPlanningEvaluator::computeValue(TrajectorySegment* traj_in) {
+  return following_evaluator_->computeValue(traj_in);
+}
+int YawPlanningEvaluator::selectNextBest(TrajectorySegment* traj_in) {
+  return following_evaluator_->selectNextBest(traj_in);
+}
+
+bool YawPlanningEvaluator::updateSegment(TrajectorySegment* segment) {  // yaw_planning_evaluator.cpp:128-160
+  auto* info = dynamic_cast<YawPlanningInfo*>(segment->info.get());
+  if (info) {
+    for (auto& o : info->orientations) {
+      if (o.parent != segment->parent ||
+          !(o.trajectory.front().position_W == segment->trajectory.front().position_W)) {
+        const double original_yaw = o.trajectory.back().getYaw();
+        o.parent = segment->parent;
+        o.trajectory = segment->trajectory;
+        setTrajectoryYaw(&o, segment->trajectory.front().getYaw(), original_yaw);
+      }
+    }
+  }
+  if (segment->parent && info) {
+    const double dist = (planner_.getCurrentPosition() - segment->trajectory.back().position_W).norm();
+    if (p_update_range_ == 0.0 || p_update_range_ > dist) {
+      std::vector<TrajectorySegment*> again;
+      for (auto& o : info->orientations)
+        if (o.gain > p_update_gain_) again.push_back(&o);
+      const bool by_value = p_select_by_value_;
+      p_select_by_value_ = false;  // the reference re-evaluates the gain only here
+      evaluateOrientations(again);
+      p_select_by_value_ = by_value;
+    }
+    setBestYaw(segment);
+  }
+  return following_evaluator_->updateSegment(segment);
+}
+
+ModuleFactoryRegistry::Registration<SimpleYawPlanningEvaluator> SimpleYawPlanningEvaluator::registration(
+    "SimpleYawPlanningEvaluator");
+void SimpleYawPlanningEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
+  setParam<bool>(param_map, "visualize_followup", &p_visualize_followup_, true);
+  YawPlanningEvaluator::setupFromParamMap(param_map);
+}
+double SimpleYawPlanningEvaluator::sampleYaw(double original_yaw, int sample_number) {
+  return angleScaled(original_yaw + static_cast<double>(sample_number) * 2.0 * M_PI / p_n_directions_);
+}
+void SimpleYawPlanningEvaluator::setTrajectoryYaw(TrajectorySegment* segment, double /*start_yaw*/,
+                                                  double target_yaw) {
+  for (auto& p : segment->trajectory) p.setFromYaw(target_yaw);
+}
+
+ModuleFactoryRegistry::Registration<ContinuousYawPlanningEvaluator>
+    ContinuousYawPlanningEvaluator::registration("ContinuousYawPlanningEvaluator");
+void ContinuousYawPlanningEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
+  setParam<bool>(param_map, "visualize_followup", &p_visualize_followup_, true);
+  setParam<int>(param_map, "n_sections_fov", &p_n_sections_fov_, 1);
+  YawPlanningEvaluator::setupFromParamMap(param_map);
+  p_select_by_value_ = false;  // cannot select by value since views are related
+}
+bool ContinuousYawPlanningEvaluator::computeGain(TrajectorySegment* traj_in) {
+  YawPlanningEvaluator::computeGain(traj_in);
+  setBestYaw(traj_in);  // (the reference applies it twice as well, continuous_yaw_…cpp:35-42)
+  return true;
+}
+void ContinuousYawPlanningEvaluator::setBestYaw(TrajectorySegment* segment) {  // …cpp:44-92
+  auto* info = static_cast<YawPlanningInfo*>(segment->info.get());
+  const int n_ori = static_cast<int>(info->orientations.size());
+  std::vector<double> gains;
+  for (int i = 0; i < n_ori; ++i) {
+    double gain = info->orientations[i].gain;
+    for (int j = 1; j < p_n_sections_fov_; ++j) gain += info->orientations[(i + j) % n_ori].gain;
+    gains.push_back(gain);
+  }
+  double min_gain = gains[0], max_gain = gains[0];
+  int max_index = 0;
+  for (size_t i = 1; i < gains.size(); ++i) {
+    if (gains[i] > max_gain) {
+      max_gain = gains[i];
+      max_index = static_cast<int>(i);
+    } else if (gains[i] < min_gain) {
+      min_gain = gains[i];
+    }
+  }
+  double best_yaw;
+  if (max_gain > min_gain) {
+    best_yaw = angleScaled(info->orientations[max_index].trajectory.back().getYaw() +
+                           static_cast<double>(p_n_sections_fov_ - 1) / p_n_directions_ * M_PI);
+  } else {
+    const Eigen::Vector3d direction =
+        segment->trajectory.back().position_W - segment->trajectory.front().position_W;
+    best_yaw = angleScaled(std::atan2(direction[1], direction[0]));
+  }
+  setTrajectoryYaw(segment, segment->trajectory.front().getYaw(), best_yaw);
+  info->active_orientation = max_index;
+  segment->gain = 0.0;
+  for (int j = 0; j < p_n_sections_fov_; ++j) segment->gain += info->orientations[(max_index + j) % n_ori].gain;
+  // always recompute cost and value, since the trajectory can change
+  following_evaluator_->computeCost(segment);
+  following_evaluator_->computeValue(segment);
+}
+double ContinuousYawPlanningEvaluator::sampleYaw(double original_yaw, int sample_number) {
+  return angleScaled(original_yaw + static_cast<double>(sample_number) * 2.0 * M_PI / p_n_directions_);
+}
+void ContinuousYawPlanningEvaluator::setTrajectoryYaw(TrajectorySegment* segment, double /*start_yaw*/,
+                                                      double target_yaw) {
+  for (auto& p : segment->trajectory) p.setFromYaw(target_yaw);
 }
 
 }  // namespace trajectory_evaluator

@@ -207,16 +207,159 @@ int runGains(char** argv) {
   return 0;
 }
 
+// Stand-ins for the cost / value / updater modules (outside this path) so that select_by_value,
+// ContinuousYawPlanningEvaluator::setBestYaw and updateSegment can run.
+class TestSegmentLength : public CostComputer {
+ public:
+  explicit TestSegmentLength(PlannerI& planner) : CostComputer(planner) {}
+  void setupFromParamMap(Module::ParamMap*) override {}
+  bool computeCost(TrajectorySegment* t) override {
+    t->cost = 1.0 + t->trajectory.back().getYaw();  // depends on the applied yaw
+    return true;
+  }
+  static ModuleFactoryRegistry::Registration<TestSegmentLength> registration;
+};
+ModuleFactoryRegistry::Registration<TestSegmentLength> TestSegmentLength::registration("TestSegmentLength");
+class TestLinearValue : public ValueComputer {
+ public:
+  explicit TestLinearValue(PlannerI& planner) : ValueComputer(planner) {}
+  void setupFromParamMap(Module::ParamMap*) override {}
+  bool computeValue(TrajectorySegment* t) override {
+    t->value = t->gain - 100.0 * t->cost;
+    return true;
+  }
+  static ModuleFactoryRegistry::Registration<TestLinearValue> registration;
+};
+ModuleFactoryRegistry::Registration<TestLinearValue> TestLinearValue::registration("TestLinearValue");
+class TestUpdater : public EvaluatorUpdater {
+ public:
+  explicit TestUpdater(PlannerI& planner) : EvaluatorUpdater(planner) {}
+  void setupFromParamMap(Module::ParamMap*) override {}
+  bool updateSegment(TrajectorySegment*) override { return true; }
+  static ModuleFactoryRegistry::Registration<TestUpdater> registration;
+};
+ModuleFactoryRegistry::Registration<TestUpdater> TestUpdater::registration("TestUpdater");
+
+bool loadMap(const char* path, YamlTree* tree, int32_t* vps, int32_t* n_blocks, std::vector<int32_t>* idx,
+             std::vector<float>* dist, std::vector<uint8_t>* obs, std::vector<float>* weight) {
+  std::ifstream mf(path, std::ios::binary);
+  if (!mf) return false;
+  float vs = 0;
+  mf.read(reinterpret_cast<char*>(vps), 4);
+  mf.read(reinterpret_cast<char*>(&vs), 4);
+  mf.read(reinterpret_cast<char*>(n_blocks), 4);
+  const size_t nv = static_cast<size_t>(*vps) * *vps * *vps;
+  if (!readVec(mf, idx, 3 * static_cast<size_t>(*n_blocks)) || !readVec(mf, dist, nv * *n_blocks) ||
+      !readVec(mf, obs, nv * *n_blocks) || !readVec(mf, weight, nv * *n_blocks))
+    return false;
+  tree->set("/map/type", "VoxbloxMap");
+  tree->set("/map/tsdf_voxel_size", std::to_string(vs));
+  tree->set("/map/tsdf_voxels_per_side", std::to_string(*vps));
+  return true;
+}
+
+// a chain of segments (parents matter for updateSegment) read from the segments file
+void loadSegments(const char* path, TrajectorySegment* root, std::vector<TrajectorySegment*>* segments) {
+  std::ifstream sf(path, std::ios::binary);
+  int32_t n_seg = 0, pts = 0;
+  sf.read(reinterpret_cast<char*>(&n_seg), 4);
+  sf.read(reinterpret_cast<char*>(&pts), 4);
+  for (int s = 0; s < n_seg; ++s) {
+    TrajectorySegment* seg = (s == 0) ? root : segments->back()->spawnChild();
+    for (int p = 0; p < pts; ++p) {
+      int64_t t;
+      double v[7];
+      sf.read(reinterpret_cast<char*>(&t), 8);
+      sf.read(reinterpret_cast<char*>(v), 56);
+      EigenTrajectoryPoint tp;
+      tp.time_from_start_ns = t;
+      tp.position_W = Eigen::Vector3d(v[0], v[1], v[2]);
+      tp.orientation_W_B = Eigen::Quaterniond(v[3], v[4], v[5], v[6]);
+      seg->trajectory.push_back(tp);
+    }
+    segments->push_back(seg);
+  }
+}
+
+void printYaw(std::ofstream& out, const char* tag, int s, const TrajectorySegment& seg) {
+  auto* info = dynamic_cast<trajectory_evaluator::YawPlanningInfo*>(seg.info.get());
+  out << tag << " " << s << " " << seg.gain << " " << seg.cost << " " << seg.value << " "
+      << (info ? info->active_orientation : -1) << " " << seg.trajectory.back().getYaw() << " "
+      << seg.trajectory.front().getYaw();
+  if (info)
+    for (const auto& o : info->orientations) out << " " << o.gain;
+  out << "\n";
+}
+
+// yaw planning: reference call (one segment per computeGain), the batch call, updateSegment
+int runYaw(char** argv) {
+  YamlTree tree;
+  std::string err;
+  if (!tree.loadFile(argv[2], &err)) {
+    std::cerr << err << "\n";
+    return 2;
+  }
+  int32_t vps = 0, n_blocks = 0;
+  std::vector<int32_t> idx;
+  std::vector<float> dist, weight;
+  std::vector<uint8_t> obs;
+  if (!loadMap(argv[3], &tree, &vps, &n_blocks, &idx, &dist, &obs, &weight)) {
+    std::cerr << "cannot read map\n";
+    return 2;
+  }
+  TestPlanner planner(tree);
+  planner.build("/map", "/trajectory_evaluator");
+  auto* vmap = dynamic_cast<map::VoxbloxMap*>(planner.map_.get());
+  auto* eval = dynamic_cast<trajectory_evaluator::YawPlanningEvaluator*>(planner.evaluator_.get());
+  if (!vmap || !eval) {
+    std::cerr << "config does not name a VoxbloxMap / YawPlanningEvaluator\n";
+    return 2;
+  }
+  vmap->uploadBlocks(n_blocks, idx.data(), dist.data(), obs.data(), weight.data());
+  std::ofstream out(argv[5]);
+  out.precision(17);
+  {
+    TrajectorySegment root;
+    std::vector<TrajectorySegment*> segments;
+    loadSegments(argv[4], &root, &segments);
+    for (size_t s = 0; s < segments.size(); ++s) {
+      eval->computeGain(segments[s]);
+      printYaw(out, "yaw", static_cast<int>(s), *segments[s]);
+    }
+    // updater path on an unchanged map: same orientation gains, same choice
+    planner.position_ = segments.back()->trajectory.back().position_W;
+    for (size_t s = 0; s < segments.size(); ++s) {
+      const bool ok = eval->updateSegment(segments[s]);
+      out << "ok " << ok << "\n";
+      printYaw(out, "yupdate", static_cast<int>(s), *segments[s]);
+    }
+  }
+  {
+    TrajectorySegment root;
+    std::vector<TrajectorySegment*> segments;
+    loadSegments(argv[4], &root, &segments);
+    const bool ok = eval->computeGains(segments);
+    out << "ok " << ok << "\n";
+    for (size_t s = 0; s < segments.size(); ++s) printYaw(out, "ybatch", static_cast<int>(s), *segments[s]);
+    auto* info = dynamic_cast<trajectory_evaluator::YawPlanningInfo*>(segments[0]->info.get());
+    auto* di = info ? dynamic_cast<trajectory_evaluator::DeviceSensorInfo*>(info->orientations[0].info.get())
+                    : nullptr;
+    out << "device_list " << (di ? di->n_voxels : 0) << "\n";
+  }
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
   try {
     if (argc >= 3 && std::strcmp(argv[1], "config") == 0) return runConfig(argc, argv);
     if (argc >= 6 && std::strcmp(argv[1], "gains") == 0) return runGains(argv);
+    if (argc >= 6 && std::strcmp(argv[1], "yaw") == 0) return runYaw(argv);
   } catch (const std::exception& e) {
     std::cerr << "exception: " << e.what() << "\n";
     return 3;
   }
-  std::cerr << "usage: test_host config <yaml> [ns] | gains <yaml> <map.bin> <segments.bin> <out.txt>\n";
+  std::cerr << "usage: test_host config <yaml> [ns] | gains|yaw <yaml> <map.bin> <segments.bin> <out.txt>\n";
   return 1;
 }

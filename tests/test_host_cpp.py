@@ -187,3 +187,104 @@ def test_modules_from_yaml_match_oracle_voxeltype_parents(built, room02, tmp_pat
     assert want["n_visible"][1] < want["n_visible"][0]    # parents did clear something
     # the batch API refuses clear_from_parents
     assert all(v[0] == 0 for v in r["batch"].values())
+
+
+def _yaw_of(q):
+    w, x, y, z = q
+    return np.arctan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z))
+
+
+def _quat_of_yaw(yaw):
+    return np.array([np.cos(yaw / 2.0), 0.0, 0.0, np.sin(yaw / 2.0)])
+
+
+def _angle_scaled(a):
+    a = np.fmod(a, 2.0 * np.pi)
+    return a + 2.0 * np.pi * (a < 0)
+
+
+def parse_yaw(path):
+    res = {"yaw": {}, "yupdate": {}, "ybatch": {}, "ok": [], "device_list": None}
+    for line in open(path):
+        t = line.split()
+        if t[0] in ("yaw", "yupdate", "ybatch"):
+            v = [float(x) for x in t[2:]]
+            res[t[0]][int(t[1])] = dict(gain=v[0], cost=v[1], value=v[2], active=int(v[3]), yaw=v[4],
+                                        front_yaw=v[5], gains=v[6:])
+        elif t[0] == "ok":
+            res["ok"].append(int(t[1]))
+        elif t[0] == "device_list":
+            res["device_list"] = int(t[1])
+    return res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,ekind,n_dir,n_fov,by_value", [
+    ("planner_yaw_simple.yaml", "NaiveEvaluator", 12, 1, False),
+    ("planner_yaw_simple_value.yaml", "VoxelTypeEvaluator", 5, 1, True),
+    ("planner_yaw_continuous.yaml", "NaiveEvaluator", 12, 3, False),
+])
+def test_yaw_planning_evaluators_match_oracle(built, room02, tmp_path, cfg, ekind, n_dir, n_fov, by_value):
+    """Simple/ContinuousYawPlanningEvaluator (yaw_planning_evaluator.cpp:48-110,
+    continuous_yaw_planning_evaluator.cpp:44-92): per-orientation gains against the oracle, the
+    reference's selection rule restated here, and the one-launch batch call against the
+    per-segment call."""
+    from mav_active_3d_planning_b200 import synth
+    from oracle import oracle_py as O
+    n_seg, pts = 5, 3
+    pos, quat = synth.candidate_views(room02, n_seg * pts, seed=41)
+    pos[pts * 2: pts * 3] = pos[pts * 2]          # a segment that does not move: "indifferent" needs atan2(0,0)
+    mp, sp = write_inputs(str(tmp_path), room02, pos, quat, pts, 100_000_000)
+    out = os.path.join(str(tmp_path), "yaw.txt")
+    subprocess.run([EXE, "yaw", os.path.join(GOLD, cfg), mp, sp, out], check=True, timeout=300)
+    r = parse_yaw(out)
+    assert r["ok"] and all(r["ok"])
+    om = O.OracleMap.from_synth(room02)
+    cam = dict(resolution_x=320, resolution_y=240, focal_length=160.0, ray_length=5.0, downsampling_factor=2.0)
+    oc = om.caster("IterativeRayCaster", **cam)
+    bv = dict(x_min=2, x_max=18, y_min=2, y_max=18, z_min=0.5, z_max=7)
+    ep = O.eval_params(ekind, bounding_volume=bv)
+    for s in range(n_seg):
+        last = s * pts + pts - 1
+        original = _yaw_of(quat[last])
+        yaws = [_angle_scaled(original + float(i) * 2.0 * np.pi / n_dir) for i in range(n_dir)]
+        qs = np.array([_quat_of_yaw(y) for y in yaws])
+        want = oc.compute_gains(ep, np.repeat(pos[last:last + 1], n_dir, axis=0), qs)["gain"]
+        applied = [_yaw_of(q) for q in qs]
+        if n_fov > 1:
+            score = [sum(want[(i + j) % n_dir] for j in range(n_fov)) for i in range(n_dir)]
+        elif by_value:
+            score = [want[i] - 100.0 * (1.0 + applied[i]) for i in range(n_dir)]
+        else:
+            score = list(want)
+        # the reference's scan (first strict maximum; "min" only updated in the else branch)
+        if n_fov > 1:
+            mx = mn = score[0]
+            best = 0
+            rng = range(1, n_dir)
+        else:
+            mx, mn, best, rng = -np.inf, np.inf, 0, range(n_dir)
+            mx, mn = np.finfo(float).min, np.finfo(float).max
+        for i in rng:
+            if score[i] > mx:
+                mx, best = score[i], i
+            elif score[i] < mn:
+                mn = score[i]
+        if mx > mn:
+            best_yaw = _angle_scaled(applied[best] + (float(n_fov - 1) / n_dir * np.pi if n_fov > 1 else 0.0))
+        else:
+            d = pos[last] - pos[s * pts]
+            best_yaw = _angle_scaled(np.arctan2(d[1], d[0]))
+        final = _yaw_of(_quat_of_yaw(best_yaw))
+        gain = sum(want[(best + j) % n_dir] for j in range(n_fov))
+        for tag in ("yaw", "ybatch", "yupdate"):
+            got = r[tag][s]
+            assert got["gains"] == list(want), (tag, s)
+            assert got["active"] == best and got["gain"] == gain, (tag, s)
+            assert got["yaw"] == final and got["front_yaw"] == final, (tag, s)
+            if n_fov > 1:
+                assert got["cost"] == 1.0 + final and got["value"] == gain - 100.0 * (1.0 + final)
+            elif by_value:
+                assert got["cost"] == 1.0 + applied[best] and got["value"] == score[best]
+        assert max(want) > 0
+    assert (r["device_list"] > 0) == (cfg == "planner_yaw_simple_value.yaml")
