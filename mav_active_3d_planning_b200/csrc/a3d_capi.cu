@@ -104,7 +104,7 @@ struct a3d_ctx {
   // staging / scratch
   DevBuf<float> st_dist, st_w;
   DevBuf<uint8_t> st_obs;
-  DevBuf<int32_t> st_slots, st_aff_slots, st_aff_nbr, st_aff_idx;
+  DevBuf<int32_t> st_slots, st_aff_slots, st_aff_nbr, st_aff_idx, st_unalloc_idx;
   DevBuf<double> sc_pts, sc_out;
   DevBuf<uint8_t> sc_u8;
   DevBuf<double> sc_pos, sc_quat, sc_gains, sc_centres, sc_origin;
@@ -338,6 +338,41 @@ int slab_reserve(a3d_ctx* ctx, size_t n_slots, bool want_weight) {
   return A3D_OK;
 }
 
+// Frontier bits of the dense volume's words for the unallocated blocks (inside the volume's box) that
+// touch one of the given allocated blocks.  The caller synchronises the stream afterwards.
+int vol_refresh_unallocated(a3d_ctx* ctx, const MapView& mv, const std::vector<int32_t>& slots_in) {
+  if (!mv.vol) return A3D_OK;
+  std::unordered_map<Key3, int32_t, Key3Hash> seen;
+  std::vector<int32_t> idx;
+  for (int32_t s : slots_in) {
+    const Key3 k = ctx->slot_key[s];
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const Key3 q{k.x + dx, k.y + dy, k.z + dz};
+          if (ctx->slots.count(q) || seen.count(q)) continue;
+          bool inside = true;
+          const int32_t c[3] = {q.x, q.y, q.z};
+          for (int a = 0; a < 3; ++a)
+            inside = inside && c[a] >= ctx->dir_lo[a] &&
+                     static_cast<int64_t>(c[a]) < static_cast<int64_t>(ctx->dir_lo[a]) + ctx->dir_n[a];
+          if (!inside) continue;
+          seen.emplace(q, 1);
+          idx.insert(idx.end(), {q.x, q.y, q.z});
+        }
+  }
+  if (idx.empty()) return A3D_OK;
+  CK(ctx->st_unalloc_idx.reserve(idx.size()));
+  CK(cudaMemcpyAsync(ctx->st_unalloc_idx.p, idx.data(), idx.size() * sizeof(int32_t),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  launch_vol_frontier_unallocated(ctx->stream, mv, ctx->d_vol, static_cast<int>(idx.size() / 3),
+                                  ctx->st_unalloc_idx.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));  // idx is a local
+  return A3D_OK;
+}
+
 // K1b + K1c for every allocated block in `affected` (slots): refresh aprons, rebuild meta bytes.
 int refresh_blocks(a3d_ctx* ctx, const std::vector<int32_t>& affected) {
   const int n = static_cast<int>(affected.size());
@@ -369,10 +404,12 @@ int refresh_blocks(a3d_ctx* ctx, const std::vector<int32_t>& affected) {
   launch_refresh_aprons(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_nbr.p, ctx->d_dist);
   launch_build_meta(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword,
                     mv.vol ? ctx->d_vol : nullptr);
-  ctx->launches += 2;
+  launch_build_frontier(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword,
+                        mv.vol ? ctx->d_vol : nullptr);
+  ctx->launches += 3;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
-  return A3D_OK;
+  return vol_refresh_unallocated(ctx, mv, affected);
 }
 
 // Slots of the allocated blocks in the 3x3x3 neighbourhood of the given block indices.
@@ -435,7 +472,7 @@ int vol_ensure(a3d_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
   ctx->vol_on = true;
   ctx->vol_stale = false;
-  return A3D_OK;
+  return vol_refresh_unallocated(ctx, ctx->view(), sl);
 }
 
 // Shared by the host- and device-pointer upload entry points.
@@ -598,7 +635,8 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   CK(ctx->sc_counter.reserve(2));
   CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 2 * sizeof(unsigned int), ctx->stream));
 
-  const bool wave_ok = e && !emit && !dig_dev && e->p.kind != A3D_EVAL_VOXEL_WEIGHT &&
+  const bool wave_ok = e && !emit && !dig_dev &&
+                       !(e->p.kind == A3D_EVAL_VOXEL_WEIGHT && set_dig_dev) &&
                        std::min(c->view.res_x, c->view.res_y) <= cast_wave_max_diag() &&
                        c->view.n_rays < (1 << 24);
   if (ctx->opt_cast_kernel == 2 && !wave_ok)
@@ -617,10 +655,10 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     // number of segments is slower — throughput follows the number of resident warps)
     int grid = std::max(1, std::min(n_segments, ctx->sm_count * cast_wave_blocks_per_sm()));
     size_t stride = 0;
-    while (grid > 1 && wave_scratch_bytes(c->view.n_rays, grid, set_dig_dev != nullptr, &stride) >
-                           (size_t(6) << 30))
+    const bool extra = set_dig_dev != nullptr || e->p.kind == A3D_EVAL_VOXEL_WEIGHT;
+    while (grid > 1 && wave_scratch_bytes(c->view.n_rays, grid, extra, &stride) > (size_t(6) << 30))
       grid /= 2;
-    CK(ctx->sc_wave.reserve(wave_scratch_bytes(c->view.n_rays, grid, set_dig_dev != nullptr, &stride)));
+    CK(ctx->sc_wave.reserve(wave_scratch_bytes(c->view.n_rays, grid, extra, &stride)));
     const size_t n_words = static_cast<size_t>(n_segments) / 32 + 1;
     CK(ctx->sc_inexact.reserve(n_words));
     CK(cudaMemsetAsync(ctx->sc_inexact.p, 0, n_words * sizeof(unsigned int), ctx->stream));
@@ -714,6 +752,7 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
   ctx->st_aff_slots.release();
   ctx->st_aff_nbr.release();
   ctx->st_aff_idx.release();
+  ctx->st_unalloc_idx.release();
   ctx->st_dist.release();
   ctx->st_w.release();
   ctx->st_obs.release();

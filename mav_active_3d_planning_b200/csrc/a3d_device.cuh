@@ -301,6 +301,12 @@ static __device__ __noinline__ int voxel_state_generic(const MapView& m, float p
 
 // ---- fast path ----------------------------------------------------------------------------------
 constexpr uint32_t kWordNoBlock = 0x00020000u;  // centre state UNKNOWN, not observed, all cells UNKNOWN
+// Meta-word bits 23:19 (k_build_frontier): FrontierEvaluator::isFrontierVoxel of this voxel for
+// checking_distance 1, precomputed for every voxel whose centre is UNKNOWN or unobserved.
+//   bit 19: 6-neighbourhood, surface_frontiers    bit 20: 6-neighbourhood, any known neighbour
+//   bit 21: 26-neighbourhood, surface_frontiers   bit 22: 26-neighbourhood, any known neighbour
+//   bit 23: bits 22:19 are valid
+constexpr uint32_t kWordFrontierValid = 1u << 23;
 
 // State of the float point p inside a MIXED interpolation cell: voxel v (in range) of allocated block
 // b (slot), octant sc.  Reads the 8 corners from the padded cube and interpolates like the reference.
@@ -523,11 +529,83 @@ __device__ __forceinline__ bool is_frontier_voxel(const MapView& m, const Center
   return false;
 }
 
+// is_frontier_voxel for the voxel with global coordinate g and centre double c, from meta words where
+// they suffice.  With checking_distance == 1 the neighbour points c ± voxel_size lie within a few float
+// ulps of the neighbour voxels' centres, i.e. inside the neighbour voxel where its 8 interpolation
+// cells meet; when all 8 cell classes of that voxel agree, the state there is that class whichever
+// cell the rounding picks.  A neighbour whose cells disagree is evaluated literally.  Returns 1 / 0,
+// or -1 when the shortcut does not apply at all (no dense volume, other checking distance).
+__device__ __forceinline__ uint32_t neighbour_cells(const MapView& m, int g0, int g1, int g2) {
+  const uint32_t u0 = static_cast<uint32_t>(g0 - m.vol_lo[0]), u1 = static_cast<uint32_t>(g1 - m.vol_lo[1]),
+                 u2 = static_cast<uint32_t>(g2 - m.vol_lo[2]);
+  uint32_t cells = 0;  // outside the box: no block, all cells UNKNOWN
+  if ((u0 < m.vol_n[0]) & (u1 < m.vol_n[1]) & (u2 < m.vol_n[2]))
+    cells = __ldg(m.vol + vol_offset(m, u0, u1, u2)) & 0xFFFFu;
+  return cells;
+}
+static __device__ __noinline__ int neighbour_state_literal(const MapView& m, const CenterTables& ct,
+                                                          const EvalView& e, const D3& c, int sx, int sy,
+                                                          int sz) {
+  D3 q;
+  q.x = __dadd_rn(c.x, sx > 0 ? e.nb_step : (sx < 0 ? -e.nb_step : 0.0));
+  q.y = __dadd_rn(c.y, sy > 0 ? e.nb_step : (sy < 0 ? -e.nb_step : 0.0));
+  q.z = __dadd_rn(c.z, sz > 0 ? e.nb_step : (sz < 0 ? -e.nb_step : 0.0));
+  return voxel_state(m, ct, q);
+}
+__device__ __forceinline__ int neighbour_state(const MapView& m, const CenterTables& ct, const EvalView& e,
+                                               const D3& c, uint32_t cells, int sx, int sy, int sz) {
+  if (cells == 0x0000u) return 2;  // UNKNOWN everywhere
+  if (cells == 0x5555u) return 1;  // FREE everywhere
+  if (cells == 0xAAAAu) return 0;  // OCCUPIED everywhere
+  return neighbour_state_literal(m, ct, e, c, sx, sy, sz);
+}
+__device__ __forceinline__ int is_frontier_by_meta(const MapView& m, const CenterTables& ct,
+                                                   const EvalView& e, const D3& c, int g0, int g1, int g2) {
+  if (!m.vol || e.nb_step != m.c_vs) return -1;
+  if (!e.accurate_frontiers) {
+    // 6-neighbourhood (+x,-x,+y,-y,+z,-z): all six words requested before the first is looked at
+    uint32_t cells[6];
+    cells[0] = neighbour_cells(m, g0 + 1, g1, g2);
+    cells[1] = neighbour_cells(m, g0 - 1, g1, g2);
+    cells[2] = neighbour_cells(m, g0, g1 + 1, g2);
+    cells[3] = neighbour_cells(m, g0, g1 - 1, g2);
+    cells[4] = neighbour_cells(m, g0, g1, g2 + 1);
+    cells[5] = neighbour_cells(m, g0, g1, g2 - 1);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int axis = i >> 1, sgn = (i & 1) ? -1 : 1;
+      const int s = neighbour_state(m, ct, e, c, cells[i], axis == 0 ? sgn : 0, axis == 1 ? sgn : 0,
+                                    axis == 2 ? sgn : 0);
+      if (s == 2) continue;
+      return e.surface_frontiers ? (s == 0) : 1;
+    }
+    return 0;
+  }
+#pragma unroll 1
+  for (int i = 0; i < 26; ++i) {
+    int sx, sy, sz;
+    frontier_offset(true, i, &sx, &sy, &sz);
+    const int s = neighbour_state(m, ct, e, c, neighbour_cells(m, g0 + sx, g1 + sy, g2 + sz), sx, sy, sz);
+    if (s == 2) continue;
+    return e.surface_frontiers ? (s == 0) : 1;
+  }
+  return 0;
+}
+
+// is_frontier_voxel from the precomputed bits of the voxel's own meta word: 1 / 0, or -1 when the
+// word carries none (no block, other checking distance).
+__device__ __forceinline__ int is_frontier_from_word(const MapView& m, const EvalView& e, uint32_t word) {
+  if (!(word & kWordFrontierValid) || e.nb_step != m.c_vs) return -1;
+  const int bit = (e.accurate_frontiers ? 21 : 19) + (e.surface_frontiers ? 0 : 1);
+  return static_cast<int>((word >> bit) & 1u);
+}
+
 // VoxelWeightEvaluator::getVoxelValue (voxel_weight_evaluator.cpp:60-83) for a list entry with centre
-// c, given its state cs (centre_state) and TSDF weight w.
+// c, given its state cs (centre_state) and TSDF weight w.  frontier_hint: is_frontier_by_meta() of the
+// voxel or -1.
 __device__ __forceinline__ double voxel_weight_value(const MapView& m, const CenterTables& ct,
                                                      const EvalView& e, const D3& c, int cs, double w,
-                                                     const D3& origin) {
+                                                     const D3& origin, int frontier_hint = -1) {
   const int state = cs & 3;
   if (state == 0) {  // surface voxel
     const double dx = c.x - origin.x, dy = c.y - origin.y, dz = c.z - origin.z;
@@ -538,7 +616,10 @@ __device__ __forceinline__ double voxel_weight_value(const MapView& m, const Cen
     return gain > e.min_impact_factor ? gain : 0.0;
   }
   if (state == 2) {  // unobserved voxel
-    if (e.frontier_voxel_weight > 0.0 && is_frontier_voxel(m, ct, e, c)) return e.frontier_voxel_weight;
+    if (e.frontier_voxel_weight > 0.0) {
+      const bool frontier = frontier_hint >= 0 ? frontier_hint != 0 : is_frontier_voxel(m, ct, e, c);
+      if (frontier) return e.frontier_voxel_weight;
+    }
     return e.new_voxel_weight;
   }
   return 0.0;

@@ -66,6 +66,11 @@ void launch_refresh_aprons(cudaStream_t st, const MapView& m, int n, const int32
 void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                        const int32_t* block_idx_dev /*n×3*/, uint32_t* mword_slab,
                        uint32_t* vol /*dense meta volume described by m.vol_lo / m.vol_n, or null*/);
+// frontier bits of the meta words (after launch_build_meta of all affected blocks)
+void launch_build_frontier(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
+                           const int32_t* block_idx_dev /*n×3*/, uint32_t* mword_slab, uint32_t* vol);
+void launch_vol_frontier_unallocated(cudaStream_t st, const MapView& m, uint32_t* vol, int n,
+                                     const int32_t* block_idx_dev /*n×3, unallocated blocks inside the box*/);
 // dense meta volume maintenance: fill everything / the listed blocks with "no block", copy the
 // listed blocks' meta words in
 void launch_vol_fill(cudaStream_t st, const MapView& m, uint32_t* vol, int n_blocks,

@@ -78,6 +78,7 @@ struct WaveScratch {
 struct LaneCounters {
   unsigned long long packed;
   unsigned long long digest;  // DIGEST instantiations only
+  double wsum;                // VoxelWeightEvaluator instantiations only: partial gain
   unsigned n_samp;
 };
 constexpr int kFieldBits = 21;
@@ -168,6 +169,7 @@ struct ViewShared {  // per-view constants, one copy per CTA in shared memory
   double q[4];
   // index-certification margin of this view (NaN: no sample of the view may take the fast path)
   float delta, delta_hi;  // delta_hi = 0.5f - delta
+  double org[3];          // VoxelWeightEvaluator: the segment's reference point (last trajectory point)
 };
 
 // Bounding-volume test on integer voxel coordinates: for an axis-aligned volume, centre(g) inside
@@ -475,13 +477,18 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
   const int sc = cur.flags & 7;
   const bool safe = (cur.flags & 8) != 0;
   SampleInfo si;
-  D3 cc{0.0, 0.0, 0.0};
+  D3 cc{0.0, 0.0, 0.0};  // centre of the entry's voxel, formed only where something needs it
+  bool have_cc = false;
   bool in_bv = true;
-  constexpr bool kNeedCentre = DIGEST || EVAL == A3D_EVAL_FRONTIER;
+  auto centre = [&]() {
+    if (have_cc) return;
+    const int vmask = m.vps - 1;  // (certified samples only: the literal path delivers its centre)
+    cc.x = __dadd_rn(static_cast<double>(origin_point(g[0] >> m.vps_shift, m.bs_f)), ct.d[(g[0] & vmask) + 1]);
+    cc.y = __dadd_rn(static_cast<double>(origin_point(g[1] >> m.vps_shift, m.bs_f)), ct.d[(g[1] & vmask) + 1]);
+    cc.z = __dadd_rn(static_cast<double>(origin_point(g[2] >> m.vps_shift, m.bs_f)), ct.d[(g[2] & vmask) + 1]);
+    have_cc = true;
+  };
   if (safe) {
-    const int b0 = g[0] >> m.vps_shift, b1 = g[1] >> m.vps_shift, b2 = g[2] >> m.vps_shift;
-    const int vmask = m.vps - 1;
-    const int v0 = g[0] & vmask, v1 = g[1] & vmask, v2 = g[2] & vmask;
     const uint32_t word = cur.word;
     const int cls = (word >> (2 * sc)) & 3;
     si.st = cls == kCellUnknown ? 2 : (cls == kCellFree ? 1 : 0);
@@ -493,11 +500,9 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
       sample_point(vw, lt, d_this, pp, pf);
       si.st = mixed_state(m, ct, pf[0], pf[1], pf[2], g[0], g[1], g[2], sc);
     }
-    if (kNeedCentre || bv_mode == 2) {
-      cc.x = __dadd_rn(static_cast<double>(origin_point(b0, m.bs_f)), ct.d[v0 + 1]);
-      cc.y = __dadd_rn(static_cast<double>(origin_point(b1, m.bs_f)), ct.d[v1 + 1]);
-      cc.z = __dadd_rn(static_cast<double>(origin_point(b2, m.bs_f)), ct.d[v2 + 1]);
-      if (bv_mode) in_bv = bv_contains(e, cc);  // simulated_sensor_evaluator.cpp:50-57
+    if (bv_mode == 2) {
+      centre();
+      in_bv = bv_contains(e, cc);  // simulated_sensor_evaluator.cpp:50-57
     } else if (bv_mode) {
       in_bv = (g[0] >= bvg.lo[0]) & (g[0] <= bvg.hi[0]) & (g[1] >= bvg.lo[1]) & (g[1] <= bvg.hi[1]) &
               (g[2] >= bvg.lo[2]) & (g[2] <= bvg.hi[2]);
@@ -512,6 +517,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     if (bad) lt.inexact = 1;
     si = out.si;
     cc = out.cc;
+    have_cc = true;
     if (bv_mode) in_bv = bv_contains(e, cc);
   }
   const bool emit = ITER || si.st != 0;
@@ -520,22 +526,44 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
   const bool first = emit & (rs.prev.g0 == kNoIdent);
   if (emit) rs.prev = si.id;
   int cat;
+  double wval = 0.0;
   if (EVAL == A3D_EVAL_VOXEL_TYPE) {
     cat = si.cs & 3;  // retained entries are always inside the bounding volume
+  } else if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+    cat = 1;
+    if (keep && (si.cs & 3) != 1) {  // voxel_weight_evaluator.cpp:43-83 (free voxels score nothing)
+      int hint = -1;
+      if (safe && (si.cs & 3) == 2 && e.frontier_voxel_weight > 0.0) hint = is_frontier_from_word(m, e, cur.word);
+      double w = 0.0;
+      if ((si.cs & 3) == 0 || (hint < 0 && e.frontier_voxel_weight > 0.0)) centre();
+      if ((si.cs & 3) == 0) w = voxel_weight(m, cc);
+      if (safe && hint < 0 && (si.cs & 3) == 2 && e.frontier_voxel_weight > 0.0)
+        hint = is_frontier_by_meta(m, ct, e, cc, g[0], g[1], g[2]);
+      wval = voxel_weight_value(m, ct, e, cc, si.cs, w, D3{vw.org[0], vw.org[1], vw.org[2]}, hint);
+      lc.wsum += wval;
+    }
   } else {
     cat = 1;
     if (keep && !(si.cs & 4)) {
       if (EVAL == A3D_EVAL_NAIVE) {
         cat = 0;
-      } else if (is_frontier_voxel(m, ct, e, cc)) {
-        cat = 0;
+      } else {
+        int hint = safe ? is_frontier_from_word(m, e, cur.word) : -1;
+        if (hint < 0) {
+          centre();
+          if (safe) hint = is_frontier_by_meta(m, ct, e, cc, g[0], g[1], g[2]);
+        }
+        if (hint >= 0 ? hint != 0 : is_frontier_voxel(m, ct, e, cc)) cat = 0;
       }
     }
   }
   lc.packed += bvg.inc[keep ? cat : 3];
   unsigned long long h = 0;
   if (DIGEST) {
-    h = keep ? digest_entry(cc) : 0ull;
+    if (keep) {
+      centre();
+      h = digest_entry(cc);
+    }
     lc.digest += h;
   }
   if (first) {
@@ -546,6 +574,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     if (bad) lt.inexact = 1;
     __stcs(&rec.info[rec_at], static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0)));
     if (DIGEST) rec.first_hash[rec_at] = h;
+    if (EVAL == A3D_EVAL_VOXEL_WEIGHT) rec.first_hash[rec_at] = __double_as_longlong(wval);
   }
   if (si.st == 0) {
     rs.d = d_this;
@@ -595,6 +624,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   double* const s_mark_hit = s_dyn;
   unsigned* const s_mark_list = reinterpret_cast<unsigned*>(s_dyn + c.diag_max);
   __shared__ unsigned long long s_packed, s_digest;
+  __shared__ double s_wsum;
   __shared__ unsigned s_nsamp;
   __shared__ BvGrid bvg;
   __shared__ LaneTable lt;
@@ -648,6 +678,12 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         if (m.vps_shift >= 0 && t_max < 1048576.0) delta = static_cast<float>(t_max * 5e-7) + m.fast_c0;
         vw.delta = delta;
         vw.delta_hi = 0.5f - delta;
+        if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+          const double* o = b.seg_origin ? b.seg_origin + 3 * seg : b.pos + 3 * (v_end - 1);
+          vw.org[0] = o[0];
+          vw.org[1] = o[1];
+          vw.org[2] = o[2];
+        }
         s_done_diag = (ITER && n > 1) ? 0 : n_diag;
         s_unit_cursor = 0;
       }
@@ -908,6 +944,8 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
             // the first entry of this part repeats the previous raw entry: std::unique drops it
             lc.packed -= 1ull << (kFieldBits * (info & 7));
             if (DIGEST) lc.digest -= ws.rec.first_hash[at];
+            if (EVAL == A3D_EVAL_VOXEL_WEIGHT)
+              lc.wsum -= __longlong_as_double(static_cast<long long>(ws.rec.first_hash[at]));
           }
           if (em) carry_key = __shfl_sync(kFull, lk, 31 - __clz(em));
         }
@@ -921,6 +959,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
     if (threadIdx.x == 0) {
       s_packed = 0;
       s_digest = 0;
+      s_wsum = 0.0;
       s_nsamp = 0;
     }
     __syncthreads();
@@ -930,6 +969,12 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
       for (int off = 16; off > 0; off >>= 1) {
         pk += __shfl_xor_sync(kFull, pk, off);
         if (DIGEST) dg += __shfl_xor_sync(kFull, dg, off);
+      }
+      double wv = lc.wsum;
+      if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) wv += __shfl_xor_sync(kFull, wv, off);
+        if (lane == 0) atomicAdd(&s_wsum, wv);
       }
       const unsigned tsmp = __reduce_add_sync(kFull, lc.n_samp);
       if (lane == 0) {
@@ -956,6 +1001,8 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         g += n_unk * e.gains[0];
         g += n_free * e.gains[2];
         g += n_occ * e.gains[1];
+      } else if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+        g = s_wsum;
       } else {
         g = static_cast<double>(c0);
       }
@@ -998,6 +1045,9 @@ static void launch_wave_c(cudaStream_t st, const MapView& m, const CasterView& c
     case A3D_EVAL_NAIVE:
       launch_wave_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, e, b, digest, grid, ws, inexact);
       break;
+    case A3D_EVAL_VOXEL_WEIGHT:  // (never with a digest: the value record shares the hash slot)
+      launch_wave_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, e, b, false, grid, ws, inexact);
+      break;
     default:
       launch_wave_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, e, b, digest, grid, ws, inexact);
       break;
@@ -1010,7 +1060,8 @@ static void launch_wave_c(cudaStream_t st, const MapView& m, const CasterView& c
 void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                       const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact) {
   size_t stride = 0;
-  wave_scratch_bytes(c.n_rays, grid, digest, &stride);
+  const bool extra = digest || e.kind == A3D_EVAL_VOXEL_WEIGHT;  // per-part first_hash / first value
+  wave_scratch_bytes(c.n_rays, grid, extra, &stride);
   WaveScratch ws{};
   ws.rays_stride = stride;
   uint8_t* p = static_cast<uint8_t*>(scratch);
@@ -1019,7 +1070,7 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
   p += g * stride * 2 * 8;
   ws.rec.last_key = reinterpret_cast<unsigned long long*>(p);
   p += g * stride * 2 * 8;
-  if (digest) {
+  if (extra) {
     ws.rec.first_hash = reinterpret_cast<unsigned long long*>(p);
     p += g * stride * 2 * 8;
   }

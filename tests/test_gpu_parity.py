@@ -478,10 +478,15 @@ def test_wave_dense_volume_tracks_map_edits(capi, O):
     caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
     oc = om.caster("IterativeRayCaster", **CAM_BASE)
     ev, ep = ctx.evaluator("VoxelTypeEvaluator"), O.eval_params("VoxelTypeEvaluator")
+    # the frontier bits of the meta words (allocated and unallocated voxels) must follow the edits too
+    fr = [(ctx.evaluator("FrontierEvaluator", **kw), O.eval_params("FrontierEvaluator", **kw))
+          for kw in (dict(), dict(accurate_frontiers=True, surface_frontiers=False))]
     pos, quat = synth.candidate_views(m, 16, seed=9)
 
     def check():
         _check_wave(_wave(ctx, caster, ev, pos, quat), oc.compute_gains(ep, pos, quat, n_threads=8))
+        for fe, fp in fr:
+            _check_wave(_wave(ctx, caster, fe, pos, quat), oc.compute_gains(fp, pos, quat, n_threads=8))
 
     third = m.n_blocks // 3
     for part in (order[:third], order[third:2 * third], order[2 * third:]):   # box grows
@@ -573,9 +578,12 @@ def test_voxel_weight_evaluator(capi, O, room02, ckind):
             assert np.array_equal(got[k], want[k]), k
         assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
         assert want["gain"].max() > 1.0
-        # digests=False must not switch to the wavefront kernel for this evaluator
-        got2 = ctx.compute_gains(caster, ev, pos, quat, digests=False)
-        assert ctx.last_cast_kernel == 1 and np.allclose(got2["gain"], want["gain"], rtol=GAIN_RTOL)
+        # without ordered digests the wavefront kernel evaluates it (partial sums per lane)
+        got2 = ctx.compute_gains(caster, ev, pos, quat, digests=False, set_digests=False)
+        assert ctx.last_cast_kernel == 2
+        assert np.allclose(got2["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
+        for k in ("n_samples", "n_visible"):
+            assert np.array_equal(got2[k], want[k]), k
         # multi-view segments with an explicit origin per segment, and the stored-list fold
         seg = np.repeat(np.arange(6, dtype=np.int32), 4)
         org = pos[::4] + 0.3
@@ -583,6 +591,10 @@ def test_voxel_weight_evaluator(capi, O, room02, ckind):
         want = oc.compute_gains(oe, pos, quat, seg, 6, seg_origin=org)
         assert np.array_equal(got["digest"], want["digest"])
         assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
+        got2 = ctx.compute_gains(caster, ev, pos, quat, seg, 6, seg_origin=org, digests=False, set_digests=False)
+        assert ctx.last_cast_kernel == 2
+        assert np.allclose(got2["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
+        assert np.array_equal(got2["n_visible"], want["n_visible"])
         lst, _, g1 = ctx.visible_voxels(caster, pos[:4], quat[:4], evaluator=ev, origin=org[0])
         assert np.isclose(g1, want["gain"][0], rtol=GAIN_RTOL)
         g2, left, _ = ctx.gain_from_voxels(ev, lst, origin=org[0])

@@ -23,8 +23,12 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--views", default="1024,4096,16384,65536")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--evaluator", default=None, help="override the workload's evaluator, e.g. VoxelWeight")
+    ap.add_argument("--cast-kernel", type=int, default=0, help="0 auto, 1 scan-order, 2 wavefront")
     args = ap.parse_args()
-    cfg = synth.CONFIGS[args.workload]
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.evaluator:
+        cfg["evaluator"] = args.evaluator
     t0 = time.time()
     if cfg["map"] == "room":
         m = synth.room_map(cfg["voxel_size"])
@@ -39,6 +43,7 @@ def main():
     caster = ctx.caster(kind, resolution_x=cfg["resolution"][0], resolution_y=cfg["resolution"][1],
                         focal_length=cfg["focal_length"], ray_length=cfg["ray_length"])
     ev = ctx.evaluator(cfg["evaluator"] + "Evaluator")
+    ctx.set_option("cast_kernel", args.cast_kernel)
     dev = torch.device("cuda", 0)
     peak = 6555.2
     try:
@@ -61,11 +66,12 @@ def main():
             if r:
                 ms.append(k)
         S, V = int(t_nsamp.sum().item()), int(t_nvis.sum().item())
-        fold = {"VoxelType": 8 * V, "Naive": V, "Frontier": V}[cfg["evaluator"]]   # lower bound for Frontier
+        # (lower bound for Frontier; VoxelWeight: centre state + one TSDF weight)
+        fold = {"VoxelType": 8 * V, "Naive": V, "Frontier": V, "VoxelWeight": 9 * V}[cfg["evaluator"]]
         lookups = 8 * S + fold
         best = min(ms)
         alg = 32 * S + 4 * fold + 64 * n
-        print(json.dumps({"workload": args.workload, "views": n, "map_blocks": m.n_blocks,
+        print(json.dumps({"workload": args.workload, "evaluator": cfg["evaluator"], "views": n, "map_blocks": m.n_blocks,
                           "map_gen_s": round(t_map, 1), "map_upload_s": round(t_up, 2),
                           "kernel_ms": best, "views_per_s": n / (best * 1e-3),
                           "lookups_per_s": lookups / (best * 1e-3),
