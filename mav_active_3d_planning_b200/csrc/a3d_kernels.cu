@@ -749,10 +749,11 @@ __global__ void __launch_bounds__(256)
           c[voxel_state(m, ct, v) + (bv_contains(e, v) ? 0 : 3)]++;
         } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
           const int s = voxel_state(m, ct, v);
-          wsum += voxel_weight_value(m, ct, e, v, s, s == 0 ? voxel_weight(m, v) : 0.0, origin);
+          const int hint = (s == 2 && e.frontier_voxel_weight > 0.0) ? frontier_hint_for_centre(m, ct, e, v) : -1;
+          wsum += voxel_weight_value(m, ct, e, v, s, s == 0 ? voxel_weight(m, v) : 0.0, origin, hint);
         } else {
           kp = !is_observed(m, v);
-          if (kp && (e.kind == A3D_EVAL_NAIVE || is_frontier_voxel(m, ct, e, v))) c[0]++;
+          if (kp && (e.kind == A3D_EVAL_NAIVE || is_frontier_entry(m, ct, e, v))) c[0]++;
         }
       }
       if (erases) {
@@ -861,11 +862,12 @@ __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
       cnt[s + (bv_contains(e, c) ? 0 : 3)]++;
     } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
       const int s = voxel_state(m, ct, c);
-      wsum += voxel_weight_value(m, ct, e, c, s, s == 0 ? voxel_weight(m, c) : 0.0, origin);
+      const int hint = (s == 2 && e.frontier_voxel_weight > 0.0) ? frontier_hint_for_centre(m, ct, e, c) : -1;
+      wsum += voxel_weight_value(m, ct, e, c, s, s == 0 ? voxel_weight(m, c) : 0.0, origin, hint);
     } else {
       kp = !is_observed(m, c);
       if (kp && e.kind == A3D_EVAL_NAIVE) cnt[0]++;
-      if (kp && e.kind == A3D_EVAL_FRONTIER && is_frontier_voxel(m, ct, e, c)) cnt[0]++;
+      if (kp && e.kind == A3D_EVAL_FRONTIER && is_frontier_entry(m, ct, e, c)) cnt[0]++;
     }
     if (kp) left++;
     if (keep) keep[i] = kp ? 1 : 0;
