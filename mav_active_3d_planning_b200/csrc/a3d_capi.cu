@@ -64,6 +64,48 @@ struct DevBuf {  // grow-only device scratch
   }
 };
 
+// Grow-only pinned host staging for the small index lists of a map update: copies from it are truly
+// asynchronous (a pageable source would make every cudaMemcpyAsync synchronise the stream first).
+// Reuse is fenced by an event recorded after the last copy that reads the buffer.
+struct PinBuf {
+  int32_t* p = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+  cudaError_t reserve(size_t n) {
+    if (pending) {
+      cudaError_t e = cudaEventSynchronize(ev);
+      if (e != cudaSuccess) return e;
+      pending = false;
+    }
+    if (n <= cap) return cudaSuccess;
+    const size_t want = std::max<size_t>(std::max(n, cap + cap / 2), 1024);
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want * sizeof(int32_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  cudaError_t mark(cudaStream_t st) {
+    if (!ev) {
+      cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    pending = true;
+    return cudaEventRecord(ev, st);
+  }
+  void release() {
+    if (pending && ev) cudaEventSynchronize(ev);
+    if (p) cudaFreeHost(p);
+    if (ev) cudaEventDestroy(ev);
+    p = nullptr;
+    ev = nullptr;
+    cap = 0;
+    pending = false;
+  }
+};
+
 }  // namespace
 
 struct a3d_ctx {
@@ -105,6 +147,7 @@ struct a3d_ctx {
   DevBuf<float> st_dist, st_w;
   DevBuf<uint8_t> st_obs;
   DevBuf<int32_t> st_slots, st_aff_slots, st_aff_nbr, st_aff_idx, st_unalloc_idx;
+  PinBuf pin_slots, pin_aff, pin_unalloc;
   DevBuf<double> sc_pts, sc_out;
   DevBuf<uint8_t> sc_u8;
   DevBuf<double> sc_pos, sc_quat, sc_gains, sc_centres, sc_origin;
@@ -338,14 +381,15 @@ int slab_reserve(a3d_ctx* ctx, size_t n_slots, bool want_weight) {
   return A3D_OK;
 }
 
-// Frontier bits of the dense volume's words for the unallocated blocks (inside the volume's box) that
-// touch one of the given allocated blocks.  The caller synchronises the stream afterwards.
-int vol_refresh_unallocated(a3d_ctx* ctx, const MapView& mv, const std::vector<int32_t>& slots_in) {
-  if (!mv.vol) return A3D_OK;
+// Frontier bits of the dense volume's words for the unallocated blocks (inside the volume's box) in the
+// 3x3x3 neighbourhood of the changed blocks: exactly the unallocated blocks whose outer voxel layer can
+// see a changed voxel through its neighbour test.
+int vol_refresh_unallocated(a3d_ctx* ctx, const MapView& mv, int n_changed, const int32_t* changed_idx) {
+  if (!mv.vol || n_changed <= 0) return A3D_OK;
   std::unordered_map<Key3, int32_t, Key3Hash> seen;
   std::vector<int32_t> idx;
-  for (int32_t s : slots_in) {
-    const Key3 k = ctx->slot_key[s];
+  for (int i = 0; i < n_changed; ++i) {
+    const Key3 k{changed_idx[3 * i], changed_idx[3 * i + 1], changed_idx[3 * i + 2]};
     for (int dz = -1; dz <= 1; ++dz)
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx) {
@@ -362,54 +406,63 @@ int vol_refresh_unallocated(a3d_ctx* ctx, const MapView& mv, const std::vector<i
         }
   }
   if (idx.empty()) return A3D_OK;
+  CK(ctx->pin_unalloc.reserve(idx.size()));
+  std::copy(idx.begin(), idx.end(), ctx->pin_unalloc.p);
   CK(ctx->st_unalloc_idx.reserve(idx.size()));
-  CK(cudaMemcpyAsync(ctx->st_unalloc_idx.p, idx.data(), idx.size() * sizeof(int32_t),
+  CK(cudaMemcpyAsync(ctx->st_unalloc_idx.p, ctx->pin_unalloc.p, idx.size() * sizeof(int32_t),
                      cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->pin_unalloc.mark(ctx->stream));
   launch_vol_frontier_unallocated(ctx->stream, mv, ctx->d_vol, static_cast<int>(idx.size() / 3),
                                   ctx->st_unalloc_idx.p);
   ctx->launches++;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(ctx->stream));  // idx is a local
   return A3D_OK;
 }
 
 // K1b + K1c for every allocated block in `affected` (slots): refresh aprons, rebuild meta bytes.
-int refresh_blocks(a3d_ctx* ctx, const std::vector<int32_t>& affected) {
+int refresh_blocks(a3d_ctx* ctx, const std::vector<int32_t>& affected, int n_changed,
+                   const int32_t* changed_idx) {
   const int n = static_cast<int>(affected.size());
-  if (n == 0) return A3D_OK;
-  std::vector<int32_t> nbr(static_cast<size_t>(n) * 27), idx(static_cast<size_t>(n) * 3);
-  for (int a = 0; a < n; ++a) {
-    const Key3 k = ctx->slot_key[affected[a]];
-    idx[3 * a] = k.x;
-    idx[3 * a + 1] = k.y;
-    idx[3 * a + 2] = k.z;
-    for (int dz = -1; dz <= 1; ++dz)
-      for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          auto it = ctx->slots.find(Key3{k.x + dx, k.y + dy, k.z + dz});
-          nbr[static_cast<size_t>(a) * 27 + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] =
-              it == ctx->slots.end() ? -1 : it->second;
-        }
-  }
-  CK(ctx->st_aff_slots.reserve(n));
-  CK(ctx->st_aff_nbr.reserve(nbr.size()));
-  CK(ctx->st_aff_idx.reserve(idx.size()));
-  CK(cudaMemcpyAsync(ctx->st_aff_slots.p, affected.data(), n * sizeof(int32_t),
-                     cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->st_aff_nbr.p, nbr.data(), nbr.size() * sizeof(int32_t),
-                     cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->st_aff_idx.p, idx.data(), idx.size() * sizeof(int32_t),
-                     cudaMemcpyHostToDevice, ctx->stream));
   const MapView mv = ctx->view();
-  launch_refresh_aprons(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_nbr.p, ctx->d_dist);
-  launch_build_meta(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword,
-                    mv.vol ? ctx->d_vol : nullptr);
-  launch_build_frontier(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword,
-                        mv.vol ? ctx->d_vol : nullptr);
-  ctx->launches += 3;
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
-  return vol_refresh_unallocated(ctx, mv, affected);
+  if (n > 0) {
+    // pinned staging: [slots n | neighbours 27n | block indices 3n]
+    CK(ctx->pin_aff.reserve(static_cast<size_t>(n) * 31));
+    int32_t* h_slots = ctx->pin_aff.p;
+    int32_t* nbr = h_slots + n;
+    int32_t* idx = nbr + static_cast<size_t>(n) * 27;
+    for (int a = 0; a < n; ++a) {
+      h_slots[a] = affected[a];
+      const Key3 k = ctx->slot_key[affected[a]];
+      idx[3 * a] = k.x;
+      idx[3 * a + 1] = k.y;
+      idx[3 * a + 2] = k.z;
+      for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            auto it = ctx->slots.find(Key3{k.x + dx, k.y + dy, k.z + dz});
+            nbr[static_cast<size_t>(a) * 27 + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] =
+                it == ctx->slots.end() ? -1 : it->second;
+          }
+    }
+    CK(ctx->st_aff_slots.reserve(n));
+    CK(ctx->st_aff_nbr.reserve(static_cast<size_t>(n) * 27));
+    CK(ctx->st_aff_idx.reserve(static_cast<size_t>(n) * 3));
+    CK(cudaMemcpyAsync(ctx->st_aff_slots.p, h_slots, n * sizeof(int32_t), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CK(cudaMemcpyAsync(ctx->st_aff_nbr.p, nbr, static_cast<size_t>(n) * 27 * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->st_aff_idx.p, idx, static_cast<size_t>(n) * 3 * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->pin_aff.mark(ctx->stream));
+    launch_refresh_aprons(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_nbr.p, ctx->d_dist);
+    launch_build_meta(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword,
+                      mv.vol ? ctx->d_vol : nullptr);
+    launch_build_frontier(ctx->stream, mv, n, ctx->st_aff_slots.p, ctx->st_aff_idx.p, ctx->d_mword,
+                          mv.vol ? ctx->d_vol : nullptr);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+  }
+  return vol_refresh_unallocated(ctx, mv, n_changed, changed_idx);
 }
 
 // Slots of the allocated blocks in the 3x3x3 neighbourhood of the given block indices.
@@ -472,7 +525,10 @@ int vol_ensure(a3d_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
   ctx->vol_on = true;
   ctx->vol_stale = false;
-  return vol_refresh_unallocated(ctx, ctx->view(), sl);
+  int rc = vol_refresh_unallocated(ctx, ctx->view(), n, idx.data());
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return A3D_OK;
 }
 
 // Shared by the host- and device-pointer upload entry points.
@@ -523,10 +579,12 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
   // payload, in chunks bounded by the staging size
   const size_t nv = static_cast<size_t>(ctx->nv);
   const int chunk = static_cast<int>(std::max<size_t>(1, (size_t(256) << 20) / (nv * 4)));
+  CK(ctx->pin_slots.reserve(n));
+  std::copy(slot_of.begin(), slot_of.end(), ctx->pin_slots.p);
   for (int i0 = 0; i0 < n; i0 += chunk) {
     const int m = std::min(chunk, n - i0);
     CK(ctx->st_slots.reserve(m));
-    CK(cudaMemcpyAsync(ctx->st_slots.p, slot_of.data() + i0, m * sizeof(int32_t),
+    CK(cudaMemcpyAsync(ctx->st_slots.p, ctx->pin_slots.p + i0, m * sizeof(int32_t),
                        cudaMemcpyHostToDevice, ctx->stream));
     const float* dsrc = dist + static_cast<size_t>(i0) * nv;
     const uint8_t* osrc = obs + static_cast<size_t>(i0) * nv;
@@ -549,13 +607,17 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
     launch_apply_blocks(ctx->stream, ctx->view(), m, ctx->st_slots.p, dsrc, osrc, wsrc, ctx->d_dist,
                         ctx->has_weight ? ctx->d_weight : nullptr);
     ctx->launches++;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));  // staging buffers are reused by the next chunk
+    CK(cudaGetLastError());  // (staging buffers are reused by the next chunk in stream order)
   }
+  CK(ctx->pin_slots.mark(ctx->stream));
   // aprons + meta of the uploaded blocks and of their allocated neighbours
   std::vector<int32_t> affected;
   collect_affected(ctx, n, block_idx, &affected);
-  return refresh_blocks(ctx, affected);
+  rc = refresh_blocks(ctx, affected, n, block_idx);
+  if (rc) return rc;
+  // one synchronisation per update: on return the caller's payload has been consumed
+  CK(cudaStreamSynchronize(ctx->stream));
+  return A3D_OK;
 }
 
 int point_query(a3d_ctx* ctx, int what, int64_t n, const double* pts, void* out0, size_t out0_elt,
@@ -753,6 +815,9 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
   ctx->st_aff_nbr.release();
   ctx->st_aff_idx.release();
   ctx->st_unalloc_idx.release();
+  ctx->pin_slots.release();
+  ctx->pin_aff.release();
+  ctx->pin_unalloc.release();
   ctx->st_dist.release();
   ctx->st_w.release();
   ctx->st_obs.release();
@@ -826,14 +891,16 @@ int a3d_map_remove_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx) {
   if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
   if (n < 0 || (n > 0 && !block_idx)) return ctx->fail(A3D_ERR_INVALID, "null block_idx");
   CK(cudaSetDevice(ctx->device));
-  bool dirty = false;
+  std::vector<int32_t> removed;  // indices of the blocks that were allocated (they lie inside the box)
   for (int i = 0; i < n; ++i) {
     auto it = ctx->slots.find(Key3{block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2]});
     if (it == ctx->slots.end()) continue;
     ctx->free_slots.push_back(it->second);
     ctx->slots.erase(it);
-    dirty = true;
+    removed.insert(removed.end(), {block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2]});
   }
+  const bool dirty = !removed.empty();
+  const int n_removed = static_cast<int>(removed.size() / 3);
   if (dirty) {
     table_rebuild(ctx, ctx->slots.size());
     int rc = table_upload(ctx);
@@ -842,18 +909,18 @@ int a3d_map_remove_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx) {
     if (mv.vol) {
       // removed blocks inside the (unchanged) box read "no block" again; blocks that were not
       // allocated hold that value already
-      CK(ctx->st_aff_idx.reserve(static_cast<size_t>(n) * 3));
-      CK(cudaMemcpyAsync(ctx->st_aff_idx.p, block_idx, static_cast<size_t>(n) * 3 * sizeof(int32_t),
+      CK(ctx->st_aff_idx.reserve(removed.size()));
+      CK(cudaMemcpyAsync(ctx->st_aff_idx.p, removed.data(), removed.size() * sizeof(int32_t),
                          cudaMemcpyHostToDevice, ctx->stream));
-      launch_vol_fill(ctx->stream, mv, ctx->d_vol, n, ctx->st_aff_idx.p);
+      launch_vol_fill(ctx->stream, mv, ctx->d_vol, n_removed, ctx->st_aff_idx.p);
       ctx->launches++;
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(ctx->stream));
     }
     // the removed blocks' neighbours must stop mirroring them
     std::vector<int32_t> affected;
-    collect_affected(ctx, n, block_idx, &affected);
-    rc = refresh_blocks(ctx, affected);
+    collect_affected(ctx, n_removed, removed.data(), &affected);
+    rc = refresh_blocks(ctx, affected, n_removed, removed.data());
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
   }

@@ -185,9 +185,13 @@ void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* 
                                                                        mword_slab, vol, use_smem);
 }
 
-// Bits 23:19 of a meta word for the voxel with centre c: first neighbour that is not UNKNOWN in the
-// 6- and in the 26-neighbourhood (frontier_evaluator.cpp:69-98 with checking_distance 1).
-__device__ __forceinline__ uint32_t frontier_bits(const MapView& m, const CenterTables& ct, const D3& c) {
+// Bits 23:19 of a meta word for the voxel with global coordinate g and centre c: first neighbour that
+// is not UNKNOWN in the 6- and in the 26-neighbourhood (frontier_evaluator.cpp:69-98 with
+// checking_distance 1).  A neighbour whose 8 cell classes agree (read from the dense volume, whose
+// class bits the preceding k_build_meta pass wrote) has that state; the others are evaluated
+// literally at the point the reference would form (neighbour_cells / is_frontier_by_meta explain why).
+__device__ __forceinline__ uint32_t frontier_bits(const MapView& m, const CenterTables& ct, const D3& c,
+                                                 int g0, int g1, int g2) {
   uint32_t bits = kWordFrontierValid;
 #pragma unroll 1
   for (int nb = 0; nb < 2; ++nb) {
@@ -196,11 +200,18 @@ __device__ __forceinline__ uint32_t frontier_bits(const MapView& m, const Center
     for (int i = 0; i < count; ++i) {
       int sx, sy, sz;
       frontier_offset(nb != 0, i, &sx, &sy, &sz);
-      D3 q;
-      q.x = __dadd_rn(c.x, sx > 0 ? m.c_vs : (sx < 0 ? -m.c_vs : 0.0));
-      q.y = __dadd_rn(c.y, sy > 0 ? m.c_vs : (sy < 0 ? -m.c_vs : 0.0));
-      q.z = __dadd_rn(c.z, sz > 0 ? m.c_vs : (sz < 0 ? -m.c_vs : 0.0));
-      const int st = voxel_state(m, ct, q);
+      int st = -1;
+      if (m.vol) {
+        const uint32_t cells = neighbour_cells(m, g0 + sx, g1 + sy, g2 + sz);
+        st = cells == 0x0000u ? 2 : (cells == 0x5555u ? 1 : (cells == 0xAAAAu ? 0 : -1));
+      }
+      if (st < 0) {
+        D3 q;
+        q.x = __dadd_rn(c.x, sx > 0 ? m.c_vs : (sx < 0 ? -m.c_vs : 0.0));
+        q.y = __dadd_rn(c.y, sy > 0 ? m.c_vs : (sy < 0 ? -m.c_vs : 0.0));
+        q.z = __dadd_rn(c.z, sz > 0 ? m.c_vs : (sz < 0 ? -m.c_vs : 0.0));
+        st = voxel_state(m, ct, q);
+      }
       if (st == 2) continue;
       bits |= (st == 0 ? 1u : 0u) << (19 + 2 * nb);
       bits |= 1u << (20 + 2 * nb);
@@ -221,30 +232,33 @@ __global__ void k_build_frontier(MapView m, int n, const int32_t* __restrict__ s
   init_center_tables(m, &ct);
   __syncthreads();
   const int vps = m.vps;
-  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+  // flat over (block, voxel): a delta of a few blocks still fills the machine
+  const long long total = static_cast<long long>(n) * m.nv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int a = static_cast<int>(i / m.nv), lin = static_cast<int>(i - static_cast<long long>(a) * m.nv);
     const int slot = slots[a];
     const int32_t* bi = block_idx + 3 * a;
-    for (int lin = threadIdx.x; lin < m.nv; lin += blockDim.x) {
-      const int z = lin / (vps * vps), rem = lin % (vps * vps), y = rem / vps, x = rem % vps;
-      uint32_t* wp = mword_slab + static_cast<size_t>(slot) * m.nv + mword_offset(m, x, y, z);
-      uint32_t word = *wp & ~(0x1Fu << 19);
-      const bool candidate = ((word >> 16) & 3u) == 2u || !((word >> 18) & 1u);
-      if (candidate) {
-        const D3 c{__dadd_rn(static_cast<double>(origin_point(bi[0], m.bs_f)), ct.d[x + 1]),
-                   __dadd_rn(static_cast<double>(origin_point(bi[1], m.bs_f)), ct.d[y + 1]),
-                   __dadd_rn(static_cast<double>(origin_point(bi[2], m.bs_f)), ct.d[z + 1])};
-        const uint32_t bits = frontier_bits(m, ct, c);
-        word |= bits;
-      }
-      *wp = word;
-      if (vol) vol[vol_index(m, bi, x, y, z)] = word;
+    const int z = lin / (vps * vps), rem = lin % (vps * vps), y = rem / vps, x = rem % vps;
+    uint32_t* wp = mword_slab + static_cast<size_t>(slot) * m.nv + mword_offset(m, x, y, z);
+    uint32_t word = *wp & ~(0x1Fu << 19);
+    const bool candidate = ((word >> 16) & 3u) == 2u || !((word >> 18) & 1u);
+    if (candidate) {
+      const D3 c{__dadd_rn(static_cast<double>(origin_point(bi[0], m.bs_f)), ct.d[x + 1]),
+                 __dadd_rn(static_cast<double>(origin_point(bi[1], m.bs_f)), ct.d[y + 1]),
+                 __dadd_rn(static_cast<double>(origin_point(bi[2], m.bs_f)), ct.d[z + 1])};
+      word |= frontier_bits(m, ct, c, bi[0] * vps + x, bi[1] * vps + y, bi[2] * vps + z);
     }
+    *wp = word;
+    if (vol) vol[vol_index(m, bi, x, y, z)] = word;
   }
 }
 
 void launch_build_frontier(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                            const int32_t* block_idx_dev, uint32_t* mword_slab, uint32_t* vol) {
-  if (n > 0) k_build_frontier<<<std::min(n, 148 * 8), 256, 0, st>>>(m, n, slots_dev, block_idx_dev, mword_slab, vol);
+  if (n > 0)
+    k_build_frontier<<<grid_for(static_cast<long long>(n) * m.nv, 256), 256, 0, st>>>(m, n, slots_dev, block_idx_dev,
+                                                                                       mword_slab, vol);
 }
 
 // Dense-volume words of UNALLOCATED blocks next to allocated ones: "no block" plus the frontier bits
@@ -257,26 +271,29 @@ __global__ void k_vol_frontier_unallocated(MapView m, uint32_t* __restrict__ vol
   init_center_tables(m, &ct);
   __syncthreads();
   const int vps = m.vps;
-  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+  const long long total = static_cast<long long>(n) * m.nv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int a = static_cast<int>(i / m.nv), lin = static_cast<int>(i - static_cast<long long>(a) * m.nv);
     const int32_t* bi = block_idx + 3 * a;
-    for (int lin = threadIdx.x; lin < m.nv; lin += blockDim.x) {
-      const int z = lin / (vps * vps), rem = lin % (vps * vps), y = rem / vps, x = rem % vps;
-      uint32_t bits = kWordFrontierValid;
-      // only the outer voxel layer of the block has a neighbour in another block
-      if (x == 0 || y == 0 || z == 0 || x == vps - 1 || y == vps - 1 || z == vps - 1) {
-        const D3 c{__dadd_rn(static_cast<double>(origin_point(bi[0], m.bs_f)), ct.d[x + 1]),
-                   __dadd_rn(static_cast<double>(origin_point(bi[1], m.bs_f)), ct.d[y + 1]),
-                   __dadd_rn(static_cast<double>(origin_point(bi[2], m.bs_f)), ct.d[z + 1])};
-        bits = frontier_bits(m, ct, c);
-      }
-      vol[vol_index(m, bi, x, y, z)] = kWordNoBlock | bits;
+    const int z = lin / (vps * vps), rem = lin % (vps * vps), y = rem / vps, x = rem % vps;
+    uint32_t bits = kWordFrontierValid;
+    // only the outer voxel layer of the block has a neighbour in another block
+    if (x == 0 || y == 0 || z == 0 || x == vps - 1 || y == vps - 1 || z == vps - 1) {
+      const D3 c{__dadd_rn(static_cast<double>(origin_point(bi[0], m.bs_f)), ct.d[x + 1]),
+                 __dadd_rn(static_cast<double>(origin_point(bi[1], m.bs_f)), ct.d[y + 1]),
+                 __dadd_rn(static_cast<double>(origin_point(bi[2], m.bs_f)), ct.d[z + 1])};
+      bits = frontier_bits(m, ct, c, bi[0] * vps + x, bi[1] * vps + y, bi[2] * vps + z);
     }
+    vol[vol_index(m, bi, x, y, z)] = kWordNoBlock | bits;
   }
 }
 
 void launch_vol_frontier_unallocated(cudaStream_t st, const MapView& m, uint32_t* vol, int n,
                                      const int32_t* block_idx_dev) {
-  if (n > 0) k_vol_frontier_unallocated<<<std::min(n, 148 * 8), 256, 0, st>>>(m, vol, n, block_idx_dev);
+  if (n > 0)
+    k_vol_frontier_unallocated<<<grid_for(static_cast<long long>(n) * m.nv, 256), 256, 0, st>>>(m, vol, n,
+                                                                                                block_idx_dev);
 }
 
 __global__ void k_vol_fill_all(uint32_t* __restrict__ vol, size_t n_words) {
