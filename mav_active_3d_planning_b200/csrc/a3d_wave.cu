@@ -7,11 +7,15 @@
 //  * Every lane marches its OWN ray part: the previous raw list entry it needs for the
 //    adjacent-unique test (camera_model.cpp:58) is in its own registers, the sample distance is
 //    accumulated in a register exactly like the reference does (`distance += p_ray_step_`), and no
-//    shuffle or ballot is needed per sample.  Voxel identity is the integer triple
+//    shuffle is needed per sample.  Voxel identity is the integer triple
 //    g = block*vps + voxel (+ artefact flags), equal iff the reference's double centre triples are
 //    equal (fp artefact indices are canonicalised or flagged, see make_ident_slow).  Lanes are
 //    persistent: when a ray ends (range or OCCUPIED hit) the lane pulls the next ready ray, so
 //    occlusion does not idle lanes.
+//  * A sample whose voxel coordinate floor(pf / voxel_size) is provably what voxblox's own index
+//    arithmetic yields ("certified", see sample_prepare) costs ONE load of the voxel's meta word
+//    from the dense meta volume: cell class, centre state, observed flag and frontier bits all
+//    come out of that word.  Everything else is evaluated literally.
 //  * What couples rays — `std::unique` across the boundary between two consecutive rays / views —
 //    is repaired afterwards: each ray part records its first and last key and what its first entry
 //    contributed; a scan-order pass (fix-up) un-counts first entries that equal the previous
@@ -20,8 +24,8 @@
 //    rays (i'<=i, j'<=j) only, so rays on one anti-diagonal are independent.  Warp 0 walks the
 //    anti-diagonals: it casts the rays that start before the last section only up to
 //    c_split_distances_[n-1] — the part that decides every markNeighboringRays call ("marking
-//    parts") — and applies their marks in scan order, last-writer-wins resolved by a per-entry
-//    writer index.  Every ray whose table entry then reads n-1 (fresh last-section starts AND
+//    parts") — and applies their marks: an entry keeps the value of its highest writer (= the
+//    last writer in scan order), so the marks commute and are applied with atomicMax.  Every ray whose table entry then reads n-1 (fresh last-section starts AND
 //    survivors of the marking parts, whose own cell gets marked n-1) has its last section cast as a
 //    "leaf part".  Leaf parts come from a shared supply (one unit = up to 32 rays of a finished
 //    anti-diagonal); warp 1 only casts leaf parts, warp 0 fills the lanes its marking parts leave
@@ -135,12 +139,8 @@ __device__ __forceinline__ uint64_t pack_key(const Ident& id, unsigned* inexact)
 
 // Per-lane state of the ray part a lane is marching (kept small: it lives in registers across the
 // whole engine loop).
-#ifndef A3D_WAVE_PREFETCH
-#define A3D_WAVE_PREFETCH 0  // 1: request a sample's meta word one step ahead of its use
-#endif
-
 // Index part of a sample: voxel coordinate, cell octant and the meta word (requested).
-struct Prefetched {
+struct Prepared {
   int g0, g1, g2;  // floor(pf / voxel_size) per axis
   int flags;       // bits 2:0 cell octant, bit 3: certified (see ray_step)
   uint32_t word;   // meta word of voxel g (certified samples only)
@@ -159,9 +159,6 @@ struct LaneTable {
 struct RayState {
   double d;           // distance of the next sample (accumulated like `distance += p_ray_step_`)
   Ident prev;         // previous raw entry (g0 == kNoIdent: none yet)
-#if A3D_WAVE_PREFETCH
-  Prefetched nx;      // the sample at distance d
-#endif
 };
 
 struct ViewShared {  // per-view constants, one copy per CTA in shared memory
@@ -386,7 +383,7 @@ __device__ __forceinline__ void sample_point(const ViewShared& vw, const LaneTab
 // can occur ("certified").  Such a sample costs one load from the dense meta volume (or a directory
 // load and a meta-word load when the volume is not available).  Everything else (≈ 12*delta of the
 // samples, plus cells whose class is MIXED) is evaluated literally by ray_step().
-__device__ __forceinline__ Prefetched sample_prepare(const MapView& m, const ViewShared& vw,
+__device__ __forceinline__ Prepared sample_prepare(const MapView& m, const ViewShared& vw,
                                                      const LaneTable& lt, double d) {
   constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (T + kMagic) - kMagic = rint(T) for |T| < 2^22
   double pp[3];
@@ -425,7 +422,7 @@ __device__ __forceinline__ Prefetched sample_prepare(const MapView& m, const Vie
     sc = sc_l;
     safe = ok && m.vps_shift >= 0 && vw.delta == vw.delta;  // (NaN margin: certification is off)
   }
-  Prefetched nx;
+  Prepared nx;
   nx.g0 = g[0];
   nx.g1 = g[1];
   nx.g2 = g[2];
@@ -450,11 +447,11 @@ __device__ __forceinline__ Prefetched sample_prepare(const MapView& m, const Vie
   return nx;
 }
 
-// One sample of the lane's ray: folds the prepared sample rs.nx (distance rs.d) and prepares the
-// next one.  Returns true when the part is finished (hit or end reached) and then leaves in rs.d the
-// distance of the OCCUPIED sample that ended it, or -1.
+// One sample of the lane's ray (distance rs.d): index arithmetic + meta word, then the fold.
+// Returns true when the part is finished (hit or end reached) and then leaves in rs.d the distance
+// of the OCCUPIED sample that ended it, or -1.
 // rec_base + (marking part ? 0 : n_rays) + ray: index of this part's record.  Precondition:
-// rs.d < lt.d_end (and rs.nx prepared for rs.d when prefetching).
+// rs.d < lt.d_end.
 template <int CASTER, int EVAL, bool DIGEST>
 __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
                                          const ViewShared& vw, const BvGrid& bvg, const int bv_mode,
@@ -462,16 +459,9 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
                                          const Records& rec, size_t rec_base, int role, int n_rays) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   const double d_this = rs.d;
-#if A3D_WAVE_PREFETCH
-  const Prefetched cur = rs.nx;
+  const Prepared cur = sample_prepare(m, vw, lt, d_this);
   rs.d = __dadd_rn(d_this, step);
   const bool more = rs.d < lt.d_end[threadIdx.x];
-  if (more) rs.nx = sample_prepare(m, vw, lt, rs.d);  // its load overlaps the fold below
-#else
-  const Prefetched cur = sample_prepare(m, vw, lt, d_this);
-  rs.d = __dadd_rn(d_this, step);
-  const bool more = rs.d < lt.d_end[threadIdx.x];
-#endif
   lc.n_samp++;
   const int g[3] = {cur.g0, cur.g1, cur.g2};
   const int sc = cur.flags & 7;
@@ -804,9 +794,6 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                 lt.mark[threadIdx.x] = mark_idx;
                 const int ms = static_cast<int>(it & 0xFF);
                 ray_begin(rs, lt, c, vw, static_cast<int>(it >> 8), c.split[ms]);
-#if A3D_WAVE_PREFETCH
-                rs.nx = sample_prepare(m, vw, lt, rs.d);
-#endif
                 start_s[it >> 8] = static_cast<uint8_t>(ms);  // read by leaf lanes after the diagonal
                 lt.d_end[threadIdx.x] = d_mark_end;
                 role = 2;  // split[s] < split[n-1] for s < n-1: at least one sample
@@ -859,9 +846,6 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
                 ray_begin(rs, lt, c, vw, r, d0);
                 lt.d_end[threadIdx.x] = d_leaf_end;
                 role = (rs.d < d_leaf_end) ? 1 : 0;
-#if A3D_WAVE_PREFETCH
-                if (role) rs.nx = sample_prepare(m, vw, lt, rs.d);
-#endif
               }
               const int taken = min(n_idle, pend_count);
               pend_head = (pend_head + taken) % kPendCap;
