@@ -600,12 +600,12 @@ __device__ __forceinline__ int is_frontier_from_word(const MapView& m, const Eva
   return static_cast<int>((word >> bit) & 1u);
 }
 
-// is_frontier_from_word for a stored list entry: c must be, bit for bit, the centre double of the
-// voxel its own index arithmetic lands in (true for every entry that came from a canonical voxel);
-// otherwise -1 and the caller evaluates the test literally.
-__device__ __forceinline__ int frontier_hint_for_centre(const MapView& m, const CenterTables& ct,
-                                                        const EvalView& e, const D3& c) {
-  if (e.nb_step != m.c_vs) return -1;
+// Meta word of the voxel whose centre double is, bit for bit, the stored list entry c (true for every
+// entry that came from a canonical voxel).  Such an entry's voxel state (= the precomputed centre
+// state), observed flag and frontier bits are all in that word.  False: the caller evaluates the
+// entry literally.
+__device__ __forceinline__ bool centre_word(const MapView& m, const CenterTables& ct, const D3& c,
+                                            uint32_t* word_out) {
   const double cd[3] = {c.x, c.y, c.z};
   int b[3], v[3];
 #pragma unroll
@@ -614,19 +614,26 @@ __device__ __forceinline__ int frontier_hint_for_centre(const MapView& m, const 
     b[k] = grid_index(p, m.bs_inv_f);
     const float origin = origin_point(b[k], m.bs_f);
     v[k] = grid_index(__fsub_rn(p, origin), m.vs_inv_f);
-    if (static_cast<unsigned>(v[k]) >= static_cast<unsigned>(m.vps)) return -1;
-    if (__dadd_rn(static_cast<double>(origin), ct.d[v[k] + 1]) != cd[k]) return -1;
+    if (static_cast<unsigned>(v[k]) >= static_cast<unsigned>(m.vps)) return false;
+    if (__dadd_rn(static_cast<double>(origin), ct.d[v[k] + 1]) != cd[k]) return false;
   }
-  const int slot = find_slot(m, b[0], b[1], b[2]);
-  uint32_t word = 0;
-  if (slot >= 0) {
-    word = __ldg(m.mword + static_cast<size_t>(slot) * m.nv + mword_offset(m, v[0], v[1], v[2]));
-  } else if (m.vol) {
+  uint32_t word = kWordNoBlock;
+  if (m.vol) {
     const uint32_t u0 = static_cast<uint32_t>(b[0] * m.vps + v[0] - m.vol_lo[0]),
                    u1 = static_cast<uint32_t>(b[1] * m.vps + v[1] - m.vol_lo[1]),
                    u2 = static_cast<uint32_t>(b[2] * m.vps + v[2] - m.vol_lo[2]);
     if ((u0 < m.vol_n[0]) & (u1 < m.vol_n[1]) & (u2 < m.vol_n[2])) word = __ldg(m.vol + vol_offset(m, u0, u1, u2));
+  } else {
+    const int slot = find_slot(m, b[0], b[1], b[2]);
+    if (slot >= 0) word = __ldg(m.mword + static_cast<size_t>(slot) * m.nv + mword_offset(m, v[0], v[1], v[2]));
   }
+  *word_out = word;
+  return true;
+}
+__device__ __forceinline__ int frontier_hint_for_centre(const MapView& m, const CenterTables& ct,
+                                                        const EvalView& e, const D3& c) {
+  uint32_t word;
+  if (!centre_word(m, ct, c, &word)) return -1;
   return is_frontier_from_word(m, e, word);
 }
 // the frontier test of a stored list entry: precomputed bit where it applies, else literal

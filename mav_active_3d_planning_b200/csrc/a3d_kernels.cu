@@ -762,15 +762,24 @@ __global__ void __launch_bounds__(256)
       if (i < cnt) {
         v = D3{list[3 * i], list[3 * i + 1], list[3 * i + 2]};
         kp = true;
+        // state / observed / frontier bits from the voxel's meta word when v is a canonical centre
+        uint32_t word = 0;
+        const bool have = centre_word(m, ct, v, &word);
         if (e.kind == A3D_EVAL_VOXEL_TYPE) {
-          c[voxel_state(m, ct, v) + (bv_contains(e, v) ? 0 : 3)]++;
+          const int st = have ? static_cast<int>((word >> 16) & 3u) : voxel_state(m, ct, v);
+          c[st + (bv_contains(e, v) ? 0 : 3)]++;
         } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
-          const int s = voxel_state(m, ct, v);
-          const int hint = (s == 2 && e.frontier_voxel_weight > 0.0) ? frontier_hint_for_centre(m, ct, e, v) : -1;
-          wsum += voxel_weight_value(m, ct, e, v, s, s == 0 ? voxel_weight(m, v) : 0.0, origin, hint);
+          const int st = have ? static_cast<int>((word >> 16) & 3u) : voxel_state(m, ct, v);
+          const int hint = (have && st == 2 && e.frontier_voxel_weight > 0.0) ? is_frontier_from_word(m, e, word) : -1;
+          wsum += voxel_weight_value(m, ct, e, v, st, st == 0 ? voxel_weight(m, v) : 0.0, origin, hint);
         } else {
-          kp = !is_observed(m, v);
-          if (kp && (e.kind == A3D_EVAL_NAIVE || is_frontier_entry(m, ct, e, v))) c[0]++;
+          kp = have ? !((word >> 18) & 1u) : !is_observed(m, v);
+          if (kp && e.kind == A3D_EVAL_FRONTIER) {
+            const int hint = have ? is_frontier_from_word(m, e, word) : -1;
+            if (hint >= 0 ? hint != 0 : is_frontier_voxel(m, ct, e, v)) c[0]++;
+          } else if (kp) {
+            c[0]++;
+          }
         }
       }
       if (erases) {
@@ -874,17 +883,22 @@ __global__ void k_gain_from_voxels(MapView m, EvalView e, long long n,
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const D3 c{centres[3 * i], centres[3 * i + 1], centres[3 * i + 2]};
     bool kp = true;
+    uint32_t word = 0;
+    const bool have = centre_word(m, ct, c, &word);
     if (e.kind == A3D_EVAL_VOXEL_TYPE) {
-      const int s = voxel_state(m, ct, c);
+      const int s = have ? static_cast<int>((word >> 16) & 3u) : voxel_state(m, ct, c);
       cnt[s + (bv_contains(e, c) ? 0 : 3)]++;
     } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
-      const int s = voxel_state(m, ct, c);
-      const int hint = (s == 2 && e.frontier_voxel_weight > 0.0) ? frontier_hint_for_centre(m, ct, e, c) : -1;
+      const int s = have ? static_cast<int>((word >> 16) & 3u) : voxel_state(m, ct, c);
+      const int hint = (have && s == 2 && e.frontier_voxel_weight > 0.0) ? is_frontier_from_word(m, e, word) : -1;
       wsum += voxel_weight_value(m, ct, e, c, s, s == 0 ? voxel_weight(m, c) : 0.0, origin, hint);
     } else {
-      kp = !is_observed(m, c);
+      kp = have ? !((word >> 18) & 1u) : !is_observed(m, c);
       if (kp && e.kind == A3D_EVAL_NAIVE) cnt[0]++;
-      if (kp && e.kind == A3D_EVAL_FRONTIER && is_frontier_entry(m, ct, e, c)) cnt[0]++;
+      if (kp && e.kind == A3D_EVAL_FRONTIER) {
+        const int hint = have ? is_frontier_from_word(m, e, word) : -1;
+        if (hint >= 0 ? hint != 0 : is_frontier_voxel(m, ct, e, c)) cnt[0]++;
+      }
     }
     if (kp) left++;
     if (keep) keep[i] = kp ? 1 : 0;
