@@ -50,6 +50,21 @@ def test_yaml_factory_builds_param_maps_like_the_ros_factory(built):
     assert p["/target_bounding_volume"]["x_max"] == "18.0"
 
 
+def test_yaw_planning_config_parses_like_the_reference_layout(built):
+    """following_evaluator nests under the yaw-planning evaluator exactly like in
+    app_reconstruction/cfg/planners/reconstruction_planner.yaml:59-100."""
+    yml = os.path.join(GOLD, "planner_yaw_continuous.yaml")
+    p, t, reg = run_config(yml)
+    assert t["/trajectory_evaluator"] == "ContinuousYawPlanningEvaluator"
+    assert p["/trajectory_evaluator"]["n_directions"] == "12" and p["/trajectory_evaluator"]["n_sections_fov"] == "3"
+    for name in ("SimpleYawPlanningEvaluator", "ContinuousYawPlanningEvaluator"):
+        assert name in reg
+    p, t, _ = run_config(yml, "/trajectory_evaluator/following_evaluator")
+    assert t["/trajectory_evaluator/following_evaluator"] == "NaiveEvaluator"
+    assert t["/trajectory_evaluator/following_evaluator/sensor_model"] == "IterativeRayCaster"
+    assert p["/trajectory_evaluator/following_evaluator/sensor_model"]["downsampling_factor"] == "2.0"
+
+
 def test_reference_planner_configs_load_unchanged(built):
     cfg = "/root/reference/active_3d_planning_app_reconstruction/cfg/planners"
     if not os.path.isdir(cfg):
