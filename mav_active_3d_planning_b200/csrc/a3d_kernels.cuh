@@ -96,7 +96,8 @@ int cast_gain_block_threads();
 // throughput kernel (a3d_wave.cu)
 size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride);
 void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
-                      const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact);
+                      const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact,
+                      bool wide /*8-warp CTAs: batches below the SM count*/);
 int cast_wave_threads();
 int cast_wave_max_diag();
 int cast_wave_blocks_per_sm();

@@ -47,6 +47,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 #endif
 constexpr int kWaveWarps = A3D_WAVE_WARPS;
 constexpr int kWaveThreads = 32 * kWaveWarps;
+constexpr int kWaveWideWarps = 8;  // CTA width for batches smaller than the SM count
 constexpr uint64_t kNoKey = ~0ull;  // "no entry"
 constexpr uint64_t kKeyOverflow = 1ull << 63;
 constexpr int kKeyBits = 20, kKeyBias = 1 << 19;
@@ -148,11 +149,12 @@ struct Prepared {
 
 // Per-lane state that is read once per sample or less lives in shared memory, one column per
 // thread: the kernel is register-bound (measured: every spilled value costs more than these loads).
+template <int THREADS>
 struct LaneTable {
-  double dir[3][kWaveThreads];  // world direction of the lane's ray
-  double d_end[kWaveThreads];   // the part ends before this distance
-  int r[kWaveThreads];          // ray id
-  int mark[kWaveThreads];       // index of the lane's marking part in the diagonal's list
+  double dir[3][THREADS];  // world direction of the lane's ray
+  double d_end[THREADS];   // the part ends before this distance
+  int r[THREADS];          // ray id
+  int mark[THREADS];       // index of the lane's marking part in the diagonal's list
   unsigned inexact;             // any lane met a case the scan-order kernel must decide
 };
 
@@ -230,7 +232,8 @@ __device__ void init_bv_grid(const MapView& m, const CenterTables& ct, const Eva
   if (a == 0) g->mode = !e.bv_is_setup ? 0 : (g->fast ? 1 : 2);
 }
 
-__device__ __forceinline__ void ray_begin(RayState& rs, LaneTable& lt, const CasterView& c,
+template <class LT>
+__device__ __forceinline__ void ray_begin(RayState& rs, LT& lt, const CasterView& c,
                                           const ViewShared& vw, int r, double d0) {
   const Q4 q{vw.q[0], vw.q[1], vw.q[2], vw.q[3]};
   const D3 dir = rotate(q, D3{c.cam_dirs[3 * r], c.cam_dirs[3 * r + 1], c.cam_dirs[3 * r + 2]});
@@ -359,7 +362,8 @@ __device__ __noinline__ void sample_exact(const MapView& m, const CenterTables& 
 
 // Position of the sample at distance d of the lane's ray, double and float (the reference casts the
 // double point to voxblox::Point).
-__device__ __forceinline__ void sample_point(const ViewShared& vw, const LaneTable& lt, double d,
+template <class LT>
+__device__ __forceinline__ void sample_point(const ViewShared& vw, const LT& lt, double d,
                                              double (&pp)[3], float (&pf)[3]) {
   const double dx = lt.dir[0][threadIdx.x], dy = lt.dir[1][threadIdx.x], dz = lt.dir[2][threadIdx.x];
   pp[0] = __dadd_rn(vw.P0[0], __dmul_rn(d, dx));
@@ -383,8 +387,9 @@ __device__ __forceinline__ void sample_point(const ViewShared& vw, const LaneTab
 // can occur ("certified").  Such a sample costs one load from the dense meta volume (or a directory
 // load and a meta-word load when the volume is not available).  Everything else (≈ 12*delta of the
 // samples, plus cells whose class is MIXED) is evaluated literally by ray_step().
-__device__ __forceinline__ Prepared sample_prepare(const MapView& m, const ViewShared& vw,
-                                                     const LaneTable& lt, double d) {
+template <class LT>
+__device__ __forceinline__ Prepared sample_prepare(const MapView& m, const ViewShared& vw, const LT& lt,
+                                                   double d) {
   constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (T + kMagic) - kMagic = rint(T) for |T| < 2^22
   double pp[3];
   float pf[3];
@@ -452,10 +457,10 @@ __device__ __forceinline__ Prepared sample_prepare(const MapView& m, const ViewS
 // of the OCCUPIED sample that ended it, or -1.
 // rec_base + (marking part ? 0 : n_rays) + ray: index of this part's record.  Precondition:
 // rs.d < lt.d_end.
-template <int CASTER, int EVAL, bool DIGEST>
+template <int CASTER, int EVAL, bool DIGEST, class LT>
 __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
                                          const ViewShared& vw, const BvGrid& bvg, const int bv_mode,
-                                         const double step, RayState& rs, LaneTable& lt, LaneCounters& lc,
+                                         const double step, RayState& rs, LT& lt, LaneCounters& lc,
                                          const Records& rec, size_t rec_base, int role, int n_rays) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   const double d_this = rs.d;
@@ -589,8 +594,10 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
 
 }  // namespace
 
-template <int CASTER, int EVAL, bool DIGEST>
-__global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
+// WARPS: 2 for throughput (as many CTAs as the registers allow), 8 for batches smaller than the SM
+// count, where a view's leaf parts are better spread over more lanes of the one CTA that owns it.
+template <int CASTER, int EVAL, bool DIGEST, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN_BLOCKS : 2)
     k_cast_wave(const MapView m, const CasterView c, const EvalView e, const Batch b,
                 const WaveScratch ws, unsigned int* __restrict__ inexact_flags) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
@@ -607,7 +614,8 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   __shared__ int s_seg;
   __shared__ volatile int s_done_diag;         // anti-diagonals whose table entries are final
   __shared__ unsigned s_unit_cursor;           // next leaf-supply unit
-  __shared__ unsigned s_pending[kWaveWarps][kPendCap];  // per-warp ring of ready rays waiting for a lane
+  constexpr int kThreads = 32 * WARPS;
+  __shared__ unsigned s_pending[WARPS][kPendCap];  // per-warp ring of ready rays waiting for a lane
   // marking rays of the current diagonal (dynamic shared memory, sized by the longest diagonal):
   // their hit distance (< 0: none) and r << 8 | s
   extern __shared__ double s_dyn[];
@@ -617,7 +625,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
   __shared__ double s_wsum;
   __shared__ unsigned s_nsamp;
   __shared__ BvGrid bvg;
-  __shared__ LaneTable lt;
+  __shared__ LaneTable<kThreads> lt;
   init_center_tables(m, &ct);
   __syncthreads();
   if (threadIdx.x < 32) init_bv_grid(m, ct, e, &bvg);
@@ -677,7 +685,7 @@ __global__ void __launch_bounds__(kWaveThreads, A3D_WAVE_MIN_BLOCKS)
         s_done_diag = (ITER && n > 1) ? 0 : n_diag;
         s_unit_cursor = 0;
       }
-      for (int r = threadIdx.x; r < n_rays; r += kWaveThreads) {
+      for (int r = threadIdx.x; r < n_rays; r += kThreads) {
         if (ITER) {
           table[r] = 0u;
           start_s[r] = 0xFF;
@@ -1009,31 +1017,34 @@ size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride
 template <int CASTER, int EVAL>
 static void launch_wave_t(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                           const Batch& b, bool digest, int grid, const WaveScratch& ws,
-                          unsigned int* inexact) {
-  if (digest)
-    k_cast_wave<CASTER, EVAL, true>
-        <<<grid, kWaveThreads, static_cast<size_t>(c.diag_max) * 12, st>>>(m, c, e, b, ws, inexact);
+                          unsigned int* inexact, bool wide) {
+  const size_t smem = static_cast<size_t>(c.diag_max) * 12;
+  if (digest && wide)
+    k_cast_wave<CASTER, EVAL, true, kWaveWideWarps><<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
+  else if (digest)
+    k_cast_wave<CASTER, EVAL, true, kWaveWarps><<<grid, kWaveThreads, smem, st>>>(m, c, e, b, ws, inexact);
+  else if (wide)
+    k_cast_wave<CASTER, EVAL, false, kWaveWideWarps><<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
   else
-    k_cast_wave<CASTER, EVAL, false>
-        <<<grid, kWaveThreads, static_cast<size_t>(c.diag_max) * 12, st>>>(m, c, e, b, ws, inexact);
+    k_cast_wave<CASTER, EVAL, false, kWaveWarps><<<grid, kWaveThreads, smem, st>>>(m, c, e, b, ws, inexact);
 }
 
 template <int CASTER>
 static void launch_wave_c(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                           const Batch& b, bool digest, int grid, const WaveScratch& ws,
-                          unsigned int* inexact) {
+                          unsigned int* inexact, bool wide) {
   switch (e.kind) {
     case A3D_EVAL_VOXEL_TYPE:
-      launch_wave_t<CASTER, A3D_EVAL_VOXEL_TYPE>(st, m, c, e, b, digest, grid, ws, inexact);
+      launch_wave_t<CASTER, A3D_EVAL_VOXEL_TYPE>(st, m, c, e, b, digest, grid, ws, inexact, wide);
       break;
     case A3D_EVAL_NAIVE:
-      launch_wave_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, e, b, digest, grid, ws, inexact);
+      launch_wave_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, e, b, digest, grid, ws, inexact, wide);
       break;
     case A3D_EVAL_VOXEL_WEIGHT:  // (never with a digest: the value record shares the hash slot)
-      launch_wave_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, e, b, false, grid, ws, inexact);
+      launch_wave_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, e, b, false, grid, ws, inexact, wide);
       break;
     default:
-      launch_wave_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, e, b, digest, grid, ws, inexact);
+      launch_wave_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, e, b, digest, grid, ws, inexact, wide);
       break;
   }
 }
@@ -1042,7 +1053,8 @@ static void launch_wave_c(cudaStream_t st, const MapView& m, const CasterView& c
 // digest (sum of digest_entry over the stored list, mod 2^64).  inexact: one bit per segment, set
 // when a voxel key overflowed the 20-bit packing (the host re-evaluates those with k_cast_gain).
 void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
-                      const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact) {
+                      const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact,
+                      bool wide) {
   size_t stride = 0;
   const bool extra = digest || e.kind == A3D_EVAL_VOXEL_WEIGHT;  // per-part first_hash / first value
   wave_scratch_bytes(c.n_rays, grid, extra, &stride);
@@ -1064,9 +1076,9 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
   p += g * stride * 2;
   ws.start_s = p;
   if (c.kind == A3D_CASTER_ITERATIVE)
-    launch_wave_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, digest, grid, ws, inexact);
+    launch_wave_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, digest, grid, ws, inexact, wide);
   else
-    launch_wave_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, digest, grid, ws, inexact);
+    launch_wave_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, digest, grid, ws, inexact, wide);
 }
 
 int cast_wave_threads() { return kWaveThreads; }

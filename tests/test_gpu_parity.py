@@ -334,12 +334,22 @@ def test_error_codes(capi):
 
 # ---- wavefront kernel (k_cast_wave): same gains / counts / order-independent digest -----------------
 def _wave(ctx, caster, ev, *a, **kw):
+    """Wavefront kernel, both CTA widths (2 warps: throughput, 8 warps: small batches); the two must
+    agree bit for bit on the integer outputs."""
     ctx.set_option("cast_kernel", 2)
     try:
+        ctx.set_option("wave_cta", 1)
         r = ctx.compute_gains(caster, ev, *a, digests=False, **kw)
+        assert ctx.last_cast_kernel == 2
+        ctx.set_option("wave_cta", 2)
+        w = ctx.compute_gains(caster, ev, *a, digests=False, **kw)
+        assert ctx.last_cast_kernel == 2
     finally:
         ctx.set_option("cast_kernel", 0)
-    assert ctx.last_cast_kernel == 2
+        ctx.set_option("wave_cta", 0)
+    for k in ("n_samples", "n_visible", "set_digest"):
+        assert np.array_equal(r[k], w[k]), k
+    assert np.allclose(r["gain"], w["gain"], rtol=1e-12, atol=0)
     return r
 
 
