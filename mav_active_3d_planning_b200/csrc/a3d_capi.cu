@@ -676,7 +676,8 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
                  const double* quat_dev, const int32_t* first_dev, int n_segments, double* gains_dev,
                  unsigned long long* nvis_dev, unsigned long long* nsamp_dev,
                  unsigned long long* dig_dev, unsigned long long* set_dig_dev, double* centres_dev,
-                 long long cap, bool emit, const double* seg_origin_dev) {
+                 long long cap, bool emit, const double* seg_origin_dev,
+                 const long long* emit_offset_dev = nullptr) {
   if (ctx->h_table.empty()) {
     table_rebuild(ctx, 0);
     int rc = table_upload(ctx);
@@ -694,17 +695,22 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   b.set_digests = set_dig_dev;
   b.centres_out = centres_dev;
   b.cap = cap;
+  b.emit_offset = emit_offset_dev;
   b.seg_origin = seg_origin_dev;
   CK(ctx->sc_counter.reserve(2));
   CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 2 * sizeof(unsigned int), ctx->stream));
 
-  const bool wave_ok = e && !emit && !dig_dev &&
+  // The wavefront kernel emits lists through per-part slot ranges (4 MB of scratch per resident view
+  // on the bench workload) that decode voxel keys with a shift: a latency win for the per-segment call
+  // and small batches (2.2 vs 6.6 ms for one view), a loss against the scan-order kernel's streaming
+  // writes for thousands of segments (36 vs 27 ms for 2048).
+  const bool emit_by_wave = emit && ctx->view().vps_shift >= 0 && n_segments <= 2 * ctx->sm_count;
+  const bool wave_ok = e && !dig_dev && (!emit || emit_by_wave) &&
                        !(e->p.kind == A3D_EVAL_VOXEL_WEIGHT && set_dig_dev) &&
                        std::min(c->view.res_x, c->view.res_y) <= cast_wave_max_diag() &&
                        c->view.n_rays < (1 << 24);
   if (ctx->opt_cast_kernel == 2 && !wave_ok)
-    return ctx->fail(A3D_ERR_UNSUPPORTED,
-                     "cast_kernel=2 (wavefront) cannot produce ordered lists/digests");
+    return ctx->fail(A3D_ERR_UNSUPPORTED, "cast_kernel=2 (wavefront) cannot produce ordered digests");
   const bool use_wave = wave_ok && ctx->opt_cast_kernel != 1;
   ctx->last_cast_kernel = use_wave ? 2 : 1;
   if (use_wave) {
@@ -719,9 +725,11 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     int grid = std::max(1, std::min(n_segments, ctx->sm_count * cast_wave_blocks_per_sm()));
     size_t stride = 0;
     const bool extra = set_dig_dev != nullptr || e->p.kind == A3D_EVAL_VOXEL_WEIGHT;
-    while (grid > 1 && wave_scratch_bytes(c->view.n_rays, grid, extra, &stride) > (size_t(6) << 30))
+    const int emit_kmax = emit ? c->view.kmax : 0;
+    while (grid > 1 &&
+           wave_scratch_bytes(c->view.n_rays, grid, extra, &stride, emit_kmax) > (size_t(emit ? 16 : 6) << 30))
       grid /= 2;
-    CK(ctx->sc_wave.reserve(wave_scratch_bytes(c->view.n_rays, grid, extra, &stride)));
+    CK(ctx->sc_wave.reserve(wave_scratch_bytes(c->view.n_rays, grid, extra, &stride, emit_kmax)));
     const size_t n_words = static_cast<size_t>(n_segments) / 32 + 1;
     CK(ctx->sc_inexact.reserve(n_words));
     CK(cudaMemsetAsync(ctx->sc_inexact.p, 0, n_words * sizeof(unsigned int), ctx->stream));
@@ -1513,32 +1521,14 @@ int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_e
   CK(store->d_off.reserve(off.size()));
   CK(cudaMemcpyAsync(store->d_off.p, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice,
                      ctx->stream));
-  {
-    Batch b{};
-    b.pos = ctx->sc_pos.p;
-    b.quat = ctx->sc_quat.p;
-    b.view_first = ctx->sc_first.p;
-    b.n_segments = n_segments;
-    b.gains = ctx->sc_gains.p;
-    b.n_visible = ctx->sc_nvis.p;
-    b.n_samples = ctx->sc_nsamp.p;
-    b.centres_out = arena.p;
-    b.emit_offset = store->d_off.p;
-    b.seg_origin = seg_origin ? ctx->sc_origin.p : nullptr;
-    const int block = cast_gain_block_threads();
-    int grid = std::max(1, std::min(n_segments, ctx->sm_count * 32));
-    if (caster->view.kind == A3D_CASTER_ITERATIVE) {
-      b.table_stride = (static_cast<size_t>(caster->view.n_rays) + 15) / 16 * 16;
-      CK(ctx->sc_tables.reserve(b.table_stride * grid));
-      b.tables = ctx->sc_tables.p;
-    }
-    CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 2 * sizeof(unsigned int), ctx->stream));
-    b.work_counter = ctx->sc_counter.p;
-    launch_cast_gain(ctx->stream, ctx->view(), caster->view, &eval->view, b, false, true, grid, block);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
+  rc = enqueue_cast(ctx, caster, eval, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, n_segments,
+                    ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr, arena.p, 0, true,
+                    seg_origin ? ctx->sc_origin.p : nullptr, store->d_off.p);
+  if (rc) {
+    cudaFree(arena.p);
+    return rc;
   }
+  CK(cudaStreamSynchronize(ctx->stream));
   const int arena_id = static_cast<int>(store->arenas.size());
   store->arenas.push_back(arena);
   for (int s = 0; s < n_segments; ++s) {

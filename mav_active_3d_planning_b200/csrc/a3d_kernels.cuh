@@ -94,7 +94,8 @@ void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long lo
                           const double* other, uint8_t* keep);
 int cast_gain_block_threads();
 // throughput kernel (a3d_wave.cu)
-size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride);
+size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride,
+                          int emit_kmax /*> 0: list emission, slots per ray part*/);
 void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                       const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact,
                       bool wide /*8-warp CTAs: batches below the SM count*/);

@@ -74,6 +74,12 @@ struct WaveScratch {
   uint8_t* start_s;    // per CTA: original start section of rays cast as marking parts, 0xFF none
   Records rec;         // per CTA
   size_t rays_stride;  // n_rays rounded up (elements) per CTA
+  // list emission (null / 0 when only gains are asked): the kept entries of every ray part as packed
+  // keys, kmax slots per part; how many; where the part's entries go in the segment's ordered list
+  unsigned long long* ent;  // [2][n_rays][kmax]
+  uint16_t* cnt;            // [2][n_rays]
+  uint32_t* off;            // [2][n_rays]: offset within the segment's list | (first entry dropped) << 31
+  int kmax;
 };
 
 // Per-lane accumulators of a segment.  `packed`: three 21-bit fields, field c counts list entries of
@@ -155,6 +161,7 @@ struct LaneTable {
   double d_end[THREADS];   // the part ends before this distance
   int r[THREADS];          // ray id
   int mark[THREADS];       // index of the lane's marking part in the diagonal's list
+  int kept[THREADS];       // list emission: entries of the lane's part stored so far
   unsigned inexact;             // any lane met a case the scan-order kernel must decide
 };
 
@@ -243,6 +250,7 @@ __device__ __forceinline__ void ray_begin(RayState& rs, LT& lt, const CasterView
   rs.d = d0;
   rs.prev = Ident{kNoIdent, 0, 0};
   lt.r[threadIdx.x] = r;
+  lt.kept[threadIdx.x] = 0;
 }
 
 // Everything about one sample that the list logic needs.
@@ -461,7 +469,8 @@ template <int CASTER, int EVAL, bool DIGEST, class LT>
 __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
                                          const ViewShared& vw, const BvGrid& bvg, const int bv_mode,
                                          const double step, RayState& rs, LT& lt, LaneCounters& lc,
-                                         const Records& rec, size_t rec_base, int role, int n_rays) {
+                                         const Records& rec, size_t rec_base, int role, int n_rays,
+                                         unsigned long long* ent, int kmax) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   const double d_this = rs.d;
   const Prepared cur = sample_prepare(m, vw, lt, d_this);
@@ -561,6 +570,16 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     }
     lc.digest += h;
   }
+  if (ent && keep) {
+    // list emission: the kept entry, in the part's own slot range (ordered within the part)
+    unsigned bad = 0;
+    const unsigned long long key = pack_key(si.id, &bad);
+    if (bad) lt.inexact = 1;
+    const int k = lt.kept[threadIdx.x];
+    if (k < kmax)
+      __stcs(&ent[(rec_base + (role == 2 ? 0 : n_rays) + lt.r[threadIdx.x]) * static_cast<size_t>(kmax) + k], key);
+    lt.kept[threadIdx.x] = k + 1;
+  }
   if (first) {
     // record of the part's first entry, written once
     unsigned bad = 0;
@@ -652,6 +671,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
 
     LaneCounters lc{};
     uint64_t carry_key = kNoKey;  // last emitted key so far in this segment (warp 0, uniform)
+    unsigned emit_pos = 0;        // list emission: entries of the segment's list placed so far (warp 0)
 
     for (int view = v_begin; view < v_end; ++view) {
       // per-view init (after the previous view's fix-up): pose, ray table, start sections, records
@@ -884,7 +904,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
           for (int it = 0; it < max_it; ++it) {
             if (role > 0) {
               if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, bvg, bv_mode, step, rs, lt, lc, ws.rec, cta_base * 2,
-                                                 role, n_rays))
+                                                 role, n_rays, ws.ent, ws.kmax))
                 role = -role;  // finished: bookkeeping after the round
             }
             bool stop = __popc(__ballot_sync(kFull, role <= 0)) >= idle_limit;
@@ -900,6 +920,10 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
                   cta_base * 2 + (role == -2 ? 0 : static_cast<size_t>(n_rays)) + lt.r[threadIdx.x];
               __stcs(&ws.rec.last_key[rec_at], pack_key(rs.prev, &bad));
               if (bad) lt.inexact = 1;
+              if (ws.ent) {
+                if (lt.kept[threadIdx.x] > ws.kmax) lt.inexact = 1;  // cannot happen (kmax bounds a part)
+                ws.cnt[rec_at] = static_cast<uint16_t>(min(lt.kept[threadIdx.x], ws.kmax));
+              }
             }
             if (role == -2) s_mark_hit[lt.mark[threadIdx.x]] = rs.d;
             role = 0;
@@ -932,7 +956,20 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
           const int src = below ? 31 - __clz(below) : 0;
           uint64_t prev = __shfl_sync(kFull, lk, src);
           if (!below) prev = carry_key;
-          if (emitted && fk == prev && (info & 16)) {
+          const bool drop = emitted && fk == prev && (info & 16);
+          if (ws.ent) {
+            // where this part's kept entries go in the segment's ordered list
+            const unsigned n_out = emitted ? static_cast<unsigned>(ws.cnt[at]) - (drop ? 1u : 0u) : 0u;
+            unsigned incl = n_out;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const unsigned t = __shfl_up_sync(kFull, incl, o);
+              if (static_cast<int>(lane) >= o) incl += t;
+            }
+            if (emitted) ws.off[at] = (emit_pos + incl - n_out) | (drop ? 0x80000000u : 0u);
+            emit_pos += __shfl_sync(kFull, incl, 31);
+          }
+          if (drop) {
             // the first entry of this part repeats the previous raw entry: std::unique drops it
             lc.packed -= 1ull << (kFieldBits * (info & 7));
             if (DIGEST) lc.digest -= ws.rec.first_hash[at];
@@ -940,6 +977,44 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
               lc.wsum -= __longlong_as_double(static_cast<long long>(ws.rec.first_hash[at]));
           }
           if (em) carry_key = __shfl_sync(kFull, lk, 31 - __clz(em));
+        }
+      }
+
+      // ---------------- list emission: every warp copies ray parts into the ordered list ----------
+      if (ws.ent) {
+        __syncthreads();
+        const long long emit_base = b.emit_offset ? b.emit_offset[seg] : 0;
+        const long long emit_cap = b.emit_offset ? b.emit_offset[seg + 1] - emit_base : b.cap;
+        const int vmask = m.vps - 1;
+        for (int q = static_cast<int>(warp); q < 2 * n_rays; q += WARPS) {
+          const size_t at = cta_base * 2 + static_cast<size_t>(q & 1) * n_rays + (q >> 1);
+          if (!(ws.rec.info[at] & 8)) continue;
+          const unsigned o = ws.off[at];
+          const int skip = static_cast<int>(o >> 31);
+          const int n_out = static_cast<int>(ws.cnt[at]) - skip;
+          const long long first_idx = static_cast<long long>(o & 0x7FFFFFFFu);
+          for (int k = static_cast<int>(lane); k < n_out; k += 32) {
+            const long long idx = first_idx + k;
+            if (idx >= emit_cap) break;
+            const unsigned long long key = __ldcs(&ws.ent[at * static_cast<size_t>(ws.kmax) + k + skip]);
+            double* dst = b.centres_out + 3 * (emit_base + idx);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const int g = static_cast<int>((key >> (kKeyBits * a)) & ((1u << kKeyBits) - 1u)) - kKeyBias;
+              int bb = g >> m.vps_shift, vv = g & vmask;
+              if ((key >> (60 + a)) & 1u) {
+                // raw artefact index on this axis (make_ident_slow): voxel -1 of block b, or voxel vps
+                if (vv == vmask) {
+                  bb += 1;
+                  vv = -1;
+                } else {
+                  bb -= 1;
+                  vv = m.vps;
+                }
+              }
+              dst[a] = __dadd_rn(static_cast<double>(origin_point(bb, m.bs_f)), ct.d[vv + 1]);
+            }
+          }
         }
       }
     }  // views
@@ -1007,10 +1082,11 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
   }
 }
 
-size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride) {
+size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride, int emit_kmax) {
   const size_t stride = (static_cast<size_t>(n_rays) + 31) / 32 * 32;
   *rays_stride = stride;
   size_t per_cta = stride * 4 + stride + 2 * stride * (8 + 8 + 1) + (digest ? 2 * stride * 8 : 0);
+  if (emit_kmax > 0) per_cta += 2 * stride * (static_cast<size_t>(emit_kmax) * 8 + 2 + 4);
   return per_cta * static_cast<size_t>(grid) + 256;
 }
 
@@ -1057,7 +1133,8 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
                       bool wide) {
   size_t stride = 0;
   const bool extra = digest || e.kind == A3D_EVAL_VOXEL_WEIGHT;  // per-part first_hash / first value
-  wave_scratch_bytes(c.n_rays, grid, extra, &stride);
+  const int emit_kmax = b.centres_out ? c.kmax : 0;
+  wave_scratch_bytes(c.n_rays, grid, extra, &stride, emit_kmax);
   WaveScratch ws{};
   ws.rays_stride = stride;
   uint8_t* p = static_cast<uint8_t*>(scratch);
@@ -1070,8 +1147,19 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
     ws.rec.first_hash = reinterpret_cast<unsigned long long*>(p);
     p += g * stride * 2 * 8;
   }
+  if (emit_kmax > 0) {
+    ws.ent = reinterpret_cast<unsigned long long*>(p);
+    p += g * stride * 2 * 8 * static_cast<size_t>(emit_kmax);
+    ws.kmax = emit_kmax;
+  }
   ws.table = reinterpret_cast<uint32_t*>(p);
   p += g * stride * 4;
+  if (emit_kmax > 0) {
+    ws.off = reinterpret_cast<uint32_t*>(p);
+    p += g * stride * 2 * 4;
+    ws.cnt = reinterpret_cast<uint16_t*>(p);
+    p += g * stride * 2 * 2;
+  }
   ws.rec.info = p;
   p += g * stride * 2;
   ws.start_s = p;

@@ -527,6 +527,61 @@ def test_wave_dense_volume_tracks_map_edits(capi, O):
     ctx.close()
 
 
+@pytest.mark.parametrize("ckind", ["IterativeRayCaster", "SimpleRayCaster"])
+def test_wave_kernel_emits_ordered_lists(capi, O, room02, ckind):
+    """Ordered visible-voxel lists from the wavefront kernel (per-part slot ranges + scan-order
+    offsets): bit-exact against the oracle's list, single view and multi-view segment, with a
+    bounding volume, both CTA widths, and identical to what the scan-order kernel writes."""
+    import dataclasses
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    cam = dict(CAM_BASE, mounting_translation=(0.05, 0.0, 0.1))
+    caster = ctx.caster(ckind, **cam)
+    oc = om.caster(ckind, **cam)
+    pos, quat = synth.candidate_views(room02, 6, seed=23)
+    pos[3:] = pos[:3] + 0.07          # overlapping views: std::unique across view boundaries matters
+    bv = dict(x_min=2, x_max=18, y_min=2, y_max=18, z_min=0.5, z_max=7)
+    for ekind, kw in (("VoxelTypeEvaluator", {}), ("NaiveEvaluator", dict(bounding_volume=bv)),
+                      ("VoxelWeightEvaluator", {})):
+        ev = ctx.evaluator(ekind, **kw)
+        oe = O.eval_params(ekind, **kw)
+        for sl in (slice(0, 1), slice(0, 6)):
+            want, _ = oc.visible_voxels(pos[sl], quat[sl])
+            if kw:
+                want = want[O.bv_contains(oe, want) == 1]
+            wg = oc.compute_gains(oe, pos[sl], quat[sl], np.zeros(sl.stop - sl.start, np.int32), 1)
+            for width in (1, 2):
+                ctx.set_option("wave_cta", width)
+                lst, ns, gain = ctx.visible_voxels(caster, pos[sl], quat[sl], evaluator=ev)
+                assert ctx.last_cast_kernel == 2
+                assert lst.shape == want.shape and np.array_equal(lst, want)
+                assert ns == wg["n_samples"][0] and np.isclose(gain, wg["gain"][0], rtol=GAIN_RTOL, atol=1e-12)
+            ctx.set_option("wave_cta", 0)
+            ctx.set_option("cast_kernel", 1)
+            ref, _, _ = ctx.visible_voxels(caster, pos[sl], quat[sl], evaluator=ev)
+            ctx.set_option("cast_kernel", 0)
+            assert ctx.last_cast_kernel == 1 and np.array_equal(ref, want)
+        # capacity too small: the count is still reported
+        with pytest.raises(capi.A3DError):
+            ctx.visible_voxels(caster, pos[:1], quat[:1], evaluator=ev, cap=10)
+    ctx.close()
+    # 9.6 km from the origin voxblox produces artefact indices: those segments take the scan-order path
+    m0 = synth.room_map(0.2)
+    shift = np.array([3000, -2000, 500], np.int32)
+    m = dataclasses.replace(m0, block_idx=m0.block_idx + shift)
+    ctx, om = make_pair(capi, O, m)
+    caster = ctx.caster(ckind, **CAM_BASE)
+    oc = om.caster(ckind, **CAM_BASE)
+    pos, quat = synth.candidate_views(m0, 3, seed=5)
+    pos = pos + shift.astype(np.float64) * float(np.float32(0.2) * np.float32(16))
+    ev = ctx.evaluator("VoxelTypeEvaluator")
+    for v in range(3):
+        lst, _, _ = ctx.visible_voxels(caster, pos[v:v + 1], quat[v:v + 1], evaluator=ev)
+        want, _ = oc.visible_voxels(pos[v:v + 1], quat[v:v + 1])
+        assert np.array_equal(lst, want)
+    ctx.close()
+
+
 def test_wave_kernel_empty_map_and_far_poses(capi, O):
     """Unallocated space and poses beyond the 20-bit voxel-key range (scan-order re-evaluation)."""
     ctx = capi.Context(0)
