@@ -705,8 +705,13 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   // and small batches (2.2 vs 6.6 ms for one view), a loss against the scan-order kernel's streaming
   // writes for thousands of segments (36 vs 27 ms for 2048).
   const bool emit_by_wave = emit && ctx->view().vps_shift >= 0 && n_segments <= 2 * ctx->sm_count;
-  const bool wave_ok = e && !dig_dev && (!emit || emit_by_wave) &&
-                       !(e->p.kind == A3D_EVAL_VOXEL_WEIGHT && set_dig_dev) &&
+  // A list alone (no evaluator: the sensor model's own getVisibleVoxels) is the Naive fold with the
+  // gain ignored and no bounding volume.
+  EvalView no_eval{};
+  no_eval.kind = A3D_EVAL_NAIVE;
+  const EvalView& ev_view = e ? e->view : no_eval;
+  const bool wave_ok = (e || emit_by_wave) && !dig_dev && (!emit || emit_by_wave) &&
+                       !(ev_view.kind == A3D_EVAL_VOXEL_WEIGHT && set_dig_dev) &&
                        std::min(c->view.res_x, c->view.res_y) <= cast_wave_max_diag() &&
                        c->view.n_rays < (1 << 24);
   if (ctx->opt_cast_kernel == 2 && !wave_ok)
@@ -724,7 +729,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     // number of segments is slower — throughput follows the number of resident warps)
     int grid = std::max(1, std::min(n_segments, ctx->sm_count * cast_wave_blocks_per_sm()));
     size_t stride = 0;
-    const bool extra = set_dig_dev != nullptr || e->p.kind == A3D_EVAL_VOXEL_WEIGHT;
+    const bool extra = set_dig_dev != nullptr || ev_view.kind == A3D_EVAL_VOXEL_WEIGHT;
     const int emit_kmax = emit ? c->view.kmax : 0;
     while (grid > 1 &&
            wave_scratch_bytes(c->view.n_rays, grid, extra, &stride, emit_kmax) > (size_t(emit ? 16 : 6) << 30))
@@ -734,7 +739,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     CK(ctx->sc_inexact.reserve(n_words));
     CK(cudaMemsetAsync(ctx->sc_inexact.p, 0, n_words * sizeof(unsigned int), ctx->stream));
     b.work_counter = ctx->sc_counter.p;
-    launch_cast_wave(ctx->stream, ctx->view(), c->view, e->view, b, set_dig_dev != nullptr, grid,
+    launch_cast_wave(ctx->stream, ctx->view(), c->view, ev_view, b, set_dig_dev != nullptr, grid,
                      ctx->sc_wave.p, ctx->sc_inexact.p, /*wide=*/ctx->opt_wave_cta == 2 || (ctx->opt_wave_cta == 0 && n_segments <= ctx->sm_count));
     ctx->launches++;
     CK(cudaGetLastError());
