@@ -711,7 +711,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   no_eval.kind = A3D_EVAL_NAIVE;
   const EvalView& ev_view = e ? e->view : no_eval;
   const bool wave_ok = (e || emit_by_wave) && !dig_dev && (!emit || emit_by_wave) &&
-                       !(ev_view.kind == A3D_EVAL_VOXEL_WEIGHT && set_dig_dev) &&
+                       !(ev_view.kind == A3D_EVAL_VOXEL_WEIGHT && set_dig_dev) && !(emit && set_dig_dev) &&
                        std::min(c->view.res_x, c->view.res_y) <= cast_wave_max_diag() &&
                        c->view.n_rays < (1 << 24);
   if (ctx->opt_cast_kernel == 2 && !wave_ok)

@@ -465,7 +465,7 @@ __device__ __forceinline__ Prepared sample_prepare(const MapView& m, const ViewS
 // of the OCCUPIED sample that ended it, or -1.
 // rec_base + (marking part ? 0 : n_rays) + ray: index of this part's record.  Precondition:
 // rs.d < lt.d_end.
-template <int CASTER, int EVAL, bool DIGEST, class LT>
+template <int CASTER, int EVAL, bool DIGEST, bool EMIT, class LT>
 __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& ct, const EvalView& e,
                                          const ViewShared& vw, const BvGrid& bvg, const int bv_mode,
                                          const double step, RayState& rs, LT& lt, LaneCounters& lc,
@@ -570,7 +570,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     }
     lc.digest += h;
   }
-  if (ent && keep) {
+  if (EMIT && keep) {
     // list emission: the kept entry, in the part's own slot range (ordered within the part)
     unsigned bad = 0;
     const unsigned long long key = pack_key(si.id, &bad);
@@ -615,7 +615,8 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
 
 // WARPS: 2 for throughput (as many CTAs as the registers allow), 8 for batches smaller than the SM
 // count, where a view's leaf parts are better spread over more lanes of the one CTA that owns it.
-template <int CASTER, int EVAL, bool DIGEST, int WARPS>
+// EMIT: also write the ordered visible-voxel lists (8-warp CTAs only).
+template <int CASTER, int EVAL, bool DIGEST, int WARPS, bool EMIT>
 __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN_BLOCKS : 2)
     k_cast_wave(const MapView m, const CasterView c, const EvalView e, const Batch b,
                 const WaveScratch ws, unsigned int* __restrict__ inexact_flags) {
@@ -903,7 +904,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
 #pragma unroll 1
           for (int it = 0; it < max_it; ++it) {
             if (role > 0) {
-              if (ray_step<CASTER, EVAL, DIGEST>(m, ct, e, vw, bvg, bv_mode, step, rs, lt, lc, ws.rec, cta_base * 2,
+              if (ray_step<CASTER, EVAL, DIGEST, EMIT>(m, ct, e, vw, bvg, bv_mode, step, rs, lt, lc, ws.rec, cta_base * 2,
                                                  role, n_rays, ws.ent, ws.kmax))
                 role = -role;  // finished: bookkeeping after the round
             }
@@ -920,7 +921,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
                   cta_base * 2 + (role == -2 ? 0 : static_cast<size_t>(n_rays)) + lt.r[threadIdx.x];
               __stcs(&ws.rec.last_key[rec_at], pack_key(rs.prev, &bad));
               if (bad) lt.inexact = 1;
-              if (ws.ent) {
+              if (EMIT) {
                 if (lt.kept[threadIdx.x] > ws.kmax) lt.inexact = 1;  // cannot happen (kmax bounds a part)
                 ws.cnt[rec_at] = static_cast<uint16_t>(min(lt.kept[threadIdx.x], ws.kmax));
               }
@@ -957,7 +958,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
           uint64_t prev = __shfl_sync(kFull, lk, src);
           if (!below) prev = carry_key;
           const bool drop = emitted && fk == prev && (info & 16);
-          if (ws.ent) {
+          if (EMIT) {
             // where this part's kept entries go in the segment's ordered list
             const unsigned n_out = emitted ? static_cast<unsigned>(ws.cnt[at]) - (drop ? 1u : 0u) : 0u;
             unsigned incl = n_out;
@@ -981,7 +982,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
       }
 
       // ---------------- list emission: every warp copies ray parts into the ordered list ----------
-      if (ws.ent) {
+      if (EMIT) {
         __syncthreads();
         const long long emit_base = b.emit_offset ? b.emit_offset[seg] : 0;
         const long long emit_cap = b.emit_offset ? b.emit_offset[seg + 1] - emit_base : b.cap;
@@ -1095,14 +1096,19 @@ static void launch_wave_t(cudaStream_t st, const MapView& m, const CasterView& c
                           const Batch& b, bool digest, int grid, const WaveScratch& ws,
                           unsigned int* inexact, bool wide) {
   const size_t smem = static_cast<size_t>(c.diag_max) * 12;
-  if (digest && wide)
-    k_cast_wave<CASTER, EVAL, true, kWaveWideWarps><<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
+  if (ws.ent)  // list emission: always the wide CTA, never together with a digest
+    k_cast_wave<CASTER, EVAL, false, kWaveWideWarps, true>
+        <<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
+  else if (digest && wide)
+    k_cast_wave<CASTER, EVAL, true, kWaveWideWarps, false>
+        <<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
   else if (digest)
-    k_cast_wave<CASTER, EVAL, true, kWaveWarps><<<grid, kWaveThreads, smem, st>>>(m, c, e, b, ws, inexact);
+    k_cast_wave<CASTER, EVAL, true, kWaveWarps, false><<<grid, kWaveThreads, smem, st>>>(m, c, e, b, ws, inexact);
   else if (wide)
-    k_cast_wave<CASTER, EVAL, false, kWaveWideWarps><<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
+    k_cast_wave<CASTER, EVAL, false, kWaveWideWarps, false>
+        <<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
   else
-    k_cast_wave<CASTER, EVAL, false, kWaveWarps><<<grid, kWaveThreads, smem, st>>>(m, c, e, b, ws, inexact);
+    k_cast_wave<CASTER, EVAL, false, kWaveWarps, false><<<grid, kWaveThreads, smem, st>>>(m, c, e, b, ws, inexact);
 }
 
 template <int CASTER>
