@@ -1,0 +1,78 @@
+"""The wavefront kernel's "certified sample" claim (a3d_wave.cu sample_prepare), checked on the CPU:
+whenever frac(pf / voxel_size) keeps more than delta from 0, 1/2 and 1 on an axis, voxblox's own
+fp32 index arithmetic lands on block/voxel floor(T), getVoxelCenter's voxel
+(double subtraction) is the same one, and the sign of pf - centre is the one frac(T) predicts.
+numpy float32 arithmetic is IEEE round-to-nearest without contraction, like the device intrinsics."""
+import numpy as np
+import pytest
+
+F = np.float32
+EPS = F(1e-6)
+MAGIC = F(12582912.0)
+
+
+def literal(p64, vs, vps):
+    """(block*vps + voxel from getVoxelState's arithmetic, same from getVoxelCenter's, below-centre flag,
+    in-range flag) per axis, exactly as the reference computes them."""
+    vs = F(vs)
+    vs_inv = F(1.0 / float(vs))
+    bs = F(vs * F(vps))
+    bs_inv = F(1.0 / float(bs))
+    pf = p64.astype(F)
+    bi = np.floor(pf * bs_inv + EPS).astype(np.int64)
+    origin = (bi.astype(F) * bs).astype(F)
+    v_state = np.floor((pf - origin).astype(F) * vs_inv + EPS).astype(np.int64)
+    v_centre = np.floor((p64 - origin.astype(np.float64)).astype(F) * vs_inv + EPS).astype(np.int64)
+    vc = np.clip(v_state, 0, vps - 1)
+    centre = (origin + ((vc.astype(F).astype(np.float64) + 0.5) * float(vs)).astype(F)).astype(F)
+    below = (pf - centre).astype(F) < 0
+    in_range = (v_state >= 0) & (v_state < vps)
+    return bi * vps + v_state, bi * vps + v_centre, below, in_range
+
+
+def certified(p64, vs, vps, t_max):
+    vs = F(vs)
+    vs_inv = F(1.0 / float(vs))
+    pf = p64.astype(F)
+    T = (pf * vs_inv).astype(F)
+    s = (T + MAGIC).astype(F)
+    fr = (T - (s - MAGIC).astype(F)).astype(F)
+    delta = F(F(t_max * 5e-7) + F((vps + 1) * (16.0 * 5.97e-8 + 1.1e-6)))
+    af = np.abs(fr)
+    safe = (af > delta) & (af < F(0.5) - delta)
+    below_int = (fr < 0)
+    g = (s.view(np.int32).astype(np.int64) - 0x4B400000) - below_int.astype(np.int64)
+    return safe, g, ~below_int, delta
+
+
+@pytest.mark.parametrize("vs,vps", [(0.1, 16), (0.2, 16), (0.05, 16), (0.2, 8), (0.1, 32), (0.37, 4)])
+@pytest.mark.parametrize("extent", [8.0, 60.0, 700.0, 9000.0])
+def test_certified_samples_agree_with_the_literal_index_arithmetic(vs, vps, extent):
+    rng = np.random.default_rng(int(vs * 1000) + vps + int(extent))
+    n = 400_000
+    vsd = float(F(vs))
+    # uniform points, plus points hugging voxel faces and voxel centres within a few fp32 ulps
+    p = (rng.random(n) * 2.0 - 1.0) * extent
+    k = rng.integers(-int(extent / vsd), int(extent / vsd), n)
+    ulp = np.spacing(np.abs(k * vsd).astype(F)).astype(np.float64)
+    faces = k * vsd + rng.integers(-40, 41, n) * ulp * 0.25
+    centres = (k + 0.5) * vsd + rng.integers(-40, 41, n) * ulp * 0.25
+    near = k * vsd + (rng.random(n) - 0.5) * 4e-3 * vsd
+    pts = np.concatenate([p, faces, centres, near])
+    t_max = (extent + 5.0) * float(F(1.0 / vsd)) * 1.001 + 2.0
+    safe, g, below, delta = certified(pts, vs, vps, t_max)
+    g_state, g_centre, below_lit, in_range = literal(pts, vs, vps)
+    assert safe.any() and (~safe).any()
+    ok = safe
+    assert np.all(in_range[ok]), "certified sample with an artefact voxel index"
+    assert np.array_equal(g[ok], g_state[ok]), "block/voxel of getVoxelState differs"
+    assert np.array_equal(g[ok], g_centre[ok]), "voxel of getVoxelCenter differs"
+    assert np.array_equal(below[ok], below_lit[ok]), "interpolation octant differs"
+    # the margin is not vacuous: it certifies the bulk of ordinary samples at room scale
+    if extent <= 60.0:
+        assert safe[:n].mean() > 0.99
+    # and it is needed: without it the shortcut does disagree near faces / centres
+    bad = (g != g_state) | (g != g_centre) | (below != below_lit)
+    assert not np.any(bad & ok)
+    if extent >= 60.0:
+        assert np.any(bad & ~ok)
