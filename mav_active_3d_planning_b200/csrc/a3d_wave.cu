@@ -604,6 +604,9 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
 #ifndef A3D_WAVE_DRY_STEPS
 #define A3D_WAVE_DRY_STEPS 8  // round length while idle lanes cannot be refilled
 #endif
+#ifndef A3D_WAVE_SCHED_LEAF_MAX
+#define A3D_WAVE_SCHED_LEAF_MAX 32  // leaf parts the scheduler warp may cast while anti-diagonals are open
+#endif
 #ifndef A3D_WAVE_IDLE_BREAK
 #define A3D_WAVE_IDLE_BREAK 12  // idle lanes that end a round early (32: never)
 #endif
@@ -830,6 +833,11 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
               mark_head += take_mark;
               n_run += take_mark;
               n_idle -= take_mark;
+#if A3D_WAVE_SCHED_LEAF_MAX < 32
+              // keep lanes of the scheduler warp free for the marking parts of the next anti-diagonals
+              if (!sched_done)
+                n_idle = min(n_idle, max(0, A3D_WAVE_SCHED_LEAF_MAX - __popc(__ballot_sync(kFull, role == 1))));
+#endif
             }
             if (n_idle > 0) {
               // top up the ring from the shared supply
@@ -865,7 +873,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
                 __syncwarp();
               }
               const int lrank = rank - take_mark;
-              if (role == 0 && lrank >= 0 && lrank < pend_count) {
+              if (role == 0 && lrank >= 0 && lrank < min(pend_count, n_idle)) {
                 const int r = static_cast<int>(pending[(pend_head + lrank) % kPendCap]);
                 double d0 = 0.0;
                 if (ITER) {
