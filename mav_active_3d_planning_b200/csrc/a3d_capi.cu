@@ -728,6 +728,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     // as many CTAs as can be resident (measured: trimming the grid so that every CTA gets the same
     // number of segments is slower — throughput follows the number of resident warps)
     int grid = std::max(1, std::min(n_segments, ctx->sm_count * cast_wave_blocks_per_sm()));
+    if (emit) grid = std::max(1, std::min(n_segments, 2 * ctx->sm_count));  // resident 8-warp CTAs
     size_t stride = 0;
     const bool extra = set_dig_dev != nullptr || ev_view.kind == A3D_EVAL_VOXEL_WEIGHT;
     const int emit_kmax = emit ? c->view.kmax : 0;
