@@ -158,7 +158,7 @@ struct a3d_ctx {
   DevBuf<uint8_t> sc_wave;
   int opt_cast_kernel = 0;  // 0 auto, 1 scan-order kernel (k_cast_gain), 2 wavefront kernel (k_cast_wave)
   int last_cast_kernel = 0;
-  int opt_wave_cta = 0;  // 0 auto (8-warp CTAs for batches up to the SM count), 1 always 2 warps, 2 always 8
+  int opt_wave_cta = 0;  // 0 auto (8-warp CTAs for batches up to twice the SM count), 1 always 2 warps, 2 always 8
 
   int fail(int code, const std::string& msg) const {
     err = msg;
@@ -741,7 +741,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     CK(cudaMemsetAsync(ctx->sc_inexact.p, 0, n_words * sizeof(unsigned int), ctx->stream));
     b.work_counter = ctx->sc_counter.p;
     launch_cast_wave(ctx->stream, ctx->view(), c->view, ev_view, b, set_dig_dev != nullptr, grid,
-                     ctx->sc_wave.p, ctx->sc_inexact.p, /*wide=*/ctx->opt_wave_cta == 2 || (ctx->opt_wave_cta == 0 && n_segments <= ctx->sm_count));
+                     ctx->sc_wave.p, ctx->sc_inexact.p, /*wide=*/ctx->opt_wave_cta == 2 || (ctx->opt_wave_cta == 0 && n_segments <= 2 * ctx->sm_count));
     ctx->launches++;
     CK(cudaGetLastError());
     seg_mask = ctx->sc_inexact.p;

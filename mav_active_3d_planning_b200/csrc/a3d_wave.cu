@@ -616,8 +616,8 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
 
 }  // namespace
 
-// WARPS: 2 for throughput (as many CTAs as the registers allow), 8 for batches smaller than the SM
-// count, where a view's leaf parts are better spread over more lanes of the one CTA that owns it.
+// WARPS: 2 for throughput (as many CTAs as the registers allow), 8 for batches up to twice the SM
+// count (two such CTAs fit an SM), where a view's leaf parts are better spread over more lanes of the one CTA that owns it.
 // EMIT: also write the ordered visible-voxel lists (8-warp CTAs only).
 template <int CASTER, int EVAL, bool DIGEST, int WARPS, bool EMIT>
 __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN_BLOCKS : 2)
