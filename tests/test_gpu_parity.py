@@ -367,6 +367,9 @@ def _check_wave(got, want):
                                                      z_max=6, rotation=20.0))),
     ("NaiveEvaluator", {}),
     ("FrontierEvaluator", dict(accurate_frontiers=True)),
+    ("FrontierEvaluator", dict(surface_frontiers=False)),
+    # another checking distance: the precomputed frontier bits do not apply, literal neighbour test
+    ("FrontierEvaluator", dict(surface_frontiers=False, checking_distance=2.0)),
 ])
 def test_wave_kernel_cfg1(capi, O, room02, ckind, ekind, kw):
     from mav_active_3d_planning_b200 import synth
@@ -633,7 +636,9 @@ def test_voxel_weight_evaluator(capi, O, room02, ckind):
     pos, quat = synth.candidate_views(room02, 24, seed=51)
     for kw in (dict(), dict(frontier_voxel_weight=0.5, min_impact_factor=0.02, new_voxel_weight=0.05,
                             ray_angle_x=0.003, ray_angle_y=0.002, accurate_frontiers=True,
-                            bounding_volume=dict(x_min=3, x_max=17, y_min=3, y_max=17, z_min=0.5, z_max=8))):
+                            bounding_volume=dict(x_min=3, x_max=17, y_min=3, y_max=17, z_min=0.5, z_max=8)),
+               # another checking distance: the precomputed frontier bits do not apply
+               dict(frontier_voxel_weight=0.5, new_voxel_weight=0.05, checking_distance=1.5)):
         ev = ctx.evaluator("VoxelWeightEvaluator", **kw)
         oe = O.eval_params("VoxelWeightEvaluator", **kw)
         got = ctx.compute_gains(caster, ev, pos, quat)
