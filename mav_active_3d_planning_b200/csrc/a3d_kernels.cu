@@ -167,8 +167,14 @@ __global__ void k_build_meta(MapView m, int n, const int32_t* __restrict__ slots
                                   static_cast<double>(center_point(y, m.vs_f)));
       const double cz = __dadd_rn(static_cast<double>(origin_point(bi[2], m.bs_f)),
                                   static_cast<double>(center_point(z, m.vs_f)));
-      const int centre = voxel_state_generic(m, __double2float_rn(cx), __double2float_rn(cy),
-                                             __double2float_rn(cz));
+      // The centre lies within a few float ulps of where the voxel's 8 cells meet: when their classes
+      // agree, the state there is that class whichever cell the rounding picks; else literally.
+      const uint32_t cells = word & 0xFFFFu;
+      const int centre = cells == 0x0000u ? 2
+                         : cells == 0x5555u ? 1
+                         : cells == 0xAAAAu ? 0
+                                            : voxel_state_generic(m, __double2float_rn(cx), __double2float_rn(cy),
+                                                                  __double2float_rn(cz));
       word |= static_cast<uint32_t>(centre) << 16;
       word |= static_cast<uint32_t>(obs) << 18;
       mword_slab[static_cast<size_t>(slot) * m.nv + mword_offset(m, x, y, z)] = word;
