@@ -6,6 +6,7 @@
 //                                                    from the YAML, upload the map dump, evaluate the
 //                                                    segments one by one (reference API) and as a batch
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -159,7 +160,10 @@ int runGains(char** argv) {
   out << "grid " << cam->rayGridX() << " " << cam->rayGridY() << " " << cam->numSections() << "\n";
   // reference API: one segment per call, voxel list stored in the segment
   for (int s = 0; s < n_seg; ++s) {
+    const auto t0 = std::chrono::steady_clock::now();
     const bool ok = eval->computeGain(segments[s]);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    out << "# computeGain " << s << " " << ms << " ms\n";
     auto* info = dynamic_cast<trajectory_evaluator::SimulatedSensorInfo*>(segments[s]->info.get());
     out << "single " << s << " " << ok << " " << segments[s]->gain << " "
         << (info ? info->visible_voxels.size() : 0) << " " << (info ? digestOf(info->visible_voxels) : 0)
