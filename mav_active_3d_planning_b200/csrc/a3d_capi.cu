@@ -181,6 +181,7 @@ struct a3d_ctx {
     }
     m.P = P;
     m.P3 = P3;
+    m.n_slots = static_cast<int32_t>(slab_slots);
     m.brick_nx = (vps % 4 == 0) ? vps / 4 : 0;
     m.vps_shift = -1;
     for (int k = 0; k < 7; ++k)

@@ -37,6 +37,24 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// -DA3D_BOUNDS_CHECK: every computed index into the map mirror / kernel scratch is checked on the
+// device and a violation traps (compute-sanitizer is not available on the GPU pool this was
+// developed on; the GPU test-suite is run once against such a build).
+#ifdef A3D_BOUNDS_CHECK
+#include <cstdio>
+#define A3D_DEV_CHECK(cond)                                                                  \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      printf("A3D_DEV_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__);               \
+      __trap();                                                                              \
+    }                                                                                        \
+  } while (0)
+#else
+#define A3D_DEV_CHECK(cond) \
+  do {                      \
+  } while (0)
+#endif
+
 namespace a3d {
 
 // Unobserved voxels are stored as this exact bit pattern in the distance slab (observed flag
@@ -66,6 +84,7 @@ struct MapView {
   int32_t nv;                        // vps^3
   int32_t P;                         // vps + 2
   int32_t P3;                        // P^3
+  int32_t n_slots;                   // slots the slabs hold (bounds checks)
   int32_t brick_nx;                  // vps/4 if the meta words are stored in 4x4x2 bricks, else 0
   int32_t vps_shift;                 // log2(vps) when vps is a power of two, else -1
   // dense meta volume: the meta words again, indexed by GLOBAL voxel coordinate g = block*vps + voxel
@@ -148,6 +167,9 @@ __device__ __forceinline__ void init_center_tables(const MapView& m, CenterTable
 // stored in 4x4x2 bricks (32 words = one 128-byte line) so that a step in any direction usually stays
 // in the line the lane touched last; otherwise plain voxblox linear order.
 __device__ __forceinline__ int mword_offset(const MapView& m, int x, int y, int z) {
+  A3D_DEV_CHECK(static_cast<unsigned>(x) < static_cast<unsigned>(m.vps) &&
+                static_cast<unsigned>(y) < static_cast<unsigned>(m.vps) &&
+                static_cast<unsigned>(z) < static_cast<unsigned>(m.vps));
   if (m.brick_nx) {
     const int brick = ((z >> 1) * m.brick_nx + (y >> 2)) * m.brick_nx + (x >> 2);
     return (brick << 5) | ((z & 1) << 4) | ((y & 3) << 2) | (x & 3);
@@ -158,11 +180,14 @@ __device__ __forceinline__ int mword_offset(const MapView& m, int x, int y, int 
 // Offset of box-relative voxel (u0,u1,u2) in the dense meta volume: 4x4x2 bricks of 32 words (one
 // 128-byte line), bricks x fastest.  vol_n[] are multiples of vps, vps a power of two >= 4.
 __device__ __forceinline__ uint32_t vol_offset(const MapView& m, uint32_t u0, uint32_t u1, uint32_t u2) {
+  A3D_DEV_CHECK(u0 < m.vol_n[0] && u1 < m.vol_n[1] && u2 < m.vol_n[2]);
   const uint32_t brick = ((u2 >> 1) * m.vol_by + (u1 >> 2)) * m.vol_bx + (u0 >> 2);
   return (brick << 5) | ((u2 & 1u) << 4) | ((u1 & 3u) << 2) | (u0 & 3u);
 }
 
 __device__ __forceinline__ size_t padded_index(const MapView& m, int slot, int x, int y, int z) {
+  A3D_DEV_CHECK(slot >= 0 && slot < m.n_slots && x >= -1 && x <= m.vps && y >= -1 && y <= m.vps && z >= -1 &&
+                z <= m.vps);
   return static_cast<size_t>(slot) * m.P3 + ((z + 1) * m.P + (y + 1)) * m.P + (x + 1);
 }
 

@@ -576,6 +576,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     const unsigned long long key = pack_key(si.id, &bad);
     if (bad) lt.inexact = 1;
     const int k = lt.kept[threadIdx.x];
+    A3D_DEV_CHECK(lt.r[threadIdx.x] >= 0 && lt.r[threadIdx.x] < n_rays && k < kmax);
     if (k < kmax)
       __stcs(&ent[(rec_base + (role == 2 ? 0 : n_rays) + lt.r[threadIdx.x]) * static_cast<size_t>(kmax) + k], key);
     lt.kept[threadIdx.x] = k + 1;
@@ -584,6 +585,7 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
     // record of the part's first entry, written once
     unsigned bad = 0;
     const size_t rec_at = rec_base + (role == 2 ? 0 : n_rays) + lt.r[threadIdx.x];
+    A3D_DEV_CHECK(lt.r[threadIdx.x] >= 0 && lt.r[threadIdx.x] < n_rays);
     __stcs(&rec.first_key[rec_at], pack_key(si.id, &bad));
     if (bad) lt.inexact = 1;
     __stcs(&rec.info[rec_at], static_cast<uint8_t>((keep ? cat : kCatNone) | 8 | (keep ? 16 : 0)));
@@ -779,6 +781,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
                     const int tmax = mx == 0 ? n - 1 : n - 2 - (31 - __clz(mx));
                     const int t = min(tmax, b_tl);
                     const int val = (t == b_sh) ? -1 : t + 1;
+                    A3D_DEV_CHECK((b_ri + dx) * c.res_y + b_rj + dy < n_rays);
                     atomicMax(&table[(b_ri + dx) * c.res_y + b_rj + dy], b_wr | static_cast<uint8_t>(val));
                   }
                 }
@@ -804,6 +807,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
               }
               const bool marking = s >= 0 && s < n - 1;
               const unsigned mm = __ballot_sync(kFull, marking);
+              A3D_DEV_CHECK(n_mark + __popc(mm) <= c.diag_max);
               if (marking)
                 s_mark_list[n_mark + __popc(mm & lt_mask)] = (static_cast<unsigned>(r) << 8) | s;
               n_mark += __popc(mm);
@@ -1006,6 +1010,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN
             const long long idx = first_idx + k;
             if (idx >= emit_cap) break;
             const unsigned long long key = __ldcs(&ws.ent[at * static_cast<size_t>(ws.kmax) + k + skip]);
+            A3D_DEV_CHECK(k + skip < static_cast<int>(ws.cnt[at]) && ws.cnt[at] <= ws.kmax);
             double* dst = b.centres_out + 3 * (emit_base + idx);
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
