@@ -6,6 +6,9 @@
 //                                                    from the YAML, upload the map dump, evaluate the
 //                                                    segments one by one (reference API) and as a batch
 #include <cstdio>
+#include <bitset>
+#include <map>
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <fstream>
@@ -13,6 +16,7 @@
 #include <memory>
 
 #include "a3d_host/trajectory_evaluator.h"
+#include "a3d_host/voxblox_adapter.h"
 #include "a3d_host/yaml_factory.h"
 
 using namespace active_3d_planning;  // NOLINT
@@ -353,6 +357,134 @@ int runYaw(char** argv) {
   return 0;
 }
 
+// ---- a mock of the part of voxblox's layer API the adapter uses (same names and signatures) -------
+namespace mockvbx {
+struct Update {
+  enum Status { kMap, kMesh, kEsdf, kCount };
+};
+struct BlockIndex {
+  int v[3];
+  int x() const { return v[0]; }
+  int y() const { return v[1]; }
+  int z() const { return v[2]; }
+  bool operator<(const BlockIndex& o) const {
+    return std::lexicographical_compare(v, v + 3, o.v, o.v + 3);
+  }
+};
+typedef std::vector<BlockIndex> BlockIndexList;
+struct EsdfVoxel {
+  float distance = 0.0f;
+  bool observed = false;
+  bool hallucinated = false, in_queue = false, fixed = false;
+};
+struct TsdfVoxel {
+  float distance = 0.0f;
+  float weight = 0.0f;
+};
+template <class V>
+struct Block {
+  std::vector<V> voxels;
+  std::bitset<Update::kCount> upd;
+  size_t num_voxels() const { return voxels.size(); }
+  const V& getVoxelByLinearIndex(size_t i) const { return voxels[i]; }
+  V& getVoxelByLinearIndex(size_t i) { return voxels[i]; }
+  std::bitset<Update::kCount>& updated() { return upd; }
+};
+template <class V>
+struct Layer {
+  float vs = 0.1f;
+  size_t vps = 16;
+  std::map<BlockIndex, std::shared_ptr<Block<V>>> blocks;
+  size_t voxels_per_side() const { return vps; }
+  float voxel_size() const { return vs; }
+  void getAllUpdatedBlocks(Update::Status bit, BlockIndexList* out) const {
+    for (const auto& kv : blocks)
+      if (kv.second->upd[bit]) out->push_back(kv.first);
+  }
+  Block<V>& getBlockByIndex(const BlockIndex& i) { return *blocks.at(i); }
+  std::shared_ptr<Block<V>> getBlockPtrByIndex(const BlockIndex& i) {
+    auto it = blocks.find(i);
+    return it == blocks.end() ? nullptr : it->second;
+  }
+};
+}  // namespace mockvbx
+
+// the voxblox layer adapter: fill mock layers from the map file, sync, evaluate, touch one block, sync
+int runAdapter(char** argv) {
+  YamlTree tree;
+  std::string err;
+  if (!tree.loadFile(argv[2], &err)) {
+    std::cerr << err << "\n";
+    return 2;
+  }
+  int32_t vps = 0, n_blocks = 0;
+  std::vector<int32_t> idx;
+  std::vector<float> dist, weight;
+  std::vector<uint8_t> obs;
+  if (!loadMap(argv[3], &tree, &vps, &n_blocks, &idx, &dist, &obs, &weight)) {
+    std::cerr << "cannot read map\n";
+    return 2;
+  }
+  const size_t nv = static_cast<size_t>(vps) * vps * vps;
+  mockvbx::Layer<mockvbx::EsdfVoxel> esdf;
+  mockvbx::Layer<mockvbx::TsdfVoxel> tsdf;
+  esdf.vps = tsdf.vps = static_cast<size_t>(vps);
+  for (int b = 0; b < n_blocks; ++b) {
+    const mockvbx::BlockIndex bi{{idx[3 * b], idx[3 * b + 1], idx[3 * b + 2]}};
+    auto eb = std::make_shared<mockvbx::Block<mockvbx::EsdfVoxel>>();
+    eb->voxels.resize(nv);
+    for (size_t i = 0; i < nv; ++i) {
+      eb->voxels[i].distance = dist[b * nv + i];
+      eb->voxels[i].observed = obs[b * nv + i] != 0;
+    }
+    eb->upd.set(mockvbx::Update::kMap);
+    eb->upd.set(mockvbx::Update::kMesh);
+    esdf.blocks[bi] = eb;
+    if (b % 3 != 0) {  // the TSDF layer lacks some blocks: weight 0 there
+      auto tb = std::make_shared<mockvbx::Block<mockvbx::TsdfVoxel>>();
+      tb->voxels.resize(nv);
+      for (size_t i = 0; i < nv; ++i) tb->voxels[i].weight = weight[b * nv + i];
+      tsdf.blocks[bi] = tb;
+    }
+  }
+  TestPlanner planner(tree);
+  planner.build("/map", "/trajectory_evaluator");
+  auto* vmap = dynamic_cast<map::VoxbloxMap*>(planner.map_.get());
+  auto* eval = dynamic_cast<trajectory_evaluator::SimulatedSensorEvaluator*>(planner.evaluator_.get());
+  if (!vmap || !eval) return 2;
+  std::ofstream out(argv[5]);
+  out.precision(17);
+  const int sent = map::syncUpdatedBlocks<mockvbx::BlockIndexList>(vmap, &esdf, &tsdf, mockvbx::Update::kMap);
+  size_t still_map = 0, still_mesh = 0;
+  for (const auto& kv : esdf.blocks) {
+    still_map += kv.second->upd[mockvbx::Update::kMap];
+    still_mesh += kv.second->upd[mockvbx::Update::kMesh];
+  }
+  out << "sent " << sent << " blocks " << vmap->numBlocks() << " flags_map " << still_map << " flags_mesh "
+      << still_mesh << "\n";
+  out << "again " << map::syncUpdatedBlocks<mockvbx::BlockIndexList>(vmap, &esdf, &tsdf, mockvbx::Update::kMap) << "\n";
+  TrajectorySegment root;
+  std::vector<TrajectorySegment*> segments;
+  loadSegments(argv[4], &root, &segments);
+  const bool bok = eval->computeGains(segments);
+  for (size_t s = 0; s < segments.size(); ++s) out << "batch " << s << " " << bok << " " << segments[s]->gain << "\n";
+  // weights: present block vs block missing in the TSDF layer
+  const Eigen::Vector3d p = segments[0]->trajectory.back().position_W;
+  out << "weight " << vmap->getVoxelWeight(p) << "\n";
+  // one block changes: everything becomes observed free space at 1 m
+  auto& first = *esdf.blocks.begin();
+  for (auto& v : first.second->voxels) {
+    v.distance = 1.0f;
+    v.observed = true;
+  }
+  first.second->upd.set(mockvbx::Update::kMap);
+  out << "delta " << map::syncUpdatedBlocks<mockvbx::BlockIndexList>(vmap, &esdf, &tsdf, mockvbx::Update::kMap) << " "
+      << first.first.x() << " " << first.first.y() << " " << first.first.z() << "\n";
+  eval->computeGains(segments);
+  for (size_t s = 0; s < segments.size(); ++s) out << "batch2 " << s << " 1 " << segments[s]->gain << "\n";
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -360,10 +492,11 @@ int main(int argc, char** argv) {
     if (argc >= 3 && std::strcmp(argv[1], "config") == 0) return runConfig(argc, argv);
     if (argc >= 6 && std::strcmp(argv[1], "gains") == 0) return runGains(argv);
     if (argc >= 6 && std::strcmp(argv[1], "yaw") == 0) return runYaw(argv);
+    if (argc >= 6 && std::strcmp(argv[1], "adapter") == 0) return runAdapter(argv);
   } catch (const std::exception& e) {
     std::cerr << "exception: " << e.what() << "\n";
     return 3;
   }
-  std::cerr << "usage: test_host config <yaml> [ns] | gains|yaw <yaml> <map.bin> <segments.bin> <out.txt>\n";
+  std::cerr << "usage: test_host config <yaml> [ns] | gains|yaw|adapter <yaml> <map.bin> <segments.bin> <out.txt>\n";
   return 1;
 }

@@ -303,3 +303,43 @@ def test_yaw_planning_evaluators_match_oracle(built, room02, tmp_path, cfg, ekin
                 assert got["cost"] == 1.0 + applied[best] and got["value"] == score[best]
         assert max(want) > 0
     assert (r["device_list"] > 0) == (cfg == "planner_yaw_simple_value.yaml")
+
+
+@pytest.mark.gpu
+def test_voxblox_layer_adapter(built, room02, tmp_path):
+    """SURVEY.md §8(f)-3: blocks flagged Update::kMap in (mock) voxblox ESDF/TSDF layers reach the
+    device mirror through map::syncUpdatedBlocks; gains afterwards equal the oracle's on the same map,
+    the flag is cleared (other flags untouched), a second sync sends nothing, a changed block one."""
+    from mav_active_3d_planning_b200 import synth
+    from oracle import oracle_py as O
+    pos, quat = synth.candidate_views(room02, 5, seed=11)
+    mp, sp = write_inputs(str(tmp_path), room02, pos, quat, 1, 0)
+    out = os.path.join(str(tmp_path), "adapter.txt")
+    subprocess.run([EXE, "adapter", os.path.join(GOLD, "planner_naive_iterative.yaml"), mp, sp, out],
+                   check=True, timeout=300)
+    lines = [l.split() for l in open(out)]
+    sent = next(l for l in lines if l[0] == "sent")
+    assert int(sent[1]) == room02.n_blocks and int(sent[3]) == room02.n_blocks
+    assert int(sent[5]) == 0 and int(sent[7]) == room02.n_blocks      # kMap cleared, kMesh untouched
+    assert int(next(l for l in lines if l[0] == "again")[1]) == 0
+    om = O.OracleMap.from_synth(room02)
+    cam = dict(resolution_x=320, resolution_y=240, focal_length=160.0, ray_length=5.0)
+    oc = om.caster("IterativeRayCaster", **cam)
+    ep = O.eval_params("NaiveEvaluator", bounding_volume=dict(x_min=2, x_max=18, y_min=2, y_max=18, z_min=0.5, z_max=7))
+    want = oc.compute_gains(ep, pos, quat)["gain"]
+    got = {int(l[1]): float(l[3]) for l in lines if l[0] == "batch"}
+    assert [got[s] for s in range(5)] == list(want)
+    # TSDF weight at the first pose: the mock TSDF layer lacks every third block (weight 0 there)
+    w = np.array(room02.weight, np.float32)
+    w[0::3] = 0.0
+    om.upload_blocks(room02.block_idx, room02.dist, room02.observed, w)
+    assert float(next(l for l in lines if l[0] == "weight")[1]) == om.voxel_weight(pos[:1])[0]
+    # the changed block
+    d = next(l for l in lines if l[0] == "delta")
+    assert int(d[1]) == 1
+    bi = np.array([[int(d[2]), int(d[3]), int(d[4])]], np.int32)
+    nv = room02.vps ** 3
+    om.upload_blocks(bi, np.full((1, nv), 1.0, np.float32), np.ones((1, nv), np.uint8), np.zeros((1, nv), np.float32))
+    want2 = oc.compute_gains(ep, pos, quat)["gain"]
+    got2 = {int(l[1]): float(l[3]) for l in lines if l[0] == "batch2"}
+    assert [got2[s] for s in range(5)] == list(want2)
