@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Randomised cross-check of the wavefront kernel (both CTA widths, gains and ordered lists) against the
+scan-order kernel, which tests/test_gpu_parity.py pins to the oracle: random voxel sizes, voxels per
+side, camera intrinsics / mounting, casters, evaluators, bounding volumes, map offsets and segment
+layouts.  Integer outputs and lists must agree bit for bit, gains to 1e-9 relative.
+    python tools/fuzz_wave_vs_scan.py --cases 60 --seed 1"""
+import argparse
+import dataclasses
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mav_active_3d_planning_b200 import capi, synth  # noqa: E402
+
+
+def one_case(rng, case):
+    vs = float(rng.choice([0.08, 0.1, 0.15, 0.2, 0.3]))
+    vps = int(rng.choice([8, 16, 16, 32]))
+    m = synth.room_map(vs, vps=vps)
+    shift = np.zeros(3, np.int32)
+    if rng.random() < 0.3:
+        shift = rng.integers(-400, 400, 3).astype(np.int32)
+        m = dataclasses.replace(m, block_idx=m.block_idx + shift)
+    ctx = capi.Context(0)
+    ctx.upload_map(m)
+    ckind = str(rng.choice(["IterativeRayCaster", "SimpleRayCaster", "IterativeRayCaster"]))
+    cam = dict(resolution_x=int(rng.choice([160, 320, 400])), resolution_y=int(rng.choice([120, 240, 300])),
+               focal_length=float(rng.choice([100.0, 160.0, 250.0])), ray_length=float(rng.choice([3.0, 5.0, 7.5])),
+               downsampling_factor=float(rng.choice([1.0, 1.5, 2.5])))
+    if rng.random() < 0.5:
+        q = rng.normal(size=4)
+        q[0] = abs(q[0]) + 2.0
+        cam.update(mounting_translation=tuple(rng.normal(0, 0.1, 3)), mounting_rotation=tuple(q / np.linalg.norm(q)))
+    caster = ctx.caster(ckind, **cam)
+    ekind = str(rng.choice(["VoxelTypeEvaluator", "NaiveEvaluator", "FrontierEvaluator", "VoxelWeightEvaluator"]))
+    kw = {}
+    if rng.random() < 0.6:
+        lo = rng.random(3) * 4.0
+        hi = np.array(m.extent) - rng.random(3) * 4.0
+        off = shift.astype(np.float64) * float(np.float32(vs) * np.float32(vps))
+        kw["bounding_volume"] = dict(x_min=lo[0] + off[0], x_max=hi[0] + off[0], y_min=lo[1] + off[1],
+                                     y_max=hi[1] + off[1], z_min=lo[2] + off[2], z_max=hi[2] + off[2],
+                                     rotation=float(rng.choice([0.0, 0.0, 17.0])))
+    if ekind in ("FrontierEvaluator", "VoxelWeightEvaluator"):
+        kw.update(accurate_frontiers=bool(rng.random() < 0.4), surface_frontiers=bool(rng.random() < 0.6),
+                  checking_distance=float(rng.choice([1.0, 1.0, 1.0, 2.0])))
+    if ekind == "VoxelWeightEvaluator":
+        kw.update(frontier_voxel_weight=float(rng.choice([0.0, 0.5, 1.0])), new_voxel_weight=0.05)
+    ev = ctx.evaluator(ekind, **kw)
+    n_views = int(rng.choice([1, 5, 24, 160, 320]))
+    pos, quat = synth.candidate_views(synth.room_map(vs, vps=vps), n_views, seed=int(rng.integers(1 << 30)))
+    pos = pos + shift.astype(np.float64) * float(np.float32(vs) * np.float32(vps))
+    if rng.random() < 0.4 and n_views >= 5:   # multi-view segments
+        per = int(rng.choice([2, 3, 5]))
+        n_seg = n_views // per
+        seg = np.repeat(np.arange(n_seg, dtype=np.int32), per)
+        pos, quat = pos[:n_seg * per], quat[:n_seg * per]
+        args = (pos, quat, seg, n_seg)
+    else:
+        args = (pos, quat)
+    sd = ekind != "VoxelWeightEvaluator"
+    ctx.set_option("cast_kernel", 1)
+    ref = ctx.compute_gains(caster, ev, *args, digests=False, set_digests=sd)
+    ctx.set_option("cast_kernel", 2)
+    bad = []
+    for width in (1, 2):
+        ctx.set_option("wave_cta", width)
+        got = ctx.compute_gains(caster, ev, *args, digests=False, set_digests=sd)
+        for k in ("n_samples", "n_visible") + (("set_digest",) if sd else ()):
+            if not np.array_equal(got[k], ref[k]):
+                bad.append(f"{k} width {width}")
+        if not np.allclose(got["gain"], ref["gain"], rtol=1e-9, atol=1e-12):
+            bad.append(f"gain width {width}")
+    ctx.set_option("wave_cta", 0)
+    # ordered list of the first segment's views
+    first = slice(0, 1) if len(args) == 2 else slice(0, int(np.sum(args[2] == 0)))
+    ctx.set_option("cast_kernel", 1)
+    l_ref, _, g_ref = ctx.visible_voxels(caster, pos[first], quat[first], evaluator=ev)
+    ctx.set_option("cast_kernel", 0)
+    l_got, _, g_got = ctx.visible_voxels(caster, pos[first], quat[first], evaluator=ev)
+    if ctx.last_cast_kernel != 2:
+        bad.append("list call did not use the wavefront kernel")
+    if l_ref.shape != l_got.shape or not np.array_equal(l_ref, l_got):
+        bad.append("ordered list")
+    if not np.isclose(g_ref, g_got, rtol=1e-9, atol=1e-12):
+        bad.append("list gain")
+    ctx.close()
+    return dict(case=case, vs=vs, vps=vps, caster=ckind, evaluator=ekind, kw={k: (v if not isinstance(v, dict) else "bv") for k, v in kw.items()},
+                cam=cam["resolution_x"], shift=shift.tolist(), views=n_views, segments=len(ref["gain"]),
+                samples=int(ref["n_samples"].sum()), list_len=int(len(l_ref)), bad=bad)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=40)
+    ap.add_argument("--seed", type=int, default=1)
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    t0 = time.time()
+    n_bad = 0
+    total = 0
+    for c in range(args.cases):
+        r = one_case(rng, c)
+        total += r["samples"]
+        if r["bad"]:
+            n_bad += 1
+            print(json.dumps(r), flush=True)
+    print(json.dumps(dict(cases=args.cases, seed=args.seed, mismatching_cases=n_bad, samples_checked=total,
+                          seconds=round(time.time() - t0, 1))))
+    sys.exit(1 if n_bad else 0)
+
+
+if __name__ == "__main__":
+    main()
