@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mav_active_3d_planning_b200 import capi, synth  # noqa: E402
 
 
-def one_case(rng, case):
+def one_case(rng, case, oracle=None, max_views=None):
     vs = float(rng.choice([0.08, 0.1, 0.15, 0.2, 0.3]))
     vps = int(rng.choice([8, 16, 16, 32]))
     m = synth.room_map(vs, vps=vps)
@@ -52,6 +52,8 @@ def one_case(rng, case):
         kw.update(frontier_voxel_weight=float(rng.choice([0.0, 0.5, 1.0])), new_voxel_weight=0.05)
     ev = ctx.evaluator(ekind, **kw)
     n_views = int(rng.choice([1, 5, 24, 160, 320]))
+    if max_views:
+        n_views = min(n_views, max_views)
     pos, quat = synth.candidate_views(synth.room_map(vs, vps=vps), n_views, seed=int(rng.integers(1 << 30)))
     pos = pos + shift.astype(np.float64) * float(np.float32(vs) * np.float32(vps))
     if rng.random() < 0.4 and n_views >= 5:   # multi-view segments
@@ -67,6 +69,16 @@ def one_case(rng, case):
     ref = ctx.compute_gains(caster, ev, *args, digests=False, set_digests=sd)
     ctx.set_option("cast_kernel", 2)
     bad = []
+    if oracle is not None:
+        # the scan-order kernel itself against the CPU oracle on this random configuration
+        om = oracle.OracleMap.from_synth(m)
+        oc = om.caster(ckind, **cam)
+        want = oc.compute_gains(oracle.eval_params(ekind, **kw), *args, n_threads=8)
+        for k in ("n_samples", "n_visible") + (("set_digest",) if sd else ()):
+            if not np.array_equal(ref[k], want[k]):
+                bad.append(f"oracle {k}")
+        if not np.allclose(ref["gain"], want["gain"], rtol=1e-5, atol=1e-12):
+            bad.append("oracle gain")
     for width in (1, 2):
         ctx.set_option("wave_cta", width)
         got = ctx.compute_gains(caster, ev, *args, digests=False, set_digests=sd)
@@ -98,13 +110,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--oracle", action="store_true",
+                    help="also check the scan-order kernel against the CPU oracle (at most 5 views per case)")
     args = ap.parse_args()
+    oracle = None
+    if args.oracle:
+        from oracle import oracle_py as oracle  # noqa: F811  (test infrastructure: this tool is a checker)
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
     n_bad = 0
     total = 0
     for c in range(args.cases):
-        r = one_case(rng, c)
+        r = one_case(rng, c, oracle=oracle, max_views=5 if oracle else None)
         total += r["samples"]
         if r["bad"]:
             n_bad += 1
