@@ -27,6 +27,26 @@ def one_case(rng, case, oracle=None, max_views=None):
         m = dataclasses.replace(m, block_idx=m.block_idx + shift)
     ctx = capi.Context(0)
     ctx.upload_map(m)
+    om = oracle.OracleMap.from_synth(m) if oracle is not None else None
+    edits = rng.random() < 0.4
+    if edits:
+        # a cast first (builds the dense volume), then overwrites, removals and new blocks outside the box
+        warm = ctx.caster("SimpleRayCaster", resolution_x=160, resolution_y=120, focal_length=100.0, ray_length=3.0)
+        p0, q0 = synth.candidate_views(synth.room_map(vs, vps=vps), 1, seed=3)
+        ctx.compute_gains(warm, ctx.evaluator("NaiveEvaluator"),
+                          p0 + shift.astype(np.float64) * float(np.float32(vs) * np.float32(vps)), q0, digests=False)
+        sel = rng.choice(m.n_blocks, max(1, m.n_blocks // 10), replace=False)
+        nd = (m.dist[sel] + rng.normal(0, 0.05, m.dist[sel].shape)).astype(np.float32)
+        no = (rng.random(m.observed[sel].shape) < 0.7).astype(np.uint8)
+        rem = rng.choice(m.n_blocks, max(1, m.n_blocks // 20), replace=False)
+        far = (m.block_idx[rng.choice(m.n_blocks, 2, replace=False)] + np.array([[40, 0, 0], [0, -35, 3]])).astype(np.int32)
+        fd = np.full((2, vps ** 3), 0.5 * vs, np.float32)
+        for mm in (ctx, om):
+            if mm is None:
+                continue
+            mm.upload_blocks(m.block_idx[sel], nd, no)
+            mm.remove_blocks(m.block_idx[rem])
+            mm.upload_blocks(far, fd, np.ones((2, vps ** 3), np.uint8))
     ckind = str(rng.choice(["IterativeRayCaster", "SimpleRayCaster", "IterativeRayCaster"]))
     cam = dict(resolution_x=int(rng.choice([160, 320, 400])), resolution_y=int(rng.choice([120, 240, 300])),
                focal_length=float(rng.choice([100.0, 160.0, 250.0])), ray_length=float(rng.choice([3.0, 5.0, 7.5])),
@@ -71,7 +91,6 @@ def one_case(rng, case, oracle=None, max_views=None):
     bad = []
     if oracle is not None:
         # the scan-order kernel itself against the CPU oracle on this random configuration
-        om = oracle.OracleMap.from_synth(m)
         oc = om.caster(ckind, **cam)
         want = oc.compute_gains(oracle.eval_params(ekind, **kw), *args, n_threads=8)
         for k in ("n_samples", "n_visible") + (("set_digest",) if sd else ()):
@@ -101,7 +120,7 @@ def one_case(rng, case, oracle=None, max_views=None):
     if not np.isclose(g_ref, g_got, rtol=1e-9, atol=1e-12):
         bad.append("list gain")
     ctx.close()
-    return dict(case=case, vs=vs, vps=vps, caster=ckind, evaluator=ekind, kw={k: (v if not isinstance(v, dict) else "bv") for k, v in kw.items()},
+    return dict(case=case, vs=vs, vps=vps, edits=bool(edits), caster=ckind, evaluator=ekind, kw={k: (v if not isinstance(v, dict) else "bv") for k, v in kw.items()},
                 cam=cam["resolution_x"], shift=shift.tolist(), views=n_views, segments=len(ref["gain"]),
                 samples=int(ref["n_samples"].sum()), list_len=int(len(l_ref)), bad=bad)
 
