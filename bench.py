@@ -149,7 +149,7 @@ def run_reference(args):
         return
     m, pos, quat, delta = make_workload(max(args.views, 256))
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_sample or min(args.views, max(64, 4 * cores))
+    n_sample = args.cpu_sample or min(args.views, max(256, 16 * cores))
     from oracle import oracle_py as O
     om = O.OracleMap.from_synth(m)
     om.upload_blocks(*delta)
@@ -340,7 +340,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_sample = args.cpu_sample or min(n_seg, max(64, 4 * cores))
+        n_sample = args.cpu_sample or min(n_seg, max(256, 16 * cores))
         rate_all, r = cpu_oracle_rate(m, (d_idx, d_dist, d_obs), pos, quat, n_sample, cores)
         n1 = min(n_sample, 24)
         rate_1, _ = cpu_oracle_rate(m, (d_idx, d_dist, d_obs), pos, quat, n1, 1)
