@@ -50,7 +50,7 @@ extern "C" {
 #define A3D_EVAL_VOXEL_TYPE 0
 #define A3D_EVAL_NAIVE 1
 #define A3D_EVAL_FRONTIER 2
-/* "VoxelWeightEvaluator" (voxel_weight_evaluator.cpp:12-13): evaluated by the scan-order kernel */
+/* "VoxelWeightEvaluator" (voxel_weight_evaluator.cpp:12-13) */
 #define A3D_EVAL_VOXEL_WEIGHT 3
 
 typedef struct a3d_ctx a3d_ctx;
@@ -122,7 +122,7 @@ float a3d_last_kernel_ms(a3d_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 uint64_t a3d_kernel_launches(a3d_ctx* ctx);
 /* Tuning / test knobs.  "cast_kernel": 0 = automatic (default), 1 = always the scan-order kernel
-   (k_cast_gain), 2 = require the wavefront kernel (k_cast_wave; errors if ordered outputs are asked).
+   (k_cast_gain), 2 = require the wavefront kernel (k_cast_wave; errors if ordered digests are asked).
    "wave_cta": CTA width of the wavefront kernel, 0 = automatic (8 warps for batches up to twice the SM count,
    else 2), 1 = always 2 warps, 2 = always 8 warps. */
 int a3d_set_option(a3d_ctx* ctx, const char* name, int64_t value);
@@ -237,8 +237,9 @@ int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const do
 int a3d_store_create(a3d_ctx* ctx, a3d_store** out);
 void a3d_store_destroy(a3d_store* store);
 /* a3d_compute_gains + keep every segment's stored list under seg_keys[s] (replacing older lists of
- * the same key).  Two passes: gains/sizes (wavefront kernel), then the scan-order kernel writes the
- * ordered lists into an exactly sized device arena. */
+ * the same key).  Two passes: gains/sizes (wavefront kernel), then the ordered lists are written into an
+ * exactly sized device arena (wavefront kernel with list emission for up to twice the SM count
+ * segments, the scan-order kernel beyond). */
 int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
                              a3d_store* store, int n_views, const double* pos, const double* quat,
                              const int32_t* view_segment, int n_segments, const uint64_t* seg_keys,
