@@ -533,6 +533,21 @@ int vol_ensure(a3d_ctx* ctx) {
   return A3D_OK;
 }
 
+// CTA width of the wavefront kernel for a batch (wave_cta = 0).  Two 8-warp CTAs fit an SM, so a batch
+// runs in ceil(n / 2·SMs) passes of wide CTAs, each faster than a 2-warp CTA's view by up to 4x: by the
+// ratio of a view's leaf work on 64 lanes to what bounds it on 256 (its leaf work there, or the
+// scheduler warp's anti-diagonal chain).  Measured on cfg2 (ratio 1.5: wide up to 296 segments) and
+// cfg4 (SimpleRayCaster, ratio 3.2: wide up to ~890).
+bool wave_wide_auto(const CasterView& c, int n_segments, int sm_count) {
+  const bool iterative = c.kind == A3D_CASTER_ITERATIVE;
+  const double kmax = std::max(1, c.kmax);
+  const double leaf = c.n_rays * (iterative ? 0.5 * kmax : kmax) / 64.0;
+  const double chain = iterative ? 0.5 * (c.res_x + c.res_y) * (0.25 * kmax + 4.0) : 0.0;
+  const double ratio = std::min(4.0, std::max(1.0, leaf / std::max(chain, 0.25 * leaf)));
+  const int passes = (n_segments + 2 * sm_count - 1) / (2 * sm_count);
+  return passes <= std::max(1, static_cast<int>(0.95 * ratio));
+}
+
 // Shared by the host- and device-pointer upload entry points.
 int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* dist,
                        const uint8_t* obs, const float* w, bool payload_on_device) {
@@ -742,7 +757,8 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     CK(cudaMemsetAsync(ctx->sc_inexact.p, 0, n_words * sizeof(unsigned int), ctx->stream));
     b.work_counter = ctx->sc_counter.p;
     launch_cast_wave(ctx->stream, ctx->view(), c->view, ev_view, b, set_dig_dev != nullptr, grid,
-                     ctx->sc_wave.p, ctx->sc_inexact.p, /*wide=*/ctx->opt_wave_cta == 2 || (ctx->opt_wave_cta == 0 && n_segments <= 2 * ctx->sm_count));
+                     ctx->sc_wave.p, ctx->sc_inexact.p, /*wide=*/ctx->opt_wave_cta == 2 ||
+                         (ctx->opt_wave_cta == 0 && wave_wide_auto(c->view, n_segments, ctx->sm_count)));
     ctx->launches++;
     CK(cudaGetLastError());
     seg_mask = ctx->sc_inexact.p;

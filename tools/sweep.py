@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--evaluator", default=None, help="override the workload's evaluator, e.g. VoxelWeight")
     ap.add_argument("--cast-kernel", type=int, default=0, help="0 auto, 1 scan-order, 2 wavefront")
+    ap.add_argument("--wave-cta", type=int, default=0, help="0 auto, 1 two-warp CTAs, 2 eight-warp CTAs")
     args = ap.parse_args()
     cfg = dict(synth.CONFIGS[args.workload])
     if args.evaluator:
@@ -44,6 +45,7 @@ def main():
                         focal_length=cfg["focal_length"], ray_length=cfg["ray_length"])
     ev = ctx.evaluator(cfg["evaluator"] + "Evaluator")
     ctx.set_option("cast_kernel", args.cast_kernel)
+    ctx.set_option("wave_cta", args.wave_cta)
     dev = torch.device("cuda", 0)
     peak = 6555.2
     try:
