@@ -735,7 +735,10 @@ int cast_gain_block_threads() { return kCastBlock; }
 // simulated_sensor_updater.cpp:18-22 → computeGainFromVisibleVoxels).  One CTA per list.  Naive and
 // Frontier erase the observed entries from the list like the reference does (naive_evaluator.cpp:28-35,
 // frontier_evaluator.cpp:110-116): stable in-place compaction, chunk by chunk.
-__global__ void __launch_bounds__(256)
+#ifndef A3D_REFOLD_MIN_BLOCKS
+#define A3D_REFOLD_MIN_BLOCKS 4  // resident 256-thread CTAs per SM the register allocation must allow
+#endif
+__global__ void __launch_bounds__(256, A3D_REFOLD_MIN_BLOCKS)
     k_refold(MapView m, EvalView e, int n, double* __restrict__ pool,
              const long long* __restrict__ offsets, long long* __restrict__ counts,
              const double* __restrict__ origins, double* __restrict__ gains_out) {
