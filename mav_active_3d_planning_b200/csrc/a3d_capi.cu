@@ -158,7 +158,7 @@ struct a3d_ctx {
   DevBuf<uint8_t> sc_wave;
   int opt_cast_kernel = 0;  // 0 auto, 1 scan-order kernel (k_cast_gain), 2 wavefront kernel (k_cast_wave)
   int last_cast_kernel = 0;
-  int opt_wave_cta = 0;  // 0 auto (8-warp CTAs for batches up to twice the SM count), 1 always 2 warps, 2 always 8
+  int opt_wave_cta = 0;  // 0 auto (wave_warps_auto), 1 always 2 warps, 2 always 8, 3 always 4
 
   int fail(int code, const std::string& msg) const {
     err = msg;
@@ -533,19 +533,31 @@ int vol_ensure(a3d_ctx* ctx) {
   return A3D_OK;
 }
 
-// CTA width of the wavefront kernel for a batch (wave_cta = 0).  Two 8-warp CTAs fit an SM, so a batch
-// runs in ceil(n / 2·SMs) passes of wide CTAs, each faster than a 2-warp CTA's view by up to 4x: by the
-// ratio of a view's leaf work on 64 lanes to what bounds it on 256 (its leaf work there, or the
-// scheduler warp's anti-diagonal chain).  Measured on cfg2 (ratio 1.5: wide up to 296 segments) and
-// cfg4 (SimpleRayCaster, ratio 3.2: wide up to ~890).
-bool wave_wide_auto(const CasterView& c, int n_segments, int sm_count) {
+// CTA width of the wavefront kernel for a batch (wave_cta = 0): 2, 4 or 8 warps, of which 10 / 5 / 2 fit
+// an SM.  A W-warp CTA finishes a view up to W/2 times faster than a 2-warp CTA, bounded by the ratio
+// of the view's leaf work on 64 lanes to the scheduler warp's anti-diagonal chain; the batch needs
+// ceil(n / resident CTAs) passes.  Picks the width with the smallest estimate (measured on cfg2: 8 warps
+// up to 296 segments, 4 up to 740, 2 beyond; SimpleRayCaster workload: 8 warps up to ~890).
+int wave_warps_auto(const CasterView& c, int n_segments, int sm_count) {
   const bool iterative = c.kind == A3D_CASTER_ITERATIVE;
   const double kmax = std::max(1, c.kmax);
   const double leaf = c.n_rays * (iterative ? 0.5 * kmax : kmax) / 64.0;
   const double chain = iterative ? 0.5 * (c.res_x + c.res_y) * (0.25 * kmax + 4.0) : 0.0;
   const double ratio = std::min(4.0, std::max(1.0, leaf / std::max(chain, 0.25 * leaf)));
-  const int passes = (n_segments + 2 * sm_count - 1) / (2 * sm_count);
-  return passes <= std::max(1, static_cast<int>(0.95 * ratio));
+  int best = 2;
+  double best_t = 1e300;
+  const int widths[3] = {8, 4, 2}, per_sm[3] = {2, 5, cast_wave_blocks_per_sm()};
+  for (int k = 0; k < 3; ++k) {
+    const int resident = per_sm[k] * sm_count;
+    const double passes = (n_segments + resident - 1) / resident;
+    // (a wider CTA is worth >= 1.25x even for chain-bound views: no spills, fewer warps contending)
+    const double t = widths[k] == 2 ? 0.95 * passes : passes / std::max(1.25, std::min(0.5 * widths[k], ratio));
+    if (t < best_t) {
+      best_t = t;
+      best = widths[k];
+    }
+  }
+  return best;
 }
 
 // Shared by the host- and device-pointer upload entry points.
@@ -757,8 +769,10 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     CK(cudaMemsetAsync(ctx->sc_inexact.p, 0, n_words * sizeof(unsigned int), ctx->stream));
     b.work_counter = ctx->sc_counter.p;
     launch_cast_wave(ctx->stream, ctx->view(), c->view, ev_view, b, set_dig_dev != nullptr, grid,
-                     ctx->sc_wave.p, ctx->sc_inexact.p, /*wide=*/ctx->opt_wave_cta == 2 ||
-                         (ctx->opt_wave_cta == 0 && wave_wide_auto(c->view, n_segments, ctx->sm_count)));
+                     ctx->sc_wave.p, ctx->sc_inexact.p, ctx->opt_wave_cta == 1   ? 2
+                     : ctx->opt_wave_cta == 2 ? 8
+                     : ctx->opt_wave_cta == 3 ? 4
+                                              : wave_warps_auto(c->view, n_segments, ctx->sm_count));
     ctx->launches++;
     CK(cudaGetLastError());
     seg_mask = ctx->sc_inexact.p;
@@ -1271,7 +1285,7 @@ int a3d_set_option(a3d_ctx* ctx, const char* name, int64_t value) {
     return A3D_OK;
   }
   if (std::strcmp(name, "wave_cta") == 0) {
-    if (value < 0 || value > 2) return ctx->fail(A3D_ERR_INVALID, "wave_cta must be 0, 1 or 2");
+    if (value < 0 || value > 3) return ctx->fail(A3D_ERR_INVALID, "wave_cta must be 0, 1, 2 or 3");
     ctx->opt_wave_cta = static_cast<int>(value);
     return A3D_OK;
   }

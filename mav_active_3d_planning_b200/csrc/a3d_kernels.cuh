@@ -98,7 +98,7 @@ size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride
                           int emit_kmax /*> 0: list emission, slots per ray part*/);
 void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                       const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact,
-                      bool wide /*8-warp CTAs: batches below the SM count*/);
+                      int warps /*CTA width: 2 (throughput), 4 or 8 (mid-size / small batches)*/);
 int cast_wave_threads();
 int cast_wave_max_diag();
 int cast_wave_blocks_per_sm();

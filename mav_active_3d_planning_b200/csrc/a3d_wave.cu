@@ -47,7 +47,8 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 #endif
 constexpr int kWaveWarps = A3D_WAVE_WARPS;
 constexpr int kWaveThreads = 32 * kWaveWarps;
-constexpr int kWaveWideWarps = 8;  // CTA width for batches smaller than the SM count
+constexpr int kWaveWideWarps = 8;  // CTA width for small batches (2 such CTAs per SM)
+constexpr int kWaveMidWarps = 4;   // ... for mid-size batches (5 per SM)
 constexpr uint64_t kNoKey = ~0ull;  // "no entry"
 constexpr uint64_t kKeyOverflow = 1ull << 63;
 constexpr int kKeyBits = 20, kKeyBias = 1 << 19;
@@ -618,11 +619,13 @@ __device__ __forceinline__ bool ray_step(const MapView& m, const CenterTables& c
 
 }  // namespace
 
-// WARPS: 2 for throughput (as many CTAs as the registers allow), 8 for batches up to twice the SM
-// count (two such CTAs fit an SM), where a view's leaf parts are better spread over more lanes of the one CTA that owns it.
+// WARPS: 2 for throughput (as many CTAs as the registers allow), 4 and 8 for mid-size and small
+// batches (5 / 2 such CTAs fit an SM), where a view's leaf parts are better spread over more lanes of the one CTA that owns it.
 // EMIT: also write the ordered visible-voxel lists (8-warp CTAs only).
 template <int CASTER, int EVAL, bool DIGEST, int WARPS, bool EMIT>
-__global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps ? A3D_WAVE_MIN_BLOCKS : 2)
+__global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps      ? A3D_WAVE_MIN_BLOCKS
+                                             : WARPS == kWaveMidWarps ? 5
+                                                                      : 2)
     k_cast_wave(const MapView m, const CasterView c, const EvalView e, const Batch b,
                 const WaveScratch ws, unsigned int* __restrict__ inexact_flags) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
@@ -1107,19 +1110,25 @@ size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride
 template <int CASTER, int EVAL>
 static void launch_wave_t(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                           const Batch& b, bool digest, int grid, const WaveScratch& ws,
-                          unsigned int* inexact, bool wide) {
+                          unsigned int* inexact, int warps) {
   const size_t smem = static_cast<size_t>(c.diag_max) * 12;
   if (ws.ent)  // list emission: always the wide CTA, never together with a digest
     k_cast_wave<CASTER, EVAL, false, kWaveWideWarps, true>
         <<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
-  else if (digest && wide)
+  else if (digest && warps >= kWaveWideWarps)
     k_cast_wave<CASTER, EVAL, true, kWaveWideWarps, false>
         <<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
+  else if (digest && warps >= kWaveMidWarps)
+    k_cast_wave<CASTER, EVAL, true, kWaveMidWarps, false>
+        <<<grid, 32 * kWaveMidWarps, smem, st>>>(m, c, e, b, ws, inexact);
   else if (digest)
     k_cast_wave<CASTER, EVAL, true, kWaveWarps, false><<<grid, kWaveThreads, smem, st>>>(m, c, e, b, ws, inexact);
-  else if (wide)
+  else if (warps >= kWaveWideWarps)
     k_cast_wave<CASTER, EVAL, false, kWaveWideWarps, false>
         <<<grid, 32 * kWaveWideWarps, smem, st>>>(m, c, e, b, ws, inexact);
+  else if (warps >= kWaveMidWarps)
+    k_cast_wave<CASTER, EVAL, false, kWaveMidWarps, false>
+        <<<grid, 32 * kWaveMidWarps, smem, st>>>(m, c, e, b, ws, inexact);
   else
     k_cast_wave<CASTER, EVAL, false, kWaveWarps, false><<<grid, kWaveThreads, smem, st>>>(m, c, e, b, ws, inexact);
 }
@@ -1127,19 +1136,19 @@ static void launch_wave_t(cudaStream_t st, const MapView& m, const CasterView& c
 template <int CASTER>
 static void launch_wave_c(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                           const Batch& b, bool digest, int grid, const WaveScratch& ws,
-                          unsigned int* inexact, bool wide) {
+                          unsigned int* inexact, int warps) {
   switch (e.kind) {
     case A3D_EVAL_VOXEL_TYPE:
-      launch_wave_t<CASTER, A3D_EVAL_VOXEL_TYPE>(st, m, c, e, b, digest, grid, ws, inexact, wide);
+      launch_wave_t<CASTER, A3D_EVAL_VOXEL_TYPE>(st, m, c, e, b, digest, grid, ws, inexact, warps);
       break;
     case A3D_EVAL_NAIVE:
-      launch_wave_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, e, b, digest, grid, ws, inexact, wide);
+      launch_wave_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, e, b, digest, grid, ws, inexact, warps);
       break;
     case A3D_EVAL_VOXEL_WEIGHT:  // (never with a digest: the value record shares the hash slot)
-      launch_wave_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, e, b, false, grid, ws, inexact, wide);
+      launch_wave_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, e, b, false, grid, ws, inexact, warps);
       break;
     default:
-      launch_wave_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, e, b, digest, grid, ws, inexact, wide);
+      launch_wave_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, e, b, digest, grid, ws, inexact, warps);
       break;
   }
 }
@@ -1149,7 +1158,7 @@ static void launch_wave_c(cudaStream_t st, const MapView& m, const CasterView& c
 // when a voxel key overflowed the 20-bit packing (the host re-evaluates those with k_cast_gain).
 void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                       const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact,
-                      bool wide) {
+                      int warps) {
   size_t stride = 0;
   const bool extra = digest || e.kind == A3D_EVAL_VOXEL_WEIGHT;  // per-part first_hash / first value
   const int emit_kmax = b.centres_out ? c.kmax : 0;
@@ -1183,9 +1192,9 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
   p += g * stride * 2;
   ws.start_s = p;
   if (c.kind == A3D_CASTER_ITERATIVE)
-    launch_wave_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, digest, grid, ws, inexact, wide);
+    launch_wave_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, digest, grid, ws, inexact, warps);
   else
-    launch_wave_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, digest, grid, ws, inexact, wide);
+    launch_wave_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, digest, grid, ws, inexact, warps);
 }
 
 int cast_wave_threads() { return kWaveThreads; }

@@ -334,16 +334,20 @@ def test_error_codes(capi):
 
 # ---- wavefront kernel (k_cast_wave): same gains / counts / order-independent digest -----------------
 def _wave(ctx, caster, ev, *a, **kw):
-    """Wavefront kernel, both CTA widths (2 warps: throughput, 8 warps: small batches); the two must
-    agree bit for bit on the integer outputs."""
+    """Wavefront kernel, all CTA widths (2 warps: throughput, 8 / 4 warps: small / mid-size batches);
+    they must agree bit for bit on the integer outputs."""
     ctx.set_option("cast_kernel", 2)
     try:
         ctx.set_option("wave_cta", 1)
         r = ctx.compute_gains(caster, ev, *a, digests=False, **kw)
         assert ctx.last_cast_kernel == 2
-        ctx.set_option("wave_cta", 2)
-        w = ctx.compute_gains(caster, ev, *a, digests=False, **kw)
-        assert ctx.last_cast_kernel == 2
+        for width in (2, 3):
+            ctx.set_option("wave_cta", width)
+            w = ctx.compute_gains(caster, ev, *a, digests=False, **kw)
+            assert ctx.last_cast_kernel == 2
+            for k in ("n_samples", "n_visible", "set_digest"):
+                assert np.array_equal(r[k], w[k]), (k, width)
+            assert np.allclose(r["gain"], w["gain"], rtol=1e-12, atol=0)
     finally:
         ctx.set_option("cast_kernel", 0)
         ctx.set_option("wave_cta", 0)

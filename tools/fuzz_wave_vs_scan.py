@@ -98,7 +98,7 @@ def one_case(rng, case, oracle=None, max_views=None):
                 bad.append(f"oracle {k}")
         if not np.allclose(ref["gain"], want["gain"], rtol=1e-5, atol=1e-12):
             bad.append("oracle gain")
-    for width in (1, 2):
+    for width in (1, 2, 3):
         ctx.set_option("wave_cta", width)
         got = ctx.compute_gains(caster, ev, *args, digests=False, set_digests=sd)
         for k in ("n_samples", "n_visible") + (("set_digest",) if sd else ()):
