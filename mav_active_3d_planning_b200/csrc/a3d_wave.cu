@@ -37,7 +37,19 @@
 #include "../../include/a3d.h"
 #include "a3d_kernels.cuh"
 
+// The kernel has ~40 instantiations; to halve the build time this file is compiled as two translation
+// units: as itself (part 1: IterativeRayCaster instantiations + the public entry points) and through
+// a3d_wave_simple.cu (part 2: SimpleRayCaster instantiations only).
+#ifndef A3D_WAVE_PART
+#define A3D_WAVE_PART 1
+#endif
+
 namespace a3d {
+
+void launch_wave_iterative(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                           bool digest, int grid, const void* ws, unsigned int* inexact, int warps);
+void launch_wave_simple(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                        bool digest, int grid, const void* ws, unsigned int* inexact, int warps);
 
 namespace {
 
@@ -1099,6 +1111,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps      ? A3D_WAV
   }
 }
 
+#if A3D_WAVE_PART == 1
 size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride, int emit_kmax) {
   const size_t stride = (static_cast<size_t>(n_rays) + 31) / 32 * 32;
   *rays_stride = stride;
@@ -1106,6 +1119,7 @@ size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride
   if (emit_kmax > 0) per_cta += 2 * stride * (static_cast<size_t>(emit_kmax) * 8 + 2 + 4);
   return per_cta * static_cast<size_t>(grid) + 256;
 }
+#endif
 
 template <int CASTER, int EVAL>
 static void launch_wave_t(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
@@ -1153,6 +1167,21 @@ static void launch_wave_c(cudaStream_t st, const MapView& m, const CasterView& c
   }
 }
 
+#if A3D_WAVE_PART == 1
+void launch_wave_iterative(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                           bool digest, int grid, const void* ws, unsigned int* inexact, int warps) {
+  launch_wave_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, digest, grid, *static_cast<const WaveScratch*>(ws), inexact,
+                                      warps);
+}
+#else
+void launch_wave_simple(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                        bool digest, int grid, const void* ws, unsigned int* inexact, int warps) {
+  launch_wave_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, digest, grid, *static_cast<const WaveScratch*>(ws), inexact,
+                                   warps);
+}
+#endif
+
+#if A3D_WAVE_PART == 1
 // scratch: wave_scratch_bytes() bytes, carved here.  b.set_digests receives the ORDER-INDEPENDENT
 // digest (sum of digest_entry over the stored list, mod 2^64).  inexact: one bit per segment, set
 // when a voxel key overflowed the 20-bit packing (the host re-evaluates those with k_cast_gain).
@@ -1192,13 +1221,14 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
   p += g * stride * 2;
   ws.start_s = p;
   if (c.kind == A3D_CASTER_ITERATIVE)
-    launch_wave_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, digest, grid, ws, inexact, warps);
+    launch_wave_iterative(st, m, c, e, b, digest, grid, &ws, inexact, warps);
   else
-    launch_wave_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, digest, grid, ws, inexact, warps);
+    launch_wave_simple(st, m, c, e, b, digest, grid, &ws, inexact, warps);
 }
 
 int cast_wave_threads() { return kWaveThreads; }
 int cast_wave_max_diag() { return kMarkCap; }
 int cast_wave_blocks_per_sm() { return A3D_WAVE_MIN_BLOCKS; }
+#endif  // A3D_WAVE_PART == 1
 
 }  // namespace a3d

@@ -5,5 +5,5 @@
 set -e
 cd "$(dirname "$0")/.."
 ${NVCC:-/usr/local/cuda/bin/nvcc} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
-  -Xcompiler -fPIC -shared -DA3D_BOUNDS_CHECK -o variant_check.so mav_active_3d_planning_b200/csrc/*.cu
+  -Xcompiler -fPIC -shared --threads 0 -DA3D_BOUNDS_CHECK -o variant_check.so mav_active_3d_planning_b200/csrc/*.cu
 echo "built $PWD/variant_check.so"
