@@ -582,6 +582,16 @@ void orc_distance(const orc_map* m, int64_t n, const double* p, double* dist, ui
   }
 }
 
+const char* orc_impl(void) { return "port"; }
+
+// vbx/src/map/voxblox.cpp:32-41
+void orc_traversable(const orc_map* m, int64_t n, const double* p, double collision_radius, uint8_t* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    double d = 0.0;
+    out[i] = (m->getDistanceAtPosition(V3{p[3 * i], p[3 * i + 1], p[3 * i + 2]}, &d) && d > collision_radius) ? 1 : 0;
+  }
+}
+
 orc_caster* orc_caster_create(const orc_map* m, const orc_caster_params* p) {
   orc_caster* c = new orc_caster();
   c->map = m;

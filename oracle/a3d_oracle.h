@@ -41,6 +41,8 @@ typedef struct {
   double mount_q[4];           /* w,x,y,z, already normalised (sensor_model.cpp:21-27) */
   double field_of_view_x;      /* lidar only, degrees (lidar_model.cpp:170-171) */
   double field_of_view_y;
+  double mount_q_raw[4];       /* w,x,y,z as configured, before sensor_model.cpp:27 normalises it
+                                  (read by oracle/_ref only, which lets the reference normalise) */
 } orc_caster_params;
 
 typedef struct {
@@ -59,6 +61,8 @@ typedef struct {
   double bv_quat[4];            /* w,x,y,z of AngleAxis(-rotation*pi/180, Z) (bounding_volume.cpp:21) */
   /* voxel_weight_evaluator.cpp:17-22 */
   double frontier_voxel_weight, min_impact_factor, new_voxel_weight, ray_angle_x, ray_angle_y;
+  double bv_rotation_deg;       /* bounding_volume.cpp:19 `rotation` as configured (read by oracle/_ref
+                                   only; the restatement uses bv_quat) */
 } orc_eval_params;
 
 /* ---- map (VoxbloxLite: restated voxblox Layer<EsdfVoxel>/<TsdfVoxel> + Interpolator) ---- */
@@ -78,6 +82,11 @@ void orc_is_observed(const orc_map* m, int64_t n, const double* pts, uint8_t* ou
 void orc_voxel_weight(const orc_map* m, int64_t n, const double* pts, double* out);
 /* interpolated distance + success flag (EsdfMap::getDistanceAtPosition) */
 void orc_distance(const orc_map* m, int64_t n, const double* pts, double* dist, uint8_t* ok);
+
+/* VoxbloxMap::isTraversable (vbx/src/map/voxblox.cpp:32-41) for a given collision radius */
+void orc_traversable(const orc_map* m, int64_t n, const double* pts, double collision_radius, uint8_t* out);
+/* "port" for liba3d_oracle.so (the restatement), "reference" for _ref/liba3d_ref.so */
+const char* orc_impl(void);
 
 /* ---- caster (camera_model.cpp, simple_ray_caster.cpp, iterative_ray_caster.cpp) ---- */
 orc_caster* orc_caster_create(const orc_map* m, const orc_caster_params* p);

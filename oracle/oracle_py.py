@@ -21,7 +21,8 @@ class CasterParams(C.Structure):
                 ("_pad", C.c_int32), ("ray_length", C.c_double), ("focal_length", C.c_double),
                 ("ray_step", C.c_double), ("downsampling_factor", C.c_double),
                 ("mount_t", C.c_double * 3), ("mount_q", C.c_double * 4),
-                ("field_of_view_x", C.c_double), ("field_of_view_y", C.c_double)]
+                ("field_of_view_x", C.c_double), ("field_of_view_y", C.c_double),
+                ("mount_q_raw", C.c_double * 4)]
 
 
 class EvalParams(C.Structure):
@@ -32,7 +33,7 @@ class EvalParams(C.Structure):
                 ("bv_max", C.c_double * 3), ("bv_quat", C.c_double * 4),
                 ("frontier_voxel_weight", C.c_double), ("min_impact_factor", C.c_double),
                 ("new_voxel_weight", C.c_double), ("ray_angle_x", C.c_double),
-                ("ray_angle_y", C.c_double)]
+                ("ray_angle_y", C.c_double), ("bv_rotation_deg", C.c_double)]
 
 
 _CASTER_KINDS = {"SimpleRayCaster": 0, "IterativeRayCaster": 1, "IterativeRayCasterLidar": 2}
@@ -49,16 +50,50 @@ def build(force: bool = False) -> str:
     return LIB_PATH
 
 
+REF_LIB_PATH = os.path.join(_HERE, "_ref", "liba3d_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
+
+def build_ref(force: bool = False) -> str | None:
+    """Compile oracle/_ref (the reference's own sources behind the orc_* API) when /root/reference is
+    present; returns the library path, or None when it can neither be built nor found prebuilt."""
+    if os.path.isdir(REFERENCE_ROOT):
+        subprocess.run(["make", "-C", _HERE, "-j8", "_ref"] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+    return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB_PATH)
+
+
 _lib = None
+_ref_lib = None
 
 
-def lib():
+def ref_lib():
+    """oracle/_ref/liba3d_ref.so — same entry points, reference code underneath."""
+    global _ref_lib
+    if _ref_lib is None:
+        if not os.path.exists(REF_LIB_PATH):
+            raise FileNotFoundError(REF_LIB_PATH + " (make -C oracle _ref needs /root/reference)")
+        _ref_lib = _bind(C.CDLL(REF_LIB_PATH))
+    return _ref_lib
+
+
+def lib(impl: str = "oracle"):
     global _lib
+    if impl == "ref":
+        return ref_lib()
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
         build()
-    L = C.CDLL(LIB_PATH)
+    _lib = _bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _bind(L):
     vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
     P = C.POINTER
     L.orc_map_create.argtypes = [C.c_float, C.c_int]
@@ -97,7 +132,10 @@ def lib():
     L.orc_bv_contains.restype = None
     L.orc_digest.argtypes = [i64, vp]
     L.orc_digest.restype = C.c_uint64
-    _lib = L
+    L.orc_traversable.argtypes = [vp, i64, vp, dbl, vp]
+    L.orc_traversable.restype = None
+    L.orc_impl.argtypes = []
+    L.orc_impl.restype = C.c_char_p
     return L
 
 
@@ -124,7 +162,9 @@ def caster_params(kind, *, ray_length=5.0, focal_length=320.0, resolution_x=640,
     p.ray_step, p.downsampling_factor = float(ray_step), float(downsampling_factor)
     p.mount_t[:] = [float(x) for x in mounting_translation]
     w, x, y, z = [float(v) for v in mounting_rotation]
-    n = math.sqrt(((x * x + y * y) + z * z) + w * w)
+    p.mount_q_raw[:] = [w, x, y, z]
+    # Quaterniond::normalized(): coeffs (x,y,z,w) squared, summed two lanes at a time (SSE2)
+    n = math.sqrt((x * x + z * z) + (y * y + w * w))
     p.mount_q[:] = [w / n, x / n, y / n, z / n]
     return p
 
@@ -153,20 +193,22 @@ def eval_params(kind, *, clear_from_parents=False, accurate_frontiers=False, sur
     p.bv_min[:] = lo
     p.bv_max[:] = hi
     p.bv_is_setup = int(hi[0] > lo[0] and hi[1] > lo[1] and hi[2] > lo[2])
+    p.bv_rotation_deg = float(bv.get("rotation", 0.0))
     ang = float(bv.get("rotation", 0.0)) * math.pi / -180.0
     p.bv_quat[:] = [math.cos(ang * 0.5), 0.0, 0.0, math.sin(ang * 0.5)]
     return p
 
 
 class OracleMap:
-    def __init__(self, voxel_size: float, vps: int = 16):
-        self.L = lib()
+    def __init__(self, voxel_size: float, vps: int = 16, impl: str = "oracle"):
+        self.L = lib(impl)
+        self.impl = impl
         self.h = self.L.orc_map_create(C.c_float(voxel_size), vps)
         self.vps = vps
 
     @classmethod
-    def from_synth(cls, m):
-        o = cls(m.voxel_size, m.vps)
+    def from_synth(cls, m, impl: str = "oracle"):
+        o = cls(m.voxel_size, m.vps, impl)
         o.upload_blocks(m.block_idx, m.dist, m.observed, m.weight)
         return o
 
@@ -232,6 +274,12 @@ class OracleMap:
 
     def caster(self, kind, **kw):
         return OracleCaster(self, caster_params(kind, **kw))
+
+    def traversable(self, pts, collision_radius):
+        pts = _pts(pts)
+        out = np.empty(len(pts), np.uint8)
+        self.L.orc_traversable(self.h, len(pts), _ptr(pts), float(collision_radius), _ptr(out))
+        return out
 
     def gain_from_voxels(self, eparams, centres, origin=None):
         centres = _pts(centres) if len(centres) else np.zeros((0, 3))
@@ -314,17 +362,17 @@ class OracleCaster:
                     n_fold_lookups=fold)
 
 
-def sample_viewpoints(sampling_time, times_ns):
+def sample_viewpoints(sampling_time, times_ns, impl="oracle"):
     t = np.ascontiguousarray(times_ns, np.int64)
     out = np.zeros(len(t) + 1, np.int32)
-    n = lib().orc_sample_viewpoints(float(sampling_time), len(t), _ptr(t), _ptr(out))
+    n = lib(impl).orc_sample_viewpoints(float(sampling_time), len(t), _ptr(t), _ptr(out))
     return out[:n].copy()
 
 
-def bv_contains(eparams, pts):
+def bv_contains(eparams, pts, impl="oracle"):
     pts = _pts(pts)
     out = np.empty(len(pts), np.uint8)
-    lib().orc_bv_contains(C.byref(eparams), len(pts), _ptr(pts), _ptr(out))
+    lib(impl).orc_bv_contains(C.byref(eparams), len(pts), _ptr(pts), _ptr(out))
     return out
 
 
