@@ -127,10 +127,18 @@ def make_workload(n_views, seed=42):
     return m, pos, quat, (d_idx, d_dist, d_obs)
 
 
-def cpu_oracle_rate(m, delta, pos, quat, n_sample, n_threads):
-    """views/s of the CPU oracle (literal port of the reference path) on the first n_sample views."""
+def cpu_impl():
+    """("ref", "reference") when oracle/_ref/liba3d_ref.so — the reference's own unmodified sources
+    behind the orc_* API, built in the container that has /root/reference — travelled with the
+    snapshot; else ("oracle", "port"), the restatement."""
     from oracle import oracle_py as O
-    om = O.OracleMap.from_synth(m)
+    return ("ref", "reference") if O.have_ref() else ("oracle", "port")
+
+
+def cpu_oracle_rate(m, delta, pos, quat, n_sample, n_threads):
+    """views/s of the reference's CPU implementation of the path on the first n_sample views."""
+    from oracle import oracle_py as O
+    om = O.OracleMap.from_synth(m, impl=cpu_impl()[0])
     om.upload_blocks(*delta)
     oc = om.caster("IterativeRayCaster", **CAM)
     ep = O.eval_params("VoxelTypeEvaluator")
@@ -142,8 +150,9 @@ def cpu_oracle_rate(m, delta, pos, quat, n_sample, n_threads):
 
 
 def run_reference(args):
-    """--impl reference: the CPU port of the reference path (the reference itself cannot be built
-    here), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: its
+    unmodified sources, one planner + map copy per host thread; falls back to the restatement in
+    oracle/ when that library is absent), all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -151,7 +160,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n_sample = args.cpu_sample or min(args.views, max(256, 16 * cores))
     from oracle import oracle_py as O
-    om = O.OracleMap.from_synth(m)
+    impl, kind = cpu_impl()
+    om = O.OracleMap.from_synth(m, impl=impl)
     om.upload_blocks(*delta)
     oc = om.caster("IterativeRayCaster", **CAM)
     ep = O.eval_params("VoxelTypeEvaluator")
@@ -168,8 +178,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 step / f32 lookup", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "views_per_gpu": args.views},
-        "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port",
+        "config": {"workload": WORKLOAD, "views_per_gpu": args.views, "views_timed": n_sample},
+        "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -347,7 +357,7 @@ def run_ours(args):
         ok = bool(np.array_equal(r["n_samples"].astype(np.int64), nsamp[:n_sample]) and
                   np.allclose(r["gain"], gains[:n_sample], rtol=1e-5, atol=0))
         out["cpu_baseline"] = {
-            "value": rate_all, "unit": "views/s", "cores": cores, "kind": "port",
+            "value": rate_all, "unit": "views/s", "cores": cores, "kind": cpu_impl()[1],
             "sample": f"first {n_sample} of {n_seg} candidate views, {cores} threads over views",
             "single_thread_value": rate_1, "single_thread_sample": f"first {n1} views",
             "matches_gpu": ok}

@@ -84,7 +84,8 @@ def caster_params(kind, *, ray_length=5.0, focal_length=320.0, resolution_x=640,
     p.ray_step, p.downsampling_factor = float(ray_step), float(downsampling_factor)
     p.mount_t[:] = [float(x) for x in mounting_translation]
     w, x, y, z = [float(v) for v in mounting_rotation]
-    n = math.sqrt(((x * x + y * y) + z * z) + w * w)
+    # Eigen's Quaterniond::normalized(): coeffs (x,y,z,w) squared and summed two lanes at a time
+    n = math.sqrt((x * x + z * z) + (y * y + w * w))
     p.mount_q[:] = [w / n, x / n, y / n, z / n]
     return p
 

@@ -77,7 +77,8 @@ class Quaterniond {
   double z() const { return z_; }
   Vector3d vec() const { return {x_, y_, z_}; }
   Quaterniond normalized() const {
-    const double n = std::sqrt(((x_ * x_ + y_ * y_) + z_ * z_) + w_ * w_);
+    // Eigen 3.3 (SSE2): coeffs x,y,z,w squared, reduced two lanes at a time
+    const double n = std::sqrt((x_ * x_ + z_ * z_) + (y_ * y_ + w_ * w_));
     return {w_ / n, x_ / n, y_ / n, z_ / n};
   }
   // Hamilton product
