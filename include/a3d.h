@@ -196,7 +196,8 @@ void a3d_eval_destroy(a3d_eval* e);
  *   seg_origin (input, nullable, n_segments×3): position of each segment's last trajectory point,
  *                  the `origin` of VoxelWeightEvaluator (voxel_weight_evaluator.cpp:53); default =
  *                  body position of the segment's last view
- * Synchronous on return.  clear_from_parents is not supported by the batch call. */
+ * Synchronous on return.  An evaluator with clear_from_parents needs the tree: use
+ * a3d_compute_gains_tree or a3d_compute_gains_stored (this call returns A3D_ERR_UNSUPPORTED). */
 int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                       const double* pos, const double* quat, const int32_t* view_segment,
                       int n_segments, double* gains_out, uint64_t* n_visible_out,
@@ -213,7 +214,8 @@ int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval
 /* One segment with its voxel list materialised (parity / visualisation / the per-segment
  * SensorModel::getVisibleVoxelsFromTrajectory + storeTrajectoryInformation API):
  *   eval == NULL: the sensor model's list (camera_model.cpp:15-60), no gain;
- *   eval != NULL: the list the evaluator stores (after the bounding-volume filter) and its gain.
+ *   eval != NULL: the list after the evaluator's bounding-volume filter and the gain of that list
+ *                 (clear_from_parents is not applied here: the caller owns the ancestors' lists).
  * centres_out cap×3 doubles; *n_out = full list length even if > cap (then A3D_ERR_CAPACITY). */
 int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
                        const double* pos, const double* quat, double* centres_out, int64_t cap,
@@ -232,31 +234,54 @@ int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const do
 /* ---- device-resident stored lists -------------------------------------------
  * The reference keeps each segment's voxel list in TrajectorySegment::info (SimulatedSensorInfo,
  * simulated_sensor_evaluator.h:54-58) so that SimulatedSensorUpdater can re-fold the gain after the
- * map changed without casting rays again (evaluator_updater/simulated_sensor_updater.cpp:18-22).  A
- * store keeps those lists in HBM, keyed by a caller-chosen 64-bit id (e.g. the segment's address). */
+ * map changed without casting rays again (evaluator_updater/simulated_sensor_updater.cpp:18-22), and
+ * so that clear_from_parents can subtract what the ancestors already see
+ * (simulated_sensor_evaluator.cpp:60-76).  A store keeps those lists in HBM as packed 64-bit voxel
+ * keys (8 B per entry instead of the 24-B centre triple; two entries have equal centre doubles iff
+ * their keys are equal), keyed by a caller-chosen non-zero 64-bit id (e.g. the segment's address). */
 int a3d_store_create(a3d_ctx* ctx, a3d_store** out);
 void a3d_store_destroy(a3d_store* store);
-/* a3d_compute_gains + keep every segment's stored list under seg_keys[s] (replacing older lists of
- * the same key).  Two passes: gains/sizes (wavefront kernel), then the ordered lists are written into an
- * exactly sized device arena (wavefront kernel with list emission for up to twice the SM count
- * segments, the scan-order kernel beyond). */
+/* Batched SimulatedSensorEvaluator::computeGain that also keeps every segment's stored list under
+ * seg_keys[s] (replacing older lists of the same key; keys must be distinct and non-zero).
+ *   parent_keys (nullable, n_segments): store key of each segment's parent (TrajectorySegment::parent),
+ *     0 for none.  Read only when the evaluator has clear_from_parents: entries that occur in the
+ *     stored list of any ancestor are dropped (:60-76; a hash-set probe per ancestor instead of
+ *     std::find).  A parent is either stored already or part of this batch (any order).
+ *   The stored list is what the reference holds after computeGain returned: for Naive and Frontier
+ *   evaluators the observed entries are erased (naive_evaluator.cpp:28-35, frontier_evaluator.cpp:110-116);
+ *   n_visible_out is the size handed to storeTrajectoryInformation (before that erasure), digests /
+ *   set digests are of that list.  Outputs other than gains_out are nullable.
+ * Passes: gains/sizes (wavefront kernel) → ordered key lists into an exactly sized arena (wavefront
+ * kernel with list emission up to twice the SM count segments, scan-order kernel beyond) → where
+ * needed, k_list_pipeline (parent filter, digests, fold + erasure), level by level of the tree. */
 int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
                              a3d_store* store, int n_views, const double* pos, const double* quat,
                              const int32_t* view_segment, int n_segments, const uint64_t* seg_keys,
-                             double* gains_out, uint64_t* n_visible_out, const double* seg_origin);
-/* computeGainFromVisibleVoxels for n stored lists against the CURRENT map, one launch.  Naive and
+                             const uint64_t* parent_keys, double* gains_out, uint64_t* n_visible_out,
+                             uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* set_digests_out,
+                             const double* seg_origin);
+/* a3d_compute_gains for a batch that carries its own tree: parent_index[s] (nullable) = index of
+ * segment s's parent inside the batch (must be < s) or -1.  This is the batch form of computeGain
+ * with clear_from_parents (simulated_sensor_evaluator.cpp:60-76); lists live in a temporary store. */
+int a3d_compute_gains_tree(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
+                           const double* pos, const double* quat, const int32_t* view_segment,
+                           int n_segments, const int32_t* parent_index, double* gains_out,
+                           uint64_t* n_visible_out, uint64_t* n_samples_out, uint64_t* digests_out,
+                           uint64_t* set_digests_out, const double* seg_origin);
+/* computeGainFromVisibleVoxels for n stored lists against the CURRENT map, one launch per arena
+ * (k_list_pipeline: the fold reads each entry's meta word straight from its key).  Naive and
  * Frontier evaluators also erase the observed entries from the stored lists, like the reference.
- * n_left_out (nullable): list sizes afterwards.  Unknown key → A3D_ERR_INVALID. */
+ * n_left_out (nullable): list sizes afterwards.  Unknown or repeated key → A3D_ERR_INVALID. */
 int a3d_store_refold(a3d_ctx* ctx, const a3d_eval* eval, a3d_store* store, int n,
                      const uint64_t* seg_keys, double* gains_out, uint64_t* n_left_out,
                      const double* seg_origin);
 int a3d_store_erase(a3d_store* store, int n, const uint64_t* seg_keys);
 /* number of entries stored under key, -1 if absent */
 int64_t a3d_store_list_size(const a3d_store* store, uint64_t key);
-/* copy a stored list back (cap×3 doubles); *n_out = its length */
+/* copy a stored list back as centre doubles (cap×3); *n_out = its length */
 int a3d_store_get(a3d_ctx* ctx, const a3d_store* store, uint64_t key, double* centres_out, int64_t cap,
                   int64_t* n_out);
-/* bytes of HBM currently held by the store */
+/* bytes of HBM currently held by the store (lists and hash sets) */
 int64_t a3d_store_bytes(const a3d_store* store);
 
 /* clear_from_parents step of SimulatedSensorEvaluator::computeGain

@@ -38,6 +38,7 @@ EXPORTS = [
     "a3d_caster_direction", "a3d_eval_create", "a3d_eval_destroy", "a3d_compute_gains",
     "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_filter_not_in",
     "a3d_bv_contains", "a3d_store_create", "a3d_store_destroy", "a3d_compute_gains_stored",
+    "a3d_compute_gains_tree",
     "a3d_store_refold", "a3d_store_erase", "a3d_store_list_size", "a3d_store_get", "a3d_store_bytes",
 ]
 
@@ -181,7 +182,9 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_store_create.argtypes = [vp, P(vp)]
     lib.a3d_store_destroy.argtypes = [vp]
     lib.a3d_store_destroy.restype = None
-    lib.a3d_compute_gains_stored.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.a3d_compute_gains_stored.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp,
+                                             vp, vp, vp]
+    lib.a3d_compute_gains_tree.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.a3d_store_refold.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
     lib.a3d_store_erase.argtypes = [vp, C.c_int, vp]
     lib.a3d_store_list_size.argtypes = [vp, u64]
@@ -352,11 +355,12 @@ class Context:
         return int(self.lib.a3d_last_cast_kernel(self.h))
 
     def compute_gains(self, caster, evaluator, pos, quat, view_segment=None, n_segments=None,
-                      digests=True, set_digests=True, seg_origin=None):
+                      digests=True, set_digests=True, seg_origin=None, parent=None):
         """Batched SimulatedSensorEvaluator::computeGain.  Returns dict(gain, n_visible, n_samples,
         digest, set_digest) of per-segment arrays.  Default: one view per segment.  ``digests=True``
         (ordered digest) selects the scan-order kernel; with ``digests=False`` the wavefront kernel
-        runs."""
+        runs.  ``parent`` (index of each segment's parent in the batch, -1 = none) routes through
+        a3d_compute_gains_tree: the batch form of clear_from_parents."""
         pos = _pts(pos)
         quat = np.ascontiguousarray(quat, np.float64)
         n_views = len(pos)
@@ -370,6 +374,14 @@ class Context:
         nsamp = np.zeros(n_segments, np.uint64)
         dig = np.zeros(n_segments, np.uint64) if digests else None
         sdig = np.zeros(n_segments, np.uint64) if set_digests else None
+        if parent is not None:
+            parent = np.ascontiguousarray(parent, np.int32)
+            assert len(parent) == n_segments
+            self._ck(self.lib.a3d_compute_gains_tree(
+                self.h, caster.h, evaluator.h, n_views, _ptr(pos), _ptr(quat), _ptr(view_segment), n_segments,
+                _ptr(parent), _ptr(gains), _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(sdig),
+                _ptr(None if seg_origin is None else np.ascontiguousarray(seg_origin, np.float64))))
+            return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig, set_digest=sdig)
         self._ck(self.lib.a3d_compute_gains(self.h, caster.h, evaluator.h, n_views, _ptr(pos),
                                             _ptr(quat), _ptr(view_segment), n_segments, _ptr(gains),
                                             _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(sdig),
@@ -447,7 +459,10 @@ class Store:
         except Exception:
             pass
 
-    def compute_gains(self, caster, evaluator, keys, pos, quat, view_segment=None, seg_origin=None):
+    def compute_gains(self, caster, evaluator, keys, pos, quat, view_segment=None, seg_origin=None,
+                      parent_keys=None, digests=False):
+        """a3d_compute_gains_stored.  ``parent_keys``: store key of each segment's parent (0 = none),
+        used when the evaluator has clear_from_parents."""
         pos = _pts(pos)
         quat = np.ascontiguousarray(quat, np.float64)
         keys = np.ascontiguousarray(keys, np.uint64)
@@ -457,11 +472,16 @@ class Store:
         view_segment = np.ascontiguousarray(view_segment, np.int32)
         gains = np.zeros(n_seg, np.float64)
         nvis = np.zeros(n_seg, np.uint64)
+        nsamp = np.zeros(n_seg, np.uint64)
+        dig = np.zeros(n_seg, np.uint64) if digests else None
+        sdig = np.zeros(n_seg, np.uint64) if digests else None
         org = None if seg_origin is None else np.ascontiguousarray(seg_origin, np.float64)
+        pk = None if parent_keys is None else np.ascontiguousarray(parent_keys, np.uint64)
         self.ctx._ck(self.ctx.lib.a3d_compute_gains_stored(
             self.ctx.h, caster.h, evaluator.h, self.h, len(pos), _ptr(pos), _ptr(quat),
-            _ptr(view_segment), n_seg, _ptr(keys), _ptr(gains), _ptr(nvis), _ptr(org)))
-        return dict(gain=gains, n_visible=nvis)
+            _ptr(view_segment), n_seg, _ptr(keys), _ptr(pk), _ptr(gains), _ptr(nvis), _ptr(nsamp), _ptr(dig),
+            _ptr(sdig), _ptr(org)))
+        return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig, set_digest=sdig)
 
     def refold(self, evaluator, keys, seg_origin=None):
         keys = np.ascontiguousarray(keys, np.uint64)

@@ -156,6 +156,7 @@ struct a3d_ctx {
   DevBuf<int8_t> sc_tables;
   DevBuf<unsigned int> sc_counter, sc_inexact;
   DevBuf<uint8_t> sc_wave;
+  uint64_t config_gen = 0;  // bumped when a3d_map_config changes the geometry: older casters/evals are stale
   int opt_cast_kernel = 0;  // 0 auto, 1 scan-order kernel (k_cast_gain), 2 wavefront kernel (k_cast_wave)
   int last_cast_kernel = 0;
   int opt_wave_cta = 0;  // 0 auto (wave_warps_auto), 1 always 2 warps, 2 always 8, 3 always 4
@@ -210,6 +211,7 @@ struct a3d_ctx {
 
 struct a3d_caster {
   a3d_ctx* ctx;
+  uint64_t config_gen = 0;
   a3d_caster_params p;
   a3d_caster_info info;
   std::vector<double> h_dirs;
@@ -223,20 +225,27 @@ struct a3d_caster {
 
 struct a3d_eval {
   a3d_ctx* ctx;
+  uint64_t config_gen = 0;
   a3d_eval_params p;
   EvalView view{};
 };
 
-// Device-resident stored lists: every a3d_compute_gains_stored call owns one arena; a key maps to a
-// slice of an arena; an arena is freed when its last key is replaced or erased.
+// Device-resident stored lists (packed voxel keys, a3d_keys.cuh): every a3d_compute_gains_stored call
+// owns one arena; a key maps to a slice of an arena; an arena is freed when its last user is replaced
+// or erased.  Hash sets of the lists (clear_from_parents membership tests) live in arenas of their own.
 struct StoreArena {
-  double* p = nullptr;
-  size_t entries = 0;
+  unsigned long long* p = nullptr;  // list keys, or hash-set tables
+  size_t entries = 0;               // 8-byte words
   int live = 0;
 };
 struct StoreEntry {
   int arena;
   long long offset, count;
+  uint64_t parent = 0;     // store key of the segment's parent (0: none)
+  int set_arena = -1;      // hash set of the stored list: arena, offset (words), size - 1
+  long long set_off = 0;
+  uint32_t set_mask = 0;
+  bool set_stale = true;   // the list changed since the set was built (refold erased entries)
 };
 struct a3d_store {
   a3d_ctx* ctx;
@@ -244,16 +253,33 @@ struct a3d_store {
   std::unordered_map<uint64_t, StoreEntry> lists;
   DevBuf<long long> d_off, d_cnt;
   DevBuf<double> d_gain, d_origin;
-  void drop(uint64_t key) {
-    auto it = lists.find(key);
-    if (it == lists.end()) return;
-    StoreArena& a = arenas[it->second.arena];
+  DevBuf<unsigned long long> d_u64;   // n_stored | digests | set digests of a pipeline launch
+  DevBuf<int> d_anc_first;
+  DevBuf<unsigned long long*> d_tab;  // ancestor tables / tables to build
+  DevBuf<uint32_t> d_mask;
+  void unref(int arena) {
+    if (arena < 0) return;
+    StoreArena& a = arenas[arena];
     if (--a.live == 0 && a.p) {
       cudaFree(a.p);
       a.p = nullptr;
       a.entries = 0;
     }
+  }
+  void drop(uint64_t key) {
+    auto it = lists.find(key);
+    if (it == lists.end()) return;
+    unref(it->second.arena);
+    unref(it->second.set_arena);
     lists.erase(it);
+  }
+  int new_arena(size_t words, cudaError_t* err) {
+    StoreArena a;
+    a.entries = words;
+    *err = cudaMalloc(&a.p, std::max<size_t>(words, 1) * 8);
+    if (*err != cudaSuccess) return -1;
+    arenas.push_back(a);
+    return static_cast<int>(arenas.size()) - 1;
   }
 };
 
@@ -570,7 +596,9 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
   if (n == 0) return A3D_OK;
   CK(cudaSetDevice(ctx->device));
   // slot assignment
+  // slot | 1<<30 for blocks allocated by this call (their TSDF weights start at 0 when none are sent)
   std::vector<int32_t> slot_of(n);
+  constexpr int32_t kFreshSlot = 1 << 30;
   bool table_dirty = false;
   for (int i = 0; i < n; ++i) {
     const Key3 k{block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2]};
@@ -589,7 +617,7 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
     ctx->slots.emplace(k, s);
     if (ctx->slot_key.size() <= static_cast<size_t>(s)) ctx->slot_key.resize(s + 1);
     ctx->slot_key[s] = k;
-    slot_of[i] = s;
+    slot_of[i] = s | kFreshSlot;
     table_dirty = true;
   }
   int rc = slab_reserve(ctx, static_cast<size_t>(ctx->next_slot), w != nullptr);
@@ -600,7 +628,7 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
     } else {
       for (int i = 0; i < n; ++i)
         table_insert(ctx->h_table, block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2],
-                     slot_of[i]);
+                     slot_of[i] & ~kFreshSlot);
     }
     rc = table_upload(ctx);
     if (rc) return rc;
@@ -705,7 +733,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
                  unsigned long long* nvis_dev, unsigned long long* nsamp_dev,
                  unsigned long long* dig_dev, unsigned long long* set_dig_dev, double* centres_dev,
                  long long cap, bool emit, const double* seg_origin_dev,
-                 const long long* emit_offset_dev = nullptr) {
+                 const long long* emit_offset_dev = nullptr, unsigned long long* keys_dev = nullptr) {
   if (ctx->h_table.empty()) {
     table_rebuild(ctx, 0);
     int rc = table_upload(ctx);
@@ -725,8 +753,10 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   b.cap = cap;
   b.emit_offset = emit_offset_dev;
   b.seg_origin = seg_origin_dev;
-  CK(ctx->sc_counter.reserve(2));
-  CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+  b.keys_out = keys_dev;
+  CK(ctx->sc_counter.reserve(4));
+  CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+  b.key_error = ctx->sc_counter.p + 2;
 
   // The wavefront kernel emits lists through per-part slot ranges (4 MB of scratch per resident view
   // on the bench workload) that decode voxel keys with a shift: a latency win for the per-segment call
@@ -801,6 +831,10 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
 }
 
 }  // namespace
+
+#define CHECK_FRESH(obj)                                                                              \
+  if ((obj) && (obj)->config_gen != ctx->config_gen)                                                  \
+  return ctx->fail(A3D_ERR_STATE, "caster/evaluator was created before a3d_map_config changed the map geometry")
 
 extern "C" {
 
@@ -910,6 +944,28 @@ int a3d_map_config(a3d_ctx* ctx, float voxel_size, int vps) {
     return ctx->fail(A3D_ERR_INVALID, "voxel_size must be > 0 and 1 <= voxels_per_side <= 64");
   if (ctx->configured && !ctx->slots.empty())
     return ctx->fail(A3D_ERR_STATE, "map already holds blocks; a3d_map_clear first");
+  if (ctx->configured && (vps != ctx->vps || voxel_size != ctx->vs_f)) {
+    // a new geometry: the slabs are sized per slot by vps, casters and evaluators cache the voxel size
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_dist) cudaFree(ctx->d_dist);
+    if (ctx->d_mword) cudaFree(ctx->d_mword);
+    if (ctx->d_weight) cudaFree(ctx->d_weight);
+    if (ctx->d_vol) cudaFree(ctx->d_vol);
+    ctx->d_dist = nullptr;
+    ctx->d_mword = nullptr;
+    ctx->d_weight = nullptr;
+    ctx->d_vol = nullptr;
+    ctx->vol_words = 0;
+    ctx->vol_on = false;
+    ctx->vol_stale = true;
+    ctx->slab_slots = 0;
+    ctx->has_weight = false;
+    ctx->slot_key.clear();
+    ctx->h_dir.clear();
+    ctx->dir_enabled = false;
+    ctx->config_gen++;
+  }
   // voxblox Layer / Block constructors
   ctx->vs_f = voxel_size;
   ctx->vps = vps;
@@ -1117,6 +1173,7 @@ int a3d_caster_create(a3d_ctx* ctx, const a3d_caster_params* p, a3d_caster** out
 
   // Camera-frame directions (camera_model.cpp:161-168 as called at simple_ray_caster.cpp:41-44)
   a3d_caster* c = new a3d_caster();
+  c->config_gen = ctx->config_gen;
   c->ctx = ctx;
   c->p = *p;
   c->info = info;
@@ -1245,6 +1302,7 @@ int a3d_eval_create(a3d_ctx* ctx, const a3d_eval_params* p, a3d_eval** out) {
   if (p->kind == A3D_EVAL_VOXEL_WEIGHT && !(p->ray_angle_x * p->ray_angle_y > 0.0))
     return ctx->fail(A3D_ERR_INVALID, "ray_angle_x * ray_angle_y expected > 0.0");
   a3d_eval* e = new a3d_eval();
+  e->config_gen = ctx->config_gen;
   e->ctx = ctx;
   e->p = *p;
   e->view = make_eval_view(ctx, *p);
@@ -1262,8 +1320,11 @@ int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval
   if (!ctx) return A3D_ERR_INVALID;
   if (!caster || !eval || caster->ctx != ctx || eval->ctx != ctx)
     return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
+  CHECK_FRESH(caster);
+  CHECK_FRESH(eval);
   if (eval->p.clear_from_parents)
-    return ctx->fail(A3D_ERR_UNSUPPORTED, "clear_from_parents is not supported by the batch call");
+    return ctx->fail(A3D_ERR_UNSUPPORTED,
+                     "clear_from_parents needs the tree: use a3d_compute_gains_tree or a3d_compute_gains_stored");
   if (n_views < 0 || n_segments < 0) return ctx->fail(A3D_ERR_INVALID, "negative count");
   if (n_segments == 0) return A3D_OK;
   if (!pos_dev || !quat_dev || !view_first_dev || !gains_dev)
@@ -1302,6 +1363,8 @@ int a3d_compute_gains(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* ev
   if (!ctx) return A3D_ERR_INVALID;
   if (!caster || !eval || caster->ctx != ctx || eval->ctx != ctx)
     return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
+  CHECK_FRESH(caster);
+  CHECK_FRESH(eval);
   if (n_views < 0 || n_segments < 0) return ctx->fail(A3D_ERR_INVALID, "negative count");
   if (n_segments == 0) return A3D_OK;
   if ((n_views > 0 && (!pos || !quat || !view_segment)) || !gains_out)
@@ -1372,8 +1435,8 @@ int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* e
   if (!ctx) return A3D_ERR_INVALID;
   if (!caster || caster->ctx != ctx || (eval && eval->ctx != ctx))
     return ctx->fail(A3D_ERR_INVALID, "caster/eval missing or from another context");
-  if (eval && eval->p.clear_from_parents)
-    return ctx->fail(A3D_ERR_UNSUPPORTED, "clear_from_parents is not supported");
+  CHECK_FRESH(caster);
+  CHECK_FRESH(eval);
   if (n_views < 0 || cap < 0 || (n_views > 0 && (!pos || !quat)) || (cap > 0 && !centres_out) ||
       !n_out)
     return ctx->fail(A3D_ERR_INVALID, "bad argument");
@@ -1427,6 +1490,7 @@ int a3d_gain_from_voxels(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const do
                          double* gain_out, int64_t* n_left_out, uint8_t* keep_out, const double* origin) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!eval || eval->ctx != ctx) return ctx->fail(A3D_ERR_INVALID, "eval missing");
+  CHECK_FRESH(eval);
   if (n < 0 || (n > 0 && !centres) || !gain_out) return ctx->fail(A3D_ERR_INVALID, "bad argument");
   CK(cudaSetDevice(ctx->device));
   if (ctx->h_table.empty()) {
@@ -1498,6 +1562,10 @@ void a3d_store_destroy(a3d_store* store) {
   store->d_cnt.release();
   store->d_gain.release();
   store->d_origin.release();
+  store->d_u64.release();
+  store->d_anc_first.release();
+  store->d_tab.release();
+  store->d_mask.release();
   delete store;
 }
 int a3d_store_erase(a3d_store* store, int n, const uint64_t* seg_keys) {
@@ -1515,7 +1583,7 @@ int64_t a3d_store_list_size(const a3d_store* store, uint64_t key) {
 int64_t a3d_store_bytes(const a3d_store* store) {
   int64_t b = 0;
   if (store)
-    for (const auto& a : store->arenas) b += static_cast<int64_t>(a.entries) * 24;
+    for (const auto& a : store->arenas) b += static_cast<int64_t>(a.entries) * 8;
   return b;
 }
 int a3d_store_get(a3d_ctx* ctx, const a3d_store* store, uint64_t key, double* centres_out, int64_t cap,
@@ -1528,58 +1596,340 @@ int a3d_store_get(a3d_ctx* ctx, const a3d_store* store, uint64_t key, double* ce
   const int64_t n = std::min<int64_t>(cap, it->second.count);
   CK(cudaSetDevice(ctx->device));
   if (n > 0) {
-    CK(cudaMemcpyAsync(centres_out, store->arenas[it->second.arena].p + 3 * it->second.offset,
-                       24 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
+    // keys → the centre doubles the reference holds in SimulatedSensorInfo::visible_voxels
+    CK(ctx->sc_centres.reserve(3 * static_cast<size_t>(n)));
+    launch_keys_to_centres(ctx->stream, ctx->view(), n, store->arenas[it->second.arena].p + it->second.offset,
+                           ctx->sc_centres.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(centres_out, ctx->sc_centres.p, 24 * static_cast<size_t>(n), cudaMemcpyDeviceToHost,
+                       ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
   return it->second.count > cap ? ctx->fail(A3D_ERR_CAPACITY, "centres_out too small") : A3D_OK;
 }
 
+namespace {
+
+uint32_t set_size_for(long long count) {
+  uint32_t sz = 16;
+  while (sz < 2ull * static_cast<unsigned long long>(std::max<long long>(count, 1))) sz <<= 1;
+  return sz;
+}
+
+// (Re)builds the hash sets of the given stored lists where missing or stale, one arena for the new ones.
+int ensure_sets(a3d_ctx* ctx, a3d_store* store, const std::vector<uint64_t>& keys) {
+  std::vector<StoreEntry*> todo;
+  size_t new_words = 0;
+  for (uint64_t k : keys) {
+    auto it = store->lists.find(k);
+    if (it == store->lists.end()) return ctx->fail(A3D_ERR_INVALID, "parent key not in store");
+    StoreEntry& e = it->second;
+    if (e.set_arena >= 0 && !e.set_stale) continue;
+    if (std::find(todo.begin(), todo.end(), &e) != todo.end()) continue;
+    todo.push_back(&e);
+    if (e.set_arena < 0) new_words += set_size_for(e.count);
+  }
+  if (todo.empty()) return A3D_OK;
+  int arena = -1;
+  if (new_words > 0) {
+    cudaError_t err;
+    arena = store->new_arena(new_words, &err);
+    if (arena < 0) return ctx->cuda_fail(err, "cudaMalloc(hash sets)");
+  }
+  long long cursor = 0;
+  const int n = static_cast<int>(todo.size());
+  std::vector<long long> cnt(n);
+  std::vector<unsigned long long*> tabs(2 * static_cast<size_t>(n));  // [tables | lists] (lists may sit in different arenas)
+  std::vector<uint32_t> masks(n);
+  for (int i = 0; i < n; ++i) {
+    StoreEntry& e = *todo[i];
+    if (e.set_arena < 0) {
+      e.set_arena = arena;
+      e.set_off = cursor;
+      e.set_mask = set_size_for(e.count) - 1;
+      cursor += static_cast<long long>(e.set_mask) + 1;
+      store->arenas[arena].live++;
+    }
+    tabs[i] = store->arenas[e.set_arena].p + e.set_off;
+    masks[i] = e.set_mask;
+    CK(cudaMemsetAsync(tabs[i], 0xFF, (static_cast<size_t>(e.set_mask) + 1) * 8, ctx->stream));
+    tabs[n + i] = store->arenas[e.arena].p + e.offset;
+    cnt[i] = e.count;
+    e.set_stale = false;
+  }
+  CK(store->d_cnt.reserve(n));
+  CK(store->d_tab.reserve(tabs.size()));
+  CK(store->d_mask.reserve(n));
+  CK(cudaMemcpyAsync(store->d_cnt.p, cnt.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(store->d_tab.p, tabs.data(), tabs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(store->d_mask.p, masks.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  launch_build_sets(ctx->stream, n, store->d_tab.p + n, store->d_cnt.p, store->d_tab.p, store->d_mask.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));  // host vectors above are pageable
+  return A3D_OK;
+}
+
+// k_list_pipeline over the given stored lists (all in one arena): parent filter (when `parents`),
+// digests, fold.  Results come back in the order of `keys`.
+int run_list_pipeline(a3d_ctx* ctx, const a3d_eval* eval, a3d_store* store, const std::vector<uint64_t>& keys,
+                      bool parents, bool fold, const double* seg_origin /*per key, nullable*/,
+                      double* gains_out, uint64_t* n_stored_out, uint64_t* digests_out, uint64_t* set_digests_out) {
+  const int n = static_cast<int>(keys.size());
+  if (n == 0) return A3D_OK;
+  std::vector<StoreEntry*> ent(n);
+  for (int i = 0; i < n; ++i) ent[i] = &store->lists.at(keys[i]);
+  const int arena = ent[0]->arena;
+  std::vector<long long> off(n), cnt(n);
+  std::vector<int> anc_first(n + 1, 0);
+  std::vector<unsigned long long*> tabs;
+  std::vector<uint32_t> masks;
+  if (parents) {
+    std::vector<uint64_t> anc_keys;
+    for (int i = 0; i < n; ++i)
+      for (uint64_t k = ent[i]->parent; k != 0;) {
+        auto it = store->lists.find(k);
+        if (it == store->lists.end()) return ctx->fail(A3D_ERR_INVALID, "parent key not in store");
+        anc_keys.push_back(k);
+        k = it->second.parent;
+        if (anc_keys.size() > (size_t(1) << 26)) return ctx->fail(A3D_ERR_INVALID, "parent chain does not end");
+      }
+    int rc = ensure_sets(ctx, store, anc_keys);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+      for (uint64_t k = ent[i]->parent; k != 0; k = store->lists.at(k).parent) {
+        const StoreEntry& a = store->lists.at(k);
+        tabs.push_back(store->arenas[a.set_arena].p + a.set_off);
+        masks.push_back(a.set_mask);
+      }
+      anc_first[i + 1] = static_cast<int>(tabs.size());
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    if (ent[i]->arena != arena) return ctx->fail(A3D_ERR_STATE, "lists of one pipeline launch span arenas");
+    off[i] = ent[i]->offset;
+    cnt[i] = ent[i]->count;
+  }
+  CK(store->d_off.reserve(n));
+  CK(store->d_cnt.reserve(n));
+  CK(store->d_gain.reserve(n));
+  CK(store->d_u64.reserve(3 * static_cast<size_t>(n)));
+  CK(cudaMemcpyAsync(store->d_off.p, off.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(store->d_cnt.p, cnt.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  ListBatch lb{};
+  lb.n = n;
+  lb.pool = store->arenas[arena].p;
+  lb.offsets = store->d_off.p;
+  lb.counts = store->d_cnt.p;
+  lb.n_stored = store->d_u64.p;
+  lb.digests = digests_out ? store->d_u64.p + n : nullptr;
+  lb.set_digests = set_digests_out ? store->d_u64.p + 2 * static_cast<size_t>(n) : nullptr;
+  lb.gains = fold ? store->d_gain.p : nullptr;
+  if (seg_origin) {
+    CK(store->d_origin.reserve(3 * static_cast<size_t>(n)));
+    CK(cudaMemcpyAsync(store->d_origin.p, seg_origin, 24 * static_cast<size_t>(n), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    lb.origins = store->d_origin.p;
+  }
+  if (parents && !tabs.empty()) {
+    CK(store->d_anc_first.reserve(n + 1));
+    CK(store->d_tab.reserve(tabs.size()));
+    CK(store->d_mask.reserve(masks.size()));
+    CK(cudaMemcpyAsync(store->d_anc_first.p, anc_first.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CK(cudaMemcpyAsync(store->d_tab.p, tabs.data(), tabs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(store->d_mask.p, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    lb.anc_first = store->d_anc_first.p;
+    lb.anc_table = store->d_tab.p;
+    lb.anc_mask = store->d_mask.p;
+  }
+  if (ctx->h_table.empty()) {
+    table_rebuild(ctx, 0);
+    int rc = table_upload(ctx);
+    if (rc) return rc;
+  }
+  int rc = vol_ensure(ctx);
+  if (rc) return rc;
+  launch_list_pipeline(ctx->stream, ctx->view(), eval->view, lb);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  std::vector<unsigned long long> u(3 * static_cast<size_t>(n));
+  std::vector<double> g(n);
+  CK(cudaMemcpyAsync(cnt.data(), store->d_cnt.p, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(u.data(), store->d_u64.p, u.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (fold) CK(cudaMemcpyAsync(g.data(), store->d_gain.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) {
+    if (cnt[i] != ent[i]->count) ent[i]->set_stale = true;
+    ent[i]->count = cnt[i];
+    if (fold && gains_out) gains_out[i] = g[i];
+    if (n_stored_out) n_stored_out[i] = u[i];
+    if (digests_out) digests_out[i] = u[n + i];
+    if (set_digests_out) set_digests_out[i] = u[2 * static_cast<size_t>(n) + i];
+  }
+  return A3D_OK;
+}
+
+}  // namespace
+
 int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
                              a3d_store* store, int n_views, const double* pos, const double* quat,
                              const int32_t* view_segment, int n_segments, const uint64_t* seg_keys,
-                             double* gains_out, uint64_t* n_visible_out, const double* seg_origin) {
+                             const uint64_t* parent_keys, double* gains_out, uint64_t* n_visible_out,
+                             uint64_t* n_samples_out, uint64_t* digests_out, uint64_t* set_digests_out,
+                             const double* seg_origin) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!store || store->ctx != ctx || (n_segments > 0 && !seg_keys))
     return ctx->fail(A3D_ERR_INVALID, "store/keys missing");
-  // pass 1: gains and list sizes
+  if (!eval) return ctx->fail(A3D_ERR_INVALID, "eval missing");
+  const bool chained = eval->p.clear_from_parents && parent_keys;
+  {
+    std::unordered_map<uint64_t, int> seen;
+    for (int s = 0; s < n_segments; ++s) {
+      if (seg_keys[s] == 0) return ctx->fail(A3D_ERR_INVALID, "segment key 0 is reserved (no parent)");
+      if (!seen.emplace(seg_keys[s], s).second) return ctx->fail(A3D_ERR_INVALID, "duplicate segment key");
+    }
+  }
+  // pass 1: gains (final unless the list pipeline folds below), raw list sizes, sample counts
   std::vector<uint64_t> nvis(static_cast<size_t>(std::max(n_segments, 0)));
-  int rc = a3d_compute_gains(ctx, caster, eval, n_views, pos, quat, view_segment, n_segments, gains_out,
-                             nvis.data(), nullptr, nullptr, nullptr, seg_origin);
+  a3d_eval plain = *eval;
+  plain.p.clear_from_parents = 0;  // (the batch cast itself never looks at parents)
+  int rc = a3d_compute_gains(ctx, caster, &plain, n_views, pos, quat, view_segment, n_segments, gains_out,
+                             nvis.data(), n_samples_out, nullptr, nullptr, seg_origin);
   if (rc) return rc;
   if (n_segments == 0) return A3D_OK;
   std::vector<long long> off(static_cast<size_t>(n_segments) + 1, 0);
   for (int s = 0; s < n_segments; ++s) off[s + 1] = off[s] + static_cast<long long>(nvis[s]);
   const size_t total = static_cast<size_t>(off[n_segments]);
-  // pass 2: ordered lists into one exactly sized arena (inputs are still in the context scratch)
-  StoreArena arena;
-  arena.entries = total;
-  CK(cudaMalloc(&arena.p, std::max<size_t>(total, 1) * 24));
-  CK(store->d_off.reserve(off.size()));
-  CK(cudaMemcpyAsync(store->d_off.p, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice,
-                     ctx->stream));
-  rc = enqueue_cast(ctx, caster, eval, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, n_segments,
-                    ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr, arena.p, 0, true,
-                    seg_origin ? ctx->sc_origin.p : nullptr, store->d_off.p);
-  if (rc) {
-    cudaFree(arena.p);
-    return rc;
-  }
-  CK(cudaStreamSynchronize(ctx->stream));
-  const int arena_id = static_cast<int>(store->arenas.size());
-  store->arenas.push_back(arena);
-  for (int s = 0; s < n_segments; ++s) {
-    store->drop(seg_keys[s]);
-    store->lists[seg_keys[s]] = StoreEntry{arena_id, off[s], static_cast<long long>(nvis[s])};
-    store->arenas[arena_id].live++;
-  }
-  if (store->arenas[arena_id].live == 0) {
+  // pass 2: ordered lists as packed voxel keys into one exactly sized arena (inputs are still in the
+  // context scratch)
+  cudaError_t merr;
+  const int arena_id = store->new_arena(total, &merr);
+  if (arena_id < 0) return ctx->cuda_fail(merr, "cudaMalloc(list arena)");
+  auto fail_arena = [&](int code) {
     cudaFree(store->arenas[arena_id].p);
     store->arenas[arena_id].p = nullptr;
     store->arenas[arena_id].entries = 0;
+    return code;
+  };
+  if (cudaSuccess != store->d_off.reserve(off.size())) return fail_arena(ctx->fail(A3D_ERR_CUDA, "cudaMalloc"));
+  CK(cudaMemcpyAsync(store->d_off.p, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  rc = enqueue_cast(ctx, caster, &plain, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, n_segments,
+                    ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr, nullptr, 0, true,
+                    seg_origin ? ctx->sc_origin.p : nullptr, store->d_off.p, store->arenas[arena_id].p);
+  if (rc) return fail_arena(rc);
+  unsigned int key_error = 0;
+  CK(cudaMemcpyAsync(&key_error, ctx->sc_counter.p + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail_arena(ctx->fail(A3D_ERR_CUDA, "list emission failed"));
+  if (key_error)
+    return fail_arena(ctx->fail(A3D_ERR_UNSUPPORTED,
+                                "a voxel coordinate does not fit the 20-bit list keys (pose beyond 2^19 voxels from the origin)"));
+  // register the lists (old lists of the same keys go first, so the new arena is never released here)
+  for (int s = 0; s < n_segments; ++s) store->drop(seg_keys[s]);
+  for (int s = 0; s < n_segments; ++s) {
+    StoreEntry e{};
+    e.arena = arena_id;
+    e.offset = off[s];
+    e.count = static_cast<long long>(nvis[s]);
+    e.parent = chained ? parent_keys[s] : 0;
+    store->lists[seg_keys[s]] = e;
+    store->arenas[arena_id].live++;
+  }
+  // list pipeline: needed when parents filter the lists, when the fold erases entries (Naive and
+  // Frontier store the post-erasure list, naive_evaluator.cpp:28-35) or when digests are asked
+  const bool erases = eval->p.kind == A3D_EVAL_NAIVE || eval->p.kind == A3D_EVAL_FRONTIER;
+  if (chained || erases || digests_out || set_digests_out) {
+    // levels: a segment is ready when its parent is not in this batch or was processed already
+    std::unordered_map<uint64_t, int> in_batch;
+    for (int s = 0; s < n_segments; ++s) in_batch.emplace(seg_keys[s], s);
+    std::vector<int> level(n_segments, 0);
+    int max_level = 0;
+    if (chained) {
+      for (int s = 0; s < n_segments; ++s) {
+        if (parent_keys[s] != 0 && !in_batch.count(parent_keys[s]) && !store->lists.count(parent_keys[s]))
+          return ctx->fail(A3D_ERR_INVALID, "parent key neither stored nor in this batch");
+      }
+      // (depth by following parents; chains are short, cycles are rejected)
+      for (int s = 0; s < n_segments; ++s) {
+        int d = 0;
+        uint64_t k = parent_keys[s];
+        while (k != 0) {
+          auto it = in_batch.find(k);
+          if (it == in_batch.end()) break;
+          k = parent_keys[it->second];
+          if (++d > n_segments) return ctx->fail(A3D_ERR_INVALID, "parent keys form a cycle");
+        }
+        level[s] = d;
+        max_level = std::max(max_level, d);
+      }
+    }
+    for (int lv = 0; lv <= max_level; ++lv) {
+      std::vector<uint64_t> keys;
+      std::vector<int> idx;
+      std::vector<double> org;
+      for (int s = 0; s < n_segments; ++s)
+        if (level[s] == lv) {
+          keys.push_back(seg_keys[s]);
+          idx.push_back(s);
+          if (eval->p.kind == A3D_EVAL_VOXEL_WEIGHT) {
+            // the segment's reference point: given, or the body position of its last view
+            const double* o = nullptr;
+            if (seg_origin) {
+              o = seg_origin + 3 * s;
+            } else {
+              int last = -1;
+              for (int v = 0; v < n_views; ++v)
+                if (view_segment[v] == s) last = v;
+              o = last >= 0 ? pos + 3 * last : nullptr;
+            }
+            for (int c = 0; c < 3; ++c) org.push_back(o ? o[c] : 0.0);
+          }
+        }
+      const int m = static_cast<int>(keys.size());
+      std::vector<double> g(m);
+      std::vector<uint64_t> ns(m), dg(m), sd(m);
+      rc = run_list_pipeline(ctx, eval, store, keys, chained, true, org.empty() ? nullptr : org.data(), g.data(),
+                             ns.data(), digests_out ? dg.data() : nullptr, set_digests_out ? sd.data() : nullptr);
+      if (rc) return rc;
+      for (int i = 0; i < m; ++i) {
+        gains_out[idx[i]] = g[i];
+        nvis[idx[i]] = ns[i];
+        if (digests_out) digests_out[idx[i]] = dg[i];
+        if (set_digests_out) set_digests_out[idx[i]] = sd[i];
+      }
+    }
   }
   if (n_visible_out) std::copy(nvis.begin(), nvis.end(), n_visible_out);
   return A3D_OK;
+}
+
+int a3d_compute_gains_tree(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval, int n_views,
+                           const double* pos, const double* quat, const int32_t* view_segment,
+                           int n_segments, const int32_t* parent_index, double* gains_out,
+                           uint64_t* n_visible_out, uint64_t* n_samples_out, uint64_t* digests_out,
+                           uint64_t* set_digests_out, const double* seg_origin) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (n_segments < 0) return ctx->fail(A3D_ERR_INVALID, "negative count");
+  std::vector<uint64_t> keys(static_cast<size_t>(n_segments)), parents(static_cast<size_t>(n_segments), 0);
+  for (int s = 0; s < n_segments; ++s) {
+    keys[s] = static_cast<uint64_t>(s) + 1;
+    if (parent_index) {
+      if (parent_index[s] >= s || parent_index[s] < -1)
+        return ctx->fail(A3D_ERR_INVALID, "parent_index must be -1 or the index of an earlier segment");
+      parents[s] = parent_index[s] < 0 ? 0 : static_cast<uint64_t>(parent_index[s]) + 1;
+    }
+  }
+  a3d_store* tmp = nullptr;
+  int rc = a3d_store_create(ctx, &tmp);
+  if (rc) return rc;
+  rc = a3d_compute_gains_stored(ctx, caster, eval, tmp, n_views, pos, quat, view_segment, n_segments, keys.data(),
+                                parent_index ? parents.data() : nullptr, gains_out, n_visible_out, n_samples_out,
+                                digests_out, set_digests_out, seg_origin);
+  a3d_store_destroy(tmp);
+  return rc;
 }
 
 int a3d_store_refold(a3d_ctx* ctx, const a3d_eval* eval, a3d_store* store, int n,
@@ -1589,63 +1939,48 @@ int a3d_store_refold(a3d_ctx* ctx, const a3d_eval* eval, a3d_store* store, int n
   if (!store || store->ctx != ctx || !eval || eval->ctx != ctx || n < 0 ||
       (n > 0 && (!seg_keys || !gains_out)))
     return ctx->fail(A3D_ERR_INVALID, "bad argument");
+  CHECK_FRESH(eval);
   if (eval->p.kind == A3D_EVAL_VOXEL_WEIGHT && !seg_origin)
     return ctx->fail(A3D_ERR_INVALID, "VoxelWeightEvaluator needs the segment origins");
   if (n == 0) return A3D_OK;
   CK(cudaSetDevice(ctx->device));
   // group the requested lists by arena (one launch per arena; typically one)
   std::vector<int> order(n);
-  std::vector<const StoreEntry*> ent(n);
-  for (int i = 0; i < n; ++i) {
-    auto it = store->lists.find(seg_keys[i]);
-    if (it == store->lists.end()) return ctx->fail(A3D_ERR_INVALID, "key not in store");
-    ent[i] = &it->second;
-    order[i] = i;
+  {
+    std::unordered_map<uint64_t, int> seen;
+    for (int i = 0; i < n; ++i) {
+      if (!store->lists.count(seg_keys[i])) return ctx->fail(A3D_ERR_INVALID, "key not in store");
+      if (!seen.emplace(seg_keys[i], i).second) return ctx->fail(A3D_ERR_INVALID, "duplicate segment key");
+      order[i] = i;
+    }
   }
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ent[a]->arena < ent[b]->arena; });
-  std::vector<long long> off(n), cnt(n);
-  std::vector<double> org(seg_origin ? 3 * static_cast<size_t>(n) : 0), gains(n);
-  for (int k = 0; k < n; ++k) {
-    off[k] = ent[order[k]]->offset;
-    cnt[k] = ent[order[k]]->count;
-    if (seg_origin)
-      for (int c = 0; c < 3; ++c) org[3 * k + c] = seg_origin[3 * order[k] + c];
-  }
-  CK(store->d_off.reserve(n));
-  CK(store->d_cnt.reserve(n));
-  CK(store->d_gain.reserve(n));
-  CK(cudaMemcpyAsync(store->d_off.p, off.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(store->d_cnt.p, cnt.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  if (seg_origin) {
-    CK(store->d_origin.reserve(org.size()));
-    CK(cudaMemcpyAsync(store->d_origin.p, org.data(), org.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  }
-  if (ctx->h_table.empty()) {
-    table_rebuild(ctx, 0);
-    int rc = table_upload(ctx);
-    if (rc) return rc;
-  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return store->lists.at(seg_keys[a]).arena < store->lists.at(seg_keys[b]).arena;
+  });
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int k0 = 0; k0 < n;) {
     int k1 = k0;
-    while (k1 < n && ent[order[k1]]->arena == ent[order[k0]]->arena) ++k1;
-    launch_refold(ctx->stream, ctx->view(), eval->view, k1 - k0, store->arenas[ent[order[k0]]->arena].p,
-                  store->d_off.p + k0, store->d_cnt.p + k0, seg_origin ? store->d_origin.p + 3 * k0 : nullptr,
-                  store->d_gain.p + k0);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    const int arena = store->lists.at(seg_keys[order[k0]]).arena;
+    while (k1 < n && store->lists.at(seg_keys[order[k1]]).arena == arena) ++k1;
+    const int m = k1 - k0;
+    std::vector<uint64_t> keys(m);
+    std::vector<double> org(seg_origin ? 3 * static_cast<size_t>(m) : 0), g(m);
+    for (int i = 0; i < m; ++i) {
+      keys[i] = seg_keys[order[k0 + i]];
+      if (seg_origin)
+        for (int c = 0; c < 3; ++c) org[3 * i + c] = seg_origin[3 * order[k0 + i] + c];
+    }
+    int rc = run_list_pipeline(ctx, eval, store, keys, false, true, seg_origin ? org.data() : nullptr, g.data(), nullptr,
+                               nullptr, nullptr);
+    if (rc) return rc;
+    for (int i = 0; i < m; ++i) {
+      gains_out[order[k0 + i]] = g[i];
+      if (n_left_out) n_left_out[order[k0 + i]] = static_cast<uint64_t>(store->lists.at(keys[i]).count);
+    }
     k0 = k1;
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
-  CK(cudaMemcpyAsync(gains.data(), store->d_gain.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(cnt.data(), store->d_cnt.p, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  for (int k = 0; k < n; ++k) {
-    gains_out[order[k]] = gains[k];
-    store->lists[seg_keys[order[k]]].count = cnt[k];
-    if (n_left_out) n_left_out[order[k]] = static_cast<uint64_t>(cnt[k]);
-  }
   return A3D_OK;
 }
 
@@ -1675,6 +2010,7 @@ int a3d_filter_not_in(a3d_ctx* ctx, int64_t n, const double* centres, int64_t m,
 int a3d_bv_contains(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* pts, uint8_t* out) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!eval || eval->ctx != ctx) return ctx->fail(A3D_ERR_INVALID, "eval missing");
+  CHECK_FRESH(eval);
   if (n < 0 || (n > 0 && (!pts || !out))) return ctx->fail(A3D_ERR_INVALID, "bad argument");
   if (n == 0) return A3D_OK;
   CK(cudaSetDevice(ctx->device));

@@ -20,6 +20,7 @@
 // with a ballot; the previous raw list entry for the adjacent-unique test comes from the
 // neighbouring lane (shuffle) or from a warp-uniform carry across chunks, rays and views.
 #include "a3d_kernels.cuh"
+#include "a3d_keys.cuh"
 
 #include <algorithm>
 
@@ -46,7 +47,10 @@ __global__ void k_apply_blocks(MapView m, int n, const int32_t* __restrict__ slo
     const int blk = static_cast<int>(i / m.nv);
     const int lin = static_cast<int>(i - static_cast<long long>(blk) * m.nv);
     const int z = lin / vv, rem = lin - z * vv, y = rem / m.vps, x = rem - y * m.vps;
-    const int slot = slots[blk];
+    // bit 30: the slot was allocated by this upload.  Without a weight payload (an ESDF-only delta) the
+    // TSDF weights of blocks that already exist stay as they are; only fresh slots start at 0.
+    const bool fresh = (slots[blk] >> 30) & 1;
+    const int slot = slots[blk] & ~(1 << 30);
     const float d = dist_src[i];
     uint32_t bits = __float_as_uint(d);
     if (!obs_src[i]) {
@@ -55,7 +59,7 @@ __global__ void k_apply_blocks(MapView m, int n, const int32_t* __restrict__ slo
       bits = 0x7FC00000u;  // canonical NaN for observed voxels
     }
     dist_slab[padded_index(m, slot, x, y, z)] = __uint_as_float(bits);
-    if (weight_slab) weight_slab[static_cast<size_t>(slot) * m.nv + lin] = w_src ? w_src[i] : 0.0f;
+    if (weight_slab && (w_src || fresh)) weight_slab[static_cast<size_t>(slot) * m.nv + lin] = w_src ? w_src[i] : 0.0f;
   }
 }
 
@@ -406,22 +410,6 @@ void launch_bv_contains(cudaStream_t st, const EvalView& e, long long n, const d
 }
 
 // ---------------------------------------------------------------------------------------------
-// VoxelTypeEvaluator's switch without breaks (voxel_type_evaluator.cpp:69-85): UNKNOWN adds
-// unknown+free+occupied, FREE adds free+occupied, OCCUPIED adds occupied.
-__device__ __forceinline__ double voxel_type_gain(const EvalView& e, const unsigned long long* n) {
-  // n[state + 3*outside]; state 0 OCC, 1 FREE, 2 UNKNOWN; gains: unk, occ, free, unk_o, occ_o, free_o
-  double g = 0.0;
-  for (int o = 0; o < 2; ++o) {
-    const double n_unk = static_cast<double>(n[2 + 3 * o]);
-    const double n_free = static_cast<double>(n[1 + 3 * o] + n[2 + 3 * o]);
-    const double n_occ = static_cast<double>(n[0 + 3 * o] + n[1 + 3 * o] + n[2 + 3 * o]);
-    g += n_unk * e.gains[0 + 3 * o];
-    g += n_free * e.gains[2 + 3 * o];
-    g += n_occ * e.gains[1 + 3 * o];
-  }
-  return g;
-}
-
 constexpr int kCastBlock = 32;  // one warp per CTA: a warp owns a whole segment
 #ifndef A3D_CAST_MIN_BLOCKS
 #define A3D_CAST_MIN_BLOCKS 28  // resident CTAs (= warps) per SM the register allocation must allow
@@ -574,10 +562,16 @@ __global__ void __launch_bounds__(kCastBlock, A3D_CAST_MIN_BLOCKS)
             if (EMIT) {
               const long long idx = static_cast<long long>(n_vis) + rank;
               if (keep && idx < emit_cap) {
-                double* dst = b.centres_out + 3 * (emit_base + idx);
-                dst[0] = cc.x;
-                dst[1] = cc.y;
-                dst[2] = cc.z;
+                if (b.keys_out) {
+                  unsigned bad = 0;
+                  b.keys_out[emit_base + idx] = key_from_block_voxel(m, ct, bi, vi, &bad);
+                  if (bad) *b.key_error = 1u;
+                } else {
+                  double* dst = b.centres_out + 3 * (emit_base + idx);
+                  dst[0] = cc.x;
+                  dst[1] = cc.y;
+                  dst[2] = cc.z;
+                }
               }
             }
             if (DIGEST) {
@@ -729,119 +723,6 @@ void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, co
 }
 
 int cast_gain_block_threads() { return kCastBlock; }
-
-// ---------------------------------------------------------------------------------------------
-// Re-fold of stored lists that live on the device (SimulatedSensorUpdater::updateSegment,
-// simulated_sensor_updater.cpp:18-22 → computeGainFromVisibleVoxels).  One CTA per list.  Naive and
-// Frontier erase the observed entries from the list like the reference does (naive_evaluator.cpp:28-35,
-// frontier_evaluator.cpp:110-116): stable in-place compaction, chunk by chunk.
-#ifndef A3D_REFOLD_MIN_BLOCKS
-#define A3D_REFOLD_MIN_BLOCKS 4  // resident 256-thread CTAs per SM the register allocation must allow
-#endif
-__global__ void __launch_bounds__(256, A3D_REFOLD_MIN_BLOCKS)
-    k_refold(MapView m, EvalView e, int n, double* __restrict__ pool,
-             const long long* __restrict__ offsets, long long* __restrict__ counts,
-             const double* __restrict__ origins, double* __restrict__ gains_out) {
-  __shared__ CenterTables ct;
-  __shared__ unsigned s_warp[8];
-  __shared__ unsigned long long s_cnt[6];
-  __shared__ double s_w;
-  __shared__ long long s_base;
-  init_center_tables(m, &ct);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const bool erases = e.kind == A3D_EVAL_NAIVE || e.kind == A3D_EVAL_FRONTIER;
-  for (int li = blockIdx.x; li < n; li += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
-    if (threadIdx.x == 0) {
-      s_w = 0.0;
-      s_base = 0;
-    }
-    __syncthreads();
-    double* list = pool + 3 * offsets[li];
-    const long long cnt = counts[li];
-    const D3 origin = origins ? D3{origins[3 * li], origins[3 * li + 1], origins[3 * li + 2]}
-                              : D3{0.0, 0.0, 0.0};
-    unsigned c[6] = {0, 0, 0, 0, 0, 0};
-    double wsum = 0.0;
-    for (long long c0 = 0; c0 < cnt; c0 += blockDim.x) {
-      const long long i = c0 + threadIdx.x;
-      bool kp = false;
-      D3 v{0.0, 0.0, 0.0};
-      if (i < cnt) {
-        v = D3{list[3 * i], list[3 * i + 1], list[3 * i + 2]};
-        kp = true;
-        // state / observed / frontier bits from the voxel's meta word when v is a canonical centre
-        uint32_t word = 0;
-        const bool have = centre_word(m, ct, v, &word);
-        if (e.kind == A3D_EVAL_VOXEL_TYPE) {
-          const int st = have ? static_cast<int>((word >> 16) & 3u) : voxel_state(m, ct, v);
-          c[st + (bv_contains(e, v) ? 0 : 3)]++;
-        } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
-          const int st = have ? static_cast<int>((word >> 16) & 3u) : voxel_state(m, ct, v);
-          const int hint = (have && st == 2 && e.frontier_voxel_weight > 0.0) ? is_frontier_from_word(m, e, word) : -1;
-          wsum += voxel_weight_value(m, ct, e, v, st, st == 0 ? voxel_weight(m, v) : 0.0, origin, hint);
-        } else {
-          kp = have ? !((word >> 18) & 1u) : !is_observed(m, v);
-          if (kp && e.kind == A3D_EVAL_FRONTIER) {
-            const int hint = have ? is_frontier_from_word(m, e, word) : -1;
-            if (hint >= 0 ? hint != 0 : is_frontier_voxel(m, ct, e, v)) c[0]++;
-          } else if (kp) {
-            c[0]++;
-          }
-        }
-      }
-      if (erases) {
-        // stable compaction of this chunk to list[s_base ...)
-        const unsigned bal = __ballot_sync(kFull, kp);
-        if (lane == 0) s_warp[warp] = __popc(bal);
-        __syncthreads();  // all reads of the chunk are done, warp counts visible
-        unsigned before = 0, total = 0;
-        for (unsigned w = 0; w < blockDim.x / 32; ++w) {
-          before += w < warp ? s_warp[w] : 0;
-          total += s_warp[w];
-        }
-        const long long base = s_base;
-        if (kp) {
-          double* dst = list + 3 * (base + before + __popc(bal & ((1u << lane) - 1u)));
-          dst[0] = v.x;
-          dst[1] = v.y;
-          dst[2] = v.z;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base = base + total;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const unsigned t = __reduce_add_sync(kFull, c[k]);
-      if (lane == 0 && t) atomicAdd(&s_cnt[k], static_cast<unsigned long long>(t));
-    }
-    if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(kFull, wsum, off);
-      if (lane == 0) atomicAdd(&s_w, wsum);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (e.kind == A3D_EVAL_VOXEL_TYPE) {
-        gains_out[li] = voxel_type_gain(e, s_cnt);
-      } else if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
-        gains_out[li] = s_w;
-      } else {
-        gains_out[li] = static_cast<double>(s_cnt[0]);
-        counts[li] = s_base;
-      }
-    }
-  }
-}
-
-void launch_refold(cudaStream_t st, const MapView& m, const EvalView& e, int n, double* pool,
-                   const long long* offsets, long long* counts, const double* origins,
-                   double* gains_out) {
-  if (n <= 0) return;
-  k_refold<<<std::min(n, 148 * 8), 256, 0, st>>>(m, e, n, pool, offsets, counts, origins, gains_out);
-}
 
 // ---------------------------------------------------------------------------------------------
 // clear_from_parents (simulated_sensor_evaluator.cpp:60-76): keep[i] = 0 if centre i occurs anywhere

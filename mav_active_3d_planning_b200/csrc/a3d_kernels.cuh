@@ -44,6 +44,8 @@ struct Batch {
   const unsigned int* seg_mask;     // k_cast_gain: if set, only segments whose bit is 1 are evaluated
   const double* seg_origin;         // n_segments×3 or null (VoxelWeightEvaluator's origin)
   double* centres_out;  // emit mode: cap×3 (single segment) or the pool the offsets index
+  unsigned long long* keys_out;  // emit mode, instead of centres_out: packed voxel keys (a3d_keys.cuh)
+  unsigned int* key_error;       // set to 1 when an entry does not fit a key (keys_out only)
   long long cap;
   const long long* emit_offset;  // emit mode, many segments: n_segments+1 entry offsets into centres_out
   int8_t* tables;       // per-warp ray tables (iterative), table_stride bytes each
@@ -52,6 +54,39 @@ struct Batch {
 };
 
 enum { kEvalNone = -1 };
+
+// VoxelTypeEvaluator's switch without breaks (voxel_type_evaluator.cpp:69-85): UNKNOWN adds
+// unknown+free+occupied, FREE adds free+occupied, OCCUPIED adds occupied.
+__device__ __forceinline__ double voxel_type_gain(const EvalView& e, const unsigned long long* n) {
+  // n[state + 3*outside]; state 0 OCC, 1 FREE, 2 UNKNOWN; gains: unk, occ, free, unk_o, occ_o, free_o
+  double g = 0.0;
+  for (int o = 0; o < 2; ++o) {
+    const double n_unk = static_cast<double>(n[2 + 3 * o]);
+    const double n_free = static_cast<double>(n[1 + 3 * o] + n[2 + 3 * o]);
+    const double n_occ = static_cast<double>(n[0 + 3 * o] + n[1 + 3 * o] + n[2 + 3 * o]);
+    g += n_unk * e.gains[0 + 3 * o];
+    g += n_free * e.gains[2 + 3 * o];
+    g += n_occ * e.gains[1 + 3 * o];
+  }
+  return g;
+}
+
+// One batch of device-resident lists for k_list_pipeline (a3d_lists.cu); every array has n entries
+// unless noted.
+struct ListBatch {
+  int n;
+  unsigned long long* pool;        // packed voxel keys of the arena
+  const long long* offsets;        // where each list starts in pool
+  long long* counts;               // in: list sizes; out: sizes of what stays stored
+  unsigned long long* n_stored;    // out (nullable): size after the parent filter, before the fold's erasure
+  unsigned long long* digests;     // out (nullable): ordered digest of that list
+  unsigned long long* set_digests; // out (nullable)
+  double* gains;                   // out (nullable: no fold)
+  const double* origins;           // n×3 (VoxelWeightEvaluator) or null
+  const int* anc_first;            // n+1 offsets into anc_table / anc_mask, or null: no parent filter
+  const unsigned long long* const* anc_table;  // hash set of each ancestor's stored list
+  const uint32_t* anc_mask;        // its size - 1
+};
 
 struct LaunchCfg {
   int grid, block;
@@ -86,12 +121,13 @@ void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, co
 void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& e, long long n,
                              const double* centres, unsigned long long* counters /*8*/,
                              uint8_t* keep, D3 origin, double* gain_acc /*1, VoxelWeight*/);
-// re-fold of device-resident stored lists, one CTA per list (SimulatedSensorUpdater path)
-void launch_refold(cudaStream_t st, const MapView& m, const EvalView& e, int n, double* pool,
-                   const long long* offsets /*n*/, long long* counts /*n, in/out*/,
-                   const double* origins /*n×3 or null*/, double* gains_out /*n*/);
 void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long long m,
                           const double* other, uint8_t* keep);
+void launch_list_pipeline(cudaStream_t st, const MapView& m, const EvalView& e, const ListBatch& lb);
+void launch_build_sets(cudaStream_t st, int n, const unsigned long long* const* lists, const long long* counts,
+                       unsigned long long* const* tables, const uint32_t* masks);
+void launch_keys_to_centres(cudaStream_t st, const MapView& m, long long n, const unsigned long long* keys,
+                            double* centres);
 int cast_gain_block_threads();
 // throughput kernel (a3d_wave.cu)
 size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride,

@@ -36,6 +36,7 @@
 
 #include "../../include/a3d.h"
 #include "a3d_kernels.cuh"
+#include "a3d_keys.cuh"
 
 // The kernel has ~40 instantiations; to halve the build time this file is compiled as two translation
 // units: as itself (part 1: IterativeRayCaster instantiations + the public entry points) and through
@@ -61,9 +62,6 @@ constexpr int kWaveWarps = A3D_WAVE_WARPS;
 constexpr int kWaveThreads = 32 * kWaveWarps;
 constexpr int kWaveWideWarps = 8;  // CTA width for small batches (2 such CTAs per SM)
 constexpr int kWaveMidWarps = 4;   // ... for mid-size batches (5 per SM)
-constexpr uint64_t kNoKey = ~0ull;  // "no entry"
-constexpr uint64_t kKeyOverflow = 1ull << 63;
-constexpr int kKeyBits = 20, kKeyBias = 1 << 19;
 constexpr int kCatNone = 7;
 constexpr int kNoIdent = INT32_MIN;
 #ifndef A3D_WAVE_MIN_BLOCKS
@@ -106,56 +104,6 @@ struct LaneCounters {
   unsigned n_samp;
 };
 constexpr int kFieldBits = 21;
-
-// Identity of an emitted list entry: g[k] = b[k]*vps + v[k]; bit 30 of g[k] set: axis k keeps a raw
-// artefact voxel index (v = -1 or vps) whose centre double differs from the canonical voxel's
-// (valid g are < 2^19 in magnitude, larger ones flag the segment for the scan-order kernel).
-struct Ident {
-  int g0, g1, g2;
-};
-constexpr int kRawAxisBit = 1 << 30;
-
-// Artefact voxel indices (getGridIndexFromPoint lands one voxel outside the block because of the
-// float block-index rounding): per axis, name the voxel canonically when its centre double
-// (voxblox.cpp:72-79) equals the canonical voxel's centre double, else keep it raw and flag it.
-__device__ __noinline__ Ident make_ident_slow(const MapView& m, const CenterTables& ct, int b0, int b1,
-                                              int b2, int v0, int v1, int v2, unsigned* inexact) {
-  const int b[3] = {b0, b1, b2}, v[3] = {v0, v1, v2};
-  int g[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    g[k] = b[k] * m.vps + v[k];
-    if (g[k] <= -kKeyBias || g[k] >= kKeyBias) *inexact = 1;
-    if (v[k] >= 0 && v[k] < m.vps) continue;
-    if (v[k] < -1 || v[k] > m.vps) {
-      *inexact = 1;  // not an artefact the reference arithmetic can produce; scan-order kernel decides
-      continue;
-    }
-    const int bq = v[k] < 0 ? b[k] - 1 : b[k] + 1;
-    const int vq = v[k] < 0 ? m.vps - 1 : 0;
-    const double a = __dadd_rn(static_cast<double>(origin_point(b[k], m.bs_f)), ct.d[v[k] + 1]);
-    const double c = __dadd_rn(static_cast<double>(origin_point(bq, m.bs_f)), ct.d[vq + 1]);
-    if (a != c) g[k] ^= kRawAxisBit;
-  }
-  return Ident{g[0], g[1], g[2]};
-}
-
-__device__ __forceinline__ uint64_t pack_key(const Ident& id, unsigned* inexact) {
-  // bit30 != bit31 ⇒ raw-axis flag
-  const int flags = static_cast<int>(static_cast<unsigned>(id.g0 ^ (id.g0 << 1)) >> 31) |
-                    static_cast<int>(static_cast<unsigned>(id.g1 ^ (id.g1 << 1)) >> 31) << 1 |
-                    static_cast<int>(static_cast<unsigned>(id.g2 ^ (id.g2 << 1)) >> 31) << 2;
-  const int h0 = (flags & 1) ? id.g0 ^ kRawAxisBit : id.g0, h1 = (flags & 2) ? id.g1 ^ kRawAxisBit : id.g1,
-            h2 = (flags & 4) ? id.g2 ^ kRawAxisBit : id.g2;
-  const unsigned u0 = static_cast<unsigned>(h0 + kKeyBias), u1 = static_cast<unsigned>(h1 + kKeyBias),
-                 u2 = static_cast<unsigned>(h2 + kKeyBias);
-  if ((u0 | u1 | u2) >> kKeyBits) {
-    *inexact = 1;
-    return kKeyOverflow;
-  }
-  return static_cast<uint64_t>(u0) | (static_cast<uint64_t>(u1) << kKeyBits) |
-         (static_cast<uint64_t>(u2) << (2 * kKeyBits)) | (static_cast<uint64_t>(flags) << 60);
-}
 
 // Per-lane state of the ray part a lane is marching (kept small: it lives in registers across the
 // whole engine loop).
@@ -1013,7 +961,6 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps      ? A3D_WAV
         __syncthreads();
         const long long emit_base = b.emit_offset ? b.emit_offset[seg] : 0;
         const long long emit_cap = b.emit_offset ? b.emit_offset[seg + 1] - emit_base : b.cap;
-        const int vmask = m.vps - 1;
         for (int q = static_cast<int>(warp); q < 2 * n_rays; q += WARPS) {
           const size_t at = cta_base * 2 + static_cast<size_t>(q & 1) * n_rays + (q >> 1);
           if (!(ws.rec.info[at] & 8)) continue;
@@ -1026,22 +973,14 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == kWaveWarps      ? A3D_WAV
             if (idx >= emit_cap) break;
             const unsigned long long key = __ldcs(&ws.ent[at * static_cast<size_t>(ws.kmax) + k + skip]);
             A3D_DEV_CHECK(k + skip < static_cast<int>(ws.cnt[at]) && ws.cnt[at] <= ws.kmax);
-            double* dst = b.centres_out + 3 * (emit_base + idx);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-              const int g = static_cast<int>((key >> (kKeyBits * a)) & ((1u << kKeyBits) - 1u)) - kKeyBias;
-              int bb = g >> m.vps_shift, vv = g & vmask;
-              if ((key >> (60 + a)) & 1u) {
-                // raw artefact index on this axis (make_ident_slow): voxel -1 of block b, or voxel vps
-                if (vv == vmask) {
-                  bb += 1;
-                  vv = -1;
-                } else {
-                  bb -= 1;
-                  vv = m.vps;
-                }
-              }
-              dst[a] = __dadd_rn(static_cast<double>(origin_point(bb, m.bs_f)), ct.d[vv + 1]);
+            if (b.keys_out) {
+              b.keys_out[emit_base + idx] = key;
+            } else {
+              const D3 cc = key_centre(m, ct, key);
+              double* dst = b.centres_out + 3 * (emit_base + idx);
+              dst[0] = cc.x;
+              dst[1] = cc.y;
+              dst[2] = cc.z;
             }
           }
         }
@@ -1190,7 +1129,7 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
                       int warps) {
   size_t stride = 0;
   const bool extra = digest || e.kind == A3D_EVAL_VOXEL_WEIGHT;  // per-part first_hash / first value
-  const int emit_kmax = b.centres_out ? c.kmax : 0;
+  const int emit_kmax = (b.centres_out || b.keys_out) ? c.kmax : 0;
   wave_scratch_bytes(c.n_rays, grid, extra, &stride, emit_kmax);
   WaveScratch ws{};
   ws.rays_stride = stride;

@@ -551,7 +551,7 @@ SimulatedSensorEvaluator::~SimulatedSensorEvaluator() {
 
 bool SimulatedSensorEvaluator::computeGainsStored(const std::vector<TrajectorySegment*>& segments) {
   auto* cam = dynamic_cast<sensor_model::CameraModel*>(sensor_model_.get());
-  if (!cam || !cam->handle() || !eval_ || p_clear_from_parents_) return false;
+  if (!cam || !cam->handle() || !eval_) return false;
   if (!device_lists_) {
     a3d_store* st = nullptr;
     if (a3d_store_create(gpu_map_->context(), &st) != A3D_OK) return false;
@@ -559,9 +559,30 @@ bool SimulatedSensorEvaluator::computeGainsStored(const std::vector<TrajectorySe
   }
   std::vector<double> pos, quat, origins(segments.size() * 3, 0.0);
   std::vector<int32_t> view_segment;
-  std::vector<uint64_t> keys(segments.size()), n_vis(segments.size());
+  std::vector<uint64_t> keys(segments.size()), n_vis(segments.size()), parent_keys(segments.size(), 0);
+  std::map<const TrajectorySegment*, uint64_t> in_batch;
   for (size_t s = 0; s < segments.size(); ++s) {
     keys[s] = next_key_++;
+    in_batch[segments[s]] = keys[s];
+  }
+  for (size_t s = 0; s < segments.size(); ++s) {
+    if (p_clear_from_parents_) {
+      // simulated_sensor_evaluator.cpp:60-76 walks traj_in->parent upwards; on the device the chain is
+      // key → parent key.  The nearest ancestor that holds a list starts it (it links on to its own).
+      for (const TrajectorySegment* a = segments[s]->parent; a; a = a->parent) {
+        auto hit = in_batch.find(a);
+        if (hit != in_batch.end()) {
+          parent_keys[s] = hit->second;
+          break;
+        }
+        if (auto* d = dynamic_cast<DeviceSensorInfo*>(a->info.get())) {
+          if (d->store.lock() != device_lists_) return false;
+          parent_keys[s] = d->key;
+          break;
+        }
+        if (dynamic_cast<SimulatedSensorInfo*>(a->info.get())) return false;  // host-side list: per-segment path
+      }
+    }
     if (segments[s]->trajectory.empty()) continue;
     std::vector<int> indices;
     cam->sampleViewpoints(&indices, *segments[s]);
@@ -573,7 +594,8 @@ bool SimulatedSensorEvaluator::computeGainsStored(const std::vector<TrajectorySe
   if (a3d_compute_gains_stored(gpu_map_->context(), cam->handle(), eval_, device_lists_->store,
                                static_cast<int>(view_segment.size()), pos.data(), quat.data(),
                                view_segment.data(), static_cast<int>(segments.size()), keys.data(),
-                               gains.data(), n_vis.data(), origins.data()) != A3D_OK) {
+                               p_clear_from_parents_ ? parent_keys.data() : nullptr, gains.data(), n_vis.data(),
+                               nullptr, nullptr, nullptr, origins.data()) != A3D_OK) {
     planner_.printError(std::string("a3d_compute_gains_stored: ") + a3d_last_error(gpu_map_->context()));
     return false;
   }
@@ -642,7 +664,9 @@ void SimulatedSensorEvaluator::buildEval() {
   }
   a3d_eval_params p{};
   p.kind = evalKind();
-  p.clear_from_parents = 0;  // handled per segment in computeGain (a3d_filter_not_in)
+  // read by a3d_compute_gains_stored (computeGainsStored: ancestors' lists are subtracted on the
+  // device); the per-segment computeGain below filters against host-side lists with a3d_filter_not_in
+  p.clear_from_parents = p_clear_from_parents_ ? 1 : 0;
   p.surface_frontiers = 1;
   p.checking_distance = 1.0;
   p.gains[0] = 1.0;

@@ -718,14 +718,19 @@ def test_device_resident_lists_and_refold(capi, O, room02):
         ev = ctx.evaluator(ekind, **kw)
         oe = O.eval_params(ekind, **kw)
         store = capi.Store(ctx)
-        got = store.compute_gains(caster, ev, keys, pos, quat)
+        got = store.compute_gains(caster, ev, keys, pos, quat, digests=True)
         want = oc.compute_gains(oe, pos, quat)
-        assert np.array_equal(got["n_visible"], want["n_visible"])
+        for k in ("n_visible", "n_samples", "digest", "set_digest"):
+            assert np.array_equal(got[k], want[k]), (ekind, k)
         assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
         lists = [store.get(k) for k in keys]
         for s in range(12):
-            assert len(lists[s]) == want["n_visible"][s] and O.digest(lists[s]) == want["digest"][s]
-        assert store.nbytes == 24 * int(want["n_visible"].sum())
+            # what the reference holds after computeGain: Naive / Frontier erased the observed entries
+            ref_list, _ = oc.visible_voxels(pos[s:s + 1], quat[s:s + 1])
+            if ekind[0] != "V":
+                ref_list = ref_list[om.is_observed(ref_list) == 0]
+            assert np.array_equal(lists[s], ref_list), (ekind, s)
+        assert store.nbytes == 8 * int(want["n_visible"].sum())   # packed voxel keys
         # two rounds of map deltas: more of the map becomes observed, distances move
         for _ in range(2):
             sel = rng.choice(room02.n_blocks, room02.n_blocks // 5, replace=False)
@@ -745,9 +750,97 @@ def test_device_resident_lists_and_refold(capi, O, room02):
         om.upload_blocks(room02.block_idx, room02.dist, room02.observed, room02.weight)
         store.compute_gains(caster, ev, keys[:6], pos[:6], quat[:6])
         store.erase(keys[6:])
-        assert store.list_size(keys[7]) == -1 and store.list_size(keys[0]) == want["n_visible"][0]
-        assert store.nbytes == 24 * int(want["n_visible"][:6].sum())
+        assert store.list_size(keys[7]) == -1 and store.list_size(keys[0]) == len(store.get(keys[0]))
+        assert store.nbytes == 8 * int(want["n_visible"][:6].sum())
         with pytest.raises(capi.A3DError):
             store.refold(ev, keys[6:8])
+        with pytest.raises(capi.A3DError):   # repeated keys in one call
+            store.refold(ev, keys[[0, 0]])
+        with pytest.raises(capi.A3DError):
+            store.compute_gains(caster, ev, keys[[1, 1]], pos[:2], quat[:2])
         store.close()
+    ctx.close()
+
+
+def test_store_clear_from_parents(capi, O, room02):
+    """Batch clear_from_parents on the device (simulated_sensor_evaluator.cpp:60-76): ancestors given by
+    store keys, in the same batch and from earlier calls; every evaluator; against the oracle's tree."""
+    from mav_active_3d_planning_b200 import synth
+    import golden_cases as G
+    ctx, om = make_pair(capi, O, room02)
+    pos, quat = G.chain_poses(*synth.candidate_views(room02, 8))
+    parent = G.CHAIN_PARENT
+    keys = np.arange(1, 9, dtype=np.uint64) * 1000
+    pkeys = np.where(parent < 0, 0, keys[np.maximum(parent, 0)]).astype(np.uint64)
+    for ckind in ("IterativeRayCaster", "SimpleRayCaster"):
+        caster = ctx.caster(ckind, **CAM_BASE)
+        oc = om.caster(ckind, **CAM_BASE)
+        for ekind, kw in (("VoxelTypeEvaluator", dict(gain_free=0.5, gain_occupied=0.25)), ("NaiveEvaluator", {}),
+                          ("FrontierEvaluator", {}), ("VoxelWeightEvaluator", {})):
+            ev = ctx.evaluator(ekind, clear_from_parents=True, **kw)
+            want = oc.compute_gains(O.eval_params(ekind, clear_from_parents=True, **kw), pos, quat, parent=parent)
+            # (a) the whole tree in one call
+            got = ctx.compute_gains(caster, ev, pos, quat, parent=parent)
+            for k in ("n_visible", "n_samples", "digest", "set_digest"):
+                assert np.array_equal(got[k], want[k]), (ckind, ekind, k)
+            assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
+            # (b) like the planner: the tree grows call by call, parents are already in the store
+            store = capi.Store(ctx)
+            for lo, hi in ((0, 1), (1, 3), (3, 8)):
+                r = store.compute_gains(caster, ev, keys[lo:hi], pos[lo:hi], quat[lo:hi], parent_keys=pkeys[lo:hi],
+                                        digests=True)
+                for k in ("n_visible", "digest"):
+                    assert np.array_equal(r[k], want[k][lo:hi]), (ckind, ekind, k, lo)
+                assert np.allclose(r["gain"], want["gain"][lo:hi], rtol=GAIN_RTOL, atol=0)
+            with pytest.raises(capi.A3DError):
+                store.compute_gains(caster, ev, keys[:1] + 7, pos[:1], quat[:1], parent_keys=np.array([424242], np.uint64))
+            store.close()
+    ctx.close()
+
+
+def test_map_reconfigure_after_clear(capi, O):
+    """a3d_map_config with a different voxels_per_side after a3d_map_clear: slabs are re-sized, objects
+    built for the old geometry are refused."""
+    from mav_active_3d_planning_b200 import synth
+    m8, m16 = synth.room_map(0.2, 8), synth.room_map(0.2, 16)
+    ctx = capi.Context(0)
+    ctx.upload_map(m8)
+    old_caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    old_ev = ctx.evaluator("VoxelTypeEvaluator")
+    pos, quat = synth.candidate_views(m16, 6, seed=3)
+    ctx.compute_gains(old_caster, old_ev, pos, quat)
+    ctx.clear()
+    ctx.upload_map(m16)     # map_config(0.2, 16) + upload
+    with pytest.raises(capi.A3DError) as e:
+        ctx.compute_gains(old_caster, old_ev, pos, quat)
+    assert e.value.code == -3
+    om = O.OracleMap.from_synth(m16)
+    pts = probe_points(m16, 5000, 5)
+    assert np.array_equal(ctx.voxel_state(pts), om.voxel_state(pts))
+    assert np.array_equal(ctx.voxel_weight(pts), om.voxel_weight(pts))
+    caster, ev = ctx.caster("IterativeRayCaster", **CAM_BASE), ctx.evaluator("VoxelTypeEvaluator")
+    want = om.caster("IterativeRayCaster", **CAM_BASE).compute_gains(O.eval_params("VoxelTypeEvaluator"), pos, quat)
+    got = ctx.compute_gains(caster, ev, pos, quat)
+    for k in ("n_visible", "n_samples", "digest"):
+        assert np.array_equal(got[k], want[k]), k
+    ctx.close()
+
+
+def test_esdf_only_delta_keeps_tsdf_weights(capi, O, room02):
+    """A delta without weights (ESDF-only layer message, the multi-GPU broadcast payload) must not wipe
+    the TSDF weights of blocks that already exist: VoxelWeightEvaluator parity afterwards."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    rng = np.random.default_rng(21)
+    sel = rng.choice(room02.n_blocks, room02.n_blocks // 3, replace=False)
+    nd = (room02.dist[sel] + rng.normal(0, 0.02, room02.dist[sel].shape)).astype(np.float32)
+    ctx.upload_blocks(room02.block_idx[sel], nd, room02.observed[sel])                      # no weights
+    om.upload_blocks(room02.block_idx[sel], nd, room02.observed[sel], room02.weight[sel])   # weights unchanged
+    pts = probe_points(room02, 5000, 6)
+    assert np.array_equal(ctx.voxel_weight(pts), om.voxel_weight(pts))
+    pos, quat = synth.candidate_views(room02, 8, seed=4)
+    caster, ev = ctx.caster("IterativeRayCaster", **CAM_BASE), ctx.evaluator("VoxelWeightEvaluator")
+    want = om.caster("IterativeRayCaster", **CAM_BASE).compute_gains(O.eval_params("VoxelWeightEvaluator"), pos, quat)
+    got = ctx.compute_gains(caster, ev, pos, quat, digests=False, set_digests=False)
+    assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
     ctx.close()
