@@ -57,6 +57,9 @@ typedef struct a3d_ctx a3d_ctx;
 typedef struct a3d_caster a3d_caster;
 typedef struct a3d_eval a3d_eval;
 typedef struct a3d_store a3d_store;
+typedef struct a3d_group a3d_group;
+typedef struct a3d_group_caster a3d_group_caster;
+typedef struct a3d_group_eval a3d_group_eval;
 
 /* Parameters of a CameraModel subclass exactly as setupFromParamMap parses them
    (core/src/module/sensor_model/sensor_model.cpp:9-27, camera_model.cpp:170-183,
@@ -292,6 +295,44 @@ int a3d_filter_not_in(a3d_ctx* ctx, int64_t n, const double* centres, int64_t m,
 
 /* BoundingVolume::contains (core/src/data/bounding_volume.cpp:33-57), batched. */
 int a3d_bv_contains(a3d_ctx* ctx, const a3d_eval* eval, int64_t n, const double* pts, uint8_t* out);
+
+/* ---- multi-GPU group (SURVEY.md §8(b),(e)) ----------------------------------------------------------
+ * The N-GPU form of the calls above for ONE host thread of ONE process — what the reference's planner
+ * (single-threaded, online_planner.cpp:414-416) would hold instead of a context.  A group owns one
+ * a3d_ctx per device and one NCCL communicator per device (ncclCommInitAll; NCCL is dlopen-ed here, a
+ * single-GPU group never loads it).  The map mirror is REPLICATED: an update goes host → GPU 0 once,
+ * is ncclBroadcast over NVLink to the other GPUs and applied by every GPU to its own mirror.
+ * Segments are SHARDED: dealt to the GPUs in blocks of `deal_block` segments (option, default 64; all
+ * views of a segment stay on one GPU), every GPU casts its share, the per-segment records
+ * (gain, n_visible, n_samples, digests) are ncclAllGather-ed and returned in the caller's order.
+ * Same argument meaning, error codes and outputs as the single-context calls they mirror. */
+int a3d_group_create(const int* device_ids, int n_dev, a3d_group** out);
+void a3d_group_destroy(a3d_group* g);
+/* text of the last error (g == NULL: of the last failed a3d_group_create) */
+const char* a3d_group_last_error(const a3d_group* g);
+int a3d_group_size(const a3d_group* g);
+/* the i-th device's context, e.g. for point queries or event timing (owned by the group) */
+a3d_ctx* a3d_group_ctx(a3d_group* g, int i);
+int a3d_group_map_config(a3d_group* g, float voxel_size, int voxels_per_side);
+int a3d_group_map_upload_blocks(a3d_group* g, int n, const int32_t* block_idx, const float* esdf_dist,
+                                const uint8_t* esdf_observed, const float* tsdf_weight);
+int a3d_group_map_remove_blocks(a3d_group* g, int n, const int32_t* block_idx);
+int a3d_group_map_clear(a3d_group* g);
+int a3d_group_caster_create(a3d_group* g, const a3d_caster_params* p, a3d_group_caster** out);
+void a3d_group_caster_destroy(a3d_group_caster* c);
+int a3d_group_caster_get_info(const a3d_group_caster* c, a3d_caster_info* out);
+int a3d_group_eval_create(a3d_group* g, const a3d_eval_params* p, a3d_group_eval** out);
+void a3d_group_eval_destroy(a3d_group_eval* e);
+/* "deal_block" (see above) or any a3d_set_option name, applied to every device */
+int a3d_group_set_option(a3d_group* g, const char* name, int64_t value);
+/* a3d_compute_gains over all GPUs of the group; synchronous on return */
+int a3d_group_compute_gains(a3d_group* g, const a3d_group_caster* caster, const a3d_group_eval* eval, int n_views,
+                            const double* pos, const double* quat, const int32_t* view_segment, int n_segments,
+                            double* gains_out, uint64_t* n_visible_out, uint64_t* n_samples_out,
+                            uint64_t* digests_out, uint64_t* set_digests_out, const double* seg_origin);
+/* max over the devices of a3d_last_kernel_ms / sum of a3d_kernel_launches */
+float a3d_group_last_kernel_ms(a3d_group* g);
+uint64_t a3d_group_kernel_launches(a3d_group* g);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,11 @@ EXPORTS = [
     "a3d_caster_direction", "a3d_eval_create", "a3d_eval_destroy", "a3d_compute_gains",
     "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_filter_not_in",
     "a3d_bv_contains", "a3d_store_create", "a3d_store_destroy", "a3d_compute_gains_stored",
-    "a3d_compute_gains_tree",
+    "a3d_compute_gains_tree", "a3d_group_create", "a3d_group_destroy", "a3d_group_last_error", "a3d_group_size",
+    "a3d_group_ctx", "a3d_group_map_config", "a3d_group_map_upload_blocks", "a3d_group_map_remove_blocks",
+    "a3d_group_map_clear", "a3d_group_caster_create", "a3d_group_caster_destroy", "a3d_group_caster_get_info",
+    "a3d_group_eval_create", "a3d_group_eval_destroy", "a3d_group_set_option", "a3d_group_compute_gains",
+    "a3d_group_last_kernel_ms", "a3d_group_kernel_launches",
     "a3d_store_refold", "a3d_store_erase", "a3d_store_list_size", "a3d_store_get", "a3d_store_bytes",
 ]
 
@@ -184,6 +188,31 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_store_destroy.restype = None
     lib.a3d_compute_gains_stored.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp,
                                              vp, vp, vp]
+    lib.a3d_group_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    lib.a3d_group_destroy.argtypes = [vp]
+    lib.a3d_group_destroy.restype = None
+    lib.a3d_group_last_error.argtypes = [vp]
+    lib.a3d_group_last_error.restype = C.c_char_p
+    lib.a3d_group_size.argtypes = [vp]
+    lib.a3d_group_ctx.argtypes = [vp, C.c_int]
+    lib.a3d_group_ctx.restype = vp
+    lib.a3d_group_map_config.argtypes = [vp, C.c_float, C.c_int]
+    lib.a3d_group_map_upload_blocks.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    lib.a3d_group_map_remove_blocks.argtypes = [vp, C.c_int, vp]
+    lib.a3d_group_map_clear.argtypes = [vp]
+    lib.a3d_group_caster_create.argtypes = [vp, C.POINTER(CasterParams), C.POINTER(vp)]
+    lib.a3d_group_caster_destroy.argtypes = [vp]
+    lib.a3d_group_caster_destroy.restype = None
+    lib.a3d_group_caster_get_info.argtypes = [vp, C.POINTER(CasterInfo)]
+    lib.a3d_group_eval_create.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(vp)]
+    lib.a3d_group_eval_destroy.argtypes = [vp]
+    lib.a3d_group_eval_destroy.restype = None
+    lib.a3d_group_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.a3d_group_compute_gains.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.a3d_group_last_kernel_ms.argtypes = [vp]
+    lib.a3d_group_last_kernel_ms.restype = C.c_float
+    lib.a3d_group_kernel_launches.argtypes = [vp]
+    lib.a3d_group_kernel_launches.restype = C.c_uint64
     lib.a3d_compute_gains_tree.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.a3d_store_refold.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
     lib.a3d_store_erase.argtypes = [vp, C.c_int, vp]
@@ -551,3 +580,100 @@ class Evaluator:
                 self.ctx.lib.a3d_eval_destroy(self.h)
         except Exception:
             pass
+
+
+class Group:
+    """N GPUs behind one handle, one host thread, one process (a3d_group_*): map replicated with an NCCL
+    broadcast of every update, segments dealt to the GPUs, gains all-gathered."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.a3d_group_create(ids, len(devices), C.byref(h))
+        if rc:
+            raise A3DError(rc, (self.lib.a3d_group_last_error(None) or b"").decode())
+        self.h = h
+        self.devices = list(devices)
+        self._keep = []
+
+    def _ck(self, rc):
+        if rc:
+            raise A3DError(rc, (self.lib.a3d_group_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            for kind, h in self._keep:
+                (self.lib.a3d_group_caster_destroy if kind == "c" else self.lib.a3d_group_eval_destroy)(h)
+            self._keep = []
+            self.lib.a3d_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_map(self, m):
+        self._ck(self.lib.a3d_group_map_config(self.h, C.c_float(m.voxel_size), m.vps))
+        self.upload_blocks(m.block_idx, m.dist, m.observed, m.weight)
+
+    def upload_blocks(self, block_idx, dist, observed, weight=None):
+        block_idx = np.ascontiguousarray(block_idx, np.int32)
+        dist = np.ascontiguousarray(dist, np.float32)
+        observed = np.ascontiguousarray(observed, np.uint8)
+        if weight is not None:
+            weight = np.ascontiguousarray(weight, np.float32)
+        self._ck(self.lib.a3d_group_map_upload_blocks(self.h, block_idx.shape[0], _ptr(block_idx), _ptr(dist),
+                                                      _ptr(observed), _ptr(weight)))
+
+    def remove_blocks(self, block_idx):
+        block_idx = np.ascontiguousarray(block_idx, np.int32)
+        self._ck(self.lib.a3d_group_map_remove_blocks(self.h, block_idx.shape[0], _ptr(block_idx)))
+
+    def set_option(self, name, value):
+        self._ck(self.lib.a3d_group_set_option(self.h, name.encode(), int(value)))
+
+    def caster(self, kind, **kw):
+        p = caster_params(kind, **kw)
+        h = C.c_void_p()
+        self._ck(self.lib.a3d_group_caster_create(self.h, C.byref(p), C.byref(h)))
+        self._keep.append(("c", h))
+        return h
+
+    def evaluator(self, kind, **kw):
+        p = eval_params(kind, **kw)
+        h = C.c_void_p()
+        self._ck(self.lib.a3d_group_eval_create(self.h, C.byref(p), C.byref(h)))
+        self._keep.append(("e", h))
+        return h
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.a3d_group_last_kernel_ms(self.h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.a3d_group_kernel_launches(self.h))
+
+    def compute_gains(self, caster, evaluator, pos, quat, view_segment=None, n_segments=None, digests=True,
+                      set_digests=True, seg_origin=None):
+        pos = _pts(pos)
+        quat = np.ascontiguousarray(quat, np.float64)
+        n_views = len(pos)
+        if view_segment is None:
+            view_segment = np.arange(n_views, dtype=np.int32)
+        view_segment = np.ascontiguousarray(view_segment, np.int32)
+        if n_segments is None:
+            n_segments = int(view_segment.max()) + 1 if n_views else 0
+        gains = np.zeros(n_segments, np.float64)
+        nvis = np.zeros(n_segments, np.uint64)
+        nsamp = np.zeros(n_segments, np.uint64)
+        dig = np.zeros(n_segments, np.uint64) if digests else None
+        sdig = np.zeros(n_segments, np.uint64) if set_digests else None
+        self._ck(self.lib.a3d_group_compute_gains(
+            self.h, caster, evaluator, n_views, _ptr(pos), _ptr(quat), _ptr(view_segment), n_segments, _ptr(gains),
+            _ptr(nvis), _ptr(nsamp), _ptr(dig), _ptr(sdig),
+            _ptr(None if seg_origin is None else np.ascontiguousarray(seg_origin, np.float64))))
+        return dict(gain=gains, n_visible=nvis, n_samples=nsamp, digest=dig, set_digest=sdig)

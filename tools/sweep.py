@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--evaluator", default=None, help="override the workload's evaluator, e.g. VoxelWeight")
     ap.add_argument("--cast-kernel", type=int, default=0, help="0 auto, 1 scan-order, 2 wavefront")
     ap.add_argument("--wave-cta", type=int, default=0, help="0 auto, 1 two-warp CTAs, 2 eight-warp CTAs")
+    ap.add_argument("--wave-help", type=int, default=1, help="cross-CTA help: 0 off, 1 on")
+    ap.add_argument("--wave-helpers", type=int, default=-1, help="surplus CTAs per segment for small batches")
     args = ap.parse_args()
     cfg = dict(synth.CONFIGS[args.workload])
     if args.evaluator:
@@ -46,6 +48,12 @@ def main():
     ev = ctx.evaluator(cfg["evaluator"] + "Evaluator")
     ctx.set_option("cast_kernel", args.cast_kernel)
     ctx.set_option("wave_cta", args.wave_cta)
+    try:
+        ctx.set_option("wave_help", args.wave_help)
+        if args.wave_helpers >= 0:
+            ctx.set_option("wave_helpers", args.wave_helpers)
+    except capi.A3DError:
+        pass  # (an older build of the library under A/B test)
     dev = torch.device("cuda", 0)
     peak = 6555.2
     try:
