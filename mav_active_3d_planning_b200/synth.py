@@ -112,39 +112,56 @@ def _sdf_chunk(x, y, z, extent, shell, boxes, dmax):
     return np.clip(d, -dmax, dmax)
 
 
-def _build(voxel_size, vps, extent, boxes, waypoints, obs_radius, dmax, weight_seed):
+def _build_slab(args):
+    """One x-slab of blocks (bx): (block_idx, dist, observed) of its allocated blocks, or None."""
+    bx, vs, vps, nb, extent, boxes, wp, obs_radius, dmax = args
+    nv = vps ** 3
+    yv = (np.arange(nb[1] * vps) + 0.5) * vs
+    zv = (np.arange(nb[2] * vps) + 0.5) * vs
+    xv = (np.arange(bx * vps, (bx + 1) * vps) + 0.5) * vs
+    # skip x-slabs that no waypoint sphere reaches
+    if np.all(np.abs(np.clip(wp[:, 0], xv[0], xv[-1]) - wp[:, 0]) > obs_radius):
+        return None
+    d = _sdf_chunk(xv, yv, zv, extent, vs, boxes, dmax)
+    obs = np.zeros(d.shape, bool)
+    for w in wp:
+        r2 = ((xv - w[0]) ** 2)[:, None, None] + ((yv - w[1]) ** 2)[None, :, None] \
+            + ((zv - w[2]) ** 2)[None, None, :]
+        obs |= r2 <= obs_radius * obs_radius
+    # (vps, nby, vps, nbz, vps) → (nby, nbz, z, y, x)
+    d5 = d.reshape(vps, nb[1], vps, nb[2], vps).transpose(1, 3, 4, 2, 0).reshape(nb[1], nb[2], nv)
+    o5 = obs.reshape(vps, nb[1], vps, nb[2], vps).transpose(1, 3, 4, 2, 0).reshape(nb[1], nb[2], nv)
+    keep = o5.any(axis=2)
+    by, bz = np.nonzero(keep)
+    if len(by) == 0:
+        return None
+    return (np.stack([np.full(len(by), bx), by, bz], 1).astype(np.int32), d5[by, bz].astype(np.float32),
+            o5[by, bz].astype(np.uint8))
+
+
+def _build(voxel_size, vps, extent, boxes, waypoints, obs_radius, dmax, weight_seed, workers=None):
     vs = float(np.float32(voxel_size))
     bs = vs * vps
     nb = [int(math.ceil(extent[k] / bs - 1e-9)) for k in range(3)]
     wp = np.asarray(waypoints, np.float64)
-    idx_l, dist_l, obs_l, w_l = [], [], [], []
     nv = vps ** 3
-    yv = (np.arange(nb[1] * vps) + 0.5) * vs
-    zv = (np.arange(nb[2] * vps) + 0.5) * vs
-    for bx in range(nb[0]):
-        xv = (np.arange(bx * vps, (bx + 1) * vps) + 0.5) * vs
-        # skip x-slabs that no waypoint sphere reaches
-        if np.all(np.abs(np.clip(wp[:, 0], xv[0], xv[-1]) - wp[:, 0]) > obs_radius):
-            continue
-        d = _sdf_chunk(xv, yv, zv, extent, vs, boxes, dmax)
-        obs = np.zeros(d.shape, bool)
-        for w in wp:
-            r2 = ((xv - w[0]) ** 2)[:, None, None] + ((yv - w[1]) ** 2)[None, :, None] \
-                + ((zv - w[2]) ** 2)[None, None, :]
-            obs |= r2 <= obs_radius * obs_radius
-        # (vps, nby, vps, nbz, vps) → (nby, nbz, z, y, x)
-        d5 = d.reshape(vps, nb[1], vps, nb[2], vps).transpose(1, 3, 4, 2, 0).reshape(nb[1], nb[2], nv)
-        o5 = obs.reshape(vps, nb[1], vps, nb[2], vps).transpose(1, 3, 4, 2, 0).reshape(nb[1], nb[2], nv)
-        keep = o5.any(axis=2)
-        by, bz = np.nonzero(keep)
-        if len(by) == 0:
-            continue
-        idx_l.append(np.stack([np.full(len(by), bx), by, bz], 1).astype(np.int32))
-        dist_l.append(d5[by, bz].astype(np.float32))
-        obs_l.append(o5[by, bz].astype(np.uint8))
-    block_idx = np.concatenate(idx_l) if idx_l else np.zeros((0, 3), np.int32)
-    dist = np.concatenate(dist_l) if dist_l else np.zeros((0, nv), np.float32)
-    observed = np.concatenate(obs_l) if obs_l else np.zeros((0, nv), np.uint8)
+    jobs = [(bx, vs, vps, nb, tuple(extent), boxes, wp, obs_radius, dmax) for bx in range(nb[0])]
+    # big scenes (cfg3: 63 slabs of 6.4 M voxels) are built slab-parallel; the result does not depend
+    # on the number of workers (slabs are independent and concatenated in order)
+    if workers is None:
+        import os
+        workers = min(16, os.cpu_count() or 1) if nb[0] * nb[1] * nb[2] * nv > 64_000_000 else 1
+    if workers > 1:
+        import concurrent.futures as cf
+        import multiprocessing as mp
+        with cf.ProcessPoolExecutor(workers, mp_context=mp.get_context("fork")) as ex:
+            slabs = list(ex.map(_build_slab, jobs))
+    else:
+        slabs = [_build_slab(j) for j in jobs]
+    slabs = [s for s in slabs if s is not None]
+    block_idx = np.concatenate([s[0] for s in slabs]) if slabs else np.zeros((0, 3), np.int32)
+    dist = np.concatenate([s[1] for s in slabs]) if slabs else np.zeros((0, nv), np.float32)
+    observed = np.concatenate([s[2] for s in slabs]) if slabs else np.zeros((0, nv), np.uint8)
     wrng = np.random.Generator(np.random.PCG64(weight_seed))
     weight = (wrng.random(dist.shape, dtype=np.float32) * 99.0 + 1.0) * observed
     return SynthMap(vs, vps, block_idx, dist, observed, weight.astype(np.float32), tuple(extent), boxes)
