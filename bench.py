@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--views", type=int, default=4096, help="candidate segments per GPU")
+    ap.add_argument("--global-views", type=int, default=0,
+                    help="strong scaling: this many candidate segments in total, the SAME list for every N "
+                         "(gain_digest in the JSON line is then equal for every N)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="views in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -202,10 +205,13 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    n_seg = args.views
-    # every rank evaluates its own shard of the global candidate list (weak scaling)
-    m, pos_all, quat_all, (d_idx, d_dist, d_obs) = make_workload(n_seg * world)
-    lo, hi = scheduler.shard_bounds(n_seg * world, world, rank)
+    # every rank evaluates its own shard of the global candidate list: --views per GPU (weak scaling) or
+    # --global-views in total (strong scaling, the same list whatever N is)
+    strong = args.global_views > 0
+    n_global = args.global_views if strong else args.views * world
+    m, pos_all, quat_all, (d_idx, d_dist, d_obs) = make_workload(n_global)
+    lo, hi = scheduler.shard_bounds(n_global, world, rank)
+    n_seg = hi - lo
     pos = np.ascontiguousarray(pos_all[lo:hi])
     quat = np.ascontiguousarray(quat_all[lo:hi])
 
@@ -225,21 +231,32 @@ def run_ours(args):
     nv = m.vps ** 3
     n_delta = d_idx.shape[0]
     dist_bytes = n_delta * nv * 4
-    payload = torch.zeros(dist_bytes + n_delta * nv, dtype=torch.uint8, device=dev)
+    # two receive buffers: the delta of planning step k+1 is broadcast (NCCL, its own stream) while
+    # step k casts; step k+1 waits for it before applying it
+    payloads = [torch.zeros(dist_bytes + n_delta * nv, dtype=torch.uint8, device=dev) for _ in range(2)]
     if rank == 0:
-        payload[:dist_bytes] = torch.from_numpy(d_dist.view(np.uint8).reshape(-1)).to(dev)
-        payload[dist_bytes:] = torch.from_numpy(d_obs.reshape(-1)).to(dev)
+        for pl in payloads:
+            pl[:dist_bytes] = torch.from_numpy(d_dist.view(np.uint8).reshape(-1)).to(dev)
+            pl[dist_bytes:] = torch.from_numpy(d_obs.reshape(-1)).to(dev)
+    pending = {"work": None, "buf": 0}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
 
     def step_device():
+        payload = payloads[pending["buf"]]
         if world > 1:
-            dist.broadcast(payload, src=0)
+            if pending["work"] is None:          # first step: nothing was prefetched
+                dist.broadcast(payload, src=0)
+            else:
+                pending["work"].wait()           # this step's delta, sent while the previous step cast
         ctx.upload_blocks_dev(d_idx, payload.data_ptr(), payload.data_ptr() + dist_bytes)
+        if world > 1:                            # next step's delta travels during this step's cast
+            pending["buf"] ^= 1
+            pending["work"] = dist.broadcast(payloads[pending["buf"]], src=0, async_op=True)
         ctx.compute_gains_dev(caster, ev, n_seg, t_pos.data_ptr(), t_quat.data_ptr(),
                               t_first.data_ptr(), n_seg, t_gain.data_ptr(), t_nvis.data_ptr(),
                               t_nsamp.data_ptr(), 0)
-        return scheduler.gather_gains(t_gain, n_seg * world)
+        return scheduler.gather_gains(t_gain, n_global)
 
     def barrier():
         if world > 1:
@@ -285,11 +302,15 @@ def run_ours(args):
 
         def step_host():
             if world > 1:
-                dist.broadcast(payload, src=0)  # delta still travels rank0 → all on the device side
+                dist.broadcast(payloads[0], src=0)  # delta still travels rank0 → all on the device side
             ctx.upload_blocks(d_idx, h_ddist, h_dobs)
             r = ctx.compute_gains(caster, ev, h_pos, h_quat, h_seg, n_seg, digests=False,
                                   set_digests=False)
+            if world > 1:   # the gains of every rank, gathered (host result → device → NCCL)
+                t_gain_h.copy_(torch.from_numpy(r["gain"]), non_blocking=False)
+                r["all_gains"] = scheduler.gather_gains(t_gain_h, n_global)
             return r
+        t_gain_h = torch.zeros(n_seg, dtype=torch.float64, device=dev)
         for _ in range(2):
             step_host()
         barrier()
@@ -315,7 +336,13 @@ def run_ours(args):
     k_ms = float(np.mean(kernel_ms))
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    steps_views = n_seg * world * args.steps
+    steps_views = n_global * args.steps
+    import hashlib
+    all_gains = step_device().cpu().numpy()     # gathered vector, identical on every rank
+    gain_digest = hashlib.sha256(np.ascontiguousarray(all_gains).tobytes()).hexdigest()[:16]
+    if pending["work"] is not None:
+        pending["work"].wait()
+        torch.cuda.synchronize()
     value = steps_views / (total_ms * 1e-3)
     h2d = h_pos.nbytes + h_quat.nbytes + h_seg.nbytes + h_ddist.nbytes + h_dobs.nbytes + d_idx.nbytes
     d2h = n_seg * 8 * 3
@@ -328,9 +355,9 @@ def run_ours(args):
     out = {
         "metric": "candidate_views_per_sec", "value": value, "unit": "views/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f64 step / f32 lookup", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "views_per_gpu": n_seg, "global_views": n_seg * world,
+        "config": {"workload": WORKLOAD, "views_per_gpu": n_seg, "global_views": n_global,
                    "map_blocks": m.n_blocks, "delta_blocks_per_step": int(n_delta),
                    "samples_per_view": S / n_seg, "visible_per_view": V / n_seg,
                    "l2": "512 MiB buffer written between timed iterations (L2 flush)",
@@ -339,6 +366,8 @@ def run_ours(args):
         "kernel_ms": k_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "traffic_source": "dram__bytes_read+write of one ncu --set full capture of this kernel on "
+                                       "this workload at 4096 views (profiles/traffic.json), not measured in this run",
                      "kernel": ("k_cast_wave" if ctx.last_cast_kernel == 2 else "k_cast_gain") +
                      "<Iterative,VoxelType>",
                      "algorithmic_bytes_per_launch": alg_bytes},
@@ -346,7 +375,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "gain_checksum": float(gains.sum()),
+        "gain_checksum": float(gains.sum()), "gain_digest": gain_digest,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
