@@ -125,12 +125,14 @@ float a3d_last_kernel_ms(a3d_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 uint64_t a3d_kernel_launches(a3d_ctx* ctx);
 /* Tuning / test knobs.  "cast_kernel": 0 = automatic (default), 1 = always the scan-order kernel
-   (k_cast_gain), 2 = require the wavefront kernel (k_cast_wave; errors if ordered digests are asked).
+   (k_cast_gain), 2 = require the wavefront kernel (k_cast_wave; errors if ordered digests are asked),
+   3 = require the kernel chain (a3d_split.cu: gains and counts only; errors if digests are asked or
+   the dense meta volume does not exist).
    "wave_cta": CTA width of the wavefront kernel, 0 = automatic (8 or 4 warps for small and mid-size
    batches, else 2), 1 = always 2 warps, 2 = always 8 warps, 3 = always 4 warps. */
 int a3d_set_option(a3d_ctx* ctx, const char* name, int64_t value);
-/* Which kernel the last a3d_compute_gains*() used: 1 scan-order, 2 wavefront (+ scan-order re-evaluation
-   of flagged segments). */
+/* Which kernel the last a3d_compute_gains*() used: 1 scan-order, 2 wavefront, 3 kernel chain (2 and 3:
+   + scan-order re-evaluation of flagged segments). */
 int a3d_last_cast_kernel(const a3d_ctx* ctx);
 
 /* ---- map mirror: replaces VoxbloxMap (active_3d_planning_voxblox/src/map/voxblox.cpp) ------- */

@@ -157,7 +157,8 @@ struct a3d_ctx {
   DevBuf<unsigned int> sc_counter, sc_inexact;
   DevBuf<uint8_t> sc_wave;
   uint64_t config_gen = 0;  // bumped when a3d_map_config changes the geometry: older casters/evals are stale
-  int opt_cast_kernel = 0;  // 0 auto, 1 scan-order kernel (k_cast_gain), 2 wavefront kernel (k_cast_wave)
+  // 0 auto, 1 scan-order kernel (k_cast_gain), 2 wavefront kernel (k_cast_wave), 3 kernel chain (a3d_split.cu)
+  int opt_cast_kernel = 0;
   int last_cast_kernel = 0;
   int opt_wave_cta = 0;  // 0 auto (wave_warps_auto), 1 always 2 warps, 2 always 8, 3 always 4
 
@@ -733,7 +734,8 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
                  unsigned long long* nvis_dev, unsigned long long* nsamp_dev,
                  unsigned long long* dig_dev, unsigned long long* set_dig_dev, double* centres_dev,
                  long long cap, bool emit, const double* seg_origin_dev,
-                 const long long* emit_offset_dev = nullptr, unsigned long long* keys_dev = nullptr) {
+                 const long long* emit_offset_dev = nullptr, unsigned long long* keys_dev = nullptr,
+                 int n_views = -1 /* total views of the batch when the caller knows it */) {
   if (ctx->h_table.empty()) {
     table_rebuild(ctx, 0);
     int rc = table_upload(ctx);
@@ -774,14 +776,52 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
                        c->view.n_rays < (1 << 24);
   if (ctx->opt_cast_kernel == 2 && !wave_ok)
     return ctx->fail(A3D_ERR_UNSUPPORTED, "cast_kernel=2 (wavefront) cannot produce ordered digests");
-  const bool use_wave = wave_ok && ctx->opt_cast_kernel != 1;
-  ctx->last_cast_kernel = use_wave ? 2 : 1;
-  if (use_wave) {
+  bool use_wave = wave_ok && ctx->opt_cast_kernel != 1 && ctx->opt_cast_kernel != 3;
+  // the kernel chain of a3d_split.cu: gains / counts only, dense meta volume required
+  bool use_split = e && !emit && !dig_dev && !set_dig_dev && n_views >= 0 &&
+                   (ctx->opt_cast_kernel == 0 || ctx->opt_cast_kernel == 3);
+  if (use_wave || use_split) {
     int rc = vol_ensure(ctx);
     if (rc) return rc;
   }
+  use_split = use_split && cast_split_supported(ctx->view(), c->view);
+  if (ctx->opt_cast_kernel == 3 && !use_split)
+    return ctx->fail(A3D_ERR_UNSUPPORTED,
+                     "cast_kernel=3 (kernel chain) needs the dense meta volume and gains-only outputs");
+  if (use_split) use_wave = false;
+  ctx->last_cast_kernel = use_split ? 3 : use_wave ? 2 : 1;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const unsigned int* seg_mask = nullptr;
+  if (use_split) {
+    const size_t per_view = cast_split_bytes_per_view(c->view, ev_view.kind, nullptr);
+    const long long max_views = static_cast<long long>(std::max<size_t>(1, (size_t(4) << 30) / per_view));
+    std::vector<int32_t> h_first;  // needed only to cut the batch into chunks that fit the scratch
+    if (n_views > max_views) {
+      h_first.resize(static_cast<size_t>(n_segments) + 1);
+      CK(cudaMemcpyAsync(h_first.data(), first_dev, h_first.size() * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                         ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const size_t n_words = static_cast<size_t>(n_segments) / 32 + 1;
+    CK(ctx->sc_inexact.reserve(n_words));
+    CK(cudaMemsetAsync(ctx->sc_inexact.p, 0, n_words * sizeof(unsigned int), ctx->stream));
+    for (int seg = 0; seg < n_segments;) {
+      int seg_end = n_segments, v0 = 0, v1 = n_views;
+      if (!h_first.empty()) {
+        v0 = h_first[seg];
+        seg_end = seg + 1;  // (a single segment larger than the budget gets a larger scratch)
+        while (seg_end < n_segments && h_first[seg_end + 1] - v0 <= max_views) ++seg_end;
+        v1 = h_first[seg_end];
+      }
+      CK(ctx->sc_wave.reserve(static_cast<size_t>(v1 - v0) * per_view + 256));
+      launch_cast_split(ctx->stream, ctx->view(), c->view, ev_view, b, seg, seg_end - seg, v0, v1 - v0,
+                        ctx->sc_wave.p, ctx->sc_inexact.p, ctx->sm_count);
+      ctx->launches += cast_split_launches(c->view);
+      CK(cudaGetLastError());
+      seg = seg_end;
+    }
+    seg_mask = ctx->sc_inexact.p;
+  }
   if (use_wave) {
     // as many CTAs as can be resident (measured: trimming the grid so that every CTA gets the same
     // number of segments is slower — throughput follows the number of resident warps)
@@ -1335,13 +1375,13 @@ int a3d_compute_gains_dev(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval
                       reinterpret_cast<unsigned long long*>(n_samples_dev),
                       reinterpret_cast<unsigned long long*>(digests_dev),
                       reinterpret_cast<unsigned long long*>(set_digests_dev), nullptr, 0, false,
-                      seg_origin_dev);
+                      seg_origin_dev, nullptr, nullptr, n_views);
 }
 
 int a3d_set_option(a3d_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return A3D_ERR_INVALID;
   if (std::strcmp(name, "cast_kernel") == 0) {
-    if (value < 0 || value > 2) return ctx->fail(A3D_ERR_INVALID, "cast_kernel must be 0, 1 or 2");
+    if (value < 0 || value > 3) return ctx->fail(A3D_ERR_INVALID, "cast_kernel must be 0, 1, 2 or 3");
     ctx->opt_cast_kernel = static_cast<int>(value);
     return A3D_OK;
   }

@@ -45,6 +45,63 @@ def certified(p64, vs, vps, t_max):
     return safe, g, ~below_int, delta
 
 
+def certified_fma(P0, direction, d, vs, vps, t_max):
+    """The kernel's form of the test: half-voxel coordinate z = fma(float(d), dz, z0) in fp32, without
+    the reference's point.  (fp32 fma emulated in float64: the product of two floats is exact there.)"""
+    vs_inv = float(F(1.0 / float(F(vs))))
+    dz = (direction * (2.0 * vs_inv)).astype(F)
+    z0 = (P0 * (2.0 * vs_inv) - 0.5).astype(F)
+    z = (d.astype(F).astype(np.float64)[:, None] * dz.astype(np.float64) + z0.astype(np.float64)).astype(F)
+    s = (z + MAGIC).astype(F)
+    fr = (z - (s - MAGIC).astype(F)).astype(F)
+    lim = F(0.5) - F(2.0) * F(F(t_max * 9e-7) + F((vps + 1) * (16.0 * 5.97e-8 + 1.1e-6)))
+    safe = np.all(np.abs(fr) < lim, axis=1)
+    h = s.view(np.int32).astype(np.int64) - 0x4B400000
+    return safe, h >> 1, (h & 1) == 0, lim
+
+
+@pytest.mark.parametrize("vs,vps", [(0.1, 16), (0.2, 16), (0.05, 16), (0.2, 8), (0.1, 32), (0.37, 4)])
+@pytest.mark.parametrize("extent", [8.0, 60.0, 700.0, 9000.0])
+def test_fma_certified_samples_agree_with_the_literal_index_arithmetic(vs, vps, extent):
+    """Samples generated the way the caster generates them (camera position + distance * direction,
+    distance accumulated in steps of the voxel size); a share of the rays is aimed so that samples hug
+    voxel faces / centres."""
+    rng = np.random.default_rng(int(vs * 1000) + 7 * vps + int(extent))
+    n = 600_000
+    vsd = float(F(vs))
+    ray_length = 8.0
+    P0 = (rng.random((n, 3)) * 2.0 - 1.0) * extent
+    direction = rng.normal(size=(n, 3))
+    direction /= np.linalg.norm(direction, axis=1)[:, None]
+    # axis-aligned and nearly axis-aligned rays from positions on / next to faces and centres
+    k = n // 3
+    direction[:k] = np.eye(3)[rng.integers(0, 3, k)] * rng.choice([-1.0, 1.0], k)[:, None]
+    direction[:k] += rng.normal(size=(k, 3)) * rng.choice([0.0, 1e-7, 1e-4], k)[:, None]
+    snap = np.round(P0[:k] / vsd * 2.0) / 2.0 * vsd
+    P0[:k] = snap + rng.integers(-40, 41, (k, 3)) * np.spacing(np.abs(snap).astype(F)).astype(np.float64) * 0.25
+    d = rng.integers(0, int(ray_length / vsd), n) * vsd + rng.integers(-3, 4, n) * 1e-15
+    pts = P0 + d[:, None] * direction  # fp64 multiply, then add: the reference's point
+    t_max = (extent + ray_length) * float(F(1.0 / vsd)) * 1.001 + 2.0
+    safe, g, below, lim = certified_fma(P0, direction, d, vs, vps, t_max)
+    g_state, g_centre, below_lit, in_range = literal(pts, vs, vps)
+    if lim > 0:
+        assert safe.any()
+    assert (~safe).any()
+    assert np.all(in_range[safe]), "certified sample with an artefact voxel index"
+    assert np.array_equal(g[safe], g_state[safe]), "block/voxel of getVoxelState differs"
+    assert np.array_equal(g[safe], g_centre[safe]), "voxel of getVoxelCenter differs"
+    assert np.array_equal(below[safe], below_lit[safe]), "interpolation octant differs"
+    if extent <= 60.0:
+        assert safe[k:].mean() > 0.97
+    # how much of the margin the worst observed disagreement uses (must stay well below 1)
+    bad = np.any((g != g_state) | (g != g_centre) | (below != below_lit), axis=1)
+    if bad.any():
+        vs_inv = float(F(1.0 / vsd))
+        y = pts * (2.0 * vs_inv)
+        dist = np.abs(y - np.round(y)).min(axis=1) / 2.0  # distance of T from 0, 1/2, 1 (voxel units)
+        assert dist[bad].max() < 0.5 * (0.5 - float(lim)) / 2.0 + 1e-12
+
+
 @pytest.mark.parametrize("vs,vps", [(0.1, 16), (0.2, 16), (0.05, 16), (0.2, 8), (0.1, 32), (0.37, 4)])
 @pytest.mark.parametrize("extent", [8.0, 60.0, 700.0, 9000.0])
 def test_certified_samples_agree_with_the_literal_index_arithmetic(vs, vps, extent):

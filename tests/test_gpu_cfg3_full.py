@@ -49,4 +49,10 @@ def test_cfg3_full_size_against_reference_goldens(cfg3, ek):
         for k in ("n_visible", "n_samples", "set_digest") + (("digest",) if digests else ()):
             assert np.array_equal(r[k], gold[f"{ek}/{k}"]), (ek, k, digests)
         assert np.allclose(r["gain"], gold[f"{ek}/gain"], rtol=1e-5, atol=0), (ek, digests)
+    # gains and counts only: the kernel chain (a3d_split.cu)
+    r = ctx.compute_gains(caster, ev, pos, quat, digests=False, set_digests=False)
+    assert ctx.last_cast_kernel == 3
+    for k in ("n_visible", "n_samples"):
+        assert np.array_equal(r[k], gold[f"{ek}/{k}"]), (ek, k, "chain")
+    assert np.allclose(r["gain"], gold[f"{ek}/gain"], rtol=1e-5, atol=0), (ek, "chain")
     assert int(gold[f"{ek}/n_samples"].max()) > 1_000_000   # full-size views: > 10^6 samples each

@@ -652,8 +652,17 @@ def test_voxel_weight_evaluator(capi, O, room02, ckind):
             assert np.array_equal(got[k], want[k]), k
         assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
         assert want["gain"].max() > 1.0
-        # without ordered digests the wavefront kernel evaluates it (partial sums per lane)
+        # without digests the kernel chain evaluates it (partial sums per ray part) ...
         got2 = ctx.compute_gains(caster, ev, pos, quat, digests=False, set_digests=False)
+        assert ctx.last_cast_kernel == 3
+        assert np.allclose(got2["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
+        # ... and bit-reproducibly so (fixed summation order)
+        again = ctx.compute_gains(caster, ev, pos, quat, digests=False, set_digests=False)
+        assert np.array_equal(got2["gain"], again["gain"])
+        # ... or the wavefront kernel (partial sums per lane)
+        ctx.set_option("cast_kernel", 2)
+        got2 = ctx.compute_gains(caster, ev, pos, quat, digests=False, set_digests=False)
+        ctx.set_option("cast_kernel", 0)
         assert ctx.last_cast_kernel == 2
         assert np.allclose(got2["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
         for k in ("n_samples", "n_visible"):
@@ -666,7 +675,7 @@ def test_voxel_weight_evaluator(capi, O, room02, ckind):
         assert np.array_equal(got["digest"], want["digest"])
         assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
         got2 = ctx.compute_gains(caster, ev, pos, quat, seg, 6, seg_origin=org, digests=False, set_digests=False)
-        assert ctx.last_cast_kernel == 2
+        assert ctx.last_cast_kernel == 3
         assert np.allclose(got2["gain"], want["gain"], rtol=GAIN_RTOL, atol=1e-12)
         assert np.array_equal(got2["n_visible"], want["n_visible"])
         lst, _, g1 = ctx.visible_voxels(caster, pos[:4], quat[:4], evaluator=ev, origin=org[0])

@@ -107,6 +107,18 @@ def one_case(rng, case, oracle=None, max_views=None):
         if not np.allclose(got["gain"], ref["gain"], rtol=1e-9, atol=1e-12):
             bad.append(f"gain width {width}")
     ctx.set_option("wave_cta", 0)
+    # the kernel chain (a3d_split.cu): gains and counts only; VoxelWeight gains are summed in another
+    # order than the scan-order kernel's
+    ctx.set_option("cast_kernel", 0)
+    got = ctx.compute_gains(caster, ev, *args, digests=False, set_digests=False)
+    if ctx.last_cast_kernel == 3:
+        for k in ("n_samples", "n_visible"):
+            if not np.array_equal(got[k], ref[k]):
+                bad.append(f"{k} chain")
+        if not np.allclose(got["gain"], ref["gain"], rtol=1e-9, atol=1e-12):
+            bad.append("gain chain")
+    elif vps in (8, 16, 32) and not edits:
+        bad.append(f"kernel chain not used (kernel {ctx.last_cast_kernel})")
     # ordered list of the first segment's views
     first = slice(0, 1) if len(args) == 2 else slice(0, int(np.sum(args[2] == 0)))
     ctx.set_option("cast_kernel", 1)
