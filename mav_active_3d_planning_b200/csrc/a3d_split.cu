@@ -157,9 +157,8 @@ __device__ __forceinline__ void part_begin(Part& p, S& sh, const MapView& m, con
   p.at = at;
 }
 
-// One sample of the lane's part (camera_model / ray caster inner loop + the evaluator's per-voxel
-// test).  Returns true when the part is finished (hit or end reached) and then leaves in p.d the
-// distance of the OCCUPIED sample that ended it, or -1.  Precondition: p.d < p.d_end.
+// One sample, up to the point where the list logic takes over: voxel state at the sample point,
+// identity / centre state of the voxel getVoxelCenter names, bounding-volume test.
 //
 // Index arithmetic: with T = pf / voxel_size per axis, floor(2T) names the voxel (g = floor(2T) >> 1)
 // and the half of it the point lies in (interpolation cell octant).  voxblox reaches the same through
@@ -171,38 +170,41 @@ __device__ __forceinline__ void part_begin(Part& p, S& sh, const MapView& m, con
 // is "certified": rint(z) = floor(2T), block and voxel indices are in range, getVoxelState's and
 // getVoxelCenter's voxels coincide, and it costs one load from the dense meta volume.  The others
 // (~0.3 %) and the MIXED cells form the exact fp64 point and are evaluated literally.
-template <int CASTER, int EVAL, class S>
-__device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, const S& sh, const ViewRec& vw,
-                                          const int bv_mode, const double step, const uint32_t* __restrict__ tab,
-                                          const SplitScratch& sc, Part& p, unsigned& inexact) {
-  constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
+struct Eval {
+  SampleInfo si;
+  int g[3];       // voxel coordinate (certified samples)
+  uint32_t word;  // meta word of that voxel (certified samples)
+  bool safe;      // certified
+  bool in_bv;
+  bool have_cc;
+  D3 cc;          // centre of the entry's voxel, formed only where something needs it
+};
+
+template <class S>
+__device__ __forceinline__ Eval sample_eval(const MapView& m, const EvalView& e, const S& sh, const ViewRec& vw,
+                                            const int bv_mode, const uint32_t* __restrict__ tab, const double d_this,
+                                            const float (&dz)[3], unsigned& inexact) {
   constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (z + kMagic) - kMagic = rint(z) for |z| < 2^22
   const CenterTables& ct = sh.ct;
   const BvGrid& bvg = sh.bvg;
-  const double d_this = p.d;
   const float df = __double2float_rn(d_this);
-  int g[3];
+  Eval ev;
   int oct = 0;
   bool safe = true;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float z = __fmaf_rn(df, p.dz[a], vw.z0[a]);
+    const float z = __fmaf_rn(df, dz[a], vw.z0[a]);
     const float s = __fadd_rn(z, kMagic);
     const float fr = __fsub_rn(z, __fsub_rn(s, kMagic));  // z - rint(z), exact, in [-1/2, 1/2]
     safe &= fabsf(fr) < vw.lim;
     const int h = __float_as_int(s) - 0x4B400000;  // rint(z) = floor(2T)
-    g[a] = h >> 1;
+    ev.g[a] = h >> 1;
     oct |= (~h & 1) << a;  // bit set: the point is below the voxel centre on this axis
   }
-  p.d = __dadd_rn(d_this, step);
-  const bool more = p.d < p.d_end;
-  p.rec += 1ull << kCntSampShift;
-
-  SampleInfo si;
-  D3 cc{0.0, 0.0, 0.0};  // centre of the entry's voxel, formed only where something needs it
-  bool have_cc = false;
-  bool in_bv = true;
-  uint32_t word = kWordNoBlock;
+  ev.cc = D3{0.0, 0.0, 0.0};
+  ev.have_cc = false;
+  ev.in_bv = true;
+  ev.word = kWordNoBlock;
   double pp[3];
   float pf[3];
   auto point = [&]() {  // the reference's sample point, double and float
@@ -227,36 +229,34 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
       ok &= (static_cast<unsigned>(vs) < static_cast<unsigned>(m.vps)) & (vs == vi);
       const float centre = __fadd_rn(origin, center_point(min(max(vs, 0), m.vps - 1), m.vs_f));
       oct_l |= (__fsub_rn(pf[a], centre) < 0.0f) ? (1 << a) : 0;
-      g[a] = bi * m.vps + vs;
+      ev.g[a] = bi * m.vps + vs;
     }
     oct = oct_l;
     safe = ok && vw.lim == vw.lim;  // (NaN margin: certification is off)
   }
-  auto centre = [&]() {
-    if (have_cc) return;
-    const int vmask = m.vps - 1;  // (certified samples only: the literal path delivers its centre)
-    cc.x = __dadd_rn(static_cast<double>(origin_point(g[0] >> m.vps_shift, m.bs_f)), ct.d[(g[0] & vmask) + 1]);
-    cc.y = __dadd_rn(static_cast<double>(origin_point(g[1] >> m.vps_shift, m.bs_f)), ct.d[(g[1] & vmask) + 1]);
-    cc.z = __dadd_rn(static_cast<double>(origin_point(g[2] >> m.vps_shift, m.bs_f)), ct.d[(g[2] & vmask) + 1]);
-    have_cc = true;
-  };
+  ev.safe = safe;
   if (safe) {
-    word = vol_word(m, g, tab);
+    const uint32_t word = vol_word(m, ev.g, tab);
+    ev.word = word;
     const int cls = (word >> (2 * oct)) & 3;
     static_assert(kCellUnknown == 0 && kCellFree == 1 && kCellOccupied == 2, "state = 2 - class");
-    si.st = 2 - cls;
-    si.cs = centre_state_from_word(word);
-    si.id = Ident{g[0], g[1], g[2]};
+    ev.si.st = 2 - cls;
+    ev.si.cs = centre_state_from_word(word);
+    ev.si.id = Ident{ev.g[0], ev.g[1], ev.g[2]};
     if (cls == kCellMixed) {
       point();
-      si.st = mixed_state(m, ct, pf[0], pf[1], pf[2], g[0], g[1], g[2], oct);
+      ev.si.st = mixed_state(m, ct, pf[0], pf[1], pf[2], ev.g[0], ev.g[1], ev.g[2], oct);
     }
     if (bv_mode == 2) {
-      centre();
-      in_bv = bv_contains(e, cc);  // simulated_sensor_evaluator.cpp:50-57
+      const int vmask = m.vps - 1;
+      ev.cc.x = __dadd_rn(static_cast<double>(origin_point(ev.g[0] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[0] & vmask) + 1]);
+      ev.cc.y = __dadd_rn(static_cast<double>(origin_point(ev.g[1] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[1] & vmask) + 1]);
+      ev.cc.z = __dadd_rn(static_cast<double>(origin_point(ev.g[2] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[2] & vmask) + 1]);
+      ev.have_cc = true;
+      ev.in_bv = bv_contains(e, ev.cc);  // simulated_sensor_evaluator.cpp:50-57
     } else if (bv_mode) {
-      in_bv = (g[0] >= bvg.lo[0]) & (g[0] <= bvg.hi[0]) & (g[1] >= bvg.lo[1]) & (g[1] <= bvg.hi[1]) &
-              (g[2] >= bvg.lo[2]) & (g[2] <= bvg.hi[2]);
+      ev.in_bv = (ev.g[0] >= bvg.lo[0]) & (ev.g[0] <= bvg.hi[0]) & (ev.g[1] >= bvg.lo[1]) & (ev.g[1] <= bvg.hi[1]) &
+                 (ev.g[2] >= bvg.lo[2]) & (ev.g[2] <= bvg.hi[2]);
     }
   } else {
     ExactOut out;
@@ -264,32 +264,43 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
     point();
     sample_exact(m, ct, pp[0], pp[1], pp[2], &out, &bad);
     inexact |= bad;
-    si = out.si;
-    cc = out.cc;
-    have_cc = true;
-    if (bv_mode) in_bv = bv_contains(e, cc);
+    ev.si = out.si;
+    ev.cc = out.cc;
+    ev.have_cc = true;
+    if (bv_mode) ev.in_bv = bv_contains(e, ev.cc);
   }
-  const bool emit = ITER || si.st != 0;
-  const bool keep = emit & in_bv &
-                    ((si.id.g0 != p.prev.g0) | (si.id.g1 != p.prev.g1) | (si.id.g2 != p.prev.g2));
-  const bool first = emit & (p.prev.g0 == kNoIdent);
-  if (emit) p.prev = si.id;
+  return ev;
+}
+
+// Fold category of a retained (or not) list entry and, for VoxelWeightEvaluator, its value.
+template <int EVAL, class S>
+__device__ __forceinline__ int entry_category(const MapView& m, const EvalView& e, const S& sh, const ViewRec& vw,
+                                              Eval& ev, const bool keep, double& wval) {
+  const CenterTables& ct = sh.ct;
+  const SampleInfo& si = ev.si;
+  auto centre = [&]() {
+    if (ev.have_cc) return;
+    const int vmask = m.vps - 1;  // (certified samples only: the literal path delivers its centre)
+    ev.cc.x = __dadd_rn(static_cast<double>(origin_point(ev.g[0] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[0] & vmask) + 1]);
+    ev.cc.y = __dadd_rn(static_cast<double>(origin_point(ev.g[1] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[1] & vmask) + 1]);
+    ev.cc.z = __dadd_rn(static_cast<double>(origin_point(ev.g[2] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[2] & vmask) + 1]);
+    ev.have_cc = true;
+  };
   int cat;
-  double wval = 0.0;
+  wval = 0.0;
   if (EVAL == A3D_EVAL_VOXEL_TYPE) {
     cat = si.cs & 3;  // retained entries are always inside the bounding volume
   } else if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
     cat = 1;
     if (keep && (si.cs & 3) != 1) {  // voxel_weight_evaluator.cpp:43-83 (free voxels score nothing)
       int hint = -1;
-      if (safe && (si.cs & 3) == 2 && e.frontier_voxel_weight > 0.0) hint = is_frontier_from_word(m, e, word);
+      if (ev.safe && (si.cs & 3) == 2 && e.frontier_voxel_weight > 0.0) hint = is_frontier_from_word(m, e, ev.word);
       double w = 0.0;
       if ((si.cs & 3) == 0 || (hint < 0 && e.frontier_voxel_weight > 0.0)) centre();
-      if ((si.cs & 3) == 0) w = voxel_weight(m, cc);
-      if (safe && hint < 0 && (si.cs & 3) == 2 && e.frontier_voxel_weight > 0.0)
-        hint = is_frontier_by_meta(m, ct, e, cc, g[0], g[1], g[2]);
-      wval = voxel_weight_value(m, ct, e, cc, si.cs, w, D3{vw.org[0], vw.org[1], vw.org[2]}, hint);
-      if (first) p.first_val = wval; else p.wsum += wval;
+      if ((si.cs & 3) == 0) w = voxel_weight(m, ev.cc);
+      if (ev.safe && hint < 0 && (si.cs & 3) == 2 && e.frontier_voxel_weight > 0.0)
+        hint = is_frontier_by_meta(m, ct, e, ev.cc, ev.g[0], ev.g[1], ev.g[2]);
+      wval = voxel_weight_value(m, ct, e, ev.cc, si.cs, w, D3{vw.org[0], vw.org[1], vw.org[2]}, hint);
     }
   } else {
     cat = 1;
@@ -297,14 +308,41 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
       if (EVAL == A3D_EVAL_NAIVE) {
         cat = 0;
       } else {
-        int hint = safe ? is_frontier_from_word(m, e, word) : -1;
+        int hint = ev.safe ? is_frontier_from_word(m, e, ev.word) : -1;
         if (hint < 0) {
           centre();
-          if (safe) hint = is_frontier_by_meta(m, ct, e, cc, g[0], g[1], g[2]);
+          if (ev.safe) hint = is_frontier_by_meta(m, ct, e, ev.cc, ev.g[0], ev.g[1], ev.g[2]);
         }
-        if (hint >= 0 ? hint != 0 : is_frontier_voxel(m, ct, e, cc)) cat = 0;
+        if (hint >= 0 ? hint != 0 : is_frontier_voxel(m, ct, e, ev.cc)) cat = 0;
       }
     }
+  }
+  return cat;
+}
+
+// One sample of the lane's part (camera_model / ray caster inner loop + the evaluator's per-voxel
+// test).  Returns true when the part is finished (hit or end reached) and then leaves in p.d the
+// distance of the OCCUPIED sample that ended it, or -1.  Precondition: p.d < p.d_end.
+template <int CASTER, int EVAL, class S>
+__device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, const S& sh, const ViewRec& vw,
+                                          const int bv_mode, const double step, const uint32_t* __restrict__ tab,
+                                          const SplitScratch& sc, Part& p, unsigned& inexact) {
+  constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
+  const double d_this = p.d;
+  Eval ev = sample_eval(m, e, sh, vw, bv_mode, tab, d_this, p.dz, inexact);
+  p.d = __dadd_rn(d_this, step);
+  const bool more = p.d < p.d_end;
+  p.rec += 1ull << kCntSampShift;
+  const SampleInfo& si = ev.si;
+  const bool emit = ITER || si.st != 0;
+  const bool keep = emit & ev.in_bv &
+                    ((si.id.g0 != p.prev.g0) | (si.id.g1 != p.prev.g1) | (si.id.g2 != p.prev.g2));
+  const bool first = emit & (p.prev.g0 == kNoIdent);
+  if (emit) p.prev = si.id;
+  double wval;
+  const int cat = entry_category<EVAL>(m, e, sh, vw, ev, keep, wval);
+  if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+    if (first) p.first_val = wval; else p.wsum += wval;
   }
   p.rec += static_cast<unsigned long long>(keep) << (kCntBits * cat);
   if (first) {
@@ -320,6 +358,103 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
   }
   if (!more) p.d = -1.0;
   return !more;
+}
+
+// A whole marking part by the warp: lane k evaluates sample k of the ray (accumulated distances from
+// CasterView::dseq, as k_cast_gain does), the first OCCUPIED sample ends it.  Used on the
+// anti-diagonal chain, where the latency of a part — not lane occupancy — is what counts.  Returns the
+// hit distance (-1: none).  All lanes must call; `at` = the part's record.
+template <int EVAL, class S>
+__device__ __forceinline__ double part_by_warp(const MapView& m, const CasterView& c, const EvalView& e, S& sh,
+                                               const ViewRec& vw, const int bv_mode, const uint32_t* __restrict__ tab,
+                                               const SplitScratch& sc, const int r, const int s0, const size_t at,
+                                               unsigned& inexact) {
+  const unsigned lane = threadIdx.x & 31u;
+  const int n = c.n_sections;
+  const int n_s = c.seg_end[s0 * n + (n - 2)];  // samples before c_split_distances_[n-1]
+  const double* const dseq = c.dseq + static_cast<size_t>(s0) * c.kmax;
+  // every lane holds the ray's direction (the literal paths read it per thread)
+  const Q4 q{vw.q[0], vw.q[1], vw.q[2], vw.q[3]};
+  const D3 dir = rotate(q, D3{c.cam_dirs[3 * r], c.cam_dirs[3 * r + 1], c.cam_dirs[3 * r + 2]});
+  sh.dir[0][threadIdx.x] = dir.x;
+  sh.dir[1][threadIdx.x] = dir.y;
+  sh.dir[2][threadIdx.x] = dir.z;
+  const double k2 = 2.0 * static_cast<double>(m.vs_inv_f);
+  const float dz[3] = {__double2float_rn(__dmul_rn(dir.x, k2)), __double2float_rn(__dmul_rn(dir.y, k2)),
+                       __double2float_rn(__dmul_rn(dir.z, k2))};
+  unsigned long long rec = 0;
+  double wsum = 0.0, first_val = 0.0, hit_d = -1.0;
+  Ident carry{kNoIdent, 0, 0};  // last raw entry of the previous chunk of 32 samples
+  Ident last{kNoIdent, 0, 0};
+  for (int k0 = 0; k0 < n_s; k0 += 32) {
+    const int k = k0 + static_cast<int>(lane);
+    const bool in = k < n_s;
+    const double d = in ? __ldg(dseq + k) : 0.0;
+    Eval ev;
+    ev.si.st = 1;
+    ev.si.cs = 0;
+    ev.si.id = Ident{0, 0, 0};
+    ev.in_bv = false;
+    if (in) ev = sample_eval(m, e, sh, vw, bv_mode, tab, d, dz, inexact);
+    const unsigned occ = __ballot_sync(kFull, in && ev.si.st == 0);
+    const int n_valid = occ ? __ffs(occ) : min(32, n_s - k0);  // the hit sample is part of the list
+    const bool valid = static_cast<int>(lane) < n_valid;
+    // previous raw entry: the lane below (every sample of an iterative ray is emitted)
+    Ident prev;
+    prev.g0 = __shfl_up_sync(kFull, ev.si.id.g0, 1);
+    prev.g1 = __shfl_up_sync(kFull, ev.si.id.g1, 1);
+    prev.g2 = __shfl_up_sync(kFull, ev.si.id.g2, 1);
+    if (lane == 0) prev = carry;
+    const bool keep = valid & ev.in_bv &
+                      ((ev.si.id.g0 != prev.g0) | (ev.si.id.g1 != prev.g1) | (ev.si.id.g2 != prev.g2));
+    double wval = 0.0;
+    int cat = 3;
+    if (valid) cat = entry_category<EVAL>(m, e, sh, vw, ev, keep, wval);
+    const bool first = k == 0;
+    rec += static_cast<unsigned long long>(n_valid) << kCntSampShift;
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      rec += static_cast<unsigned long long>(__popc(__ballot_sync(kFull, keep && cat == cc))) << (kCntBits * cc);
+    if (first) {
+      unsigned bad = 0;
+      __stcs(&sc.first_key[at], pack_key(ev.si.id, &bad));
+      inexact |= bad;
+    }
+    // lane 0 of the first chunk describes the first entry to everybody
+    if (k0 == 0) {
+      const int keep0 = __shfl_sync(kFull, static_cast<int>(keep), 0), cat0 = __shfl_sync(kFull, cat, 0);
+      rec |= kRecEmitted | (keep0 ? kRecKept : 0ull) | (static_cast<unsigned long long>(keep0 ? cat0 : 3) << kRecCatShift);
+    }
+    if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+      double w = (keep && !first) ? wval : 0.0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(kFull, w, off);
+      wsum += w;
+      if (k0 == 0) first_val = __shfl_sync(kFull, keep ? wval : 0.0, 0);
+    }
+    const int tail = n_valid - 1;
+    last.g0 = __shfl_sync(kFull, ev.si.id.g0, tail);
+    last.g1 = __shfl_sync(kFull, ev.si.id.g1, tail);
+    last.g2 = __shfl_sync(kFull, ev.si.id.g2, tail);
+    carry = last;
+    if (occ) {
+      hit_d = __shfl_sync(kFull, d, tail);
+      break;
+    }
+  }
+  if (lane == 0) {
+    if (last.g0 != kNoIdent) {
+      unsigned bad = 0;
+      __stcs(&sc.last_key[at], pack_key(last, &bad));
+      inexact |= bad;
+    }
+    __stcs(&sc.rec[at], rec);
+    if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+      __stcs(&sc.wsum[at], wsum);
+      __stcs(&sc.first_val[at], first_val);
+    }
+  }
+  return hit_d;
 }
 
 template <int EVAL>
@@ -395,41 +530,52 @@ __device__ __forceinline__ void load_view(S& sh, const SplitScratch& sc, int vie
 }
 
 // ---- k_split_mark ------------------------------------------------------------------------------------
-// One warp per view.  Dynamic shared memory: per warp diag_max hit distances + diag_max list items,
-// then the volume offset tables.
+// One warp per view, ray table in global memory (any camera size).  Dynamic shared memory: per warp
+// diag_max hit distances + diag_max list items, then the volume offset tables.
 template <int EVAL>
 __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
     k_split_mark(const MapView m, const CasterView c, const EvalView e, int n_views, const SplitScratch sc) {
-  constexpr int CASTER = A3D_CASTER_ITERATIVE;
+  constexpr bool SMEM_TABLE = false;
+  constexpr int kWarps = kSplitWarps;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int n_rays = c.n_rays, n = c.n_sections, n_diag = c.res_x + c.res_y - 1;
   __shared__ CtaShared sh;
   extern __shared__ double s_dyn[];
   double* const s_hit = s_dyn + static_cast<size_t>(warp) * c.diag_max;
-  unsigned* const s_list_all = reinterpret_cast<unsigned*>(s_dyn + static_cast<size_t>(kSplitWarps) * c.diag_max);
+  unsigned* const s_list_all = reinterpret_cast<unsigned*>(s_dyn + static_cast<size_t>(kWarps) * c.diag_max);
   unsigned* const s_list = s_list_all + static_cast<size_t>(warp) * c.diag_max;
-  uint32_t* const s_tab = s_list_all + static_cast<size_t>(kSplitWarps) * c.diag_max;
+  uint32_t* const s_tab = s_list_all + static_cast<size_t>(kWarps) * c.diag_max;
   const uint32_t tab_n = vol_tab_entries(m);
+  uint32_t* const s_table = nullptr;
   const uint32_t* const tab = tab_n ? s_tab : nullptr;
   cta_prologue(m, e, sh, s_tab, tab_n);
   const int bv_mode = sh.bvg.mode;
   const double step = c.ray_step;
   const double d_mark_end = c.split[n - 1];
 
-  for (int view = blockIdx.x * kSplitWarps + warp; view < n_views; view += gridDim.x * kSplitWarps) {
+  for (int view = blockIdx.x * kWarps + warp; view < n_views; view += gridDim.x * kWarps) {
     load_view(sh, sc, view, warp, lane);
     const ViewRec& vw = sh.vw[warp];
-    uint32_t* const table = sc.table + static_cast<size_t>(view) * sc.stride;
+    uint32_t* const g_table = sc.table + static_cast<size_t>(view) * sc.stride;
     uint8_t* const start_s = sc.start_s + static_cast<size_t>(view) * sc.stride;
     const size_t rec0 = static_cast<size_t>(view) * 2 * sc.stride;  // marking parts: part 0
     for (int r = lane; r < n_rays; r += 32) {
-      table[r] = 0u;
+      if (SMEM_TABLE) s_table[r] = 0u; else g_table[r] = 0u;
       start_s[r] = 0xFF;
       __stcs(&sc.rec[rec0 + r], 0ull);
     }
-    __threadfence_block();
+    if (!SMEM_TABLE) __threadfence_block();
     __syncwarp();
+    // table access: shared memory, or L2 (atomics are performed there, reads bypass L1)
+    auto t_read = [&](int r) -> uint32_t { return SMEM_TABLE ? s_table[r] : __ldcg(&g_table[r]); };
+    auto t_max = [&](int r, unsigned v) {
+      if (SMEM_TABLE) atomicMax(&s_table[r], v); else atomicMax(&g_table[r], v);
+    };
+    auto t_fence = [&]() {
+      if (!SMEM_TABLE) __threadfence_block();
+      __syncwarp();
+    };
     unsigned inexact = 0;
     uint32_t* const dlist = sc.dlist + static_cast<size_t>(view) * sc.stride;
     int n_def = 0;
@@ -448,7 +594,7 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
         int s = -1, r = 0;
         if (i <= i_hi) {
           r = i * c.res_y + (diag - i);
-          s = static_cast<int>(static_cast<int8_t>(__ldcg(&table[r]) & 0xFFu));
+          s = static_cast<int>(static_cast<int8_t>(t_read(r) & 0xFFu));
         }
         const bool deferred = s == n - 2;
         const bool marking = s >= 0 && s < n - 2;
@@ -461,39 +607,29 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
           const int ri = i, rj = diag - i;
           const unsigned ent = ((static_cast<unsigned>(r) + 1u) << 8) | static_cast<uint8_t>(n - 1);
           const bool in_x = ri + 1 < c.res_x, in_y = rj + 1 < c.res_y;
-          atomicMax(&table[r], ent);
-          if (in_y) atomicMax(&table[r + 1], ent);
-          if (in_x) atomicMax(&table[r + c.res_y], ent);
-          if (in_x && in_y) atomicMax(&table[r + c.res_y + 1], ent);
+          t_max(r, ent);
+          if (in_y) t_max(r + 1, ent);
+          if (in_x) t_max(r + c.res_y, ent);
+          if (in_x && in_y) t_max(r + c.res_y + 1, ent);
         }
         n_def += __popc(dm);
         any_def |= dm;
       }
       __syncwarp();
       if (n_mark == 0) {
-        if (any_def) __threadfence_block();
+        if (any_def) t_fence();
         any_def = 0;
-        __syncwarp();
         continue;
       }
       any_def = 0;
-      // cast them, one per lane
-      for (int base = 0; base < n_mark; base += 32) {
-        const int qi = base + static_cast<int>(lane);
-        bool active = qi < n_mark;
-        Part p;
-        if (active) {
-          const unsigned it = s_list[qi];
-          const int r = static_cast<int>(it >> 8), ms = static_cast<int>(it & 0xFF);
-          part_begin(p, sh, m, c, vw, r, c.split[ms], d_mark_end, rec0 + r);
+      // cast them, one after the other, each by the whole warp
+      for (int qi = 0; qi < n_mark; ++qi) {
+        const unsigned it = s_list[qi];
+        const int r = static_cast<int>(it >> 8), ms = static_cast<int>(it & 0xFF);
+        const double hd = part_by_warp<EVAL>(m, c, e, sh, vw, bv_mode, tab, sc, r, ms, rec0 + r, inexact);
+        if (lane == 0) {
+          s_hit[qi] = hd;
           start_s[r] = static_cast<uint8_t>(ms);  // read by k_split_leaf
-        }
-        while (__any_sync(kFull, active)) {
-          if (active && part_step<CASTER, EVAL>(m, e, sh, vw, bv_mode, step, tab, sc, p, inexact)) {
-            part_end<EVAL>(sc, p, inexact);
-            s_hit[qi] = p.d;
-            active = false;
-          }
         }
       }
       __syncwarp();
@@ -519,10 +655,10 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
           // start section n-2 (most marking rays): the 2x2 square gets one value
           const unsigned ent = wr | static_cast<uint8_t>(hit ? -1 : n - 1);
           const bool in_x = ri + 1 < c.res_x, in_y = rj + 1 < c.res_y;
-          atomicMax(&table[rr], ent);
-          if (in_y) atomicMax(&table[rr + 1], ent);
-          if (in_x) atomicMax(&table[rr + c.res_y], ent);
-          if (in_x && in_y) atomicMax(&table[rr + c.res_y + 1], ent);
+          t_max(rr, ent);
+          if (in_y) t_max(rr + 1, ent);
+          if (in_x) t_max(rr + c.res_y, ent);
+          if (in_x && in_y) t_max(rr + c.res_y + 1, ent);
         }
         // larger squares: the warp shares the cells of one ray at a time
         unsigned big = __ballot_sync(kFull, valid && w0 > 2);
@@ -540,15 +676,160 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
             const int tmax = mx == 0 ? n - 1 : n - 2 - (31 - __clz(mx));
             const int t = min(tmax, b_tl);
             const int val = (t == b_sh) ? -1 : t + 1;
-            atomicMax(&table[(b_ri + dx) * c.res_y + b_rj + dy], b_wr | static_cast<uint8_t>(val));
+            t_max((b_ri + dx) * c.res_y + b_rj + dy, b_wr | static_cast<uint8_t>(val));
           }
         }
       }
-      __threadfence_block();
+      t_fence();
+    }
+    if (SMEM_TABLE) {
       __syncwarp();
+      for (int r = lane; r < n_rays; r += 32) g_table[r] = s_table[r];
     }
     if (lane == 0) sc.dcount[view] = static_cast<unsigned>(n_def);
     if (__any_sync(kFull, inexact != 0) && lane == 0) sc.view_flags[view] = 1u;
+  }
+}
+
+// ---- k_split_mark_cta --------------------------------------------------------------------------------
+// The same walk with one CTA (4 warps) per view and the ray table in shared memory, for cameras whose
+// table fits: every step of the anti-diagonal chain is a shared-memory access instead of an L2 round
+// trip, and the marking parts of one anti-diagonal are cast by different warps at the same time.
+// What remains per anti-diagonal is one part's latency.  Dynamic shared memory: diag_max hit distances,
+// diag_max list items, the volume offset tables, n_rays table entries.
+template <int EVAL>
+__global__ void __launch_bounds__(kSplitThreads, 6)
+    k_split_mark_cta(const MapView m, const CasterView c, const EvalView e, int n_views, const SplitScratch sc) {
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int n_rays = c.n_rays, n = c.n_sections, n_diag = c.res_x + c.res_y - 1;
+  __shared__ CtaShared sh;
+  __shared__ int s_n_mark, s_n_def;
+  __shared__ unsigned s_inexact;
+  extern __shared__ double s_dyn[];
+  double* const s_hit = s_dyn;
+  unsigned* const s_list = reinterpret_cast<unsigned*>(s_dyn + c.diag_max);
+  uint32_t* const s_tab = s_list + c.diag_max;
+  const uint32_t tab_n = vol_tab_entries(m);
+  const uint32_t* const tab = tab_n ? s_tab : nullptr;
+  uint32_t* const s_table = s_tab + tab_n;
+  cta_prologue(m, e, sh, s_tab, tab_n);
+  const int bv_mode = sh.bvg.mode;
+
+  for (int view = blockIdx.x; view < n_views; view += gridDim.x) {
+    __syncthreads();
+    load_view(sh, sc, view, warp, lane);  // (every warp keeps its own copy)
+    const ViewRec& vw = sh.vw[warp];
+    uint8_t* const start_s = sc.start_s + static_cast<size_t>(view) * sc.stride;
+    uint32_t* const dlist = sc.dlist + static_cast<size_t>(view) * sc.stride;
+    const size_t rec0 = static_cast<size_t>(view) * 2 * sc.stride;  // marking parts: part 0
+    for (int r = threadIdx.x; r < n_rays; r += kSplitThreads) {
+      s_table[r] = 0u;
+      start_s[r] = 0xFF;
+      __stcs(&sc.rec[rec0 + r], 0ull);
+    }
+    if (threadIdx.x == 0) {
+      s_n_def = 0;
+      s_inexact = 0;
+    }
+    unsigned inexact = 0;
+
+    for (int diag = 0; diag < n_diag; ++diag) {
+      if (threadIdx.x == 0) s_n_mark = 0;
+      __syncthreads();  // table final up to this diagonal; counters reset
+      // The rays of this diagonal that start before the last section (see k_split_mark): section n-2
+      // starts get their provisional mark and go to the list of k_split_mark2, earlier starts are cast
+      // here.  Neither list needs an order (marks commute, records are per ray).
+      const int i_lo = max(0, diag - (c.res_y - 1)), i_hi = min(c.res_x - 1, diag);
+      for (int base = i_lo + 32 * static_cast<int>(warp); base <= i_hi; base += kSplitThreads) {
+        const int i = base + static_cast<int>(lane);
+        int s = -1, r = 0;
+        if (i <= i_hi) {
+          r = i * c.res_y + (diag - i);
+          s = static_cast<int>(static_cast<int8_t>(s_table[r] & 0xFFu));
+        }
+        const bool deferred = s == n - 2;
+        const bool marking = s >= 0 && s < n - 2;
+        const unsigned mm = __ballot_sync(kFull, marking), dm = __ballot_sync(kFull, deferred);
+        int m_at = 0, d_at = 0;
+        if (lane == 0) {
+          if (mm) m_at = atomicAdd(&s_n_mark, __popc(mm));
+          if (dm) d_at = atomicAdd(&s_n_def, __popc(dm));
+        }
+        m_at = __shfl_sync(kFull, m_at, 0);
+        d_at = __shfl_sync(kFull, d_at, 0);
+        if (marking) s_list[m_at + __popc(mm & lt_mask)] = (static_cast<unsigned>(r) << 8) | s;
+        if (deferred) {
+          dlist[d_at + __popc(dm & lt_mask)] = static_cast<uint32_t>(r);
+          start_s[r] = static_cast<uint8_t>(n - 2);
+          const int ri = i, rj = diag - i;
+          const unsigned ent = ((static_cast<unsigned>(r) + 1u) << 8) | static_cast<uint8_t>(n - 1);
+          const bool in_x = ri + 1 < c.res_x, in_y = rj + 1 < c.res_y;
+          atomicMax(&s_table[r], ent);
+          if (in_y) atomicMax(&s_table[r + 1], ent);
+          if (in_x) atomicMax(&s_table[r + c.res_y], ent);
+          if (in_x && in_y) atomicMax(&s_table[r + c.res_y + 1], ent);
+        }
+      }
+      __syncthreads();
+      const int n_mark = s_n_mark;
+      if (n_mark == 0) continue;
+      // cast them: each warp takes every fourth one
+      for (int qi = static_cast<int>(warp); qi < n_mark; qi += kSplitWarps) {
+        const unsigned it = s_list[qi];
+        const int r = static_cast<int>(it >> 8), ms = static_cast<int>(it & 0xFF);
+        const double hd = part_by_warp<EVAL>(m, c, e, sh, vw, bv_mode, tab, sc, r, ms, rec0 + r, inexact);
+        if (lane == 0) {
+          s_hit[qi] = hd;
+          start_s[r] = static_cast<uint8_t>(ms);  // read by k_split_leaf
+        }
+      }
+      __syncthreads();
+      // markNeighboringRays of every marking ray of the diagonal (see k_split_mark)
+      for (int base = 32 * static_cast<int>(warp); base < n_mark; base += kSplitThreads) {
+        const int qi = base + static_cast<int>(lane);
+        const bool valid = qi < n_mark;
+        const unsigned it = valid ? s_list[qi] : 0u;
+        const int rr = static_cast<int>(it >> 8), ss = static_cast<int>(it & 0xFF);
+        const double hd = valid ? s_hit[qi] : -1.0;
+        const bool hit = hd >= 0.0;
+        int seg_h = ss;
+        if (hit) {
+          while (!(hd < c.split[seg_h + 1])) ++seg_h;
+        }
+        const int t_last = hit ? seg_h : n - 2;
+        const int w0 = 1 << (n - 1 - ss);
+        const int ri = rr / c.res_y, rj = rr - ri * c.res_y;
+        const unsigned wr = (static_cast<unsigned>(rr) + 1u) << 8;
+        unsigned big = __ballot_sync(kFull, valid);
+        while (big) {
+          const int src = __ffs(big) - 1;
+          big &= big - 1;
+          const int b_ri = __shfl_sync(kFull, ri, src), b_rj = __shfl_sync(kFull, rj, src);
+          const int b_w0 = __shfl_sync(kFull, w0, src), b_tl = __shfl_sync(kFull, t_last, src);
+          const int b_sh = __shfl_sync(kFull, hit ? seg_h : -1, src);
+          const unsigned b_wr = __shfl_sync(kFull, wr, src);
+          const int nx = min(b_w0, c.res_x - b_ri), ny = min(b_w0, c.res_y - b_rj);
+          for (int cell = lane; cell < nx * ny; cell += 32) {
+            const int dx = cell / ny, dy = cell - dx * ny;
+            const int mx = max(dx, dy);
+            const int tmax = mx == 0 ? n - 1 : n - 2 - (31 - __clz(mx));
+            const int t = min(tmax, b_tl);
+            const int val = (t == b_sh) ? -1 : t + 1;
+            atomicMax(&s_table[(b_ri + dx) * c.res_y + b_rj + dy], b_wr | static_cast<uint8_t>(val));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t* const g_table = sc.table + static_cast<size_t>(view) * sc.stride;
+    for (int r = threadIdx.x; r < n_rays; r += kSplitThreads) g_table[r] = s_table[r];
+    if (__any_sync(kFull, inexact != 0) && lane == 0) atomicOr(&s_inexact, 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sc.dcount[view] = static_cast<unsigned>(s_n_def);
+      sc.view_flags[view] = s_inexact;
+    }
   }
 }
 
@@ -651,7 +932,7 @@ __global__ void __launch_bounds__(kSplitThreads)
     const int vl = view - view0;
     if (lane == 0 && sc.view_flags[vl]) inexact = 1;
     const size_t rec0 = static_cast<size_t>(vl) * sc.parts * sc.stride;
-    constexpr int kAhead = 4;  // chunks whose records are requested before the first is looked at
+    constexpr int kAhead = 8;  // chunks whose records are requested before the first is looked at
     for (int base0 = 0; base0 < n_rays; base0 += kAhead * per_it) {
       unsigned long long recs[kAhead];
       uint64_t fks[kAhead], lks[kAhead];
@@ -740,9 +1021,19 @@ void launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, cons
   k_split_views<<<(n_seg + 127) / 128, 128, 0, st>>>(m, c, b, seg0, n_seg, view0, sc);
   const size_t tab_bytes = static_cast<size_t>(vol_tab_entries(m)) * 4;
   if (CASTER == A3D_CASTER_ITERATIVE && c.n_sections > 1) {
-    const size_t smem = static_cast<size_t>(kSplitWarps) * c.diag_max * 12 + tab_bytes;
-    const int grid = std::max(1, std::min((n_views + kSplitWarps - 1) / kSplitWarps, sm_count * A3D_SPLIT_MARK_BLOCKS));
-    k_split_mark<EVAL><<<grid, kSplitThreads, smem, st>>>(m, c, e, n_views, sc);
+    // the ray table in shared memory when it fits next to the other tables (at most 8 views per SM)
+    const size_t smem_1 = static_cast<size_t>(c.diag_max) * 12 + tab_bytes + static_cast<size_t>(c.n_rays) * 4;
+    // ... and the batch is small enough for latency to matter more than the number of resident views
+    // (cfg2: one view 0.89 -> 0.37 ms, 148 views 1.23 -> 0.69 ms; beyond ~2000 views the one-warp-per-view
+    // kernel wins: 4096 views 1.7 vs 2.6 ms)
+    if (smem_1 <= 40 * 1024 && n_views <= sm_count * 12) {
+      k_split_mark_cta<EVAL><<<std::max(1, std::min(n_views, sm_count * 8)), kSplitThreads, smem_1, st>>>(m, c, e, n_views, sc);
+    } else {
+      const size_t smem = static_cast<size_t>(kSplitWarps) * c.diag_max * 12 + tab_bytes;
+      const int grid =
+          std::max(1, std::min((n_views + kSplitWarps - 1) / kSplitWarps, sm_count * A3D_SPLIT_MARK_BLOCKS));
+      k_split_mark<EVAL><<<grid, kSplitThreads, smem, st>>>(m, c, e, n_views, sc);
+    }
   } else if (CASTER == A3D_CASTER_ITERATIVE) {
     // a single section: no marking parts; every ray is cast whole by k_split_leaf
     cudaMemsetAsync(sc.table, 0, static_cast<size_t>(n_views) * sc.stride * 4, st);
