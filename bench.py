@@ -274,6 +274,7 @@ def run_ours(args):
         ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         kernel_ms = []
+        stage_ms = []
         barrier()
         for i in range(args.steps):
             flush.fill_(i & 0xFF)  # evict L2 between timed iterations (outside the events)
@@ -283,6 +284,7 @@ def run_ours(args):
             kernel_ms.append(None)
             ev_b[i].synchronize()
             kernel_ms[-1] = ctx.last_kernel_ms
+            stage_ms.append(ctx.last_stage_ms)
         barrier()
         launches = ctx.kernel_launches - launches0
         total_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b))
@@ -334,6 +336,11 @@ def run_ours(args):
     alg_bytes = 32 * S + 32 * V + (56 + 8) * n_seg       # SURVEY.md §8(d), VoxelType fold
     lookups = 8 * S + 8 * V
     k_ms = float(np.mean(kernel_ms))
+    chain = ctx.last_cast_kernel == 3
+    stages = {}
+    if chain and stage_ms and all(len(x) == 5 for x in stage_ms):
+        names = ["k_split_views", "k_split_mark", "k_split_leaf<deferred marking parts>", "k_split_leaf", "k_split_fix"]
+        stages = {n: float(np.mean([x[k] for x in stage_ms])) for k, n in enumerate(names)}
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     steps_views = n_global * args.steps
@@ -366,10 +373,15 @@ def run_ours(args):
         "kernel_ms": k_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "traffic_source": "dram__bytes_read+write of one ncu --set full capture of this kernel on "
-                                       "this workload at 4096 views (profiles/traffic.json), not measured in this run",
-                     "kernel": ("k_cast_wave" if ctx.last_cast_kernel == 2 else "k_cast_gain") +
+                     "traffic_source": "sum of dram__bytes_read+write over the kernels of one cast in an ncu --set full "
+                                       "capture of this workload at 4096 views (profiles/traffic.json), not measured "
+                                       "in this run",
+                     # one "launch" = the cast of the batch: the kernel chain of a3d_split.cu (its kernels'
+                     # shares below), or the single wavefront / scan-order kernel
+                     "kernel": ("kernel chain k_split_views+mark+leaf<deferred>+leaf+fix" if chain else
+                                "k_cast_wave" if ctx.last_cast_kernel == 2 else "k_cast_gain") +
                      "<Iterative,VoxelType>",
+                     "kernel_ms_by_stage": stages,
                      "algorithmic_bytes_per_launch": alg_bytes},
         "e2e": {"value": steps_views / e2e_s, "unit": "views/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},

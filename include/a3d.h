@@ -122,6 +122,11 @@ void* a3d_ctx_stream(a3d_ctx* ctx);
 /* Device time in ms of the ray-cast/gain kernel of the most recent a3d_compute_gains*() call
    (CUDA events on the context stream); < 0 if none. */
 float a3d_last_kernel_ms(a3d_ctx* ctx);
+/* When that call ran the kernel chain (a3d_last_cast_kernel() == 3): device time of each of its kernels
+   (last chunk of the batch), in launch order — IterativeRayCaster: views, mark, section n-2 marking
+   parts, leaf parts, fix-up; SimpleRayCaster: views, rays, fix-up.  Returns how many were written
+   (<= cap; 0: not available), < 0 on a bad argument. */
+int a3d_last_stage_ms(a3d_ctx* ctx, float* out_ms, int cap);
 /* Number of kernels this context has launched so far. */
 uint64_t a3d_kernel_launches(a3d_ctx* ctx);
 /* Tuning / test knobs.  "cast_kernel": 0 = automatic (default), 1 = always the scan-order kernel

@@ -30,7 +30,7 @@ _EVAL_KINDS = {"VoxelTypeEvaluator": EVAL_VOXEL_TYPE, "NaiveEvaluator": EVAL_NAI
 
 # every symbol include/a3d.h declares
 EXPORTS = [
-    "a3d_ctx_create", "a3d_ctx_destroy", "a3d_last_error", "a3d_ctx_stream", "a3d_last_kernel_ms",
+    "a3d_ctx_create", "a3d_ctx_destroy", "a3d_last_error", "a3d_ctx_stream", "a3d_last_kernel_ms", "a3d_last_stage_ms",
     "a3d_kernel_launches", "a3d_set_option", "a3d_last_cast_kernel", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev",
     "a3d_map_remove_blocks", "a3d_map_clear", "a3d_map_num_blocks", "a3d_map_voxel_size",
     "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
@@ -150,6 +150,8 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_ctx_stream.restype = vp
     lib.a3d_last_kernel_ms.argtypes = [vp]
     lib.a3d_last_kernel_ms.restype = C.c_float
+    lib.a3d_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    lib.a3d_last_stage_ms.restype = C.c_int
     lib.a3d_kernel_launches.argtypes = [vp]
     lib.a3d_kernel_launches.restype = u64
     lib.a3d_map_config.argtypes = [vp, C.c_float, C.c_int]
@@ -370,6 +372,14 @@ class Context:
     @property
     def last_kernel_ms(self) -> float:
         return float(self.lib.a3d_last_kernel_ms(self.h))
+
+    @property
+    def last_stage_ms(self):
+        """Device time of each kernel of the kernel chain in the last compute_gains call ([] if another
+        kernel ran): views, mark, deferred marking parts, leaf parts, fix-up (iterative caster)."""
+        buf = (C.c_float * 8)()
+        n = int(self.lib.a3d_last_stage_ms(self.h, buf, 8))
+        return [float(buf[k]) for k in range(max(n, 0))]
 
     @property
     def kernel_launches(self) -> int:

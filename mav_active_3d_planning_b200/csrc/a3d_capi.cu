@@ -113,6 +113,8 @@ struct a3d_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_stage[6] = {};  // kernel chain (a3d_split.cu): after each of its kernels, last chunk
+  int n_stage = 0;
   bool timed = false;
   uint64_t launches = 0;
   mutable std::string err;
@@ -814,8 +816,10 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
         v1 = h_first[seg_end];
       }
       CK(ctx->sc_wave.reserve(static_cast<size_t>(v1 - v0) * per_view + 256));
-      launch_cast_split(ctx->stream, ctx->view(), c->view, ev_view, b, seg, seg_end - seg, v0, v1 - v0,
-                        ctx->sc_wave.p, ctx->sc_inexact.p, ctx->sm_count);
+      for (auto& evs : ctx->ev_stage)
+        if (!evs) CK(cudaEventCreate(&evs));
+      ctx->n_stage = launch_cast_split(ctx->stream, ctx->view(), c->view, ev_view, b, seg, seg_end - seg, v0, v1 - v0,
+                                       ctx->sc_wave.p, ctx->sc_inexact.p, ctx->sm_count, ctx->ev_stage);
       ctx->launches += cast_split_launches(c->view);
       CK(cudaGetLastError());
       seg = seg_end;
@@ -921,6 +925,8 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& evs : ctx->ev_stage)
+    if (evs) cudaEventDestroy(evs);
   if (ctx->d_dist) cudaFree(ctx->d_dist);
   if (ctx->d_weight) cudaFree(ctx->d_weight);
   if (ctx->d_mword) cudaFree(ctx->d_mword);
@@ -975,6 +981,15 @@ float a3d_last_kernel_ms(a3d_ctx* ctx) {
   float ms = -1.0f;
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0f;
   return ms;
+}
+int a3d_last_stage_ms(a3d_ctx* ctx, float* out_ms, int cap) {
+  if (!ctx || !out_ms || cap < 0) return A3D_ERR_INVALID;
+  if (!ctx->timed || ctx->last_cast_kernel != 3 || ctx->n_stage < 2) return 0;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return 0;
+  int n = 0;
+  for (int k = 0; k + 1 < ctx->n_stage && n < cap; ++k, ++n)
+    if (cudaEventElapsedTime(&out_ms[n], ctx->ev_stage[k], ctx->ev_stage[k + 1]) != cudaSuccess) return n;
+  return n;
 }
 uint64_t a3d_kernel_launches(a3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

@@ -139,9 +139,10 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
 bool cast_split_supported(const MapView& m, const CasterView& c);
 size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out);
 int cast_split_launches(const CasterView& c);
-void launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
-                       int seg0, int n_seg, int view0, int n_views, void* scratch, unsigned int* inexact,
-                       int sm_count);
+// stage_events (6, or null): recorded before the first and after each kernel; returns how many were recorded
+int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                      int seg0, int n_seg, int view0, int n_views, void* scratch, unsigned int* inexact,
+                      int sm_count, cudaEvent_t* stage_events);
 int cast_wave_threads();
 int cast_wave_max_diag();
 int cast_wave_blocks_per_sm();

@@ -47,6 +47,13 @@ constexpr int kSplitThreads = 32 * kSplitWarps;
 #ifndef A3D_SPLIT_MARK_BLOCKS
 #define A3D_SPLIT_MARK_BLOCKS 7
 #endif
+// (measured on cfg2, 4096 views: VoxelType 8 CTAs 3.44 ms / 6 CTAs 4.1 ms; Frontier 8: 4.33 / 6: 4.18;
+// VoxelWeight 8: 5.82 / 6: 5.18)
+constexpr int leaf_blocks(int caster, int eval) {
+  return caster != A3D_CASTER_ITERATIVE ? 5
+         : (eval == A3D_EVAL_FRONTIER || eval == A3D_EVAL_VOXEL_WEIGHT) ? (A3D_SPLIT_LEAF_BLOCKS > 6 ? 6 : A3D_SPLIT_LEAF_BLOCKS)
+                                                                        : A3D_SPLIT_LEAF_BLOCKS;
+}
 constexpr int kSplitMaxDiag = 256;  // longest anti-diagonal k_split_mark keeps in shared memory
 
 // record word: 4 x 15-bit counters, then what the first entry was counted as
@@ -272,35 +279,62 @@ __device__ __forceinline__ Eval sample_eval(const MapView& m, const EvalView& e,
   return ev;
 }
 
+// The evaluators' per-entry work beyond a look at the meta word lives in functions of its own
+// (not inlined): their registers would otherwise be charged to the sample loop, which runs at 64.
+__device__ __forceinline__ D3 centre_of_voxel(const MapView& m, const CenterTables& ct, int g0, int g1, int g2) {
+  const int vmask = m.vps - 1;
+  return D3{__dadd_rn(static_cast<double>(origin_point(g0 >> m.vps_shift, m.bs_f)), ct.d[(g0 & vmask) + 1]),
+            __dadd_rn(static_cast<double>(origin_point(g1 >> m.vps_shift, m.bs_f)), ct.d[(g1 & vmask) + 1]),
+            __dadd_rn(static_cast<double>(origin_point(g2 >> m.vps_shift, m.bs_f)), ct.d[(g2 & vmask) + 1])};
+}
+// FrontierEvaluator::isFrontierVoxel (frontier_evaluator.cpp:69-98) where the precomputed bit of the
+// voxel's meta word does not apply: neighbours' cell classes, else literally.
+__device__ __noinline__ bool frontier_test_slow(const MapView& m, const CenterTables& ct, const EvalView& e,
+                                                int g0, int g1, int g2, double cx, double cy, double cz,
+                                                bool have_cc, bool safe) {
+  const D3 cc = have_cc ? D3{cx, cy, cz} : centre_of_voxel(m, ct, g0, g1, g2);
+  const int hint = safe ? is_frontier_by_meta(m, ct, e, cc, g0, g1, g2) : -1;
+  return hint >= 0 ? hint != 0 : is_frontier_voxel(m, ct, e, cc);
+}
+// VoxelWeightEvaluator::getVoxelValue (voxel_weight_evaluator.cpp:60-83) of a retained entry that is
+// not FREE.
+__device__ __noinline__ double voxel_weight_entry(const MapView& m, const CenterTables& ct, const EvalView& e,
+                                                  int g0, int g1, int g2, double cx, double cy, double cz,
+                                                  bool have_cc, bool safe, uint32_t word, int cs, double ox,
+                                                  double oy, double oz) {
+  int hint = -1;
+  if (safe && (cs & 3) == 2 && e.frontier_voxel_weight > 0.0) hint = is_frontier_from_word(m, e, word);
+  if ((cs & 3) == 2 && (hint >= 0 || !(e.frontier_voxel_weight > 0.0)))
+    return (hint > 0) ? e.frontier_voxel_weight : e.new_voxel_weight;  // nothing else to look at
+  const D3 cc = have_cc ? D3{cx, cy, cz} : centre_of_voxel(m, ct, g0, g1, g2);
+  double w = 0.0;
+  if ((cs & 3) == 0) w = voxel_weight(m, cc);
+  if (safe && hint < 0 && (cs & 3) == 2 && e.frontier_voxel_weight > 0.0)
+    hint = is_frontier_by_meta(m, ct, e, cc, g0, g1, g2);
+  return voxel_weight_value(m, ct, e, cc, cs, w, D3{ox, oy, oz}, hint);
+}
+
 // Fold category of a retained (or not) list entry and, for VoxelWeightEvaluator, its value.
 template <int EVAL, class S>
 __device__ __forceinline__ int entry_category(const MapView& m, const EvalView& e, const S& sh, const ViewRec& vw,
                                               Eval& ev, const bool keep, double& wval) {
   const CenterTables& ct = sh.ct;
   const SampleInfo& si = ev.si;
-  auto centre = [&]() {
-    if (ev.have_cc) return;
-    const int vmask = m.vps - 1;  // (certified samples only: the literal path delivers its centre)
-    ev.cc.x = __dadd_rn(static_cast<double>(origin_point(ev.g[0] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[0] & vmask) + 1]);
-    ev.cc.y = __dadd_rn(static_cast<double>(origin_point(ev.g[1] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[1] & vmask) + 1]);
-    ev.cc.z = __dadd_rn(static_cast<double>(origin_point(ev.g[2] >> m.vps_shift, m.bs_f)), ct.d[(ev.g[2] & vmask) + 1]);
-    ev.have_cc = true;
-  };
   int cat;
   wval = 0.0;
   if (EVAL == A3D_EVAL_VOXEL_TYPE) {
     cat = si.cs & 3;  // retained entries are always inside the bounding volume
   } else if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
     cat = 1;
-    if (keep && (si.cs & 3) != 1) {  // voxel_weight_evaluator.cpp:43-83 (free voxels score nothing)
-      int hint = -1;
-      if (ev.safe && (si.cs & 3) == 2 && e.frontier_voxel_weight > 0.0) hint = is_frontier_from_word(m, e, ev.word);
-      double w = 0.0;
-      if ((si.cs & 3) == 0 || (hint < 0 && e.frontier_voxel_weight > 0.0)) centre();
-      if ((si.cs & 3) == 0) w = voxel_weight(m, ev.cc);
-      if (ev.safe && hint < 0 && (si.cs & 3) == 2 && e.frontier_voxel_weight > 0.0)
-        hint = is_frontier_by_meta(m, ct, e, ev.cc, ev.g[0], ev.g[1], ev.g[2]);
-      wval = voxel_weight_value(m, ct, e, ev.cc, si.cs, w, D3{vw.org[0], vw.org[1], vw.org[2]}, hint);
+    if (keep && (si.cs & 3) != 1) {  // (free voxels score nothing)
+      // unobserved voxel whose frontier bit is in the meta word (the bulk): no call
+      const bool fw = e.frontier_voxel_weight > 0.0;
+      const int hint = ((si.cs & 3) == 2 && ev.safe && fw) ? is_frontier_from_word(m, e, ev.word) : -1;
+      if ((si.cs & 3) == 2 && (hint >= 0 || !fw))
+        wval = hint > 0 ? e.frontier_voxel_weight : e.new_voxel_weight;
+      else
+        wval = voxel_weight_entry(m, ct, e, ev.g[0], ev.g[1], ev.g[2], ev.cc.x, ev.cc.y, ev.cc.z, ev.have_cc, ev.safe,
+                                  ev.word, si.cs, vw.org[0], vw.org[1], vw.org[2]);
     }
   } else {
     cat = 1;
@@ -308,12 +342,11 @@ __device__ __forceinline__ int entry_category(const MapView& m, const EvalView& 
       if (EVAL == A3D_EVAL_NAIVE) {
         cat = 0;
       } else {
-        int hint = ev.safe ? is_frontier_from_word(m, e, ev.word) : -1;
-        if (hint < 0) {
-          centre();
-          if (ev.safe) hint = is_frontier_by_meta(m, ct, e, ev.cc, ev.g[0], ev.g[1], ev.g[2]);
-        }
-        if (hint >= 0 ? hint != 0 : is_frontier_voxel(m, ct, e, ev.cc)) cat = 0;
+        const int hint = ev.safe ? is_frontier_from_word(m, e, ev.word) : -1;
+        if (hint >= 0 ? hint != 0
+                      : frontier_test_slow(m, ct, e, ev.g[0], ev.g[1], ev.g[2], ev.cc.x, ev.cc.y, ev.cc.z, ev.have_cc,
+                                           ev.safe))
+          cat = 0;
       }
     }
   }
@@ -838,7 +871,7 @@ __global__ void __launch_bounds__(kSplitThreads, 6)
 // DEFERRED = true (k_split_mark2): unit = 32 entries of the view's list of rays that start in section
 // n-2; cast through that section; a ray that hits raises its provisional marks to -1.
 template <int CASTER, int EVAL, bool DEFERRED>
-__global__ void __launch_bounds__(kSplitThreads, CASTER == A3D_CASTER_ITERATIVE ? A3D_SPLIT_LEAF_BLOCKS : 5)
+__global__ void __launch_bounds__(kSplitThreads, leaf_blocks(CASTER, EVAL))
     k_split_leaf(const MapView m, const CasterView c, const EvalView e, int n_views, const SplitScratch sc) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1015,10 +1048,16 @@ __global__ void __launch_bounds__(kSplitThreads)
 }
 
 template <int CASTER, int EVAL>
-void launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
-                    int seg0, int n_seg, int view0, int n_views, const SplitScratch& sc, unsigned int* inexact,
-                    int sm_count) {
+int launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                   int seg0, int n_seg, int view0, int n_views, const SplitScratch& sc, unsigned int* inexact,
+                   int sm_count, cudaEvent_t* evs) {
+  int n_ev = 0;
+  auto stamp = [&]() {
+    if (evs) cudaEventRecord(evs[n_ev++], st);
+  };
+  stamp();
   k_split_views<<<(n_seg + 127) / 128, 128, 0, st>>>(m, c, b, seg0, n_seg, view0, sc);
+  stamp();
   const size_t tab_bytes = static_cast<size_t>(vol_tab_entries(m)) * 4;
   if (CASTER == A3D_CASTER_ITERATIVE && c.n_sections > 1) {
     // the ray table in shared memory when it fits next to the other tables (at most 8 views per SM)
@@ -1041,36 +1080,37 @@ void launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, cons
     cudaMemsetAsync(sc.rec, 0, static_cast<size_t>(n_views) * 2 * sc.stride * 8, st);
     cudaMemsetAsync(sc.dcount, 0, static_cast<size_t>(n_views) * 4, st);
   }
+  if (CASTER == A3D_CASTER_ITERATIVE) stamp();
   {
     const long long units = static_cast<long long>(n_views) * ((c.n_rays + 31) / 32);
-    const int per_sm = CASTER == A3D_CASTER_ITERATIVE ? A3D_SPLIT_LEAF_BLOCKS : 5;
+    const int per_sm = leaf_blocks(CASTER, EVAL);
     const int grid = static_cast<int>(std::max(1ll, std::min((units + kSplitWarps - 1) / kSplitWarps,
                                                              static_cast<long long>(sm_count) * per_sm * 4)));
     if (CASTER == A3D_CASTER_ITERATIVE && c.n_sections > 1)
       k_split_leaf<CASTER, EVAL, true><<<grid, kSplitThreads, tab_bytes, st>>>(m, c, e, n_views, sc);
+    if (CASTER == A3D_CASTER_ITERATIVE) stamp();
     k_split_leaf<CASTER, EVAL, false><<<grid, kSplitThreads, tab_bytes, st>>>(m, c, e, n_views, sc);
+    stamp();
   }
   k_split_fix<CASTER, EVAL><<<(n_seg + kSplitWarps - 1) / kSplitWarps, kSplitThreads, 0, st>>>(
       e, b, seg0, n_seg, view0, c.n_rays, sc, inexact);
+  stamp();
+  return n_ev;
 }
 
 template <int CASTER>
-void launch_split_c(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
-                    int seg0, int n_seg, int view0, int n_views, const SplitScratch& sc, unsigned int* inexact,
-                    int sm_count) {
+int launch_split_c(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                   int seg0, int n_seg, int view0, int n_views, const SplitScratch& sc, unsigned int* inexact,
+                   int sm_count, cudaEvent_t* evs) {
   switch (e.kind) {
     case A3D_EVAL_VOXEL_TYPE:
-      launch_split_t<CASTER, A3D_EVAL_VOXEL_TYPE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count);
-      break;
+      return launch_split_t<CASTER, A3D_EVAL_VOXEL_TYPE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
     case A3D_EVAL_NAIVE:
-      launch_split_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count);
-      break;
+      return launch_split_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
     case A3D_EVAL_VOXEL_WEIGHT:
-      launch_split_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count);
-      break;
+      return launch_split_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
     default:
-      launch_split_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count);
-      break;
+      return launch_split_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
   }
 }
 
@@ -1098,9 +1138,9 @@ int cast_split_launches(const CasterView& c) { return c.kind == A3D_CASTER_ITERA
 // Segments [seg0, seg0 + n_seg) = views [view0, view0 + n_views) of the batch; scratch holds
 // n_views * cast_split_bytes_per_view() + 256 bytes.  inexact: one bit per segment (batch-wide
 // numbering), set when a sample needs the scan-order kernel's decision.
-void launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
-                       int seg0, int n_seg, int view0, int n_views, void* scratch, unsigned int* inexact,
-                       int sm_count) {
+int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                      int seg0, int n_seg, int view0, int n_views, void* scratch, unsigned int* inexact,
+                      int sm_count, cudaEvent_t* stage_events) {
   SplitScratch sc{};
   size_t stride = 0;
   cast_split_bytes_per_view(c, e.kind, &stride);
@@ -1132,10 +1172,11 @@ void launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, c
     sc.dcount = reinterpret_cast<unsigned int*>(p);
     p += (nv * 4 + 7) / 8 * 8;
     sc.start_s = p;
-    launch_split_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count);
-  } else {
-    launch_split_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count);
+    return launch_split_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count,
+                                                stage_events);
   }
+  return launch_split_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count,
+                                           stage_events);
 }
 
 }  // namespace a3d

@@ -24,10 +24,8 @@ def main():
     ap.add_argument("--views", default="1024,4096,16384,65536")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--evaluator", default=None, help="override the workload's evaluator, e.g. VoxelWeight")
-    ap.add_argument("--cast-kernel", type=int, default=0, help="0 auto, 1 scan-order, 2 wavefront")
+    ap.add_argument("--cast-kernel", type=int, default=0, help="0 auto, 1 scan-order, 2 wavefront, 3 kernel chain")
     ap.add_argument("--wave-cta", type=int, default=0, help="0 auto, 1 two-warp CTAs, 2 eight-warp CTAs")
-    ap.add_argument("--wave-help", type=int, default=1, help="cross-CTA help: 0 off, 1 on")
-    ap.add_argument("--wave-helpers", type=int, default=-1, help="surplus CTAs per segment for small batches")
     args = ap.parse_args()
     cfg = dict(synth.CONFIGS[args.workload])
     if args.evaluator:
@@ -48,12 +46,6 @@ def main():
     ev = ctx.evaluator(cfg["evaluator"] + "Evaluator")
     ctx.set_option("cast_kernel", args.cast_kernel)
     ctx.set_option("wave_cta", args.wave_cta)
-    try:
-        ctx.set_option("wave_help", args.wave_help)
-        if args.wave_helpers >= 0:
-            ctx.set_option("wave_helpers", args.wave_helpers)
-    except capi.A3DError:
-        pass  # (an older build of the library under A/B test)
     dev = torch.device("cuda", 0)
     peak = 6555.2
     try:
@@ -75,6 +67,7 @@ def main():
             k = ctx.last_kernel_ms
             if r:
                 ms.append(k)
+                stages = getattr(ctx, "last_stage_ms", [])
         S, V = int(t_nsamp.sum().item()), int(t_nvis.sum().item())
         # (lower bound for Frontier; VoxelWeight: centre state + one TSDF weight)
         fold = {"VoxelType": 8 * V, "Naive": V, "Frontier": V, "VoxelWeight": 9 * V}[cfg["evaluator"]]
@@ -87,7 +80,8 @@ def main():
                           "lookups_per_s": lookups / (best * 1e-3),
                           "samples_per_view": S / n, "algorithmic_GBps": alg / (best * 1e-3) / 1e9,
                           "frac_of_hbm": alg / (best * 1e-3) / 1e9 / peak,
-                          "kernel": ctx.last_cast_kernel, "gain_sum": float(t_gain.sum().item())}), flush=True)
+                          "kernel": ctx.last_cast_kernel, "stage_ms": [round(x, 3) for x in stages],
+                          "gain_sum": float(t_gain.sum().item())}), flush=True)
 
 
 if __name__ == "__main__":
