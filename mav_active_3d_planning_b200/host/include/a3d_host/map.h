@@ -9,11 +9,13 @@
 #pragma once
 
 #include <cstdint>
+#include <string>
 #include <vector>
 
 #include "a3d_host/data.h"
 
 struct a3d_ctx;
+struct a3d_group;
 
 namespace active_3d_planning {
 
@@ -50,8 +52,10 @@ class VoxbloxMap : public TSDFMap {
   explicit VoxbloxMap(PlannerI& planner);  // NOLINT
   ~VoxbloxMap() override;
 
-  // params: tsdf_voxel_size (0.1), tsdf_voxels_per_side (16), max_weight (10000), device (0) —
-  // the voxblox server parameters of app_reconstruction/launch/example.launch:143-144
+  // params: tsdf_voxel_size (0.1), tsdf_voxels_per_side (16), max_weight (10000) — the voxblox server
+  // parameters of app_reconstruction/launch/example.launch:143-144 — and where the mirror lives:
+  // device (0), or devices ("0,1,2,3": one replica per GPU behind an a3d_group; batch gain calls are
+  // then sharded over all of them)
   void setupFromParamMap(Module::ParamMap* param_map) override;
   bool checkParamsValid(std::string* error_message) override;
 
@@ -78,11 +82,16 @@ class VoxbloxMap : public TSDFMap {
   void areTraversable(const std::vector<Eigen::Vector3d>& points, std::vector<unsigned char>* out);
 
   a3d_ctx* context() { return ctx_; }
+  // non-null when `devices` names more than one GPU (context() is then the first GPU's)
+  a3d_group* group() { return group_; }
+  int numDevices() const;
 
  protected:
   static ModuleFactoryRegistry::Registration<VoxbloxMap> registration;
   void check(int rc, const char* what);
   a3d_ctx* ctx_;
+  a3d_group* group_;
+  std::string p_devices_;
   double p_voxel_size_;
   int p_voxels_per_side_;
   double c_voxel_size_;  // double(float voxel size), voxblox.cpp:26

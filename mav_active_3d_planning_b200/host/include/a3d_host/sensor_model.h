@@ -11,6 +11,8 @@
 
 #include "a3d_host/map.h"
 
+struct a3d_group_caster;
+
 struct a3d_caster;
 
 namespace active_3d_planning {
@@ -55,6 +57,14 @@ class CameraModel : public SensorModel {
   int rayGridY() const;
   int numSections() const;
   a3d_caster* handle() { return caster_; }
+  a3d_group_caster* groupHandle() { return group_caster_; }  // non-null on a multi-GPU map
+
+  // `test: true` (camera_model.cpp:31-54): the reference times every getVisibleVoxels call on the
+  // wall clock and logs mean / stddev every 20 calls.  Here the time of a view is the CUDA-event
+  // time of the device call that cast it, divided by the views of that call; same log line.
+  void noteCastTime(double device_ms, int n_views);
+  // (mean, stddev, count) over everything noted so far, in ms per view
+  void castTimeStats(double* mean, double* stddev, size_t* count) const;
 
  protected:
   virtual int casterKind() const = 0;
@@ -62,6 +72,8 @@ class CameraModel : public SensorModel {
   map::VoxbloxMap* gpu_map_;
   a3d_caster* caster_;          // with the mounting transform (trajectory-level calls)
   a3d_caster* caster_camera_;   // identity mount (getVisibleVoxels takes a camera pose)
+  a3d_group_caster* group_caster_;  // the trajectory-level caster on every GPU of the map's group
+  std::vector<double> time_count_;
   double p_ray_length_, p_sampling_time_, p_focal_length_, p_ray_step_, p_downsampling_factor_;
   double p_fov_x_deg_, p_fov_y_deg_;  // lidar casters only
   int p_resolution_x_, p_resolution_y_;

@@ -20,6 +20,7 @@
 #include "a3d_host/sensor_model.h"
 
 struct a3d_eval;
+struct a3d_group_eval;
 struct a3d_store;
 
 namespace active_3d_planning {
@@ -39,10 +40,16 @@ class NextSelector : public Module {
   explicit NextSelector(PlannerI& planner) : Module(planner) {}  // NOLINT
   virtual int selectNextBest(TrajectorySegment* traj_in) = 0;
 };
+// Update step of the planner's evaluator (module/trajectory_evaluator.h:80-90): false = drop the
+// segment and its subtree.  The reference walks the tree and updates one segment per call
+// (online_planner.cpp:679-693); the device wants the tree at once, so the primary form here is the
+// batch: updateSegments() looks at every segment whose `alive` flag is set, clears the flag of those it
+// drops and may re-evaluate the others in ONE launch.  updateSegment() is the one-element batch.
 class EvaluatorUpdater : public Module {
  public:
   explicit EvaluatorUpdater(PlannerI& planner) : Module(planner) {}  // NOLINT
-  virtual bool updateSegment(TrajectorySegment* segment) = 0;
+  virtual void updateSegments(const std::vector<TrajectorySegment*>& segments, std::vector<uint8_t>* alive) = 0;
+  virtual bool updateSegment(TrajectorySegment* segment);
 };
 
 class TrajectoryEvaluator : public Module {
@@ -56,9 +63,16 @@ class TrajectoryEvaluator : public Module {
   virtual bool computeValue(TrajectorySegment* traj_in);
   virtual int selectNextBest(TrajectorySegment* traj_in);
   virtual bool updateSegment(TrajectorySegment* segment);
+  // additive: OnlinePlanner::updateEvaluatorStep (online_planner.cpp:679-693) for the whole tree below
+  // `root` in one pass of the updater chain — every surviving segment is updated, the subtrees of the
+  // dropped ones are removed.  Returns how many segments were removed.
+  virtual int updateTree(TrajectorySegment* root);
+  // batch form of updateSegment (default: the updater chain's batch)
+  virtual void updateSegments(const std::vector<TrajectorySegment*>& segments, std::vector<uint8_t>* alive);
   void setupFromParamMap(Module::ParamMap* param_map) override;
 
  protected:
+  EvaluatorUpdater* updater();
   std::unique_ptr<BoundingVolume> bounding_volume_;
   std::string p_cost_args_, p_value_args_, p_next_args_, p_updater_args_;
   std::unique_ptr<CostComputer> cost_computer_;
@@ -111,8 +125,12 @@ class SimulatedSensorEvaluator : public TrajectoryEvaluator {
   // simulated_sensor_updater.cpp:18-22), in one launch
   virtual bool updateGains(const std::vector<TrajectorySegment*>& segments);
   SensorModel* sensorModel() { return sensor_model_.get(); }
+  // device time (CUDA events) spent in gain evaluation since the last call: the `Gain` column of the
+  // planner's performance log (online_planner.cpp:97-101, 413-420)
+  double takeGainTimeMs();
 
  protected:
+  void noteDeviceTime(int n_views, bool group);
   virtual bool storeTrajectoryInformation(TrajectorySegment* traj_in,
                                           const std::vector<Eigen::Vector3d>& new_voxels);
   virtual int evalKind() const = 0;
@@ -123,6 +141,8 @@ class SimulatedSensorEvaluator : public TrajectoryEvaluator {
   map::VoxbloxMap* gpu_map_;
   std::unique_ptr<SensorModel> sensor_model_;
   a3d_eval* eval_;
+  a3d_group_eval* group_eval_;
+  double perf_gain_ms_ = 0.0;
   std::shared_ptr<DeviceListStore> device_lists_;
   uint64_t next_key_ = 1;
   bool p_clear_from_parents_, p_visualize_sensor_view_;
@@ -201,6 +221,8 @@ class YawPlanningEvaluator : public TrajectoryEvaluator {
   bool computeValue(TrajectorySegment* traj_in) override;
   int selectNextBest(TrajectorySegment* traj_in) override;
   bool updateSegment(TrajectorySegment* segment) override;
+  // the stale orientations of all the segments are re-evaluated in one launch
+  void updateSegments(const std::vector<TrajectorySegment*>& segments, std::vector<uint8_t>* alive) override;
   void setupFromParamMap(Module::ParamMap* param_map) override;
   bool checkParamsValid(std::string* error_message) override;
   // additive: computeGain for many segments, all their orientations in one launch
@@ -223,6 +245,7 @@ class YawPlanningEvaluator : public TrajectoryEvaluator {
   void spawnOrientations(TrajectorySegment* traj_in);
   // gain (and cost/value if select_by_value) of the given oriented copies
   bool evaluateOrientations(const std::vector<TrajectorySegment*>& copies);
+  bool collectStaleOrientations(TrajectorySegment* segment, std::vector<TrajectorySegment*>* again);
 };
 
 class SimpleYawPlanningEvaluator : public YawPlanningEvaluator {

@@ -3,6 +3,7 @@
 // host code parses parameters, samples view points, moves buffers and keeps the reference's
 // ownership / error conventions.  Reference citations are relative to the reference checkout.
 #include <algorithm>
+#include <map>
 #include <cmath>
 #include <limits>
 #include <cstdio>
@@ -48,8 +49,9 @@ bool ModuleFactoryRegistry::isRegistered(const std::string& name) {
 }
 
 void ModuleFactory::getDefaultType(const std::type_index& module_index, std::string* type) {
-  // module_factory.cpp:14-25 — of the reference's defaults only BoundingVolume is on this path
+  // module_factory.cpp:14-25 — the reference's defaults for the module kinds of this path
   if (module_index == std::type_index(typeid(BoundingVolume))) *type = "BoundingVolume";
+  if (module_index == std::type_index(typeid(EvaluatorUpdater))) *type = "UpdateNothing";
 }
 void ModuleFactory::registerLinkableModule(const std::string& name, Module* module) {
   linkable_module_list_[name] = module;  // module_factory.cpp:27-31
@@ -132,12 +134,16 @@ namespace map {
 ModuleFactoryRegistry::Registration<VoxbloxMap> VoxbloxMap::registration("VoxbloxMap");
 
 VoxbloxMap::VoxbloxMap(PlannerI& planner)
-    : TSDFMap(planner), ctx_(nullptr), p_voxel_size_(0.1), p_voxels_per_side_(16), c_voxel_size_(0.1),
-      c_maximum_weight_(10000.0), p_device_(0) {}
+    : TSDFMap(planner), ctx_(nullptr), group_(nullptr), p_voxel_size_(0.1), p_voxels_per_side_(16),
+      c_voxel_size_(0.1), c_maximum_weight_(10000.0), p_device_(0) {}
 
 VoxbloxMap::~VoxbloxMap() {
-  if (ctx_) a3d_ctx_destroy(ctx_);
+  if (group_)
+    a3d_group_destroy(group_);  // owns the per-device contexts
+  else if (ctx_)
+    a3d_ctx_destroy(ctx_);
 }
+int VoxbloxMap::numDevices() const { return group_ ? a3d_group_size(group_) : (ctx_ ? 1 : 0); }
 
 void VoxbloxMap::check(int rc, const char* what) {
   if (rc == A3D_OK) return;
@@ -150,13 +156,30 @@ void VoxbloxMap::setupFromParamMap(Module::ParamMap* param_map) {
   setParam<int>(param_map, "tsdf_voxels_per_side", &p_voxels_per_side_, 16);
   setParam<double>(param_map, "max_weight", &c_maximum_weight_, 10000.0);
   setParam<int>(param_map, "device", &p_device_, 0);
+  setParam<std::string>(param_map, "devices", &p_devices_, "");
   if (!(p_voxel_size_ > 0.0) || p_voxels_per_side_ < 1) return;  // reported by checkParamsValid
-  const int rc = a3d_ctx_create(p_device_, &ctx_);
-  if (rc != A3D_OK) {
-    // no CPU fallback: a map without a device cannot answer anything
-    throw std::runtime_error(std::string("VoxbloxMap: no usable B200 device: ") + a3d_last_error(nullptr));
+  std::vector<int> ids;
+  for (size_t at = 0; at < p_devices_.size();) {
+    const size_t comma = p_devices_.find(',', at);
+    const std::string tok = p_devices_.substr(at, comma == std::string::npos ? std::string::npos : comma - at);
+    if (!tok.empty()) ids.push_back(std::stoi(tok));
+    if (comma == std::string::npos) break;
+    at = comma + 1;
   }
-  check(a3d_map_config(ctx_, static_cast<float>(p_voxel_size_), p_voxels_per_side_), "a3d_map_config");
+  if (ids.size() == 1) p_device_ = ids[0];
+  // no CPU fallback: a map without a device cannot answer anything
+  if (ids.size() > 1) {
+    if (a3d_group_create(ids.data(), static_cast<int>(ids.size()), &group_) != A3D_OK)
+      throw std::runtime_error(std::string("VoxbloxMap: no usable group of B200 devices: ") +
+                               a3d_group_last_error(nullptr));
+    ctx_ = a3d_group_ctx(group_, 0);
+    if (a3d_group_map_config(group_, static_cast<float>(p_voxel_size_), p_voxels_per_side_) != A3D_OK)
+      throw std::runtime_error(std::string("a3d_group_map_config: ") + a3d_group_last_error(group_));
+  } else {
+    if (a3d_ctx_create(p_device_, &ctx_) != A3D_OK)
+      throw std::runtime_error(std::string("VoxbloxMap: no usable B200 device: ") + a3d_last_error(nullptr));
+    check(a3d_map_config(ctx_, static_cast<float>(p_voxel_size_), p_voxels_per_side_), "a3d_map_config");
+  }
   c_voxel_size_ = a3d_map_voxel_size(ctx_);  // double(float voxel size), voxblox.cpp:26
 }
 
@@ -174,11 +197,21 @@ bool VoxbloxMap::checkParamsValid(std::string* error_message) {
 
 bool VoxbloxMap::uploadBlocks(int n, const int32_t* block_idx, const float* esdf_distance,
                               const uint8_t* esdf_observed, const float* tsdf_weight) {
+  if (group_) {  // host -> GPU 0 once, NCCL broadcast to the replicas, applied by every GPU
+    if (a3d_group_map_upload_blocks(group_, n, block_idx, esdf_distance, esdf_observed, tsdf_weight) != A3D_OK)
+      throw std::runtime_error(std::string("a3d_group_map_upload_blocks: ") + a3d_group_last_error(group_));
+    return true;
+  }
   check(a3d_map_upload_blocks(ctx_, n, block_idx, esdf_distance, esdf_observed, tsdf_weight),
         "a3d_map_upload_blocks");
   return true;
 }
 bool VoxbloxMap::removeBlocks(int n, const int32_t* block_idx) {
+  if (group_) {
+    if (a3d_group_map_remove_blocks(group_, n, block_idx) != A3D_OK)
+      throw std::runtime_error(std::string("a3d_group_map_remove_blocks: ") + a3d_group_last_error(group_));
+    return true;
+  }
   check(a3d_map_remove_blocks(ctx_, n, block_idx), "a3d_map_remove_blocks");
   return true;
 }
@@ -263,7 +296,7 @@ namespace sensor_model {
 
 CameraModel::CameraModel(PlannerI& planner)
     : SensorModel(planner), gpu_map_(nullptr), caster_(nullptr), caster_camera_(nullptr),
-      p_ray_length_(5.0), p_sampling_time_(0.0), p_focal_length_(320.0), p_ray_step_(0.0),
+      group_caster_(nullptr), p_ray_length_(5.0), p_sampling_time_(0.0), p_focal_length_(320.0), p_ray_step_(0.0),
       p_downsampling_factor_(1.0), p_fov_x_deg_(360.0), p_fov_y_deg_(30.0), p_resolution_x_(640),
       p_resolution_y_(480), p_test_(false),
       c_field_of_view_x_(0.0), c_field_of_view_y_(0.0) {}
@@ -271,6 +304,7 @@ CameraModel::CameraModel(PlannerI& planner)
 CameraModel::~CameraModel() {
   if (caster_) a3d_caster_destroy(caster_);
   if (caster_camera_) a3d_caster_destroy(caster_camera_);
+  if (group_caster_) a3d_group_caster_destroy(group_caster_);
 }
 
 void CameraModel::setupFromParamMap(Module::ParamMap* param_map) {  // camera_model.cpp:170-183
@@ -337,6 +371,10 @@ void CameraModel::buildCasters(Module::ParamMap* param_map) {
     caster_ = nullptr;
     return;
   }
+  if (gpu_map_->group() && a3d_group_caster_create(gpu_map_->group(), &p, &group_caster_) != A3D_OK) {
+    planner_.printError(std::string("a3d_group_caster_create: ") + a3d_group_last_error(gpu_map_->group()));
+    group_caster_ = nullptr;
+  }
   for (int k = 0; k < 3; ++k) p.mount_t[k] = 0.0;
   p.mount_q[0] = 1.0;
   p.mount_q[1] = p.mount_q[2] = p.mount_q[3] = 0.0;
@@ -375,6 +413,28 @@ void CameraModel::sampleViewpoints(std::vector<int>* result, const TrajectorySeg
       result->push_back(i);
     }
   }
+}
+
+void CameraModel::noteCastTime(double device_ms, int n_views) {
+  if (!p_test_ || n_views <= 0 || !(device_ms >= 0.0)) return;
+  const size_t before = time_count_.size();
+  time_count_.insert(time_count_.end(), static_cast<size_t>(n_views), device_ms / n_views);
+  if (time_count_.size() / 20 == before / 20) return;  // the reference logs at every 20th view
+  double mean, stddev;
+  size_t count;
+  castTimeStats(&mean, &stddev, &count);
+  planner_.printInfo("Raycasting: Mean: " + std::to_string(mean) + " ms, Stddev: " + std::to_string(stddev) +
+                     " ms");
+}
+void CameraModel::castTimeStats(double* mean, double* stddev, size_t* count) const {
+  const size_t n = time_count_.size();
+  double m = 0.0, v = 0.0;
+  for (double t : time_count_) m += t;
+  if (n) m /= static_cast<double>(n);
+  for (double t : time_count_) v += (t - m) * (t - m);
+  *mean = m;
+  *stddev = n ? std::sqrt(v / static_cast<double>(n)) : 0.0;
+  *count = n;
 }
 
 void CameraModel::getDirectionVector(Eigen::Vector3d* result, double relative_x, double relative_y) {
@@ -433,6 +493,7 @@ bool CameraModel::getVisibleVoxelsFromTrajectory(std::vector<Eigen::Vector3d>* r
   if (!runVisible(gpu_map_->context(), caster_, nullptr, static_cast<int>(indices.size()), pos.data(),
                   quat.data(), result, nullptr, planner_))
     return false;
+  noteCastTime(a3d_last_kernel_ms(gpu_map_->context()), static_cast<int>(indices.size()));
   // entries appended to a non-empty *result still get the reference's whole-vector unique
   if (before > 0) result->erase(std::unique(result->begin(), result->end()), result->end());
   return true;
@@ -442,8 +503,10 @@ bool CameraModel::getVisibleVoxels(std::vector<Eigen::Vector3d>* result, const E
                                    const Eigen::Quaterniond& orientation) {
   if (!caster_camera_) return false;
   const double quat[4] = {orientation.w(), orientation.x(), orientation.y(), orientation.z()};
-  return runVisible(gpu_map_->context(), caster_camera_, nullptr, 1, position.data(), quat, result,
-                    nullptr, planner_);
+  const bool ok = runVisible(gpu_map_->context(), caster_camera_, nullptr, 1, position.data(), quat, result,
+                             nullptr, planner_);
+  if (ok) noteCastTime(a3d_last_kernel_ms(gpu_map_->context()), 1);
+  return ok;
 }
 
 ModuleFactoryRegistry::Registration<SimpleRayCaster> SimpleRayCaster::registration("SimpleRayCaster");
@@ -522,11 +585,48 @@ int TrajectoryEvaluator::selectNextBest(TrajectorySegment* traj_in) {
     next_selector_ = planner_.getFactory().createModule<NextSelector>(p_next_args_, planner_, verbose_modules_);
   return next_selector_->selectNextBest(traj_in);
 }
-bool TrajectoryEvaluator::updateSegment(TrajectorySegment* segment) {
+EvaluatorUpdater* TrajectoryEvaluator::updater() {
   if (!evaluator_updater_)
     evaluator_updater_ =
         planner_.getFactory().createModule<EvaluatorUpdater>(p_updater_args_, planner_, verbose_modules_);
-  return evaluator_updater_->updateSegment(segment);
+  return evaluator_updater_.get();
+}
+bool TrajectoryEvaluator::updateSegment(TrajectorySegment* segment) { return updater()->updateSegment(segment); }
+void TrajectoryEvaluator::updateSegments(const std::vector<TrajectorySegment*>& segments,
+                                         std::vector<uint8_t>* alive) {
+  updater()->updateSegments(segments, alive);
+}
+int TrajectoryEvaluator::updateTree(TrajectorySegment* root) {
+  // every segment below the root, parents before children
+  std::vector<TrajectorySegment*> all;
+  for (auto& c : root->children) all.push_back(c.get());
+  for (size_t at = 0; at < all.size(); ++at)
+    for (auto& c : all[at]->children) all.push_back(c.get());
+  if (all.empty()) return 0;
+  std::vector<uint8_t> alive(all.size(), 1);
+  updateSegments(all, &alive);
+  // a dropped segment takes its subtree with it (the reference never descends into it)
+  std::map<const TrajectorySegment*, size_t> at;
+  for (size_t i = 0; i < all.size(); ++i) at[all[i]] = i;
+  int removed = 0;
+  for (size_t i = 0; i < all.size(); ++i) {
+    const TrajectorySegment* up = all[i]->parent;
+    if (up != root && !alive[at[up]]) alive[i] = 0;
+    removed += alive[i] ? 0 : 1;
+  }
+  // erase from the deepest level upwards so that no erased pointer is looked at again
+  for (size_t i = all.size(); i-- > 0;) {
+    if (alive[i]) continue;
+    auto& siblings = all[i]->parent->children;
+    siblings.erase(std::find_if(siblings.begin(), siblings.end(),
+                                [&](const std::unique_ptr<TrajectorySegment>& c) { return c.get() == all[i]; }));
+  }
+  return removed;
+}
+bool EvaluatorUpdater::updateSegment(TrajectorySegment* segment) {
+  std::vector<uint8_t> alive(1, 1);
+  updateSegments({segment}, &alive);
+  return alive[0] != 0;
 }
 
 namespace trajectory_evaluator {
@@ -534,7 +634,7 @@ using sensor_model::detail::gatherPoses;
 using sensor_model::detail::runVisible;
 
 SimulatedSensorEvaluator::SimulatedSensorEvaluator(PlannerI& planner)
-    : TrajectoryEvaluator(planner), map_(nullptr), gpu_map_(nullptr), eval_(nullptr),
+    : TrajectoryEvaluator(planner), map_(nullptr), gpu_map_(nullptr), eval_(nullptr), group_eval_(nullptr),
       p_clear_from_parents_(false), p_visualize_sensor_view_(false) {}
 
 DeviceListStore::~DeviceListStore() {
@@ -547,6 +647,19 @@ DeviceSensorInfo::~DeviceSensorInfo() {
 SimulatedSensorEvaluator::~SimulatedSensorEvaluator() {
   device_lists_.reset();  // before the evaluator object; the map (context) outlives the evaluator
   if (eval_) a3d_eval_destroy(eval_);
+  if (group_eval_) a3d_group_eval_destroy(group_eval_);
+}
+
+double SimulatedSensorEvaluator::takeGainTimeMs() {
+  const double t = perf_gain_ms_;
+  perf_gain_ms_ = 0.0;
+  return t;
+}
+void SimulatedSensorEvaluator::noteDeviceTime(int n_views, bool group) {
+  const double ms = group ? a3d_group_last_kernel_ms(gpu_map_->group()) : a3d_last_kernel_ms(gpu_map_->context());
+  if (!(ms >= 0.0)) return;
+  perf_gain_ms_ += ms;
+  if (auto* cam = dynamic_cast<sensor_model::CameraModel*>(sensor_model_.get())) cam->noteCastTime(ms, n_views);
 }
 
 bool SimulatedSensorEvaluator::computeGainsStored(const std::vector<TrajectorySegment*>& segments) {
@@ -599,6 +712,7 @@ bool SimulatedSensorEvaluator::computeGainsStored(const std::vector<TrajectorySe
     planner_.printError(std::string("a3d_compute_gains_stored: ") + a3d_last_error(gpu_map_->context()));
     return false;
   }
+  noteDeviceTime(static_cast<int>(view_segment.size()), false);
   for (size_t s = 0; s < segments.size(); ++s) {
     auto* info = new DeviceSensorInfo();
     info->key = keys[s];
@@ -691,6 +805,10 @@ void SimulatedSensorEvaluator::buildEval() {
   eval_ = nullptr;
   if (a3d_eval_create(gpu_map_->context(), &p, &eval_) != A3D_OK)
     planner_.printError(std::string("a3d_eval_create: ") + a3d_last_error(gpu_map_->context()));
+  if (group_eval_) a3d_group_eval_destroy(group_eval_);
+  group_eval_ = nullptr;
+  if (gpu_map_->group() && a3d_group_eval_create(gpu_map_->group(), &p, &group_eval_) != A3D_OK)
+    planner_.printError(std::string("a3d_group_eval_create: ") + a3d_group_last_error(gpu_map_->group()));
 }
 
 bool SimulatedSensorEvaluator::computeGain(TrajectorySegment* traj_in) {
@@ -706,6 +824,7 @@ bool SimulatedSensorEvaluator::computeGain(TrajectorySegment* traj_in) {
   if (!runVisible(gpu_map_->context(), cam->handle(), eval_, static_cast<int>(indices.size()), pos.data(),
                   quat.data(), &new_voxels, nullptr, planner_))
     return false;
+  noteDeviceTime(static_cast<int>(indices.size()), false);
   if (p_clear_from_parents_) {  // :60-76, one device pass per ancestor
     std::vector<uint8_t> keep(new_voxels.size(), 1);
     std::vector<double> flat(new_voxels.size() * 3);
@@ -778,32 +897,69 @@ bool SimulatedSensorEvaluator::computeGainFromVisibleVoxels(TrajectorySegment* t
 bool SimulatedSensorEvaluator::computeGains(const std::vector<TrajectorySegment*>& segments) {
   auto* cam = dynamic_cast<sensor_model::CameraModel*>(sensor_model_.get());
   if (!cam || !cam->handle() || !eval_) return false;
+  const size_t n = segments.size();
+  // clear_from_parents (simulated_sensor_evaluator.cpp:60-76) as a batch: a segment's list loses what
+  // its ancestors inside the batch see.  The device call wants parents before children, so the batch
+  // is laid out by depth; `order[k]` = position in `segments` of the k-th segment handed over.
+  std::vector<size_t> order(n);
+  for (size_t s = 0; s < n; ++s) order[s] = s;
+  std::vector<int32_t> parent_index;
   if (p_clear_from_parents_) {
-    planner_.printWarning("computeGains: clear_from_parents needs per-segment lists; use computeGain");
-    return false;
+    std::vector<int> depth(n, 0);
+    for (size_t s = 0; s < n; ++s)
+      for (TrajectorySegment* a = segments[s]->parent; a; a = a->parent) ++depth[s];
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return depth[a] < depth[b]; });
+    std::map<const TrajectorySegment*, int32_t> slot;
+    for (size_t k = 0; k < n; ++k) slot[segments[order[k]]] = static_cast<int32_t>(k);
+    parent_index.assign(n, -1);
+    for (size_t k = 0; k < n; ++k) {
+      // nearest ancestor that is part of the batch (the ones in between contribute no list)
+      for (TrajectorySegment* a = segments[order[k]]->parent; a; a = a->parent) {
+        auto it = slot.find(a);
+        if (it != slot.end()) {
+          parent_index[k] = it->second;
+          break;
+        }
+      }
+    }
   }
-  std::vector<double> pos, quat;
+  std::vector<double> pos, quat, origins(n * 3, 0.0);
   std::vector<int32_t> view_segment;
-  for (size_t s = 0; s < segments.size(); ++s) {
-    if (segments[s]->trajectory.empty()) continue;
+  for (size_t k = 0; k < n; ++k) {
+    TrajectorySegment* seg = segments[order[k]];
+    if (seg->trajectory.empty()) continue;
     std::vector<int> indices;
-    cam->sampleViewpoints(&indices, *segments[s]);
-    gatherPoses(*segments[s], indices, &pos, &quat);
-    view_segment.insert(view_segment.end(), indices.size(), static_cast<int32_t>(s));
+    cam->sampleViewpoints(&indices, *seg);
+    gatherPoses(*seg, indices, &pos, &quat);
+    view_segment.insert(view_segment.end(), indices.size(), static_cast<int32_t>(k));
+    for (int c = 0; c < 3; ++c) origins[3 * k + c] = seg->trajectory.back().position_W[c];
   }
-  std::vector<double> gains(segments.size(), 0.0), origins(segments.size() * 3, 0.0);
-  for (size_t s = 0; s < segments.size(); ++s)
-    if (!segments[s]->trajectory.empty())
-      for (int k = 0; k < 3; ++k) origins[3 * s + k] = segments[s]->trajectory.back().position_W[k];
-  const int rc = a3d_compute_gains(gpu_map_->context(), cam->handle(), eval_,
-                                   static_cast<int>(view_segment.size()), pos.data(), quat.data(),
-                                   view_segment.data(), static_cast<int>(segments.size()), gains.data(),
-                                   nullptr, nullptr, nullptr, nullptr, origins.data());
+  std::vector<double> gains(n, 0.0);
+  const int n_views = static_cast<int>(view_segment.size());
+  // every GPU of the map's group takes a share of the segments (the tree form stays on one GPU: the
+  // ancestors' lists would have to travel)
+  const bool sharded = !p_clear_from_parents_ && gpu_map_->group() && cam->groupHandle() && group_eval_;
+  int rc;
+  if (sharded) {
+    rc = a3d_group_compute_gains(gpu_map_->group(), cam->groupHandle(), group_eval_, n_views, pos.data(),
+                                 quat.data(), view_segment.data(), static_cast<int>(n), gains.data(), nullptr,
+                                 nullptr, nullptr, nullptr, origins.data());
+  } else if (p_clear_from_parents_) {
+    rc = a3d_compute_gains_tree(gpu_map_->context(), cam->handle(), eval_, n_views, pos.data(), quat.data(),
+                                view_segment.data(), static_cast<int>(n), parent_index.data(), gains.data(),
+                                nullptr, nullptr, nullptr, nullptr, origins.data());
+  } else {
+    rc = a3d_compute_gains(gpu_map_->context(), cam->handle(), eval_, n_views, pos.data(), quat.data(),
+                           view_segment.data(), static_cast<int>(n), gains.data(), nullptr, nullptr, nullptr,
+                           nullptr, origins.data());
+  }
   if (rc != A3D_OK) {
-    planner_.printError(std::string("a3d_compute_gains: ") + a3d_last_error(gpu_map_->context()));
+    planner_.printError(std::string("computeGains: ") + (sharded ? a3d_group_last_error(gpu_map_->group())
+                                                                 : a3d_last_error(gpu_map_->context())));
     return false;
   }
-  for (size_t s = 0; s < segments.size(); ++s) segments[s]->gain = gains[s];
+  noteDeviceTime(n_views, sharded);
+  for (size_t k = 0; k < n; ++k) segments[order[k]]->gain = gains[k];
   return true;
 }
 
@@ -890,10 +1046,39 @@ void VoxelWeightEvaluator::fillEvalParams(void* ptr) {
 }
 
 // ---- yaw planning -------------------------------------------------------------------------------
+// The reference evaluates the n_directions yaw copies of a segment one after the other and then
+// picks one (yaw_planning_evaluator.cpp:48-110, continuous_yaw_planning_evaluator.cpp:35-92).  Here
+// the copies of any number of segments form ONE batch for the device (evaluateOrientations) and the
+// pick is a reduction over the copies' scores (pickOrientation), shared by both evaluators.
 namespace {
-double angleScaled(double angle) {  // tools/defaults.cpp:11-14
+double wrapAngle(double angle) {  // into [0, 2 pi), like tools/defaults.cpp:11-14
   angle = std::fmod(angle, 2.0 * M_PI);
-  return angle + 2.0 * M_PI * (angle < 0);
+  return angle < 0 ? angle + 2.0 * M_PI : angle;
+}
+// Index of the first maximum of `score`, and whether the scores discriminate between orientations at
+// all.  The reference decides the latter with a running minimum that skips every element which raised
+// the running maximum; `seeded` tells whether both start from score[0] (continuous evaluator) or from
+// +-infinity (plain evaluator) — with the latter e.g. strictly increasing scores count as
+// indifferent, which parity keeps.
+struct Pick {
+  int index;
+  bool indifferent;
+};
+Pick pickOrientation(const std::vector<double>& score, bool seeded) {
+  double hi = seeded ? score[0] : std::numeric_limits<double>::lowest();
+  double lo = seeded ? score[0] : std::numeric_limits<double>::max();
+  int best = 0;
+  for (size_t i = seeded ? 1 : 0; i < score.size(); ++i) {
+    const bool raises = score[i] > hi;
+    if (raises) best = static_cast<int>(i);
+    hi = raises ? score[i] : hi;
+    lo = raises ? lo : std::min(lo, score[i]);
+  }
+  return Pick{best, !(hi > lo)};
+}
+double travelYaw(const TrajectorySegment& segment) {
+  const Eigen::Vector3d d = segment.trajectory.back().position_W - segment.trajectory.front().position_W;
+  return wrapAngle(std::atan2(d[1], d[0]));
 }
 }  // namespace
 
@@ -901,19 +1086,19 @@ YawPlanningEvaluator::YawPlanningEvaluator(PlannerI& planner)
     : TrajectoryEvaluator(planner), p_n_directions_(4), p_select_by_value_(false), p_update_range_(-1.0),
       p_update_gain_(0.0), p_batch_orientations_(true), p_keep_visible_voxels_(false) {}
 
-void YawPlanningEvaluator::setupFromParamMap(Module::ParamMap* param_map) {  // yaw_planning_evaluator.cpp:17-38
+void YawPlanningEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
+  // parameter names and defaults of yaw_planning_evaluator.cpp:17-38 (update_range < 0: no updates)
   setParam<int>(param_map, "n_directions", &p_n_directions_, 4);
   setParam<bool>(param_map, "select_by_value", &p_select_by_value_, false);
-  setParam<double>(param_map, "update_range", &p_update_range_, -1.0);  // default is no updates
+  setParam<double>(param_map, "update_range", &p_update_range_, -1.0);
   setParam<double>(param_map, "update_gain", &p_update_gain_, 0.0);
   setParam<bool>(param_map, "batch_orientations", &p_batch_orientations_, true);
   setParam<bool>(param_map, "keep_visible_voxels", &p_keep_visible_voxels_, false);
   planner_.getFactory().registerLinkableModule("YawPlanningEvaluator", this);
   std::string args;
-  const std::string param_ns = (*param_map)["param_namespace"];
-  setParam<std::string>(param_map, "following_evaluator_args", &args, param_ns + "/following_evaluator");
-  following_evaluator_ =
-      planner_.getFactory().createModule<TrajectoryEvaluator>(args, planner_, verbose_modules_);
+  setParam<std::string>(param_map, "following_evaluator_args", &args,
+                        (*param_map)["param_namespace"] + "/following_evaluator");
+  following_evaluator_ = planner_.getFactory().createModule<TrajectoryEvaluator>(args, planner_, verbose_modules_);
   TrajectoryEvaluator::setupFromParamMap(param_map);
 }
 
@@ -926,47 +1111,35 @@ bool YawPlanningEvaluator::checkParamsValid(std::string* error_message) {
 }
 
 void YawPlanningEvaluator::spawnOrientations(TrajectorySegment* traj_in) {
-  const double start_yaw = traj_in->trajectory.front().getYaw();
-  const double original_yaw = traj_in->trajectory.back().getYaw();
-  traj_in->info = std::make_unique<YawPlanningInfo>();
-  auto* info = static_cast<YawPlanningInfo*>(traj_in->info.get());
-  info->active_orientation = 0;
-  info->orientations.reserve(p_n_directions_);
+  auto info = std::make_unique<YawPlanningInfo>();
+  const double from = traj_in->trajectory.front().getYaw(), to = traj_in->trajectory.back().getYaw();
+  info->orientations.resize(p_n_directions_);
   for (int i = 0; i < p_n_directions_; ++i) {
-    info->orientations.push_back(traj_in->shallowCopy());
-    setTrajectoryYaw(&info->orientations.back(), start_yaw, sampleYaw(original_yaw, i));
+    info->orientations[i] = traj_in->shallowCopy();
+    setTrajectoryYaw(&info->orientations[i], from, sampleYaw(to, i));
   }
+  traj_in->info = std::move(info);
 }
 
 bool YawPlanningEvaluator::evaluateOrientations(const std::vector<TrajectorySegment*>& copies) {
   if (copies.empty()) return true;
-  bool done = false;
-  auto* sim = dynamic_cast<SimulatedSensorEvaluator*>(following_evaluator_.get());
-  if (p_batch_orientations_ && sim)
-    done = p_keep_visible_voxels_ ? sim->computeGainsStored(copies) : sim->computeGains(copies);
-  bool ok = true;
-  if (!done)  // the reference's loop (yaw_planning_evaluator.cpp:57-60)
-    for (TrajectorySegment* c : copies) ok = following_evaluator_->computeGain(c) && ok;
-  if (p_select_by_value_)
-    for (TrajectorySegment* c : copies) {
-      following_evaluator_->computeCost(c);
-      following_evaluator_->computeValue(c);
-    }
+  auto* device = p_batch_orientations_ ? dynamic_cast<SimulatedSensorEvaluator*>(following_evaluator_.get()) : nullptr;
+  bool ok = device && (p_keep_visible_voxels_ ? device->computeGainsStored(copies) : device->computeGains(copies));
+  if (!ok) {  // another kind of following evaluator: copy by copy
+    ok = true;
+    for (TrajectorySegment* c : copies) ok &= following_evaluator_->computeGain(c);
+  }
+  for (TrajectorySegment* c : copies) {
+    if (!p_select_by_value_) break;
+    following_evaluator_->computeCost(c);
+    following_evaluator_->computeValue(c);
+  }
   return ok;
-}
-
-bool YawPlanningEvaluator::computeGain(TrajectorySegment* traj_in) {  // yaw_planning_evaluator.cpp:48-71
-  spawnOrientations(traj_in);
-  auto* info = static_cast<YawPlanningInfo*>(traj_in->info.get());
-  std::vector<TrajectorySegment*> copies;
-  for (auto& o : info->orientations) copies.push_back(&o);
-  evaluateOrientations(copies);
-  setBestYaw(traj_in);
-  return true;
 }
 
 bool YawPlanningEvaluator::computeGains(const std::vector<TrajectorySegment*>& segments) {
   std::vector<TrajectorySegment*> copies;
+  copies.reserve(segments.size() * p_n_directions_);
   for (TrajectorySegment* seg : segments) {
     spawnOrientations(seg);
     for (auto& o : static_cast<YawPlanningInfo*>(seg->info.get())->orientations) copies.push_back(&o);
@@ -975,41 +1148,29 @@ bool YawPlanningEvaluator::computeGains(const std::vector<TrajectorySegment*>& s
   for (TrajectorySegment* seg : segments) setBestYaw(seg);
   return ok;
 }
+bool YawPlanningEvaluator::computeGain(TrajectorySegment* traj_in) {
+  computeGains({traj_in});
+  return true;
+}
 
-void YawPlanningEvaluator::setBestYaw(TrajectorySegment* segment) {  // yaw_planning_evaluator.cpp:73-110
+void YawPlanningEvaluator::setBestYaw(TrajectorySegment* segment) {
   auto* info = static_cast<YawPlanningInfo*>(segment->info.get());
-  double min_gain = std::numeric_limits<double>::max();
-  double max_gain = std::numeric_limits<double>::lowest();
-  int max_index = 0;
-  for (size_t i = 0; i < info->orientations.size(); ++i) {
-    const double gain = p_select_by_value_ ? info->orientations[i].value : info->orientations[i].gain;
-    if (gain > max_gain) {
-      max_gain = gain;
-      max_index = static_cast<int>(i);
-    } else if (gain < min_gain) {
-      min_gain = gain;
-    }
-  }
-  double best_yaw;
-  if (max_gain > min_gain) {
-    best_yaw = angleScaled(info->orientations[max_index].trajectory.back().getYaw());
-  } else {  // indifferent, use direction of travel
-    const Eigen::Vector3d direction =
-        segment->trajectory.back().position_W - segment->trajectory.front().position_W;
-    best_yaw = angleScaled(std::atan2(direction[1], direction[0]));
-  }
-  setTrajectoryYaw(segment, segment->trajectory.front().getYaw(), best_yaw);
-  info->active_orientation = max_index;
-  segment->gain = info->orientations[max_index].gain;
+  std::vector<double> score(info->orientations.size());
+  for (size_t i = 0; i < score.size(); ++i)
+    score[i] = p_select_by_value_ ? info->orientations[i].value : info->orientations[i].gain;
+  const Pick pick = pickOrientation(score, false);
+  const TrajectorySegment& chosen = info->orientations[pick.index];
+  setTrajectoryYaw(segment, segment->trajectory.front().getYaw(),
+                   pick.indifferent ? travelYaw(*segment) : wrapAngle(chosen.trajectory.back().getYaw()));
+  info->active_orientation = pick.index;
+  segment->gain = chosen.gain;
   if (p_select_by_value_) {
-    segment->cost = info->orientations[max_index].cost;
-    segment->value = info->orientations[max_index].value;
+    segment->cost = chosen.cost;
+    segment->value = chosen.value;
   }
 }
 
-bool YawPlanningEvaluator::computeCost(TrajectorySegment* traj_in) {
-  return following_evaluator_->computeCost(traj_in);
-}
+bool YawPlanningEvaluator::computeCost(TrajectorySegment* traj_in) { return following_evaluator_->computeCost(traj_in); }
 bool YawPlanningEvaluator::computeValue(TrajectorySegment* traj_in) {
   return following_evaluator_->computeValue(traj_in);
 }
@@ -1017,33 +1178,46 @@ int YawPlanningEvaluator::selectNextBest(TrajectorySegment* traj_in) {
   return following_evaluator_->selectNextBest(traj_in);
 }
 
-bool YawPlanningEvaluator::updateSegment(TrajectorySegment* segment) {  // yaw_planning_evaluator.cpp:128-160
+// Which copies of `segment` an update re-evaluates (yaw_planning_evaluator.cpp:128-160): copies follow
+// their segment when it was re-parented or moved; a non-root segment within update_range of the robot
+// gets the gain of every copy above update_gain again.  Appends them to *again.
+bool YawPlanningEvaluator::collectStaleOrientations(TrajectorySegment* segment, std::vector<TrajectorySegment*>* again) {
   auto* info = dynamic_cast<YawPlanningInfo*>(segment->info.get());
-  if (info) {
-    for (auto& o : info->orientations) {
-      if (o.parent != segment->parent ||
-          !(o.trajectory.front().position_W == segment->trajectory.front().position_W)) {
-        const double original_yaw = o.trajectory.back().getYaw();
-        o.parent = segment->parent;
-        o.trajectory = segment->trajectory;
-        setTrajectoryYaw(&o, segment->trajectory.front().getYaw(), original_yaw);
-      }
-    }
+  if (!info) return false;
+  for (auto& o : info->orientations) {
+    const bool moved = o.parent != segment->parent ||
+                       !(o.trajectory.front().position_W == segment->trajectory.front().position_W);
+    if (!moved) continue;
+    const double yaw = o.trajectory.back().getYaw();
+    o.parent = segment->parent;
+    o.trajectory = segment->trajectory;
+    setTrajectoryYaw(&o, segment->trajectory.front().getYaw(), yaw);
   }
-  if (segment->parent && info) {
-    const double dist = (planner_.getCurrentPosition() - segment->trajectory.back().position_W).norm();
-    if (p_update_range_ == 0.0 || p_update_range_ > dist) {
-      std::vector<TrajectorySegment*> again;
-      for (auto& o : info->orientations)
-        if (o.gain > p_update_gain_) again.push_back(&o);
-      const bool by_value = p_select_by_value_;
-      p_select_by_value_ = false;  // the reference re-evaluates the gain only here
-      evaluateOrientations(again);
-      p_select_by_value_ = by_value;
-    }
-    setBestYaw(segment);
-  }
-  return following_evaluator_->updateSegment(segment);
+  if (!segment->parent) return false;
+  const double dist = (planner_.getCurrentPosition() - segment->trajectory.back().position_W).norm();
+  if (p_update_range_ == 0.0 || p_update_range_ > dist)
+    for (auto& o : info->orientations)
+      if (o.gain > p_update_gain_) again->push_back(&o);
+  return true;
+}
+
+void YawPlanningEvaluator::updateSegments(const std::vector<TrajectorySegment*>& segments,
+                                          std::vector<uint8_t>* alive) {
+  // the stale copies of ALL segments are one batch; gains only, whatever select_by_value says
+  std::vector<TrajectorySegment*> again, repick;
+  for (size_t i = 0; i < segments.size(); ++i)
+    if ((*alive)[i] && collectStaleOrientations(segments[i], &again)) repick.push_back(segments[i]);
+  const bool by_value = p_select_by_value_;
+  p_select_by_value_ = false;
+  evaluateOrientations(again);
+  p_select_by_value_ = by_value;
+  for (TrajectorySegment* seg : repick) setBestYaw(seg);
+  following_evaluator_->updateSegments(segments, alive);
+}
+bool YawPlanningEvaluator::updateSegment(TrajectorySegment* segment) {
+  std::vector<uint8_t> alive(1, 1);
+  updateSegments({segment}, &alive);
+  return alive[0] != 0;
 }
 
 ModuleFactoryRegistry::Registration<SimpleYawPlanningEvaluator> SimpleYawPlanningEvaluator::registration(
@@ -1053,7 +1227,7 @@ void SimpleYawPlanningEvaluator::setupFromParamMap(Module::ParamMap* param_map) 
   YawPlanningEvaluator::setupFromParamMap(param_map);
 }
 double SimpleYawPlanningEvaluator::sampleYaw(double original_yaw, int sample_number) {
-  return angleScaled(original_yaw + static_cast<double>(sample_number) * 2.0 * M_PI / p_n_directions_);
+  return wrapAngle(original_yaw + static_cast<double>(sample_number) * 2.0 * M_PI / p_n_directions_);
 }
 void SimpleYawPlanningEvaluator::setTrajectoryYaw(TrajectorySegment* segment, double /*start_yaw*/,
                                                   double target_yaw) {
@@ -1066,51 +1240,32 @@ void ContinuousYawPlanningEvaluator::setupFromParamMap(Module::ParamMap* param_m
   setParam<bool>(param_map, "visualize_followup", &p_visualize_followup_, true);
   setParam<int>(param_map, "n_sections_fov", &p_n_sections_fov_, 1);
   YawPlanningEvaluator::setupFromParamMap(param_map);
-  p_select_by_value_ = false;  // cannot select by value since views are related
+  p_select_by_value_ = false;  // the sections of one view are not independent: gains only
 }
 bool ContinuousYawPlanningEvaluator::computeGain(TrajectorySegment* traj_in) {
-  YawPlanningEvaluator::computeGain(traj_in);
-  setBestYaw(traj_in);  // (the reference applies it twice as well, continuous_yaw_…cpp:35-42)
-  return true;
+  return YawPlanningEvaluator::computeGain(traj_in);
 }
-void ContinuousYawPlanningEvaluator::setBestYaw(TrajectorySegment* segment) {  // …cpp:44-92
+void ContinuousYawPlanningEvaluator::setBestYaw(TrajectorySegment* segment) {
+  // A view covers n_sections_fov adjacent sections of the yaw circle: its score is the circular
+  // window sum of the section gains (continuous_yaw_planning_evaluator.cpp:44-92), added in the
+  // reference's order (section i first, then i+1 ...).
   auto* info = static_cast<YawPlanningInfo*>(segment->info.get());
-  const int n_ori = static_cast<int>(info->orientations.size());
-  std::vector<double> gains;
-  for (int i = 0; i < n_ori; ++i) {
-    double gain = info->orientations[i].gain;
-    for (int j = 1; j < p_n_sections_fov_; ++j) gain += info->orientations[(i + j) % n_ori].gain;
-    gains.push_back(gain);
-  }
-  double min_gain = gains[0], max_gain = gains[0];
-  int max_index = 0;
-  for (size_t i = 1; i < gains.size(); ++i) {
-    if (gains[i] > max_gain) {
-      max_gain = gains[i];
-      max_index = static_cast<int>(i);
-    } else if (gains[i] < min_gain) {
-      min_gain = gains[i];
-    }
-  }
-  double best_yaw;
-  if (max_gain > min_gain) {
-    best_yaw = angleScaled(info->orientations[max_index].trajectory.back().getYaw() +
-                           static_cast<double>(p_n_sections_fov_ - 1) / p_n_directions_ * M_PI);
-  } else {
-    const Eigen::Vector3d direction =
-        segment->trajectory.back().position_W - segment->trajectory.front().position_W;
-    best_yaw = angleScaled(std::atan2(direction[1], direction[0]));
-  }
-  setTrajectoryYaw(segment, segment->trajectory.front().getYaw(), best_yaw);
-  info->active_orientation = max_index;
-  segment->gain = 0.0;
-  for (int j = 0; j < p_n_sections_fov_; ++j) segment->gain += info->orientations[(max_index + j) % n_ori].gain;
-  // always recompute cost and value, since the trajectory can change
-  following_evaluator_->computeCost(segment);
+  const int n = static_cast<int>(info->orientations.size());
+  std::vector<double> window(n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < p_n_sections_fov_; ++j) window[i] += info->orientations[(i + j) % n].gain;
+  const Pick pick = pickOrientation(window, true);
+  const double centre = info->orientations[pick.index].trajectory.back().getYaw() +
+                        static_cast<double>(p_n_sections_fov_ - 1) / p_n_directions_ * M_PI;
+  setTrajectoryYaw(segment, segment->trajectory.front().getYaw(),
+                   pick.indifferent ? travelYaw(*segment) : wrapAngle(centre));
+  info->active_orientation = pick.index;
+  segment->gain = window[pick.index];
+  following_evaluator_->computeCost(segment);  // the trajectory may have changed
   following_evaluator_->computeValue(segment);
 }
 double ContinuousYawPlanningEvaluator::sampleYaw(double original_yaw, int sample_number) {
-  return angleScaled(original_yaw + static_cast<double>(sample_number) * 2.0 * M_PI / p_n_directions_);
+  return wrapAngle(original_yaw + static_cast<double>(sample_number) * 2.0 * M_PI / p_n_directions_);
 }
 void ContinuousYawPlanningEvaluator::setTrajectoryYaw(TrajectorySegment* segment, double /*start_yaw*/,
                                                       double target_yaw) {

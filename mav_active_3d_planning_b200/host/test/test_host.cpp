@@ -15,8 +15,10 @@
 #include <iostream>
 #include <memory>
 
+#include "../../../include/a3d.h"
 #include "a3d_host/trajectory_evaluator.h"
 #include "a3d_host/voxblox_adapter.h"
+#include "a3d_host/evaluator_updater.h"
 #include "a3d_host/yaml_factory.h"
 
 using namespace active_3d_planning;  // NOLINT
@@ -243,7 +245,7 @@ class TestUpdater : public EvaluatorUpdater {
  public:
   explicit TestUpdater(PlannerI& planner) : EvaluatorUpdater(planner) {}
   void setupFromParamMap(Module::ParamMap*) override {}
-  bool updateSegment(TrajectorySegment*) override { return true; }
+  void updateSegments(const std::vector<TrajectorySegment*>&, std::vector<uint8_t>*) override {}
   static ModuleFactoryRegistry::Registration<TestUpdater> registration;
 };
 ModuleFactoryRegistry::Registration<TestUpdater> TestUpdater::registration("TestUpdater");
@@ -485,6 +487,78 @@ int runAdapter(char** argv) {
   return 0;
 }
 
+// The planner's evaluator update step (online_planner.cpp:679-693) through the updater chain the YAML
+// names: evaluate a chain of segments on the first map, overwrite blocks from the second map file,
+// updateTree(), print what is left.  mode "stored": the segments' lists live on the device
+// (computeGainsStored) — the SimulatedSensorUpdater then re-folds them in one launch.
+int runUpdate(char** argv) {
+  YamlTree tree;
+  std::string err;
+  if (!tree.loadFile(argv[2], &err)) {
+    std::cerr << err << "\n";
+    return 2;
+  }
+  int32_t vps = 0, n_blocks = 0;
+  std::vector<int32_t> idx;
+  std::vector<float> dist, weight;
+  std::vector<uint8_t> obs;
+  if (!loadMap(argv[3], &tree, &vps, &n_blocks, &idx, &dist, &obs, &weight)) return 2;
+  TestPlanner planner(tree);
+  planner.build("/map", "/trajectory_evaluator");
+  auto* vmap = dynamic_cast<map::VoxbloxMap*>(planner.map_.get());
+  auto* eval = planner.evaluator_.get();
+  auto* sim = dynamic_cast<trajectory_evaluator::SimulatedSensorEvaluator*>(eval);
+  if (!vmap || !sim) return 2;
+  vmap->uploadBlocks(n_blocks, idx.data(), dist.data(), obs.data(), weight.data());
+  std::ofstream out(argv[5]);
+  out.precision(17);
+  TrajectorySegment root;
+  std::vector<TrajectorySegment*> segments;
+  loadSegments(argv[4], &root, &segments);
+  std::vector<TrajectorySegment*> below(segments.begin() + 1, segments.end());
+  const bool stored = std::strcmp(argv[7], "stored") == 0;
+  if (stored) {
+    out << "ok " << sim->computeGainsStored(below) << "\n";
+  } else {
+    for (TrajectorySegment* s : below) sim->computeGain(s);
+  }
+  for (TrajectorySegment* s : below) {
+    eval->computeCost(s);
+    eval->computeValue(s);
+  }
+  for (size_t s = 0; s < below.size(); ++s)
+    out << "before " << s << " " << below[s]->gain << " " << below[s]->cost << " " << below[s]->value << "\n";
+  // the map changes
+  YamlTree unused;
+  int32_t vps2 = 0, n2 = 0;
+  std::vector<int32_t> idx2;
+  std::vector<float> dist2, weight2;
+  std::vector<uint8_t> obs2;
+  if (!loadMap(argv[6], &unused, &vps2, &n2, &idx2, &dist2, &obs2, &weight2)) return 2;
+  vmap->uploadBlocks(n2, idx2.data(), dist2.data(), obs2.data(), weight2.data());
+  planner.position_ = root.trajectory.back().position_W;
+  sim->takeGainTimeMs();
+  const uint64_t launches0 = a3d_kernel_launches(vmap->context());
+  const int removed = eval->updateTree(&root);
+  out << "removed " << removed << " launches " << (a3d_kernel_launches(vmap->context()) - launches0)
+      << " gain_ms " << sim->takeGainTimeMs() << "\n";
+  int depth = 0;
+  for (TrajectorySegment* s = &root; !s->children.empty(); s = s->children[0].get(), ++depth) {
+    const TrajectorySegment& c = *s->children[0];
+    out << "after " << depth << " " << c.gain << " " << c.cost << " " << c.value << "\n";
+  }
+  // the per-segment contract on what is left (unchanged map: same numbers)
+  for (TrajectorySegment* s = &root; !s->children.empty(); s = s->children[0].get())
+    out << "single " << eval->updateSegment(s->children[0].get()) << " " << s->children[0]->gain << "\n";
+  if (auto* cam = dynamic_cast<sensor_model::CameraModel*>(sim->sensorModel())) {
+    double mean = 0, stddev = 0;
+    size_t count = 0;
+    cam->castTimeStats(&mean, &stddev, &count);
+    out << "casttime " << mean << " " << stddev << " " << count << "\n";
+  }
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -493,10 +567,12 @@ int main(int argc, char** argv) {
     if (argc >= 6 && std::strcmp(argv[1], "gains") == 0) return runGains(argv);
     if (argc >= 6 && std::strcmp(argv[1], "yaw") == 0) return runYaw(argv);
     if (argc >= 6 && std::strcmp(argv[1], "adapter") == 0) return runAdapter(argv);
+    if (argc >= 8 && std::strcmp(argv[1], "update") == 0) return runUpdate(argv);
   } catch (const std::exception& e) {
     std::cerr << "exception: " << e.what() << "\n";
     return 3;
   }
-  std::cerr << "usage: test_host config <yaml> [ns] | gains|yaw|adapter <yaml> <map.bin> <segments.bin> <out.txt>\n";
+  std::cerr << "usage: test_host config <yaml> [ns] | gains|yaw|adapter <yaml> <map.bin> <segments.bin> <out.txt> | "
+               "update <yaml> <map.bin> <segments.bin> <out.txt> <map2.bin> stored|host\n";
   return 1;
 }

@@ -200,8 +200,10 @@ def test_modules_from_yaml_match_oracle_voxeltype_parents(built, room02, tmp_pat
         assert np.isclose(gain, want["gain"][s], rtol=1e-5, atol=0)
         assert r["refold"][s] == 1
     assert want["n_visible"][1] < want["n_visible"][0]    # parents did clear something
-    # the batch API refuses clear_from_parents
-    assert all(v[0] == 0 for v in r["batch"].values())
+    # the batch call subtracts the ancestors' lists on the device (a3d_compute_gains_tree)
+    for s in range(n_seg):
+        ok, gain = r["batch"][s]
+        assert ok == 1 and np.isclose(gain, want["gain"][s], rtol=1e-5, atol=0)
 
 
 def _yaw_of(q):
@@ -343,3 +345,145 @@ def test_voxblox_layer_adapter(built, room02, tmp_path):
     want2 = oc.compute_gains(ep, pos, quat)["gain"]
     got2 = {int(l[1]): float(l[3]) for l in lines if l[0] == "batch2"}
     assert [got2[s] for s in range(5)] == list(want2)
+
+
+def _changed_map(m, seed=5):
+    """the same blocks with a third of them observed free space now (what an integrator update does)"""
+    import dataclasses
+    rng = np.random.default_rng(seed)
+    sel = rng.choice(m.n_blocks, m.n_blocks // 3, replace=False)
+    dist, obs = m.dist.copy(), m.observed.copy()
+    dist[sel] = 1.0
+    obs[sel] = 1
+    return dataclasses.replace(m, dist=dist, observed=obs)
+
+
+def parse_update(path):
+    res = {"before": {}, "after": {}, "single": []}
+    for line in open(path):
+        t = line.split()
+        if t[0] in ("before", "after"):
+            res[t[0]][int(t[1])] = tuple(float(x) for x in t[2:5])
+        elif t[0] == "removed":
+            res["removed"], res["launches"], res["gain_ms"] = int(t[1]), int(t[3]), float(t[5])
+        elif t[0] == "single":
+            res["single"].append((int(t[1]), float(t[2])))
+        elif t[0] == "casttime":
+            res["casttime"] = (float(t[1]), float(t[2]), int(t[3]))
+        elif t[0] == "ok":
+            res["ok"] = int(t[1])
+    return res
+
+
+@pytest.mark.gpu
+def test_simulated_sensor_updater_refolds_the_tree_in_one_launch(built, room02, tmp_path):
+    """evaluator_updater: SimulatedSensorUpdater -> PruneDirect (simulated_sensor_updater.cpp:18-22,
+    prune_direct.cpp:33-39) through TrajectoryEvaluator::updateTree: the gain of every stored list
+    against the changed map equals the oracle's fold of the SAME lists, the chain is cut where the gain
+    falls below the bound, and the whole tree costs one re-fold launch."""
+    from mav_active_3d_planning_b200 import synth
+    from oracle import oracle_py as O
+    n = 7
+    pos, quat = synth.candidate_views(room02, n, seed=61)
+    m2 = _changed_map(room02)
+    cam = dict(resolution_x=320, resolution_y=240, focal_length=160.0, ray_length=5.0, downsampling_factor=2.0)
+    ep = O.eval_params("VoxelTypeEvaluator", gain_unknown=1.0, gain_occupied=0.5, gain_free=0.25)
+    om1, om2 = O.OracleMap.from_synth(room02), O.OracleMap.from_synth(m2)
+    oc = om1.caster("IterativeRayCaster", **cam)
+
+    def refolded(i):
+        lst, _ = oc.visible_voxels(pos[i:i + 1], quat[i:i + 1])
+        return om2.gain_from_voxels(ep, lst)[0]
+    # order the chain below the root by falling gain-after-the-change, so that a bound cuts it in the middle
+    order = [0] + sorted(range(1, n), key=refolded, reverse=True)
+    pos, quat = pos[order], quat[order]
+    after = np.array([refolded(i) for i in range(1, n)])
+    before = oc.compute_gains(ep, pos[1:], quat[1:])["gain"]
+    assert np.any(after != before)
+    cut = (n - 1) // 2
+    assert after[cut - 1] > after[cut]
+    bound = 0.5 * float(after[cut - 1] + after[cut])
+    mp, sp = write_inputs(str(tmp_path), room02, pos, quat, 1, 0)
+    d2 = os.path.join(str(tmp_path), "m2")
+    os.makedirs(d2)
+    mp2, _ = write_inputs(d2, m2, pos, quat, 1, 0)
+    yml = os.path.join(str(tmp_path), "planner.yaml")
+    open(yml, "w").write(open(os.path.join(GOLD, "planner_update_sensor.yaml")).read()
+                         .replace("minimum_gain: 1200.0", f"minimum_gain: {bound!r}"))
+    out = os.path.join(str(tmp_path), "update.txt")
+    subprocess.run([EXE, "update", yml, mp, sp, out, mp2, "stored"], check=True, timeout=300)
+    r = parse_update(out)
+    assert r["ok"] == 1
+    for s in range(n - 1):
+        assert np.isclose(r["before"][s][0], before[s], rtol=1e-5, atol=0)
+    assert r["removed"] == (n - 1) - cut and sorted(r["after"]) == list(range(cut))
+    for s in range(cut):
+        assert np.isclose(r["after"][s][0], after[s], rtol=1e-5, atol=0)
+        assert r["after"][s][1:] == r["before"][s][1:]          # this chain does not touch cost / value
+    assert r["launches"] <= 2                                   # the tree is one re-fold, not n
+    assert r["gain_ms"] >= 0.0
+    assert [x[0] for x in r["single"]] == [1] * cut
+    assert np.allclose([x[1] for x in r["single"]], after[:cut], rtol=1e-5, atol=0)
+    # `test: true` of the sensor model: one timing entry per view cast (camera_model.cpp:31-54)
+    mean, std, count = r["casttime"]
+    assert count == n - 1 and mean > 0.0
+
+
+@pytest.mark.gpu
+def test_update_all_recasts_the_tree_as_one_batch(built, room02, tmp_path):
+    """evaluator_updater: ConstrainedUpdater -> UpdateAll (constrained_updater.cpp:17-30,
+    update_all.cpp:16-27): segments within update_range of the robot get gain, cost and value again —
+    one cast for all of them —, the others keep theirs; nothing is dropped."""
+    from mav_active_3d_planning_b200 import synth
+    from oracle import oracle_py as O
+    n = 9
+    pos, quat = synth.candidate_views(room02, n, seed=67)
+    m2 = _changed_map(room02, seed=9)
+    mp, sp = write_inputs(str(tmp_path), room02, pos, quat, 1, 0)
+    d2 = os.path.join(str(tmp_path), "m2")
+    os.makedirs(d2)
+    mp2, _ = write_inputs(d2, m2, pos, quat, 1, 0)
+    cam = dict(resolution_x=320, resolution_y=240, focal_length=160.0, ray_length=5.0, downsampling_factor=2.0)
+    ep = O.eval_params("NaiveEvaluator")
+    om1, om2 = O.OracleMap.from_synth(room02), O.OracleMap.from_synth(m2)
+    before = om1.caster("SimpleRayCaster", **cam).compute_gains(ep, pos[1:], quat[1:])["gain"]
+    recast = om2.caster("SimpleRayCaster", **cam).compute_gains(ep, pos[1:], quat[1:])["gain"]
+    out = os.path.join(str(tmp_path), "update.txt")
+    subprocess.run([EXE, "update", os.path.join(GOLD, "planner_update_all.yaml"), mp, sp, out, mp2, "host"],
+                   check=True, timeout=300)
+    r = parse_update(out)
+    near = (np.linalg.norm(pos[1:] - pos[0], axis=1) <= 6.0) & (before > 0.0)
+    assert near.any() and (~near).any() and np.any(recast[near] != before[near])
+    assert r["removed"] == 0 and sorted(r["after"]) == list(range(n - 1))
+    for s in range(n - 1):
+        want = recast[s] if near[s] else before[s]
+        gain, cost, value = r["after"][s]
+        assert gain == want and cost == r["before"][s][1] and value == want - 100.0 * cost
+    assert r["launches"] <= 8      # one batch cast (kernel chain + flagged-segment pass), not one per segment
+
+
+@pytest.mark.gpu
+def test_host_batch_gains_sharded_over_two_gpus(built, room02, tmp_path):
+    """map: devices: "0,1" — VoxbloxMap holds an a3d_group (replicated mirror, NCCL broadcast of the
+    upload), SimulatedSensorEvaluator::computeGains shards the segments over both GPUs and gathers the
+    gains: same numbers as one GPU, as the oracle."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from mav_active_3d_planning_b200 import synth
+    from oracle import oracle_py as O
+    pos, quat = synth.candidate_views(room02, 6, seed=3)
+    mp, sp = write_inputs(str(tmp_path), room02, pos, quat, 1, 0)
+    yml = os.path.join(str(tmp_path), "planner.yaml")
+    open(yml, "w").write(open(os.path.join(GOLD, "planner_naive_iterative.yaml")).read() +
+                         '\nmap:\n  devices: "0,1"\n')
+    out = os.path.join(str(tmp_path), "out.txt")
+    subprocess.run([EXE, "gains", yml, mp, sp, out], check=True, timeout=300)
+    r = parse_out(out)
+    om = O.OracleMap.from_synth(room02)
+    oc = om.caster("IterativeRayCaster", resolution_x=320, resolution_y=240, focal_length=160.0, ray_length=5.0)
+    ep = O.eval_params("NaiveEvaluator", bounding_volume=dict(x_min=2, x_max=18, y_min=2, y_max=18, z_min=0.5, z_max=7))
+    want = oc.compute_gains(ep, pos, quat)
+    for s in range(6):
+        assert r["batch"][s] == (1, want["gain"][s])          # sharded batch call
+        assert r["single"][s][0] == 1 and r["single"][s][1] == want["gain"][s]   # per-segment call, GPU 0
