@@ -150,6 +150,12 @@ int a3d_map_config(a3d_ctx* ctx, float voxel_size, int voxels_per_side);
    merge of voxblox::EsdfServer (run_experiment.launch:180-181). */
 int a3d_map_upload_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* esdf_dist,
                           const uint8_t* esdf_observed, const float* tsdf_weight);
+/* TSDF weights alone (what a `tsdf_map_in` layer message carries, run_experiment.launch:181) for blocks
+   the mirror already holds: n blocks, vps^3 floats each, voxblox's linear voxel order.  Blocks
+   without an ESDF block on the device are skipped; applied_out (nullable, n bytes) tells which ones
+   were written.  Distances, observed flags and the meta words are untouched. */
+int a3d_map_upload_weights(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* tsdf_weight,
+                           uint8_t* applied_out);
 /* Same with payload pointers in device memory (e.g. the receive buffer of an NCCL broadcast);
    block_idx stays on the host. */
 int a3d_map_upload_blocks_dev(a3d_ctx* ctx, int n, const int32_t* block_idx,

@@ -31,7 +31,7 @@ _EVAL_KINDS = {"VoxelTypeEvaluator": EVAL_VOXEL_TYPE, "NaiveEvaluator": EVAL_NAI
 # every symbol include/a3d.h declares
 EXPORTS = [
     "a3d_ctx_create", "a3d_ctx_destroy", "a3d_last_error", "a3d_ctx_stream", "a3d_last_kernel_ms", "a3d_last_stage_ms",
-    "a3d_kernel_launches", "a3d_set_option", "a3d_last_cast_kernel", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev",
+    "a3d_kernel_launches", "a3d_set_option", "a3d_last_cast_kernel", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev", "a3d_map_upload_weights",
     "a3d_map_remove_blocks", "a3d_map_clear", "a3d_map_num_blocks", "a3d_map_voxel_size",
     "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
     "a3d_map_distance", "a3d_map_traversable", "a3d_caster_create", "a3d_caster_destroy", "a3d_caster_get_info",
@@ -157,6 +157,7 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_map_config.argtypes = [vp, C.c_float, C.c_int]
     lib.a3d_map_upload_blocks.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     lib.a3d_map_upload_blocks_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    lib.a3d_map_upload_weights.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.a3d_map_remove_blocks.argtypes = [vp, C.c_int, vp]
     lib.a3d_map_clear.argtypes = [vp]
     lib.a3d_map_num_blocks.argtypes = [vp]
@@ -293,6 +294,15 @@ class Context:
         block_idx = np.ascontiguousarray(block_idx, np.int32)
         self._ck(self.lib.a3d_map_upload_blocks_dev(self.h, block_idx.shape[0], _ptr(block_idx),
                                                     dist_ptr, observed_ptr, weight_ptr or None))
+
+    def upload_weights(self, block_idx, weight):
+        """TSDF weights alone, for blocks the mirror holds; returns the mask of blocks written."""
+        block_idx = np.ascontiguousarray(block_idx, np.int32)
+        weight = np.ascontiguousarray(weight, np.float32)
+        applied = np.zeros(block_idx.shape[0], np.uint8)
+        self._ck(self.lib.a3d_map_upload_weights(self.h, block_idx.shape[0], _ptr(block_idx), _ptr(weight),
+                                                 _ptr(applied)))
+        return applied.astype(bool)
 
     def upload_map(self, m):
         """Upload a synth.SynthMap."""

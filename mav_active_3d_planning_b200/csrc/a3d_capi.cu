@@ -1043,6 +1043,28 @@ int a3d_map_upload_blocks_dev(a3d_ctx* ctx, int n, const int32_t* block_idx, con
   return upload_blocks_impl(ctx, n, block_idx, dist_dev, obs_dev, w_dev, true);
 }
 
+int a3d_map_upload_weights(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* tsdf_weight,
+                           uint8_t* applied_out) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
+  if (n < 0 || (n > 0 && (!block_idx || !tsdf_weight))) return ctx->fail(A3D_ERR_INVALID, "null block payload");
+  if (n == 0) return A3D_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc = slab_reserve(ctx, static_cast<size_t>(std::max(ctx->next_slot, 1)), true);
+  if (rc) return rc;
+  const size_t nv = static_cast<size_t>(ctx->nv);
+  for (int i = 0; i < n; ++i) {
+    const Key3 k{block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2]};
+    auto it = ctx->slots.find(k);
+    if (applied_out) applied_out[i] = it != ctx->slots.end();
+    if (it == ctx->slots.end()) continue;  // no ESDF block there yet: the caller keeps it
+    CK(cudaMemcpyAsync(ctx->d_weight + static_cast<size_t>(it->second) * nv, tsdf_weight + static_cast<size_t>(i) * nv,
+                       nv * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return A3D_OK;
+}
+
 int a3d_map_remove_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx) {
   if (!ctx) return A3D_ERR_INVALID;
   if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");

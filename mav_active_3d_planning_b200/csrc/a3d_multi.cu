@@ -84,6 +84,26 @@ struct Buf {  // grow-only device buffer on a fixed device
   }
 };
 
+struct Pinned {  // grow-only page-locked host buffer: copies from / to it are truly asynchronous
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max<size_t>(n + n / 2, 4096);
+    const cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocPortable);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
 constexpr int kRecWords = 5;  // per segment: gain bits | n_visible | n_samples | digest | set digest
 
 struct Device {
@@ -95,12 +115,14 @@ struct Device {
   Buf<double> pos, quat, origin;
   Buf<int32_t> first;
   Buf<unsigned long long> rec, all;  // this GPU's records (per×5 words) / everyone's
+  Pinned stage;                      // this GPU's share of a batch: pos | quat | origin | first
 };
 
 }  // namespace
 
 struct a3d_group {
   std::vector<Device> dev;
+  Pinned result;  // gathered records on their way back to the caller
   std::string err;
   int block = 64;  // segments are dealt to the GPUs in blocks of this many
   float voxel_size = 0.0f;
@@ -202,8 +224,10 @@ void a3d_group_destroy(a3d_group* g) {
     d.first.release();
     d.rec.release();
     d.all.release();
+    d.stage.release();
     a3d_ctx_destroy(d.ctx);
   }
+  g->result.release();
   delete g;
 }
 
@@ -391,39 +415,61 @@ int a3d_group_compute_gains(a3d_group* g, const a3d_group_caster* caster, const 
   for (int i = 0; i < N; ++i) per = std::max(per, mine[i].size());
   const bool want_dig = digests_out != nullptr, want_sdig = set_digests_out != nullptr;
 
-  // enqueue on every GPU: inputs, cast, then (stream order) the all-gather
-  std::vector<std::vector<double>> hp(N), hq(N), ho(N);
-  std::vector<std::vector<int32_t>> hf(N);
+  // Every GPU's share is laid out in page-locked memory first (whole blocks of segments at a time:
+  // their views are contiguous in the caller's arrays), then all GPUs are started back to back with
+  // asynchronous copies — no GPU waits for the host to prepare another one's share.
+  std::vector<int> n_views_of(N, 0);
   for (int i = 0; i < N; ++i) {
     Device& d = g->dev[i];
     const int ns = static_cast<int>(mine[i].size());
-    hf[i].assign(static_cast<size_t>(ns) + 1, 0);
-    for (int k = 0; k < ns; ++k) {
-      const int s = mine[i][k];
-      for (int v = first[s]; v < first[s + 1]; ++v) {
-        hp[i].insert(hp[i].end(), pos + 3 * v, pos + 3 * v + 3);
-        hq[i].insert(hq[i].end(), quat + 4 * v, quat + 4 * v + 4);
-      }
-      hf[i][k + 1] = hf[i][k] + (first[s + 1] - first[s]);
-      if (seg_origin) ho[i].insert(ho[i].end(), seg_origin + 3 * s, seg_origin + 3 * s + 3);
+    int nvw = 0;
+    for (int s : mine[i]) nvw += first[s + 1] - first[s];
+    n_views_of[i] = nvw;
+    const size_t b_pos = 24 * static_cast<size_t>(nvw), b_quat = 32 * static_cast<size_t>(nvw),
+                 b_org = seg_origin ? 24 * static_cast<size_t>(ns) : 0, b_first = 4 * (static_cast<size_t>(ns) + 1);
+    GCK(cudaSetDevice(d.id));
+    GCK(d.stream ? cudaStreamSynchronize(d.stream) : cudaSuccess);  // (the staging of the previous call is free)
+    GCK(d.stage.reserve(b_pos + b_quat + b_org + b_first));
+    double* hp = reinterpret_cast<double*>(d.stage.p);
+    double* hq = reinterpret_cast<double*>(d.stage.p + b_pos);
+    double* ho = reinterpret_cast<double*>(d.stage.p + b_pos + b_quat);
+    int32_t* hf = reinterpret_cast<int32_t*>(d.stage.p + b_pos + b_quat + b_org);
+    hf[0] = 0;
+    size_t vw = 0;
+    for (int k = 0; k < ns;) {
+      // a run of consecutive segments = one run of consecutive views
+      int k1 = k + 1;
+      while (k1 < ns && mine[i][k1] == mine[i][k1 - 1] + 1) ++k1;
+      const int s0 = mine[i][k], s1 = mine[i][k1 - 1] + 1;
+      const size_t nv_run = static_cast<size_t>(first[s1] - first[s0]);
+      std::memcpy(hp + 3 * vw, pos + 3 * static_cast<size_t>(first[s0]), 24 * nv_run);
+      std::memcpy(hq + 4 * vw, quat + 4 * static_cast<size_t>(first[s0]), 32 * nv_run);
+      if (seg_origin) std::memcpy(ho + 3 * static_cast<size_t>(k), seg_origin + 3 * static_cast<size_t>(s0), 24 * static_cast<size_t>(s1 - s0));
+      for (int s = s0; s < s1; ++s, ++k) hf[k + 1] = hf[k] + (first[s + 1] - first[s]);
+      vw += nv_run;
     }
-    const int nvw = hf[i][ns];
+  }
+  for (int i = 0; i < N; ++i) {
+    Device& d = g->dev[i];
+    const int ns = static_cast<int>(mine[i].size()), nvw = n_views_of[i];
+    const size_t b_pos = 24 * static_cast<size_t>(nvw), b_quat = 32 * static_cast<size_t>(nvw),
+                 b_org = seg_origin ? 24 * static_cast<size_t>(ns) : 0, b_first = 4 * (static_cast<size_t>(ns) + 1);
     GCK(cudaSetDevice(d.id));
     GCK(d.pos.reserve(3 * static_cast<size_t>(std::max(nvw, 1))));
     GCK(d.quat.reserve(4 * static_cast<size_t>(std::max(nvw, 1))));
-    GCK(d.first.reserve(hf[i].size()));
+    GCK(d.first.reserve(static_cast<size_t>(ns) + 1));
     GCK(d.rec.reserve(per * kRecWords));
     GCK(d.all.reserve(per * kRecWords * N));
     GCK(cudaMemsetAsync(d.rec.p, 0, per * kRecWords * 8, d.stream));
     if (nvw > 0) {
-      GCK(cudaMemcpyAsync(d.pos.p, hp[i].data(), hp[i].size() * 8, cudaMemcpyHostToDevice, d.stream));
-      GCK(cudaMemcpyAsync(d.quat.p, hq[i].data(), hq[i].size() * 8, cudaMemcpyHostToDevice, d.stream));
+      GCK(cudaMemcpyAsync(d.pos.p, d.stage.p, b_pos, cudaMemcpyHostToDevice, d.stream));
+      GCK(cudaMemcpyAsync(d.quat.p, d.stage.p + b_pos, b_quat, cudaMemcpyHostToDevice, d.stream));
     }
-    GCK(cudaMemcpyAsync(d.first.p, hf[i].data(), hf[i].size() * 4, cudaMemcpyHostToDevice, d.stream));
+    GCK(cudaMemcpyAsync(d.first.p, d.stage.p + b_pos + b_quat + b_org, b_first, cudaMemcpyHostToDevice, d.stream));
     const double* org_dev = nullptr;
     if (seg_origin && ns > 0) {
-      GCK(d.origin.reserve(ho[i].size()));
-      GCK(cudaMemcpyAsync(d.origin.p, ho[i].data(), ho[i].size() * 8, cudaMemcpyHostToDevice, d.stream));
+      GCK(d.origin.reserve(3 * static_cast<size_t>(ns)));
+      GCK(cudaMemcpyAsync(d.origin.p, d.stage.p + b_pos + b_quat, b_org, cudaMemcpyHostToDevice, d.stream));
       org_dev = d.origin.p;
     }
     if (ns > 0) {
@@ -450,15 +496,17 @@ int a3d_group_compute_gains(a3d_group* g, const a3d_group_caster* caster, const 
     NCK(g_nccl.GroupEnd());
     gathered = g->dev[0].all.p;
   }
-  std::vector<unsigned long long> host(per * kRecWords * N);
+  const size_t n_words = per * kRecWords * static_cast<size_t>(N);
   GCK(cudaSetDevice(g->dev[0].id));
-  GCK(cudaMemcpyAsync(host.data(), gathered, host.size() * 8, cudaMemcpyDeviceToHost, g->dev[0].stream));
+  GCK(g->result.reserve(n_words * 8));
+  const unsigned long long* const host = reinterpret_cast<const unsigned long long*>(g->result.p);
+  GCK(cudaMemcpyAsync(g->result.p, gathered, n_words * 8, cudaMemcpyDeviceToHost, g->dev[0].stream));
   for (auto& d : g->dev) {
     GCK(cudaSetDevice(d.id));
     GCK(cudaStreamSynchronize(d.stream));
   }
   for (int i = 0; i < N; ++i) {
-    const unsigned long long* r = host.data() + static_cast<size_t>(i) * per * kRecWords;
+    const unsigned long long* r = host + static_cast<size_t>(i) * per * kRecWords;
     for (size_t k = 0; k < mine[i].size(); ++k) {
       const int s = mine[i][k];
       std::memcpy(&gains_out[s], &r[k], 8);

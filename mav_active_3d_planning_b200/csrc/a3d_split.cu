@@ -584,8 +584,6 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
   const uint32_t* const tab = tab_n ? s_tab : nullptr;
   cta_prologue(m, e, sh, s_tab, tab_n);
   const int bv_mode = sh.bvg.mode;
-  const double step = c.ray_step;
-  const double d_mark_end = c.split[n - 1];
 
   for (int view = blockIdx.x * kWarps + warp; view < n_views; view += gridDim.x * kWarps) {
     load_view(sh, sc, view, warp, lane);

@@ -72,6 +72,8 @@ class VoxbloxMap : public TSDFMap {
   // insert-or-overwrite n blocks; voxel order x + vps*(y + vps*z); tsdf_weight may be null
   bool uploadBlocks(int n, const int32_t* block_idx, const float* esdf_distance,
                     const uint8_t* esdf_observed, const float* tsdf_weight);
+  // TSDF weights alone, for blocks the mirror holds (a3d_map_upload_weights)
+  bool uploadWeights(int n, const int32_t* block_idx, const float* tsdf_weight);
   bool removeBlocks(int n, const int32_t* block_idx);
   int64_t numBlocks() const;
   int voxelsPerSide() const { return p_voxels_per_side_; }

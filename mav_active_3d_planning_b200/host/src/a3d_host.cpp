@@ -206,6 +206,17 @@ bool VoxbloxMap::uploadBlocks(int n, const int32_t* block_idx, const float* esdf
         "a3d_map_upload_blocks");
   return true;
 }
+bool VoxbloxMap::uploadWeights(int n, const int32_t* block_idx, const float* tsdf_weight) {
+  // every replica of a group holds the weights (the group has no weights-only broadcast: one plain
+  // upload per device; TSDF updates are a few blocks per planner iteration)
+  const int n_dev = numDevices();
+  for (int i = 0; i < n_dev; ++i) {
+    a3d_ctx* c = group_ ? a3d_group_ctx(group_, i) : ctx_;
+    if (a3d_map_upload_weights(c, n, block_idx, tsdf_weight, nullptr) != A3D_OK)
+      throw std::runtime_error(std::string("a3d_map_upload_weights: ") + a3d_last_error(c));
+  }
+  return true;
+}
 bool VoxbloxMap::removeBlocks(int n, const int32_t* block_idx) {
   if (group_) {
     if (a3d_group_map_remove_blocks(group_, n, block_idx) != A3D_OK)

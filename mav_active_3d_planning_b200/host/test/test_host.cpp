@@ -19,6 +19,7 @@
 #include "a3d_host/trajectory_evaluator.h"
 #include "a3d_host/voxblox_adapter.h"
 #include "a3d_host/evaluator_updater.h"
+#include "a3d_host/layer_msg.h"
 #include "a3d_host/yaml_factory.h"
 
 using namespace active_3d_planning;  // NOLINT
@@ -559,6 +560,84 @@ int runUpdate(char** argv) {
   return 0;
 }
 
+// voxblox_msgs/Layer messages → device mirror: the map file is encoded into ESDF and TSDF layer
+// messages (encoder written from the message description in a3d_host/layer_msg.h), sent in the order a
+// running system may deliver them (TSDF of some blocks first, ESDF in two messages, the remaining TSDF),
+// then the evaluator of the YAML runs on the mirror.
+int runLayer(char** argv) {
+  YamlTree tree;
+  std::string err;
+  if (!tree.loadFile(argv[2], &err)) {
+    std::cerr << err << "\n";
+    return 2;
+  }
+  int32_t vps = 0, n_blocks = 0;
+  std::vector<int32_t> idx;
+  std::vector<float> dist, weight;
+  std::vector<uint8_t> obs;
+  if (!loadMap(argv[3], &tree, &vps, &n_blocks, &idx, &dist, &obs, &weight)) return 2;
+  TestPlanner planner(tree);
+  planner.build("/map", "/trajectory_evaluator");
+  auto* vmap = dynamic_cast<map::VoxbloxMap*>(planner.map_.get());
+  auto* sim = dynamic_cast<trajectory_evaluator::SimulatedSensorEvaluator*>(planner.evaluator_.get());
+  if (!vmap || !sim) return 2;
+  const size_t nv = static_cast<size_t>(vps) * vps * vps;
+  auto encode = [&](const char* type, int b0, int b1, uint8_t action) {
+    map::LayerMsg msg;
+    msg.voxel_size = vmap->getVoxelSize();
+    msg.voxels_per_side = static_cast<uint32_t>(vps);
+    msg.layer_type = type;
+    msg.action = action;
+    const bool esdf = std::strcmp(type, "esdf") == 0;
+    for (int b = b0; b < b1; ++b) {
+      map::BlockMsg bm;
+      bm.x_index = idx[3 * b];
+      bm.y_index = idx[3 * b + 1];
+      bm.z_index = idx[3 * b + 2];
+      for (size_t i = 0; i < nv; ++i) {
+        uint32_t w0, w1;
+        std::memcpy(&w0, &dist[b * nv + i], 4);
+        bm.data.push_back(w0);
+        if (esdf) {
+          // observed in the low byte, a parent direction in the upper three (ignored by the mirror)
+          bm.data.push_back((obs[b * nv + i] ? 1u : 0u) | (static_cast<uint32_t>((i * 2654435761u) >> 8) << 8));
+        } else {
+          std::memcpy(&w1, &weight[b * nv + i], 4);
+          bm.data.push_back(w1);
+          bm.data.push_back(0x80FF40FFu);  // colour
+        }
+      }
+      msg.blocks.push_back(std::move(bm));
+    }
+    return msg;
+  };
+  std::ofstream out(argv[5]);
+  out.precision(17);
+  map::LayerReceiver rx(vmap);
+  const int half = n_blocks / 2, third = n_blocks / 3;
+  out << "tsdf_first " << rx.onTsdfLayer(encode("tsdf", 0, half, map::kLayerUpdate)) << " pending "
+      << rx.pendingWeightBlocks() << "\n";
+  out << "esdf_a " << rx.onEsdfLayer(encode("esdf", 0, third, map::kLayerUpdate)) << "\n";
+  out << "esdf_b " << rx.onEsdfLayer(encode("esdf", third, n_blocks, map::kLayerUpdate)) << " pending "
+      << rx.pendingWeightBlocks() << "\n";
+  out << "tsdf_rest " << rx.onTsdfLayer(encode("tsdf", half, n_blocks, map::kLayerUpdate)) << " pending "
+      << rx.pendingWeightBlocks() << "\n";
+  out << "blocks " << vmap->numBlocks() << " received " << rx.blocksReceived() << "\n";
+  // a message of another layer type / geometry is refused
+  map::LayerMsg bad = encode("esdf", 0, 1, map::kLayerUpdate);
+  bad.voxels_per_side += 1;
+  out << "refused " << !rx.onEsdfLayer(bad) << " " << !rx.onTsdfLayer(encode("esdf", 0, 1, map::kLayerUpdate)) << "\n";
+  TrajectorySegment root;
+  std::vector<TrajectorySegment*> segments;
+  loadSegments(argv[4], &root, &segments);
+  sim->computeGains(segments);
+  for (size_t s = 0; s < segments.size(); ++s) out << "batch " << s << " 1 " << segments[s]->gain << "\n";
+  out << "weight " << vmap->getVoxelWeight(segments[0]->trajectory.back().position_W) << "\n";
+  // ACTION_RESET: the sender's layer replaces the mirror
+  out << "reset " << rx.onEsdfLayer(encode("esdf", 0, third, map::kLayerReset)) << " blocks " << vmap->numBlocks() << "\n";
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -568,11 +647,12 @@ int main(int argc, char** argv) {
     if (argc >= 6 && std::strcmp(argv[1], "yaw") == 0) return runYaw(argv);
     if (argc >= 6 && std::strcmp(argv[1], "adapter") == 0) return runAdapter(argv);
     if (argc >= 8 && std::strcmp(argv[1], "update") == 0) return runUpdate(argv);
+    if (argc >= 6 && std::strcmp(argv[1], "layer") == 0) return runLayer(argv);
   } catch (const std::exception& e) {
     std::cerr << "exception: " << e.what() << "\n";
     return 3;
   }
-  std::cerr << "usage: test_host config <yaml> [ns] | gains|yaw|adapter <yaml> <map.bin> <segments.bin> <out.txt> | "
+  std::cerr << "usage: test_host config <yaml> [ns] | gains|yaw|adapter|layer <yaml> <map.bin> <segments.bin> <out.txt> | "
                "update <yaml> <map.bin> <segments.bin> <out.txt> <map2.bin> stored|host\n";
   return 1;
 }

@@ -1,7 +1,14 @@
 /*
  * a3d_oracle.cpp — CPU oracle for the view-gain hot path.  TEST INFRASTRUCTURE ONLY
- * (see a3d_oracle.h).  PARITY UNPINNED (no reference tests / goldens exist; reference not
- * buildable here).
+ * (see a3d_oracle.h).
+ *
+ * PINNED against the reference's own code: oracle/_ref compiles the unmodified reference sources of
+ * the path (ref_driver.cpp lists them) behind this same API, and tests/test_ref_pin.py demands
+ * `_ref == oracle` bit for bit (ordered lists, counts, digests, gains; cfg1/cfg2/cfg4 poses, mounting,
+ * multi-view segments, all five evaluators incl. clear_from_parents, 200 fuzz cases).  What reference
+ * code does NOT pin — because it lives in un-vendored dependencies that are restated in both libraries —
+ * is the voxblox arithmetic (grid-index helpers, nearest-voxel access, the 8-corner interpolation:
+ * ref_shim/voxblox_shim.h) and the floating-point order of six Eigen expressions (ref_shim/eigen_shim.h).
  *
  * Every function cites the reference file:line (relative to /root/reference) it restates.
  * "voxblox:" citations name files of the un-vendored dependency github.com/ethz-asl/voxblox

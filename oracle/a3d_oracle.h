@@ -6,11 +6,14 @@
  * baseline.  Nothing in the product (mav_active_3d_planning_b200/, include/) may call it;
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
  *
- * PARITY UNPINNED: the reference ships no tests or golden vectors and cannot be compiled in
- * this container (needs Eigen, glog, ROS, voxblox — none installed, no network).  The voxblox
- * arithmetic (un-vendored dependency, unpinned in mav_active_3d_planning_https.rosinstall:5)
- * is restated from its published sources and isolated in
- * VoxbloxLite::getDistanceAtPosition so it can be re-pinned later.
+ * PINNED by the reference's own code, except for the voxblox arithmetic: the reference ships no
+ * tests or golden vectors, but its sources for this path compile against Eigen / glog / voxblox
+ * stand-ins (oracle/Makefile target `_ref`, ref_driver.cpp, ref_shim/), and tests/test_ref_pin.py
+ * demands that library == this one bit for bit; tests/golden/*.npz hold its outputs for the GPU box.
+ * The voxblox arithmetic (un-vendored dependency, unpinned in
+ * mav_active_3d_planning_https.rosinstall:5) is restated from its published sources (SURVEY.md
+ * Appendix A) in both libraries — VoxbloxLite::getDistanceAtPosition here, ref_shim/voxblox_shim.h
+ * there — and is the part that stays "parity unpinned".
  */
 #ifndef A3D_ORACLE_H_
 #define A3D_ORACLE_H_

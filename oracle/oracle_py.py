@@ -1,7 +1,7 @@
 """ctypes binding of the CPU oracle (oracle/liba3d_oracle.so).  TEST INFRASTRUCTURE ONLY.
 
 Importers allowed: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs.
-PARITY UNPINNED — see oracle/a3d_oracle.h.
+Parity status (pinned by oracle/_ref except for the voxblox arithmetic): see oracle/a3d_oracle.h.
 """
 from __future__ import annotations
 

@@ -487,3 +487,35 @@ def test_host_batch_gains_sharded_over_two_gpus(built, room02, tmp_path):
     for s in range(6):
         assert r["batch"][s] == (1, want["gain"][s])          # sharded batch call
         assert r["single"][s][0] == 1 and r["single"][s][1] == want["gain"][s]   # per-segment call, GPU 0
+
+
+@pytest.mark.gpu
+def test_layer_messages(built, room02, tmp_path):
+    """SURVEY.md §8(f)-3, the wire half: voxblox_msgs/Layer messages (ESDF: distance + observed, TSDF:
+    weight) decoded by map::LayerReceiver into the device mirror, in an order where TSDF weights arrive
+    before their ESDF blocks; VoxelWeightEvaluator gains and a TSDF weight equal the oracle's on the same
+    map; mismatching messages are refused; ACTION_RESET replaces the mirror."""
+    from mav_active_3d_planning_b200 import synth
+    from oracle import oracle_py as O
+    pos, quat = synth.candidate_views(room02, 5, seed=13)
+    mp, sp = write_inputs(str(tmp_path), room02, pos, quat, 1, 0)
+    out = os.path.join(str(tmp_path), "layer.txt")
+    subprocess.run([EXE, "layer", os.path.join(GOLD, "planner_voxelweight.yaml"), mp, sp, out], check=True, timeout=300)
+    lines = {l.split()[0]: l.split() for l in open(out) if not l.startswith("batch")}
+    nb = room02.n_blocks
+    assert lines["tsdf_first"][1] == "1" and int(lines["tsdf_first"][3]) == nb // 2     # all kept for later
+    assert lines["esdf_a"][1] == "1" and lines["esdf_b"][1] == "1" and int(lines["esdf_b"][3]) == 0
+    assert lines["tsdf_rest"][1] == "1" and int(lines["tsdf_rest"][3]) == 0
+    assert int(lines["blocks"][1]) == nb and int(lines["blocks"][3]) == nb
+    assert lines["refused"][1:] == ["1", "1"]
+    om = O.OracleMap.from_synth(room02)
+    oc = om.caster("IterativeRayCaster", resolution_x=320, resolution_y=240, focal_length=160.0, ray_length=5.0,
+                   downsampling_factor=2.0)
+    ep = O.eval_params("VoxelWeightEvaluator", accurate_frontiers=True, checking_distance=1.0,
+                       frontier_voxel_weight=1.0, new_voxel_weight=0.0, min_impact_factor=0.01,
+                       ray_angle_x=0.002454, ray_angle_y=0.002681)
+    want = oc.compute_gains(ep, pos, quat)["gain"]
+    got = {int(l.split()[1]): float(l.split()[3]) for l in open(out) if l.startswith("batch")}
+    assert np.allclose([got[s] for s in range(5)], want, rtol=1e-5, atol=1e-12) and want.max() > 0
+    assert float(lines["weight"][1]) == om.voxel_weight(pos[:1])[0]
+    assert lines["reset"][1] == "1" and int(lines["reset"][3]) == nb // 3
