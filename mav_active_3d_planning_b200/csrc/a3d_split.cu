@@ -42,12 +42,12 @@ namespace {
 constexpr int kSplitWarps = 4;  // warps per CTA (independent: no CTA-wide barrier after the prologue)
 constexpr int kSplitThreads = 32 * kSplitWarps;
 #ifndef A3D_SPLIT_LEAF_BLOCKS
-#define A3D_SPLIT_LEAF_BLOCKS 8  // resident CTAs per SM the leaf kernel's register allocation must allow
+#define A3D_SPLIT_LEAF_BLOCKS 9  // resident CTAs per SM the leaf kernel's register allocation must allow
 #endif
 #ifndef A3D_SPLIT_MARK_BLOCKS
 #define A3D_SPLIT_MARK_BLOCKS 7
 #endif
-// (measured on cfg2, 4096 views: VoxelType 8 CTAs 3.44 ms / 6 CTAs 4.1 ms; Frontier 8: 4.33 / 6: 4.18;
+// (measured on cfg2, 4096 views: VoxelType 9 CTAs 3.35 ms / 8: 3.45 / 6: 4.1; Frontier 8: 4.33 / 6: 4.18;
 // VoxelWeight 8: 5.82 / 6: 5.18)
 constexpr int leaf_blocks(int caster, int eval) {
   return caster != A3D_CASTER_ITERATIVE ? 5
@@ -723,13 +723,14 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
 }
 
 // ---- k_split_mark_cta --------------------------------------------------------------------------------
-// The same walk with one CTA (4 warps) per view and the ray table in shared memory, for cameras whose
-// table fits: every step of the anti-diagonal chain is a shared-memory access instead of an L2 round
-// trip, and the marking parts of one anti-diagonal are cast by different warps at the same time.
-// What remains per anti-diagonal is one part's latency.  Dynamic shared memory: diag_max hit distances,
-// diag_max list items, the volume offset tables, n_rays table entries.
-template <int EVAL>
-__global__ void __launch_bounds__(kSplitThreads, 6)
+// The same walk with one CTA (4 warps) per view: the marking parts of one anti-diagonal are cast by
+// different warps at the same time, so that what remains per anti-diagonal is one part's latency.
+// SMEM_TABLE: the ray table lives in shared memory (cameras whose table fits) — every step of the chain
+// is a shared-memory access instead of an L2 round trip — and is copied out at the end; otherwise it
+// stays in global memory (L2 atomics, reads that bypass L1).  Dynamic shared memory: diag_max hit
+// distances, diag_max list items, the volume offset tables, (SMEM_TABLE) n_rays table entries.
+template <int EVAL, bool SMEM_TABLE>
+__global__ void __launch_bounds__(kSplitThreads, SMEM_TABLE ? 6 : 7)
     k_split_mark_cta(const MapView m, const CasterView c, const EvalView e, int n_views, const SplitScratch sc) {
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -754,8 +755,17 @@ __global__ void __launch_bounds__(kSplitThreads, 6)
     uint8_t* const start_s = sc.start_s + static_cast<size_t>(view) * sc.stride;
     uint32_t* const dlist = sc.dlist + static_cast<size_t>(view) * sc.stride;
     const size_t rec0 = static_cast<size_t>(view) * 2 * sc.stride;  // marking parts: part 0
+    uint32_t* const g_table = sc.table + static_cast<size_t>(view) * sc.stride;
+    auto t_read = [&](int r) -> uint32_t { return SMEM_TABLE ? s_table[r] : __ldcg(&g_table[r]); };
+    auto t_max = [&](int r, unsigned v) {
+      if (SMEM_TABLE) atomicMax(&s_table[r], v); else atomicMax(&g_table[r], v);
+    };
+    auto t_sync = [&]() {  // marks of every warp visible to every warp
+      if (!SMEM_TABLE) __threadfence_block();
+      __syncthreads();
+    };
     for (int r = threadIdx.x; r < n_rays; r += kSplitThreads) {
-      s_table[r] = 0u;
+      if (SMEM_TABLE) s_table[r] = 0u; else g_table[r] = 0u;
       start_s[r] = 0xFF;
       __stcs(&sc.rec[rec0 + r], 0ull);
     }
@@ -767,7 +777,7 @@ __global__ void __launch_bounds__(kSplitThreads, 6)
 
     for (int diag = 0; diag < n_diag; ++diag) {
       if (threadIdx.x == 0) s_n_mark = 0;
-      __syncthreads();  // table final up to this diagonal; counters reset
+      t_sync();  // table final up to this diagonal; counters reset
       // The rays of this diagonal that start before the last section (see k_split_mark): section n-2
       // starts get their provisional mark and go to the list of k_split_mark2, earlier starts are cast
       // here.  Neither list needs an order (marks commute, records are per ray).
@@ -777,7 +787,7 @@ __global__ void __launch_bounds__(kSplitThreads, 6)
         int s = -1, r = 0;
         if (i <= i_hi) {
           r = i * c.res_y + (diag - i);
-          s = static_cast<int>(static_cast<int8_t>(s_table[r] & 0xFFu));
+          s = static_cast<int>(static_cast<int8_t>(t_read(r) & 0xFFu));
         }
         const bool deferred = s == n - 2;
         const bool marking = s >= 0 && s < n - 2;
@@ -796,10 +806,10 @@ __global__ void __launch_bounds__(kSplitThreads, 6)
           const int ri = i, rj = diag - i;
           const unsigned ent = ((static_cast<unsigned>(r) + 1u) << 8) | static_cast<uint8_t>(n - 1);
           const bool in_x = ri + 1 < c.res_x, in_y = rj + 1 < c.res_y;
-          atomicMax(&s_table[r], ent);
-          if (in_y) atomicMax(&s_table[r + 1], ent);
-          if (in_x) atomicMax(&s_table[r + c.res_y], ent);
-          if (in_x && in_y) atomicMax(&s_table[r + c.res_y + 1], ent);
+          t_max(r, ent);
+          if (in_y) t_max(r + 1, ent);
+          if (in_x) t_max(r + c.res_y, ent);
+          if (in_x && in_y) t_max(r + c.res_y + 1, ent);
         }
       }
       __syncthreads();
@@ -847,14 +857,14 @@ __global__ void __launch_bounds__(kSplitThreads, 6)
             const int tmax = mx == 0 ? n - 1 : n - 2 - (31 - __clz(mx));
             const int t = min(tmax, b_tl);
             const int val = (t == b_sh) ? -1 : t + 1;
-            atomicMax(&s_table[(b_ri + dx) * c.res_y + b_rj + dy], b_wr | static_cast<uint8_t>(val));
+            t_max((b_ri + dx) * c.res_y + b_rj + dy, b_wr | static_cast<uint8_t>(val));
           }
         }
       }
     }
     __syncthreads();
-    uint32_t* const g_table = sc.table + static_cast<size_t>(view) * sc.stride;
-    for (int r = threadIdx.x; r < n_rays; r += kSplitThreads) g_table[r] = s_table[r];
+    if (SMEM_TABLE)
+      for (int r = threadIdx.x; r < n_rays; r += kSplitThreads) g_table[r] = s_table[r];
     if (__any_sync(kFull, inexact != 0) && lane == 0) atomicOr(&s_inexact, 1u);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1064,7 +1074,12 @@ int launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, const
     // (cfg2: one view 0.89 -> 0.37 ms, 148 views 1.23 -> 0.69 ms; beyond ~2000 views the one-warp-per-view
     // kernel wins: 4096 views 1.7 vs 2.6 ms)
     if (smem_1 <= 40 * 1024 && n_views <= sm_count * 12) {
-      k_split_mark_cta<EVAL><<<std::max(1, std::min(n_views, sm_count * 8)), kSplitThreads, smem_1, st>>>(m, c, e, n_views, sc);
+      k_split_mark_cta<EVAL, true><<<std::max(1, std::min(n_views, sm_count * 8)), kSplitThreads, smem_1, st>>>(m, c, e, n_views, sc);
+    } else if (smem_1 > 40 * 1024 && n_views <= sm_count * 7) {
+      // table too large for shared memory, batch small enough for one resident CTA per view: the
+      // CTA-per-view walk on the global table (cfg3, 1024 views: 5.8 ms with one warp per view)
+      const size_t smem_g = static_cast<size_t>(c.diag_max) * 12 + tab_bytes;
+      k_split_mark_cta<EVAL, false><<<std::max(1, n_views), kSplitThreads, smem_g, st>>>(m, c, e, n_views, sc);
     } else {
       const size_t smem = static_cast<size_t>(kSplitWarps) * c.diag_max * 12 + tab_bytes;
       const int grid =

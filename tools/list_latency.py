@@ -33,7 +33,7 @@ def main():
         out["single_view_" + name] = dict(kernel_ms=min(ks[1:]), wall_ms=min(ws[1:]), entries=len(lst))
         for n in (12, 148, 2048):
             store = capi.Store(ctx)
-            keys = np.arange(n, dtype=np.uint64)
+            keys = np.arange(1, n + 1, dtype=np.uint64)
             best = 1e9
             for r in range(3):
                 t0 = time.perf_counter()

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (raw + source pages) into text: key metrics, SASS opcode mix, hot blocks.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--blocks]"""
+"""Summarise an .ncu-rep (raw + source pages) into text: key metrics of every kernel in the report, then
+the SASS opcode mix, stall mix and (--blocks) hot blocks of ONE kernel (--kernel K: the K-th launch in
+the report, default 0).
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--blocks] [--kernel K]"""
 import collections
 import csv
 import io
@@ -8,8 +10,8 @@ import subprocess
 import sys
 
 
-def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+def page(rep, name, extra=()):
+    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv", *extra], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
@@ -41,8 +43,20 @@ def main():
         for h, u, v in zip(hdr, units, row):
             if any(h.startswith(k.strip()) and (not k.endswith(" ") or h == k.strip()) for k in KEYS):
                 print(f"  {h:75s} {v:>18s} {u}")
-    src = page(rep, "source")
+    k = int(sys.argv[sys.argv.index("--kernel") + 1]) if "--kernel" in sys.argv else 0
+    src = page(rep, "source", ("--launch-skip", str(k), "--launch-count", "1"))
+    print("\n== SASS of launch", k, ":", src[0][1][:110] if len(src[0]) > 1 else "")
     hdr = src[1]
+    # (the page repeats the kernel once per view; keep the first copy)
+    seen_addr = set()
+    body = []
+    for r in src[2:]:
+        if len(r) >= len(hdr) and r[0].startswith("0x"):
+            if r[0] in seen_addr:
+                break
+            seen_addr.add(r[0])
+        body.append(r)
+    src = src[:2] + body
     ix = {h: i for i, h in enumerate(hdr)}
     ops, samples = collections.Counter(), collections.Counter()
     stalls = collections.Counter()

@@ -24,7 +24,7 @@ def main():
     for ekind in ("VoxelTypeEvaluator", "NaiveEvaluator"):
         ev = ctx.evaluator(ekind)
         store = capi.Store(ctx)
-        keys = np.arange(n, dtype=np.uint64)
+        keys = np.arange(1, n + 1, dtype=np.uint64)  # (key 0 means "no parent")
         t0 = time.perf_counter()
         r = store.compute_gains(caster, ev, keys, pos, quat)
         t_store = time.perf_counter() - t0
