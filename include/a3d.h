@@ -204,7 +204,9 @@ void a3d_eval_destroy(a3d_eval* e);
  *   view_segment n_views, non-decreasing, values in [0,n_segments): which segment a view belongs to.
  * Outputs, one per segment (each nullable except gains_out):
  *   gains_out      TrajectorySegment::gain
- *   n_visible_out  size of the voxel list the reference would store in SimulatedSensorInfo
+ *   n_visible_out  size of the voxel list the reference hands to storeTrajectoryInformation (after
+ *                  unique and the bounding-volume filter; Naive and Frontier erase the observed entries
+ *                  from the stored list afterwards, naive_evaluator.cpp:28-35 — that is not subtracted)
  *   n_samples_out  ray samples taken (= getVoxelState calls made by the caster)
  *   digests_out    order-sensitive 64-bit digest of that stored list (DESIGN.md "digest");
  *                  asking for it selects the scan-order kernel

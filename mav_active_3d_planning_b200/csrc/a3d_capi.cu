@@ -780,7 +780,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     return ctx->fail(A3D_ERR_UNSUPPORTED, "cast_kernel=2 (wavefront) cannot produce ordered digests");
   bool use_wave = wave_ok && ctx->opt_cast_kernel != 1 && ctx->opt_cast_kernel != 3;
   // the kernel chain of a3d_split.cu: gains / counts only, dense meta volume required
-  bool use_split = e && !emit && !dig_dev && !set_dig_dev && n_views >= 0 &&
+  bool use_split = (e || emit) && !dig_dev && !set_dig_dev && n_views >= 0 && (!emit || ctx->view().vps_shift >= 0) &&
                    (ctx->opt_cast_kernel == 0 || ctx->opt_cast_kernel == 3);
   if (use_wave || use_split) {
     int rc = vol_ensure(ctx);
@@ -795,7 +795,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const unsigned int* seg_mask = nullptr;
   if (use_split) {
-    const size_t per_view = cast_split_bytes_per_view(c->view, ev_view.kind, nullptr);
+    const size_t per_view = cast_split_bytes_per_view(c->view, ev_view.kind, nullptr, emit);
     const long long max_views = static_cast<long long>(std::max<size_t>(1, (size_t(4) << 30) / per_view));
     std::vector<int32_t> h_first;  // needed only to cut the batch into chunks that fit the scratch
     if (n_views > max_views) {
@@ -820,7 +820,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
         if (!evs) CK(cudaEventCreate(&evs));
       ctx->n_stage = launch_cast_split(ctx->stream, ctx->view(), c->view, ev_view, b, seg, seg_end - seg, v0, v1 - v0,
                                        ctx->sc_wave.p, ctx->sc_inexact.p, ctx->sm_count, ctx->ev_stage);
-      ctx->launches += cast_split_launches(c->view);
+      ctx->launches += cast_split_launches(c->view, emit);
       CK(cudaGetLastError());
       seg = seg_end;
     }
@@ -1541,7 +1541,7 @@ int a3d_visible_voxels(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* e
   }
   int rc = enqueue_cast(ctx, caster, eval, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, 1,
                         ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr,
-                        ctx->sc_centres.p, cap, true, origin_dev);
+                        ctx->sc_centres.p, cap, true, origin_dev, nullptr, nullptr, n_views);
   if (rc) return rc;
   unsigned long long nvis = 0, nsamp = 0;
   double gain = 0.0;
@@ -1896,7 +1896,7 @@ int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_e
                      ctx->stream));
   rc = enqueue_cast(ctx, caster, &plain, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, n_segments,
                     ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr, nullptr, 0, true,
-                    seg_origin ? ctx->sc_origin.p : nullptr, store->d_off.p, store->arenas[arena_id].p);
+                    seg_origin ? ctx->sc_origin.p : nullptr, store->d_off.p, store->arenas[arena_id].p, n_views);
   if (rc) return fail_arena(rc);
   unsigned int key_error = 0;
   CK(cudaMemcpyAsync(&key_error, ctx->sc_counter.p + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));

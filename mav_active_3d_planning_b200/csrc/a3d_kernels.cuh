@@ -135,10 +135,11 @@ size_t wave_scratch_bytes(int n_rays, int grid, bool digest, size_t* rays_stride
 void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e,
                       const Batch& b, bool digest, int grid, void* scratch, unsigned int* inexact,
                       int warps /*CTA width: 2 (throughput), 4 or 8 (mid-size / small batches)*/);
-// throughput path as a chain of kernels (a3d_split.cu): gains / counts only, dense meta volume required
+// throughput path as a chain of kernels (a3d_split.cu): gains / counts and, when Batch::centres_out or
+// keys_out is set, the ordered lists; no digests; dense meta volume required
 bool cast_split_supported(const MapView& m, const CasterView& c);
-size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out);
-int cast_split_launches(const CasterView& c);
+size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out, bool emit);
+int cast_split_launches(const CasterView& c, bool emit);
 // stage_events (6, or null): recorded before the first and after each kernel; returns how many were recorded
 int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
                       int seg0, int n_seg, int view0, int n_views, void* scratch, unsigned int* inexact,

@@ -87,7 +87,18 @@ struct SplitScratch {
   double* first_val;              // ... value of the first entry
   size_t stride;                  // n_rays rounded up to 32
   int parts;                      // 2 (iterative: marking part, leaf part) or 1
+  // list emission (null / 0 when only gains are asked): the retained entries of every ray part as
+  // packed keys, kmax slots per part; where the part's entries go in its segment's ordered list
+  unsigned long long* ent;        // [n_views][parts][stride][kmax]
+  uint32_t* off;                  // [n_views][parts][stride]: offset in the segment's list | (first entry dropped) << 31
+  int32_t* view_seg;              // [n_views] segment of each view (batch-wide numbering)
+  int kmax;
 };
+
+// entries a part has retained so far, from its record word
+__device__ __forceinline__ int rec_kept(unsigned long long rec) {
+  return static_cast<int>((rec & kCntMask) + ((rec >> kCntBits) & kCntMask) + ((rec >> (2 * kCntBits)) & kCntMask));
+}
 
 __host__ __device__ inline uint32_t vol_tab_entries(const MapView& m) {
   const uint32_t n = m.vol_n[0] + m.vol_n[1] + m.vol_n[2];
@@ -377,6 +388,11 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
   if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
     if (first) p.first_val = wval; else p.wsum += wval;
   }
+  if (sc.ent && keep) {  // list emission: the retained entry, in the part's own slot range
+    unsigned bad = 0;
+    __stcs(&sc.ent[p.at * static_cast<size_t>(sc.kmax) + rec_kept(p.rec)], pack_key(si.id, &bad));
+    inexact |= bad;
+  }
   p.rec += static_cast<unsigned long long>(keep) << (kCntBits * cat);
   if (first) {
     // the part's first raw entry: its key now, what it was counted as in the record word
@@ -444,6 +460,15 @@ __device__ __forceinline__ double part_by_warp(const MapView& m, const CasterVie
     int cat = 3;
     if (valid) cat = entry_category<EVAL>(m, e, sh, vw, ev, keep, wval);
     const bool first = k == 0;
+    if (sc.ent) {  // list emission: retained entries in sample order
+      const unsigned km = __ballot_sync(kFull, keep);
+      if (keep) {
+        unsigned bad = 0;
+        __stcs(&sc.ent[at * static_cast<size_t>(sc.kmax) + rec_kept(rec) + __popc(km & ((1u << lane) - 1u))],
+               pack_key(ev.si.id, &bad));
+        inexact |= bad;
+      }
+    }
     rec += static_cast<unsigned long long>(n_valid) << kCntSampShift;
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc)
@@ -540,6 +565,7 @@ __global__ void k_split_views(const MapView m, const CasterView c, const Batch b
     for (int a = 0; a < 3; ++a) vw.z0[a] = static_cast<float>(vw.P0[a] * k - 0.5);
     sc.views[view - view0] = vw;
     sc.view_flags[view - view0] = 0u;
+    if (sc.view_seg) sc.view_seg[view - view0] = seg;
   }
 }
 
@@ -968,6 +994,7 @@ __global__ void __launch_bounds__(kSplitThreads)
   double wsum = 0.0;
   unsigned inexact = 0;
   uint64_t carry = kNoKey;  // last raw entry so far in this segment (warp-uniform)
+  unsigned emit_pos = 0;    // list emission: entries of the segment's list placed so far (warp-uniform)
   const int per_it = ITER ? 16 : 32;
   for (int view = v_begin; view < v_end; ++view) {
     const int vl = view - view0;
@@ -1014,6 +1041,19 @@ __global__ void __launch_bounds__(kSplitThreads)
           wsum += sc.wsum[ats[k]];
           if (emitted && kept && !drop) wsum += sc.first_val[ats[k]];
         }
+        if (sc.off) {
+          // where this part's retained entries go in the segment's ordered list
+          const unsigned n_out = static_cast<unsigned>(rec_kept(rec)) - (drop ? 1u : 0u);
+          unsigned incl = n_out;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, incl, o);
+            if (static_cast<int>(lane) >= o) incl += t;
+          }
+          if (((rec >> kCntSampShift) & kCntMask) != 0 || emitted)
+            sc.off[ats[k]] = (emit_pos + incl - n_out) | (drop ? 0x80000000u : 0u);
+          emit_pos += __shfl_sync(kFull, incl, 31);
+        }
         if (em) carry = __shfl_sync(kFull, lk, 31 - __clz(em));
       }
     }
@@ -1052,6 +1092,51 @@ __global__ void __launch_bounds__(kSplitThreads)
     if (b.n_visible) b.n_visible[seg] = t0 + t1 + t2;
     if (b.n_samples) b.n_samples[seg] = tn;
     if (inexact) atomicOr(&inexact_flags[seg >> 5], 1u << (seg & 31));
+  }
+}
+
+// ---- k_split_emit ------------------------------------------------------------------------------------
+// List emission, last step: every ray part's retained entries move from its slot range to their place
+// in the segment's ordered list (offsets from k_split_fix), as packed keys or as the centre doubles
+// the reference holds.  One lane per part, 32 consecutive parts in scan order per warp: neighbouring
+// lanes write neighbouring ranges.
+__global__ void __launch_bounds__(kSplitThreads)
+    k_split_emit(const MapView m, const Batch b, int n_views, int n_rays, const SplitScratch sc) {
+  __shared__ CenterTables ct;
+  init_center_tables(m, &ct);
+  __syncthreads();
+  const long long n_parts = static_cast<long long>(n_views) * sc.parts * n_rays;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < n_parts;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // scan order within a view: ray by ray, marking part before leaf part
+    const int view = static_cast<int>(q / (static_cast<long long>(sc.parts) * n_rays));
+    const int rest = static_cast<int>(q - static_cast<long long>(view) * sc.parts * n_rays);
+    const int ray = rest / sc.parts, part = rest - ray * sc.parts;
+    const size_t at = (static_cast<size_t>(view) * sc.parts + part) * sc.stride + ray;
+    const unsigned long long rec = sc.rec[at];
+    const int kept = rec_kept(rec);
+    if (kept == 0) continue;
+    const uint32_t o = sc.off[at];
+    const int skip = static_cast<int>(o >> 31);
+    const long long first_idx = static_cast<long long>(o & 0x7FFFFFFFu);
+    const int seg = sc.view_seg[view];
+    const long long base = b.emit_offset ? b.emit_offset[seg] : 0;
+    const long long cap = b.emit_offset ? b.emit_offset[seg + 1] - base : b.cap;
+    const unsigned long long* src = sc.ent + at * static_cast<size_t>(sc.kmax);
+    for (int k = skip; k < kept; ++k) {
+      const long long idx = first_idx + (k - skip);
+      if (idx >= cap) break;
+      const unsigned long long key = __ldcs(src + k);
+      if (b.keys_out) {
+        b.keys_out[base + idx] = key;
+      } else {
+        const D3 cc = key_centre(m, ct, key);
+        double* dst = b.centres_out + 3 * (base + idx);
+        dst[0] = cc.x;
+        dst[1] = cc.y;
+        dst[2] = cc.z;
+      }
+    }
   }
 }
 
@@ -1108,6 +1193,12 @@ int launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, const
   k_split_fix<CASTER, EVAL><<<(n_seg + kSplitWarps - 1) / kSplitWarps, kSplitThreads, 0, st>>>(
       e, b, seg0, n_seg, view0, c.n_rays, sc, inexact);
   stamp();
+  if (sc.ent) {
+    const long long n_parts = static_cast<long long>(n_views) * sc.parts * c.n_rays;
+    const int grid = static_cast<int>(std::max(1ll, std::min((n_parts + kSplitThreads - 1) / kSplitThreads,
+                                                             static_cast<long long>(sm_count) * 16)));
+    k_split_emit<<<grid, kSplitThreads, 0, st>>>(m, b, n_views, c.n_rays, sc);
+  }
   return n_ev;
 }
 
@@ -1136,17 +1227,18 @@ bool cast_split_supported(const MapView& m, const CasterView& c) {
   return c.n_rays < (1 << 23);
 }
 
-size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out) {
+size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out, bool emit) {
   const size_t stride = (static_cast<size_t>(c.n_rays) + 31) / 32 * 32;
   if (stride_out) *stride_out = stride;
   const size_t parts = c.kind == A3D_CASTER_ITERATIVE ? 2 : 1;
   size_t per_view = parts * stride * (8 + 8 + 8) + sizeof(ViewRec) + 8;
+  if (emit) per_view += parts * stride * (static_cast<size_t>(c.kmax) * 8 + 4) + 8;
   if (eval_kind == A3D_EVAL_VOXEL_WEIGHT) per_view += parts * stride * 16;
   if (c.kind == A3D_CASTER_ITERATIVE) per_view += stride * 9 + 8;
   return per_view;
 }
 
-int cast_split_launches(const CasterView& c) { return c.kind == A3D_CASTER_ITERATIVE ? 5 : 3; }
+int cast_split_launches(const CasterView& c, bool emit) { return (c.kind == A3D_CASTER_ITERATIVE ? 5 : 3) + (emit ? 1 : 0); }
 
 // Segments [seg0, seg0 + n_seg) = views [view0, view0 + n_views) of the batch; scratch holds
 // n_views * cast_split_bytes_per_view() + 256 bytes.  inexact: one bit per segment (batch-wide
@@ -1156,7 +1248,8 @@ int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, co
                       int sm_count, cudaEvent_t* stage_events) {
   SplitScratch sc{};
   size_t stride = 0;
-  cast_split_bytes_per_view(c, e.kind, &stride);
+  const bool emit = b.centres_out != nullptr || b.keys_out != nullptr;
+  cast_split_bytes_per_view(c, e.kind, &stride, emit);
   sc.stride = stride;
   sc.parts = c.kind == A3D_CASTER_ITERATIVE ? 2 : 1;
   uint8_t* p = static_cast<uint8_t*>(scratch);
@@ -1174,6 +1267,15 @@ int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, co
     p += slots * 8;
     sc.first_val = reinterpret_cast<double*>(p);
     p += slots * 8;
+  }
+  if (emit) {
+    sc.kmax = c.kmax;
+    sc.ent = reinterpret_cast<unsigned long long*>(p);
+    p += slots * static_cast<size_t>(c.kmax) * 8;
+    sc.off = reinterpret_cast<uint32_t*>(p);
+    p += (slots * 4 + 7) / 8 * 8;
+    sc.view_seg = reinterpret_cast<int32_t*>(p);
+    p += (nv * 4 + 7) / 8 * 8;
   }
   sc.view_flags = reinterpret_cast<unsigned int*>(p);
   p += (nv * 4 + 7) / 8 * 8;

@@ -557,6 +557,13 @@ def test_wave_kernel_emits_ordered_lists(capi, O, room02, ckind):
             if kw:
                 want = want[O.bv_contains(oe, want) == 1]
             wg = oc.compute_gains(oe, pos[sl], quat[sl], np.zeros(sl.stop - sl.start, np.int32), 1)
+            # the kernel chain with list emission (default) ...
+            lst, ns, gain = ctx.visible_voxels(caster, pos[sl], quat[sl], evaluator=ev)
+            assert ctx.last_cast_kernel == 3
+            assert lst.shape == want.shape and np.array_equal(lst, want)
+            assert ns == wg["n_samples"][0] and np.isclose(gain, wg["gain"][0], rtol=GAIN_RTOL, atol=1e-12)
+            # ... the wavefront kernel's emission ...
+            ctx.set_option("cast_kernel", 2)
             for width in (1, 2):
                 ctx.set_option("wave_cta", width)
                 lst, ns, gain = ctx.visible_voxels(caster, pos[sl], quat[sl], evaluator=ev)
@@ -564,6 +571,7 @@ def test_wave_kernel_emits_ordered_lists(capi, O, room02, ckind):
                 assert lst.shape == want.shape and np.array_equal(lst, want)
                 assert ns == wg["n_samples"][0] and np.isclose(gain, wg["gain"][0], rtol=GAIN_RTOL, atol=1e-12)
             ctx.set_option("wave_cta", 0)
+            # ... and the scan-order kernel
             ctx.set_option("cast_kernel", 1)
             ref, _, _ = ctx.visible_voxels(caster, pos[sl], quat[sl], evaluator=ev)
             ctx.set_option("cast_kernel", 0)

@@ -123,14 +123,16 @@ def one_case(rng, case, oracle=None, max_views=None):
     first = slice(0, 1) if len(args) == 2 else slice(0, int(np.sum(args[2] == 0)))
     ctx.set_option("cast_kernel", 1)
     l_ref, _, g_ref = ctx.visible_voxels(caster, pos[first], quat[first], evaluator=ev)
+    for kernel in (2, 0):   # wavefront kernel's emission; default = the kernel chain's where it applies
+        ctx.set_option("cast_kernel", kernel)
+        l_got, _, g_got = ctx.visible_voxels(caster, pos[first], quat[first], evaluator=ev)
+        if kernel == 2 and ctx.last_cast_kernel != 2:
+            bad.append("list call did not use the wavefront kernel")
+        if l_ref.shape != l_got.shape or not np.array_equal(l_ref, l_got):
+            bad.append(f"ordered list (kernel {ctx.last_cast_kernel})")
+        if not np.isclose(g_ref, g_got, rtol=1e-9, atol=1e-12):
+            bad.append(f"list gain (kernel {ctx.last_cast_kernel})")
     ctx.set_option("cast_kernel", 0)
-    l_got, _, g_got = ctx.visible_voxels(caster, pos[first], quat[first], evaluator=ev)
-    if ctx.last_cast_kernel != 2:
-        bad.append("list call did not use the wavefront kernel")
-    if l_ref.shape != l_got.shape or not np.array_equal(l_ref, l_got):
-        bad.append("ordered list")
-    if not np.isclose(g_ref, g_got, rtol=1e-9, atol=1e-12):
-        bad.append("list gain")
     ctx.close()
     return dict(case=case, vs=vs, vps=vps, edits=bool(edits), caster=ckind, evaluator=ekind, kw={k: (v if not isinstance(v, dict) else "bv") for k, v in kw.items()},
                 cam=cam["resolution_x"], shift=shift.tolist(), views=n_views, segments=len(ref["gain"]),

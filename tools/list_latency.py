@@ -22,7 +22,7 @@ def main():
     ev = ctx.evaluator("VoxelTypeEvaluator")
     pos, quat = synth.candidate_views(m, 2048, seed=42)
     out = {}
-    for name, opt in (("wave", 0), ("scan", 1)):
+    for name, opt in (("chain", 0), ("wave", 2), ("scan", 1)):  # default = kernel chain with list emission
         ctx.set_option("cast_kernel", opt)
         ks, ws = [], []
         for v in range(6):
