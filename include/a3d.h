@@ -131,8 +131,8 @@ int a3d_last_stage_ms(a3d_ctx* ctx, float* out_ms, int cap);
 uint64_t a3d_kernel_launches(a3d_ctx* ctx);
 /* Tuning / test knobs.  "cast_kernel": 0 = automatic (default), 1 = always the scan-order kernel
    (k_cast_gain), 2 = require the wavefront kernel (k_cast_wave; errors if ordered digests are asked),
-   3 = require the kernel chain (a3d_split.cu: gains and counts only; errors if digests are asked or
-   the dense meta volume does not exist).
+   3 = require the kernel chain (a3d_split.cu: gains, counts and ordered lists; errors if digests are
+   asked or the dense meta volume does not exist).
    "wave_cta": CTA width of the wavefront kernel, 0 = automatic (8 or 4 warps for small and mid-size
    batches, else 2), 1 = always 2 warps, 2 = always 8 warps, 3 = always 4 warps. */
 int a3d_set_option(a3d_ctx* ctx, const char* name, int64_t value);
@@ -269,8 +269,8 @@ void a3d_store_destroy(a3d_store* store);
  *   evaluators the observed entries are erased (naive_evaluator.cpp:28-35, frontier_evaluator.cpp:110-116);
  *   n_visible_out is the size handed to storeTrajectoryInformation (before that erasure), digests /
  *   set digests are of that list.  Outputs other than gains_out are nullable.
- * Passes: gains/sizes (wavefront kernel) → ordered key lists into an exactly sized arena (wavefront
- * kernel with list emission up to twice the SM count segments, scan-order kernel beyond) → where
+ * Passes: gains/sizes (kernel chain) → ordered key lists into an exactly sized arena (kernel chain
+ * with list emission; the wavefront / scan-order kernels where the chain does not apply) → where
  * needed, k_list_pipeline (parent filter, digests, fold + erasure), level by level of the tree. */
 int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
                              a3d_store* store, int n_views, const double* pos, const double* quat,

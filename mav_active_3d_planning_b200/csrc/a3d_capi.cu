@@ -779,7 +779,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   if (ctx->opt_cast_kernel == 2 && !wave_ok)
     return ctx->fail(A3D_ERR_UNSUPPORTED, "cast_kernel=2 (wavefront) cannot produce ordered digests");
   bool use_wave = wave_ok && ctx->opt_cast_kernel != 1 && ctx->opt_cast_kernel != 3;
-  // the kernel chain of a3d_split.cu: gains / counts only, dense meta volume required
+  // the kernel chain of a3d_split.cu: gains / counts / ordered lists (no digests), dense meta volume required
   bool use_split = (e || emit) && !dig_dev && !set_dig_dev && n_views >= 0 && (!emit || ctx->view().vps_shift >= 0) &&
                    (ctx->opt_cast_kernel == 0 || ctx->opt_cast_kernel == 3);
   if (use_wave || use_split) {
@@ -789,7 +789,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   use_split = use_split && cast_split_supported(ctx->view(), c->view);
   if (ctx->opt_cast_kernel == 3 && !use_split)
     return ctx->fail(A3D_ERR_UNSUPPORTED,
-                     "cast_kernel=3 (kernel chain) needs the dense meta volume and gains-only outputs");
+                     "cast_kernel=3 (kernel chain) needs the dense meta volume and cannot produce digests");
   if (use_split) use_wave = false;
   ctx->last_cast_kernel = use_split ? 3 : use_wave ? 2 : 1;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
