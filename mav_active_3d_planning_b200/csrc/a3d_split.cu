@@ -130,6 +130,7 @@ __device__ __forceinline__ uint32_t vol_word(const MapView& m, const int (&g)[3]
   if ((u0 < m.vol_n[0]) & (u1 < m.vol_n[1]) & (u2 < m.vol_n[2])) {
     const uint32_t off = tab ? tab[u0] + tab[m.vol_n[0] + u1] + tab[m.vol_n[0] + m.vol_n[1] + u2]
                              : vol_offset(m, u0, u1, u2);
+    A3D_DEV_CHECK(off == vol_offset(m, u0, u1, u2));
     word = __ldg(m.vol + off);
   }
   return word;
@@ -390,6 +391,7 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
   }
   if (sc.ent && keep) {  // list emission: the retained entry, in the part's own slot range
     unsigned bad = 0;
+    A3D_DEV_CHECK(rec_kept(p.rec) < sc.kmax);
     __stcs(&sc.ent[p.at * static_cast<size_t>(sc.kmax) + rec_kept(p.rec)], pack_key(si.id, &bad));
     inexact |= bad;
   }
@@ -464,6 +466,7 @@ __device__ __forceinline__ double part_by_warp(const MapView& m, const CasterVie
       const unsigned km = __ballot_sync(kFull, keep);
       if (keep) {
         unsigned bad = 0;
+        A3D_DEV_CHECK(rec_kept(rec) + __popc(km & ((1u << lane) - 1u)) < sc.kmax);
         __stcs(&sc.ent[at * static_cast<size_t>(sc.kmax) + rec_kept(rec) + __popc(km & ((1u << lane) - 1u))],
                pack_key(ev.si.id, &bad));
         inexact |= bad;
@@ -627,6 +630,7 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
     // table access: shared memory, or L2 (atomics are performed there, reads bypass L1)
     auto t_read = [&](int r) -> uint32_t { return SMEM_TABLE ? s_table[r] : __ldcg(&g_table[r]); };
     auto t_max = [&](int r, unsigned v) {
+      A3D_DEV_CHECK(r >= 0 && r < n_rays);
       if (SMEM_TABLE) atomicMax(&s_table[r], v); else atomicMax(&g_table[r], v);
     };
     auto t_fence = [&]() {
@@ -656,6 +660,7 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
         const bool deferred = s == n - 2;
         const bool marking = s >= 0 && s < n - 2;
         const unsigned mm = __ballot_sync(kFull, marking), dm = __ballot_sync(kFull, deferred);
+        A3D_DEV_CHECK(n_mark + __popc(mm) <= c.diag_max && n_def + __popc(dm) <= n_rays);
         if (marking) s_list[n_mark + __popc(mm & lt_mask)] = (static_cast<unsigned>(r) << 8) | s;
         n_mark += __popc(mm);
         if (deferred) {
@@ -784,6 +789,7 @@ __global__ void __launch_bounds__(kSplitThreads, SMEM_TABLE ? 6 : 7)
     uint32_t* const g_table = sc.table + static_cast<size_t>(view) * sc.stride;
     auto t_read = [&](int r) -> uint32_t { return SMEM_TABLE ? s_table[r] : __ldcg(&g_table[r]); };
     auto t_max = [&](int r, unsigned v) {
+      A3D_DEV_CHECK(r >= 0 && r < n_rays);
       if (SMEM_TABLE) atomicMax(&s_table[r], v); else atomicMax(&g_table[r], v);
     };
     auto t_sync = [&]() {  // marks of every warp visible to every warp
@@ -825,6 +831,7 @@ __global__ void __launch_bounds__(kSplitThreads, SMEM_TABLE ? 6 : 7)
         }
         m_at = __shfl_sync(kFull, m_at, 0);
         d_at = __shfl_sync(kFull, d_at, 0);
+        A3D_DEV_CHECK(m_at + __popc(mm) <= c.diag_max && d_at + __popc(dm) <= n_rays);
         if (marking) s_list[m_at + __popc(mm & lt_mask)] = (static_cast<unsigned>(r) << 8) | s;
         if (deferred) {
           dlist[d_at + __popc(dm & lt_mask)] = static_cast<uint32_t>(r);
@@ -1126,6 +1133,7 @@ __global__ void __launch_bounds__(kSplitThreads)
     for (int k = skip; k < kept; ++k) {
       const long long idx = first_idx + (k - skip);
       if (idx >= cap) break;
+      A3D_DEV_CHECK(k < sc.kmax && idx >= 0);
       const unsigned long long key = __ldcs(src + k);
       if (b.keys_out) {
         b.keys_out[base + idx] = key;
