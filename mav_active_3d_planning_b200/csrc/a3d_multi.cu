@@ -449,30 +449,43 @@ int a3d_group_compute_gains(a3d_group* g, const a3d_group_caster* caster, const 
       vw += nv_run;
     }
   }
-  for (int i = 0; i < N; ++i) {
+  // one host thread per GPU issues that GPU's copies and launches (a cast is ~30 runtime calls; issued
+  // from one thread for 8 GPUs they cost more than the 512-view cast itself)
+  std::vector<int> rcs(N, A3D_OK);
+  std::vector<std::string> errs(N);
+  auto issue = [&](int i) {
     Device& d = g->dev[i];
     const int ns = static_cast<int>(mine[i].size()), nvw = n_views_of[i];
     const size_t b_pos = 24 * static_cast<size_t>(nvw), b_quat = 32 * static_cast<size_t>(nvw),
                  b_org = seg_origin ? 24 * static_cast<size_t>(ns) : 0, b_first = 4 * (static_cast<size_t>(ns) + 1);
-    GCK(cudaSetDevice(d.id));
-    GCK(d.pos.reserve(3 * static_cast<size_t>(std::max(nvw, 1))));
-    GCK(d.quat.reserve(4 * static_cast<size_t>(std::max(nvw, 1))));
-    GCK(d.first.reserve(static_cast<size_t>(ns) + 1));
-    GCK(d.rec.reserve(per * kRecWords));
-    GCK(d.all.reserve(per * kRecWords * N));
-    GCK(cudaMemsetAsync(d.rec.p, 0, per * kRecWords * 8, d.stream));
+    auto ck = [&](cudaError_t e, const char* what) {
+      if (e != cudaSuccess && rcs[i] == A3D_OK) {
+        rcs[i] = A3D_ERR_CUDA;
+        errs[i] = std::string(what) + ": " + cudaGetErrorString(e);
+      }
+      return e == cudaSuccess;
+    };
+    if (!ck(cudaSetDevice(d.id), "cudaSetDevice")) return;
+    if (!ck(d.pos.reserve(3 * static_cast<size_t>(std::max(nvw, 1))), "cudaMalloc") ||
+        !ck(d.quat.reserve(4 * static_cast<size_t>(std::max(nvw, 1))), "cudaMalloc") ||
+        !ck(d.first.reserve(static_cast<size_t>(ns) + 1), "cudaMalloc") ||
+        !ck(d.rec.reserve(per * kRecWords), "cudaMalloc") || !ck(d.all.reserve(per * kRecWords * N), "cudaMalloc"))
+      return;
+    ck(cudaMemsetAsync(d.rec.p, 0, per * kRecWords * 8, d.stream), "cudaMemsetAsync");
     if (nvw > 0) {
-      GCK(cudaMemcpyAsync(d.pos.p, d.stage.p, b_pos, cudaMemcpyHostToDevice, d.stream));
-      GCK(cudaMemcpyAsync(d.quat.p, d.stage.p + b_pos, b_quat, cudaMemcpyHostToDevice, d.stream));
+      ck(cudaMemcpyAsync(d.pos.p, d.stage.p, b_pos, cudaMemcpyHostToDevice, d.stream), "cudaMemcpyAsync");
+      ck(cudaMemcpyAsync(d.quat.p, d.stage.p + b_pos, b_quat, cudaMemcpyHostToDevice, d.stream), "cudaMemcpyAsync");
     }
-    GCK(cudaMemcpyAsync(d.first.p, d.stage.p + b_pos + b_quat + b_org, b_first, cudaMemcpyHostToDevice, d.stream));
+    ck(cudaMemcpyAsync(d.first.p, d.stage.p + b_pos + b_quat + b_org, b_first, cudaMemcpyHostToDevice, d.stream),
+       "cudaMemcpyAsync");
     const double* org_dev = nullptr;
     if (seg_origin && ns > 0) {
-      GCK(d.origin.reserve(3 * static_cast<size_t>(ns)));
-      GCK(cudaMemcpyAsync(d.origin.p, d.stage.p + b_pos + b_quat, b_org, cudaMemcpyHostToDevice, d.stream));
+      if (!ck(d.origin.reserve(3 * static_cast<size_t>(ns)), "cudaMalloc")) return;
+      ck(cudaMemcpyAsync(d.origin.p, d.stage.p + b_pos + b_quat, b_org, cudaMemcpyHostToDevice, d.stream),
+         "cudaMemcpyAsync");
       org_dev = d.origin.p;
     }
-    if (ns > 0) {
+    if (ns > 0 && rcs[i] == A3D_OK) {
       // record layout on the device: five arrays of `per` words (struct of arrays)
       unsigned long long* r = d.rec.p;
       const int rc = a3d_compute_gains_dev(d.ctx, caster->c[i], eval->e[i], nvw, d.pos.p, d.quat.p, d.first.p, ns,
@@ -480,9 +493,20 @@ int a3d_group_compute_gains(a3d_group* g, const a3d_group_caster* caster, const 
                                            reinterpret_cast<uint64_t*>(r + 2 * per),
                                            want_dig ? reinterpret_cast<uint64_t*>(r + 3 * per) : nullptr,
                                            want_sdig ? reinterpret_cast<uint64_t*>(r + 4 * per) : nullptr, org_dev);
-      if (rc) return sub_fail(g, i, rc);
+      if (rc) {
+        rcs[i] = rc;
+        errs[i] = std::string("GPU ") + std::to_string(d.id) + ": " + a3d_last_error(d.ctx);
+      }
     }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int i = 1; i < N; ++i) th.emplace_back(issue, i);
+    issue(0);
+    for (auto& t : th) t.join();
   }
+  for (int i = 0; i < N; ++i)
+    if (rcs[i] != A3D_OK) return g->fail(rcs[i], errs[i]);
   const unsigned long long* gathered = g->dev[0].rec.p;
   if (N > 1) {
     NCK(g_nccl.GroupStart());
