@@ -488,6 +488,85 @@ int runAdapter(char** argv) {
   return 0;
 }
 
+// ---- device-free: the updater chain and updateTree on a hand-made tree ----------------------------
+// An evaluator without a sensor: the gain of a segment is the x coordinate of its end point times a
+// factor that the test changes between evaluation and update ("the map changed").
+class TestPlainEvaluator : public TrajectoryEvaluator {
+ public:
+  explicit TestPlainEvaluator(PlannerI& planner) : TrajectoryEvaluator(planner) {}
+  bool computeGain(TrajectorySegment* t) override {
+    ++n_gain_calls;
+    t->gain = factor * t->trajectory.back().position_W.x();
+    return true;
+  }
+  static double factor;
+  static int n_gain_calls;
+  static ModuleFactoryRegistry::Registration<TestPlainEvaluator> registration;
+};
+double TestPlainEvaluator::factor = 1.0;
+int TestPlainEvaluator::n_gain_calls = 0;
+ModuleFactoryRegistry::Registration<TestPlainEvaluator> TestPlainEvaluator::registration("TestPlainEvaluator");
+
+void printTree(std::ostream& out, const TrajectorySegment& s, const std::string& path) {
+  out << "node " << (path.empty() ? "root" : path) << " " << s.gain << " " << s.cost << " " << s.value << "\n";
+  for (size_t i = 0; i < s.children.size(); ++i)
+    printTree(out, *s.children[i], path + (path.empty() ? "" : ".") + std::to_string(static_cast<int>(
+                                              s.children[i]->trajectory.back().position_W.y())));
+}
+
+// tree <yaml>: root at x = 0; children named by the y coordinate of their end point:
+//   1 (x=5) -> 11 (x=6) -> 111 (x=1)       2 (x=2) -> 21 (x=9)       3 (x=40, far away) -> 31 (x=8)
+int runTree(char** argv) {
+  YamlTree tree;
+  std::string err;
+  if (!tree.loadFile(argv[2], &err)) {
+    std::cerr << err << "\n";
+    return 2;
+  }
+  TestPlanner planner(tree);
+  planner.evaluator_ = planner.factory_.createModule<TrajectoryEvaluator>("/trajectory_evaluator", planner, true);
+  TrajectoryEvaluator* eval = planner.evaluator_.get();
+  TrajectorySegment root;
+  auto point = [](double x, double y) {
+    EigenTrajectoryPoint p;
+    p.position_W = Eigen::Vector3d(x, y, 0.0);
+    p.orientation_W_B = Eigen::Quaterniond(1, 0, 0, 0);
+    return p;
+  };
+  root.trajectory.push_back(point(0, 0));
+  auto add = [&](TrajectorySegment* parent, double x, int name) {
+    TrajectorySegment* c = parent->spawnChild();
+    c->trajectory.push_back(parent->trajectory.back());
+    c->trajectory.push_back(point(x, name));
+    return c;
+  };
+  TrajectorySegment* n1 = add(&root, 5, 1);
+  TrajectorySegment* n11 = add(n1, 6, 11);
+  add(n11, 1, 111);
+  TrajectorySegment* n2 = add(&root, 2, 2);
+  add(n2, 9, 21);
+  TrajectorySegment* n3 = add(&root, 40, 3);
+  add(n3, 8, 31);
+  std::vector<TrajectorySegment*> all;
+  root.getTree(&all);
+  for (TrajectorySegment* s : all) {
+    if (s == &root) continue;
+    eval->computeGain(s);
+    eval->computeCost(s);
+    eval->computeValue(s);
+  }
+  printTree(std::cout, root, "");
+  TestPlainEvaluator::factor = 2.0;
+  TestPlainEvaluator::n_gain_calls = 0;
+  planner.position_ = Eigen::Vector3d(0, 0, 0);
+  const int removed = eval->updateTree(&root);
+  std::cout << "removed " << removed << " gain_calls " << TestPlainEvaluator::n_gain_calls << "\n";
+  printTree(std::cout, root, "");
+  // the per-segment contract on a survivor and on a segment the chain drops
+  std::cout << "single " << eval->updateSegment(root.children[0].get()) << "\n";
+  return 0;
+}
+
 // The planner's evaluator update step (online_planner.cpp:679-693) through the updater chain the YAML
 // names: evaluate a chain of segments on the first map, overwrite blocks from the second map file,
 // updateTree(), print what is left.  mode "stored": the segments' lists live on the device
@@ -648,11 +727,12 @@ int main(int argc, char** argv) {
     if (argc >= 6 && std::strcmp(argv[1], "adapter") == 0) return runAdapter(argv);
     if (argc >= 8 && std::strcmp(argv[1], "update") == 0) return runUpdate(argv);
     if (argc >= 6 && std::strcmp(argv[1], "layer") == 0) return runLayer(argv);
+    if (argc >= 3 && std::strcmp(argv[1], "tree") == 0) return runTree(argv);
   } catch (const std::exception& e) {
     std::cerr << "exception: " << e.what() << "\n";
     return 3;
   }
-  std::cerr << "usage: test_host config <yaml> [ns] | gains|yaw|adapter|layer <yaml> <map.bin> <segments.bin> <out.txt> | "
+  std::cerr << "usage: test_host config <yaml> [ns] | tree <yaml> | gains|yaw|adapter|layer <yaml> <map.bin> <segments.bin> <out.txt> | "
                "update <yaml> <map.bin> <segments.bin> <out.txt> <map2.bin> stored|host\n";
   return 1;
 }

@@ -80,6 +80,38 @@ def test_reference_planner_configs_load_unchanged(built):
         subprocess.run([EXE, "config", os.path.join(cfg, f)], capture_output=True, check=True)
 
 
+def test_updater_chain_and_update_tree_without_a_device(built):
+    """evaluator_updater chain from YAML (ConstrainedUpdater -> UpdateAll -> PruneDirect, parameters and
+    semantics of constrained_updater.cpp:17-30, update_all.cpp:16-27, prune_direct.cpp:33-39) through
+    TrajectoryEvaluator::updateTree on a hand-made tree, no GPU involved: only the segments the
+    constraint lets through are evaluated again, a dropped segment takes its subtree with it, the
+    others keep their numbers; updateSegment is the one-element case."""
+    out = subprocess.run([EXE, "tree", os.path.join(GOLD, "planner_update_tree_cpu.yaml")], capture_output=True,
+                         text=True, check=True).stdout
+    blocks, cur = [], None
+    for line in out.splitlines():
+        t = line.split()
+        if t[0] == "node":
+            if t[1] == "root":
+                cur = {}
+                blocks.append(cur)
+            cur[t[1]] = tuple(float(x) for x in t[2:5])
+        elif t[0] == "removed":
+            removed, calls = int(t[1]), int(t[3])
+        elif t[0] == "single":
+            single = int(t[1])
+    before, after = blocks
+    # gain = x of the end point, cost = 1 (TestSegmentLength at yaw 0), value = gain - 100 cost
+    assert before == {"root": (0, 0, 0), "1": (5, 1, -95), "1.11": (6, 1, -94), "1.11.111": (1, 1, -99),
+                      "2": (2, 1, -98), "2.21": (9, 1, -91), "3": (40, 1, -60), "3.31": (8, 1, -92)}
+    # within 10 m of the robot and above gain 1.5: segments 1 and 2 -> evaluated again with the doubled
+    # factor (10 and 4); 2 falls below PruneDirect's 5 and goes with its child; the rest is untouched
+    assert calls == 2 and removed == 2
+    assert after == {"root": (0, 0, 0), "1": (10, 1, -90), "1.11": (6, 1, -94), "1.11.111": (1, 1, -99),
+                     "3": (40, 1, -60), "3.31": (8, 1, -92)}
+    assert single == 1
+
+
 def write_inputs(tmp, m, pos, quat, pts_per_seg, dt_ns):
     mp, sp = os.path.join(tmp, "map.bin"), os.path.join(tmp, "segments.bin")
     with open(mp, "wb") as f:
