@@ -2071,13 +2071,15 @@ int a3d_filter_not_in(a3d_ctx* ctx, int64_t n, const double* centres, int64_t m,
   CK(ctx->sc_pts.reserve(3 * n));
   CK(ctx->sc_out.reserve(3 * m));
   CK(ctx->sc_u8.reserve(n));
+  if (m >= (1ll << 30)) return ctx->fail(A3D_ERR_INVALID, "list too long");
+  CK(ctx->sc_first.reserve(filter_table_slots(m)));  // (hash set of the ancestor's entries)
   CK(cudaMemcpyAsync(ctx->sc_pts.p, centres, 24 * static_cast<size_t>(n), cudaMemcpyHostToDevice,
                      ctx->stream));
   CK(cudaMemcpyAsync(ctx->sc_out.p, other, 24 * static_cast<size_t>(m), cudaMemcpyHostToDevice,
                      ctx->stream));
   CK(cudaMemcpyAsync(ctx->sc_u8.p, keep_inout, n, cudaMemcpyHostToDevice, ctx->stream));
-  launch_filter_not_in(ctx->stream, n, ctx->sc_pts.p, m, ctx->sc_out.p, ctx->sc_u8.p);
-  ctx->launches++;
+  launch_filter_not_in(ctx->stream, n, ctx->sc_pts.p, m, ctx->sc_out.p, ctx->sc_u8.p, ctx->sc_first.p);
+  ctx->launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(keep_inout, ctx->sc_u8.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

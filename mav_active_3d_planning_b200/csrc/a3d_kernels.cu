@@ -727,34 +727,75 @@ int cast_gain_block_threads() { return kCastBlock; }
 // ---------------------------------------------------------------------------------------------
 // clear_from_parents (simulated_sensor_evaluator.cpp:60-76): keep[i] = 0 if centre i occurs anywhere
 // in the ancestor's stored list (exact double comparison, like std::find on Eigen::Vector3d).
-__global__ void k_filter_not_in(long long n, const double* __restrict__ a, long long m,
-                                const double* __restrict__ other, uint8_t* __restrict__ keep) {
-  __shared__ double tile[256 * 3];
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  double x = 0, y = 0, z = 0;
-  if (i < n) {
-    x = a[3 * i];
-    y = a[3 * i + 1];
-    z = a[3 * i + 2];
+// The ancestor's list goes into an open-addressing hash set of entry indices (linear probing, load
+// <= 1/2), the new list probes it: O(n + m) instead of the n x m comparisons of the literal loop.
+// Equality is operator== on the three doubles: -0.0 equals 0.0 (hashed as 0.0), a NaN equals nothing
+// (never inserted, never found).
+__device__ __forceinline__ bool centre_hash(const double* __restrict__ c, uint32_t* h_out) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double v = c[k];
+    ok &= (v == v);
+    unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v == 0.0 ? 0.0 : v));
+    h = (h ^ bits) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 29;
   }
-  bool found = false;
-  for (long long t0 = 0; t0 < m; t0 += 256) {
-    const int cnt = static_cast<int>(min(256LL, m - t0));
-    __syncthreads();
-    for (int k = threadIdx.x; k < cnt * 3; k += blockDim.x) tile[k] = other[3 * t0 + k];
-    __syncthreads();
-    if (i < n && !found) {
-      for (int k = 0; k < cnt; ++k)
-        found |= (tile[3 * k] == x) & (tile[3 * k + 1] == y) & (tile[3 * k + 2] == z);
+  *h_out = static_cast<uint32_t>(h ^ (h >> 32));
+  return ok;
+}
+__device__ __forceinline__ bool centre_equal(const double* __restrict__ a, const double* __restrict__ b) {
+  return (a[0] == b[0]) & (a[1] == b[1]) & (a[2] == b[2]);
+}
+
+__global__ void k_centre_set_build(long long m, const double* __restrict__ other, int* __restrict__ table,
+                                   uint32_t mask) {
+  const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (j >= m) return;
+  const double* c = other + 3 * j;
+  uint32_t h;
+  if (!centre_hash(c, &h)) return;
+  for (uint32_t s = h & mask;; s = (s + 1) & mask) {
+    const int old = atomicCAS(&table[s], -1, static_cast<int>(j));
+    if (old < 0) return;                                     // claimed an empty slot
+    if (centre_equal(other + 3 * static_cast<long long>(old), c)) return;  // already present
+  }
+}
+
+__global__ void k_filter_not_in(long long n, const double* __restrict__ a, const double* __restrict__ other,
+                                const int* __restrict__ table, uint32_t mask, uint8_t* __restrict__ keep) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double* c = a + 3 * i;
+  uint32_t h;
+  if (!centre_hash(c, &h)) return;
+  for (uint32_t s = h & mask;; s = (s + 1) & mask) {
+    const int j = table[s];
+    if (j < 0) return;
+    if (centre_equal(other + 3 * static_cast<long long>(j), c)) {
+      keep[i] = 0;
+      return;
     }
   }
-  if (i < n && found) keep[i] = 0;
+}
+
+// table: filter_table_slots(m) ints of scratch
+size_t filter_table_slots(long long m) {
+  size_t cap = 64;
+  while (cap < 2 * static_cast<size_t>(m)) cap <<= 1;
+  return cap;
 }
 
 void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long long m,
-                          const double* other, uint8_t* keep) {
+                          const double* other, uint8_t* keep, int* table) {
   if (n <= 0 || m <= 0) return;
-  k_filter_not_in<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(n, a, m, other, keep);
+  const size_t cap = filter_table_slots(m);
+  cudaMemsetAsync(table, 0xFF, cap * sizeof(int), st);
+  k_centre_set_build<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(m, other, table,
+                                                                             static_cast<uint32_t>(cap - 1));
+  k_filter_not_in<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(n, a, other, table,
+                                                                          static_cast<uint32_t>(cap - 1), keep);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -121,8 +121,9 @@ void launch_cast_gain(cudaStream_t st, const MapView& m, const CasterView& c, co
 void launch_gain_from_voxels(cudaStream_t st, const MapView& m, const EvalView& e, long long n,
                              const double* centres, unsigned long long* counters /*8*/,
                              uint8_t* keep, D3 origin, double* gain_acc /*1, VoxelWeight*/);
+size_t filter_table_slots(long long m);  // ints of scratch launch_filter_not_in needs for a list of m entries
 void launch_filter_not_in(cudaStream_t st, long long n, const double* a, long long m,
-                          const double* other, uint8_t* keep);
+                          const double* other, uint8_t* keep, int* table);
 void launch_list_pipeline(cudaStream_t st, const MapView& m, const EvalView& e, const ListBatch& lb);
 void launch_build_sets(cudaStream_t st, int n, const unsigned long long* const* lists, const long long* counts,
                        unsigned long long* const* tables, const uint32_t* masks);

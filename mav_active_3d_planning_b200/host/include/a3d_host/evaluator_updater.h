@@ -7,6 +7,9 @@
 //                           (a3d_store_refold) instead of one computeGainFromVisibleVoxels per segment
 //                           (simulated_sensor_updater.cpp:18-22),
 //   UpdateAll               re-casts every segment in one batch (update_all.cpp:16-27),
+//   YawPlanningUpdater      re-evaluates the orientation copies of ALL segments in reach as one cast
+//                           (yaw_planning_updaters.cpp:56-119), YawPlanningUpdateAdapter hands the active
+//                           copies of all segments to its following updater as one batch (:21-41),
 // and the host-only stages (PruneDirect, ConstrainedUpdater, ResetTree, UpdateNothing) are filters over
 // the flags.  updateSegment(segment) — the reference's per-segment contract — is the one-element
 // batch (EvaluatorUpdater::updateSegment).  Names, parameters and defaults are the reference's, so
@@ -98,6 +101,35 @@ class SimulatedSensorUpdater : public ChainedUpdater {  // simulated_sensor_upda
  protected:
   static ModuleFactoryRegistry::Registration<SimulatedSensorUpdater> registration;
   trajectory_evaluator::SimulatedSensorEvaluator* evaluator_;
+};
+
+// yaw_planning_updaters.cpp:14-52 — lets updaters that know nothing about YawPlanningInfo work on the
+// active orientation of every segment: parameter dynamic_trajectories.
+class YawPlanningUpdateAdapter : public ChainedUpdater {
+ public:
+  explicit YawPlanningUpdateAdapter(PlannerI& planner) : ChainedUpdater(planner) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+  void updateSegments(const std::vector<TrajectorySegment*>& segments, std::vector<uint8_t>* alive) override;
+
+ protected:
+  static ModuleFactoryRegistry::Registration<YawPlanningUpdateAdapter> registration;
+  bool p_dynamic_trajectories_;
+};
+
+// yaw_planning_updaters.cpp:54-138 — every orientation of a segment in reach is evaluated again, the best
+// one becomes the segment: parameters select_by_value, dynamic_trajectories, update_range (default -1:
+// nothing is re-evaluated), update_gain.
+class YawPlanningUpdater : public ChainedUpdater {
+ public:
+  explicit YawPlanningUpdater(PlannerI& planner) : ChainedUpdater(planner), evaluator_(nullptr) {}  // NOLINT
+  void setupFromParamMap(Module::ParamMap* param_map) override;
+  void updateSegments(const std::vector<TrajectorySegment*>& segments, std::vector<uint8_t>* alive) override;
+
+ protected:
+  static ModuleFactoryRegistry::Registration<YawPlanningUpdater> registration;
+  trajectory_evaluator::YawPlanningEvaluator* evaluator_;
+  bool p_select_by_value_, p_dynamic_trajectories_;
+  double p_update_range_, p_update_gain_;
 };
 
 }  // namespace evaluator_updater

@@ -228,6 +228,12 @@ class YawPlanningEvaluator : public TrajectoryEvaluator {
   // additive: computeGain for many segments, all their orientations in one launch
   virtual bool computeGains(const std::vector<TrajectorySegment*>& segments);
   TrajectoryEvaluator* followingEvaluator() { return following_evaluator_.get(); }
+  // for evaluator_updater::YawPlanningUpdater: the gains of oriented copies (of any number of segments)
+  // in one launch where the following evaluator can, and a copy turned to another yaw
+  bool computeOrientationGains(const std::vector<TrajectorySegment*>& copies);
+  void turnOrientation(TrajectorySegment* copy, double start_yaw, double target_yaw) {
+    setTrajectoryYaw(copy, start_yaw, target_yaw);
+  }
 
  protected:
   std::unique_ptr<TrajectoryEvaluator> following_evaluator_;

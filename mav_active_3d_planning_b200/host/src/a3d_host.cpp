@@ -1148,6 +1148,14 @@ bool YawPlanningEvaluator::evaluateOrientations(const std::vector<TrajectorySegm
   return ok;
 }
 
+bool YawPlanningEvaluator::computeOrientationGains(const std::vector<TrajectorySegment*>& copies) {
+  const bool by_value = p_select_by_value_;  // gains only: the caller decides about cost and value
+  p_select_by_value_ = false;
+  const bool ok = evaluateOrientations(copies);
+  p_select_by_value_ = by_value;
+  return ok;
+}
+
 bool YawPlanningEvaluator::computeGains(const std::vector<TrajectorySegment*>& segments) {
   std::vector<TrajectorySegment*> copies;
   copies.reserve(segments.size() * p_n_directions_);

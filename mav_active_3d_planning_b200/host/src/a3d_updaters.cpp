@@ -129,5 +129,109 @@ void SimulatedSensorUpdater::updateSegments(const std::vector<TrajectorySegment*
   follow(segments, alive);
 }
 
+ModuleFactoryRegistry::Registration<YawPlanningUpdateAdapter> YawPlanningUpdateAdapter::registration(
+    "YawPlanningUpdateAdapter");
+void YawPlanningUpdateAdapter::setupFromParamMap(Module::ParamMap* param_map) {
+  setParam<bool>(param_map, "dynamic_trajectories", &p_dynamic_trajectories_, false);
+  ChainedUpdater::setupFromParamMap(param_map);
+}
+void YawPlanningUpdateAdapter::updateSegments(const std::vector<TrajectorySegment*>& segments,
+                                              std::vector<uint8_t>* alive) {
+  // the active orientation of every segment, brought up to date with its segment, as ONE batch for the
+  // following updater; what that one decides about a copy does not remove the segment (:40 returns true)
+  std::vector<TrajectorySegment*> owners, active;
+  for (size_t i = 0; i < segments.size(); ++i) {
+    if (!(*alive)[i]) continue;
+    auto* info = dynamic_cast<trajectory_evaluator::YawPlanningInfo*>(segments[i]->info.get());
+    if (!info || info->orientations.empty()) continue;
+    TrajectorySegment& copy = info->orientations[info->active_orientation];
+    if (p_dynamic_trajectories_) copy.trajectory = segments[i]->trajectory;
+    copy.parent = segments[i]->parent;
+    owners.push_back(segments[i]);
+    active.push_back(&copy);
+  }
+  if (active.empty()) return;
+  std::vector<uint8_t> flags(active.size(), 1);
+  following_updater_->updateSegments(active, &flags);
+  for (size_t k = 0; k < active.size(); ++k) {
+    owners[k]->gain = active[k]->gain;
+    owners[k]->cost = active[k]->cost;
+    owners[k]->value = active[k]->value;
+  }
+}
+
+ModuleFactoryRegistry::Registration<YawPlanningUpdater> YawPlanningUpdater::registration("YawPlanningUpdater");
+void YawPlanningUpdater::setupFromParamMap(Module::ParamMap* param_map) {
+  setParam<bool>(param_map, "select_by_value", &p_select_by_value_, false);
+  setParam<bool>(param_map, "dynamic_trajectories", &p_dynamic_trajectories_, false);
+  setParam<double>(param_map, "update_range", &p_update_range_, -1.0);
+  setParam<double>(param_map, "update_gain", &p_update_gain_, 0.0);
+  ChainedUpdater::setupFromParamMap(param_map);
+  evaluator_ = dynamic_cast<trajectory_evaluator::YawPlanningEvaluator*>(
+      planner_.getFactory().readLinkableModule("YawPlanningEvaluator"));
+}
+void YawPlanningUpdater::updateSegments(const std::vector<TrajectorySegment*>& segments,
+                                        std::vector<uint8_t>* alive) {
+  using trajectory_evaluator::YawPlanningInfo;
+  if (!evaluator_) {
+    planner_.printError("'YawPlanningUpdater' requires a yaw planning evaluator!");
+    follow(segments, alive);
+    return;
+  }
+  // pass 1: copies follow a segment that changed; the copies to evaluate again, of all segments
+  const Eigen::Vector3d here = planner_.getCurrentPosition();
+  std::vector<TrajectorySegment*> owners, again;
+  for (size_t i = 0; i < segments.size(); ++i) {
+    TrajectorySegment* seg = segments[i];
+    if (!(*alive)[i] || !seg->parent) continue;
+    auto* info = dynamic_cast<YawPlanningInfo*>(seg->info.get());
+    if (!info || info->orientations.empty()) continue;
+    owners.push_back(seg);
+    const TrajectorySegment& act = info->orientations[info->active_orientation];
+    if (p_dynamic_trajectories_ && (act.gain != seg->gain || act.parent != seg->parent)) {
+      for (TrajectorySegment& o : info->orientations) {
+        const double yaw = o.trajectory.back().getYaw();
+        o.parent = seg->parent;
+        o.trajectory = seg->trajectory;
+        evaluator_->turnOrientation(&o, seg->trajectory.front().getYaw(), yaw);
+      }
+    }
+    if ((here - seg->trajectory.back().position_W).norm() <= p_update_range_)
+      for (TrajectorySegment& o : info->orientations)
+        if (o.gain > p_update_gain_) again.push_back(&o);
+  }
+  // one cast for all of them
+  evaluator_->computeOrientationGains(again);
+  // pass 2: the best orientation becomes the segment (first one wins ties; the first copy's cost and
+  // value are taken as they are, :86-90)
+  TrajectoryEvaluator* following = evaluator_->followingEvaluator();
+  for (TrajectorySegment* seg : owners) {
+    auto* info = static_cast<YawPlanningInfo*>(seg->info.get());
+    int best = 0;
+    double best_score = p_select_by_value_ ? info->orientations[0].value : info->orientations[0].gain;
+    for (size_t k = 1; k < info->orientations.size(); ++k) {
+      TrajectorySegment& o = info->orientations[k];
+      if (p_select_by_value_) {
+        following->computeCost(&o);
+        following->computeValue(&o);
+      }
+      const double score = p_select_by_value_ ? o.value : o.gain;
+      if (score > best_score) {
+        best = static_cast<int>(k);
+        best_score = score;
+      }
+    }
+    info->active_orientation = best;
+    const TrajectorySegment& chosen = info->orientations[best];
+    seg->trajectory = chosen.trajectory;
+    seg->gain = chosen.gain;
+    if (p_select_by_value_) {
+      seg->cost = chosen.cost;
+      seg->value = chosen.value;
+    }
+  }
+  follow(segments, alive);
+}
+
 }  // namespace evaluator_updater
 }  // namespace active_3d_planning

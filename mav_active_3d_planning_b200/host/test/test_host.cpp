@@ -567,6 +567,100 @@ int runTree(char** argv) {
   return 0;
 }
 
+// ---- device-free: the yaw-planning updaters (yaw_planning_updaters.cpp) ------------------------------
+// A following evaluator whose gain depends on where the segment looks at its end: 10 + 5 cos(yaw - phase),
+// times a factor; the test turns the phase between evaluation and update ("what is worth seeing moved").
+class TestYawEvaluator : public TrajectoryEvaluator {
+ public:
+  explicit TestYawEvaluator(PlannerI& planner) : TrajectoryEvaluator(planner) {}
+  bool computeGain(TrajectorySegment* t) override {
+    ++n_gain_calls;
+    t->gain = factor * (10.0 + 5.0 * std::cos(t->trajectory.back().getYaw() - phase));
+    return true;
+  }
+  static double factor, phase;
+  static int n_gain_calls;
+  static ModuleFactoryRegistry::Registration<TestYawEvaluator> registration;
+};
+double TestYawEvaluator::factor = 1.0;
+double TestYawEvaluator::phase = 0.0;
+int TestYawEvaluator::n_gain_calls = 0;
+ModuleFactoryRegistry::Registration<TestYawEvaluator> TestYawEvaluator::registration("TestYawEvaluator");
+// An updater that knows nothing about yaw planning: triples the gain of what it is given.
+class TestTripleGain : public EvaluatorUpdater {
+ public:
+  explicit TestTripleGain(PlannerI& planner) : EvaluatorUpdater(planner) {}
+  void setupFromParamMap(Module::ParamMap*) override {}
+  void updateSegments(const std::vector<TrajectorySegment*>& segments, std::vector<uint8_t>* alive) override {
+    ++n_batches;
+    for (size_t i = 0; i < segments.size(); ++i)
+      if ((*alive)[i]) segments[i]->gain *= 3.0;
+  }
+  static int n_batches;
+  static ModuleFactoryRegistry::Registration<TestTripleGain> registration;
+};
+int TestTripleGain::n_batches = 0;
+ModuleFactoryRegistry::Registration<TestTripleGain> TestTripleGain::registration("TestTripleGain");
+
+// yawtree <yaml>: root at the origin, children 1 (ends at x=5), 2 (x=2, child 21 at x=3), 3 (x=40: out of reach)
+int runYawTree(char** argv) {
+  YamlTree tree;
+  std::string err;
+  if (!tree.loadFile(argv[2], &err)) {
+    std::cerr << err << "\n";
+    return 2;
+  }
+  TestPlanner planner(tree);
+  planner.evaluator_ = planner.factory_.createModule<TrajectoryEvaluator>("/trajectory_evaluator", planner, true);
+  TrajectoryEvaluator* eval = planner.evaluator_.get();
+  TrajectorySegment root;
+  auto point = [](double x, double y) {
+    EigenTrajectoryPoint p;
+    p.position_W = Eigen::Vector3d(x, y, 0.0);
+    p.orientation_W_B = Eigen::Quaterniond(1, 0, 0, 0);
+    return p;
+  };
+  root.trajectory.push_back(point(0, 0));
+  auto add = [&](TrajectorySegment* parent, double x, int name) {
+    TrajectorySegment* c = parent->spawnChild();
+    c->trajectory.push_back(parent->trajectory.back());
+    c->trajectory.push_back(point(x, name));
+    return c;
+  };
+  add(&root, 5, 1);
+  add(add(&root, 2, 2), 3, 21);
+  add(&root, 40, 3);
+  std::vector<TrajectorySegment*> all;
+  root.getTree(&all);
+  auto print = [&]() {
+    for (TrajectorySegment* s : all) {
+      if (s == &root) continue;
+      auto* info = dynamic_cast<trajectory_evaluator::YawPlanningInfo*>(s->info.get());
+      std::cout << "node " << static_cast<int>(s->trajectory.back().position_W.y()) << " " << s->gain << " " << s->cost
+                << " " << s->value << " " << s->trajectory.back().getYaw() << " " << (info ? info->active_orientation : -1)
+                << " " << (info ? info->orientations[info->active_orientation].gain : 0.0) << "\n";
+    }
+  };
+  std::cout.precision(12);
+  for (TrajectorySegment* s : all) {
+    if (s == &root) continue;
+    eval->computeGain(s);
+    eval->computeCost(s);
+    eval->computeValue(s);
+  }
+  std::cout << "gain_calls " << TestYawEvaluator::n_gain_calls << "\n";
+  print();
+  TestYawEvaluator::phase = M_PI / 2;
+  TestYawEvaluator::factor = 2.0;
+  TestYawEvaluator::n_gain_calls = 0;
+  planner.position_ = Eigen::Vector3d(0, 0, 0);
+  const int removed = eval->updateTree(&root);
+  std::cout << "removed " << removed << " gain_calls " << TestYawEvaluator::n_gain_calls << " follower_batches "
+            << TestTripleGain::n_batches << "\n";
+  print();
+  return 0;
+}
+
 // The planner's evaluator update step (online_planner.cpp:679-693) through the updater chain the YAML
 // names: evaluate a chain of segments on the first map, overwrite blocks from the second map file,
 // updateTree(), print what is left.  mode "stored": the segments' lists live on the device
@@ -728,11 +822,12 @@ int main(int argc, char** argv) {
     if (argc >= 8 && std::strcmp(argv[1], "update") == 0) return runUpdate(argv);
     if (argc >= 6 && std::strcmp(argv[1], "layer") == 0) return runLayer(argv);
     if (argc >= 3 && std::strcmp(argv[1], "tree") == 0) return runTree(argv);
+    if (argc >= 3 && std::strcmp(argv[1], "yawtree") == 0) return runYawTree(argv);
   } catch (const std::exception& e) {
     std::cerr << "exception: " << e.what() << "\n";
     return 3;
   }
-  std::cerr << "usage: test_host config <yaml> [ns] | tree <yaml> | gains|yaw|adapter|layer <yaml> <map.bin> <segments.bin> <out.txt> | "
+  std::cerr << "usage: test_host config <yaml> [ns] | tree <yaml> | yawtree <yaml> | gains|yaw|adapter|layer <yaml> <map.bin> <segments.bin> <out.txt> | "
                "update <yaml> <map.bin> <segments.bin> <out.txt> <map2.bin> stored|host\n";
   return 1;
 }

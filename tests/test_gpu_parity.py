@@ -861,3 +861,33 @@ def test_esdf_only_delta_keeps_tsdf_weights(capi, O, room02):
     got = ctx.compute_gains(caster, ev, pos, quat, digests=False, set_digests=False)
     assert np.allclose(got["gain"], want["gain"], rtol=GAIN_RTOL, atol=0)
     ctx.close()
+
+
+def test_filter_not_in_is_std_find_on_the_three_doubles(capi):
+    """a3d_filter_not_in (clear_from_parents, simulated_sensor_evaluator.cpp:60-76) as a hash-set probe:
+    same answers as std::find with operator== on Eigen::Vector3d — duplicates on both sides, -0.0 == 0.0,
+    NaN equal to nothing, entries that differ in one ulp of one coordinate, empty lists."""
+    rng = np.random.default_rng(11)
+    ctx = capi.Context(0)
+    for n, m in [(0, 5), (5, 0), (1, 1), (1000, 37), (20000, 150000), (150000, 20000)]:
+        grid = rng.integers(-40, 40, (max(m, 1), 3)) * 0.1 + 0.05
+        other = grid[:m].copy()
+        a = np.concatenate([other[rng.integers(0, max(m, 1), n // 2)] if m else np.zeros((0, 3)),
+                            rng.integers(-40, 40, (n - (n // 2 if m else 0), 3)) * 0.1 + 0.05])
+        if n >= 1000:
+            a[0] = other[0]; a[0, 1] = np.nextafter(a[0, 1], 1e9)      # one ulp off: not equal
+            a[1] = (0.0, -0.0, 0.0); other[1] = (-0.0, 0.0, -0.0)        # signed zeros are equal
+            a[2] = (np.nan, 1.0, 2.0); other[2] = (np.nan, 1.0, 2.0)     # NaN equals nothing
+            a[3] = a[4] = other[5]                                       # duplicates
+            other[6] = other[5]
+        keep = ctx.filter_not_in(a, other)
+        with np.errstate(invalid="ignore"):
+            if n and m:
+                # exact reference by sorting on the bit patterns (zeros canonicalised, NaN rows never match)
+                ca, co = a + 0.0, other + 0.0
+                okey = {tuple(r) for r in co[~np.isnan(co).any(axis=1)].tolist()}
+                want = np.array([0 if (not np.isnan(r).any() and tuple(r) in okey) else 1 for r in ca], np.uint8)
+            else:
+                want = np.ones(n, np.uint8)
+        assert np.array_equal(keep, want), (n, m)
+    ctx.close()

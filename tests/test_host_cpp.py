@@ -112,6 +112,43 @@ def test_updater_chain_and_update_tree_without_a_device(built):
     assert single == 1
 
 
+def test_yaw_planning_updaters_without_a_device(built):
+    """YawPlanningUpdater -> YawPlanningUpdateAdapter -> (an updater that knows nothing about yaw planning)
+    from YAML, semantics of yaw_planning_updaters.cpp:21-41,56-119: the orientations of the segments in
+    reach are evaluated again as one batch and the best one becomes the segment; segments out of reach keep
+    their orientation; the adapter hands the ACTIVE copies on and copies gain / cost / value back (the
+    copies never had a cost or value, so the segment's become 0 like in the reference)."""
+    out = subprocess.run([EXE, "yawtree", os.path.join(GOLD, "planner_yaw_updaters_cpu.yaml")], capture_output=True,
+                         text=True, check=True).stdout
+    blocks, cur, info = [], None, {}
+    for line in out.splitlines():
+        t = line.split()
+        if t[0] == "gain_calls":
+            info["first_calls"] = int(t[1])
+            cur = {}
+            blocks.append(cur)
+        elif t[0] == "removed":
+            info.update(removed=int(t[1]), calls=int(t[3]), batches=int(t[5]))
+            cur = {}
+            blocks.append(cur)
+        elif t[0] == "node":
+            cur[int(t[1])] = tuple(float(x) for x in t[2:8])
+    before, after = blocks
+    # 4 segments x 4 orientations; gain 10 + 5 cos(yaw - 0): yaw 0 wins everywhere
+    assert info["first_calls"] == 16
+    for k in (1, 2, 21, 3):
+        assert before[k] == (15.0, 1.0, -85.0, 0.0, 0.0, 15.0)
+    # phase -> pi/2, factor 2: segments 1 and 2 end within 10 m of the robot -> 2 x 4 gains in the update,
+    # orientation 1 (yaw pi/2) now scores 2 * 15 = 30; the adapter's follower triples the active copy's gain
+    assert info == {"first_calls": 16, "removed": 0, "calls": 8, "batches": 1}
+    for k in (1, 2):
+        gain, cost, value, yaw, active, copy_gain = after[k]
+        assert (gain, cost, value, active, copy_gain) == (90.0, 0.0, 0.0, 1.0, 90.0)
+        assert abs(yaw - np.pi / 2) < 1e-9
+    for k in (21, 3):   # out of reach: orientation kept, only the adapter's follower acts
+        assert after[k] == (45.0, 0.0, 0.0, 0.0, 0.0, 45.0)
+
+
 def write_inputs(tmp, m, pos, quat, pts_per_seg, dt_ns):
     mp, sp = os.path.join(tmp, "map.bin"), os.path.join(tmp, "segments.bin")
     with open(mp, "wb") as f:
