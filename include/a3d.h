@@ -156,6 +156,11 @@ int a3d_map_upload_blocks(a3d_ctx* ctx, int n, const int32_t* block_idx, const f
    were written.  Distances, observed flags and the meta words are untouched. */
 int a3d_map_upload_weights(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* tsdf_weight,
                            uint8_t* applied_out);
+/* TSDF distances alone (the other member of the TSDF voxels a `tsdf_map_in` layer message carries), for
+   VoxbloxMap::getVoxelDistance (active_3d_planning_voxblox/src/map/voxblox.cpp:84-98).  Same contract as
+   a3d_map_upload_weights; the slab is allocated by the first call, blocks never sent read 0. */
+int a3d_map_upload_tsdf_distances(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* tsdf_distance,
+                                  uint8_t* applied_out);
 /* Same with payload pointers in device memory (e.g. the receive buffer of an NCCL broadcast);
    block_idx stays on the host. */
 int a3d_map_upload_blocks_dev(a3d_ctx* ctx, int n, const int32_t* block_idx,
@@ -168,7 +173,7 @@ int64_t a3d_map_num_blocks(const a3d_ctx* ctx);
 double a3d_map_voxel_size(const a3d_ctx* ctx);
 /* Batched map virtuals, n points (n×3 doubles):
    getVoxelState voxblox.cpp:48-60 | getVoxelCenter :66-81 | isObserved :43-45 |
-   getVoxelWeight :101-115 | EsdfMap::getDistanceAtPosition as used at :35-36,:50 */
+   getVoxelWeight :101-115 | getVoxelDistance :84-98 | EsdfMap::getDistanceAtPosition as used at :35-36,:50 */
 int a3d_map_voxel_state(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out);
 /* Same result as a3d_map_voxel_state, computed by the literal 8-lookup path that never reads the
    apron / meta acceleration structures (self-check of the device mirror). */
@@ -176,6 +181,9 @@ int a3d_map_voxel_state_literal(a3d_ctx* ctx, int64_t n, const double* pts, uint
 int a3d_map_voxel_center(a3d_ctx* ctx, int64_t n, const double* pts, double* out);
 int a3d_map_is_observed(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out);
 int a3d_map_voxel_weight(a3d_ctx* ctx, int64_t n, const double* pts, double* out);
+/* VoxbloxMap::getVoxelDistance (voxblox.cpp:84-98): the stored TSDF distance of the voxel a point falls in
+   (same voxel as getVoxelWeight); 0 without a block or before a3d_map_upload_tsdf_distances. */
+int a3d_map_voxel_tsdf_distance(a3d_ctx* ctx, int64_t n, const double* pts, double* out);
 int a3d_map_distance(a3d_ctx* ctx, int64_t n, const double* pts, double* dist, uint8_t* ok);
 /* Batched VoxbloxMap::isTraversable (voxblox.cpp:32-41): observed and interpolated ESDF distance >
    collision_radius — the collision checks of TrajectoryGenerator::checkTraversable

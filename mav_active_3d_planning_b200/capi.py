@@ -31,9 +31,9 @@ _EVAL_KINDS = {"VoxelTypeEvaluator": EVAL_VOXEL_TYPE, "NaiveEvaluator": EVAL_NAI
 # every symbol include/a3d.h declares
 EXPORTS = [
     "a3d_ctx_create", "a3d_ctx_destroy", "a3d_last_error", "a3d_ctx_stream", "a3d_last_kernel_ms", "a3d_last_stage_ms",
-    "a3d_kernel_launches", "a3d_set_option", "a3d_last_cast_kernel", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev", "a3d_map_upload_weights",
+    "a3d_kernel_launches", "a3d_set_option", "a3d_last_cast_kernel", "a3d_map_config", "a3d_map_upload_blocks", "a3d_map_upload_blocks_dev", "a3d_map_upload_weights", "a3d_map_upload_tsdf_distances",
     "a3d_map_remove_blocks", "a3d_map_clear", "a3d_map_num_blocks", "a3d_map_voxel_size",
-    "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight",
+    "a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed", "a3d_map_voxel_weight", "a3d_map_voxel_tsdf_distance",
     "a3d_map_distance", "a3d_map_traversable", "a3d_caster_create", "a3d_caster_destroy", "a3d_caster_get_info",
     "a3d_caster_direction", "a3d_eval_create", "a3d_eval_destroy", "a3d_compute_gains",
     "a3d_compute_gains_dev", "a3d_visible_voxels", "a3d_gain_from_voxels", "a3d_filter_not_in",
@@ -158,6 +158,7 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_map_upload_blocks.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     lib.a3d_map_upload_blocks_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     lib.a3d_map_upload_weights.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.a3d_map_upload_tsdf_distances.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.a3d_map_remove_blocks.argtypes = [vp, C.c_int, vp]
     lib.a3d_map_clear.argtypes = [vp]
     lib.a3d_map_num_blocks.argtypes = [vp]
@@ -165,7 +166,7 @@ def load_library(path: str = LIB_PATH):
     lib.a3d_map_voxel_size.argtypes = [vp]
     lib.a3d_map_voxel_size.restype = dbl
     for name in ("a3d_map_voxel_state", "a3d_map_voxel_state_literal", "a3d_map_voxel_center", "a3d_map_is_observed",
-                 "a3d_map_voxel_weight"):
+                 "a3d_map_voxel_weight", "a3d_map_voxel_tsdf_distance"):
         getattr(lib, name).argtypes = [vp, i64, vp, vp]
     lib.a3d_map_distance.argtypes = [vp, i64, vp, vp, vp]
     lib.a3d_map_traversable.argtypes = [vp, i64, vp, dbl, vp]
@@ -304,6 +305,16 @@ class Context:
                                                  _ptr(applied)))
         return applied.astype(bool)
 
+    def upload_tsdf_distances(self, block_idx, tsdf_distance):
+        """TSDF distances alone (VoxbloxMap::getVoxelDistance), for blocks the mirror holds; returns the
+        mask of blocks written."""
+        block_idx = np.ascontiguousarray(block_idx, np.int32)
+        tsdf_distance = np.ascontiguousarray(tsdf_distance, np.float32)
+        applied = np.zeros(block_idx.shape[0], np.uint8)
+        self._ck(self.lib.a3d_map_upload_tsdf_distances(self.h, block_idx.shape[0], _ptr(block_idx),
+                                                        _ptr(tsdf_distance), _ptr(applied)))
+        return applied.astype(bool)
+
     def upload_map(self, m):
         """Upload a synth.SynthMap."""
         self.map_config(m.voxel_size, m.vps)
@@ -352,6 +363,12 @@ class Context:
         pts = _pts(pts)
         out = np.empty(len(pts), np.float64)
         self._ck(self.lib.a3d_map_voxel_weight(self.h, len(pts), _ptr(pts), _ptr(out)))
+        return out
+
+    def voxel_tsdf_distance(self, pts):
+        pts = _pts(pts)
+        out = np.empty(len(pts), np.float64)
+        self._ck(self.lib.a3d_map_voxel_tsdf_distance(self.h, len(pts), _ptr(pts), _ptr(out)))
         return out
 
     def distance(self, pts):

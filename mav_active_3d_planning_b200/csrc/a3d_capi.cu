@@ -141,6 +141,7 @@ struct a3d_ctx {
   bool vol_stale = true;       // box changed (or never built): rebuilt lazily by vol_ensure()
   bool vol_on = false;         // d_vol holds the current map
   float* d_weight = nullptr;   // vps^3 floats per slot
+  float* d_tsdf = nullptr;     // vps^3 floats per slot: TSDF distances (getVoxelDistance), allocated on first upload
   size_t slab_slots = 0;
   bool has_weight = false;
   int P = 0, P3 = 0;
@@ -402,6 +403,10 @@ int slab_reserve(a3d_ctx* ctx, size_t n_slots, bool want_weight) {
       rc = slab_grow(ctx, &ctx->d_weight, ctx->slab_slots, cap, nv);
       if (rc) return rc;
     }
+    if (ctx->d_tsdf) {
+      rc = slab_grow(ctx, &ctx->d_tsdf, ctx->slab_slots, cap, nv);
+      if (rc) return rc;
+    }
     ctx->slab_slots = cap;
   }
   if (want_weight && !ctx->d_weight) {
@@ -625,6 +630,11 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
   }
   int rc = slab_reserve(ctx, static_cast<size_t>(ctx->next_slot), w != nullptr);
   if (rc) return rc;
+  if (ctx->d_tsdf)  // a block allocated by this call has no TSDF distances yet (its slot may be a reused one)
+    for (int i = 0; i < n; ++i)
+      if (slot_of[i] & kFreshSlot)
+        CK(cudaMemsetAsync(ctx->d_tsdf + static_cast<size_t>(slot_of[i] & ~kFreshSlot) * ctx->nv, 0,
+                           static_cast<size_t>(ctx->nv) * sizeof(float), ctx->stream));
   if (table_dirty) {
     if (ctx->h_table.empty() || 4 * ctx->slots.size() > ctx->h_table.size()) {
       table_rebuild(ctx, ctx->slots.size());
@@ -698,7 +708,8 @@ int point_query(a3d_ctx* ctx, int what, int64_t n, const double* pts, void* out0
   const size_t out0_bytes = static_cast<size_t>(n) * out0_elt;
   CK(ctx->sc_out.reserve((out0_bytes + 7) / 8));
   CK(ctx->sc_u8.reserve(n));
-  launch_point_query(ctx->stream, ctx->view(), what, n, ctx->sc_pts.p, ctx->sc_out.p, ctx->sc_u8.p,
+  launch_point_query(ctx->stream, ctx->view(), what, n, ctx->sc_pts.p, ctx->sc_out.p,
+                     what == kQueryTsdfDistance ? static_cast<void*>(ctx->d_tsdf) : static_cast<void*>(ctx->sc_u8.p),
                      arg);
   ctx->launches++;
   CK(cudaGetLastError());
@@ -929,6 +940,7 @@ void a3d_ctx_destroy(a3d_ctx* ctx) {
     if (evs) cudaEventDestroy(evs);
   if (ctx->d_dist) cudaFree(ctx->d_dist);
   if (ctx->d_weight) cudaFree(ctx->d_weight);
+  if (ctx->d_tsdf) cudaFree(ctx->d_tsdf);
   if (ctx->d_mword) cudaFree(ctx->d_mword);
   ctx->d_dir.release();
   if (ctx->d_vol) cudaFree(ctx->d_vol);
@@ -1006,7 +1018,9 @@ int a3d_map_config(a3d_ctx* ctx, float voxel_size, int vps) {
     if (ctx->d_dist) cudaFree(ctx->d_dist);
     if (ctx->d_mword) cudaFree(ctx->d_mword);
     if (ctx->d_weight) cudaFree(ctx->d_weight);
+    if (ctx->d_tsdf) cudaFree(ctx->d_tsdf);
     if (ctx->d_vol) cudaFree(ctx->d_vol);
+    ctx->d_tsdf = nullptr;
     ctx->d_dist = nullptr;
     ctx->d_mword = nullptr;
     ctx->d_weight = nullptr;
@@ -1059,6 +1073,32 @@ int a3d_map_upload_weights(a3d_ctx* ctx, int n, const int32_t* block_idx, const 
     if (applied_out) applied_out[i] = it != ctx->slots.end();
     if (it == ctx->slots.end()) continue;  // no ESDF block there yet: the caller keeps it
     CK(cudaMemcpyAsync(ctx->d_weight + static_cast<size_t>(it->second) * nv, tsdf_weight + static_cast<size_t>(i) * nv,
+                       nv * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return A3D_OK;
+}
+
+int a3d_map_upload_tsdf_distances(a3d_ctx* ctx, int n, const int32_t* block_idx, const float* tsdf_distance,
+                                  uint8_t* applied_out) {
+  if (!ctx) return A3D_ERR_INVALID;
+  if (!ctx->configured) return ctx->fail(A3D_ERR_STATE, "a3d_map_config must be called first");
+  if (n < 0 || (n > 0 && (!block_idx || !tsdf_distance))) return ctx->fail(A3D_ERR_INVALID, "null block payload");
+  if (n == 0) return A3D_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc = slab_reserve(ctx, static_cast<size_t>(std::max(ctx->next_slot, 1)), false);
+  if (rc) return rc;
+  const size_t nv = static_cast<size_t>(ctx->nv);
+  if (!ctx->d_tsdf) {
+    CK(cudaMalloc(&ctx->d_tsdf, ctx->slab_slots * nv * sizeof(float)));
+    CK(cudaMemsetAsync(ctx->d_tsdf, 0, ctx->slab_slots * nv * sizeof(float), ctx->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    const Key3 k{block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2]};
+    auto it = ctx->slots.find(k);
+    if (applied_out) applied_out[i] = it != ctx->slots.end();
+    if (it == ctx->slots.end()) continue;  // no ESDF block there yet: the caller keeps it
+    CK(cudaMemcpyAsync(ctx->d_tsdf + static_cast<size_t>(it->second) * nv, tsdf_distance + static_cast<size_t>(i) * nv,
                        nv * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1143,6 +1183,9 @@ int a3d_map_is_observed(a3d_ctx* ctx, int64_t n, const double* pts, uint8_t* out
 }
 int a3d_map_voxel_weight(a3d_ctx* ctx, int64_t n, const double* pts, double* out) {
   return point_query(ctx, kQueryWeight, n, pts, out, 8, nullptr);
+}
+int a3d_map_voxel_tsdf_distance(a3d_ctx* ctx, int64_t n, const double* pts, double* out) {
+  return point_query(ctx, kQueryTsdfDistance, n, pts, out, 8, nullptr);
 }
 int a3d_map_traversable(a3d_ctx* ctx, int64_t n, const double* pts, double collision_radius,
                         uint8_t* out) {

@@ -372,6 +372,15 @@ __global__ void k_point_query(MapView m, int what, long long n, const double* __
       case kQueryWeight:
         static_cast<double*>(out0)[i] = voxel_weight(m, p);
         break;
+      case kQueryTsdfDistance: {  // VoxbloxMap::getVoxelDistance (voxblox.cpp:84-98): same voxel as the weight
+        const float* tsdf = static_cast<const float*>(out1);
+        int v[3];
+        const int slot = tsdf ? nearest_voxel(m, p, v) : -1;
+        static_cast<double*>(out0)[i] =
+            slot < 0 ? 0.0
+                     : static_cast<double>(__ldg(tsdf + static_cast<size_t>(slot) * m.nv + v[0] + m.vps * (v[1] + m.vps * v[2])));
+        break;
+      }
       case kQueryTraversable: {  // VoxbloxMap::isTraversable (voxblox.cpp:32-41)
         float d = 0.0f;
         const bool ok = interp_distance_generic(m, __double2float_rn(p.x), __double2float_rn(p.y),

@@ -150,6 +150,7 @@ int cast_wave_max_diag();
 int cast_wave_blocks_per_sm();
 
 enum { kQueryState = 0, kQueryCenter = 1, kQueryObserved = 2, kQueryWeight = 3, kQueryDistance = 4,
-       kQueryStateGeneric = 5, kQueryTraversable = 6 };
+       kQueryStateGeneric = 5, kQueryTraversable = 6,
+       kQueryTsdfDistance = 7 /* out1 = the TSDF distance slab (may be null) */ };
 
 }  // namespace a3d

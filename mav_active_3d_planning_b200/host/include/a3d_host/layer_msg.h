@@ -61,6 +61,8 @@ class LayerReceiver {
     if (msg.action == kLayerReset) reset();
     const size_t nv = voxelsPerBlock();
     BlockDelta with_w, without_w;  // (the upload takes weights for all of its blocks or for none)
+    std::vector<int32_t> late_idx;  // TSDF distances that waited for their ESDF block
+    std::vector<float> late_dist;
     for (const auto& b : msg.blocks) {
       const Index idx{b.x_index, b.y_index, b.z_index};
       auto pending = pending_weights_.find(idx);
@@ -73,7 +75,11 @@ class LayerReceiver {
         d.esdf_observed.push_back((b.data[2 * i + 1] & 0xFFu) ? 1 : 0);
       }
       if (pending != pending_weights_.end()) {
-        d.tsdf_weight.insert(d.tsdf_weight.end(), pending->second.begin(), pending->second.end());
+        d.tsdf_weight.insert(d.tsdf_weight.end(), pending->second.weight.begin(), pending->second.weight.end());
+        if (!pending->second.distance.empty()) {
+          late_idx.insert(late_idx.end(), {b.x_index, b.y_index, b.z_index});
+          late_dist.insert(late_dist.end(), pending->second.distance.begin(), pending->second.distance.end());
+        }
         pending_weights_.erase(pending);
       }
       known_.insert({idx, true});
@@ -85,6 +91,8 @@ class LayerReceiver {
     if (without_w.n())
       ok &= map_->uploadBlocks(without_w.n(), without_w.block_idx.data(), without_w.esdf_distance.data(),
                                without_w.esdf_observed.data(), nullptr);
+    if (!late_idx.empty())
+      ok &= map_->uploadTsdfDistances(static_cast<int>(late_idx.size() / 3), late_idx.data(), late_dist.data());
     blocks_received_ += with_w.n() + without_w.n();
     return ok;
   }
@@ -95,22 +103,34 @@ class LayerReceiver {
     if (msg.action == kLayerReset) pending_weights_.clear();
     const size_t nv = voxelsPerBlock();
     std::vector<int32_t> idx;
-    std::vector<float> weights;
+    std::vector<float> weights, distances;
     for (const auto& b : msg.blocks) {
-      std::vector<float> w(nv);
-      for (size_t i = 0; i < nv; ++i) std::memcpy(&w[i], &b.data[3 * i + 1], 4);
+      TsdfPayload t;  // a TSDF voxel is {distance, weight, colour}
+      t.weight.resize(nv);
+      for (size_t i = 0; i < nv; ++i) std::memcpy(&t.weight[i], &b.data[3 * i + 1], 4);
+      if (mirror_tsdf_distances_) {
+        t.distance.resize(nv);
+        for (size_t i = 0; i < nv; ++i) std::memcpy(&t.distance[i], &b.data[3 * i], 4);
+      }
       const Index key{b.x_index, b.y_index, b.z_index};
       if (!known_.count(key)) {
-        pending_weights_[key] = std::move(w);  // its ESDF block has not arrived yet
+        pending_weights_[key] = std::move(t);  // its ESDF block has not arrived yet
         continue;
       }
       idx.insert(idx.end(), {b.x_index, b.y_index, b.z_index});
-      weights.insert(weights.end(), w.begin(), w.end());
+      weights.insert(weights.end(), t.weight.begin(), t.weight.end());
+      distances.insert(distances.end(), t.distance.begin(), t.distance.end());
     }
     if (idx.empty()) return true;
-    return map_->uploadWeights(static_cast<int>(idx.size() / 3), idx.data(), weights.data());
+    bool ok = map_->uploadWeights(static_cast<int>(idx.size() / 3), idx.data(), weights.data());
+    if (mirror_tsdf_distances_)
+      ok &= map_->uploadTsdfDistances(static_cast<int>(idx.size() / 3), idx.data(), distances.data());
+    return ok;
   }
 
+  // also mirror the TSDF voxels' distances (VoxbloxMap::getVoxelDistance, voxblox.cpp:84-98); off by
+  // default: nothing in the reference's core reads them
+  void mirrorTsdfDistances(bool on) { mirror_tsdf_distances_ = on; }
   size_t blocksReceived() const { return blocks_received_; }
   size_t pendingWeightBlocks() const { return pending_weights_.size(); }
 
@@ -142,7 +162,11 @@ class LayerReceiver {
   }
   VoxbloxMap* map_;
   std::map<Index, bool> known_;                          // blocks the mirror holds (sent through here)
-  std::map<Index, std::vector<float>> pending_weights_;  // TSDF weights waiting for their ESDF block
+  struct TsdfPayload {
+    std::vector<float> weight, distance;  // (distance only with mirrorTsdfDistances)
+  };
+  std::map<Index, TsdfPayload> pending_weights_;  // TSDF voxels waiting for their ESDF block
+  bool mirror_tsdf_distances_ = false;
   size_t blocks_received_ = 0;
 };
 

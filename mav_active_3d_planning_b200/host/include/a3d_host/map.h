@@ -74,6 +74,9 @@ class VoxbloxMap : public TSDFMap {
                     const uint8_t* esdf_observed, const float* tsdf_weight);
   // TSDF weights alone, for blocks the mirror holds (a3d_map_upload_weights)
   bool uploadWeights(int n, const int32_t* block_idx, const float* tsdf_weight);
+  // TSDF distances alone, for blocks the mirror holds (a3d_map_upload_tsdf_distances): what
+  // getVoxelDistance reads
+  bool uploadTsdfDistances(int n, const int32_t* block_idx, const float* tsdf_distance);
   bool removeBlocks(int n, const int32_t* block_idx);
   int64_t numBlocks() const;
   int voxelsPerSide() const { return p_voxels_per_side_; }

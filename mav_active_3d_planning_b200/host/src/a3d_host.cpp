@@ -217,6 +217,15 @@ bool VoxbloxMap::uploadWeights(int n, const int32_t* block_idx, const float* tsd
   }
   return true;
 }
+bool VoxbloxMap::uploadTsdfDistances(int n, const int32_t* block_idx, const float* tsdf_distance) {
+  const int n_dev = numDevices();  // (queries go to the first device; the replicas stay interchangeable)
+  for (int i = 0; i < n_dev; ++i) {
+    a3d_ctx* c = group_ ? a3d_group_ctx(group_, i) : ctx_;
+    if (a3d_map_upload_tsdf_distances(c, n, block_idx, tsdf_distance, nullptr) != A3D_OK)
+      throw std::runtime_error(std::string("a3d_map_upload_tsdf_distances: ") + a3d_last_error(c));
+  }
+  return true;
+}
 bool VoxbloxMap::removeBlocks(int n, const int32_t* block_idx) {
   if (group_) {
     if (a3d_group_map_remove_blocks(group_, n, block_idx) != A3D_OK)
@@ -270,11 +279,12 @@ bool VoxbloxMap::getVoxelCenter(Eigen::Vector3d* center, const Eigen::Vector3d& 
   *center = Eigen::Vector3d(c[0], c[1], c[2]);
   return true;
 }
-double VoxbloxMap::getVoxelDistance(const Eigen::Vector3d&) {
-  // voxblox.cpp:84-98 reads the TSDF layer's distance; only the VoxelWeightEvaluator (outside this
-  // path) uses it and the mirror does not hold TSDF distances yet
-  planner_.printError("VoxbloxMap::getVoxelDistance is not mirrored on the device");
-  return 0.0;
+double VoxbloxMap::getVoxelDistance(const Eigen::Vector3d& point) {
+  // voxblox.cpp:84-98: the TSDF layer's stored distance of the voxel the point falls in (0 without one);
+  // the mirror holds it for the blocks sent through uploadTsdfDistances
+  double d = 0.0;
+  check(a3d_map_voxel_tsdf_distance(ctx_, 1, point.data(), &d), "a3d_map_voxel_tsdf_distance");
+  return d;
 }
 double VoxbloxMap::getVoxelWeight(const Eigen::Vector3d& point) {
   double w = 0.0;

@@ -787,6 +787,7 @@ int runLayer(char** argv) {
   std::ofstream out(argv[5]);
   out.precision(17);
   map::LayerReceiver rx(vmap);
+  rx.mirrorTsdfDistances(true);  // (the test's TSDF voxels carry the ESDF distance array as their distance)
   const int half = n_blocks / 2, third = n_blocks / 3;
   out << "tsdf_first " << rx.onTsdfLayer(encode("tsdf", 0, half, map::kLayerUpdate)) << " pending "
       << rx.pendingWeightBlocks() << "\n";
@@ -806,6 +807,8 @@ int runLayer(char** argv) {
   sim->computeGains(segments);
   for (size_t s = 0; s < segments.size(); ++s) out << "batch " << s << " 1 " << segments[s]->gain << "\n";
   out << "weight " << vmap->getVoxelWeight(segments[0]->trajectory.back().position_W) << "\n";
+  out << "tsdf_distance " << vmap->getVoxelDistance(segments[0]->trajectory.back().position_W) << " "
+      << vmap->getVoxelDistance(Eigen::Vector3d(-50.0, -50.0, -50.0)) << "\n";
   // ACTION_RESET: the sender's layer replaces the mirror
   out << "reset " << rx.onEsdfLayer(encode("esdf", 0, third, map::kLayerReset)) << " blocks " << vmap->numBlocks() << "\n";
   return 0;

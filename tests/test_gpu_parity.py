@@ -891,3 +891,39 @@ def test_filter_not_in_is_std_find_on_the_three_doubles(capi):
                 want = np.ones(n, np.uint8)
         assert np.array_equal(keep, want), (n, m)
     ctx.close()
+
+
+def test_voxel_tsdf_distance(capi, O, room02):
+    """VoxbloxMap::getVoxelDistance (voxblox.cpp:84-98) = the getVoxelWeight lookup (:101-115) on the other
+    member of the TSDF voxel: checked against the oracle's weight lookup on a map whose weight member holds
+    the TSDF distances.  0 before any upload, for blocks never sent, for unknown blocks (reported through the
+    applied mask) and for a block that was removed and allocated again."""
+    m = room02
+    rng = np.random.default_rng(3)
+    tsdf = rng.normal(0.0, 0.3, m.dist.shape).astype(np.float32)
+    ctx = capi.Context(0)
+    ctx.upload_map(m)
+    pts = probe_points(m, 4000, 17)
+    assert not ctx.voxel_tsdf_distance(pts).any()
+    half = m.n_blocks // 2
+    unknown = np.array([[900, 900, 900]], np.int32)
+    applied = ctx.upload_tsdf_distances(np.concatenate([m.block_idx[:half], unknown]),
+                                        np.concatenate([tsdf[:half], tsdf[:1]]))
+    assert applied[:half].all() and not applied[half]
+    want_src = tsdf.copy()
+    want_src[half:] = 0.0
+    om = O.OracleMap(m.voxel_size, m.vps)
+    om.upload_blocks(m.block_idx, m.dist, m.observed, want_src)
+    want = om.voxel_weight(pts)
+    got = ctx.voxel_tsdf_distance(pts)
+    assert np.array_equal(got, want) and np.count_nonzero(got) > 1000
+    # the weights are a separate member
+    assert np.array_equal(ctx.voxel_weight(pts), O.OracleMap.from_synth(m).voxel_weight(pts))
+    # a removed block's slot is reused by the next new block: it starts without TSDF distances
+    ctx.remove_blocks(m.block_idx[:1])
+    ctx.upload_blocks(m.block_idx[:1], m.dist[:1], m.observed[:1], m.weight[:1])
+    want_src[0] = 0.0
+    om2 = O.OracleMap(m.voxel_size, m.vps)
+    om2.upload_blocks(m.block_idx, m.dist, m.observed, want_src)
+    assert np.array_equal(ctx.voxel_tsdf_distance(pts), om2.voxel_weight(pts))
+    ctx.close()

@@ -587,4 +587,11 @@ def test_layer_messages(built, room02, tmp_path):
     got = {int(l.split()[1]): float(l.split()[3]) for l in open(out) if l.startswith("batch")}
     assert np.allclose([got[s] for s in range(5)], want, rtol=1e-5, atol=1e-12) and want.max() > 0
     assert float(lines["weight"][1]) == om.voxel_weight(pos[:1])[0]
+    # getVoxelDistance (voxblox.cpp:84-98) reads the other member of the same TSDF voxel; the test's TSDF
+    # messages carry the ESDF distance array there: the oracle's weight lookup on a map whose weight member
+    # holds that array is the same arithmetic.  No block: 0.
+    od = O.OracleMap(room02.voxel_size, room02.vps)
+    od.upload_blocks(room02.block_idx, room02.dist, room02.observed, room02.dist)
+    assert float(lines["tsdf_distance"][1]) == od.voxel_weight(pos[:1])[0]
+    assert float(lines["tsdf_distance"][2]) == 0.0
     assert lines["reset"][1] == "1" and int(lines["reset"][3]) == nb // 3
