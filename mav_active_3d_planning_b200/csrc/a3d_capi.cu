@@ -630,11 +630,6 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
   }
   int rc = slab_reserve(ctx, static_cast<size_t>(ctx->next_slot), w != nullptr);
   if (rc) return rc;
-  if (ctx->d_tsdf)  // a block allocated by this call has no TSDF distances yet (its slot may be a reused one)
-    for (int i = 0; i < n; ++i)
-      if (slot_of[i] & kFreshSlot)
-        CK(cudaMemsetAsync(ctx->d_tsdf + static_cast<size_t>(slot_of[i] & ~kFreshSlot) * ctx->nv, 0,
-                           static_cast<size_t>(ctx->nv) * sizeof(float), ctx->stream));
   if (table_dirty) {
     if (ctx->h_table.empty() || 4 * ctx->slots.size() > ctx->h_table.size()) {
       table_rebuild(ctx, ctx->slots.size());
@@ -675,7 +670,7 @@ int upload_blocks_impl(a3d_ctx* ctx, int n, const int32_t* block_idx, const floa
       }
     }
     launch_apply_blocks(ctx->stream, ctx->view(), m, ctx->st_slots.p, dsrc, osrc, wsrc, ctx->d_dist,
-                        ctx->has_weight ? ctx->d_weight : nullptr);
+                        ctx->has_weight ? ctx->d_weight : nullptr, ctx->d_tsdf);
     ctx->launches++;
     CK(cudaGetLastError());  // (staging buffers are reused by the next chunk in stream order)
   }

@@ -39,7 +39,7 @@ static inline int grid_for(long long total, int block, int per_sm = 16) {
 __global__ void k_apply_blocks(MapView m, int n, const int32_t* __restrict__ slots,
                                const float* __restrict__ dist_src, const uint8_t* __restrict__ obs_src,
                                const float* __restrict__ w_src, float* __restrict__ dist_slab,
-                               float* __restrict__ weight_slab) {
+                               float* __restrict__ weight_slab, float* __restrict__ tsdf_slab) {
   const long long total = static_cast<long long>(n) * m.nv;
   const int vv = m.vps * m.vps;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -60,16 +60,18 @@ __global__ void k_apply_blocks(MapView m, int n, const int32_t* __restrict__ slo
     }
     dist_slab[padded_index(m, slot, x, y, z)] = __uint_as_float(bits);
     if (weight_slab && (w_src || fresh)) weight_slab[static_cast<size_t>(slot) * m.nv + lin] = w_src ? w_src[i] : 0.0f;
+    // (TSDF distances arrive on their own, a3d_map_upload_tsdf_distances: a fresh slot has none yet)
+    if (tsdf_slab && fresh) tsdf_slab[static_cast<size_t>(slot) * m.nv + lin] = 0.0f;
   }
 }
 
 void launch_apply_blocks(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                          const float* dist_src, const uint8_t* obs_src, const float* w_src,
-                         float* dist_slab, float* weight_slab) {
+                         float* dist_slab, float* weight_slab, float* tsdf_slab) {
   if (n <= 0) return;
   const long long total = static_cast<long long>(n) * m.nv;
   k_apply_blocks<<<grid_for(total, 256), 256, 0, st>>>(m, n, slots_dev, dist_src, obs_src, w_src,
-                                                       dist_slab, weight_slab);
+                                                       dist_slab, weight_slab, tsdf_slab);
 }
 
 // For every affected block (slot, 27 neighbour slots in (dz,dy,dx) order, -1 = not allocated) copy

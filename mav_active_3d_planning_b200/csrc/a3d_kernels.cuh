@@ -95,7 +95,7 @@ struct LaunchCfg {
 // launchers (a3d_kernels.cu)
 void launch_apply_blocks(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                          const float* dist_src, const uint8_t* obs_src, const float* w_src,
-                         float* dist_slab, float* weight_slab);
+                         float* dist_slab, float* weight_slab, float* tsdf_slab /* nullable */);
 void launch_refresh_aprons(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
                            const int32_t* nbr_dev /*n×27*/, float* dist_slab);
 void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* slots_dev,
