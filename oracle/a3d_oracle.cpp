@@ -549,7 +549,13 @@ int orc_map_upload_blocks(orc_map* m, int n, const int32_t* idx, const float* di
     blk->origin[2] = originPoint(b.z, m->bs_f);
     blk->dist.assign(dist + i * nv, dist + (i + 1) * nv);
     blk->observed.assign(obs + i * nv, obs + (i + 1) * nv);
-    if (w) blk->weight.assign(w + i * nv, w + (i + 1) * nv);
+    if (w) {
+      blk->weight.assign(w + i * nv, w + (i + 1) * nv);
+    } else {
+      // an ESDF-only update leaves the TSDF layer alone (two voxblox layers): the block keeps its weights
+      auto old = m->blocks.find(b);
+      if (old != m->blocks.end()) blk->weight = old->second->weight;
+    }
     m->blocks[b] = blk;
   }
   return 0;

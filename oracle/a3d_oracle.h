@@ -9,7 +9,7 @@
  * PINNED by the reference's own code, except for the voxblox arithmetic: the reference ships no
  * tests or golden vectors, but its sources for this path compile against Eigen / glog / voxblox
  * stand-ins (oracle/Makefile target `_ref`, ref_driver.cpp, ref_shim/), and tests/test_ref_pin.py
- * demands that library == this one bit for bit; tests/golden/*.npz hold its outputs for the GPU box.
+ * demands that library == this one bit for bit; the .npz files under tests/golden hold its outputs for the GPU box.
  * The voxblox arithmetic (un-vendored dependency, unpinned in
  * mav_active_3d_planning_https.rosinstall:5) is restated from its published sources (SURVEY.md
  * Appendix A) in both libraries — VoxbloxLite::getDistanceAtPosition here, ref_shim/voxblox_shim.h

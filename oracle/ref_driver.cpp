@@ -356,9 +356,10 @@ struct World {  // one planner with its own VoxbloxMap; the reference is single-
     const size_t nv = esdf()->voxels_per_side() * esdf()->voxels_per_side() * esdf()->voxels_per_side();
     for (int i = 0; i < n; ++i) {
       const voxblox::BlockIndex b(idx[3 * i], idx[3 * i + 1], idx[3 * i + 2]);
-      // insert-or-overwrite, as a voxblox layer message with action "update" does
+      // insert-or-overwrite, as a voxblox layer message with action "update" does; an ESDF-only update
+      // (w == NULL) leaves the TSDF layer alone — they are two layers
       esdf()->removeBlock(b);
-      tsdf()->removeBlock(b);
+      if (w) tsdf()->removeBlock(b);
       auto eb = esdf()->allocateBlockPtrByIndex(b);
       for (size_t k = 0; k < nv; ++k) {
         voxblox::EsdfVoxel& v = eb->getVoxelByLinearIndex(k);

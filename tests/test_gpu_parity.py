@@ -851,8 +851,9 @@ def test_esdf_only_delta_keeps_tsdf_weights(capi, O, room02):
     rng = np.random.default_rng(21)
     sel = rng.choice(room02.n_blocks, room02.n_blocks // 3, replace=False)
     nd = (room02.dist[sel] + rng.normal(0, 0.02, room02.dist[sel].shape)).astype(np.float32)
-    ctx.upload_blocks(room02.block_idx[sel], nd, room02.observed[sel])                      # no weights
-    om.upload_blocks(room02.block_idx[sel], nd, room02.observed[sel], room02.weight[sel])   # weights unchanged
+    ctx.upload_blocks(room02.block_idx[sel], nd, room02.observed[sel])   # no weights: the TSDF layer stays
+    om.upload_blocks(room02.block_idx[sel], nd, room02.observed[sel])    # (same contract in the checker)
+    assert np.count_nonzero(om.voxel_weight(probe_points(room02, 500, 6))) > 50
     pts = probe_points(room02, 5000, 6)
     assert np.array_equal(ctx.voxel_weight(pts), om.voxel_weight(pts))
     pos, quat = synth.candidate_views(room02, 8, seed=4)

@@ -257,3 +257,31 @@ def test_fuzz_200(ref):
         assert_same(ca.compute_gains(e, pos, quat, parent=parent), cb.compute_gains(e, pos, quat, parent=parent),
                     (case, kind, ek))
     assert n_cases >= 200
+
+
+def test_esdf_only_update_leaves_the_tsdf_layer_alone(ref, room02):
+    """The map stand-ins of both checkers model voxblox's two layers: a block update without weights (an
+    ESDF layer message) keeps the block's TSDF weights, one with weights replaces them, a removal drops
+    both; VoxelWeightEvaluator gains agree bit for bit afterwards."""
+    m = room02
+    rng = np.random.default_rng(8)
+    sel = rng.choice(m.n_blocks, m.n_blocks // 4, replace=False)
+    nd = (m.dist[sel] + rng.normal(0, 0.03, m.dist[sel].shape)).astype(np.float32)
+    pts = (np.asarray(m.block_idx[sel][:, None, :], np.float64) + rng.random((len(sel), 40, 3))).reshape(-1, 3) \
+        * (m.voxel_size * m.vps)
+    pos, quat = synth.candidate_views(m, 3, seed=12)
+    res = []
+    for om in both(m):
+        w0 = om.voxel_weight(pts)
+        assert np.count_nonzero(w0) > 100
+        om.upload_blocks(m.block_idx[sel], nd, m.observed[sel])                 # ESDF only
+        assert np.array_equal(om.voxel_weight(pts), w0)
+        om.upload_blocks(m.block_idx[sel[:5]], nd[:5], m.observed[sel[:5]], 2.0 * m.weight[sel[:5]])
+        om.remove_blocks(m.block_idx[sel[5:8]])
+        w1 = om.voxel_weight(pts)
+        per = 40
+        assert np.array_equal(w1[:5 * per], 2.0 * w0[:5 * per]) and not w1[5 * per:8 * per].any()
+        assert np.array_equal(w1[8 * per:], w0[8 * per:])
+        res.append(om.caster("IterativeRayCaster", **CAM_BASE).compute_gains(
+            O.eval_params("VoxelWeightEvaluator"), pos, quat))
+    assert_same(res[0], res[1], "VoxelWeight after an ESDF-only update")
