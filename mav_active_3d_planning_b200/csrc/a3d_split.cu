@@ -25,9 +25,10 @@
 //
 // A ray part leaves one record: key of its first and last raw list entry, a 64-bit word of four
 // 15-bit counters (entries per fold category, samples) + what the first entry was counted as, and for
-// VoxelWeightEvaluator the sum of its entries' values without the first one (the fix-up decides
-// whether the first entry stays, so nothing is added and subtracted again, and the sums are formed
-// in a fixed order: gains are reproducible run to run).
+// VoxelWeightEvaluator the sum of the values of the entries that have one of their own (surface voxels;
+// unobserved voxels are counted per constant), without the first entry's (the fix-up decides whether the
+// first entry stays, so nothing is added and subtracted again, and the sums are formed in a fixed order:
+// gains are reproducible run to run).
 #include <algorithm>
 
 #include "../../include/a3d.h"
@@ -47,12 +48,19 @@ constexpr int kSplitThreads = 32 * kSplitWarps;
 #ifndef A3D_SPLIT_MARK_BLOCKS
 #define A3D_SPLIT_MARK_BLOCKS 7
 #endif
-// (measured on cfg2, 4096 views: VoxelType 9 CTAs 3.35 ms / 8: 3.45 / 6: 4.1; Frontier 8: 4.33 / 6: 4.18;
-// VoxelWeight 8: 5.82 / 6: 5.18)
+// (measured on cfg2, 4096 views: VoxelType 9 CTAs 3.35 ms / 8: 3.45 / 6: 4.1; Frontier 8: 4.38 / 7: 4.20 / 6: 4.40;
+// VoxelWeight 9: 5.52 / 8: 5.41 / 7: 5.20 / 6: 5.27 — 72 registers spill no more than 80 do)
+#ifndef A3D_SPLIT_LEAF_BLOCKS_VW
+#define A3D_SPLIT_LEAF_BLOCKS_VW 7
+#endif
+#ifndef A3D_SPLIT_LEAF_BLOCKS_FR
+#define A3D_SPLIT_LEAF_BLOCKS_FR 7
+#endif
 constexpr int leaf_blocks(int caster, int eval) {
   return caster != A3D_CASTER_ITERATIVE ? 5
-         : (eval == A3D_EVAL_FRONTIER || eval == A3D_EVAL_VOXEL_WEIGHT) ? (A3D_SPLIT_LEAF_BLOCKS > 6 ? 6 : A3D_SPLIT_LEAF_BLOCKS)
-                                                                        : A3D_SPLIT_LEAF_BLOCKS;
+         : eval == A3D_EVAL_VOXEL_WEIGHT ? A3D_SPLIT_LEAF_BLOCKS_VW
+         : eval == A3D_EVAL_FRONTIER     ? A3D_SPLIT_LEAF_BLOCKS_FR
+                                         : A3D_SPLIT_LEAF_BLOCKS;
 }
 constexpr int kSplitMaxDiag = 256;  // longest anti-diagonal k_split_mark keeps in shared memory
 
@@ -83,8 +91,8 @@ struct SplitScratch {
   unsigned long long* first_key;  // [n_views][parts][stride]
   unsigned long long* last_key;
   unsigned long long* rec;        // counters + first-entry info
-  double* wsum;                   // VoxelWeightEvaluator: sum of the part's entry values, first excluded
-  double* first_val;              // ... value of the first entry
+  double* wsum;                   // VoxelWeightEvaluator: sum of the part's category-1 entry values, first entry excluded
+  double* first_val;              // ... value of the first entry (0 unless it is a category-1 entry with a value)
   size_t stride;                  // n_rays rounded up to 32
   int parts;                      // 2 (iterative: marking part, leaf part) or 1
   // list emission (null / 0 when only gains are asked): the retained entries of every ray part as
@@ -150,7 +158,6 @@ struct Part {
   double d_end;  // the part ends before this distance
   Ident prev;    // previous raw entry (g0 == kNoIdent: none yet)
   unsigned long long rec;  // counters + first-entry info
-  double wsum, first_val;  // VoxelWeightEvaluator
   float dz[3];   // 2 * dir / voxel_size
   size_t at;     // index of the part's record
 };
@@ -171,8 +178,6 @@ __device__ __forceinline__ void part_begin(Part& p, S& sh, const MapView& m, con
   p.d_end = d_end;
   p.prev = Ident{kNoIdent, 0, 0};
   p.rec = 0;
-  p.wsum = 0.0;
-  p.first_val = 0.0;
   p.at = at;
 }
 
@@ -337,13 +342,16 @@ __device__ __forceinline__ int entry_category(const MapView& m, const EvalView& 
   if (EVAL == A3D_EVAL_VOXEL_TYPE) {
     cat = si.cs & 3;  // retained entries are always inside the bounding volume
   } else if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+    // Unobserved voxels score one of two constants (voxel_weight_evaluator.cpp:72-80): they are counted —
+    // category 0: frontier_voxel_weight, 2: new_voxel_weight — and priced by the fix-up.  Category 1:
+    // everything else; only there an entry has a value of its own (surface voxels, and the unobserved
+    // voxels whose frontier test is not in the meta word).
     cat = 1;
     if (keep && (si.cs & 3) != 1) {  // (free voxels score nothing)
-      // unobserved voxel whose frontier bit is in the meta word (the bulk): no call
       const bool fw = e.frontier_voxel_weight > 0.0;
       const int hint = ((si.cs & 3) == 2 && ev.safe && fw) ? is_frontier_from_word(m, e, ev.word) : -1;
       if ((si.cs & 3) == 2 && (hint >= 0 || !fw))
-        wval = hint > 0 ? e.frontier_voxel_weight : e.new_voxel_weight;
+        cat = hint > 0 ? 0 : 2;
       else
         wval = voxel_weight_entry(m, ct, e, ev.g[0], ev.g[1], ev.g[2], ev.cc.x, ev.cc.y, ev.cc.z, ev.have_cc, ev.safe,
                                   ev.word, si.cs, vw.org[0], vw.org[1], vw.org[2]);
@@ -386,8 +394,9 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
   if (emit) p.prev = si.id;
   double wval;
   const int cat = entry_category<EVAL>(m, e, sh, vw, ev, keep, wval);
-  if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
-    if (first) p.first_val = wval; else p.wsum += wval;
+  if (EVAL == A3D_EVAL_VOXEL_WEIGHT && wval != 0.0) {
+    // rare (a surface voxel at the end of a ray): straight to the part's record, no register held for it
+    if (first) __stcs(&sc.first_val[p.at], wval); else sc.wsum[p.at] += wval;
   }
   if (sc.ent && keep) {  // list emission: the retained entry, in the part's own slot range
     unsigned bad = 0;
@@ -488,9 +497,11 @@ __device__ __forceinline__ double part_by_warp(const MapView& m, const CasterVie
     }
     if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
       double w = (keep && !first) ? wval : 0.0;
+      if (__any_sync(kFull, w != 0.0)) {  // (entries with a value of their own are rare)
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(kFull, w, off);
-      wsum += w;
+        for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(kFull, w, off);
+        wsum += w;
+      }
       if (k0 == 0) first_val = __shfl_sync(kFull, keep ? wval : 0.0, 0);
     }
     const int tail = n_valid - 1;
@@ -525,11 +536,7 @@ __device__ __forceinline__ void part_end(const SplitScratch& sc, const Part& p, 
     __stcs(&sc.last_key[p.at], pack_key(p.prev, &bad));
     inexact |= bad;
   }
-  __stcs(&sc.rec[p.at], p.rec);
-  if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
-    __stcs(&sc.wsum[p.at], p.wsum);
-    __stcs(&sc.first_val[p.at], p.first_val);
-  }
+  __stcs(&sc.rec[p.at], p.rec);  // (VoxelWeightEvaluator: wsum / first_val were written as they came)
 }
 
 // ---- k_split_views -----------------------------------------------------------------------------------
@@ -960,7 +967,13 @@ __global__ void __launch_bounds__(kSplitThreads, leaf_blocks(CASTER, EVAL))
     }
     unsigned inexact = 0;
     Part p;
-    if (active) part_begin(p, sh, m, c, vw, r, DEFERRED ? c.split[n - 2] : d0, DEFERRED ? c.split[n - 1] : c.ray_length, at);
+    if (active) {
+      part_begin(p, sh, m, c, vw, r, DEFERRED ? c.split[n - 2] : d0, DEFERRED ? c.split[n - 1] : c.ray_length, at);
+      if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
+        __stcs(&sc.wsum[at], 0.0);
+        __stcs(&sc.first_val[at], 0.0);
+      }
+    }
     while (__any_sync(kFull, active)) {
       if (active && part_step<CASTER, EVAL>(m, e, sh, vw, bv_mode, step, tab, sc, p, inexact)) {
         part_end<EVAL>(sc, p, inexact);
@@ -1091,7 +1104,9 @@ __global__ void __launch_bounds__(kSplitThreads)
       g += n_free * e.gains[2];
       g += n_occ * e.gains[1];
     } else if (EVAL == A3D_EVAL_VOXEL_WEIGHT) {
-      g = wsum;
+      g = wsum;  // entries with a value of their own, summed in a fixed order; then the counted ones
+      g += static_cast<double>(t0) * e.frontier_voxel_weight;
+      g += static_cast<double>(t2) * e.new_voxel_weight;
     } else {
       g = static_cast<double>(t0);
     }
