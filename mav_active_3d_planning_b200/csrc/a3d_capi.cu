@@ -261,14 +261,15 @@ struct a3d_store {
   DevBuf<int> d_anc_first;
   DevBuf<unsigned long long*> d_tab;  // ancestor tables / tables to build
   DevBuf<uint32_t> d_mask;
+  // Arenas come from the device's stream-ordered pool (cudaMallocAsync on the context's stream, the only
+  // stream that touches them): a released arena is handed out again without a trip to the driver and
+  // without the device-wide synchronisation of cudaFree — stored lists are replaced every time a planner
+  // re-evaluates its tree.
+  void free_arena(StoreArena& a);
   void unref(int arena) {
     if (arena < 0) return;
     StoreArena& a = arenas[arena];
-    if (--a.live == 0 && a.p) {
-      cudaFree(a.p);
-      a.p = nullptr;
-      a.entries = 0;
-    }
+    if (--a.live == 0 && a.p) free_arena(a);
   }
   void drop(uint64_t key) {
     auto it = lists.find(key);
@@ -277,15 +278,27 @@ struct a3d_store {
     unref(it->second.set_arena);
     lists.erase(it);
   }
-  int new_arena(size_t words, cudaError_t* err) {
-    StoreArena a;
-    a.entries = words;
-    *err = cudaMalloc(&a.p, std::max<size_t>(words, 1) * 8);
-    if (*err != cudaSuccess) return -1;
-    arenas.push_back(a);
-    return static_cast<int>(arenas.size()) - 1;
-  }
+  int new_arena(size_t words, cudaError_t* err);
 };
+
+void a3d_store::free_arena(StoreArena& a) {
+  if (cudaFreeAsync(a.p, ctx->stream) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(a.p);
+  }
+  a.p = nullptr;
+  a.entries = 0;
+}
+int a3d_store::new_arena(size_t words, cudaError_t* err) {
+  StoreArena a;
+  a.entries = words;
+  void* p = nullptr;
+  *err = cudaMallocAsync(&p, std::max<size_t>(words, 1) * 8, ctx->stream);
+  if (*err != cudaSuccess) return -1;
+  a.p = static_cast<unsigned long long*>(p);
+  arenas.push_back(a);
+  return static_cast<int>(arenas.size()) - 1;
+}
 
 #define CK(call)                                          \
   do {                                                    \
@@ -916,6 +929,16 @@ int a3d_ctx_create(int device_id, a3d_ctx** out) {
                      std::to_string(prop.major) + std::to_string(prop.minor);
     delete ctx;
     return A3D_ERR_CUDA;
+  }
+  {
+    // list arenas of the stores (a3d_store::new_arena) are recycled through the device's default pool:
+    // up to 8 GB of released arenas stay with it instead of going back to the driver at the next sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+      uint64_t keep = 8ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
   }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
@@ -1672,7 +1695,8 @@ void a3d_store_destroy(a3d_store* store) {
   cudaSetDevice(store->ctx->device);
   cudaStreamSynchronize(store->ctx->stream);
   for (auto& a : store->arenas)
-    if (a.p) cudaFree(a.p);
+    if (a.p) store->free_arena(a);
+  cudaStreamSynchronize(store->ctx->stream);
   store->d_off.release();
   store->d_cnt.release();
   store->d_gain.release();
@@ -1924,9 +1948,7 @@ int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_e
   const int arena_id = store->new_arena(total, &merr);
   if (arena_id < 0) return ctx->cuda_fail(merr, "cudaMalloc(list arena)");
   auto fail_arena = [&](int code) {
-    cudaFree(store->arenas[arena_id].p);
-    store->arenas[arena_id].p = nullptr;
-    store->arenas[arena_id].entries = 0;
+    store->free_arena(store->arenas[arena_id]);
     return code;
   };
   if (cudaSuccess != store->d_off.reserve(off.size())) return fail_arena(ctx->fail(A3D_ERR_CUDA, "cudaMalloc"));
