@@ -161,6 +161,9 @@ struct a3d_ctx {
   DevBuf<uint8_t> sc_wave;
   uint64_t config_gen = 0;  // bumped when a3d_map_config changes the geometry: older casters/evals are stale
   // 0 auto, 1 scan-order kernel (k_cast_gain), 2 wavefront kernel (k_cast_wave), 3 kernel chain (a3d_split.cu)
+  // stored-list calls: the next chain cast also leaves the ray parts' list offsets in the scratch
+  // (want_part_offsets), and whether the last cast did for its whole batch (launch_cast_split_direct may follow)
+  bool want_part_offsets = false, part_offsets_valid = false;
   int opt_cast_kernel = 0;
   int last_cast_kernel = 0;
   int opt_wave_cta = 0;  // 0 auto (wave_warps_auto), 1 always 2 warps, 2 always 8, 3 always 4
@@ -747,6 +750,26 @@ EvalView make_eval_view(const a3d_ctx* ctx, const a3d_eval_params& p) {
   return v;
 }
 
+// The scan-order kernel on the segments whose bit is set in seg_mask (null: all of them).
+int enqueue_scan(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, Batch* b, bool digest, bool emit,
+                 const unsigned int* seg_mask) {
+  const int block = cast_gain_block_threads();
+  const int warps_per_block = block / 32;
+  int grid = (b->n_segments + warps_per_block - 1) / warps_per_block;
+  grid = std::max(1, std::min(grid, ctx->sm_count * 32));
+  if (c->view.kind == A3D_CASTER_ITERATIVE) {
+    b->table_stride = (static_cast<size_t>(c->view.n_rays) + 15) / 16 * 16;
+    CK(ctx->sc_tables.reserve(b->table_stride * grid * warps_per_block));
+    b->tables = ctx->sc_tables.p;
+  }
+  b->work_counter = ctx->sc_counter.p + 1;
+  b->seg_mask = seg_mask;
+  launch_cast_gain(ctx->stream, ctx->view(), c->view, e ? &e->view : nullptr, *b, digest, emit, grid, block);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return A3D_OK;
+}
+
 // Enqueue the cast+gain work for a batch whose inputs/outputs are already on the device.
 // Kernel choice: the wavefront kernel (k_cast_wave) when only order-free outputs are wanted, else the
 // scan-order kernel (k_cast_gain), which also re-evaluates the rare segments k_cast_wave flags.
@@ -762,6 +785,7 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     int rc = table_upload(ctx);
     if (rc) return rc;
   }
+  ctx->part_offsets_valid = false;
   Batch b{};
   b.pos = pos_dev;
   b.quat = quat_dev;
@@ -814,7 +838,8 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const unsigned int* seg_mask = nullptr;
   if (use_split) {
-    const size_t per_view = cast_split_bytes_per_view(c->view, ev_view.kind, nullptr, emit);
+    const int mode = emit ? 1 : (ctx->want_part_offsets ? 2 : 0);
+    const size_t per_view = cast_split_bytes_per_view(c->view, ev_view.kind, nullptr, mode);
     const long long max_views = static_cast<long long>(std::max<size_t>(1, (size_t(4) << 30) / per_view));
     std::vector<int32_t> h_first;  // needed only to cut the batch into chunks that fit the scratch
     if (n_views > max_views) {
@@ -838,12 +863,13 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
       for (auto& evs : ctx->ev_stage)
         if (!evs) CK(cudaEventCreate(&evs));
       ctx->n_stage = launch_cast_split(ctx->stream, ctx->view(), c->view, ev_view, b, seg, seg_end - seg, v0, v1 - v0,
-                                       ctx->sc_wave.p, ctx->sc_inexact.p, ctx->sm_count, ctx->ev_stage);
-      ctx->launches += cast_split_launches(c->view, emit);
+                                       ctx->sc_wave.p, ctx->sc_inexact.p, ctx->sm_count, ctx->ev_stage, mode);
+      ctx->launches += cast_split_launches(c->view, mode);
       CK(cudaGetLastError());
       seg = seg_end;
     }
     seg_mask = ctx->sc_inexact.p;
+    ctx->part_offsets_valid = mode == 2 && h_first.empty();  // (one chunk: the scratch holds the whole batch)
   }
   if (use_wave) {
     // as many CTAs as can be resident (measured: trimming the grid so that every CTA gets the same
@@ -871,25 +897,43 @@ int enqueue_cast(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, const dou
     seg_mask = ctx->sc_inexact.p;
   }
   {
-    // scan-order kernel: everything (no wave) or only the segments the wave kernel flagged
-    const int block = cast_gain_block_threads();
-    const int warps_per_block = block / 32;
-    int grid = (n_segments + warps_per_block - 1) / warps_per_block;
-    grid = std::max(1, std::min(grid, ctx->sm_count * 32));
-    if (c->view.kind == A3D_CASTER_ITERATIVE) {
-      b.table_stride = (static_cast<size_t>(c->view.n_rays) + 15) / 16 * 16;
-      CK(ctx->sc_tables.reserve(b.table_stride * grid * warps_per_block));
-      b.tables = ctx->sc_tables.p;
-    }
-    b.work_counter = ctx->sc_counter.p + 1;
-    b.seg_mask = seg_mask;
-    launch_cast_gain(ctx->stream, ctx->view(), c->view, e ? &e->view : nullptr, b,
-                     dig_dev != nullptr || set_dig_dev != nullptr, emit, grid, block);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    int rc = enqueue_scan(ctx, c, e, &b, dig_dev != nullptr || set_dig_dev != nullptr, emit, seg_mask);
+    if (rc) return rc;
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
+  return A3D_OK;
+}
+
+// Second pass of a stored-list call, when the first pass (enqueue_cast with want_part_offsets) went through
+// the kernel chain in one chunk: the chain casts again and writes the lists' keys straight into the arena;
+// the segments the first pass flagged are emitted by the scan-order kernel, as in enqueue_cast.
+int enqueue_direct_emit(a3d_ctx* ctx, const a3d_caster* c, const a3d_eval* e, int n_segments, int n_views,
+                        const double* seg_origin_dev, const long long* emit_offset_dev,
+                        unsigned long long* keys_dev) {
+  Batch b{};
+  b.pos = ctx->sc_pos.p;
+  b.quat = ctx->sc_quat.p;
+  b.view_first = ctx->sc_first.p;
+  b.n_segments = n_segments;
+  b.gains = ctx->sc_gains.p;
+  b.n_visible = ctx->sc_nvis.p;
+  b.n_samples = ctx->sc_nsamp.p;
+  b.seg_origin = seg_origin_dev;
+  b.emit_offset = emit_offset_dev;
+  b.keys_out = keys_dev;
+  CK(cudaMemsetAsync(ctx->sc_counter.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+  b.key_error = ctx->sc_counter.p + 2;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  launch_cast_split_direct(ctx->stream, ctx->view(), c->view, e->view, b, n_segments, n_views, ctx->sc_wave.p,
+                           ctx->sm_count);
+  ctx->launches += cast_split_launches(c->view, 0) - 1;
+  CK(cudaGetLastError());
+  int rc = enqueue_scan(ctx, c, e, &b, false, true, ctx->sc_inexact.p);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->part_offsets_valid = false;
   return A3D_OK;
 }
 
@@ -1935,8 +1979,12 @@ int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_e
   std::vector<uint64_t> nvis(static_cast<size_t>(std::max(n_segments, 0)));
   a3d_eval plain = *eval;
   plain.p.clear_from_parents = 0;  // (the batch cast itself never looks at parents)
+  ctx->want_part_offsets = true;
   int rc = a3d_compute_gains(ctx, caster, &plain, n_views, pos, quat, view_segment, n_segments, gains_out,
                              nvis.data(), n_samples_out, nullptr, nullptr, seg_origin);
+  ctx->want_part_offsets = false;
+  const bool direct = ctx->part_offsets_valid;  // the chain ran in one chunk: its scratch knows where every part goes
+  ctx->part_offsets_valid = false;
   if (rc) return rc;
   if (n_segments == 0) return A3D_OK;
   std::vector<long long> off(static_cast<size_t>(n_segments) + 1, 0);
@@ -1954,9 +2002,13 @@ int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_e
   if (cudaSuccess != store->d_off.reserve(off.size())) return fail_arena(ctx->fail(A3D_ERR_CUDA, "cudaMalloc"));
   CK(cudaMemcpyAsync(store->d_off.p, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice,
                      ctx->stream));
-  rc = enqueue_cast(ctx, caster, &plain, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, n_segments,
-                    ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr, nullptr, 0, true,
-                    seg_origin ? ctx->sc_origin.p : nullptr, store->d_off.p, store->arenas[arena_id].p, n_views);
+  if (direct)
+    rc = enqueue_direct_emit(ctx, caster, &plain, n_segments, n_views, seg_origin ? ctx->sc_origin.p : nullptr,
+                             store->d_off.p, store->arenas[arena_id].p);
+  else
+    rc = enqueue_cast(ctx, caster, &plain, ctx->sc_pos.p, ctx->sc_quat.p, ctx->sc_first.p, n_segments,
+                      ctx->sc_gains.p, ctx->sc_nvis.p, ctx->sc_nsamp.p, nullptr, nullptr, nullptr, 0, true,
+                      seg_origin ? ctx->sc_origin.p : nullptr, store->d_off.p, store->arenas[arena_id].p, n_views);
   if (rc) return fail_arena(rc);
   unsigned int key_error = 0;
   CK(cudaMemcpyAsync(&key_error, ctx->sc_counter.p + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -139,12 +139,18 @@ void launch_cast_wave(cudaStream_t st, const MapView& m, const CasterView& c, co
 // throughput path as a chain of kernels (a3d_split.cu): gains / counts and, when Batch::centres_out or
 // keys_out is set, the ordered lists; no digests; dense meta volume required
 bool cast_split_supported(const MapView& m, const CasterView& c);
-size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out, bool emit);
-int cast_split_launches(const CasterView& c, bool emit);
+// mode 0: gains / counts; 1: list emission (b.centres_out / b.keys_out); 2: gains / counts + every ray part's
+// offset within its segment's list, for launch_cast_split_direct on the same scratch afterwards
+size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out, int mode);
+int cast_split_launches(const CasterView& c, int mode);
 // stage_events (6, or null): recorded before the first and after each kernel; returns how many were recorded
 int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
                       int seg0, int n_seg, int view0, int n_views, void* scratch, unsigned int* inexact,
-                      int sm_count, cudaEvent_t* stage_events);
+                      int sm_count, cudaEvent_t* stage_events, int mode);
+// second pass of a stored-list call (a3d_split_direct.cu): casts the whole batch again and writes the keys of
+// the retained entries to b.keys_out[b.emit_offset[segment] + place in the list]
+int launch_cast_split_direct(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                             int n_seg, int n_views, void* scratch, int sm_count);
 int cast_wave_threads();
 int cast_wave_max_diag();
 int cast_wave_blocks_per_sm();

@@ -29,12 +29,22 @@
 // unobserved voxels are counted per constant), without the first entry's (the fix-up decides whether the
 // first entry stays, so nothing is added and subtracted again, and the sums are formed in a fixed order:
 // gains are reproducible run to run).
+//
+// Stored lists (a3d_compute_gains_stored) run the chain twice: the first pass also leaves every ray
+// part's offset within its segment's list (SplitScratch::off, from the fix-up); once the arena has been
+// sized from the segments' counts, the DIRECT instantiations of the mark / leaf kernels cast again and
+// write every retained entry's key straight to its final place (launch_cast_split_direct; compiled as a
+// second translation unit, a3d_split_direct.cu, in parallel with this one).
 #include <algorithm>
 
 #include "../../include/a3d.h"
 #include "a3d_kernels.cuh"
 #include "a3d_keys.cuh"
 #include "a3d_sample.cuh"
+
+#ifndef A3D_SPLIT_PART
+#define A3D_SPLIT_PART 1  // 1: this file as such; 2: the DIRECT instantiations (a3d_split_direct.cu)
+#endif
 
 namespace a3d {
 
@@ -101,7 +111,33 @@ struct SplitScratch {
   uint32_t* off;                  // [n_views][parts][stride]: offset in the segment's list | (first entry dropped) << 31
   int32_t* view_seg;              // [n_views] segment of each view (batch-wide numbering)
   int kmax;
+  // second pass of a stored-list call (DIRECT kernels): keys go straight to direct[seg_base[segment] + offset of
+  // the part (off, first pass) + index within the part]
+  unsigned long long* direct;
+  const long long* seg_base;      // [n_segments + 1]
 };
+
+// Where a ray part's retained entries go in the second pass of a stored-list call.
+struct DirectOut {
+  unsigned long long* dst;  // place of the part's entry number `skip`
+  int skip;                 // 1: std::unique dropped the part's first entry (fix-up of the first pass)
+  int room;                 // entries left in the segment's range from dst on
+};
+__device__ __forceinline__ DirectOut direct_begin(const SplitScratch& sc, int view, size_t at) {
+  const uint32_t o = __ldg(&sc.off[at]);
+  const int seg = __ldg(&sc.view_seg[view]);
+  const long long base = __ldg(&sc.seg_base[seg]), len = __ldg(&sc.seg_base[seg + 1]) - base;
+  const long long first = static_cast<long long>(o & 0x7FFFFFFFu);
+  DirectOut d;
+  d.dst = sc.direct + base + first;
+  d.skip = static_cast<int>(o >> 31);
+  d.room = static_cast<int>(max(0ll, min(len - first, 2147483647ll)));
+  return d;
+}
+__device__ __forceinline__ void direct_put(const DirectOut& d, int k, unsigned long long key) {
+  const int i = k - d.skip;
+  if (i >= 0 && i < d.room) __stcs(d.dst + i, key);
+}
 
 // entries a part has retained so far, from its record word
 __device__ __forceinline__ int rec_kept(unsigned long long rec) {
@@ -160,6 +196,7 @@ struct Part {
   unsigned long long rec;  // counters + first-entry info
   float dz[3];   // 2 * dir / voxel_size
   size_t at;     // index of the part's record
+  DirectOut out; // DIRECT kernels only
 };
 
 template <class S>
@@ -376,7 +413,7 @@ __device__ __forceinline__ int entry_category(const MapView& m, const EvalView& 
 // One sample of the lane's part (camera_model / ray caster inner loop + the evaluator's per-voxel
 // test).  Returns true when the part is finished (hit or end reached) and then leaves in p.d the
 // distance of the OCCUPIED sample that ended it, or -1.  Precondition: p.d < p.d_end.
-template <int CASTER, int EVAL, class S>
+template <int CASTER, int EVAL, bool DIRECT, class S>
 __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, const S& sh, const ViewRec& vw,
                                           const int bv_mode, const double step, const uint32_t* __restrict__ tab,
                                           const SplitScratch& sc, Part& p, unsigned& inexact) {
@@ -398,7 +435,12 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
     // rare (a surface voxel at the end of a ray): straight to the part's record, no register held for it
     if (first) __stcs(&sc.first_val[p.at], wval); else sc.wsum[p.at] += wval;
   }
-  if (sc.ent && keep) {  // list emission: the retained entry, in the part's own slot range
+  if (DIRECT) {
+    if (keep) {  // second pass of a stored-list call: the retained entry at its final place
+      unsigned bad = 0;
+      direct_put(p.out, rec_kept(p.rec), pack_key(si.id, &bad));
+    }
+  } else if (sc.ent && keep) {  // list emission: the retained entry, in the part's own slot range
     unsigned bad = 0;
     A3D_DEV_CHECK(rec_kept(p.rec) < sc.kmax);
     __stcs(&sc.ent[p.at * static_cast<size_t>(sc.kmax) + rec_kept(p.rec)], pack_key(si.id, &bad));
@@ -424,11 +466,11 @@ __device__ __forceinline__ bool part_step(const MapView& m, const EvalView& e, c
 // CasterView::dseq, as k_cast_gain does), the first OCCUPIED sample ends it.  Used on the
 // anti-diagonal chain, where the latency of a part — not lane occupancy — is what counts.  Returns the
 // hit distance (-1: none).  All lanes must call; `at` = the part's record.
-template <int EVAL, class S>
+template <int EVAL, bool DIRECT, class S>
 __device__ __forceinline__ double part_by_warp(const MapView& m, const CasterView& c, const EvalView& e, S& sh,
                                                const ViewRec& vw, const int bv_mode, const uint32_t* __restrict__ tab,
-                                               const SplitScratch& sc, const int r, const int s0, const size_t at,
-                                               unsigned& inexact) {
+                                               const SplitScratch& sc, const int view, const int r, const int s0,
+                                               const size_t at, unsigned& inexact) {
   const unsigned lane = threadIdx.x & 31u;
   const int n = c.n_sections;
   const int n_s = c.seg_end[s0 * n + (n - 2)];  // samples before c_split_distances_[n-1]
@@ -443,6 +485,8 @@ __device__ __forceinline__ double part_by_warp(const MapView& m, const CasterVie
   const float dz[3] = {__double2float_rn(__dmul_rn(dir.x, k2)), __double2float_rn(__dmul_rn(dir.y, k2)),
                        __double2float_rn(__dmul_rn(dir.z, k2))};
   unsigned long long rec = 0;
+  DirectOut out{};
+  if (DIRECT) out = direct_begin(sc, view, at);
   double wsum = 0.0, first_val = 0.0, hit_d = -1.0;
   Ident carry{kNoIdent, 0, 0};  // last raw entry of the previous chunk of 32 samples
   Ident last{kNoIdent, 0, 0};
@@ -471,7 +515,13 @@ __device__ __forceinline__ double part_by_warp(const MapView& m, const CasterVie
     int cat = 3;
     if (valid) cat = entry_category<EVAL>(m, e, sh, vw, ev, keep, wval);
     const bool first = k == 0;
-    if (sc.ent) {  // list emission: retained entries in sample order
+    if (DIRECT) {
+      const unsigned km = __ballot_sync(kFull, keep);
+      if (keep) {
+        unsigned bad = 0;
+        direct_put(out, rec_kept(rec) + __popc(km & ((1u << lane) - 1u)), pack_key(ev.si.id, &bad));
+      }
+    } else if (sc.ent) {  // list emission: retained entries in sample order
       const unsigned km = __ballot_sync(kFull, keep);
       if (keep) {
         unsigned bad = 0;
@@ -601,7 +651,7 @@ __device__ __forceinline__ void load_view(S& sh, const SplitScratch& sc, int vie
 // ---- k_split_mark ------------------------------------------------------------------------------------
 // One warp per view, ray table in global memory (any camera size).  Dynamic shared memory: per warp
 // diag_max hit distances + diag_max list items, then the volume offset tables.
-template <int EVAL>
+template <int EVAL, bool DIRECT>
 __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
     k_split_mark(const MapView m, const CasterView c, const EvalView e, int n_views, const SplitScratch sc) {
   constexpr bool SMEM_TABLE = false;
@@ -695,7 +745,7 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
       for (int qi = 0; qi < n_mark; ++qi) {
         const unsigned it = s_list[qi];
         const int r = static_cast<int>(it >> 8), ms = static_cast<int>(it & 0xFF);
-        const double hd = part_by_warp<EVAL>(m, c, e, sh, vw, bv_mode, tab, sc, r, ms, rec0 + r, inexact);
+        const double hd = part_by_warp<EVAL, DIRECT>(m, c, e, sh, vw, bv_mode, tab, sc, view, r, ms, rec0 + r, inexact);
         if (lane == 0) {
           s_hit[qi] = hd;
           start_s[r] = static_cast<uint8_t>(ms);  // read by k_split_leaf
@@ -767,7 +817,7 @@ __global__ void __launch_bounds__(kSplitThreads, A3D_SPLIT_MARK_BLOCKS)
 // is a shared-memory access instead of an L2 round trip — and is copied out at the end; otherwise it
 // stays in global memory (L2 atomics, reads that bypass L1).  Dynamic shared memory: diag_max hit
 // distances, diag_max list items, the volume offset tables, (SMEM_TABLE) n_rays table entries.
-template <int EVAL, bool SMEM_TABLE>
+template <int EVAL, bool SMEM_TABLE, bool DIRECT>
 __global__ void __launch_bounds__(kSplitThreads, SMEM_TABLE ? 6 : 7)
     k_split_mark_cta(const MapView m, const CasterView c, const EvalView e, int n_views, const SplitScratch sc) {
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -859,7 +909,7 @@ __global__ void __launch_bounds__(kSplitThreads, SMEM_TABLE ? 6 : 7)
       for (int qi = static_cast<int>(warp); qi < n_mark; qi += kSplitWarps) {
         const unsigned it = s_list[qi];
         const int r = static_cast<int>(it >> 8), ms = static_cast<int>(it & 0xFF);
-        const double hd = part_by_warp<EVAL>(m, c, e, sh, vw, bv_mode, tab, sc, r, ms, rec0 + r, inexact);
+        const double hd = part_by_warp<EVAL, DIRECT>(m, c, e, sh, vw, bv_mode, tab, sc, view, r, ms, rec0 + r, inexact);
         if (lane == 0) {
           s_hit[qi] = hd;
           start_s[r] = static_cast<uint8_t>(ms);  // read by k_split_leaf
@@ -918,7 +968,7 @@ __global__ void __launch_bounds__(kSplitThreads, SMEM_TABLE ? 6 : 7)
 // DEFERRED = false: unit = 32 consecutive rays of one view, cast through the last section (whole ray).
 // DEFERRED = true (k_split_mark2): unit = 32 entries of the view's list of rays that start in section
 // n-2; cast through that section; a ray that hits raises its provisional marks to -1.
-template <int CASTER, int EVAL, bool DEFERRED>
+template <int CASTER, int EVAL, bool DEFERRED, bool DIRECT>
 __global__ void __launch_bounds__(kSplitThreads, leaf_blocks(CASTER, EVAL))
     k_split_leaf(const MapView m, const CasterView c, const EvalView e, int n_views, const SplitScratch sc) {
   constexpr bool ITER = (CASTER == A3D_CASTER_ITERATIVE);
@@ -973,9 +1023,10 @@ __global__ void __launch_bounds__(kSplitThreads, leaf_blocks(CASTER, EVAL))
         __stcs(&sc.wsum[at], 0.0);
         __stcs(&sc.first_val[at], 0.0);
       }
+      if (DIRECT) p.out = direct_begin(sc, view, at);
     }
     while (__any_sync(kFull, active)) {
-      if (active && part_step<CASTER, EVAL>(m, e, sh, vw, bv_mode, step, tab, sc, p, inexact)) {
+      if (active && part_step<CASTER, EVAL, DIRECT>(m, e, sh, vw, bv_mode, step, tab, sc, p, inexact)) {
         part_end<EVAL>(sc, p, inexact);
         if (DEFERRED && p.d >= 0.0) {
           // hit: the 2x2 square's marks become -1 where this ray is still the highest writer
@@ -1163,7 +1214,7 @@ __global__ void __launch_bounds__(kSplitThreads)
   }
 }
 
-template <int CASTER, int EVAL>
+template <int CASTER, int EVAL, bool DIRECT>
 int launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
                    int seg0, int n_seg, int view0, int n_views, const SplitScratch& sc, unsigned int* inexact,
                    int sm_count, cudaEvent_t* evs) {
@@ -1182,17 +1233,17 @@ int launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, const
     // (cfg2: one view 0.89 -> 0.37 ms, 148 views 1.23 -> 0.69 ms; beyond ~2000 views the one-warp-per-view
     // kernel wins: 4096 views 1.7 vs 2.6 ms)
     if (smem_1 <= 40 * 1024 && n_views <= sm_count * 12) {
-      k_split_mark_cta<EVAL, true><<<std::max(1, std::min(n_views, sm_count * 8)), kSplitThreads, smem_1, st>>>(m, c, e, n_views, sc);
+      k_split_mark_cta<EVAL, true, DIRECT><<<std::max(1, std::min(n_views, sm_count * 8)), kSplitThreads, smem_1, st>>>(m, c, e, n_views, sc);
     } else if (smem_1 > 40 * 1024 && n_views <= sm_count * 7) {
       // table too large for shared memory, batch small enough for one resident CTA per view: the
       // CTA-per-view walk on the global table (cfg3, 1024 views: 5.8 ms with one warp per view)
       const size_t smem_g = static_cast<size_t>(c.diag_max) * 12 + tab_bytes;
-      k_split_mark_cta<EVAL, false><<<std::max(1, n_views), kSplitThreads, smem_g, st>>>(m, c, e, n_views, sc);
+      k_split_mark_cta<EVAL, false, DIRECT><<<std::max(1, n_views), kSplitThreads, smem_g, st>>>(m, c, e, n_views, sc);
     } else {
       const size_t smem = static_cast<size_t>(kSplitWarps) * c.diag_max * 12 + tab_bytes;
       const int grid =
           std::max(1, std::min((n_views + kSplitWarps - 1) / kSplitWarps, sm_count * A3D_SPLIT_MARK_BLOCKS));
-      k_split_mark<EVAL><<<grid, kSplitThreads, smem, st>>>(m, c, e, n_views, sc);
+      k_split_mark<EVAL, DIRECT><<<grid, kSplitThreads, smem, st>>>(m, c, e, n_views, sc);
     }
   } else if (CASTER == A3D_CASTER_ITERATIVE) {
     // a single section: no marking parts; every ray is cast whole by k_split_leaf
@@ -1208,71 +1259,60 @@ int launch_split_t(cudaStream_t st, const MapView& m, const CasterView& c, const
     const int grid = static_cast<int>(std::max(1ll, std::min((units + kSplitWarps - 1) / kSplitWarps,
                                                              static_cast<long long>(sm_count) * per_sm * 4)));
     if (CASTER == A3D_CASTER_ITERATIVE && c.n_sections > 1)
-      k_split_leaf<CASTER, EVAL, true><<<grid, kSplitThreads, tab_bytes, st>>>(m, c, e, n_views, sc);
+      k_split_leaf<CASTER, EVAL, true, DIRECT><<<grid, kSplitThreads, tab_bytes, st>>>(m, c, e, n_views, sc);
     if (CASTER == A3D_CASTER_ITERATIVE) stamp();
-    k_split_leaf<CASTER, EVAL, false><<<grid, kSplitThreads, tab_bytes, st>>>(m, c, e, n_views, sc);
+    k_split_leaf<CASTER, EVAL, false, DIRECT><<<grid, kSplitThreads, tab_bytes, st>>>(m, c, e, n_views, sc);
     stamp();
   }
-  k_split_fix<CASTER, EVAL><<<(n_seg + kSplitWarps - 1) / kSplitWarps, kSplitThreads, 0, st>>>(
-      e, b, seg0, n_seg, view0, c.n_rays, sc, inexact);
-  stamp();
-  if (sc.ent) {
-    const long long n_parts = static_cast<long long>(n_views) * sc.parts * c.n_rays;
-    const int grid = static_cast<int>(std::max(1ll, std::min((n_parts + kSplitThreads - 1) / kSplitThreads,
-                                                             static_cast<long long>(sm_count) * 16)));
-    k_split_emit<<<grid, kSplitThreads, 0, st>>>(m, b, n_views, c.n_rays, sc);
+  if constexpr (!DIRECT) {  // (DIRECT: counters, gains and the parts' offsets are the first pass's)
+    k_split_fix<CASTER, EVAL><<<(n_seg + kSplitWarps - 1) / kSplitWarps, kSplitThreads, 0, st>>>(
+        e, b, seg0, n_seg, view0, c.n_rays, sc, inexact);
+    stamp();
+    if (sc.ent) {
+      const long long n_parts = static_cast<long long>(n_views) * sc.parts * c.n_rays;
+      const int grid = static_cast<int>(std::max(1ll, std::min((n_parts + kSplitThreads - 1) / kSplitThreads,
+                                                               static_cast<long long>(sm_count) * 16)));
+      k_split_emit<<<grid, kSplitThreads, 0, st>>>(m, b, n_views, c.n_rays, sc);
+    }
   }
   return n_ev;
 }
 
-template <int CASTER>
+template <int CASTER, bool DIRECT>
 int launch_split_c(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
                    int seg0, int n_seg, int view0, int n_views, const SplitScratch& sc, unsigned int* inexact,
                    int sm_count, cudaEvent_t* evs) {
   switch (e.kind) {
     case A3D_EVAL_VOXEL_TYPE:
-      return launch_split_t<CASTER, A3D_EVAL_VOXEL_TYPE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
+      return launch_split_t<CASTER, A3D_EVAL_VOXEL_TYPE, DIRECT>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
     case A3D_EVAL_NAIVE:
-      return launch_split_t<CASTER, A3D_EVAL_NAIVE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
+      return launch_split_t<CASTER, A3D_EVAL_NAIVE, DIRECT>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
     case A3D_EVAL_VOXEL_WEIGHT:
-      return launch_split_t<CASTER, A3D_EVAL_VOXEL_WEIGHT>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
+      return launch_split_t<CASTER, A3D_EVAL_VOXEL_WEIGHT, DIRECT>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
     default:
-      return launch_split_t<CASTER, A3D_EVAL_FRONTIER>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
+      return launch_split_t<CASTER, A3D_EVAL_FRONTIER, DIRECT>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count, evs);
   }
 }
 
-}  // namespace
-
-bool cast_split_supported(const MapView& m, const CasterView& c) {
-  if (!m.vol || m.vps_shift < 0) return false;
-  if (c.kmax >= (1 << kCntBits) - 1) return false;  // a part's counters are 15 bits wide
-  if (c.kind == A3D_CASTER_ITERATIVE && (c.diag_max > kSplitMaxDiag || c.n_sections > 31)) return false;
-  return c.n_rays < (1 << 23);
-}
-
-size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out, bool emit) {
+// bytes of scratch per view and where everything lies.  mode 0: gains / counts; 1: list emission through
+// per-part key slots; 2: gains / counts + the parts' offsets within their segment's list (first pass of a
+// stored-list call; the second pass — DIRECT — uses the same layout)
+size_t split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out, int mode) {
   const size_t stride = (static_cast<size_t>(c.n_rays) + 31) / 32 * 32;
   if (stride_out) *stride_out = stride;
   const size_t parts = c.kind == A3D_CASTER_ITERATIVE ? 2 : 1;
   size_t per_view = parts * stride * (8 + 8 + 8) + sizeof(ViewRec) + 8;
-  if (emit) per_view += parts * stride * (static_cast<size_t>(c.kmax) * 8 + 4) + 8;
+  if (mode == 1) per_view += parts * stride * static_cast<size_t>(c.kmax) * 8;
+  if (mode != 0) per_view += parts * stride * 4 + 8;
   if (eval_kind == A3D_EVAL_VOXEL_WEIGHT) per_view += parts * stride * 16;
   if (c.kind == A3D_CASTER_ITERATIVE) per_view += stride * 9 + 8;
   return per_view;
 }
 
-int cast_split_launches(const CasterView& c, bool emit) { return (c.kind == A3D_CASTER_ITERATIVE ? 5 : 3) + (emit ? 1 : 0); }
-
-// Segments [seg0, seg0 + n_seg) = views [view0, view0 + n_views) of the batch; scratch holds
-// n_views * cast_split_bytes_per_view() + 256 bytes.  inexact: one bit per segment (batch-wide
-// numbering), set when a sample needs the scan-order kernel's decision.
-int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
-                      int seg0, int n_seg, int view0, int n_views, void* scratch, unsigned int* inexact,
-                      int sm_count, cudaEvent_t* stage_events) {
+SplitScratch split_layout(const CasterView& c, int eval_kind, int mode, int n_views, void* scratch) {
   SplitScratch sc{};
   size_t stride = 0;
-  const bool emit = b.centres_out != nullptr || b.keys_out != nullptr;
-  cast_split_bytes_per_view(c, e.kind, &stride, emit);
+  split_bytes_per_view(c, eval_kind, &stride, mode);
   sc.stride = stride;
   sc.parts = c.kind == A3D_CASTER_ITERATIVE ? 2 : 1;
   uint8_t* p = static_cast<uint8_t*>(scratch);
@@ -1285,16 +1325,18 @@ int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, co
   p += slots * 8;
   sc.rec = reinterpret_cast<unsigned long long*>(p);
   p += slots * 8;
-  if (e.kind == A3D_EVAL_VOXEL_WEIGHT) {
+  if (eval_kind == A3D_EVAL_VOXEL_WEIGHT) {
     sc.wsum = reinterpret_cast<double*>(p);
     p += slots * 8;
     sc.first_val = reinterpret_cast<double*>(p);
     p += slots * 8;
   }
-  if (emit) {
+  if (mode == 1) {
     sc.kmax = c.kmax;
     sc.ent = reinterpret_cast<unsigned long long*>(p);
     p += slots * static_cast<size_t>(c.kmax) * 8;
+  }
+  if (mode != 0) {
     sc.off = reinterpret_cast<uint32_t*>(p);
     p += (slots * 4 + 7) / 8 * 8;
     sc.view_seg = reinterpret_cast<int32_t*>(p);
@@ -1310,11 +1352,57 @@ int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, co
     sc.dcount = reinterpret_cast<unsigned int*>(p);
     p += (nv * 4 + 7) / 8 * 8;
     sc.start_s = p;
-    return launch_split_c<A3D_CASTER_ITERATIVE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count,
-                                                stage_events);
   }
-  return launch_split_c<A3D_CASTER_SIMPLE>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count,
-                                           stage_events);
+  return sc;
 }
+
+}  // namespace
+
+#if A3D_SPLIT_PART == 1
+bool cast_split_supported(const MapView& m, const CasterView& c) {
+  if (!m.vol || m.vps_shift < 0) return false;
+  if (c.kmax >= (1 << kCntBits) - 1) return false;  // a part's counters are 15 bits wide
+  if (c.kind == A3D_CASTER_ITERATIVE && (c.diag_max > kSplitMaxDiag || c.n_sections > 31)) return false;
+  return c.n_rays < (1 << 23);
+}
+
+size_t cast_split_bytes_per_view(const CasterView& c, int eval_kind, size_t* stride_out, int mode) {
+  return split_bytes_per_view(c, eval_kind, stride_out, mode);
+}
+
+int cast_split_launches(const CasterView& c, int mode) {
+  return (c.kind == A3D_CASTER_ITERATIVE ? 5 : 3) + (mode == 1 ? 1 : 0);
+}
+
+// Segments [seg0, seg0 + n_seg) = views [view0, view0 + n_views) of the batch; scratch holds
+// n_views * cast_split_bytes_per_view() + 256 bytes.  inexact: one bit per segment (batch-wide
+// numbering), set when a sample needs the scan-order kernel's decision.  mode: see split_bytes_per_view
+// (1 needs b.centres_out or b.keys_out).
+int launch_cast_split(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                      int seg0, int n_seg, int view0, int n_views, void* scratch, unsigned int* inexact,
+                      int sm_count, cudaEvent_t* stage_events, int mode) {
+  const SplitScratch sc = split_layout(c, e.kind, mode, n_views, scratch);
+  if (c.kind == A3D_CASTER_ITERATIVE)
+    return launch_split_c<A3D_CASTER_ITERATIVE, false>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact,
+                                                       sm_count, stage_events);
+  return launch_split_c<A3D_CASTER_SIMPLE, false>(st, m, c, e, b, seg0, n_seg, view0, n_views, sc, inexact, sm_count,
+                                                  stage_events);
+}
+#else
+// Second pass of a stored-list call over the whole batch (segments [0, n_seg), views [0, n_views)): the
+// scratch is the one launch_cast_split(mode 2) left behind for the same batch; every retained entry goes
+// to b.keys_out[b.emit_offset[segment] + its place in the segment's list] as a packed key.  Launches:
+// cast_split_launches(c, 0) - 1 (no fix-up).
+int launch_cast_split_direct(cudaStream_t st, const MapView& m, const CasterView& c, const EvalView& e, const Batch& b,
+                             int n_seg, int n_views, void* scratch, int sm_count) {
+  SplitScratch sc = split_layout(c, e.kind, 2, n_views, scratch);
+  sc.direct = b.keys_out;
+  sc.seg_base = b.emit_offset;
+  if (c.kind == A3D_CASTER_ITERATIVE)
+    return launch_split_c<A3D_CASTER_ITERATIVE, true>(st, m, c, e, b, 0, n_seg, 0, n_views, sc, nullptr, sm_count,
+                                                      nullptr);
+  return launch_split_c<A3D_CASTER_SIMPLE, true>(st, m, c, e, b, 0, n_seg, 0, n_views, sc, nullptr, sm_count, nullptr);
+}
+#endif
 
 }  // namespace a3d

@@ -133,6 +133,36 @@ def one_case(rng, case, oracle=None, max_views=None):
         if not np.isclose(g_ref, g_got, rtol=1e-9, atol=1e-12):
             bad.append(f"list gain (kernel {ctx.last_cast_kernel})")
     ctx.set_option("cast_kernel", 0)
+    # stored lists of the whole batch (two passes of the kernel chain, the second writing the keys straight
+    # into the arena; the scan-order kernel where the chain does not apply): every segment's stored list
+    # against the scan-order kernel's ordered list of its views (Naive / Frontier store the list after the
+    # erasure of observed entries), counts and gains against the batch call
+    n_seg = len(ref["gain"])
+    if n_seg <= 64:
+        seg_of = np.arange(len(pos), dtype=np.int32) if len(args) == 2 else args[2]
+        keys = np.arange(1, n_seg + 1, dtype=np.uint64)
+        for kernel in (0, 1):
+            ctx.set_option("cast_kernel", kernel)
+            store = capi.Store(ctx)
+            st = store.compute_gains(caster, ev, keys, pos, quat, view_segment=seg_of)
+            erases = ekind in ("NaiveEvaluator", "FrontierEvaluator")
+            if not erases and not np.array_equal(st["n_visible"], ref["n_visible"]):
+                bad.append(f"stored n_visible (kernel option {kernel})")
+            if not np.array_equal(st["n_samples"], ref["n_samples"]):
+                bad.append(f"stored n_samples (kernel option {kernel})")
+            if not np.allclose(st["gain"], ref["gain"], rtol=1e-9, atol=1e-12):
+                bad.append(f"stored gain (kernel option {kernel})")
+            ctx.set_option("cast_kernel", 1)
+            for sgm in range(min(n_seg, 4)):
+                sel = seg_of == sgm
+                want_l = ctx.visible_voxels(caster, pos[sel], quat[sel], evaluator=ev)[0] if sel.any() else np.zeros((0, 3))
+                if erases and len(want_l):
+                    want_l = want_l[ctx.is_observed(want_l) == 0]
+                got_l = store.get(keys[sgm])
+                if got_l.shape != want_l.shape or not np.array_equal(got_l, want_l):
+                    bad.append(f"stored list of segment {sgm} (kernel option {kernel})")
+            store.close()
+        ctx.set_option("cast_kernel", 0)
     ctx.close()
     return dict(case=case, vs=vs, vps=vps, edits=bool(edits), caster=ckind, evaluator=ekind, kw={k: (v if not isinstance(v, dict) else "bv") for k, v in kw.items()},
                 cam=cam["resolution_x"], shift=shift.tolist(), views=n_views, segments=len(ref["gain"]),
