@@ -277,9 +277,10 @@ void a3d_store_destroy(a3d_store* store);
  *   evaluators the observed entries are erased (naive_evaluator.cpp:28-35, frontier_evaluator.cpp:110-116);
  *   n_visible_out is the size handed to storeTrajectoryInformation (before that erasure), digests /
  *   set digests are of that list.  Outputs other than gains_out are nullable.
- * Passes: gains/sizes (kernel chain) → ordered key lists into an exactly sized arena (kernel chain
- * with list emission; the wavefront / scan-order kernels where the chain does not apply) → where
- * needed, k_list_pipeline (parent filter, digests, fold + erasure), level by level of the tree. */
+ * Passes: gains / sizes / every ray part's place in its list (kernel chain) → ordered key lists into an
+ * exactly sized arena (the chain's second pass writes each key straight to its place; list emission through
+ * the chain's slots or the scan-order kernel where that does not apply) → where needed, k_list_pipeline
+ * (parent filter, digests, fold + erasure), level by level of the tree. */
 int a3d_compute_gains_stored(a3d_ctx* ctx, const a3d_caster* caster, const a3d_eval* eval,
                              a3d_store* store, int n_views, const double* pos, const double* quat,
                              const int32_t* view_segment, int n_segments, const uint64_t* seg_keys,
