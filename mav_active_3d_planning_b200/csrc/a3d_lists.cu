@@ -202,9 +202,77 @@ __global__ void __launch_bounds__(kListThreads, 4)
   }
 }
 
+// The re-fold of lists nothing can leave and whose order nobody asks about (VoxelType / VoxelWeight, no
+// parent filter, no digests: SimulatedSensorUpdater over a tree): no ranks, no barriers in the loop, no
+// write-back — every thread folds its entries with several loads in flight.  One CTA per list; sums in a
+// fixed order (the VoxelWeight gain is reproducible run to run).
+template <int KIND>
+__global__ void __launch_bounds__(kListThreads, 4)
+    k_list_fold_plain(const MapView m, const EvalView e, const ListBatch lb) {
+  __shared__ CenterTables ct;
+  __shared__ double s_wpart[kListThreads / 32];
+  __shared__ unsigned long long s_cnt[6];
+  init_center_tables(m, &ct);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (int li = blockIdx.x; li < lb.n; li += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long* const list = lb.pool + lb.offsets[li];
+    const long long cnt = lb.counts[li];
+    const D3 origin = lb.origins ? D3{lb.origins[3 * li], lb.origins[3 * li + 1], lb.origins[3 * li + 2]}
+                                 : D3{0.0, 0.0, 0.0};
+    unsigned c[6] = {0, 0, 0, 0, 0, 0};
+    double wsum = 0.0;
+#pragma unroll 4
+    for (long long i = threadIdx.x; i < cnt; i += kListThreads) {
+      const unsigned long long key = __ldcs(list + i);
+      uint32_t word = 0;
+      const bool have = key_word(m, key, &word);
+      D3 v{0.0, 0.0, 0.0};
+      if (!have || KIND == A3D_EVAL_VOXEL_WEIGHT || e.bv_is_setup) v = key_centre(m, ct, key);
+      const int st = have ? static_cast<int>((word >> 16) & 3u) : voxel_state(m, ct, v);
+      if (KIND == A3D_EVAL_VOXEL_TYPE) {
+        c[st + ((!e.bv_is_setup || bv_contains(e, v)) ? 0 : 3)]++;
+      } else {
+        const int hint = (have && st == 2 && e.frontier_voxel_weight > 0.0) ? is_frontier_from_word(m, e, word) : -1;
+        wsum += voxel_weight_value(m, ct, e, v, st, st == 0 ? voxel_weight(m, v) : 0.0, origin, hint);
+      }
+    }
+    if (KIND == A3D_EVAL_VOXEL_TYPE) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const unsigned t = __reduce_add_sync(kFull, c[k]);
+        if (lane == 0 && t) atomicAdd(&s_cnt[k], static_cast<unsigned long long>(t));
+      }
+    } else {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) wsum += __shfl_down_sync(kFull, wsum, off);
+      if (lane == 0) s_wpart[warp] = wsum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (KIND == A3D_EVAL_VOXEL_TYPE) {
+        lb.gains[li] = voxel_type_gain(e, s_cnt);
+      } else {
+        double g = 0.0;
+        for (int w = 0; w < kListThreads / 32; ++w) g += s_wpart[w];
+        lb.gains[li] = g;
+      }
+      if (lb.n_stored) lb.n_stored[li] = static_cast<unsigned long long>(cnt);
+    }
+  }
+}
+
 void launch_list_pipeline(cudaStream_t st, const MapView& m, const EvalView& e, const ListBatch& lb) {
   if (lb.n <= 0) return;
-  k_list_pipeline<<<std::min(lb.n, 148 * 4), kListThreads, 0, st>>>(m, e, lb);
+  const bool plain = lb.gains && !lb.anc_first && !lb.digests && !lb.set_digests;
+  if (plain && e.kind == A3D_EVAL_VOXEL_TYPE)
+    k_list_fold_plain<A3D_EVAL_VOXEL_TYPE><<<std::min(lb.n, 148 * 4), kListThreads, 0, st>>>(m, e, lb);
+  else if (plain && e.kind == A3D_EVAL_VOXEL_WEIGHT)
+    k_list_fold_plain<A3D_EVAL_VOXEL_WEIGHT><<<std::min(lb.n, 148 * 4), kListThreads, 0, st>>>(m, e, lb);
+  else
+    k_list_pipeline<<<std::min(lb.n, 148 * 4), kListThreads, 0, st>>>(m, e, lb);
 }
 
 // Hash sets of stored lists: tables are pre-filled with kNoKey (0xFF bytes); duplicates collapse.
