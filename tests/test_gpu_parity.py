@@ -928,3 +928,41 @@ def test_voxel_tsdf_distance(capi, O, room02):
     om2.upload_blocks(m.block_idx, m.dist, m.observed, want_src)
     assert np.array_equal(ctx.voxel_tsdf_distance(pts), om2.voxel_weight(pts))
     ctx.close()
+
+
+def test_refold_without_parents_voxelweight_and_bounding_volume(capi, O, room02):
+    """The re-fold kernel for lists nothing can leave (k_list_fold_plain: VoxelType / VoxelWeight, no parents,
+    no digests) on the cases the main re-fold test does not reach: VoxelWeightEvaluator with a reference
+    point per segment (multi-view segments), VoxelTypeEvaluator with a rotated bounding volume — gains after
+    a map delta against the oracle's fold of the same lists."""
+    from mav_active_3d_planning_b200 import synth
+    ctx, om = make_pair(capi, O, room02)
+    caster = ctx.caster("IterativeRayCaster", **CAM_BASE)
+    pos, quat = synth.candidate_views(room02, 12, seed=33)
+    seg = np.repeat(np.arange(6, dtype=np.int32), 2)
+    org = pos[1::2] + 0.2
+    keys = np.arange(1, 7, dtype=np.uint64)
+    bv = dict(x_min=3.0, x_max=16.0, y_min=2.0, y_max=15.0, z_min=0.5, z_max=6.0, rotation=25.0)
+    rng = np.random.default_rng(5)
+    sel = rng.choice(room02.n_blocks, room02.n_blocks // 4, replace=False)
+    nd = (room02.dist[sel] + rng.normal(0, 0.05, room02.dist[sel].shape)).astype(np.float32)
+    no = np.maximum(room02.observed[sel], rng.random(room02.observed[sel].shape) < 0.4).astype(np.uint8)
+    for ekind, kw, origin in (("VoxelWeightEvaluator", dict(frontier_voxel_weight=0.5, new_voxel_weight=0.02), org),
+                              ("VoxelWeightEvaluator", dict(frontier_voxel_weight=0.0, min_impact_factor=0.1), org),
+                              ("VoxelTypeEvaluator", dict(gain_free=0.25, gain_occupied=2.0, gain_unknown_outer=0.5,
+                                                          bounding_volume=bv), None)):
+        ctx.upload_blocks(room02.block_idx, room02.dist, room02.observed, room02.weight)
+        om.upload_blocks(room02.block_idx, room02.dist, room02.observed, room02.weight)
+        ev, oe = ctx.evaluator(ekind, **kw), O.eval_params(ekind, **kw)
+        store = capi.Store(ctx)
+        store.compute_gains(caster, ev, keys, pos, quat, view_segment=seg, seg_origin=origin)
+        lists = [store.get(k) for k in keys]
+        ctx.upload_blocks(room02.block_idx[sel], nd, no)
+        om.upload_blocks(room02.block_idx[sel], nd, no)
+        gains, left = store.refold(ev, keys, seg_origin=origin)
+        for s in range(6):
+            og, oleft = om.gain_from_voxels(oe, lists[s], origin=None if origin is None else origin[s])
+            assert np.isclose(gains[s], og, rtol=GAIN_RTOL, atol=1e-12) and left[s] == oleft == len(lists[s]), (ekind, s)
+        assert np.array_equal(store.refold(ev, keys, seg_origin=origin)[0], gains)   # reproducible
+        store.close()
+    ctx.close()
