@@ -479,7 +479,8 @@ void gatherPoses(const TrajectorySegment& traj, const std::vector<int>& indices,
 }
 
 bool runVisible(a3d_ctx* ctx, a3d_caster* caster, a3d_eval* eval, int n_views, const double* pos,
-                const double* quat, std::vector<Eigen::Vector3d>* out, double* gain, PlannerI& planner) {
+                const double* quat, std::vector<Eigen::Vector3d>* out, double* gain, PlannerI& planner,
+                const double* origin = nullptr) {
   a3d_caster_info info{};
   a3d_caster_get_info(caster, &info);
   int64_t cap = static_cast<int64_t>(std::max(1, n_views)) * info.c_res_x * info.c_res_y *
@@ -487,7 +488,7 @@ bool runVisible(a3d_ctx* ctx, a3d_caster* caster, a3d_eval* eval, int n_views, c
   std::vector<double> flat(static_cast<size_t>(cap) * 3);
   int64_t n = 0, n_samples = 0;
   const int rc = a3d_visible_voxels(ctx, caster, eval, n_views, pos, quat, flat.data(), cap, &n,
-                                    &n_samples, gain, nullptr);
+                                    &n_samples, gain, origin);
   if (rc != A3D_OK) {
     planner.printError(std::string("a3d_visible_voxels: ") + a3d_last_error(ctx));
     return false;
@@ -841,9 +842,16 @@ bool SimulatedSensorEvaluator::computeGain(TrajectorySegment* traj_in) {
   std::vector<double> pos, quat;
   gatherPoses(*traj_in, indices, &pos, &quat);
   // visible voxels, already restricted to the bounding volume (:50-57)
+  // When nothing is taken out of the list afterwards (no clear_from_parents, an evaluator that does not
+  // erase), the gain the cast computed on the way is the gain of the stored list: no second trip to the
+  // device with the list (VoxelWeightEvaluator measures from the last trajectory point,
+  // voxel_weight_evaluator.cpp:53).
+  const bool gain_from_cast = !p_clear_from_parents_ && (evalKind() == A3D_EVAL_VOXEL_TYPE || evalKind() == A3D_EVAL_VOXEL_WEIGHT);
+  double cast_gain = 0.0;
   std::vector<Eigen::Vector3d> new_voxels;
   if (!runVisible(gpu_map_->context(), cam->handle(), eval_, static_cast<int>(indices.size()), pos.data(),
-                  quat.data(), &new_voxels, nullptr, planner_))
+                  quat.data(), &new_voxels, gain_from_cast ? &cast_gain : nullptr, planner_,
+                  traj_in->trajectory.back().position_W.data()))
     return false;
   noteDeviceTime(static_cast<int>(indices.size()), false);
   if (p_clear_from_parents_) {  // :60-76, one device pass per ancestor
@@ -870,7 +878,10 @@ bool SimulatedSensorEvaluator::computeGain(TrajectorySegment* traj_in) {
     new_voxels.resize(w);
   }
   storeTrajectoryInformation(traj_in, new_voxels);
-  computeGainFromVisibleVoxels(traj_in);
+  if (gain_from_cast)
+    traj_in->gain = cast_gain;
+  else
+    computeGainFromVisibleVoxels(traj_in);
   return true;
 }
 
