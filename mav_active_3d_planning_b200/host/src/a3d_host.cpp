@@ -485,7 +485,10 @@ bool runVisible(a3d_ctx* ctx, a3d_caster* caster, a3d_eval* eval, int n_views, c
   a3d_caster_get_info(caster, &info);
   int64_t cap = static_cast<int64_t>(std::max(1, n_views)) * info.c_res_x * info.c_res_y *
                 std::max(1, info.samples_per_full_ray);
-  std::vector<double> flat(static_cast<size_t>(cap) * 3);
+  // (kept between calls: a fresh vector of the worst-case size would be zero-filled — 6 MB for the
+  // 320x240 camera — on every per-segment call)
+  static thread_local std::vector<double> flat;
+  if (flat.size() < static_cast<size_t>(cap) * 3) flat.resize(static_cast<size_t>(cap) * 3);
   int64_t n = 0, n_samples = 0;
   const int rc = a3d_visible_voxels(ctx, caster, eval, n_views, pos, quat, flat.data(), cap, &n,
                                     &n_samples, gain, origin);
@@ -493,9 +496,9 @@ bool runVisible(a3d_ctx* ctx, a3d_caster* caster, a3d_eval* eval, int n_views, c
     planner.printError(std::string("a3d_visible_voxels: ") + a3d_last_error(ctx));
     return false;
   }
-  out->reserve(out->size() + static_cast<size_t>(n));
-  for (int64_t i = 0; i < n; ++i)
-    out->push_back(Eigen::Vector3d(flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]));
+  static_assert(sizeof(Eigen::Vector3d) == 3 * sizeof(double), "Vector3d is three packed doubles");
+  const Eigen::Vector3d* first = reinterpret_cast<const Eigen::Vector3d*>(flat.data());
+  out->insert(out->end(), first, first + n);
   return true;
 }
 }  // namespace detail
