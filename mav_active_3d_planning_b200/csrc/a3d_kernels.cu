@@ -138,24 +138,30 @@ __device__ __forceinline__ size_t vol_index(const MapView& m, const int32_t* bi,
                     static_cast<uint32_t>(bi[2] * m.vps + z - m.vol_lo[2]));
 }
 
+// `split` CTAs share a block, each taking a slab of z layers (a delta of a few blocks is a latency
+// problem: one CTA per block leaves most of the machine idle).
 __global__ void k_build_meta(MapView m, int n, const int32_t* __restrict__ slots,
                              const int32_t* __restrict__ block_idx, uint32_t* __restrict__ mword_slab,
-                             uint32_t* __restrict__ vol, int use_smem) {
+                             uint32_t* __restrict__ vol, int use_smem, int split) {
   extern __shared__ uint8_t s_cls[];
   const int P = m.P, PP = m.P * m.P, vps = m.vps;
-  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+  const int layers = (vps + split - 1) / split;  // z layers per CTA
+  for (int unit = blockIdx.x; unit < n * split; unit += gridDim.x) {
+    const int a = unit / split, z_lo = (unit - a * split) * layers, z_hi = min(vps, z_lo + layers);
+    if (z_lo >= z_hi) continue;
     const int slot = slots[a];
     const float* __restrict__ dp = m.dist + static_cast<size_t>(slot) * m.P3;
     if (use_smem) {
+      // the cells the slab's voxels look at: padded z in [z_lo, z_hi]
       __syncthreads();
-      for (int i = threadIdx.x; i < m.P3; i += blockDim.x) {
+      for (int i = z_lo * PP + threadIdx.x; i < (z_hi + 1) * PP; i += blockDim.x) {
         const int z = i / PP, rem = i % PP, y = rem / P, x = rem % P;  // padded coords (base + 1)
         s_cls[i] = (x <= vps && y <= vps && z <= vps) ? cell_class(m, dp, i) : kCellUnknown;
       }
       __syncthreads();
     }
     const int32_t* bi = block_idx + 3 * a;
-    for (int lin = threadIdx.x; lin < m.nv; lin += blockDim.x) {
+    for (int lin = z_lo * vps * vps + threadIdx.x; lin < z_hi * vps * vps; lin += blockDim.x) {
       const int z = lin / (vps * vps), rem = lin % (vps * vps), y = rem / vps, x = rem % vps;
       uint32_t word = 0;
 #pragma unroll
@@ -193,8 +199,10 @@ void launch_build_meta(cudaStream_t st, const MapView& m, int n, const int32_t* 
                        const int32_t* block_idx_dev, uint32_t* mword_slab, uint32_t* vol) {
   if (n <= 0) return;
   const int use_smem = m.P3 <= 40 * 1024;
-  k_build_meta<<<std::min(n, 148 * 8), 256, use_smem ? m.P3 : 0, st>>>(m, n, slots_dev, block_idx_dev,
-                                                                       mword_slab, vol, use_smem);
+  int split = 1;
+  while (split < 8 && n * split * 2 <= 148 * 8 && split * 2 <= m.vps) split *= 2;
+  k_build_meta<<<std::min(n * split, 148 * 8), 256, use_smem ? m.P3 : 0, st>>>(m, n, slots_dev, block_idx_dev,
+                                                                               mword_slab, vol, use_smem, split);
 }
 
 // Bits 23:19 of a meta word for the voxel with global coordinate g and centre c: first neighbour that
