@@ -244,6 +244,7 @@ struct StoreArena {
   unsigned long long* p = nullptr;  // list keys, or hash-set tables
   size_t entries = 0;               // 8-byte words
   int live = 0;
+  bool pooled = false;              // from the stream-ordered pool (else plain cudaMalloc)
 };
 struct StoreEntry {
   int arena;
@@ -285,7 +286,7 @@ struct a3d_store {
 };
 
 void a3d_store::free_arena(StoreArena& a) {
-  if (cudaFreeAsync(a.p, ctx->stream) != cudaSuccess) {
+  if (!a.pooled || cudaFreeAsync(a.p, ctx->stream) != cudaSuccess) {
     cudaGetLastError();
     cudaFree(a.p);
   }
@@ -297,6 +298,11 @@ int a3d_store::new_arena(size_t words, cudaError_t* err) {
   a.entries = words;
   void* p = nullptr;
   *err = cudaMallocAsync(&p, std::max<size_t>(words, 1) * 8, ctx->stream);
+  a.pooled = *err == cudaSuccess;
+  if (!a.pooled) {  // (a device or driver mode without memory pools)
+    cudaGetLastError();
+    *err = cudaMalloc(&p, std::max<size_t>(words, 1) * 8);
+  }
   if (*err != cudaSuccess) return -1;
   a.p = static_cast<unsigned long long*>(p);
   arenas.push_back(a);
